@@ -1,0 +1,91 @@
+"""ctypes binding to oracle/liboracle.so (the plain-C restatement).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(_ROOT, "oracle", "liboracle.so")
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+def build():
+    subprocess.check_call(["make", "-C", os.path.join(_ROOT, "oracle"), "port"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    if not os.path.exists(_SO):
+        build()
+    L = C.CDLL(_SO)
+    L.orc_murmur64.restype = C.c_uint64
+    L.orc_murmur64.argtypes = [C.c_uint64]
+    L.orc_count_kmers.restype = C.c_uint64
+    L.orc_count_kmers.argtypes = [_u8p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  _u64p, _u32p, C.c_uint64, _u64p]
+    L.orc_accepted_kmers.restype = C.c_uint64
+    L.orc_accepted_kmers.argtypes = [_u8p, _u64p, C.c_uint32, C.c_uint32, C.c_uint32, _u64p, C.c_uint64,
+                                     _u64p, _u64p, C.c_uint64]
+    L.orc_sampler.restype = None
+    L.orc_sampler.argtypes = [C.c_uint32, C.c_double, C.c_uint32, C.c_uint32, _u8p]
+    L.orc_sim_graph.restype = C.c_uint64
+    L.orc_sim_graph.argtypes = [_u64p, _u64p, C.c_uint32, _u8p, _u8p, C.c_uint32, C.c_uint32, _u32p, _u32p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.orc_pack_ref_read.restype = C.c_uint64
+    L.orc_pack_ref_read.argtypes = [_u8p, C.c_uint64, _u8p]
+    return L
+
+
+def count_kmers(bases, offsets, k, modulo, min_count, max_count):
+    L = lib()
+    n = len(offsets) - 1
+    stats = np.zeros(5, np.uint64)
+    cap = max(1024, int(offsets[-1]) // max(1, modulo) + 1024)
+    km = np.zeros(cap, np.uint64)
+    ct = np.zeros(cap, np.uint32)
+    ns = L.orc_count_kmers(bases, offsets, n, k, modulo, min_count, max_count, km, ct, cap, stats)
+    assert ns <= cap
+    return km[:ns].copy(), ct[:ns].copy(), dict(n_reads=int(stats[0]), tot_kmers=int(stats[1]), n_unique=int(stats[2]),
+                                                 n_unique_counted=int(stats[3]), total_count_filtered=int(stats[4]))
+
+
+def accepted_kmers(bases, offsets, k, modulo, kmer_set_sorted):
+    L = lib()
+    n = len(offsets) - 1
+    cap = max(1024, int(offsets[-1]) // max(1, modulo) * 2 + 1024)
+    off = np.zeros(n + 1, np.uint64)
+    acc = np.zeros(cap, np.uint64)
+    tot = L.orc_accepted_kmers(bases, offsets, n, k, modulo, np.ascontiguousarray(kmer_set_sorted), len(kmer_set_sorted), off, acc, cap)
+    assert tot <= cap
+    return off, acc[:tot].copy()
+
+
+def sampler(rng_range, exponent, n_pseudo, n):
+    L = lib()
+    out = np.zeros(n, np.uint8)
+    L.orc_sampler(rng_range, exponent, n_pseudo, n, out)
+    return out
+
+
+def sim_graph(acc_off, acc, has_n, sampled, max_candidates, max_kmer_count, hifi=False):
+    L = lib()
+    n = len(acc_off) - 1
+    cand = np.zeros(n * max_candidates, np.uint32)
+    cand_n = np.zeros(n, np.uint32)
+    if hifi:
+        common_off = np.zeros(n * max_candidates, np.uint64)
+        common_n = np.zeros(n * max_candidates, np.uint32)
+        cap = max(1024, 4 * len(acc) * 1 + 1024)
+        common = np.zeros(cap, np.uint64)
+        tot = L.orc_sim_graph(acc_off, np.ascontiguousarray(acc), n, has_n, sampled, max_candidates, max_kmer_count, cand, cand_n,
+                              common_off.ctypes.data, common_n.ctypes.data, common.ctypes.data, cap)
+        assert tot <= cap
+        return cand.reshape(n, max_candidates), cand_n, (common_off, common_n, common[:tot])
+    L.orc_sim_graph(acc_off, np.ascontiguousarray(acc), n, has_n, sampled, max_candidates, max_kmer_count, cand, cand_n,
+                    None, None, None, 0)
+    return cand.reshape(n, max_candidates), cand_n, None
