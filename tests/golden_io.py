@@ -1,0 +1,33 @@
+"""Load a golden case: regenerate its synthetic input and parse the reference's dumps (tests only)."""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+
+import refdump
+from colord_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_case(name):
+    d = os.path.join(GOLDEN, name)
+    with open(os.path.join(d, "input.json")) as f:
+        meta = json.load(f)
+    s = synth.generate(**meta["generator"])
+    # the generator must reproduce the exact input the reference saw (numpy Generator streams are not
+    # guaranteed across numpy versions; fail loudly instead of comparing against the wrong reads)
+    assert hashlib.sha1(s.bases.tobytes()).hexdigest() == meta["bases_sha1"], "synthetic input drifted"
+    assert hashlib.sha1(s.offsets.tobytes()).hexdigest() == meta["offsets_sha1"], "synthetic input drifted"
+    params = refdump.load_params(d)
+    kmers, counts = refdump.load_kmers(d)
+    reads, packs = refdump.load_reads(d)
+    es, es_packs = refdump.load_es(d)
+    has_n = np.array([r["has_n"] for r in reads], np.uint8)
+    is_ref = np.array([r["is_ref"] for r in reads], np.uint8)
+    return SimpleNamespace(name=name, meta=meta, reads_in=s, params=params, kmers=kmers, counts=counts,
+                           reads=reads, packs=packs, es=es, es_packs=es_packs, has_n=has_n, is_ref=is_ref)
