@@ -1,0 +1,223 @@
+// api.cu — the extern "C" boundary (include/colord_b200.h) over the stage implementations.
+#include "ctx.h"
+#include <cstring>
+#include <random>
+#include <cmath>
+
+static thread_local std::string g_create_error;
+
+namespace clb {
+clb_status fail(clb_ctx* c, clb_status st, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return st; }
+clb_status cuda_fail(clb_ctx* c, cudaError_t e, const char* what)
+{
+	std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+	cudaGetLastError();
+	return fail(c, (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CLB_ERR_NO_DEVICE : CLB_ERR_CUDA, m);
+}
+clb_status s1a_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n);
+clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap_out, uint64_t* n_out, int on_device);
+clb_status s1a_counts_reset(clb_ctx* c);
+clb_status s1a_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* gs, int on_device);
+}
+using namespace clb;
+
+extern "C" {
+
+clb_status clb_create(const clb_params* p, clb_ctx** out)
+{
+	if (!p || !out) return fail(nullptr, CLB_ERR_BAD_ARG, "null argument");
+	*out = nullptr;
+	if (p->kmer_len < 8 || p->kmer_len > 32) return fail(nullptr, CLB_ERR_BAD_ARG, "kmer_len must be in [8, 32]");
+	if (p->modulo == 0 || p->max_candidates == 0 || p->min_count == 0 || p->max_count < p->min_count) return fail(nullptr, CLB_ERR_BAD_ARG, "bad filter parameters");
+	int n_dev = 0;
+	cudaError_t e = cudaGetDeviceCount(&n_dev);
+	if (e != cudaSuccess || n_dev == 0) { cudaGetLastError(); return fail(nullptr, CLB_ERR_NO_DEVICE, "no CUDA device: colord_b200 has no CPU path for the hot stages"); }
+	if (p->device < 0 || p->device >= n_dev) return fail(nullptr, CLB_ERR_BAD_ARG, "device ordinal out of range");
+	clb_ctx* c = new clb_ctx();
+	c->prm = *p;
+	c->mt = make_modtest(p->modulo);
+	e = cudaSetDevice(p->device);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) { c->own_stream = true; e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, p->device); }
+	if (e != cudaSuccess) { clb_status st = cuda_fail(nullptr, e, "clb_create"); delete c; return st; }
+	clb_status st = s1a_init(c);
+	if (st != CLB_OK) { g_create_error = c->err; clb_destroy(c); return st; }
+	*out = c;
+	return CLB_OK;
+}
+
+void clb_destroy(clb_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->prm.device);
+	cudaStreamSynchronize(c->stream);
+	s1_free(c);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+const char* clb_last_error(const clb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+clb_status clb_set_stream(clb_ctx* c, void* stream)
+{
+	if (!c) return CLB_ERR_BAD_ARG;
+	cudaStreamSynchronize(c->stream);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	c->stream = static_cast<cudaStream_t>(stream); c->own_stream = false;
+	return CLB_OK;
+}
+
+clb_status clb_synchronize(clb_ctx* c)
+{
+	if (!c) return CLB_ERR_BAD_ARG;
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+
+#define CLB_ENTER(c) do { if (!(c)) return CLB_ERR_BAD_ARG; cudaSetDevice((c)->prm.device); } while (0)
+
+clb_status clb_append_reads(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device)
+{
+	CLB_ENTER(c);
+	if (n_reads && (!offsets || !bases)) return fail(c, CLB_ERR_BAD_ARG, "null bases/offsets");
+	return s1a_append(c, bases, offsets, n_reads, on_device);
+}
+clb_status clb_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n) { CLB_ENTER(c); return s1a_counts_size(c, part, n_parts, n); }
+clb_status clb_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n, int on_device)
+{ CLB_ENTER(c); return s1a_counts_export(c, part, n_parts, kmers, counts, cap, n, on_device); }
+clb_status clb_counts_reset(clb_ctx* c) { CLB_ENTER(c); return s1a_counts_reset(c); }
+clb_status clb_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device)
+{ CLB_ENTER(c); return s1a_counts_merge(c, kmers, counts, n, n_reads_remote, on_device); }
+clb_status clb_count_finalize(clb_ctx* c, clb_kmer_stats* stats) { CLB_ENTER(c); return s1a_finalize(c, stats); }
+
+clb_status clb_filter_list(clb_ctx* c, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n)
+{
+	CLB_ENTER(c);
+	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_filter_list before clb_count_finalize");
+	if (n) *n = c->n_surv;
+	if (cap < c->n_surv) return fail(c, CLB_ERR_CAPACITY, "clb_filter_list: buffer too small");
+	if (c->n_surv == 0) return CLB_OK;
+	CLB_CUDA(c, cudaMemcpyAsync(kmers, c->sv_kmer, sizeof(uint64_t) * c->n_surv, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(counts, c->sv_count, sizeof(uint32_t) * c->n_surv, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+clb_status clb_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* gs, int on_device)
+{ CLB_ENTER(c); return s1a_filter_import(c, kmers, counts, n, gs, on_device); }
+clb_status clb_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present)
+{ CLB_ENTER(c); return s1a_filter_check(c, kmers, n, possible, present); }
+
+clb_status clb_graph_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo) { CLB_ENTER(c); return s1b_build(c, is_reference, n_pseudo); }
+
+clb_status clb_graph_accepted_size(clb_ctx* c, uint64_t* total)
+{
+	CLB_ENTER(c);
+	if (!c->graph_done) return fail(c, CLB_ERR_STATE, "graph not built");
+	*total = c->acc_total;
+	return CLB_OK;
+}
+
+clb_status clb_graph_accepted(clb_ctx* c, uint64_t* offsets, uint64_t* kmers, uint64_t cap)
+{
+	CLB_ENTER(c);
+	if (!c->graph_done) return fail(c, CLB_ERR_STATE, "graph not built");
+	if (cap < c->acc_total) return fail(c, CLB_ERR_CAPACITY, "clb_graph_accepted: buffer too small");
+	const uint64_t n = c->n_reads;
+	std::vector<uint64_t> st(n), svk(c->n_surv); std::vector<uint32_t> cn(n), ids(c->acc_total);
+	CLB_CUDA(c, cudaMemcpyAsync(st.data(), c->acc_start, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(cn.data(), c->acc_n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(ids.data(), c->acc_id, sizeof(uint32_t) * c->acc_total, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(svk.data(), c->sv_kmer, sizeof(uint64_t) * c->n_surv, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	uint64_t o = 0;
+	for (uint64_t i = 0; i < n; ++i) {          // the device arena is in completion order; the API is CSR in read order
+		offsets[i] = o;
+		for (uint32_t j = 0; j < cn[i]; ++j) kmers[o++] = svk[ids[st[i] + j]];
+	}
+	offsets[n] = o;
+	return CLB_OK;
+}
+
+clb_status clb_graph_candidates(clb_ctx* c, uint32_t* cand, uint32_t* cand_n)
+{
+	CLB_ENTER(c);
+	if (!c->graph_done) return fail(c, CLB_ERR_STATE, "graph not built");
+	const uint64_t n = c->n_reads;
+	if (!n) return CLB_OK;
+	CLB_CUDA(c, cudaMemcpyAsync(cand, c->cand, sizeof(uint32_t) * n * c->prm.max_candidates, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(cand_n, c->cand_n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+
+clb_status clb_graph_common_size(clb_ctx* c, uint64_t* total)
+{
+	CLB_ENTER(c);
+	if (!c->graph_done || !c->prm.is_hifi) return fail(c, CLB_ERR_STATE, "HiFi graph not built");
+	*total = c->common_total;
+	return CLB_OK;
+}
+
+clb_status clb_graph_common(clb_ctx* c, uint64_t* common_off, uint32_t* common_n, uint64_t* kmers, uint64_t cap)
+{
+	CLB_ENTER(c);
+	if (!c->graph_done || !c->prm.is_hifi) return fail(c, CLB_ERR_STATE, "HiFi graph not built");
+	if (cap < c->common_total) return fail(c, CLB_ERR_CAPACITY, "clb_graph_common: buffer too small");
+	const uint64_t n = c->n_reads * c->prm.max_candidates;
+	if (!n) return CLB_OK;
+	std::vector<uint32_t> cn(c->n_reads);
+	CLB_CUDA(c, cudaMemcpyAsync(common_off, c->common_off, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(common_n, c->cand_votes, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(cn.data(), c->cand_n, sizeof(uint32_t) * c->n_reads, cudaMemcpyDeviceToHost, c->stream));
+	if (c->common_total) CLB_CUDA(c, cudaMemcpyAsync(kmers, c->common, sizeof(uint64_t) * c->common_total, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	for (uint64_t i = 0; i < c->n_reads; ++i)
+		for (uint32_t j = cn[i]; j < c->prm.max_candidates; ++j) { common_n[i * c->prm.max_candidates + j] = 0; common_off[i * c->prm.max_candidates + j] = 0; }
+	return CLB_OK;
+}
+
+clb_status clb_get_packed_read(clb_ctx* c, uint32_t read_id, uint8_t* out, uint64_t cap, uint64_t* n_bytes)
+{
+	CLB_ENTER(c);
+	if (read_id >= c->n_reads) return fail(c, CLB_ERR_BAD_ARG, "read id out of range");
+	const uint64_t start = c->h_rd_start[read_id], len = c->h_rd_len[read_id];
+	const uint64_t need = (len + 3) / 4 + 1;
+	if (n_bytes) *n_bytes = need;
+	if (cap < need) return fail(c, CLB_ERR_CAPACITY, "clb_get_packed_read: buffer too small");
+	const uint64_t w0 = start >> 5, w1 = len ? (start + len - 1) >> 5 : w0;
+	std::vector<uint64_t> w(w1 - w0 + 2, 0);
+	if (len) {
+		CLB_CUDA(c, cudaMemcpyAsync(w.data(), c->pk.p + w0, sizeof(uint64_t) * (w1 - w0 + 1), cudaMemcpyDeviceToHost, c->stream));
+		CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	// re-serialise into the reference's byte layout: 4 bases per byte MSB first + trailer (reference_reads.h:35-72)
+	uint64_t nb = 0; uint8_t b = 0; uint32_t in_byte = 0;
+	for (uint64_t i = 0; i < len; ++i) {
+		const uint64_t p = start + i;
+		const uint32_t x = (uint32_t)(w[(p >> 5) - w0] >> (62 - 2 * (p & 31))) & 3u;
+		b = (uint8_t)((b << 2) | x);
+		if (++in_byte == 4) { out[nb++] = b; b = 0; in_byte = 0; }
+	}
+	if (in_byte) out[nb++] = (uint8_t)(b << (2 * (4 - in_byte)));
+	out[nb++] = (uint8_t)in_byte;
+	return CLB_OK;
+}
+
+// CRefReadsAccepter (ref_reads_accepter.h:27-57): default-seeded mt19937 + uniform_real_distribution<double>,
+// one draw per non-pseudo read.  Uses the same libstdc++ facilities so the stream is identical by construction.
+void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n, uint8_t* decisions)
+{
+	std::mt19937 mt;
+	std::uniform_real_distribution<double> dist(0.0, 1.0);
+	if (range == 0) range = 1;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (i < n_pseudo) { decisions[i] = 1; continue; }
+		const uint32_t range_no = (i - n_pseudo) / range;
+		const double p = std::pow(1.0 / (range_no + 1), exponent);
+		decisions[i] = dist(mt) <= p;
+	}
+}
+
+uint64_t clb_kernel_launches(const clb_ctx* c) { return c ? c->launches : 0; }
+
+} // extern "C"

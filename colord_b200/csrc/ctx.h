@@ -1,0 +1,132 @@
+// ctx.h — the library context: parameters, the resident read store and every stage's device state.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/colord_b200.h"
+#include "util.cuh"
+
+namespace clb {
+
+// A growable device array (cudaMallocAsync-free: plain cudaMalloc, grown geometrically on the ctx stream).
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	uint64_t cap = 0;          // elements
+	cudaError_t reserve(uint64_t n, cudaStream_t s, bool keep, uint64_t used = 0)
+	{
+		if (n <= cap) return cudaSuccess;
+		uint64_t ncap = cap ? cap : 1;
+		while (ncap < n) ncap = ncap + ncap / 2 + 1024;
+		T* q = nullptr;
+		cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+		if (e != cudaSuccess) return e;
+		if (keep && p && used) {
+			e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
+			if (e != cudaSuccess) { cudaFree(q); return e; }
+			cudaStreamSynchronize(s);
+		}
+		if (p) cudaFree(p);
+		p = q; cap = ncap;
+		return cudaSuccess;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
+
+} // namespace clb
+
+struct clb_ctx {
+	clb_params prm{};
+	clb::ModTest mt{};
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	std::string err;
+	uint64_t launches = 0;
+	int n_sm = 148;
+
+	// ---- resident read store (device) ----
+	clb::DevBuf<uint64_t> pk;        // packed bases, 32 per word
+	clb::DevBuf<uint32_t> nmask;     // bit p&31 of word p>>5: position p is N / padding
+	clb::DevBuf<uint32_t> smask;     // bit set: position p is the first base of a read
+	clb::DevBuf<uint64_t> rd_start;  // per read: first position in the device stream
+	clb::DevBuf<uint32_t> rd_len;    // per read: length in bases
+	uint64_t n_pos = 0;              // positions used in the stream (multiple of 128)
+	uint64_t n_reads = 0;
+	uint64_t n_reads_remote = 0;     // reads counted on other ranks (merged tables)
+	uint64_t n_bases = 0;
+	std::vector<uint64_t> h_rd_start; // host mirrors (small: 12 B per read)
+	std::vector<uint32_t> h_rd_len;
+	clb::DevBuf<uint8_t> stage_in;   // staging for host ASCII input
+	clb::DevBuf<uint64_t> stage_off;
+
+	// ---- stage 1a: count table ----
+	clb::CountSlot* tab = nullptr;
+	uint32_t tab_log2 = 0;
+	unsigned long long* d_scal = nullptr;   // device scalars, see enum below
+	bool finalized = false;
+	clb_kmer_stats stats{};
+	struct FillState { uint64_t used_known = 0, maybe_new = 0; } fill;   // host-side bound on the table fill
+
+	// ---- filtered set (survivors) ----
+	uint64_t* sv_keys = nullptr;     // open addressing, EMPTY64
+	uint32_t* sv_ids = nullptr;      // dense id per slot
+	uint32_t sv_log2 = 0;
+	uint64_t n_surv = 0;
+	uint64_t sum_true = 0;           // sum of unsaturated counts of survivors (bounds accepted k-mers)
+	uint64_t* sv_kmer = nullptr;     // dense: k-mer, saturated count
+	uint32_t* sv_count = nullptr;
+
+	// ---- stage 1b ----
+	bool graph_done = false;
+	uint8_t* d_has_n = nullptr;
+	std::vector<uint8_t> h_has_n, h_is_ref;
+	std::vector<uint32_t> h_ref_before;
+	uint32_t* d_ref_before = nullptr;
+	uint8_t* d_is_ref = nullptr;
+	uint32_t n_ref = 0;
+	uint64_t* acc_start = nullptr;   // per read: start in acc_id
+	uint32_t* acc_n = nullptr;
+	uint32_t* acc_id = nullptr;      // arena of dense survivor ids, read order inside a read
+	uint64_t acc_cap = 0, acc_total = 0;
+	uint32_t* post_cnt = nullptr;    // per survivor: number of reference reads holding it (then min(.,H))
+	uint64_t* post_off = nullptr;    // exclusive scan of the uncapped counts
+	uint32_t* post = nullptr;        // reference ids
+	uint64_t post_total = 0;
+	uint32_t* cand = nullptr;        // n_reads * max_candidates
+	uint32_t* cand_votes = nullptr;
+	uint32_t* cand_n = nullptr;
+	uint64_t* common_off = nullptr;  // HiFi
+	uint64_t* common = nullptr;
+	uint64_t common_total = 0;
+};
+
+namespace clb {
+
+enum Scalar : int {
+	SC_TOT_KMERS = 0, SC_N_UNIQUE, SC_N_SURV, SC_TOT_FILTERED, SC_SUM_TRUE, SC_OVERFLOW, SC_BAD_SYMBOL,
+	SC_CURSOR, SC_CURSOR2, SC_TAB_USED, SC_COUNT
+};
+
+// error plumbing
+clb_status fail(clb_ctx* c, clb_status st, const std::string& msg);
+clb_status cuda_fail(clb_ctx* c, cudaError_t e, const char* what);
+#define CLB_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return clb::cuda_fail(ctx, e__, #call); } while (0)
+#define CLB_LAUNCH_CHECK(ctx, name) do { ++(ctx)->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return clb::cuda_fail(ctx, e__, name); } while (0)
+
+// stage entry points implemented in the .cu files
+clb_status s1a_init(clb_ctx* c);
+clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device);
+clb_status s1a_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n);
+clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_out, int on_device);
+clb_status s1a_counts_reset(clb_ctx* c);
+clb_status s1a_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* global_stats, int on_device);
+clb_status s1a_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device);
+clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats);
+clb_status s1a_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
+clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo);
+void s1_free(clb_ctx* c);
+
+} // namespace clb

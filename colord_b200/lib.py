@@ -1,0 +1,236 @@
+"""ctypes binding of include/colord_b200.h.  Loading fails loudly if the CUDA library was not built."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libcolord_b200.so")
+
+STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "BAD_SYMBOL", 5: "STATE", 6: "CAPACITY"}
+EXPORTS = [
+    "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream", "clb_synchronize", "clb_append_reads",
+    "clb_counts_size", "clb_counts_export", "clb_counts_reset", "clb_counts_merge", "clb_count_finalize",
+    "clb_filter_list", "clb_filter_import", "clb_filter_check", "clb_graph_build", "clb_graph_accepted_size",
+    "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
+    "clb_sampler", "clb_kernel_launches",
+]
+
+
+class Params(C.Structure):
+    _fields_ = [("kmer_len", C.c_uint32), ("modulo", C.c_uint32), ("min_count", C.c_uint32), ("max_count", C.c_uint32),
+                ("max_candidates", C.c_uint32), ("is_hifi", C.c_uint32), ("expected_bases", C.c_uint64), ("device", C.c_int32)]
+
+
+class KmerStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("tot_kmers", C.c_uint64), ("n_unique", C.c_uint64),
+                ("n_unique_counted", C.c_uint64), ("total_count_filtered", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class ClbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"colord_b200: {STATUS.get(status, status)}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library.  No fallback: a missing build is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C colord_b200/csrc); colord_b200 has no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    L.clb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.clb_destroy.argtypes = [vp]; L.clb_destroy.restype = None
+    L.clb_last_error.argtypes = [vp]; L.clb_last_error.restype = C.c_char_p
+    L.clb_set_stream.argtypes = [vp, vp]
+    L.clb_synchronize.argtypes = [vp]
+    L.clb_append_reads.argtypes = [vp, vp, vp, u32, i32]
+    L.clb_counts_size.argtypes = [vp, u32, u32, C.POINTER(u64)]
+    L.clb_counts_export.argtypes = [vp, u32, u32, vp, vp, u64, C.POINTER(u64), i32]
+    L.clb_counts_reset.argtypes = [vp]
+    L.clb_counts_merge.argtypes = [vp, vp, vp, u64, u64, i32]
+    L.clb_count_finalize.argtypes = [vp, C.POINTER(KmerStats)]
+    L.clb_filter_list.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.clb_filter_import.argtypes = [vp, vp, vp, u64, C.POINTER(KmerStats), i32]
+    L.clb_filter_check.argtypes = [vp, vp, u64, vp, vp]
+    L.clb_graph_build.argtypes = [vp, vp, u32]
+    L.clb_graph_accepted_size.argtypes = [vp, C.POINTER(u64)]
+    L.clb_graph_accepted.argtypes = [vp, vp, vp, u64]
+    L.clb_graph_candidates.argtypes = [vp, vp, vp]
+    L.clb_graph_common_size.argtypes = [vp, C.POINTER(u64)]
+    L.clb_graph_common.argtypes = [vp, vp, vp, vp, u64]
+    L.clb_get_packed_read.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+    L.clb_sampler.argtypes = [u32, C.c_double, u32, u32, vp]; L.clb_sampler.restype = None
+    L.clb_kernel_launches.argtypes = [vp]; L.clb_kernel_launches.restype = u64
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("clb_destroy", "clb_sampler"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def sampler(rng_range, exponent, n_pseudo, n):
+    out = np.zeros(n, np.uint8)
+    load().clb_sampler(rng_range, float(exponent), n_pseudo, n, _np_ptr(out))
+    return out
+
+
+class Context:
+    """One library context (= one GPU).  Mirrors the order of calls runCompression makes (compression.cpp:432-564)."""
+
+    def __init__(self, kmer_len, modulo, min_count, max_count, max_candidates, is_hifi=False, expected_bases=0, device=0):
+        self.L = load()
+        self.params = Params(kmer_len, modulo, min_count, max_count, max_candidates, int(bool(is_hifi)), int(expected_bases), device)
+        h = C.c_void_p()
+        st = self.L.clb_create(C.byref(self.params), C.byref(h))
+        if st != 0:
+            raise ClbError(st, self.L.clb_last_error(None).decode())
+        self.h = h
+        self.n_reads = 0
+
+    def _ck(self, st):
+        if st != 0:
+            raise ClbError(st, self.L.clb_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.clb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.clb_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def synchronize(self):
+        self._ck(self.L.clb_synchronize(self.h))
+
+    # ---- stage 1a
+    def append_reads(self, bases: np.ndarray, offsets: np.ndarray):
+        bases = np.ascontiguousarray(bases, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = len(offsets) - 1
+        self._ck(self.L.clb_append_reads(self.h, _np_ptr(bases), _np_ptr(offsets), n, 0))
+        self.n_reads += n
+
+    def append_reads_device(self, bases_ptr: int, offsets_ptr: int, n_reads: int):
+        self._ck(self.L.clb_append_reads(self.h, C.c_void_p(bases_ptr), C.c_void_p(offsets_ptr), n_reads, 1))
+        self.n_reads += n_reads
+
+    def counts_export(self, part=0, n_parts=1):
+        n = C.c_uint64()
+        self._ck(self.L.clb_counts_size(self.h, part, n_parts, C.byref(n)))
+        km = np.zeros(max(1, n.value), np.uint64)
+        ct = np.zeros(max(1, n.value), np.uint32)
+        m = C.c_uint64()
+        self._ck(self.L.clb_counts_export(self.h, part, n_parts, _np_ptr(km), _np_ptr(ct), n.value, C.byref(m), 0))
+        return km[:m.value], ct[:m.value]
+
+    def counts_reset(self):
+        self._ck(self.L.clb_counts_reset(self.h))
+
+    def counts_merge(self, kmers, counts, n_reads_remote=0):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint32)
+        self._ck(self.L.clb_counts_merge(self.h, _np_ptr(kmers), _np_ptr(counts), len(kmers), n_reads_remote, 0))
+
+    def count_finalize(self):
+        st = KmerStats()
+        self._ck(self.L.clb_count_finalize(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def filter_list(self):
+        n = C.c_uint64()
+        st = self.L.clb_filter_list(self.h, None, None, 0, C.byref(n))
+        if st not in (0, 6):
+            self._ck(st)
+        km = np.zeros(max(1, n.value), np.uint64)
+        ct = np.zeros(max(1, n.value), np.uint32)
+        self._ck(self.L.clb_filter_list(self.h, _np_ptr(km), _np_ptr(ct), n.value, C.byref(n)))
+        return km[:n.value], ct[:n.value]
+
+    def filter_import(self, kmers, counts, stats=None):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        counts = np.ascontiguousarray(counts, np.uint32)
+        ks = None
+        if stats is not None:
+            ks = KmerStats(*[stats[k] for k, _ in KmerStats._fields_])
+        self._ck(self.L.clb_filter_import(self.h, _np_ptr(kmers), _np_ptr(counts), len(kmers), C.byref(ks) if ks else None, 0))
+
+    def filter_check(self, kmers):
+        kmers = np.ascontiguousarray(kmers, np.uint64)
+        poss = np.zeros(len(kmers), np.uint8)
+        pres = np.zeros(len(kmers), np.uint8)
+        self._ck(self.L.clb_filter_check(self.h, _np_ptr(kmers), len(kmers), _np_ptr(poss), _np_ptr(pres)))
+        return poss, pres
+
+    # ---- stage 1b
+    def graph_build(self, is_reference=None, n_pseudo=0):
+        if is_reference is None:
+            ptr = None
+        else:
+            is_reference = np.ascontiguousarray(is_reference, np.uint8)
+            assert len(is_reference) == self.n_reads
+            ptr = _np_ptr(is_reference)
+        self._ck(self.L.clb_graph_build(self.h, ptr, n_pseudo))
+
+    def graph_accepted(self):
+        tot = C.c_uint64()
+        self._ck(self.L.clb_graph_accepted_size(self.h, C.byref(tot)))
+        off = np.zeros(self.n_reads + 1, np.uint64)
+        km = np.zeros(max(1, tot.value), np.uint64)
+        self._ck(self.L.clb_graph_accepted(self.h, _np_ptr(off), _np_ptr(km), tot.value))
+        return off, km[:tot.value]
+
+    def graph_candidates(self):
+        mc = self.params.max_candidates
+        cand = np.zeros(max(1, self.n_reads * mc), np.uint32)
+        cn = np.zeros(max(1, self.n_reads), np.uint32)
+        self._ck(self.L.clb_graph_candidates(self.h, _np_ptr(cand), _np_ptr(cn)))
+        return cand[:self.n_reads * mc].reshape(self.n_reads, mc), cn[:self.n_reads]
+
+    def graph_common(self):
+        mc = self.params.max_candidates
+        tot = C.c_uint64()
+        self._ck(self.L.clb_graph_common_size(self.h, C.byref(tot)))
+        off = np.zeros(max(1, self.n_reads * mc), np.uint64)
+        cn = np.zeros(max(1, self.n_reads * mc), np.uint32)
+        km = np.zeros(max(1, tot.value), np.uint64)
+        self._ck(self.L.clb_graph_common(self.h, _np_ptr(off), _np_ptr(cn), _np_ptr(km), tot.value))
+        return off, cn, km[:tot.value]
+
+    def packed_read(self, read_id):
+        n = C.c_uint64()
+        st = self.L.clb_get_packed_read(self.h, read_id, None, 0, C.byref(n))
+        if st not in (0, 6):
+            self._ck(st)
+        out = np.zeros(n.value, np.uint8)
+        self._ck(self.L.clb_get_packed_read(self.h, read_id, _np_ptr(out), n.value, C.byref(n)))
+        return out
+
+    @property
+    def kernel_launches(self):
+        return int(self.L.clb_kernel_launches(self.h))

@@ -1,0 +1,126 @@
+/* colord_b200.h — C-ABI of the B200 (sm_100a) hot path of a CoLoRd-compatible long-read compressor.
+ *
+ * The reference (refresh-bio/colord @ 25b2860) has no FFI layer: its compression stages are C++ classes
+ * wired by runCompression (src/colord/compression.cpp:344).  Each entry point below replaces one of those
+ * internal seams; the reference line that a binding would swap out is cited per function.  Plain pointers
+ * and sizes only; the library owns all device memory; no exit()/exceptions cross the boundary — every
+ * call returns a clb_status and clb_last_error() explains a failure.  There is NO CPU fallback: without a
+ * CUDA device every compute entry point returns CLB_ERR_NO_DEVICE.
+ *
+ * Read representation at the boundary: ASCII bases 'A','C','G','T','N' concatenated without separators
+ * (what the reference's FASTQ reader holds before to_read_t, in_reads.cpp:24-42) + uint64 offsets[n+1].
+ * Any other byte is an error (the reference aborts on it, in_reads.cpp:31-35).
+ */
+#ifndef COLORD_B200_H
+#define COLORD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct clb_ctx clb_ctx;
+
+typedef enum {
+	CLB_OK = 0,
+	CLB_ERR_NO_DEVICE = 1,     /* no CUDA device / driver: the product has no CPU path                 */
+	CLB_ERR_CUDA = 2,          /* a CUDA runtime call or kernel failed (text in clb_last_error)       */
+	CLB_ERR_BAD_ARG = 3,
+	CLB_ERR_BAD_SYMBOL = 4,    /* input holds a byte outside ACGTN                                      */
+	CLB_ERR_STATE = 5,         /* calls made in the wrong order                                        */
+	CLB_ERR_CAPACITY = 6       /* caller-provided output buffer too small (needed size is reported)   */
+} clb_status;
+
+/* Parameters of stage 1.  Field meaning = CCompressorParams (src/colord/params.h:48) */
+typedef struct {
+	uint32_t kmer_len;          /* -k; 15..32 (compression.cpp:57-94 picks 20..26)                     */
+	uint32_t modulo;            /* -f filterHashModulo: keep k-mers with murmur64(kmer) % modulo == 0  */
+	uint32_t min_count;         /* -L minKmerCount (KMC -ci)                                           */
+	uint32_t max_count;         /* -H maxKmerCount (KMC -cs; also the cap of a k-mer's read list)     */
+	uint32_t max_candidates;    /* -c maxCandidates                                                     */
+	uint32_t is_hifi;           /* DataSource::PBHiFi: the graph also returns the shared k-mers        */
+	uint64_t expected_bases;    /* sizing hint for the count table (0 = grow on demand)                */
+	int32_t  device;            /* CUDA device ordinal                                                 */
+} clb_params;
+
+/* What CKmerCounter::GetNReads/GetTotKmers/GetNUniqueCounted (count_kmers.h:32-34) and
+ * CKmerFilter::GetTotalKmers (kmer_filter.h:140) report. */
+typedef struct {
+	uint64_t n_reads;               /* #Total_reads                                                     */
+	uint64_t tot_kmers;             /* "#Total no. of k-mers": occurrences passing the modulo filter   */
+	uint64_t n_unique;              /* distinct passing k-mers                                          */
+	uint64_t n_unique_counted;      /* survivors: min_count <= count                                    */
+	uint64_t total_count_filtered;  /* sum of survivor counts saturated at max_count                   */
+} clb_kmer_stats;
+
+clb_status clb_create(const clb_params* params, clb_ctx** out);
+void       clb_destroy(clb_ctx* ctx);
+const char* clb_last_error(const clb_ctx* ctx);          /* ctx may be NULL: error of the failed create  */
+/* Run all of this context's work on an existing CUDA stream (cudaStream_t as void*); default: own stream. */
+clb_status clb_set_stream(clb_ctx* ctx, void* cuda_stream);
+clb_status clb_synchronize(clb_ctx* ctx);
+
+/* ---- Stage 1a: k-mer counting ---------------------------------------------------------------------
+ * Replaces the CKmerCounter ctor -> run_filtering_kmc (count_kmers.cpp:28-68, filtering_kmc.h:18).
+ * clb_append_reads = one read pack (read_pack_t, utils.h:46): bases are 2-bit packed on device
+ * (layout of CReferenceReads, reference_reads.h:35-72, widened to 64-bit words) and kept resident; the
+ * canonical k-mers passing the modulo filter are counted.  `bases`/`offsets` are HOST pointers unless
+ * on_device != 0 (then both are device pointers valid on the context's stream).  May be called many times. */
+clb_status clb_append_reads(clb_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device);
+/* Raw (k-mer, count) table exchange for the multi-GPU path: each rank counts its shard of
+ * reads; k-mers are owned by partition part = owner(kmer) in [0, n_parts) (same function on every rank);
+ * rank r exports partition p to rank p (all-to-all), resets, merges what it received for its own
+ * partition, finalizes (thresholds its share), and the survivors are all-gathered and imported with
+ * clb_filter_import.  n_parts <= 1 exports everything.  Buffers are device pointers iff on_device. */
+clb_status clb_counts_size(clb_ctx* ctx, uint32_t part, uint32_t n_parts, uint64_t* n_entries);
+clb_status clb_counts_export(clb_ctx* ctx, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_entries, int on_device);
+clb_status clb_counts_reset(clb_ctx* ctx);
+clb_status clb_counts_merge(clb_ctx* ctx, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device);
+/* Thresholds (kb_sorter.h:1011-1065) and builds the filtered-k-mer set; replaces the CKmerFilter ctor
+ * (filter_kmers.cpp:45-83).  After this call no more reads can be appended. */
+clb_status clb_count_finalize(clb_ctx* ctx, clb_kmer_stats* stats);
+/* Listing of the filtered set = what CKMCFile::ReadNextKmer yields (filter_kmers.cpp:68), any order.
+ * HOST buffers.  Returns CLB_ERR_CAPACITY if cap < *n. */
+clb_status clb_filter_list(clb_ctx* ctx, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n);
+/* Replace the filtered set by a listed one (multi-GPU: the survivors gathered from all owner ranks) and,
+ * if global_stats != NULL, the statistics by the all-reduced ones. */
+clb_status clb_filter_import(clb_ctx* ctx, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* global_stats, int on_device);
+/* CKmerFilter::Possible && Check for a batch of canonical k-mers (kmer_filter.h:129-137); HOST buffers. */
+clb_status clb_filter_check(clb_ctx* ctx, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
+
+/* ---- Stage 1b: similarity graph -------------------------------------------------------------------
+ * Replaces CReadsSimilarityGraph (reads_sim_graph.cpp:530; per pack :324 / HiFi :429) over ALL appended
+ * reads at once.  is_reference[i] (HOST, one byte per read, input order) = the value of acceptRefRead
+ * the reference would compute before its hasN test, i.e. the CRefReadsAccepter decision (all ones for
+ * -R all); reads holding N are excluded inside.  n_pseudo leading reads are reference-genome
+ * pseudo-reads (inserted uncapped, never queried: reads_sim_graph.cpp:295-322). */
+clb_status clb_graph_build(clb_ctx* ctx, const uint8_t* is_reference, uint32_t n_pseudo);
+/* Accepted k-mers per read (reads_sim_graph.cpp:134-164), CSR; HOST buffers; offsets has n_reads+1. */
+clb_status clb_graph_accepted_size(clb_ctx* ctx, uint64_t* total);
+clb_status clb_graph_accepted(clb_ctx* ctx, uint64_t* offsets, uint64_t* kmers, uint64_t cap);
+/* Candidate reference reads per read (CCompressElem::ref_reads, queues_data.h:23): cand[i*max_candidates+j]
+ * for j < cand_n[i], ordered (shared k-mers desc, reference id asc).  HOST buffers. */
+clb_status clb_graph_candidates(clb_ctx* ctx, uint32_t* cand, uint32_t* cand_n);
+/* HiFi only: CCompressElem::common_kmers.  common_off[i*max_candidates+j] .. + common_n[...] index `kmers`. */
+clb_status clb_graph_common_size(clb_ctx* ctx, uint64_t* total);
+clb_status clb_graph_common(clb_ctx* ctx, uint64_t* common_off, uint32_t* common_n, uint64_t* kmers, uint64_t cap);
+
+/* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
+ * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
+ * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
+clb_status clb_get_packed_read(clb_ctx* ctx, uint32_t read_id, uint8_t* out, uint64_t cap, uint64_t* n_bytes);
+
+/* ---- Sparse reference sampler (CRefReadsAccepter, ref_reads_accepter.h:27-57) ----------------------
+ * Host-side, serial by construction (default-seeded std::mt19937 stream is part of the format).
+ * decisions[i] = ShouldAddToReference(i) for i in [0, n). */
+void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n, uint8_t* decisions);
+
+/* ---- Instrumentation -------------------------------------------------------------------------------
+ * Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t clb_kernel_launches(const clb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

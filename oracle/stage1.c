@@ -122,7 +122,11 @@ uint64_t orc_accepted_kmers(const uint8_t* bases, const uint64_t* offsets, uint3
 		int has_n = 0;
 		for (uint64_t p = offsets[r]; p < offsets[r + 1]; ++p) if (sym_of(bases[p]) > 3) { has_n = 1; break; }
 		if (has_n || len < k) continue;
-		uint64_t str = 0, rev = 0, first = total;
+		uint64_t str = 0, rev = 0;
+		/* per-read "already processed" set (reads_sim_graph.cpp:150): open addressing, key+1 so that 0 = empty */
+		uint64_t scap = 64; while (scap < 2 * (len / modulo + 16)) scap <<= 1;
+		uint64_t* seen = (uint64_t*)calloc(scap, sizeof(uint64_t));
+		uint64_t n_seen = 0;
 		for (uint64_t i = 0; i < len; ++i)
 		{
 			int s = sym_of(bases[offsets[r] + i]);
@@ -131,12 +135,20 @@ uint64_t orc_accepted_kmers(const uint8_t* bases, const uint64_t* offsets, uint3
 			if (i + 1 < k) continue;
 			uint64_t can = str < rev ? str : rev;
 			if (!orc_possible(can, modulo) || !set_has(set, n_set, can)) continue;
-			int dup = 0;
-			for (uint64_t j = first; j < total && j < cap; ++j) if (acc[j] == can) { dup = 1; break; }
+			if (2 * (n_seen + 1) > scap)
+			{	/* grow */
+				uint64_t ncap = scap * 2; uint64_t* ns = (uint64_t*)calloc(ncap, sizeof(uint64_t));
+				for (uint64_t q = 0; q < scap; ++q) if (seen[q]) { uint64_t h = orc_murmur64(seen[q]) & (ncap - 1); while (ns[h]) h = (h + 1) & (ncap - 1); ns[h] = seen[q]; }
+				free(seen); seen = ns; scap = ncap;
+			}
+			uint64_t h = orc_murmur64(can + 1) & (scap - 1); int dup = 0;
+			while (seen[h]) { if (seen[h] == can + 1) { dup = 1; break; } h = (h + 1) & (scap - 1); }
 			if (dup) continue;
+			seen[h] = can + 1; ++n_seen;
 			if (total < cap) acc[total] = can;
 			++total;
 		}
+		free(seen);
 	}
 	acc_off[n_reads] = total;
 	return total;
