@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — input MB/s of the device hot path on the north-star workload (BASELINE.json).
+
+One "step" = one pass of the hot path built so far — STAGE 1 (2-bit ingest, canonical k-mer scan +
+murmur64 % f filter + count table, thresholding into the filtered set, accepted k-mers per read,
+similarity graph with top-c candidates) — over the whole synthetic ONT workload.  Stages 2 and 3 are not
+on the device yet; `config.stages` says so and the reference arm times the SAME stage of the reference.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--gbases G] [--impl reference]
+
+value  = FASTQ-equivalent input bytes of the whole job / step time, inputs resident in HBM.
+e2e    = same through the C-ABI with HOST (pinned) buffers: H2D inside the timed region, candidates read back.
+Multi-GPU (torchrun): reads shard by id (strong scaling), one all-to-all + one all-gather of k-mer tables.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# north-star workload (SURVEY.md §8d "NS"): compress-ont default on a 50 GB ONT FASTQ, mean read 8 kb
+NS = dict(k=24, modulo=12, min_count=4, max_count=80, max_candidates=5, sparse_g=1.0, sparse_exponent=1.0,
+          mean_len=8000, genome_len=1_200_000_000, err=(0.04, 0.03, 0.03))
+HEADER_BYTES = 46 + 6          # "@read_<i> ch=<n> start_time=<ISO>\n" + "\n+\n" + two line ends
+
+
+def fastq_bytes(n_bases, n_reads):
+    return 2 * n_bases + HEADER_BYTES * n_reads
+
+
+# ----------------------------------------------------------------------------------------------------
+# synthetic reads generated on the device (plumbing; same model as colord_b200.synth / BASELINE.md §2)
+# ----------------------------------------------------------------------------------------------------
+def make_genome(torch, device, genome_len, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randint(0, 4, (genome_len,), dtype=torch.uint8, device=device, generator=g)
+
+
+def gen_reads(torch, device, genome, read_lo, read_hi, seed, out_bases=None):
+    """ASCII bases + offsets of reads [read_lo, read_hi) of the workload.  Returns (bases u8, offsets i64)."""
+    G = genome.numel()
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    e_sub, e_del, e_ins = NS["err"]
+    chunks, lens_all = [], []
+    CH = 20000
+    for lo in range(read_lo, read_hi, CH):
+        hi = min(read_hi, lo + CH)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1_000_003 + lo)
+        n = hi - lo
+        u = torch.rand((2, n), device=device, generator=g).clamp_min(1e-12)
+        lens = (-(NS["mean_len"] / 2.0) * (u[0].log() + u[1].log())).clamp(200, 200000).to(torch.int64)
+        start = (torch.rand(n, device=device, generator=g) * (G - 2.5 * lens.double() - 16).clamp_min(1)).to(torch.int64)
+        rev = torch.rand(n, device=device, generator=g) < 0.5
+        offs = torch.zeros(n + 1, dtype=torch.int64, device=device)
+        offs[1:] = torch.cumsum(lens, 0)
+        total = int(offs[-1])
+        rid = torch.repeat_interleave(torch.arange(n, device=device), lens, output_size=total)
+        r = torch.rand(total, device=device, generator=g)
+        is_sub = r < e_sub
+        is_del = (r >= e_sub) & (r < e_sub + e_del)
+        is_ins = (r >= e_sub + e_del) & (r < e_sub + e_del + e_ins)
+        step = 1 + is_del.to(torch.int64) - is_ins.to(torch.int64)
+        cs = torch.cumsum(step, 0)
+        src_off = cs - cs[offs[:-1]][rid] + step[offs[:-1]][rid] - step      # exclusive scan restarted per read
+        span = (2 * lens + 8)[rid]
+        src = torch.where(rev[rid], start[rid] + span - 1 - src_off, start[rid] + src_off).clamp_(0, G - 1)
+        base = genome[src]
+        base = torch.where(rev[rid], 3 - base, base)
+        rnd = torch.randint(0, 4, (total,), dtype=torch.uint8, device=device, generator=g)
+        base = torch.where(is_sub, (base + 1 + rnd % 3) & 3, base)
+        base = torch.where(is_ins, rnd, base)
+        chunks.append(lut[base.long()])
+        lens_all.append(lens)
+        del rid, r, is_sub, is_del, is_ins, step, cs, src_off, span, src, base, rnd
+    lens = torch.cat(lens_all)
+    offsets = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=device)
+    offsets[1:] = torch.cumsum(lens, 0)
+    bases = torch.cat(chunks) if len(chunks) > 1 else chunks[0]
+    return bases, offsets
+
+
+def sparse_range(stats, p):
+    # compression.cpp:443, :501-503
+    mean_read_len = int(stats["tot_kmers"] * p["modulo"] / max(1, stats["n_reads"]) + p["k"] - 1)
+    return max(1, int(p["sparse_g"] * stats["n_unique_counted"] * p["modulo"] / max(1, mean_read_len)))
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own stage 1 on the host cores (oracle/_ref/ref_stage1_time)
+# ----------------------------------------------------------------------------------------------------
+def reference_sample_fastq(path, n_reads=12500, genome_len=5_000_000):
+    from colord_b200 import synth
+    s = synth.generate(n_reads, genome_len, NS["mean_len"], seed=1, profile="ont")
+    s.write_fastq(path)
+    return s, os.path.getsize(path)
+
+
+def run_reference_stage1(fastq, threads):
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")
+    with tempfile.TemporaryDirectory() as tmp:
+        out = subprocess.run([exe, "compress-ont", "-k", str(NS["k"]), "-a", "22", "-t", str(threads), fastq, os.path.join(tmp, "x.out")],
+                             cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=1800)
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+def run_port_stage1(s):
+    """Fallback CPU baseline: the scalar C oracle (single thread)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib
+    t0 = time.time()
+    km, ct, st = oracle_lib.count_kmers(s.bases, s.offsets, NS["k"], NS["modulo"], NS["min_count"], NS["max_count"])
+    off, acc = oracle_lib.accepted_kmers(s.bases, s.offsets, NS["k"], NS["modulo"], km)
+    rng = max(1, int(st["n_unique_counted"] * NS["modulo"] / NS["mean_len"]))
+    sampled = oracle_lib.sampler(rng, 1.0, 0, s.n_reads)
+    oracle_lib.sim_graph(off, acc, np.zeros(s.n_reads, np.uint8), sampled, NS["max_candidates"], NS["max_count"])
+    return time.time() - t0
+
+
+def cpu_baseline(sample_reads=12500):
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = os.path.join(tmp, "sample.fastq")
+        s, nbytes = reference_sample_fastq(fq, sample_reads)
+        desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
+            r = run_reference_stage1(fq, cores)
+            return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
+                    "sample": desc + "; reference CKmerCounter+CKmerFilter+CReadsSimilarityGraph (stage 1 only)", "detail": r}
+        dt = run_port_stage1(s)
+        return {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port", "sample": desc + "; oracle/stage1.c scalar port"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")
+    with tempfile.TemporaryDirectory() as tmp:
+        fq = os.path.join(tmp, "sample.fastq")
+        s, nbytes = reference_sample_fastq(fq)
+        times = []
+        kind = "reference" if os.path.exists(exe) else "port"
+        for i in range(args.warmup + args.steps):
+            dt = run_reference_stage1(fq, cores)["stage1_s"] if kind == "reference" else run_port_stage1(s)
+            if i >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    v = nbytes / (ms / 1e3) / 1e6
+    sample = f"{s.n_reads} synthetic ONT reads / {s.n_bases} bases / {nbytes} FASTQ bytes per step (bounded sample of the workload)"
+    print(json.dumps({
+        "impl": "reference", "metric": "input MB/s, compress-ont default, stage 1 (k-mer filter + similarity graph)", "value": v, "unit": "MB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args, None),
+        "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, n_reads):
+    return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
+                        f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] / 1e9:g} Gb, 10% errors)",
+            "stages": "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph); stages 2-3 not on device yet",
+            "n_reads": n_reads, "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"reads sharded by id over {args.gpus} GPU(s)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from colord_b200 import lib
+    from colord_b200.dist import exchange_counts_and_finalize
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; colord_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib.load()
+
+    p = NS
+    n_reads_total = int(args.gbases * 1e9 / p["mean_len"])
+    lo, hi = rank * n_reads_total // world, (rank + 1) * n_reads_total // world
+    genome = make_genome(torch, device, p["genome_len"], seed=1234)
+    bases, offsets = gen_reads(torch, device, genome, lo, hi, seed=99)
+    del genome
+    torch.cuda.empty_cache()
+    n_local = hi - lo
+    n_bases_local = int(bases.numel())
+    off_u64 = offsets.contiguous()
+    tot = torch.tensor([n_bases_local, n_local], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(tot)
+    n_bases_total, n_reads_all = int(tot[0]), int(tot[1])
+    job_bytes = fastq_bytes(n_bases_total, n_reads_all)
+
+    stream = torch.cuda.Stream(device=device)
+    peak, peak_src = measured_peak_hbm()
+
+    def one_step(host_bases=None, host_offsets=None, profile=False, readback=False):
+        ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], expected_bases=n_bases_local, device=local_rank)
+        ctx.set_stream(stream.cuda_stream)
+        if profile:
+            ctx.profile_enable(True)
+        if host_bases is None:
+            ctx.append_reads_device(bases.data_ptr(), off_u64.data_ptr(), n_local)
+        else:
+            ctx.append_reads(host_bases, host_offsets)
+        with torch.cuda.stream(stream):
+            stats = exchange_counts_and_finalize(ctx, device, n_local)
+        rng = sparse_range(stats, p)
+        sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
+        ctx.graph_build(sampled)
+        out = None
+        if readback:
+            out = ctx.graph_candidates()
+        ctx.synchronize()
+        return ctx, stats, out
+
+    def timed(n_warm, n_steps, **kw):
+        times, last = [], None
+        prof = {}
+        launches = 0
+        for i in range(n_warm + n_steps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx, stats, out = one_step(profile=(i >= n_warm), **kw)
+            e1.record(stream)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if i >= n_warm:
+                times.append(e0.elapsed_time(e1))
+                for k, (ms, n) in ctx.profile().items():
+                    a = prof.get(k, (0.0, 0))
+                    prof[k] = (a[0] + ms, a[1] + n)
+                launches += ctx.kernel_launches
+            last = (stats, out)
+            ctx.close()
+        t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), prof, launches // max(1, n_steps), last
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, prof, launches, (stats, _) = timed(args.warmup, args.steps)
+    value = job_bytes / (ms / 1e3) / 1e6
+
+    e2e = None
+    if not args.no_e2e:
+        host_bases = torch.empty(n_bases_local, dtype=torch.uint8, pin_memory=True)
+        host_bases.copy_(bases)
+        host_off = offsets.cpu().numpy().astype(np.uint64)
+        hb = host_bases.numpy()
+        e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, readback=True)
+        d2h = int(out[0].nbytes + out[1].nbytes)
+        e2e = {"value": job_bytes / (e_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(n_bases_local + host_off.nbytes), "d2h_bytes_per_step": d2h, "host_memory": "pinned"}
+        del host_bases, hb
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        # roofline of the dominant kernel (k_count): algorithmic bytes per launch / mean launch time
+        kc_ms, kc_n = prof.get("k_count", (0.0, 0))
+        alg_per_base = 0.5 + 16.0 / p["modulo"]           # packed + 2 masks read, one 8 B key+count RMW per passing k-mer
+        roof = None
+        if kc_n:
+            per_launch_bytes = alg_per_base * n_bases_local * args.steps / kc_n
+            per_launch_ms = kc_ms / kc_n
+            achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+            roof = {"kernel": "k_count", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "launches": kc_n // max(1, args.steps), "ms_per_launch": per_launch_ms,
+                    "algorithmic_bytes_per_base": alg_per_base,
+                    "kernel_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}}
+        line = {
+            "metric": "input MB/s, compress-ont default, stage 1 (k-mer filter + similarity graph)", "value": value, "unit": "MB/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic (generated on device, BASELINE.md §2 error model)",
+            "config": workload_config(args, n_reads_all), "job_fastq_bytes": job_bytes, "stats": stats,
+            "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as ex:      # keep the GPU numbers even if the host baseline cannot run
+                line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,15 +90,16 @@ clb_status clb_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* c
 { CLB_ENTER(c); return s1a_counts_merge(c, kmers, counts, n, n_reads_remote, on_device); }
 clb_status clb_count_finalize(clb_ctx* c, clb_kmer_stats* stats) { CLB_ENTER(c); return s1a_finalize(c, stats); }
 
-clb_status clb_filter_list(clb_ctx* c, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n)
+clb_status clb_filter_list(clb_ctx* c, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n, int on_device)
 {
 	CLB_ENTER(c);
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_filter_list before clb_count_finalize");
 	if (n) *n = c->n_surv;
 	if (cap < c->n_surv) return fail(c, CLB_ERR_CAPACITY, "clb_filter_list: buffer too small");
 	if (c->n_surv == 0) return CLB_OK;
-	CLB_CUDA(c, cudaMemcpyAsync(kmers, c->sv_kmer, sizeof(uint64_t) * c->n_surv, cudaMemcpyDeviceToHost, c->stream));
-	CLB_CUDA(c, cudaMemcpyAsync(counts, c->sv_count, sizeof(uint32_t) * c->n_surv, cudaMemcpyDeviceToHost, c->stream));
+	const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+	CLB_CUDA(c, cudaMemcpyAsync(kmers, c->sv_kmer, sizeof(uint64_t) * c->n_surv, kind, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(counts, c->sv_count, sizeof(uint32_t) * c->n_surv, kind, c->stream));
 	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return CLB_OK;
 }
@@ -219,5 +220,23 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 }
 
 uint64_t clb_kernel_launches(const clb_ctx* c) { return c ? c->launches : 0; }
+
+clb_status clb_profile_enable(clb_ctx* c, int on)
+{
+	if (!c) return CLB_ERR_BAD_ARG;
+	prof_resolve(c);
+	c->prof_on = on != 0;
+	for (int i = 0; i < K_N; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+	return CLB_OK;
+}
+
+clb_status clb_profile_get(clb_ctx* c, const char* kernel, double* ms, uint64_t* launches)
+{
+	if (!c || !kernel) return CLB_ERR_BAD_ARG;
+	prof_resolve(c);
+	for (int i = 0; i < K_N; ++i)
+		if (std::strcmp(kernel, kernel_names[i]) == 0) { if (ms) *ms = c->prof_ms[i]; if (launches) *launches = c->prof_n[i]; return CLB_OK; }
+	return fail(c, CLB_ERR_BAD_ARG, "unknown kernel class");
+}
 
 } // extern "C"

@@ -36,6 +36,11 @@ struct DevBuf {
 
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
 
+// kernel classes for the optional per-kernel timing (clb_profile_*)
+enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_N };
+static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc" };
+struct ProfRec { int kid; cudaEvent_t a, b; };
+
 } // namespace clb
 
 struct clb_ctx {
@@ -46,6 +51,13 @@ struct clb_ctx {
 	std::string err;
 	uint64_t launches = 0;
 	int n_sm = 148;
+	// per-kernel device timing (off by default)
+	bool prof_on = false;
+	std::vector<clb::ProfRec> prof_open;
+	double prof_ms[clb::K_N] = {0};
+	uint64_t prof_n[clb::K_N] = {0};
+	cudaStream_t copy_stream = nullptr;      // H2D staging of host input overlaps the kernels
+	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 
 	// ---- resident read store (device) ----
 	clb::DevBuf<uint64_t> pk;        // packed bases, 32 per word
@@ -59,7 +71,7 @@ struct clb_ctx {
 	uint64_t n_bases = 0;
 	std::vector<uint64_t> h_rd_start; // host mirrors (small: 12 B per read)
 	std::vector<uint32_t> h_rd_len;
-	clb::DevBuf<uint8_t> stage_in;   // staging for host ASCII input
+	clb::DevBuf<uint8_t> stage_in[2];   // double-buffered staging for host ASCII input
 	clb::DevBuf<uint64_t> stage_off;
 
 	// ---- stage 1a: count table ----
@@ -115,6 +127,12 @@ clb_status fail(clb_ctx* c, clb_status st, const std::string& msg);
 clb_status cuda_fail(clb_ctx* c, cudaError_t e, const char* what);
 #define CLB_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return clb::cuda_fail(ctx, e__, #call); } while (0)
 #define CLB_LAUNCH_CHECK(ctx, name) do { ++(ctx)->launches; cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return clb::cuda_fail(ctx, e__, name); } while (0)
+
+// per-kernel timing: CLB_TIMED(ctx, K_COUNT, kernel<<<...>>>(...));
+void prof_begin(clb_ctx* c, int kid);
+void prof_end(clb_ctx* c);
+void prof_resolve(clb_ctx* c);
+#define CLB_TIMED(ctx, kid, ...) do { clb::prof_begin(ctx, kid); __VA_ARGS__; clb::prof_end(ctx); } while (0)
 
 // stage entry points implemented in the .cu files
 clb_status s1a_init(clb_ctx* c);

@@ -19,7 +19,7 @@ namespace clb {
 // HBM traffic per base: 1 B read + 0.25 B + 0.125 B written.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ bases, uint64_t n_bases, uint64_t n_words,
-	uint64_t* __restrict__ pk, uint32_t* __restrict__ nmask, uint32_t* __restrict__ smask, int aligned16,
+	uint64_t* __restrict__ pk, uint32_t* __restrict__ nmask, int aligned16,
 	unsigned long long* __restrict__ scal)
 {
 	uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) k_pack(const uint8_t* __restrict__ bases,
 				word |= (uint64_t)x << (62 - 2 * idx);
 			}
 		}
-		pk[w] = word; nmask[w] = nm; smask[w] = 0;
+		pk[w] = word; nmask[w] = nm;
 	}
 	if (bad) atomicOr(&scal[SC_BAD_SYMBOL], 1ULL);
 }
@@ -358,6 +358,32 @@ static inline uint32_t grid_for(uint64_t n_items, uint32_t threads, int n_sm, ui
 	return (uint32_t)g;
 }
 
+void prof_begin(clb_ctx* c, int kid)
+{
+	if (!c->prof_on) return;
+	ProfRec r; r.kid = kid;
+	cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+	cudaEventRecord(r.a, c->stream);
+	c->prof_open.push_back(r);
+}
+void prof_end(clb_ctx* c)
+{
+	if (!c->prof_on || c->prof_open.empty()) return;
+	cudaEventRecord(c->prof_open.back().b, c->stream);
+	if (c->prof_open.size() > 4096) prof_resolve(c);
+}
+void prof_resolve(clb_ctx* c)
+{
+	if (c->prof_open.empty()) return;
+	cudaStreamSynchronize(c->stream);
+	for (auto& r : c->prof_open) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.kid] += ms; c->prof_n[r.kid] += 1; }
+		cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+	}
+	c->prof_open.clear();
+}
+
 static clb_status read_scalars(clb_ctx* c, unsigned long long* out)
 {
 	CLB_CUDA(c, cudaMemcpyAsync(out, c->d_scal, sizeof(unsigned long long) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
@@ -370,7 +396,7 @@ static clb_status tab_alloc(clb_ctx* c, uint32_t log2cap, CountSlot** out)
 	CountSlot* t = nullptr;
 	const uint64_t cap = 1ULL << log2cap;
 	CLB_CUDA(c, cudaMalloc(&t, cap * sizeof(CountSlot)));
-	k_tab_clear<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(t, cap);
+	CLB_TIMED(c, K_TAB_MISC, (k_tab_clear<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(t, cap)));
 	CLB_LAUNCH_CHECK(c, "k_tab_clear");
 	*out = t;
 	return CLB_OK;
@@ -402,7 +428,7 @@ static clb_status tab_grow(clb_ctx* c, uint32_t new_log2)
 	if (st != CLB_OK) return st;
 	CLB_CUDA(c, cudaMemsetAsync(&c->d_scal[SC_TAB_USED], 0, sizeof(unsigned long long), c->stream));
 	const uint64_t cap = 1ULL << c->tab_log2;
-	k_tab_reinsert<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(c->tab, cap, nt, new_log2, c->d_scal);
+	CLB_TIMED(c, K_TAB_MISC, (k_tab_reinsert<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(c->tab, cap, nt, new_log2, c->d_scal)));
 	CLB_LAUNCH_CHECK(c, "k_tab_reinsert");
 	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
 	cudaFree(c->tab);
@@ -431,6 +457,10 @@ static clb_status tab_ensure(clb_ctx* c, uint64_t incoming)
 	return CLB_OK;
 }
 
+// One append = one read pack.  The bases are processed in chunks of 64 Mi positions: host input is staged
+// through two device buffers on a copy stream so the H2D of chunk i+1 overlaps k_pack/k_count of chunk i.
+constexpr uint64_t APPEND_CHUNK = 1ULL << 26;      // positions; multiple of 128
+
 clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device)
 {
 	if (c->finalized) return fail(c, CLB_ERR_STATE, "clb_append_reads after clb_count_finalize");
@@ -439,26 +469,17 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	// offsets are needed on the host too (read bookkeeping is tiny: 12 B per read)
 	std::vector<uint64_t> h_off(n_reads + 1);
 	const uint64_t* d_off = nullptr;
-	const uint8_t* d_bases = nullptr;
 	if (on_device) {
 		CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyDeviceToHost, s));
 		CLB_CUDA(c, cudaStreamSynchronize(s));
-		d_off = offsets; d_bases = bases;
+		d_off = offsets;
 	} else {
 		std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n_reads + 1));
 	}
 	for (uint32_t i = 0; i < n_reads; ++i)
 		if (h_off[i + 1] < h_off[i] || h_off[i + 1] - h_off[i] > 0xFFFFFFFFull) return fail(c, CLB_ERR_BAD_ARG, "offsets must be non-decreasing, reads < 4 Gbases");
 	const uint64_t nb = h_off[n_reads] - h_off[0];
-	if (!on_device) {
-		CLB_CUDA(c, c->stage_in.reserve(nb + 64, s, false));
-		CLB_CUDA(c, c->stage_off.reserve(n_reads + 1, s, false));
-		CLB_CUDA(c, cudaMemcpyAsync(c->stage_in.p, bases + h_off[0], nb, cudaMemcpyHostToDevice, s));
-		CLB_CUDA(c, cudaMemcpyAsync(c->stage_off.p, offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, s));
-		d_off = c->stage_off.p; d_bases = c->stage_in.p;
-	} else {
-		d_bases = bases + h_off[0];
-	}
+	const uint8_t* src = bases + h_off[0];
 	// the append occupies a multiple of 128 positions, padding is N-masked
 	const uint64_t pos0 = c->n_pos;
 	const uint64_t n_words = ((nb + 127) / 128) * 4;
@@ -470,24 +491,50 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	CLB_CUDA(c, c->smask.reserve(want_words, s, true, w0));
 	CLB_CUDA(c, c->rd_start.reserve(c->n_reads + n_reads, s, true, c->n_reads));
 	CLB_CUDA(c, c->rd_len.reserve(c->n_reads + n_reads, s, true, c->n_reads));
-
-	if (n_words) {
-		k_pack<<<grid_for(n_words, 256, c->n_sm, 8), 256, 0, s>>>(d_bases, nb, n_words, c->pk.p + w0, c->nmask.p + w0, c->smask.p + w0,
-			(reinterpret_cast<uintptr_t>(d_bases) & 15) == 0, c->d_scal);
-		CLB_LAUNCH_CHECK(c, "k_pack");
+	if (!on_device) {
+		CLB_CUDA(c, c->stage_off.reserve(n_reads + 1, s, false));
+		CLB_CUDA(c, cudaMemcpyAsync(c->stage_off.p, offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, s));
+		d_off = c->stage_off.p;
+		const uint64_t stage_bytes = std::min<uint64_t>(nb, APPEND_CHUNK) + 64;
+		for (int b = 0; b < 2; ++b) {
+			CLB_CUDA(c, c->stage_in[b].reserve(stage_bytes, s, false));
+			if (!c->ev_copied[b]) {
+				CLB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+				CLB_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[b], cudaEventDisableTiming));
+			}
+		}
+		if (!c->copy_stream) CLB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		// the copy stream must not run ahead of whatever the compute stream did to the staging buffers before
+		CLB_CUDA(c, cudaEventRecord(c->ev_consumed[0], s));
+		CLB_CUDA(c, cudaEventRecord(c->ev_consumed[1], s));
 	}
+
+	// read-start mask of the whole append first (needs only the offsets), then chunk by chunk: copy, pack, count
+	CLB_CUDA(c, cudaMemsetAsync(c->smask.p + w0, 0, sizeof(uint32_t) * n_words, s));
 	k_mark_starts<<<(n_reads + 255) / 256, 256, 0, s>>>(d_off, n_reads, pos0, c->n_reads, c->smask.p, c->rd_start.p, c->rd_len.p);
 	CLB_LAUNCH_CHECK(c, "k_mark_starts");
-
-	// count, in chunks so that the table can be re-checked / grown between launches
-	const uint64_t chunk_words = 1ULL << 23;            // 256 Mi positions per launch
-	for (uint64_t cw = 0; cw < n_words; cw += chunk_words) {
-		const uint64_t ce = std::min(n_words, cw + chunk_words);
-		const uint64_t positions = (ce - cw) * 32;
-		clb_status st = tab_ensure(c, positions / c->prm.modulo + positions / (4 * (uint64_t)c->prm.modulo) + 4096);
+	uint32_t ci = 0;
+	for (uint64_t p = 0; p < n_words * 32; p += APPEND_CHUNK, ++ci) {
+		const uint64_t pe = std::min(n_words * 32, p + APPEND_CHUNK);      // chunk = positions [p, pe) of this append
+		const uint64_t cb = p < nb ? std::min(nb, pe) - p : 0;              // real bases in the chunk
+		const uint64_t cw = (pe - p) >> 5, wb = w0 + (p >> 5);
+		const uint8_t* d_src = src + p;
+		if (!on_device) {
+			const int b = ci & 1;
+			CLB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+			if (cb) CLB_CUDA(c, cudaMemcpyAsync(c->stage_in[b].p, src + p, cb, cudaMemcpyHostToDevice, c->copy_stream));
+			CLB_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+			CLB_CUDA(c, cudaStreamWaitEvent(s, c->ev_copied[b], 0));
+			d_src = c->stage_in[b].p;
+		}
+		CLB_TIMED(c, K_PACK, (k_pack<<<grid_for(cw, 256, c->n_sm, 8), 256, 0, s>>>(d_src, cb, cw, c->pk.p + wb, c->nmask.p + wb,
+			(reinterpret_cast<uintptr_t>(d_src) & 15) == 0, c->d_scal)));
+		CLB_LAUNCH_CHECK(c, "k_pack");
+		if (!on_device) CLB_CUDA(c, cudaEventRecord(c->ev_consumed[ci & 1], s));
+		clb_status st = tab_ensure(c, (pe - p) / c->prm.modulo + (pe - p) / (4 * (uint64_t)c->prm.modulo) + 4096);
 		if (st != CLB_OK) return st;
-		k_count<false><<<grid_for(ce - cw, COUNT_THREADS, c->n_sm, 8), COUNT_THREADS, 0, s>>>(c->pk.p, c->nmask.p, c->smask.p,
-			w0, w0 + cw, w0 + ce, c->prm.kmer_len, c->mt, c->tab, c->tab_log2, c->d_scal);
+		CLB_TIMED(c, K_COUNT, (k_count<false><<<grid_for(cw, COUNT_THREADS, c->n_sm, 8), COUNT_THREADS, 0, s>>>(c->pk.p, c->nmask.p, c->smask.p,
+			w0, wb, wb + cw, c->prm.kmer_len, c->mt, c->tab, c->tab_log2, c->d_scal)));
 		CLB_LAUNCH_CHECK(c, "k_count");
 	}
 	for (uint32_t i = 0; i < n_reads; ++i) {
@@ -605,7 +652,7 @@ clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats)
 	const uint64_t local_pass = sc[SC_TOT_KMERS];
 	CLB_CUDA(c, cudaMemsetAsync(c->d_scal, 0, sizeof(unsigned long long) * SC_COUNT, s));
 	const uint64_t cap = 1ULL << c->tab_log2;
-	k_tab_stats<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, s>>>(c->tab, cap, c->prm.min_count, c->prm.max_count, c->d_scal);
+	CLB_TIMED(c, K_FINALIZE, (k_tab_stats<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, s>>>(c->tab, cap, c->prm.min_count, c->prm.max_count, c->d_scal)));
 	CLB_LAUNCH_CHECK(c, "k_tab_stats");
 	st = read_scalars(c, sc);
 	if (st != CLB_OK) return st;
@@ -618,8 +665,8 @@ clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats)
 	if (r.n_unique_counted >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_BAD_ARG, "more than 2^32 filtered k-mers");
 	st = sv_alloc(c, r.n_unique_counted);
 	if (st != CLB_OK) return st;
-	k_build_survivors<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, s>>>(c->tab, cap, c->prm.min_count, c->prm.max_count,
-		c->sv_kmer, c->sv_count, c->sv_keys, c->sv_ids, c->sv_log2, &c->d_scal[SC_CURSOR]);
+	CLB_TIMED(c, K_FINALIZE, (k_build_survivors<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, s>>>(c->tab, cap, c->prm.min_count, c->prm.max_count,
+		c->sv_kmer, c->sv_count, c->sv_keys, c->sv_ids, c->sv_log2, &c->d_scal[SC_CURSOR])));
 	CLB_LAUNCH_CHECK(c, "k_build_survivors");
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	cudaFree(c->tab); c->tab = nullptr;

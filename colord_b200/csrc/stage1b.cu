@@ -625,9 +625,9 @@ static clb_status run_accept(clb_ctx* c)
 		scal_zero(c, SC_CURSOR2);
 		uint64_t* g_map = nullptr; uint32_t* g_bits = nullptr; uint64_t* g_moff = nullptr; uint64_t* g_boff = nullptr;
 		if (pass == 0) {
-			k_accept<ACC_A_MAP, ACC_A_BM, false><<<(uint32_t)v.size(), ACC_THREADS, acc_smem(ACC_A_MAP, ACC_A_BM), s>>>(a);
+			CLB_TIMED(c, K_ACCEPT, (k_accept<ACC_A_MAP, ACC_A_BM, false><<<(uint32_t)v.size(), ACC_THREADS, acc_smem(ACC_A_MAP, ACC_A_BM), s>>>(a)));
 		} else if (pass == 1) {
-			k_accept<ACC_B_MAP, ACC_B_BM, false><<<(uint32_t)v.size(), ACC_THREADS, acc_smem(ACC_B_MAP, ACC_B_BM), s>>>(a);
+			CLB_TIMED(c, K_ACCEPT, (k_accept<ACC_B_MAP, ACC_B_BM, false><<<(uint32_t)v.size(), ACC_THREADS, acc_smem(ACC_B_MAP, ACC_B_BM), s>>>(a)));
 		} else {
 			// global scratch: a map of >= 2 * (#k-mers of the read) slots and the two bitmap arrays per read
 			std::vector<uint64_t> moff(v.size() + 1, 0), boff(v.size() + 1, 0);
@@ -646,7 +646,7 @@ static clb_status run_accept(clb_ctx* c)
 			if (e != cudaSuccess) { st = cuda_fail(c, e, "accept scratch"); }
 			else {
 				a.g_map = g_map; a.g_bits = g_bits; a.g_map_off = g_moff; a.g_bits_off = g_boff;
-				k_accept<128, 32, true><<<(uint32_t)v.size(), ACC_THREADS, 0, s>>>(a);
+				CLB_TIMED(c, K_ACCEPT, (k_accept<128, 32, true><<<(uint32_t)v.size(), ACC_THREADS, 0, s>>>(a)));
 			}
 		}
 		if (st == CLB_OK) {
@@ -680,7 +680,7 @@ static clb_status run_postings(clb_ctx* c, uint32_t n_pseudo)
 	CLB_CUDA(c, cudaMemsetAsync(c->post_cnt, 0, sizeof(uint32_t) * (ns + 1), s));
 	const uint32_t warps_grid = (uint32_t)((n * 32 + 255) / 256);
 	if (n) {
-		k_post_pass<false><<<warps_grid, 256, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_is_ref, c->d_ref_before, (uint32_t)n, c->post_cnt, nullptr, nullptr);
+		CLB_TIMED(c, K_POSTINGS, (k_post_pass<false><<<warps_grid, 256, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_is_ref, c->d_ref_before, (uint32_t)n, c->post_cnt, nullptr, nullptr)));
 		CLB_LAUNCH_CHECK(c, "k_post_pass<count>");
 	}
 	clb_status st = exclusive_scan(c, c->post_cnt, ns, c->post_off, &c->post_total);
@@ -688,7 +688,7 @@ static clb_status run_postings(clb_ctx* c, uint32_t n_pseudo)
 	CLB_CUDA(c, dev_alloc(&c->post, c->post_total));
 	if (n && c->post_total) {
 		CLB_CUDA(c, cudaMemsetAsync(c->post_cnt, 0, sizeof(uint32_t) * (ns + 1), s));
-		k_post_pass<true><<<warps_grid, 256, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_is_ref, c->d_ref_before, (uint32_t)n, c->post_cnt, c->post_off, c->post);
+		CLB_TIMED(c, K_POSTINGS, (k_post_pass<true><<<warps_grid, 256, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_is_ref, c->d_ref_before, (uint32_t)n, c->post_cnt, c->post_off, c->post)));
 		CLB_LAUNCH_CHECK(c, "k_post_pass<fill>");
 		// lists over the cap
 		uint32_t* d_over = nullptr;
@@ -723,7 +723,7 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 	a.post_cnt = c->post_cnt; a.post_off = c->post_off; a.post = c->post; a.n_pseudo = n_pseudo; a.max_cand = mc;
 	a.cand = c->cand; a.cand_votes = c->cand_votes; a.cand_n = c->cand_n; a.scal = c->d_scal;
 	scal_zero(c, SC_CURSOR2);
-	k_vote<4096, false><<<(uint32_t)n, VOTE_THREADS, 0, s>>>(a);
+	CLB_TIMED(c, K_VOTE, (k_vote<4096, false><<<(uint32_t)n, VOTE_THREADS, 0, s>>>(a)));
 	CLB_LAUNCH_CHECK(c, "k_vote");
 	unsigned long long sc[SC_COUNT];
 	clb_status st = scal_read(c, sc);
@@ -753,7 +753,7 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 	if (e == cudaSuccess) {
 		a.list = d_list; a.n_list = (uint32_t)pend.size(); a.g_keys = g_keys; a.g_off = g_off;
 		scal_zero(c, SC_CURSOR2);
-		k_vote<1, true><<<(uint32_t)pend.size(), VOTE_THREADS, 0, s>>>(a);
+		CLB_TIMED(c, K_VOTE, (k_vote<1, true><<<(uint32_t)pend.size(), VOTE_THREADS, 0, s>>>(a)));
 		++c->launches;
 		e = cudaGetLastError();
 	}
@@ -779,8 +779,8 @@ static clb_status run_common(clb_ctx* c)
 	CLB_CUDA(c, dev_alloc(&c->common, c->common_total));
 	scal_zero(c, SC_CURSOR);
 	if (n && c->common_total) {
-		k_common<<<(uint32_t)n, COMMON_THREADS, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_ref_before, c->post_cnt, c->post_off, c->post,
-			c->sv_kmer, c->cand, c->cand_votes, c->cand_n, mc, c->common_off, c->common, &c->d_scal[SC_CURSOR]);
+		CLB_TIMED(c, K_COMMON, (k_common<<<(uint32_t)n, COMMON_THREADS, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_ref_before, c->post_cnt, c->post_off, c->post,
+			c->sv_kmer, c->cand, c->cand_votes, c->cand_n, mc, c->common_off, c->common, &c->d_scal[SC_CURSOR])));
 		CLB_LAUNCH_CHECK(c, "k_common");
 	}
 	CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -826,7 +826,10 @@ clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo)
 void s1_free(clb_ctx* c)
 {
 	c->pk.release(); c->nmask.release(); c->smask.release(); c->rd_start.release(); c->rd_len.release();
-	c->stage_in.release(); c->stage_off.release();
+	c->stage_in[0].release(); c->stage_in[1].release(); c->stage_off.release();
+	prof_resolve(c);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	for (int b = 0; b < 2; ++b) { if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); if (c->ev_consumed[b]) cudaEventDestroy(c->ev_consumed[b]); }
 	void* ptrs[] = { c->tab, c->d_scal, c->sv_keys, c->sv_ids, c->sv_kmer, c->sv_count, c->d_has_n, c->d_ref_before, c->d_is_ref,
 		c->acc_start, c->acc_n, c->acc_id, c->post_cnt, c->post_off, c->post, c->cand, c->cand_votes, c->cand_n, c->common_off, c->common };
 	for (void* p : ptrs) if (p) cudaFree(p);

@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing of stage 1a (one process per GPU, torch.distributed).
+
+Reads are sharded by id; every rank counts the k-mers of its shard.  The only exchange the path has
+(SURVEY.md §8e): k-mers are owned by hash partition, so one all-to-all moves every (k-mer, count) pair to
+its owner, the owner thresholds its share, and one all-gather hands every rank the union of survivors.
+`ctx` is a colord_b200.lib.Context (or, in the CPU gloo tests, any object with the same methods); all
+buffers that cross NCCL are device tensors whose pointers go straight into the C-ABI.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+STAT_KEYS = ("n_reads", "tot_kmers", "n_unique", "n_unique_counted", "total_count_filtered")
+
+
+def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
+    """Turn per-rank count tables into the identical global filtered set on every rank.
+
+    Returns the global statistics dict.  World size 1 degenerates to ctx.count_finalize().
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return ctx.count_finalize()
+    rank = dist.get_rank(group)
+    # 1. sizes of my table's partitions, exchanged so every rank knows what it will receive
+    send_sizes = torch.tensor([ctx.counts_size(p, world) for p in range(world)], dtype=torch.int64, device=device)
+    recv_sizes = torch.empty_like(send_sizes)
+    dist.all_to_all_single(recv_sizes, send_sizes, group=group)
+    send_l, recv_l = send_sizes.tolist(), recv_sizes.tolist()
+    # 2. export partition by partition into one send buffer, all-to-all the pairs
+    send_k = torch.empty(max(1, sum(send_l)), dtype=torch.int64, device=device)
+    send_c = torch.empty(max(1, sum(send_l)), dtype=torch.int32, device=device)
+    off = 0
+    for p in range(world):
+        if send_l[p]:
+            got = ctx.counts_export_device(p, world, send_k[off:].data_ptr(), send_c[off:].data_ptr(), send_l[p])
+            assert got == send_l[p]
+        off += send_l[p]
+    recv_k = torch.empty(max(1, sum(recv_l)), dtype=torch.int64, device=device)
+    recv_c = torch.empty(max(1, sum(recv_l)), dtype=torch.int32, device=device)
+    dist.all_to_all_single(recv_k[:sum(recv_l)], send_k[:sum(send_l)], recv_l, send_l, group=group)
+    dist.all_to_all_single(recv_c[:sum(recv_l)], send_c[:sum(send_l)], recv_l, send_l, group=group)
+    # 3. my table now holds only what I own: everything every rank counted for my partition
+    ctx.counts_reset()
+    ctx.counts_merge_device(recv_k.data_ptr(), recv_c.data_ptr(), sum(recv_l), 0)
+    local = ctx.count_finalize()
+    # 4. statistics are sums over owners (n_reads over shards)
+    st = torch.tensor([n_local_reads] + [local[k] for k in STAT_KEYS[1:]], dtype=torch.int64, device=device)
+    dist.all_reduce(st, group=group)
+    stats = dict(zip(STAT_KEYS, st.tolist()))
+    # 5. all-gather the survivors (padded to the largest share)
+    n_mine = ctx.filter_size()
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    sizes[rank] = n_mine
+    dist.all_reduce(sizes, group=group)
+    sizes_l = sizes.tolist()
+    pad = max(1, max(sizes_l))
+    my_k = torch.zeros(pad, dtype=torch.int64, device=device)
+    my_c = torch.zeros(pad, dtype=torch.int32, device=device)
+    if n_mine:
+        ctx.filter_list_device(my_k.data_ptr(), my_c.data_ptr(), n_mine)
+    all_k = torch.empty(world * pad, dtype=torch.int64, device=device)
+    all_c = torch.empty(world * pad, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(all_k, my_k, group=group)
+    dist.all_gather_into_tensor(all_c, my_c, group=group)
+    keep = torch.cat([torch.arange(r * pad, r * pad + sizes_l[r], device=device) for r in range(world)]) if sum(sizes_l) else torch.zeros(0, dtype=torch.int64, device=device)
+    uni_k = all_k[keep].contiguous()
+    uni_c = all_c[keep].contiguous()
+    ctx.filter_import_device(uni_k.data_ptr(), uni_c.data_ptr(), int(uni_k.numel()), stats)
+    return stats

@@ -15,8 +15,9 @@ EXPORTS = [
     "clb_counts_size", "clb_counts_export", "clb_counts_reset", "clb_counts_merge", "clb_count_finalize",
     "clb_filter_list", "clb_filter_import", "clb_filter_check", "clb_graph_build", "clb_graph_accepted_size",
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
-    "clb_sampler", "clb_kernel_launches",
+    "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get",
 ]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc"]
 
 
 class Params(C.Structure):
@@ -62,7 +63,7 @@ def load():
     L.clb_counts_reset.argtypes = [vp]
     L.clb_counts_merge.argtypes = [vp, vp, vp, u64, u64, i32]
     L.clb_count_finalize.argtypes = [vp, C.POINTER(KmerStats)]
-    L.clb_filter_list.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.clb_filter_list.argtypes = [vp, vp, vp, u64, C.POINTER(u64), i32]
     L.clb_filter_import.argtypes = [vp, vp, vp, u64, C.POINTER(KmerStats), i32]
     L.clb_filter_check.argtypes = [vp, vp, u64, vp, vp]
     L.clb_graph_build.argtypes = [vp, vp, u32]
@@ -74,6 +75,8 @@ def load():
     L.clb_get_packed_read.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
     L.clb_sampler.argtypes = [u32, C.c_double, u32, u32, vp]; L.clb_sampler.restype = None
     L.clb_kernel_launches.argtypes = [vp]; L.clb_kernel_launches.restype = u64
+    L.clb_profile_enable.argtypes = [vp, i32]
+    L.clb_profile_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("clb_destroy", "clb_sampler"):
@@ -149,6 +152,35 @@ class Context:
         self._ck(self.L.clb_counts_export(self.h, part, n_parts, _np_ptr(km), _np_ptr(ct), n.value, C.byref(m), 0))
         return km[:m.value], ct[:m.value]
 
+    def counts_size(self, part, n_parts):
+        n = C.c_uint64()
+        self._ck(self.L.clb_counts_size(self.h, part, n_parts, C.byref(n)))
+        return n.value
+
+    def counts_export_device(self, part, n_parts, kmers_ptr, counts_ptr, cap):
+        m = C.c_uint64()
+        self._ck(self.L.clb_counts_export(self.h, part, n_parts, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), cap, C.byref(m), 1))
+        return m.value
+
+    def counts_merge_device(self, kmers_ptr, counts_ptr, n, n_reads_remote=0):
+        self._ck(self.L.clb_counts_merge(self.h, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), n, n_reads_remote, 1))
+
+    def filter_size(self):
+        n = C.c_uint64()
+        st = self.L.clb_filter_list(self.h, None, None, 0, C.byref(n), 0)
+        if st not in (0, 6):
+            self._ck(st)
+        return n.value
+
+    def filter_list_device(self, kmers_ptr, counts_ptr, cap):
+        n = C.c_uint64()
+        self._ck(self.L.clb_filter_list(self.h, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), cap, C.byref(n), 1))
+        return n.value
+
+    def filter_import_device(self, kmers_ptr, counts_ptr, n, stats=None):
+        ks = KmerStats(*[stats[k] for k, _ in KmerStats._fields_]) if stats is not None else None
+        self._ck(self.L.clb_filter_import(self.h, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), n, C.byref(ks) if ks else None, 1))
+
     def counts_reset(self):
         self._ck(self.L.clb_counts_reset(self.h))
 
@@ -164,12 +196,12 @@ class Context:
 
     def filter_list(self):
         n = C.c_uint64()
-        st = self.L.clb_filter_list(self.h, None, None, 0, C.byref(n))
+        st = self.L.clb_filter_list(self.h, None, None, 0, C.byref(n), 0)
         if st not in (0, 6):
             self._ck(st)
         km = np.zeros(max(1, n.value), np.uint64)
         ct = np.zeros(max(1, n.value), np.uint32)
-        self._ck(self.L.clb_filter_list(self.h, _np_ptr(km), _np_ptr(ct), n.value, C.byref(n)))
+        self._ck(self.L.clb_filter_list(self.h, _np_ptr(km), _np_ptr(ct), n.value, C.byref(n), 0))
         return km[:n.value], ct[:n.value]
 
     def filter_import(self, kmers, counts, stats=None):
@@ -229,6 +261,18 @@ class Context:
             self._ck(st)
         out = np.zeros(n.value, np.uint8)
         self._ck(self.L.clb_get_packed_read(self.h, read_id, _np_ptr(out), n.value, C.byref(n)))
+        return out
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.clb_profile_enable(self.h, int(on)))
+
+    def profile(self):
+        """-> {kernel class: (total ms, launches)} measured with CUDA events on the context's stream."""
+        out = {}
+        for k in KERNEL_CLASSES:
+            ms, n = C.c_double(), C.c_uint64()
+            self._ck(self.L.clb_profile_get(self.h, k.encode(), C.byref(ms), C.byref(n)))
+            out[k] = (ms.value, n.value)
         return out
 
     @property

@@ -81,8 +81,8 @@ clb_status clb_counts_merge(clb_ctx* ctx, const uint64_t* kmers, const uint32_t*
  * (filter_kmers.cpp:45-83).  After this call no more reads can be appended. */
 clb_status clb_count_finalize(clb_ctx* ctx, clb_kmer_stats* stats);
 /* Listing of the filtered set = what CKMCFile::ReadNextKmer yields (filter_kmers.cpp:68), any order.
- * HOST buffers.  Returns CLB_ERR_CAPACITY if cap < *n. */
-clb_status clb_filter_list(clb_ctx* ctx, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n);
+ * Device buffers iff on_device.  Returns CLB_ERR_CAPACITY (with *n set) if cap < *n. */
+clb_status clb_filter_list(clb_ctx* ctx, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n, int on_device);
 /* Replace the filtered set by a listed one (multi-GPU: the survivors gathered from all owner ranks) and,
  * if global_stats != NULL, the statistics by the all-reduced ones. */
 clb_status clb_filter_import(clb_ctx* ctx, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* global_stats, int on_device);
@@ -119,6 +119,11 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 /* ---- Instrumentation -------------------------------------------------------------------------------
  * Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
+/* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
+ * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
+ * k_vote, k_common, k_misc.  clb_profile_get synchronizes the stream. */
+clb_status clb_profile_enable(clb_ctx* ctx, int on);
+clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }
