@@ -342,8 +342,14 @@ def main():
             per_launch_bytes = alg_per_base * n_bases_local * args.steps / kc_n
             per_launch_ms = kc_ms / kc_n
             achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+            traffic = None
+            try:      # DRAM bytes per launch of this kernel from the committed ncu --set full capture
+                with open(os.path.join(ROOT, "profiles", "k_count_traffic.json")) as f:
+                    traffic = json.load(f)["traffic_bytes_per_launch"]
+            except Exception:
+                pass
             roof = {"kernel": "k_count", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "launches": kc_n // max(1, args.steps), "ms_per_launch": per_launch_ms,
+                    "traffic": traffic, "peak_source": peak_src, "launches": kc_n // max(1, args.steps), "ms_per_launch": per_launch_ms,
                     "algorithmic_bytes_per_base": alg_per_base,
                     "kernel_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}}
         line = {
