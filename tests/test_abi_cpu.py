@@ -55,3 +55,10 @@ def test_sampler_matches_reference(golden, case):
         pytest.skip("-R all")
     dec = lib.sampler(g.params["sparse_range"], float(g.params["sparse_exponent"]), 0, len(g.reads))
     assert np.array_equal(dec & (1 - g.has_n), g.is_ref)
+
+
+def test_cpp_host_mirror_compiles():
+    """The C++ host-side mirror of the reference classes (colord_b200/host) builds against the C-ABI."""
+    import subprocess
+    src = '#include "colord_b200/host/stage1_host.h"\nint main() { clbhost::CRefReadsAccepter a(7, 1.0, 0); return a.GetNAccepted(100) > 100; }\n'
+    subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src.encode(), check=True, cwd=ROOT)
