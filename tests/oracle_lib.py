@@ -89,3 +89,57 @@ def sim_graph(acc_off, acc, has_n, sampled, max_candidates, max_kmer_count, hifi
     L.orc_sim_graph(acc_off, np.ascontiguousarray(acc), n, has_n, sampled, max_candidates, max_kmer_count, cand, cand_n,
                     None, None, None, 0)
     return cand.reshape(n, max_candidates), cand_n, None
+
+
+class S2Params(C.Structure):
+    _fields_ = [("anchor_len", C.c_uint32), ("kmer_len", C.c_uint32), ("modulo", C.c_uint32), ("is_hifi", C.c_uint32),
+                ("min_part_len_alt", C.c_uint32), ("max_recurence", C.c_uint32), ("min_anchors", C.c_uint32),
+                ("min_mmer_frac", C.c_double), ("min_mmer_force", C.c_double), ("max_matches_mult", C.c_double), ("es_cost_mult", C.c_double)]
+
+
+def s2_params(p):
+    """From a golden params.txt dict (or the same keys)."""
+    return S2Params(p["anchor_len"], p["k"], p["modulo"], int(p.get("hifi", 0)), p["min_part_len_alt"], p["max_recurence"], p["min_anchors"],
+                    float(p["min_mmer_frac"]), float(p["min_mmer_force"]), float(p["max_matches_mult"]), float(p["es_cost_mult"]))
+
+
+def edit_script(ref_sym, enc_sym, kind, ref_tail=b"\xff", enc_tail=b"\xff"):
+    """ref_sym/enc_sym: uint8 arrays of symbols 0..3 (the part); *_tail: what follows the part in the read (guard)."""
+    L = lib()
+    L.orc_edit_script.restype = C.c_uint32
+    L.orc_edit_script.argtypes = [_u8p, C.c_uint32, _u8p, C.c_uint32, C.c_int, C.c_char_p, C.c_uint32]
+    r = np.concatenate([np.asarray(ref_sym, np.uint8), np.frombuffer(ref_tail, np.uint8)])
+    e = np.concatenate([np.asarray(enc_sym, np.uint8), np.frombuffer(enc_tail, np.uint8)])
+    cap = 2 * (len(r) + len(e)) + 16
+    buf = C.create_string_buffer(cap)
+    n = L.orc_edit_script(np.ascontiguousarray(r), len(ref_sym), np.ascontiguousarray(e), len(enc_sym), kind, buf, cap)
+    assert n <= cap
+    return buf.raw[:n]
+
+
+def encode_reads(bases, offsets, is_ref, cand, cand_n, pack_sizes, params, common=None):
+    """-> list of CompactES byte strings, one per read (oracle/stage2.c: orc_encode_reads)."""
+    L = lib()
+    L.orc_encode_reads.restype = C.c_uint64
+    L.orc_encode_reads.argtypes = [_u8p, _u64p, C.c_uint32, _u8p, _u32p, _u32p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   _u32p, C.c_uint32, C.POINTER(S2Params), _u8p, C.c_uint64, _u64p]
+    n = len(offsets) - 1
+    mc = cand.shape[1]
+    cand = np.ascontiguousarray(cand, np.uint32).reshape(-1)
+    cand_n = np.ascontiguousarray(cand_n, np.uint32)
+    pack_sizes = np.ascontiguousarray(pack_sizes, np.uint32)
+    cap = int(offsets[-1]) * 2 + 64 * n + 1024
+    out = np.zeros(cap, np.uint8)
+    es_off = np.zeros(n + 1, np.uint64)
+    if common is not None:
+        coff, cn, ckm = [np.ascontiguousarray(x) for x in common]
+        if len(ckm) == 0:
+            ckm = np.zeros(1, np.uint64)
+        args = (coff.ctypes.data, cn.ctypes.data, ckm.ctypes.data)
+    else:
+        args = (None, None, None)
+    prm = params if isinstance(params, S2Params) else s2_params(params)
+    tot = L.orc_encode_reads(np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(offsets, np.uint64), n, np.ascontiguousarray(is_ref, np.uint8),
+                             cand, cand_n, mc, *args, pack_sizes, len(pack_sizes), C.byref(prm), out, cap, es_off)
+    assert tot <= cap
+    return [out[int(es_off[i]):int(es_off[i + 1])].tobytes() for i in range(n)]
