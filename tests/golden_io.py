@@ -31,3 +31,20 @@ def load_case(name):
     is_ref = np.array([r["is_ref"] for r in reads], np.uint8)
     return SimpleNamespace(name=name, meta=meta, reads_in=s, params=params, kmers=kmers, counts=counts,
                            reads=reads, packs=packs, es=es, es_packs=es_packs, has_n=has_n, is_ref=is_ref)
+
+
+def load_edit_scripts():
+    """-> list of (kind, ref symbols, enc symbols, ref tail byte, enc tail byte, reference's edit script bytes)."""
+    import gzip
+    import struct
+    with gzip.open(os.path.join(GOLDEN, "edit_scripts.bin.gz"), "rb") as f:
+        raw = f.read()
+    (n,) = struct.unpack_from("<I", raw, 0)
+    pos, out = 4, []
+    for _ in range(n):
+        kind, rl, el, rt, et, sn = struct.unpack_from("<IIIBBI", raw, pos)
+        pos += 18
+        ref = np.frombuffer(raw, np.uint8, rl, pos).copy(); pos += rl
+        enc = np.frombuffer(raw, np.uint8, el, pos).copy(); pos += el
+        out.append((kind, ref, enc, rt, et, raw[pos:pos + sn])); pos += sn
+    return out

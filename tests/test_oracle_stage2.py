@@ -39,3 +39,16 @@ def test_compact_es_bytes(golden, case):
     got = oracle_lib.encode_reads(g.reads_in.bases, g.reads_in.offsets, g.is_ref, cand, cand_n, np.array(g.packs, np.uint32), g.params, common)
     bad = [i for i in range(len(got)) if got[i] != g.es[i]]
     assert not bad, (len(bad), bad[:10])
+
+
+def test_edit_scripts_match_reference():
+    """E6/E7 in isolation, incl. tiny inputs, flanks and inputs large enough for edlib's Hirschberg path."""
+    import golden_io
+    cases = golden_io.load_edit_scripts()
+    assert len(cases) > 300
+    bad = []
+    for i, (kind, ref, enc, rt, et, want) in enumerate(cases):
+        got = oracle_lib.edit_script(ref, enc, kind, bytes([rt]), bytes([et]))
+        if got != want:
+            bad.append((i, kind, len(ref), len(enc)))
+    assert not bad, bad[:10]
