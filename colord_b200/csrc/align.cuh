@@ -1,0 +1,424 @@
+// align.cuh — device-side unit-cost alignment with the exact path the reference obtains from edlib, plus the
+// reference's edit-script canonicalisation.  SURVEY.md §8 rows E6 / E7.
+//
+// Reference behaviour restated (see oracle/stage2.c for the scalar form and the pinning tests):
+//   * src/colord/edit_script.h:272-413   the three wrappers (NW between anchors, SHW for the right flank, SHW on reversed
+//                                         strings for the left flank), tiny inputs via find_edit_dist (:156-245)
+//   * src/colord/libs/edlib/edlib.cpp     :395-441 calculateBlock (Myers/Hyyrö bit-vector column step)
+//                                         :945-1159 traceback: prefer UP (query symbol), then LEFT (target symbol), then diagonal
+//                                         :1178-1215 stored-column traceback below 1 MiB of column data, else
+//                                         :1234-1377 Hirschberg: halve the target, split at the TOPMOST row on an optimal path
+//   * src/colord/edit_script.h:432-447, :591-671   FixInRange / refactor_edit_script
+// edlib's Ukkonen band only removes cells no optimal path visits, so the full (unbanded) bit-vector matrix gives the same moves.
+//
+// Parallel scheme: a task is owned by a group of GROUP lanes (1, 2, 4, 8 or 32).  Rows are cut into 64-row blocks; lane g of
+// the group owns block strip*GROUP + g and the group sweeps the columns as an anti-diagonal wavefront (lane g is g columns
+// behind lane g-1, the horizontal delta travels by shuffle).  Tasks with more blocks than lanes are strip-mined: the
+// horizontal deltas leaving a strip's last block are kept per column (1 byte) and feed the next strip.  Column state
+// (Pv, Mv, score of the block's last row) is stored per (column, block) for the traceback, which one lane walks with
+// popcounts.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace clb {
+
+struct SeqView {            // element i = base[i * step]; step = -1 gives a reversed view
+	const uint8_t* base; int step;
+	__device__ __forceinline__ uint8_t operator[](int i) const { return base[(long long)i * step]; }
+	__device__ __forceinline__ SeqView sub(int off) const { return SeqView{base + (long long)off * step, step}; }
+	__device__ __forceinline__ SeqView reversed(int n) const { return SeqView{base + (long long)(n - 1) * step, -step}; }
+};
+
+__host__ __device__ inline long long edlib_column_bytes(long long q, long long t) { return (2ll * 8 + 4) * ((q + 63) / 64) * t + 2ll * 4 * t; }
+constexpr long long EDLIB_TRACEBACK_LIMIT = 1024 * 1024;
+
+// Scratch layout of one task (host and device agree through this function).
+struct AlignScratch {
+	unsigned long long hist, carry, lastrow, ops, tmp, F, R, fin, stack, total;
+};
+__host__ __device__ inline AlignScratch align_scratch_layout(long long q, long long t)
+{
+	AlignScratch s{};
+	const long long B = (q + 63) / 64;
+	const bool big = edlib_column_bytes(q, t) >= EDLIB_TRACEBACK_LIMIT;
+	unsigned long long o = 0;
+	auto take = [&](unsigned long long bytes) { unsigned long long at = o; o += (bytes + 15) & ~15ULL; return at; };
+	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 : (unsigned long long)(20 * B * (t > 0 ? t : 1)));
+	s.carry = take((unsigned long long)t + 1);
+	s.lastrow = take(4ull * (t + 1));
+	s.ops = take((unsigned long long)(q + t + 2));
+	s.tmp = take((unsigned long long)(q + t + 2));
+	s.F = take(big ? 4ull * (q + 1) : 0);
+	s.R = take(big ? 4ull * (q + 1) : 0);
+	s.fin = take(big ? 20ull * B : 0);
+	s.stack = take(big ? 64ull * 5 * 4 : 0);
+	s.total = o;
+	return s;
+}
+
+// edlib.cpp:407-441 (calculateBlock); returns hout, hb = bit whose horizontal delta is returned as *sdelta
+__device__ __forceinline__ int myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint32_t score_bit, int* sdelta)
+{
+	const uint64_t hin_neg = (uint64_t)((uint32_t)(hin >> 2) & 1u);
+	const uint64_t Xv = Eq | Mv;
+	Eq |= hin_neg;
+	const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+	uint64_t Ph = Mv | ~(Xh | Pv);
+	uint64_t Mh = Pv & Xh;
+	const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+	*sdelta = (int)((Ph >> score_bit) & 1) - (int)((Mh >> score_bit) & 1);
+	Ph <<= 1; Mh <<= 1;
+	Mh |= hin_neg;
+	Ph |= (uint64_t)((hin + 1) >> 1);
+	Pv = Mh | ~(Xv | Ph);
+	Mv = Ph & Xv;
+	return hout;
+}
+
+template <int GROUP>
+struct Aligner {
+	uint32_t gl;            // lane within the group
+	uint32_t gmask;         // warp mask of the group's lanes
+	uint8_t* scratch;       // this task's scratch
+	AlignScratch lay;
+
+	__device__ __forceinline__ void gsync() const { if (GROUP > 1) __syncwarp(gmask); }
+
+	// Forward sweep of rows[0..Q) x cols[0..T).  hist_* may be null.  lastrow (int32[T]) receives D(Q-1, c) if non-null.
+	// fin_* (per block) receive the final column if non-null.  Returns D(Q-1, T-1) to every lane.
+	__device__ int sweep(SeqView rows, int Q, SeqView cols, int T, uint64_t* hist_pv, uint64_t* hist_mv, int32_t* hist_sc,
+		int32_t* lastrow, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
+	{
+		const int B = (Q + 63) >> 6;
+		int8_t* carry = reinterpret_cast<int8_t*>(scratch + lay.carry);
+		int final_score = 0;
+		for (int strip = 0; strip * GROUP < B; ++strip) {
+			const int b = strip * GROUP + (int)gl;
+			const bool act = b < B;
+			const bool last_blk = b == B - 1;
+			const uint32_t sbit = last_blk ? (uint32_t)((Q - 1) & 63) : 63u;
+			uint64_t peq0 = 0, peq1 = 0, peq2 = 0, peq3 = 0;
+			if (act) {
+				const int r0 = b << 6, r1 = min(Q, r0 + 64);
+				for (int r = r0; r < r1; ++r) {
+					const uint8_t c = rows[r]; const uint64_t bit = 1ULL << (r - r0);
+					peq0 |= c == 0 ? bit : 0; peq1 |= c == 1 ? bit : 0; peq2 |= c == 2 ? bit : 0; peq3 |= c == 3 ? bit : 0;
+				}
+			}
+			uint64_t Pv = ~0ULL, Mv = 0;
+			int score = act ? min(Q, (b << 6) + 64) : 0;        // D(last row of block, column -1) = row index + 1
+			int hout = 0;
+			const int n_steps = T + GROUP - 1;
+			for (int s = 0; s < n_steps; ++s) {
+				int hin = GROUP > 1 ? __shfl_up_sync(gmask, hout, 1, GROUP) : 0;
+				const int c = s - (int)gl;
+				if (act && c >= 0 && c < T) {
+					if (gl == 0) hin = strip == 0 ? 1 : (int)carry[c];
+					const uint8_t tc = cols[c];
+					const uint64_t Eq = tc == 0 ? peq0 : tc == 1 ? peq1 : tc == 2 ? peq2 : tc == 3 ? peq3 : 0ULL;
+					int sd;
+					hout = myers_block(Pv, Mv, Eq, hin, sbit, &sd);
+					score += sd;
+					if (gl == GROUP - 1 && !last_blk) carry[c] = (int8_t)hout;
+					if (hist_pv) { const size_t h = (size_t)c * B + b; hist_pv[h] = Pv; hist_mv[h] = Mv; hist_sc[h] = score; }
+					if (last_blk && lastrow) lastrow[c] = score;
+				}
+			}
+			if (act && fin_pv) { fin_pv[b] = Pv; fin_mv[b] = Mv; fin_sc[b] = score; }
+			if (act && last_blk) final_score = score;
+			gsync();           // carry[] written by the last lane is read by lane 0 in the next strip
+		}
+		// broadcast the final score from the lane that owns the last block
+		if (GROUP > 1) {
+			const int owner = (B - 1) % GROUP;
+			final_score = __shfl_sync(gmask, final_score, owner, GROUP);
+		}
+		return final_score;
+	}
+
+	// ---- traceback on stored columns (lane 0 of the group) ----
+	struct Hist { const uint64_t* pv; const uint64_t* mv; const int32_t* sc; int B, Q; };
+	__device__ __forceinline__ static int cell(const Hist& h, int i, int j)       // D at row i, column j (0-based, both >= 0)
+	{
+		const int b = i >> 6, bit = i & 63;
+		const int bot = (b == h.B - 1) ? ((h.Q - 1) & 63) : 63;
+		const size_t x = (size_t)j * h.B + b;
+		// rows bit+1 .. bot
+		uint64_t m = (bot == 63 ? ~0ULL : ((1ULL << (bot + 1)) - 1)) & ~((bit == 63) ? ~0ULL : ((1ULL << (bit + 1)) - 1));
+		return h.sc[x] - (__popcll(h.pv[x] & m) - __popcll(h.mv[x] & m));
+	}
+	__device__ __forceinline__ static int vertex(const Hist& h, int I, int J) { return I == 0 ? J : (J == 0 ? I : cell(h, I - 1, J - 1)); }
+
+	// writes the ops of rows[0..Q) x cols[0..T) in forward order to out; returns their number.  tmp: Q+T bytes.
+	__device__ static int traceback(const Hist& h, int Q, int T, uint8_t* out, uint8_t* tmp)
+	{
+		int I = Q, J = T, n = 0;
+		int cur = vertex(h, I, J);
+		while (I > 0 || J > 0) {
+			if (I == 0) { tmp[n++] = 2; --J; continue; }
+			if (J == 0) { tmp[n++] = 1; --I; continue; }
+			const int up = vertex(h, I - 1, J);
+			if (up + 1 == cur) { tmp[n++] = 1; --I; cur = up; continue; }
+			const int left = vertex(h, I, J - 1);
+			if (left + 1 == cur) { tmp[n++] = 2; --J; cur = left; continue; }
+			const int diag = vertex(h, I - 1, J - 1);
+			tmp[n++] = diag == cur ? 0 : 3; --I; --J; cur = diag;
+		}
+		for (int x = 0; x < n; ++x) out[x] = tmp[n - 1 - x];
+		return n;
+	}
+
+	// decode the final column of a sweep into D(y-1, T-1) for y = 1..Q, F[0] = T  (vertex values of the last column)
+	__device__ void decode_final(const uint64_t* fin_pv, const uint64_t* fin_mv, const int32_t* fin_sc, int Q, int T, uint32_t* F) const
+	{
+		const int B = (Q + 63) >> 6;
+		for (int b = (int)gl; b < B; b += GROUP) {
+			const int r0 = b << 6, r1 = min(Q, r0 + 64);
+			int v = fin_sc[b];
+			const uint64_t pv = fin_pv[b], mv = fin_mv[b];
+			for (int r = r1 - 1; r >= r0; --r) {
+				F[r + 1] = (uint32_t)v;
+				v -= (int)((pv >> (r - r0)) & 1) - (int)((mv >> (r - r0)) & 1);
+			}
+		}
+		if (gl == 0) F[0] = (uint32_t)T;
+		gsync();
+	}
+
+	// edlib's obtainAlignment for rows x cols with known optimal score `best`: ops appended to ops_out (forward order).
+	// Iterative Hirschberg with an explicit stack; all lanes of the group call.  Returns the number of ops.
+	__device__ int path(SeqView rows, int Q, SeqView cols, int T, int best, uint8_t* ops_out) const
+	{
+		uint8_t* tmp = scratch + lay.tmp;
+		int n_ops = 0;
+		if (edlib_column_bytes(Q, T) < EDLIB_TRACEBACK_LIMIT || Q == 0 || T == 0) {
+			n_ops = leaf(rows, Q, cols, T, ops_out, tmp);
+			return n_ops;
+		}
+		int32_t* stack = reinterpret_cast<int32_t*>(scratch + lay.stack);
+		uint32_t* F = reinterpret_cast<uint32_t*>(scratch + lay.F);
+		uint32_t* R = reinterpret_cast<uint32_t*>(scratch + lay.R);
+		uint64_t* fin_pv = reinterpret_cast<uint64_t*>(scratch + lay.fin);
+		int sp = 0;
+		if (gl == 0) { stack[0] = 0; stack[1] = Q; stack[2] = 0; stack[3] = T; stack[4] = best; }
+		sp = 1;
+		gsync();
+		while (sp > 0) {
+			--sp;
+			const int qo = stack[sp * 5], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], bs = stack[sp * 5 + 4];
+			gsync();
+			const SeqView r = rows.sub(qo), c = cols.sub(to);
+			if (ql == 0 || tl == 0 || edlib_column_bytes(ql, tl) < EDLIB_TRACEBACK_LIMIT) {
+				n_ops += leaf(r, ql, c, tl, ops_out + n_ops, tmp);
+				continue;
+			}
+			const int Bq = (ql + 63) >> 6;
+			uint64_t* fpv = fin_pv; uint64_t* fmv = fin_pv + Bq; int32_t* fsc = reinterpret_cast<int32_t*>(fin_pv + 2 * Bq);
+			const int lw = tl / 2, rw = tl - lw;
+			sweep(r, ql, c, lw, nullptr, nullptr, nullptr, nullptr, fpv, fmv, fsc);
+			gsync();
+			decode_final(fpv, fmv, fsc, ql, lw, F);
+			sweep(r.reversed(ql), ql, c.sub(lw).reversed(rw), rw, nullptr, nullptr, nullptr, nullptr, fpv, fmv, fsc);
+			gsync();
+			decode_final(fpv, fmv, fsc, ql, rw, R);           // R[z] = dist(last z rows, right half)
+			// topmost y in 1..ql-1 with F[y] + R[ql-y] == bs, then y = 0, then y = ql   (edlib.cpp:1305-1338)
+			int y = 0x7fffffff;
+			for (int cand = 1 + (int)gl; cand <= ql - 1; cand += GROUP) if ((int)(F[cand] + R[ql - cand]) == bs) { y = cand; break; }
+			if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) y = min(y, __shfl_xor_sync(gmask, y, d, GROUP));
+			if (y == 0x7fffffff) { if ((int)(lw + R[ql]) == bs) y = 0; else y = ql; }
+			const int ls = y == 0 ? lw : (int)F[y], rs = y == ql ? rw : (int)R[ql - y];
+			gsync();
+			if (gl == 0) {
+				int32_t* e = stack + sp * 5;          // right part first so that the left part is processed first
+				e[0] = qo + y; e[1] = ql - y; e[2] = to + lw; e[3] = rw; e[4] = rs;
+				e[5] = qo; e[6] = y; e[7] = to; e[8] = lw; e[9] = ls;
+			}
+			sp += 2;
+			gsync();
+		}
+		return n_ops;
+	}
+
+	// stored-column traceback of a problem below edlib's 1 MiB limit
+	__device__ int leaf(SeqView rows, int Q, SeqView cols, int T, uint8_t* out, uint8_t* tmp) const
+	{
+		int n = 0;
+		if (Q == 0 || T == 0) {
+			if (gl == 0) for (int i = 0; i < Q + T; ++i) out[i] = Q == 0 ? 2 : 1;
+			gsync();
+			return Q + T;
+		}
+		const int B = (Q + 63) >> 6;
+		uint64_t* hpv = reinterpret_cast<uint64_t*>(scratch + lay.hist);
+		uint64_t* hmv = hpv + (size_t)B * T;
+		int32_t* hsc = reinterpret_cast<int32_t*>(hmv + (size_t)B * T);
+		sweep(rows, Q, cols, T, hpv, hmv, hsc, nullptr, nullptr, nullptr, nullptr);
+		gsync();
+		if (gl == 0) { Hist h{hpv, hmv, hsc, B, Q}; n = traceback(h, Q, T, out, tmp); }
+		if (GROUP > 1) n = __shfl_sync(gmask, n, 0, GROUP);
+		gsync();
+		return n;
+	}
+};
+
+// ---- script symbols ----------------------------------------------------------------------------------
+__device__ __forceinline__ char mismatch_symb(uint8_t ref, uint8_t enc)      // utils.h:341-352
+{
+	// the three other bases in ACGT order are X, Y, Z
+	const int idx = enc - (enc > ref ? 1 : 0);
+	return (char)('X' + idx);
+}
+__device__ __forceinline__ bool es_is_mm(char c) { return c == 'X' || c == 'Y' || c == 'Z'; }
+__device__ __forceinline__ bool es_is_ins(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+
+__device__ inline void fix_in_range(char* es, uint32_t start, uint32_t end)   // edit_script.h:432-447
+{
+	if (end < start + 2) return;
+	--end;
+	for (;;) {
+		while (start < end && es[start] == 'M') ++start;
+		while (start < end && es[end] != 'M') --end;
+		if (start == end) break;
+		const char t = es[start]; es[start] = es[end]; es[end] = t;
+	}
+}
+// edit_script.h:591-671; ref/enc may be indexed one past the part (the byte that follows it in the read)
+__device__ inline void refactor_edit_script(SeqView ref, SeqView enc, char* es, uint32_t n)
+{
+	uint32_t ref_start = 0, ref_pos = 0, es_start = 0;
+	for (uint32_t p = 0; p < n; ++p) {
+		const char s = es[p]; const bool mm = es_is_mm(s), ins = es_is_ins(s);
+		if (ins || mm || ref[ref_start] != ref[ref_pos]) {
+			fix_in_range(es, es_start, p);
+			es_start = p; if (ins || mm) ++es_start;
+			ref_start = ref_pos;
+		}
+		if (!ins) ++ref_pos;
+	}
+	fix_in_range(es, es_start, n);
+	uint32_t enc_start = 0, enc_pos = 0; es_start = 0;
+	for (uint32_t p = 0; p < n; ++p) {
+		const char s = es[p]; const bool mm = es_is_mm(s), del = s == 'D';
+		if (del || mm || enc[enc_start] != enc[enc_pos]) {
+			fix_in_range(es, es_start, p);
+			es_start = p; if (del || mm) ++es_start;
+			enc_start = enc_pos;
+		}
+		if (!del) ++enc_pos;
+	}
+	fix_in_range(es, es_start, n);
+}
+
+// One edit-script task = CEncoder::GetEditDist (encoder.cpp:1255-1283).
+// ref/enc: views of the parts inside their reads (index rl / el = the byte after the part, 255 at a read's end).
+// kind: 0 left flank, 1 right flank, 2 between anchors.  Writes the script to out (capacity rl + el + 2); returns its length.
+// Scratch must be laid out for rows/cols = (max(rl,el), max(rl,el)) — see align_task_dims().
+__host__ __device__ inline void align_task_dims(uint32_t rl, uint32_t el, uint32_t kind, long long* q, long long* t)
+{
+	if (rl == 0 || el == 0) { *q = 1; *t = 1; return; }
+	if (kind == 2) { *q = rl; *t = el; return; }
+	const uint32_t cut = rl < 2 * el ? rl : 2 * el;
+	if (cut < 2 || el < 2) { *q = cut; *t = el; }          // global fallback, rows = ref
+	else { *q = el; *t = cut; }                              // SHW: rows = enc, cols = ref prefix
+}
+
+template <int GROUP>
+__device__ uint32_t edit_script_task(const Aligner<GROUP>& A, SeqView ref, uint32_t rl, SeqView enc, uint32_t el, uint32_t kind, char* out)
+{
+	const uint32_t gl = A.gl;
+	if (rl == 0 || el == 0) {      // edit_script.h:247-266
+		if (gl == 0) {
+			if (rl == 0) for (uint32_t i = 0; i < el; ++i) out[i] = "ACGT"[enc[i]];
+			else for (uint32_t i = 0; i < rl; ++i) out[i] = 'D';
+		}
+		A.gsync();
+		return rl == 0 ? el : rl;
+	}
+	uint8_t* ops = A.scratch + A.lay.ops;
+	int n_ops = 0;
+	uint32_t n_out = 0;
+	if (kind == 2) {
+		// NW, rows = ref, cols = enc: UP = 'D', LEFT = insertion
+		int best;
+		const bool small = edlib_column_bytes(rl, el) < EDLIB_TRACEBACK_LIMIT;
+		if (small) n_ops = A.leaf(ref, (int)rl, enc, (int)el, ops, A.scratch + A.lay.tmp);
+		else {
+			best = A.sweep(ref, (int)rl, enc, (int)el, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+			A.gsync();
+			n_ops = A.path(ref, (int)rl, enc, (int)el, best, ops);
+		}
+		if (gl == 0) {
+			uint32_t pr = 0, pe = 0;
+			for (int i = 0; i < n_ops; ++i) {
+				const uint8_t o = ops[i];
+				if (o == 0) { out[i] = 'M'; ++pr; ++pe; }
+				else if (o == 1) { out[i] = 'D'; ++pr; }
+				else if (o == 2) { out[i] = "ACGT"[enc[pe++]]; }
+				else { out[i] = mismatch_symb(ref[pr], enc[pe]); ++pr; ++pe; }
+			}
+			refactor_edit_script(ref, enc, out, (uint32_t)n_ops);
+		}
+		A.gsync();
+		return (uint32_t)n_ops;
+	}
+	// flanks: SHW of enc against a prefix of ref limited to 2*|enc| symbols; the left flank works on reversed strings
+	const uint32_t cut = rl < 2 * el ? rl : 2 * el;
+	const SeqView r = kind == 0 ? ref.reversed((int)rl) : ref;      // first `cut` symbols are used
+	const SeqView e = kind == 0 ? enc.reversed((int)el) : enc;
+	uint32_t ref_end;
+	bool rows_ref;
+	if (cut < 2 || el < 2) {       // edit_script.h:336-343: global alignment of the (cut) ref against enc, rows = ref
+		rows_ref = true; ref_end = cut - 1;
+		n_ops = A.leaf(r, (int)cut, e, (int)el, ops, A.scratch + A.lay.tmp);
+	} else {
+		rows_ref = false;
+		int32_t* lastrow = reinterpret_cast<int32_t*>(A.scratch + A.lay.lastrow);
+		const bool small = edlib_column_bytes(el, cut) < EDLIB_TRACEBACK_LIMIT;
+		const int B = ((int)el + 63) >> 6;
+		uint64_t* hpv = reinterpret_cast<uint64_t*>(A.scratch + A.lay.hist);
+		uint64_t* hmv = hpv + (size_t)B * cut;
+		int32_t* hsc = reinterpret_cast<int32_t*>(hmv + (size_t)B * cut);
+		A.sweep(e, (int)el, r, (int)cut, small ? hpv : nullptr, small ? hmv : nullptr, small ? hsc : nullptr, lastrow, nullptr, nullptr, nullptr);
+		A.gsync();
+		// leftmost column with the minimal last-row score (edlib.cpp:660-674)
+		int best = 0x7fffffff, end = 0;
+		for (int c = (int)gl; c < (int)cut; c += GROUP) { const int v = lastrow[c]; if (v < best) { best = v; end = c; } }
+		if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) {
+			const int ob = __shfl_xor_sync(A.gmask, best, d, GROUP), oe = __shfl_xor_sync(A.gmask, end, d, GROUP);
+			if (ob < best || (ob == best && oe < end)) { best = ob; end = oe; }
+		}
+		ref_end = (uint32_t)end;
+		const int T = end + 1;
+		if (small) {
+			if (gl == 0) { typename Aligner<GROUP>::Hist h{hpv, hmv, hsc, B, (int)el}; n_ops = Aligner<GROUP>::traceback(h, (int)el, T, ops, A.scratch + A.lay.tmp); }
+			if (GROUP > 1) n_ops = __shfl_sync(A.gmask, n_ops, 0, GROUP);
+			A.gsync();
+		} else n_ops = A.path(e, (int)el, r, T, best, ops);
+	}
+	if (gl == 0) {
+		// symbols of the (possibly reversed) problem in forward order
+		char* w = out;
+		uint32_t lead = 0;
+		if (kind == 0) { lead = (rl - 1) - ref_end; for (uint32_t i = 0; i < lead; ++i) out[i] = 'D'; w = out + lead; }
+		uint32_t pr = 0, pe = 0;
+		for (int i = 0; i < n_ops; ++i) {
+			const uint8_t o = ops[i];
+			const int at = kind == 0 ? n_ops - 1 - i : i;      // the left flank's script is reversed back
+			char ch;
+			if (o == 0) { ch = 'M'; ++pr; ++pe; }
+			else if (o == 3) { ch = mismatch_symb(r[pr], e[pe]); ++pr; ++pe; }
+			else if ((o == 1) == rows_ref) { ch = 'D'; ++pr; }              // UP consumes a row symbol, LEFT a column symbol
+			else { ch = "ACGT"[e[pe++]]; }
+			w[at] = ch;
+		}
+		if (kind == 0) refactor_edit_script(ref.sub((int)lead), enc, w, (uint32_t)n_ops);
+		else refactor_edit_script(ref, enc, w, (uint32_t)n_ops);
+		n_out = lead + (uint32_t)n_ops;
+	}
+	if (GROUP > 1) n_out = __shfl_sync(A.gmask, n_out, 0, GROUP);
+	A.gsync();
+	return n_out;
+}
+
+} // namespace clb

@@ -177,6 +177,14 @@ clb_status clb_graph_common(clb_ctx* c, uint64_t* common_off, uint32_t* common_n
 	return CLB_OK;
 }
 
+clb_status clb_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
+	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap)
+{
+	CLB_ENTER(c);
+	if (n && (!seqs || !ref_off || !ref_len || !enc_off || !enc_len || !kind || !out_off || !out)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s2_edit_scripts(c, seqs, n_seq_bytes, ref_off, ref_len, enc_off, enc_len, kind, n, out_off, out, cap);
+}
+
 clb_status clb_get_packed_read(clb_ctx* c, uint32_t read_id, uint8_t* out, uint64_t cap, uint64_t* n_bytes)
 {
 	CLB_ENTER(c);

@@ -37,8 +37,8 @@ struct DevBuf {
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
 
 // kernel classes for the optional per-kernel timing (clb_profile_*)
-enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_N };
-static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc" };
+enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_N };
+static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode" };
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 } // namespace clb
@@ -146,5 +146,7 @@ clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats);
 clb_status s1a_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
 clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo);
 void s1_free(clb_ctx* c);
+clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
+	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);
 
 } // namespace clb

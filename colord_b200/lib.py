@@ -15,9 +15,9 @@ EXPORTS = [
     "clb_counts_size", "clb_counts_export", "clb_counts_reset", "clb_counts_merge", "clb_count_finalize",
     "clb_filter_list", "clb_filter_import", "clb_filter_check", "clb_graph_build", "clb_graph_accepted_size",
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
-    "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get",
+    "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
 ]
-KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc"]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode"]
 
 
 class Params(C.Structure):
@@ -75,6 +75,7 @@ def load():
     L.clb_get_packed_read.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
     L.clb_sampler.argtypes = [u32, C.c_double, u32, u32, vp]; L.clb_sampler.restype = None
     L.clb_kernel_launches.argtypes = [vp]; L.clb_kernel_launches.restype = u64
+    L.clb_edit_scripts.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, u64]
     L.clb_profile_enable.argtypes = [vp, i32]
     L.clb_profile_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     for name in EXPORTS:
@@ -262,6 +263,23 @@ class Context:
         out = np.zeros(n.value, np.uint8)
         self._ck(self.L.clb_get_packed_read(self.h, read_id, _np_ptr(out), n.value, C.byref(n)))
         return out
+
+    # ---- stage 2
+    def edit_scripts(self, cases):
+        """cases: list of (kind, ref symbols, enc symbols, ref tail byte, enc tail byte) -> list of script bytes."""
+        parts, ref_off, ref_len, enc_off, enc_len, kinds, o = [], [], [], [], [], [], 0
+        for kind, ref, enc, rt, et in cases:
+            ref_off.append(o); ref_len.append(len(ref)); parts += [np.asarray(ref, np.uint8), np.array([rt], np.uint8)]; o += len(ref) + 1
+            enc_off.append(o); enc_len.append(len(enc)); parts += [np.asarray(enc, np.uint8), np.array([et], np.uint8)]; o += len(enc) + 1
+            kinds.append(kind)
+        seqs = np.concatenate(parts) if parts else np.zeros(1, np.uint8)
+        n = len(cases)
+        cap = int(sum(ref_len) + sum(enc_len) + 2 * n + 16)
+        out = np.zeros(cap, np.uint8)
+        out_off = np.zeros(n + 1, np.uint64)
+        a = [np.array(x, t) for x, t in ((ref_off, np.uint64), (ref_len, np.uint32), (enc_off, np.uint64), (enc_len, np.uint32), (kinds, np.uint32))]
+        self._ck(self.L.clb_edit_scripts(self.h, _np_ptr(seqs), len(seqs), *[_np_ptr(x) for x in a], n, _np_ptr(out_off), _np_ptr(out), cap))
+        return [out[int(out_off[i]):int(out_off[i + 1])].tobytes() for i in range(n)]
 
     def profile_enable(self, on=True):
         self._ck(self.L.clb_profile_enable(self.h, int(on)))

@@ -106,6 +106,16 @@ clb_status clb_graph_candidates(clb_ctx* ctx, uint32_t* cand, uint32_t* cand_n);
 clb_status clb_graph_common_size(clb_ctx* ctx, uint64_t* total);
 clb_status clb_graph_common(clb_ctx* ctx, uint64_t* common_off, uint32_t* common_n, uint64_t* kmers, uint64_t cap);
 
+/* ---- Stage 2: edit scripts -----------------------------------------------------------------------
+ * Batch form of CEncoder::GetEditDist (encoder.cpp:1255-1283): optimal unit-cost alignment of a part of the read being
+ * encoded against a part of the (oriented) reference read with edlib's path (edit_script.h:272-413, libs/edlib) followed
+ * by refactor_edit_script (edit_script.h:661).  seqs: symbols 0..3 (HOST); task i aligns seqs[ref_off[i] .. +ref_len[i])
+ * with seqs[enc_off[i] .. +enc_len[i]); the byte after each part must be readable and is what follows the part in its read
+ * (255 at a read's end) — the reference's canonicalisation looks at it.  kind: 0 left flank (frag 0), 1 right flank (last
+ * frag), 2 between anchors.  Scripts (alphabet M D A C G T X Y Z) are written back to back; out_off has n+1 entries. */
+clb_status clb_edit_scripts(clb_ctx* ctx, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
+	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);
+
 /* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
  * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
  * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
