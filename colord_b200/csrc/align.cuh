@@ -30,6 +30,21 @@ struct SeqView {            // element i = base[i * step]; step = -1 gives a rev
 	__device__ __forceinline__ SeqView reversed(int n) const { return SeqView{base + (long long)(n - 1) * step, -step}; }
 };
 
+// The same interface over the resident 2-bit packed read store (ctx.h: pk, 32 bases per word, first base in the top bits).
+// element i = base at absolute stream position origin + i*step, complemented if comp == 3 (reverse-complement views use
+// step = -1, comp = 3); positions outside [lo, hi) — the read's extent — give the reference's 255 guard byte.
+struct PackedView {
+	const uint64_t* pk; long long origin; int step; uint32_t comp; long long lo, hi;
+	__device__ __forceinline__ uint8_t operator[](int i) const
+	{
+		const long long a = origin + (long long)i * step;
+		if (a < lo || a >= hi) return 255;
+		return (uint8_t)(((uint32_t)(pk[a >> 5] >> (62 - 2 * (a & 31))) & 3u) ^ comp);
+	}
+	__device__ __forceinline__ PackedView sub(int off) const { PackedView v = *this; v.origin += (long long)off * step; return v; }
+	__device__ __forceinline__ PackedView reversed(int n) const { PackedView v = *this; v.origin += (long long)(n - 1) * step; v.step = -step; return v; }
+};
+
 __host__ __device__ inline long long edlib_column_bytes(long long q, long long t) { return (2ll * 8 + 4) * ((q + 63) / 64) * t + 2ll * 4 * t; }
 constexpr long long EDLIB_TRACEBACK_LIMIT = 1024 * 1024;
 
@@ -87,7 +102,8 @@ struct Aligner {
 
 	// Forward sweep of rows[0..Q) x cols[0..T).  hist_* may be null.  lastrow (int32[T]) receives D(Q-1, c) if non-null.
 	// fin_* (per block) receive the final column if non-null.  Returns D(Q-1, T-1) to every lane.
-	__device__ int sweep(SeqView rows, int Q, SeqView cols, int T, uint64_t* hist_pv, uint64_t* hist_mv, int32_t* hist_sc,
+	template <class V>
+	__device__ int sweep(V rows, int Q, V cols, int T, uint64_t* hist_pv, uint64_t* hist_mv, int32_t* hist_sc,
 		int32_t* lastrow, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
 	{
 		const int B = (Q + 63) >> 6;
@@ -188,7 +204,8 @@ struct Aligner {
 
 	// edlib's obtainAlignment for rows x cols with known optimal score `best`: ops appended to ops_out (forward order).
 	// Iterative Hirschberg with an explicit stack; all lanes of the group call.  Returns the number of ops.
-	__device__ int path(SeqView rows, int Q, SeqView cols, int T, int best, uint8_t* ops_out) const
+	template <class V>
+	__device__ int path(V rows, int Q, V cols, int T, int best, uint8_t* ops_out) const
 	{
 		uint8_t* tmp = scratch + lay.tmp;
 		int n_ops = 0;
@@ -208,7 +225,7 @@ struct Aligner {
 			--sp;
 			const int qo = stack[sp * 5], ql = stack[sp * 5 + 1], to = stack[sp * 5 + 2], tl = stack[sp * 5 + 3], bs = stack[sp * 5 + 4];
 			gsync();
-			const SeqView r = rows.sub(qo), c = cols.sub(to);
+			const V r = rows.sub(qo), c = cols.sub(to);
 			if (ql == 0 || tl == 0 || edlib_column_bytes(ql, tl) < EDLIB_TRACEBACK_LIMIT) {
 				n_ops += leaf(r, ql, c, tl, ops_out + n_ops, tmp);
 				continue;
@@ -241,7 +258,8 @@ struct Aligner {
 	}
 
 	// stored-column traceback of a problem below edlib's 1 MiB limit
-	__device__ int leaf(SeqView rows, int Q, SeqView cols, int T, uint8_t* out, uint8_t* tmp) const
+	template <class V>
+	__device__ int leaf(V rows, int Q, V cols, int T, uint8_t* out, uint8_t* tmp) const
 	{
 		int n = 0;
 		if (Q == 0 || T == 0) {
@@ -284,7 +302,8 @@ __device__ inline void fix_in_range(char* es, uint32_t start, uint32_t end)   //
 	}
 }
 // edit_script.h:591-671; ref/enc may be indexed one past the part (the byte that follows it in the read)
-__device__ inline void refactor_edit_script(SeqView ref, SeqView enc, char* es, uint32_t n)
+template <class V>
+__device__ inline void refactor_edit_script(V ref, V enc, char* es, uint32_t n)
 {
 	uint32_t ref_start = 0, ref_pos = 0, es_start = 0;
 	for (uint32_t p = 0; p < n; ++p) {
@@ -323,9 +342,12 @@ __host__ __device__ inline void align_task_dims(uint32_t rl, uint32_t el, uint32
 	else { *q = el; *t = cut; }                              // SHW: rows = enc, cols = ref prefix
 }
 
-template <int GROUP>
-__device__ uint32_t edit_script_task(const Aligner<GROUP>& A, SeqView ref, uint32_t rl, SeqView enc, uint32_t el, uint32_t kind, char* out)
+// lead_out != nullptr: the 'D' run that precedes a left flank's script (the reference symbols left of the aligned window)
+// is not written; its length is returned through *lead_out instead and the returned length excludes it.
+template <int GROUP, class V>
+__device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl, V enc, uint32_t el, uint32_t kind, char* out, uint32_t* lead_out = nullptr)
 {
+	if (lead_out) *lead_out = 0;
 	const uint32_t gl = A.gl;
 	if (rl == 0 || el == 0) {      // edit_script.h:247-266
 		if (gl == 0) {
@@ -364,8 +386,8 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, SeqView ref, uint3
 	}
 	// flanks: SHW of enc against a prefix of ref limited to 2*|enc| symbols; the left flank works on reversed strings
 	const uint32_t cut = rl < 2 * el ? rl : 2 * el;
-	const SeqView r = kind == 0 ? ref.reversed((int)rl) : ref;      // first `cut` symbols are used
-	const SeqView e = kind == 0 ? enc.reversed((int)el) : enc;
+	const V r = kind == 0 ? ref.reversed((int)rl) : ref;      // first `cut` symbols are used
+	const V e = kind == 0 ? enc.reversed((int)el) : enc;
 	uint32_t ref_end;
 	bool rows_ref;
 	if (cut < 2 || el < 2) {       // edit_script.h:336-343: global alignment of the (cut) ref against enc, rows = ref
@@ -400,7 +422,11 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, SeqView ref, uint3
 		// symbols of the (possibly reversed) problem in forward order
 		char* w = out;
 		uint32_t lead = 0;
-		if (kind == 0) { lead = (rl - 1) - ref_end; for (uint32_t i = 0; i < lead; ++i) out[i] = 'D'; w = out + lead; }
+		if (kind == 0) {
+			lead = (rl - 1) - ref_end;
+			if (lead_out) { *lead_out = lead; }
+			else { for (uint32_t i = 0; i < lead; ++i) out[i] = 'D'; w = out + lead; }
+		}
 		uint32_t pr = 0, pe = 0;
 		for (int i = 0; i < n_ops; ++i) {
 			const uint8_t o = ops[i];
@@ -414,7 +440,7 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, SeqView ref, uint3
 		}
 		if (kind == 0) refactor_edit_script(ref.sub((int)lead), enc, w, (uint32_t)n_ops);
 		else refactor_edit_script(ref, enc, w, (uint32_t)n_ops);
-		n_out = lead + (uint32_t)n_ops;
+		n_out = (lead_out ? 0 : lead) + (uint32_t)n_ops;
 	}
 	if (GROUP > 1) n_out = __shfl_sync(A.gmask, n_out, 0, GROUP);
 	A.gsync();

@@ -52,6 +52,7 @@ void clb_destroy(clb_ctx* c)
 	cudaSetDevice(c->prm.device);
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
+	s2_free(c);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -183,6 +184,52 @@ clb_status clb_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_byte
 	CLB_ENTER(c);
 	if (n && (!seqs || !ref_off || !ref_len || !enc_off || !enc_len || !kind || !out_off || !out)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
 	return s2_edit_scripts(c, seqs, n_seq_bytes, ref_off, ref_len, enc_off, enc_len, kind, n, out_off, out, cap);
+}
+
+clb_status clb_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	if (!prm) return fail(c, CLB_ERR_BAD_ARG, "null params");
+	return s2_encode(c, prm, pack_sizes, n_packs);
+}
+clb_status clb_encode_size(clb_ctx* c, uint64_t* total)
+{
+	CLB_ENTER(c);
+	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_encode has not run");
+	*total = c->es_total;
+	return CLB_OK;
+}
+clb_status clb_encode_get(clb_ctx* c, uint64_t* es_off, uint8_t* es, uint64_t cap, int on_device)
+{
+	CLB_ENTER(c);
+	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_encode has not run");
+	if (cap < c->es_total) return fail(c, CLB_ERR_CAPACITY, "clb_encode_get: buffer too small");
+	const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+	CLB_CUDA(c, cudaMemcpyAsync(es_off, c->es_off, sizeof(uint64_t) * (c->n_reads + 1), kind, c->stream));
+	if (c->es_total) CLB_CUDA(c, cudaMemcpyAsync(es, c->es.p, c->es_total, kind, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+clb_status clb_encode_keep_candidates(clb_ctx* c, int on) { if (!c) return CLB_ERR_BAD_ARG; c->keep_candidates = on != 0; return CLB_OK; }
+clb_status clb_encode_candidates_size(clb_ctx* c, uint64_t* n_words)
+{
+	if (!c || !c->enc_done || !c->keep_candidates) return fail(c, CLB_ERR_STATE, "candidates were not kept");
+	uint64_t t = 0; for (auto& v : c->dbg_cand) t += v.size();
+	*n_words = t;
+	return CLB_OK;
+}
+clb_status clb_encode_candidates(clb_ctx* c, uint64_t* cand_off, uint32_t* data, uint64_t cap_words)
+{
+	if (!c || !c->enc_done || !c->keep_candidates) return fail(c, CLB_ERR_STATE, "candidates were not kept");
+	uint64_t t = 0;
+	for (uint64_t i = 0; i < c->dbg_cand.size(); ++i) {
+		cand_off[i] = t;
+		if (t + c->dbg_cand[i].size() > cap_words) return fail(c, CLB_ERR_CAPACITY, "clb_encode_candidates: buffer too small");
+		std::memcpy(data + t, c->dbg_cand[i].data(), sizeof(uint32_t) * c->dbg_cand[i].size());
+		t += c->dbg_cand[i].size();
+	}
+	cand_off[c->dbg_cand.size()] = t;
+	return CLB_OK;
 }
 
 clb_status clb_get_packed_read(clb_ctx* c, uint32_t read_id, uint8_t* out, uint64_t cap, uint64_t* n_bytes)

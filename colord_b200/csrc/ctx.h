@@ -113,6 +113,18 @@ struct clb_ctx {
 	uint64_t* common_off = nullptr;  // HiFi
 	uint64_t* common = nullptr;
 	uint64_t common_total = 0;
+
+	// ---- stage 2 ----
+	bool enc_done = false;
+	clb::DevBuf<uint8_t> es;         // CompactES bytes of all reads, input order
+	uint64_t* es_off = nullptr;      // n_reads + 1
+	uint64_t es_total = 0;
+	uint32_t* d_ref_to_read = nullptr;
+	clb::DevBuf<uint8_t> s2_arena;   // pair / anchor arena of the current batch
+	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current wave
+	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
+	bool keep_candidates = false;
+	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)
 };
 
 namespace clb {
@@ -146,6 +158,9 @@ clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats);
 clb_status s1a_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
 clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo);
 void s1_free(clb_ctx* c);
+clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total);   // stage1b.cu; synchronizes
+clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* pack_sizes, uint32_t n_packs);
+void s2_free(clb_ctx* c);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
 	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);
 

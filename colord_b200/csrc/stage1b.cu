@@ -547,7 +547,7 @@ static clb_status scal_zero(clb_ctx* c, int which)
 
 template <typename T> static cudaError_t dev_alloc(T** p, uint64_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
 
-static clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
+clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
 {
 	const uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	uint64_t* tiles = nullptr;

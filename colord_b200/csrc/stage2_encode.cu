@@ -1,0 +1,726 @@
+// stage2_encode.cu — rows E6-E9 of SURVEY.md §8 on device, and the driver of the whole stage 2.
+//
+// The reference encodes read by read, recursing into "alternative" candidates for parts the main candidate covers badly
+// (encoder.cpp:1445-1575).  Here the recursion is turned into level waves over a batch of reads:
+//   level L:  k_task_count/k_task_fill  every new node (one AddEncodedReadWithCandidates call) lists its even fragments
+//             k_task_classify/scatter   parts are binned by lane-group class and width
+//             k_align<GROUP>            edit scripts of all parts of a bin (align.cuh)
+//             k_decide                  parts >= minPartLenToConsiderAltRead: stateless entropy test (encoder.cpp:1315-1327),
+//                                       losers get a child node on the next candidate (AdjustAnchors as a view, :778-868);
+//                                       shorter parts only prepare their CEntropyEstimator statistics
+//   then      k_estimate                one thread per read pack replays the adaptive estimator (utils.h:1060-1126) in the
+//                                       reference's order — the only serial dependency of stage 2 — and settles short parts
+//             k_emit_size/k_emit_write  one thread per read walks its node tree and run-length codes the big edit script into
+//                                       CompactES bytes (encoder.cpp:1348-1443, utils.h:69-273)
+// Double arithmetic follows the reference's operation order with explicit round-to-nearest adds/multiplies (no FMA
+// contraction); log2 is CUDA's (<= 1 ulp) where the reference uses libm's.
+#include "ctx.h"
+#include "stage2.h"
+#include "align.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace clb {
+
+clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_list, const uint32_t* d_list,
+	const uint32_t* d_ref_to_read, DevBuf<uint8_t>& arena, SegInfo* d_seg, uint32_t* d_slot_dec, Node* d_nodes, CandView* d_cviews,
+	unsigned long long* d_cursor);
+
+struct ReadStore { const uint64_t* pk; const uint64_t* rd_start; const uint32_t* rd_len; const uint32_t* nmask; const uint32_t* ref_to_read; };
+
+CLB_D PackedView enc_view(const ReadStore& R, uint32_t read, uint32_t at)
+{
+	const long long s = (long long)R.rd_start[read];
+	return PackedView{R.pk, s + at, 1, 0u, s, s + (long long)R.rd_len[read]};
+}
+// element i of the view = symbol `at + i` of the oriented reference read (reverse-complement if rev)
+CLB_D PackedView ref_view(const ReadStore& R, uint32_t ref_id, uint32_t rev, uint32_t at)
+{
+	const uint32_t rr = R.ref_to_read[ref_id];
+	const long long s = (long long)R.rd_start[rr], l = (long long)R.rd_len[rr];
+	if (!rev) return PackedView{R.pk, s + at, 1, 0u, s, s + l};
+	return PackedView{R.pk, s + l - 1 - at, -1, 3u, s, s + l};
+}
+
+CLB_HD uint32_t es_cap(uint32_t rl, uint32_t el, uint32_t kind)
+{
+	const uint64_t base = el == 0 ? 0 : rl == 0 ? el : kind == 2 ? (uint64_t)rl + el : (uint64_t)(rl < 2 * (uint64_t)el ? rl : 2 * el) + el;
+	return (uint32_t)((base + base / 8 + 8 + 3) & ~3ull);
+}
+
+// ------------------------------------------------------------------------------------------------ tasks
+// fragments of a node: part i lies between anchor i-1 and anchor i (encoder.cpp:1541-1572)
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes, const CandView* __restrict__ cviews, uint32_t n0, uint32_t n1, uint32_t c,
+	ReadStore R, const uint8_t* __restrict__ arena, uint32_t* __restrict__ cnt, uint32_t* __restrict__ capu,
+	const uint64_t* __restrict__ task_off, const uint64_t* __restrict__ cap_off, uint64_t task_base, uint64_t es_base, Task* __restrict__ tasks)
+{
+	const uint32_t id = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= n1) return;
+	const Node N = nodes_in[id];
+	if (!N.valid) { if (!FILL) { cnt[id - n0] = 0; capu[id - n0] = 0; } return; }
+	const CandView V = cviews[(size_t)id * c + N.level];
+	const uint32_t RL = R.rd_len[R.ref_to_read[V.ref_id]];
+	uint32_t cur_ref = 0, cur_enc = 0;
+	uint64_t cap_sum = 0;
+	uint64_t t = 0, eo = 0;
+	if (FILL) { t = task_base + task_off[id - n0]; eo = es_base + cap_off[id - n0] * 4; nodes[id].first_task = (uint32_t)t; }
+	for (uint32_t i = 0; i <= N.n_anch; ++i) {
+		const bool last = i == N.n_anch;
+		Anchor a{0, 0, 0};
+		if (!last) a = cv_get(arena, V, i);
+		const uint32_t end_enc = last ? N.enc_len : a.pos_enc, end_ref = last ? RL : a.pos_ref;
+		const uint32_t el = end_enc - cur_enc, rl = end_ref - cur_ref;
+		const uint32_t kind = i == 0 ? 0 : (last ? 1 : 2);
+		const uint32_t cap = es_cap(rl, el, kind);
+		if (FILL) {
+			Task T{};
+			T.node = id; T.frag = i; T.enc_start = N.enc_start + cur_enc; T.el = el; T.ref_start = cur_ref; T.rl = rl; T.kind = kind;
+			T.decision = D_PENDING; T.es_off = eo; T.child = 0xFFFFFFFFu;
+			tasks[t + i] = T;
+			eo += cap;
+		} else cap_sum += cap;
+		if (!last) { cur_ref = a.pos_ref + a.len; cur_enc = a.pos_enc + a.len; }
+	}
+	if (!FILL) { cnt[id - n0] = N.n_anch + 1; capu[id - n0] = (uint32_t)(cap_sum / 4); }
+}
+
+constexpr int N_TBIN = 16, N_GCLASS = 5, N_BINS = N_TBIN * N_GCLASS;
+struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; };
+
+CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : 4; }
+CLB_HD int ilog2_u32(uint32_t x) { int r = 0; while (x >>= 1) ++r; return r; }
+
+// Parts with an empty side need no alignment (edit_script.h:247-266): el == 0 -> 'D' x rl (kept as `lead`), rl == 0 -> the
+// part's bases as insertions.  Everything else is binned.
+__global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks, uint64_t t0, uint64_t t1, ReadStore R, const Node* __restrict__ nodes,
+	char* __restrict__ esbuf, BinStats* __restrict__ bins, uint32_t* __restrict__ bin_of)
+{
+	const uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= t1) return;
+	Task& T = tasks[t];
+	if (T.el == 0) { T.lead = T.rl; T.es_len = 0; bin_of[t - t0] = 0xFFFFFFFFu; return; }
+	if (T.rl == 0) {
+		const PackedView e = enc_view(R, nodes[T.node].read, T.enc_start);
+		char* o = esbuf + T.es_off;
+		for (uint32_t i = 0; i < T.el; ++i) o[i] = "ACGT"[e[(int)i] & 3];
+		T.lead = 0; T.es_len = T.el; bin_of[t - t0] = 0xFFFFFFFFu; return;
+	}
+	long long q, tt;
+	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
+	const int b = gclass_of(q) * N_TBIN + min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
+	bin_of[t - t0] = (uint32_t)b;
+	atomicAdd(&bins->cnt[b], 1u);
+	atomicMax(&bins->maxq[b], (unsigned int)q);
+	atomicMax(&bins->maxt[b], (unsigned int)tt);
+}
+__global__ void __launch_bounds__(256) k_task_scatter(uint64_t t0, uint64_t t1, const uint32_t* __restrict__ bin_of, BinStats* __restrict__ bins, uint32_t* __restrict__ list)
+{
+	const uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= t1) return;
+	const uint32_t b = bin_of[t - t0];
+	if (b == 0xFFFFFFFFu) return;
+	list[bins->base[b] + atomicAdd(&bins->fill[b], 1u)] = (uint32_t)(t - t0);
+}
+
+template <int GROUP>
+__global__ void __launch_bounds__(128) k_align(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
+	uint8_t* __restrict__ scratch, ReadStore R, const Node* __restrict__ nodes, const CandView* __restrict__ cviews, uint32_t c, char* __restrict__ esbuf)
+{
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t slot = tid / GROUP;
+	if (slot >= n_list) return;                 // whole groups leave together
+	Task& T = tasks[t0 + list[slot]];
+	const Node N = nodes[T.node];
+	const CandView& V = cviews[(size_t)T.node * c + N.level];
+	Aligner<GROUP> A;
+	A.gl = threadIdx.x & (GROUP - 1);
+	const uint32_t lane = threadIdx.x & 31;
+	A.gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(uint32_t)(GROUP - 1)));
+	A.scratch = scratch + (uint64_t)slot * stride;
+	long long q, tt;
+	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
+	A.lay = align_scratch_layout(q, tt);
+	const PackedView ref = ref_view(R, V.ref_id, V.rev, T.ref_start), enc = enc_view(R, N.read, T.enc_start);
+	uint32_t lead = 0;
+	const uint32_t n = edit_script_task<GROUP>(A, ref, T.rl, enc, T.el, T.kind, esbuf + T.es_off, &lead);
+	if (A.gl == 0) { T.es_len = n; T.lead = lead; }
+}
+
+// ------------------------------------------------------------------------------------------------ decisions
+CLB_D int es_code(char ch) { switch (ch) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; case 'D': return 4; case 'M': return 5; case 'X': return 6; case 'Y': return 7; case 'Z': return 8; default: return 11; } }
+CLB_D uint32_t ilog2u_bits(uint64_t x) { return x ? 64 - __clzll((long long)x) : 0; }      // utils.h ilog2 convention: number of bits
+
+// utils.h:700-757 (CEntropy::entropy): -sum p log2 p over the listed symbols in the reference's order
+CLB_D double entropy_of(const uint32_t* h, int n)
+{
+	double sum = 0;
+	for (int i = 0; i < n; ++i) sum = __dadd_rn(sum, (double)h[i]);
+	const double rec = __ddiv_rn(1.0, sum);
+	double e = 0;
+	for (int i = 0; i < n; ++i) if (h[i]) { const double p = __dmul_rn((double)h[i], rec); e = __dadd_rn(e, __dmul_rn(log2(p), p)); }
+	return -e;
+}
+
+// AdjustAnchors (encoder.cpp:778-868) on a view: keep the anchors inside [ns, ne) of the current frame, clip the border
+// anchors (drop them if less than anchor_len symbols remain inside), shift to the part's frame.
+CLB_D void cv_adjust(const uint8_t* __restrict__ arena, const CandView& v, uint32_t ns, uint32_t ne, uint32_t anchor_len, CandView& o)
+{
+	o = v; o.n = 0; o.tot = 0;
+	const uint32_t n = v.n;
+	uint32_t first = 0xFFFFFFFFu, last = 0xFFFFFFFFu;
+	for (uint32_t i = 0; i < n; ++i) { const Anchor a = cv_get(arena, v, i); if (a.pos_enc + a.len > ns) { first = i; break; } }
+	if (first == 0xFFFFFFFFu) return;
+	{ const Anchor a = cv_get(arena, v, first); if (a.pos_enc < ns && (a.pos_enc + a.len) - ns < anchor_len) ++first; }
+	for (uint32_t i = n; i-- > 0;) { if (cv_get(arena, v, i).pos_enc < ne) { last = i; break; } }
+	if (last == 0xFFFFFFFFu) return;
+	if (first < n && last < n) {
+		const Anchor a = cv_get(arena, v, last);
+		if (a.pos_enc + a.len > ne && ne - a.pos_enc < anchor_len) { if (last == 0) return; --last; }
+	}
+	if (first > last) return;
+	o.first = v.first + first; o.n = last - first + 1;
+	o.head = first == 0 ? v.head : 0; o.tail = last == n - 1 ? v.tail : 0;
+	{ const Anchor a = cv_get(arena, o, o.n - 1); if (a.pos_enc + a.len > ne) o.tail += a.pos_enc + a.len - ne; }
+	{ const Anchor a = cv_get(arena, o, 0); if (a.pos_enc < ns) o.head += ns - a.pos_enc; }
+	o.shift = v.shift + ns;
+	uint32_t tot = 0;
+	for (uint32_t i = 0; i < o.n; ++i) tot += cv_get(arena, o, i).len;
+	o.tot = tot;
+}
+
+struct DecideArgs {
+	Task* tasks; uint64_t t0, t1;
+	Node* nodes; CandView* cviews; unsigned int* node_cursor; uint32_t node_cap;
+	const uint8_t* arena; ReadStore R; char* esbuf; S2P P;
+};
+
+__global__ void __launch_bounds__(128) k_decide(DecideArgs a)
+{
+	const uint64_t t = a.t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.t1) return;
+	Task& T = a.tasks[t];
+	const Node N = a.nodes[T.node];
+	const char* es = a.esbuf + T.es_off;
+	const uint32_t n = T.es_len, lead = T.lead, el = T.el;
+	const PackedView enc = enc_view(a.R, N.read, T.enc_start);
+	if (el >= a.P.min_alt) {
+		// encoder.cpp:1300-1327: >= 10 leading deletions are left out of the comparison
+		uint32_t k = 0; while (k < n && es[k] == 'D') ++k;
+		uint32_t h[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};      // order A C D G M T X Y Z S R (utils.h:721)
+		uint32_t n_eff;
+		if (lead + k >= 10) n_eff = n - k; else { k = 0; n_eff = lead + n; h[2] = lead; }
+		for (uint32_t i = k; i < n; ++i) {
+			switch (es[i]) { case 'A': ++h[0]; break; case 'C': ++h[1]; break; case 'D': ++h[2]; break; case 'G': ++h[3]; break; case 'M': ++h[4]; break;
+			case 'T': ++h[5]; break; case 'X': ++h[6]; break; case 'Y': ++h[7]; break; default: ++h[8]; break; }
+		}
+		uint32_t hd[4] = {0, 0, 0, 0};
+		for (uint32_t i = 0; i < el; ++i) ++hd[enc[(int)i] & 3];
+		const double lhs = __dmul_rn(__dmul_rn(entropy_of(h, 11), (double)n_eff), a.P.cost_mult);
+		const double rhs = __dmul_rn(entropy_of(hd, 4), (double)el);
+		if (lhs < rhs) { T.decision = D_ES; return; }
+		// encoder.cpp:1329-1346 (EncodeWithAlternativeRead)
+		if (N.ncand <= N.level + 1 || N.level >= a.P.max_rec) { T.decision = D_PLAIN; return; }
+		const uint32_t c = a.P.c;
+		const CandView* pv = a.cviews + (size_t)T.node * c;
+		const uint32_t ns = T.enc_start - N.enc_start, ne = ns + el;
+		CandView loc[32];
+		for (uint32_t q = N.level + 1; q < N.ncand; ++q) {
+			CandView v; cv_adjust(a.arena, pv[q], ns, ne, a.P.m, v);
+			uint32_t j = q;
+			while (j > N.level + 1 && loc[j - 1].tot < v.tot) { loc[j] = loc[j - 1]; --j; }
+			loc[j] = v;
+		}
+		if (loc[N.level + 1].tot == 0) { T.decision = D_PLAIN; return; }
+		const uint32_t id = atomicAdd(a.node_cursor, 1u);
+		if (id >= a.node_cap) { T.decision = D_PLAIN; return; }          // cannot happen: capacity = nodes + tasks of the level
+		CandView* cv = a.cviews + (size_t)id * c;
+		for (uint32_t q = 0; q <= N.level; ++q) cv[q] = pv[q];
+		for (uint32_t q = N.level + 1; q < N.ncand; ++q) cv[q] = loc[q];
+		Node ch{};
+		ch.read = N.read; ch.level = N.level + 1; ch.enc_start = T.enc_start; ch.enc_len = el; ch.first_task = 0;
+		ch.n_anch = loc[N.level + 1].n; ch.ncand = N.ncand; ch.valid = 1;
+		a.nodes[id] = ch;
+		T.child = id; T.decision = D_ALT;
+		return;
+	}
+	// short part: the decision belongs to the adaptive estimator; prepare its inputs (utils.h:838-899 analyze_es)
+	uint16_t rd[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+	uint8_t* runs = reinterpret_cast<uint8_t*>(a.esbuf + T.es_off + n);
+	uint32_t n_runs = 0;
+	char cur = lead ? 'D' : ' '; uint32_t len = lead;
+	for (uint32_t i = 0; i <= n; ++i) {
+		const char x = i < n ? es[i] : ' ';
+		if (x == cur) { ++len; continue; }
+		if (cur == 'D') { if (len >= 10) { ++rd[9]; runs[n_runs++] = (uint8_t)(ilog2u_bits(len) + 1); } else rd[4] += (uint16_t)len; }
+		else if (cur == 'M') { if (len >= 15) { ++rd[10]; runs[n_runs++] = (uint8_t)(ilog2u_bits(len) + 1); } else rd[5] += (uint16_t)len; }
+		else if (cur != ' ') ++rd[es_code(cur)];
+		cur = x; len = 1;
+	}
+	uint16_t rp[4] = {0, 0, 0, 0};
+	for (uint32_t i = 0; i < el; ++i) ++rp[enc[(int)i] & 3];
+	for (int i = 0; i < 12; ++i) T.rd[i] = rd[i];
+	for (int i = 0; i < 4; ++i) T.rp[i] = rp[i];
+	T.n_runs = n_runs;
+	T.decision = D_PENDING;
+}
+
+// ------------------------------------------------------------------------------------------------ estimator
+struct Estimator {              // utils.h:760-1126
+	uint32_t dna[4], es[12], dec[2];
+	double dna_log[4], es_log[12], dec_log[2];
+	uint32_t dna_sum, es_sum, dec_sum;
+};
+CLB_D void est_rescale(uint32_t* a, int n, uint32_t& sum) { while (sum > (1u << 20)) { sum = 0; for (int i = 0; i < n; ++i) { a[i] = (a[i] + 1) / 2; sum += a[i]; } } }
+CLB_D void est_logs(const uint32_t* a, double* l, int n, uint32_t sum)
+{
+	const double rec = __ddiv_rn(1.0, (double)sum);
+	for (int i = 0; i < n; ++i) l[i] = a[i] ? -log2(__dmul_rn((double)a[i], rec)) : 0.0;
+}
+CLB_D void est_reset(Estimator& e)
+{
+	for (int i = 0; i < 4; ++i) e.dna[i] = 1; e.dna_sum = 4;
+	for (int i = 0; i < 12; ++i) e.es[i] = 1; e.es_sum = 12;
+	for (int i = 0; i < 2; ++i) e.dec[i] = 1; e.dec_sum = 2;
+	est_logs(e.dna, e.dna_log, 4, e.dna_sum); est_logs(e.es, e.es_log, 12, e.es_sum); est_logs(e.dec, e.dec_log, 2, e.dec_sum);
+}
+// base counts of a read from the packed stream
+CLB_D void read_hist(const uint64_t* __restrict__ pk, uint64_t start, uint32_t len, uint32_t* h)
+{
+	uint64_t p = start; const uint64_t end = start + len;
+	uint32_t c1 = 0, c2 = 0, c3 = 0;
+	while (p < end) {
+		const uint64_t w = pk[p >> 5];
+		const uint32_t o = (uint32_t)(p & 31);
+		const uint32_t take = (uint32_t)min((uint64_t)(32 - o), end - p);
+		// fields o .. o+take-1 (field 0 = top two bits)
+		uint64_t m = take == 32 ? ~0ULL : (((1ULL << (2 * take)) - 1) << (64 - 2 * (o + take)));
+		m &= 0x5555555555555555ULL;
+		const uint64_t lo = w & m, hi = (w >> 1) & m;
+		c3 += __popcll(lo & hi); c2 += __popcll(hi & ~lo); c1 += __popcll(lo & ~hi);
+		p += take;
+	}
+	h[0] = len - c1 - c2 - c3; h[1] = c1; h[2] = c2; h[3] = c3;
+}
+
+struct PackArgs {
+	const uint32_t* pack_first; uint32_t n_packs;       // pack_first[n_packs + 1]: read index (absolute)
+	uint32_t read_lo;
+	const uint32_t* slot_of_read;                        // per batch read: level-0 node or 0xFFFFFFFF
+	const uint8_t* has_n;
+	Task* tasks; const Node* nodes; const char* esbuf; ReadStore R;
+};
+
+__global__ void __launch_bounds__(32) k_estimate(PackArgs a)
+{
+	const uint32_t pk_i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (pk_i >= a.n_packs) return;
+	Estimator e; est_reset(e);
+	for (uint32_t r = a.pack_first[pk_i]; r < a.pack_first[pk_i + 1]; ++r) {
+		if (a.has_n[r]) continue;
+		{	// LogRead (utils.h:946)
+			uint32_t h[4]; read_hist(a.R.pk, a.R.rd_start[r], a.R.rd_len[r], h);
+			for (int i = 0; i < 4; ++i) e.dna[i] += h[i];
+			e.dna_sum += a.R.rd_len[r];
+			est_rescale(e.dna, 4, e.dna_sum);
+			est_logs(e.dna, e.dna_log, 4, e.dna_sum);
+		}
+		const uint32_t root = a.slot_of_read[r - a.read_lo];
+		if (root == 0xFFFFFFFFu || !a.nodes[root].valid) continue;
+		uint32_t st_node[10], st_i[10]; int sp = 1;
+		st_node[0] = root; st_i[0] = 0;
+		while (sp > 0) {
+			const Node& N = a.nodes[st_node[sp - 1]];
+			if (st_i[sp - 1] > N.n_anch) { --sp; continue; }
+			Task& T = a.tasks[N.first_task + st_i[sp - 1]++];
+			if (T.decision == D_ALT) { st_node[sp] = T.child; st_i[sp] = 0; ++sp; continue; }
+			if (T.decision != D_PENDING) continue;
+			// EncodeWithEditScript (utils.h:1060-1126)
+			uint32_t loc[12]; uint32_t loc_sum = e.es_sum;
+			for (int i = 0; i < 12; ++i) { loc[i] = e.es[i] + T.rd[i]; loc_sum += T.rd[i]; }
+			double es_cost = e.dec_log[0], plain_cost = e.dec_log[1];
+			est_logs(loc, e.es_log, 12, loc_sum);
+			for (int i = 0; i < 12; ++i) es_cost = __dadd_rn(es_cost, __dmul_rn((double)T.rd[i], e.es_log[i]));
+			const uint8_t* runs = reinterpret_cast<const uint8_t*>(a.esbuf + T.es_off + T.es_len);
+			for (uint32_t i = 0; i < T.n_runs; ++i) es_cost = __dadd_rn(es_cost, (double)runs[i]);
+			for (int i = 0; i < 4; ++i) plain_cost = __dadd_rn(plain_cost, __dmul_rn((double)T.rp[i], e.dna_log[i]));
+			plain_cost = __dadd_rn(plain_cost, (double)(ilog2u_bits(T.rl) + 1));
+			const bool plain = plain_cost < es_cost;
+			if (plain) { ++e.dec[1]; est_rescale(e.es, 12, e.es_sum); }
+			else { ++e.dec[0]; for (int i = 0; i < 12; ++i) e.es[i] = loc[i]; e.es_sum = loc_sum; est_rescale(e.es, 12, e.es_sum); }
+			++e.dec_sum;
+			est_rescale(e.dec, 2, e.dec_sum);
+			est_logs(e.dec, e.dec_log, 2, e.dec_sum);
+			T.decision = plain ? D_PLAIN : D_ES;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ tuple emission
+enum : uint32_t { T_INS = 0, T_DEL = 1, T_MATCH = 2, T_SUB = 3, T_ANCHOR = 4, T_SKIP = 5, T_ALT = 6, T_MAIN = 7, T_PLAIN = 8, T_START_PLAIN = 9, T_START_ES = 10, T_START_N = 11 };
+
+template <bool W>
+struct TupleOut {
+	uint8_t* p; uint64_t n;
+	CLB_D void byte(uint32_t b) { if (W) p[n] = (uint8_t)b; ++n; }
+	CLB_D void len28(uint32_t type, uint32_t v) { byte((type << 4) + (v >> 24)); byte((v >> 16) & 0xff); byte((v >> 8) & 0xff); byte(v & 0xff); }
+	CLB_D void id(uint32_t type, uint32_t x, uint32_t rev) { byte((type << 4) + rev); byte(x >> 24); byte((x >> 16) & 0xff); byte((x >> 8) & 0xff); byte(x & 0xff); }
+	// encoder.cpp:1348-1392 (singleEditScriptSymbolStore)
+	CLB_D void run(char s, uint32_t rep)
+	{
+		if (s == 'M') { if (rep >= 15) len28(T_ANCHOR, rep); else for (uint32_t i = 0; i < rep; ++i) byte(T_MATCH << 4); }
+		else if (s == 'D') { if (rep > 16) len28(T_SKIP, rep); else for (uint32_t i = 0; i < rep; ++i) byte(T_DEL << 4); }
+		else if (s == 'X' || s == 'Y' || s == 'Z') for (uint32_t i = 0; i < rep; ++i) byte((T_SUB << 4) + (uint32_t)(s - 'X'));
+		else for (uint32_t i = 0; i < rep; ++i) byte((T_INS << 4) + (uint32_t)es_code(s));
+	}
+};
+
+struct EmitArgs {
+	uint32_t read_lo, n_reads;                       // batch
+	const uint32_t* slot_of_read; const uint8_t* has_n;
+	const Task* tasks; const Node* nodes; const CandView* cviews; uint32_t c;
+	const uint8_t* arena; const char* esbuf; ReadStore R;
+	uint32_t* size; uint32_t* kind;                  // per batch read; kind 0 = edit script, 1 = plain, 2 = plain with N
+	const uint64_t* off; uint64_t base; uint8_t* out; uint64_t* es_off;
+};
+
+template <bool W>
+__device__ uint64_t emit_read(const EmitArgs& a, uint32_t root, uint8_t* dst)
+{
+	TupleOut<W> o{dst, 0};
+	struct Frame { uint32_t node, i, last_pos, cur_ref, after_d, open; } st[10];
+	int sp = 1;
+	st[0] = Frame{root, 0, 0, 0, 0, 0};
+	const CandView& V0 = a.cviews[(size_t)root * a.c];
+	const uint32_t main_ref = V0.ref_id;
+	o.id(T_START_ES, main_ref, V0.rev);
+	bool first = true;
+	char ps = 0; uint32_t pr = 0;            // pending run of the open segment
+	while (sp > 0) {
+		Frame& f = st[sp - 1];
+		const Node& N = a.nodes[f.node];
+		const CandView& V = a.cviews[(size_t)f.node * a.c + N.level];
+		// big_edit_script += symbols (the segment header is written when the first symbol arrives: encoder.cpp:1414-1443)
+		auto push = [&](char s, uint32_t rep) {
+			if (!rep) return;
+			if (!f.open) {
+				f.open = 1;
+				if (N.level == 0) { if (V.ref_id != main_ref) o.id(T_ALT, V.ref_id, V.rev); else if (!first) o.byte(T_MAIN << 4); }
+				else { if (V.ref_id != main_ref) o.id(T_ALT, V.ref_id, V.rev); else o.byte(T_MAIN << 4); }
+				ps = 'D'; pr = N.level > 0 ? f.last_pos : 0;
+			}
+			if (pr && ps == s) pr += rep;
+			else { if (pr) o.run(ps, pr); ps = s; pr = rep; }
+		};
+		auto flush = [&](uint32_t cur_pos) {
+			if (f.open) { if (pr) o.run(ps, pr); pr = 0; f.last_pos = cur_pos; first = false; f.open = 0; }
+		};
+		if (f.after_d) { const uint32_t d = f.after_d; f.after_d = 0; push('D', d); }
+		const uint32_t n_frag = 2 * N.n_anch + 1;
+		if (f.i >= n_frag) { flush(f.cur_ref); --sp; continue; }
+		const uint32_t i = f.i++;
+		if (i & 1) {
+			const Anchor an = cv_get(a.arena, V, i >> 1);
+			push('M', an.len);
+			f.cur_ref = an.pos_ref + an.len;
+			continue;
+		}
+		const Task& T = a.tasks[N.first_task + (i >> 1)];
+		const bool last = i == n_frag - 1;
+		if (T.decision == D_ES) {
+			push('D', T.lead);
+			const char* es = a.esbuf + T.es_off;
+			for (uint32_t k = 0; k < T.es_len; ++k) push(es[k], 1);
+		} else if (T.decision == D_ALT) {
+			flush(f.cur_ref);
+			if (!last) f.after_d = T.rl;
+			st[sp] = Frame{T.child, 0, 0, 0, 0, 0};
+			++sp;
+		} else {
+			const PackedView e = enc_view(a.R, N.read, T.enc_start);
+			for (uint32_t k = 0; k < T.el; ++k) push("ACGT"[e[(int)k] & 3], 1);
+			if (!last) push('D', T.rl);
+		}
+	}
+	return o.n;
+}
+
+template <bool W>
+__global__ void __launch_bounds__(128) k_emit(EmitArgs a)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n_reads) return;
+	const uint32_t r = a.read_lo + i;
+	const uint32_t root = a.slot_of_read[i];
+	if (!W) {
+		if (a.has_n[r]) { a.kind[i] = 2; a.size[i] = 1 + a.R.rd_len[r]; return; }
+		if (root == 0xFFFFFFFFu || !a.nodes[root].valid) { a.kind[i] = 1; a.size[i] = 1 + a.R.rd_len[r]; return; }
+		a.kind[i] = 0;
+		a.size[i] = (uint32_t)emit_read<false>(a, root, nullptr);
+	} else {
+		a.es_off[r] = a.base + a.off[i];
+		if (a.kind[i] == 0) emit_read<true>(a, root, a.out + a.base + a.off[i]);
+	}
+}
+
+// plain reads: start tuple + one plain(base) tuple per symbol (encoder.cpp:663-682)
+__global__ void __launch_bounds__(256) k_emit_plain(EmitArgs a)
+{
+	const uint32_t i = blockIdx.x;
+	const uint32_t k = a.kind[i];
+	if (k == 0) return;
+	const uint32_t r = a.read_lo + i;
+	uint8_t* o = a.out + a.base + a.off[i];
+	const uint64_t s = a.R.rd_start[r]; const uint32_t len = a.R.rd_len[r];
+	if (threadIdx.x == 0) o[0] = (uint8_t)((k == 2 ? T_START_N : T_START_PLAIN) << 4);
+	for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) {
+		const uint64_t p = s + j;
+		const uint32_t isn = (a.R.nmask[p >> 5] >> (p & 31)) & 1u;
+		o[1 + j] = (uint8_t)((T_PLAIN << 4) + (isn ? 4u : base_at(a.R.pk, p)));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+template <typename T> static cudaError_t dmalloc(T** p, uint64_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+struct Scoped {            // frees the batch's device buffers on every exit path
+	std::vector<void*> v;
+	template <typename T> cudaError_t get(T** p, uint64_t n) { cudaError_t e = dmalloc(p, n); if (e == cudaSuccess) v.push_back(*p); return e; }
+	~Scoped() { for (void* p : v) cudaFree(p); }
+};
+
+static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t t0, uint64_t t1, const ReadStore& R, const Node* d_nodes, const CandView* d_cviews,
+	char* d_esbuf, BinStats* d_bins)
+{
+	cudaStream_t s = c->stream;
+	const uint64_t nt = t1 - t0;
+	if (!nt) return CLB_OK;
+	Scoped mem;
+	uint32_t* d_bin_of = nullptr; uint32_t* d_list = nullptr;
+	CLB_CUDA(c, mem.get(&d_bin_of, nt));
+	CLB_CUDA(c, mem.get(&d_list, nt));
+	CLB_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(BinStats), s));
+	const uint32_t blocks = (uint32_t)((nt + 255) / 256);
+	CLB_TIMED(c, K_ENCODE, (k_task_classify<<<blocks, 256, 0, s>>>(d_tasks, t0, t1, R, d_nodes, d_esbuf, d_bins, d_bin_of)));
+	CLB_LAUNCH_CHECK(c, "k_task_classify");
+	BinStats hb;
+	CLB_CUDA(c, cudaMemcpyAsync(&hb, d_bins, sizeof(BinStats), cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	unsigned int at = 0;
+	for (int b = 0; b < N_BINS; ++b) { hb.base[b] = at; at += hb.cnt[b]; hb.fill[b] = 0; }
+	if (!at) return CLB_OK;
+	CLB_CUDA(c, cudaMemcpyAsync(d_bins, &hb, sizeof(BinStats), cudaMemcpyHostToDevice, s));
+	CLB_TIMED(c, K_ENCODE, (k_task_scatter<<<blocks, 256, 0, s>>>(t0, t1, d_bin_of, d_bins, d_list)));
+	CLB_LAUNCH_CHECK(c, "k_task_scatter");
+	static const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
+	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 6ull << 30;
+	for (int b = 0; b < N_BINS; ++b) {
+		if (!hb.cnt[b]) continue;
+		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
+		const uint64_t per_wave = std::max<uint64_t>(1, budget / stride);
+		const int g = 1 << (b / N_TBIN == 4 ? 5 : b / N_TBIN);
+		for (uint64_t w0 = 0; w0 < hb.cnt[b]; w0 += per_wave) {
+			const uint32_t m = (uint32_t)std::min<uint64_t>(per_wave, hb.cnt[b] - w0);
+			CLB_CUDA(c, c->s2_scratch.reserve(m * stride, s, false));
+			const uint32_t* list = d_list + hb.base[b] + w0;
+			const uint32_t threads = 128;
+			const uint32_t grid = (uint32_t)(((uint64_t)m * g + threads - 1) / threads);
+			prof_begin(c, K_ALIGN);
+			switch (g) {
+			case 1: k_align<1><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 2: k_align<2><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 4: k_align<4><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 8: k_align<8><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			default: k_align<32><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			}
+			prof_end(c);
+			CLB_LAUNCH_CHECK(c, "k_align");
+		}
+	}
+	CLB_CUDA(c, cudaStreamSynchronize(s));        // d_list / d_bin_of die with `mem`
+	return CLB_OK;
+}
+
+static clb_status dump_candidates(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_list, const Node* d_nodes, const CandView* d_cviews)
+{
+	const uint32_t nb = (uint32_t)h_list.size();
+	std::vector<Node> nodes(nb); std::vector<CandView> cv((size_t)nb * P.c);
+	if (!nb) return CLB_OK;
+	CLB_CUDA(c, cudaMemcpyAsync(nodes.data(), d_nodes, sizeof(Node) * nb, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaMemcpyAsync(cv.data(), d_cviews, sizeof(CandView) * nb * P.c, cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	std::vector<Anchor> an;
+	for (uint32_t i = 0; i < nb; ++i) {
+		const uint32_t r = h_list[i];
+		std::vector<uint32_t> rec;
+		for (uint32_t k = 0; k < nodes[i].ncand; ++k) {
+			const CandView& v = cv[(size_t)i * P.c + k];
+			an.resize(v.n);
+			if (v.n) CLB_CUDA(c, cudaMemcpy(an.data(), c->s2_arena.p + v.anc, sizeof(Anchor) * v.n, cudaMemcpyDeviceToHost));
+			rec.insert(rec.end(), {v.ref_id, v.rev, v.tot, v.n});
+			for (const Anchor& x : an) rec.insert(rec.end(), {x.len, x.pos_enc, x.pos_ref});
+		}
+		c->dbg_cand[r] = std::move(rec);
+	}
+	return CLB_OK;
+}
+
+// one batch = whole read packs [pack_lo, pack_hi)
+static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& pack_first, uint32_t pack_lo, uint32_t pack_hi, const std::vector<uint32_t>& h_cand_n)
+{
+	cudaStream_t s = c->stream;
+	const uint32_t lo = pack_first[pack_lo], hi = pack_first[pack_hi], nr = hi - lo;
+	if (!nr) return CLB_OK;
+	Scoped mem;
+	const ReadStore R{c->pk.p, c->rd_start.p, c->rd_len.p, c->nmask.p, c->d_ref_to_read};
+	// reads that go through the anchor search
+	std::vector<uint32_t> h_list, h_slot(nr, 0xFFFFFFFFu);
+	for (uint32_t r = lo; r < hi; ++r) if (!c->h_has_n[r] && h_cand_n[r]) { h_slot[r - lo] = (uint32_t)h_list.size(); h_list.push_back(r); }
+	const uint32_t nb = (uint32_t)h_list.size();
+	uint32_t* d_list = nullptr; uint32_t* d_slot = nullptr; uint32_t* d_pack_first = nullptr;
+	SegInfo* d_seg = nullptr; uint32_t* d_slot_dec = nullptr; unsigned long long* d_cursor = nullptr; BinStats* d_bins = nullptr;
+	CLB_CUDA(c, mem.get(&d_list, nb)); CLB_CUDA(c, mem.get(&d_slot, nr)); CLB_CUDA(c, mem.get(&d_pack_first, pack_hi - pack_lo + 1));
+	CLB_CUDA(c, mem.get(&d_seg, (uint64_t)nb * P.c * 2)); CLB_CUDA(c, mem.get(&d_slot_dec, nb)); CLB_CUDA(c, mem.get(&d_cursor, 2)); CLB_CUDA(c, mem.get(&d_bins, 1));
+	CLB_CUDA(c, cudaMemcpyAsync(d_list, h_list.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_slot, h_slot.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data() + pack_lo, sizeof(uint32_t) * (pack_hi - pack_lo + 1), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * (nb ? nb : 1), s));
+
+	DevBuf<Node> nodes; DevBuf<CandView> cviews; DevBuf<Task> tasks; DevBuf<char> esbuf;
+	struct Rel { DevBuf<Node>& a; DevBuf<CandView>& b; DevBuf<Task>& t; DevBuf<char>& e; ~Rel() { a.release(); b.release(); t.release(); e.release(); } } rel{nodes, cviews, tasks, esbuf};
+	uint64_t n_nodes = nb, n_tasks = 0, es_used = 0;
+	CLB_CUDA(c, nodes.reserve(std::max<uint64_t>(nb, 1), s, false));
+	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>((uint64_t)nb * P.c, 1), s, false));
+	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes.p, cviews.p, d_cursor);
+	if (st != CLB_OK) return st;
+	if (c->keep_candidates) { st = dump_candidates(c, P, h_list, nodes.p, cviews.p); if (st != CLB_OK) return st; }
+
+	// ---- level waves ----
+	uint64_t n0 = 0;
+	for (uint32_t level = 0; n0 < n_nodes; ++level) {
+		const uint64_t n1 = n_nodes, nn = n1 - n0;
+		uint32_t* d_cnt = nullptr; uint32_t* d_capu = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_coff = nullptr;
+		Scoped lvl;
+		CLB_CUDA(c, lvl.get(&d_cnt, nn)); CLB_CUDA(c, lvl.get(&d_capu, nn)); CLB_CUDA(c, lvl.get(&d_toff, nn)); CLB_CUDA(c, lvl.get(&d_coff, nn));
+		const uint32_t nblk = (uint32_t)((nn + 127) / 128);
+		CLB_TIMED(c, K_ENCODE, (k_tasks<false><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, d_cnt, d_capu, nullptr, nullptr, 0, 0, nullptr)));
+		CLB_LAUNCH_CHECK(c, "k_tasks<count>");
+		uint64_t nt = 0, ncap = 0;
+		st = exclusive_scan(c, d_cnt, nn, d_toff, &nt); if (st != CLB_OK) return st;
+		st = exclusive_scan(c, d_capu, nn, d_coff, &ncap); if (st != CLB_OK) return st;
+		if (n_tasks + nt >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "more than 2^32 parts in one batch: lower CLB_BATCH_MBASES");
+		CLB_CUDA(c, tasks.reserve(n_tasks + nt, s, true, n_tasks));
+		CLB_CUDA(c, esbuf.reserve(es_used + ncap * 4 + 16, s, true, es_used));
+		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
+		CLB_LAUNCH_CHECK(c, "k_tasks<fill>");
+		st = align_level(c, P, tasks.p, n_tasks, n_tasks + nt, R, nodes.p, cviews.p, esbuf.p, d_bins);
+		if (st != CLB_OK) return st;
+		// decisions; children are appended to the node array
+		const uint64_t cap_nodes = n_nodes + nt;
+		if (cap_nodes >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "too many nodes in one batch");
+		CLB_CUDA(c, nodes.reserve(cap_nodes, s, true, n_nodes));
+		CLB_CUDA(c, cviews.reserve(cap_nodes * P.c, s, true, n_nodes * P.c));
+		unsigned int cur = (unsigned int)n_nodes;
+		CLB_CUDA(c, cudaMemcpyAsync(d_cursor, &cur, sizeof(cur), cudaMemcpyHostToDevice, s));
+		if (nt) {
+			DecideArgs da{tasks.p, n_tasks, n_tasks + nt, nodes.p, cviews.p, reinterpret_cast<unsigned int*>(d_cursor), (uint32_t)cap_nodes, c->s2_arena.p, R, esbuf.p, P};
+			CLB_TIMED(c, K_ENCODE, (k_decide<<<(uint32_t)((nt + 127) / 128), 128, 0, s>>>(da)));
+			CLB_LAUNCH_CHECK(c, "k_decide");
+		}
+		CLB_CUDA(c, cudaMemcpyAsync(&cur, d_cursor, sizeof(cur), cudaMemcpyDeviceToHost, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		n_tasks += nt; es_used += ncap * 4;
+		n0 = n1; n_nodes = std::min<uint64_t>(cur, cap_nodes);
+		if (level > P.max_rec + 1) break;
+	}
+
+	// ---- adaptive estimator, one thread per pack ----
+	const uint32_t np = pack_hi - pack_lo;
+	PackArgs pa{d_pack_first, np, lo, d_slot, c->d_has_n, tasks.p, nodes.p, esbuf.p, R};
+	CLB_TIMED(c, K_ENCODE, (k_estimate<<<(np + 31) / 32, 32, 0, s>>>(pa)));
+	CLB_LAUNCH_CHECK(c, "k_estimate");
+
+	// ---- tuples ----
+	uint32_t* d_size = nullptr; uint32_t* d_kind = nullptr; uint64_t* d_off = nullptr;
+	CLB_CUDA(c, mem.get(&d_size, nr)); CLB_CUDA(c, mem.get(&d_kind, nr)); CLB_CUDA(c, mem.get(&d_off, nr));
+	EmitArgs ea{lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, cviews.p, P.c, c->s2_arena.p, esbuf.p, R, d_size, d_kind, d_off, c->es_total, nullptr, c->es_off};
+	CLB_TIMED(c, K_ENCODE, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	CLB_LAUNCH_CHECK(c, "k_emit<size>");
+	uint64_t total = 0;
+	st = exclusive_scan(c, d_size, nr, d_off, &total); if (st != CLB_OK) return st;
+	CLB_CUDA(c, c->es.reserve(c->es_total + total + 16, s, true, c->es_total));
+	ea.out = c->es.p;
+	CLB_TIMED(c, K_ENCODE, (k_emit<true><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	CLB_LAUNCH_CHECK(c, "k_emit<write>");
+	CLB_TIMED(c, K_ENCODE, (k_emit_plain<<<nr, 256, 0, s>>>(ea)));
+	CLB_LAUNCH_CHECK(c, "k_emit_plain");
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	c->es_total += total;
+	return CLB_OK;
+}
+
+clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	if (!c->graph_done) return fail(c, CLB_ERR_STATE, "clb_encode before clb_graph_build");
+	if (c->enc_done) return fail(c, CLB_ERR_STATE, "clb_encode called twice");
+	if (c->prm.is_hifi) return fail(c, CLB_ERR_STATE, "clb_encode: the HiFi k-mer anchor path (encoder.cpp:870-1012) is not on the device yet");
+	if (prm->anchor_len < 8 || prm->anchor_len > 32) return fail(c, CLB_ERR_BAD_ARG, "anchor_len must be in [8, 32]");
+	if (prm->max_recurence > 7) return fail(c, CLB_ERR_BAD_ARG, "max_recurence above 7 is not supported");
+	cudaStream_t s = c->stream;
+	const uint64_t n = c->n_reads;
+	S2P P{prm->anchor_len, prm->min_part_len_alt, prm->max_recurence, prm->min_anchors, c->prm.max_candidates,
+		prm->min_mmer_frac, prm->min_mmer_force, prm->max_matches_mult, prm->es_cost_mult};
+	// packs
+	std::vector<uint32_t> pack_first{0};
+	if (pack_sizes) {
+		uint64_t at = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) { at += pack_sizes[i]; if (pack_sizes[i]) pack_first.push_back((uint32_t)at); }
+		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
+	} else {
+		uint64_t bytes = 0;
+		for (uint64_t i = 0; i < n; ++i) {           // in_reads.cpp:62-76
+			bytes += (uint64_t)c->h_rd_len[i] + 1;
+			if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); }
+		}
+		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
+	}
+	const uint32_t np = (uint32_t)pack_first.size() - 1;
+	// reference id -> read
+	std::vector<uint32_t> r2r(c->n_ref ? c->n_ref : 1);
+	for (uint64_t i = 0, k = 0; i < n; ++i) if (c->h_is_ref[i]) r2r[k++] = (uint32_t)i;
+	CLB_CUDA(c, dmalloc(&c->d_ref_to_read, r2r.size()));
+	CLB_CUDA(c, cudaMemcpyAsync(c->d_ref_to_read, r2r.data(), sizeof(uint32_t) * r2r.size(), cudaMemcpyHostToDevice, s));
+	std::vector<uint32_t> h_cand_n(n ? n : 1);
+	if (n) CLB_CUDA(c, cudaMemcpyAsync(h_cand_n.data(), c->cand_n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	CLB_CUDA(c, dmalloc(&c->es_off, n + 1));
+	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
+	c->es_total = 0;
+	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
+	static const char* env_batch = std::getenv("CLB_BATCH_MBASES");
+	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 256) << 20;
+	for (uint32_t p = 0; p < np;) {
+		uint32_t q = p + 1;
+		auto bases_of = [&](uint32_t a, uint32_t b) { return c->h_rd_start[b - 1] + c->h_rd_len[b - 1] - c->h_rd_start[a]; };
+		while (q < np && bases_of(pack_first[p], pack_first[q + 1]) <= batch_bases) ++q;
+		clb_status st = encode_batch(c, P, pack_first, p, q, h_cand_n);
+		if (st != CLB_OK) return st;
+		p = q;
+	}
+	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	c->s2_arena.release(); c->s2_scratch.release();
+	c->enc_done = true;
+	return CLB_OK;
+}
+
+void s2_free(clb_ctx* c)
+{
+	c->es.release(); c->s2_arena.release(); c->s2_scratch.release();
+	if (c->es_off) cudaFree(c->es_off);
+	if (c->d_ref_to_read) cudaFree(c->d_ref_to_read);
+	c->es_off = nullptr; c->d_ref_to_read = nullptr;
+}
+
+} // namespace clb

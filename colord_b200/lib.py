@@ -16,6 +16,7 @@ EXPORTS = [
     "clb_filter_list", "clb_filter_import", "clb_filter_check", "clb_graph_build", "clb_graph_accepted_size",
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
+    "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode"]
 
@@ -31,6 +32,11 @@ class KmerStats(C.Structure):
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [("anchor_len", C.c_uint32), ("min_part_len_alt", C.c_uint32), ("max_recurence", C.c_uint32), ("min_anchors", C.c_uint32),
+                ("min_mmer_frac", C.c_double), ("min_mmer_force", C.c_double), ("max_matches_mult", C.c_double), ("es_cost_mult", C.c_double)]
 
 
 class ClbError(RuntimeError):
@@ -76,6 +82,12 @@ def load():
     L.clb_sampler.argtypes = [u32, C.c_double, u32, u32, vp]; L.clb_sampler.restype = None
     L.clb_kernel_launches.argtypes = [vp]; L.clb_kernel_launches.restype = u64
     L.clb_edit_scripts.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, u64]
+    L.clb_encode.argtypes = [vp, C.POINTER(EncodeParams), vp, u32]
+    L.clb_encode_size.argtypes = [vp, C.POINTER(u64)]
+    L.clb_encode_get.argtypes = [vp, vp, vp, u64, i32]
+    L.clb_encode_keep_candidates.argtypes = [vp, i32]
+    L.clb_encode_candidates_size.argtypes = [vp, C.POINTER(u64)]
+    L.clb_encode_candidates.argtypes = [vp, vp, vp, u64]
     L.clb_profile_enable.argtypes = [vp, i32]
     L.clb_profile_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     for name in EXPORTS:
@@ -280,6 +292,49 @@ class Context:
         a = [np.array(x, t) for x, t in ((ref_off, np.uint64), (ref_len, np.uint32), (enc_off, np.uint64), (enc_len, np.uint32), (kinds, np.uint32))]
         self._ck(self.L.clb_edit_scripts(self.h, _np_ptr(seqs), len(seqs), *[_np_ptr(x) for x in a], n, _np_ptr(out_off), _np_ptr(out), cap))
         return [out[int(out_off[i]):int(out_off[i + 1])].tobytes() for i in range(n)]
+
+    def encode(self, p, pack_sizes=None, keep_candidates=False):
+        """Stage 2 over all appended reads.  p: dict with the keys of a golden params.txt (anchor_len, min_part_len_alt, ...)."""
+        prm = p if isinstance(p, EncodeParams) else EncodeParams(
+            p["anchor_len"], p["min_part_len_alt"], p["max_recurence"], p["min_anchors"],
+            float(p["min_mmer_frac"]), float(p["min_mmer_force"]), float(p["max_matches_mult"]), float(p["es_cost_mult"]))
+        if keep_candidates:
+            self._ck(self.L.clb_encode_keep_candidates(self.h, 1))
+        if pack_sizes is None:
+            self._ck(self.L.clb_encode(self.h, C.byref(prm), None, 0))
+        else:
+            ps = np.ascontiguousarray(pack_sizes, np.uint32)
+            self._ck(self.L.clb_encode(self.h, C.byref(prm), _np_ptr(ps), len(ps)))
+
+    def encode_size(self):
+        n = C.c_uint64()
+        self._ck(self.L.clb_encode_size(self.h, C.byref(n)))
+        return n.value
+
+    def encoded(self, n_reads):
+        """-> (es_off[n_reads + 1], CompactES bytes) on the host."""
+        tot = self.encode_size()
+        off = np.zeros(n_reads + 1, np.uint64)
+        es = np.zeros(max(tot, 1), np.uint8)
+        self._ck(self.L.clb_encode_get(self.h, _np_ptr(off), _np_ptr(es), tot, 0))
+        return off, es[:tot]
+
+    def encode_candidates(self, n_reads):
+        """Parity tap -> per read a list of (ref_id, rev, tot, [(len, pos_enc, pos_ref), ...])."""
+        n = C.c_uint64()
+        self._ck(self.L.clb_encode_candidates_size(self.h, C.byref(n)))
+        off = np.zeros(n_reads + 1, np.uint64)
+        data = np.zeros(max(n.value, 1), np.uint32)
+        self._ck(self.L.clb_encode_candidates(self.h, _np_ptr(off), _np_ptr(data), n.value))
+        out = []
+        for i in range(n_reads):
+            rec, p, e = [], int(off[i]), int(off[i + 1])
+            while p < e:
+                ref_id, rev, tot, na = (int(x) for x in data[p:p + 4]); p += 4
+                rec.append((ref_id, rev, tot, [tuple(int(x) for x in data[p + 3 * k:p + 3 * k + 3]) for k in range(na)]))
+                p += 3 * na
+            out.append(rec)
+        return out
 
     def profile_enable(self, on=True):
         self._ck(self.L.clb_profile_enable(self.h, int(on)))

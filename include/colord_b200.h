@@ -116,6 +116,37 @@ clb_status clb_graph_common(clb_ctx* ctx, uint64_t* common_off, uint32_t* common
 clb_status clb_edit_scripts(clb_ctx* ctx, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
 	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);
 
+/* ---- Stage 2: the per-read encoder -------------------------------------------------------------------
+ * Replaces the N CEncoder threads (CEncoder::Encode, encoder.cpp:1672-1691; ctor arguments encoder.h:371-410) over ALL
+ * appended reads: m-mer anchors against the candidates (encoder.cpp:1058-1111), edit scripts of the parts between anchors
+ * (:1255-1283), edit-script / plain / alternative-read decisions (:1315-1346, utils.h:1060-1126) and the CompactES tuple
+ * bytes (:1513-1575, utils.h:69-273).  Field meaning = CCompressorParams (params.h:48). */
+typedef struct {
+	uint32_t anchor_len;            /* -a                                                                   */
+	uint32_t min_part_len_alt;      /* minPartLenToConsiderAltRead                                          */
+	uint32_t max_recurence;         /* maxRecurence                                                         */
+	uint32_t min_anchors;           /* minAnchors                                                           */
+	double min_mmer_frac;           /* minFractionOfMmersInEncode                                           */
+	double min_mmer_force;          /* minFractionOfMmersInEncodeToAlwaysEncode                             */
+	double max_matches_mult;        /* maxMatchesMultiplier                                                 */
+	double es_cost_mult;            /* editScriptCostMultiplier                                             */
+} clb_encode_params;
+/* pack_sizes[n_packs] (HOST): number of reads of every read pack, in input order — CEntropyEstimator is reset at every
+ * pack boundary (encoder.cpp:1677), so the packs are part of the result.  NULL: packs are cut by the reference's rule
+ * (a pack closes when its reads hold >= 4 MiB including one guard byte per read; in_reads.cpp:62-76, defs.h:45).
+ * Requires clb_graph_build.  The result stays on the device (stage 3 consumes it there). */
+clb_status clb_encode(clb_ctx* ctx, const clb_encode_params* params, const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status clb_encode_size(clb_ctx* ctx, uint64_t* total_bytes);
+/* es_t of every read back to back (what CEncoder pushes to compressed_queue, encoder.cpp:1681-1687); es_off has
+ * n_reads + 1 entries.  Buffers are device pointers iff on_device. */
+clb_status clb_encode_get(clb_ctx* ctx, uint64_t* es_off, uint8_t* es, uint64_t cap, int on_device);
+/* Parity tap: the candidates of every read after anchor search (Candidate, encoder.h:46), best first.  Call
+ * clb_encode_keep_candidates(ctx, 1) before clb_encode.  cand_off[n_reads + 1] indexes `data` (uint32 words): per candidate
+ * ref_id, shouldReverse, tot_anchor_len, n_anchors, then n_anchors * (len, pos_enc, pos_ref).  HOST buffers. */
+clb_status clb_encode_keep_candidates(clb_ctx* ctx, int on);
+clb_status clb_encode_candidates_size(clb_ctx* ctx, uint64_t* n_words);
+clb_status clb_encode_candidates(clb_ctx* ctx, uint64_t* cand_off, uint32_t* data, uint64_t cap_words);
+
 /* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
  * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
  * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
@@ -131,7 +162,7 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
 /* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
  * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
- * k_vote, k_common, k_misc.  clb_profile_get synchronizes the stream. */
+ * k_vote, k_common, k_misc, k_align, k_anchors, k_encode.  clb_profile_get synchronizes the stream. */
 clb_status clb_profile_enable(clb_ctx* ctx, int on);
 clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 

@@ -933,3 +933,54 @@ uint64_t orc_encode_reads(const uint8_t* bases, const uint64_t* offsets, uint32_
 	free(ob.p); free(cs); free(cm); free(sym); free(sym_off); free(len); free(has_n); free(ref_to_read);
 	return total;
 }
+
+/* Test tap: the candidates (encoder.h:46) of every read after prepareEncodeCandidates + the overlap fixes, best first.
+ * Per read cand_off[i] .. cand_off[i+1] index `out` (uint32 words): ref_id, shouldReverse, tot_anchor_len, n_anchors, then
+ * n_anchors * (len, pos_enc, pos_ref).  m-mer path only.  Returns the number of words (may exceed cap). */
+uint64_t orc_candidates(const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, const uint8_t* is_ref,
+	const uint32_t* cand, const uint32_t* cand_n, uint32_t max_cand, const orc_s2_params* P,
+	uint64_t* cand_off, uint32_t* out, uint64_t cap)
+{
+	enc_ctx C; C.P = P;
+	uint64_t* sym_off = (uint64_t*)malloc(sizeof(uint64_t) * ((size_t)n_reads + 1));
+	uint32_t* len = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)n_reads + 1));
+	uint8_t* has_n = (uint8_t*)calloc((size_t)n_reads + 1, 1);
+	uint64_t tot = 0;
+	for (uint32_t i = 0; i < n_reads; ++i) { sym_off[i] = tot; len[i] = (uint32_t)(offsets[i + 1] - offsets[i]); tot += len[i] + 1; }
+	uint8_t* sym = (uint8_t*)malloc(tot + 1);
+	for (uint32_t i = 0; i < n_reads; ++i)
+	{
+		for (uint32_t j = 0; j < len[i]; ++j)
+		{
+			uint8_t c = bases[offsets[i] + j], s;
+			switch (c) { case 'A': s = 0; break; case 'C': s = 1; break; case 'G': s = 2; break; case 'T': s = 3; break; default: s = 4; has_n[i] = 1; }
+			sym[sym_off[i] + j] = s;
+		}
+		sym[sym_off[i] + len[i]] = 255;
+	}
+	uint32_t* ref_to_read = (uint32_t*)malloc(sizeof(uint32_t) * ((size_t)n_reads + 1)); uint32_t n_ref = 0;
+	for (uint32_t i = 0; i < n_reads; ++i) if (is_ref[i]) ref_to_read[n_ref++] = i;
+	C.sym = sym; C.sym_off = sym_off; C.len = len; C.ref_to_read = ref_to_read;
+	cand_t* cs = (cand_t*)malloc(sizeof(cand_t) * (max_cand + 1));
+	uint64_t w = 0;
+	for (uint32_t i = 0; i < n_reads; ++i)
+	{
+		cand_off[i] = w;
+		if (has_n[i] || !cand_n[i]) continue;
+		const uint32_t nc = prepare_candidates(&C, sym + sym_off[i], len[i], cand + (uint64_t)i * max_cand, cand_n[i], NULL, NULL, cs);
+		for (uint32_t j = 0; j < nc; ++j)
+		{
+			fix_overlaps(cs[j].a, cs[j].n);
+			if (w + 4 + 3ull * cs[j].n <= cap)
+			{
+				out[w] = cs[j].ref_id; out[w + 1] = (uint32_t)cs[j].rev; out[w + 2] = cs[j].tot; out[w + 3] = cs[j].n;
+				for (uint32_t a = 0; a < cs[j].n; ++a) { out[w + 4 + 3 * a] = cs[j].a[a].len; out[w + 5 + 3 * a] = cs[j].a[a].pos_enc; out[w + 6 + 3 * a] = cs[j].a[a].pos_ref; }
+			}
+			w += 4 + 3ull * cs[j].n;
+			free(cs[j].a);
+		}
+	}
+	cand_off[n_reads] = w;
+	free(cs); free(sym); free(sym_off); free(len); free(has_n); free(ref_to_read);
+	return w;
+}

@@ -143,3 +143,30 @@ def encode_reads(bases, offsets, is_ref, cand, cand_n, pack_sizes, params, commo
                              cand, cand_n, mc, *args, pack_sizes, len(pack_sizes), C.byref(prm), out, cap, es_off)
     assert tot <= cap
     return [out[int(es_off[i]):int(es_off[i + 1])].tobytes() for i in range(n)]
+
+
+def candidates(bases, offsets, is_ref, cand, cand_n, params):
+    """-> per read a list of (ref_id, rev, tot, [(len, pos_enc, pos_ref), ...]) (oracle/stage2.c: orc_candidates)."""
+    L = lib()
+    L.orc_candidates.restype = C.c_uint64
+    L.orc_candidates.argtypes = [_u8p, _u64p, C.c_uint32, _u8p, _u32p, _u32p, C.c_uint32, C.POINTER(S2Params), _u64p, _u32p, C.c_uint64]
+    n = len(offsets) - 1
+    mc = cand.shape[1]
+    cand = np.ascontiguousarray(cand, np.uint32).reshape(-1)
+    cand_n = np.ascontiguousarray(cand_n, np.uint32)
+    prm = params if isinstance(params, S2Params) else s2_params(params)
+    off = np.zeros(n + 1, np.uint64)
+    cap = int(offsets[-1]) * mc + 64
+    data = np.zeros(cap, np.uint32)
+    tot = L.orc_candidates(np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(offsets, np.uint64), n, np.ascontiguousarray(is_ref, np.uint8),
+                           cand, cand_n, mc, C.byref(prm), off, data, cap)
+    assert tot <= cap
+    out = []
+    for i in range(n):
+        rec, p, e = [], int(off[i]), int(off[i + 1])
+        while p < e:
+            ref_id, rev, t, na = (int(x) for x in data[p:p + 4]); p += 4
+            rec.append((ref_id, rev, t, [tuple(int(x) for x in data[p + 3 * k:p + 3 * k + 3]) for k in range(na)]))
+            p += 3 * na
+        out.append(rec)
+    return out

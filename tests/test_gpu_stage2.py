@@ -61,3 +61,45 @@ def test_edit_scripts_random_vs_oracle(seed):
         if got[i] != want:
             bad.append((i, kind, len(ref), len(enc)))
     assert not bad, (len(bad), bad[:10])
+
+
+# ------------------------------------------------------------------------------------------------ the whole encoder
+from conftest import GOLDEN_CASES
+from test_oracle_stage2 import golden_stage2_inputs
+
+MMER_CASES = [c for c in GOLDEN_CASES if c != "hifi"]
+
+
+def _run_stage2(g, keep_candidates=False, packs=True):
+    p = g.params
+    r = g.reads_in
+    ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], is_hifi=bool(p.get("hifi", 0)))
+    ctx.append_reads(r.bases, r.offsets)
+    ctx.count_finalize()
+    sampled = lib.sampler(p["sparse_range"], float(p["sparse_exponent"]), 0, r.n_reads) if p.get("sparse", 0) else np.ones(r.n_reads, np.uint8)
+    ctx.graph_build(sampled)
+    ctx.encode(p, np.array(g.packs, np.uint32) if packs else None, keep_candidates=keep_candidates)
+    return ctx
+
+
+@pytest.mark.parametrize("case", MMER_CASES)
+def test_candidates_match_oracle(golden, case):
+    """E1-E4: anchors of every read against every candidate = the oracle's (which is pinned on the reference's tuples)."""
+    g = golden(case)
+    cand, cand_n, _ = golden_stage2_inputs(g)
+    want = oracle_lib.candidates(g.reads_in.bases, g.reads_in.offsets, g.is_ref, cand, cand_n, g.params)
+    with _run_stage2(g, keep_candidates=True) as ctx:
+        got = ctx.encode_candidates(g.reads_in.n_reads)
+    bad = [i for i in range(len(want)) if got[i] != want[i]]
+    assert not bad, (len(bad), bad[:10], got[bad[0]][:1], want[bad[0]][:1])
+
+
+@pytest.mark.parametrize("case", MMER_CASES)
+def test_compact_es_bytes_golden(golden, case):
+    """E1-E9: the CompactES bytes of every read equal what the unmodified reference's CEncoder produced."""
+    g = golden(case)
+    with _run_stage2(g) as ctx:
+        off, es = ctx.encoded(g.reads_in.n_reads)
+    got = [es[int(off[i]):int(off[i + 1])].tobytes() for i in range(g.reads_in.n_reads)]
+    bad = [i for i in range(len(got)) if got[i] != g.es[i]]
+    assert not bad, (len(bad), bad[:10])
