@@ -513,7 +513,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	CLB_CUDA(c, cudaMemcpyAsync(d_bins, &hb, sizeof(BinStats), cudaMemcpyHostToDevice, s));
 	CLB_TIMED(c, K_ENCODE, (k_task_scatter<<<blocks, 256, 0, s>>>(t0, t1, d_bin_of, d_bins, d_list)));
 	CLB_LAUNCH_CHECK(c, "k_task_scatter");
-	static const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
+	const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
 	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 6ull << 30;
 	for (int b = 0; b < N_BINS; ++b) {
 		if (!hb.cnt[b]) continue;
@@ -698,7 +698,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
 	c->es_total = 0;
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
-	static const char* env_batch = std::getenv("CLB_BATCH_MBASES");
+	const char* env_batch = std::getenv("CLB_BATCH_MBASES");
 	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 256) << 20;
 	for (uint32_t p = 0; p < np;) {
 		uint32_t q = p + 1;

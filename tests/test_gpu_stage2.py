@@ -103,3 +103,92 @@ def test_compact_es_bytes_golden(golden, case):
     got = [es[int(off[i]):int(off[i + 1])].tobytes() for i in range(g.reads_in.n_reads)]
     bad = [i for i in range(len(got)) if got[i] != g.es[i]]
     assert not bad, (len(bad), bad[:10])
+
+
+def _device_vs_oracle(s, k, f, lo, hi, c, P, pack_sizes=None, sampled=None):
+    n = s.n_reads
+    sampled = np.ones(n, np.uint8) if sampled is None else sampled
+    with lib.Context(k, f, lo, hi, c) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        ctx.graph_build(sampled)
+        cand, cn = ctx.graph_candidates()
+        ctx.encode(P, pack_sizes)
+        off, es = ctx.encoded(n)
+    got = [es[int(off[i]):int(off[i + 1])].tobytes() for i in range(n)]
+    has_n = np.array([(s.bases[int(s.offsets[i]):int(s.offsets[i + 1])] == ord("N")).any() for i in range(n)], np.uint8)
+    is_ref = (sampled & (1 - has_n)).astype(np.uint8)
+    if pack_sizes is None:          # the reference's pack rule (in_reads.cpp:62-76)
+        pack_sizes, acc, cnt = [], 0, 0
+        for i in range(n):
+            acc += int(s.offsets[i + 1] - s.offsets[i]) + 1; cnt += 1
+            if acc >= (2 << 21):
+                pack_sizes.append(cnt); acc = 0; cnt = 0
+        if cnt:
+            pack_sizes.append(cnt)
+    want = oracle_lib.encode_reads(s.bases, s.offsets, is_ref, cand, cn, np.array(pack_sizes, np.uint32), P)
+    bad = [i for i in range(n) if got[i] != want[i]]
+    n_es = sum(1 for e in want if (e[0] >> 4) == 10)
+    return bad, n_es
+
+
+P_BAL = dict(anchor_len=16, k=20, modulo=9, hifi=0, min_part_len_alt=48, max_recurence=5, min_anchors=1,
+             min_mmer_frac=0.5, min_mmer_force=0.9, max_matches_mult=10.0, es_cost_mult=1.0)
+
+
+def test_encode_ont_many_packs_and_batches(monkeypatch):
+    """1500 ONT-like reads at 24x: alternative-read recursion, reads with N, several packs, several device batches."""
+    from colord_b200 import synth
+    monkeypatch.setenv("CLB_BATCH_MBASES", "2")
+    monkeypatch.setenv("CLB_ALIGN_SCRATCH_MB", "64")
+    s = synth.generate(1500, 250000, 4000, seed=5, profile="ont", n_frac=0.02)
+    packs = [100, 1, 399, 500, 250, 250]
+    bad, n_es = _device_vs_oracle(s, 20, 9, 3, 100, 8, P_BAL, packs)
+    assert n_es > 1300
+    assert not bad, (len(bad), bad[:10])
+
+
+def test_encode_long_reads():
+    """60 kb reads: the m-mer table and Bloom filter leave shared memory, flanks reach edlib's Hirschberg sizes."""
+    from colord_b200 import synth
+    s = synth.generate(100, 500000, 60000, seed=6, profile="ont")
+    bad, n_es = _device_vs_oracle(s, 20, 9, 2, 100, 8, P_BAL)
+    assert n_es > 90
+    assert not bad, (len(bad), bad[:10])
+
+
+def test_encode_accurate_reads_big_segments():
+    """0.2 % error: thousands of m-mer pairs per candidate (global-memory sort), long anchors, few edit operations."""
+    from colord_b200 import synth
+    s = synth.generate(300, 100000, 6000, seed=7, profile="hifi")
+    bad, n_es = _device_vs_oracle(s, 20, 9, 2, 100, 8, P_BAL)
+    assert n_es > 280
+    assert not bad, (len(bad), bad[:10])
+
+
+def test_encode_repeats():
+    """Tandem repeats, a microsatellite and a homopolymer: duplicate m-mers on both sides, the match-count cap, overlap fixes."""
+    from colord_b200 import synth
+    rng = np.random.default_rng(11)
+    unit = rng.integers(0, 4, 1500, dtype=np.uint8)
+    parts = [rng.integers(0, 4, 20000, dtype=np.uint8), unit, unit, unit, rng.integers(0, 4, 8000, dtype=np.uint8),
+             np.tile(np.array([0, 1, 2, 3, 3], np.uint8), 300), rng.integers(0, 4, 6000, dtype=np.uint8), np.zeros(400, np.uint8),
+             rng.integers(0, 4, 15000, dtype=np.uint8), unit, rng.integers(0, 4, 5000, dtype=np.uint8)]
+    genome = np.concatenate(parts)
+    seqs, offs = [], [0]
+    for i in range(500):
+        ln = int(np.clip(rng.gamma(2.0, 2500), 300, 20000))
+        st = int(rng.integers(0, len(genome) - 300))
+        frag = genome[st:st + ln].copy()
+        if rng.random() < 0.5:
+            frag = 3 - frag[::-1]
+        r = rng.random(len(frag))
+        sub = r < 0.02
+        frag[sub] = (frag[sub] + rng.integers(1, 4, int(sub.sum()), dtype=np.uint8)) & 3
+        frag = frag[~((r >= 0.02) & (r < 0.04))]
+        seqs.append(np.frombuffer(b"ACGT", np.uint8)[frag]); offs.append(offs[-1] + len(frag))
+    s = synth.SynthReads(np.concatenate(seqs), None, np.array(offs, np.uint64), None)
+    P = dict(P_BAL, anchor_len=14)
+    bad, n_es = _device_vs_oracle(s, 18, 5, 2, 200, 10, P)
+    assert n_es > 400
+    assert not bad, (len(bad), bad[:10])
