@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py — input MB/s of the device hot path on the north-star workload (BASELINE.json).
 
-One "step" = one pass of the hot path built so far — STAGE 1 (2-bit ingest, canonical k-mer scan +
-murmur64 % f filter + count table, thresholding into the filtered set, accepted k-mers per read,
-similarity graph with top-c candidates) — over the whole synthetic ONT workload.  Stages 2 and 3 are not
-on the device yet; `config.stages` says so and the reference arm times the SAME stage of the reference.
+One "step" = one pass of the hot path built so far over the whole synthetic ONT workload — STAGE 1 (2-bit ingest,
+canonical k-mer scan + murmur64 % f filter + count table, thresholding into the filtered set, accepted k-mers per
+read, similarity graph with top-c candidates) and STAGE 2 (m-mer anchors against the candidates, edit scripts of the
+parts between anchors, edit-script / plain / alternative-read decisions, CompactES tuples).  Stage 3 (entropy coders) is
+not on the device yet; `config.stages` says so and the reference arm times the SAME stages of the reference
+(`--stages 1` restricts both arms to stage 1).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--gbases G] [--impl reference]
 
@@ -29,6 +31,9 @@ sys.path.insert(0, ROOT)
 # north-star workload (SURVEY.md §8d "NS"): compress-ont default on a 50 GB ONT FASTQ, mean read 8 kb
 NS = dict(k=24, modulo=12, min_count=4, max_count=80, max_candidates=5, sparse_g=1.0, sparse_exponent=1.0,
           mean_len=8000, genome_len=1_200_000_000, err=(0.04, 0.03, 0.03))
+# stage 2 at the same preset (arg_parse.cpp:154 "memory": level 1) and the anchor length compression.cpp:57-94 picks for 25 Gbases
+NS_S2 = dict(anchor_len=22, min_part_len_alt=64, max_recurence=3, min_anchors=1, min_mmer_frac=0.5, min_mmer_force=0.9,
+             max_matches_mult=10.0, es_cost_mult=1.0)
 HEADER_BYTES = 46 + 6          # "@read_<i> ch=<n> start_time=<ISO>\n" + "\n+\n" + two line ends
 
 
@@ -147,11 +152,12 @@ def reference_sample_fastq(path, n_reads=12500, genome_len=5_000_000):
     return s, os.path.getsize(path)
 
 
-def run_reference_stage1(fastq, threads):
+def run_reference_stage1(fastq, threads, stages="12"):
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")
     with tempfile.TemporaryDirectory() as tmp:
-        out = subprocess.run([exe, "compress-ont", "-k", str(NS["k"]), "-a", "22", "-t", str(threads), fastq, os.path.join(tmp, "x.out")],
-                             cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=1800)
+        out = subprocess.run([exe, "compress-ont", "-k", str(NS["k"]), "-a", str(NS_S2["anchor_len"]), "-t", str(threads), fastq, os.path.join(tmp, "x.out")],
+                             cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=1800,
+                             env=dict(os.environ, COLORD_TIME_STAGES=stages))
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     return json.loads(line)
 
@@ -170,16 +176,17 @@ def run_port_stage1(s):
     return time.time() - t0
 
 
-def cpu_baseline(sample_reads=12500):
+def cpu_baseline(sample_reads=12500, stages="12"):
     cores = os.cpu_count() or 1
     with tempfile.TemporaryDirectory() as tmp:
         fq = os.path.join(tmp, "sample.fastq")
         s, nbytes = reference_sample_fastq(fq, sample_reads)
         desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
-            r = run_reference_stage1(fq, cores)
+            r = run_reference_stage1(fq, cores, stages)
+            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + ("+CEncoder threads (stages 1+2)" if stages == "12" else " (stage 1 only)")
             return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
-                    "sample": desc + "; reference CKmerCounter+CKmerFilter+CReadsSimilarityGraph (stage 1 only)", "detail": r}
+                    "sample": desc + "; unmodified reference " + what, "detail": r}
         dt = run_port_stage1(s)
         return {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port", "sample": desc + "; oracle/stage1.c scalar port"}
 
@@ -196,14 +203,14 @@ def main_reference(args):
         times = []
         kind = "reference" if os.path.exists(exe) else "port"
         for i in range(args.warmup + args.steps):
-            dt = run_reference_stage1(fq, cores)["stage1_s"] if kind == "reference" else run_port_stage1(s)
+            dt = run_reference_stage1(fq, cores, args.stages)["stage1_s"] if kind == "reference" else run_port_stage1(s)
             if i >= args.warmup:
                 times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     v = nbytes / (ms / 1e3) / 1e6
     sample = f"{s.n_reads} synthetic ONT reads / {s.n_bases} bases / {nbytes} FASTQ bytes per step (bounded sample of the workload)"
     print(json.dumps({
-        "impl": "reference", "metric": "input MB/s, compress-ont default, stage 1 (k-mer filter + similarity graph)", "value": v, "unit": "MB/s",
+        "impl": "reference", "metric": metric_name(args), "value": v, "unit": "MB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, None),
@@ -212,10 +219,16 @@ def main_reference(args):
     }))
 
 
+def metric_name(args):
+    return "input MB/s, compress-ont default, " + ("stages 1+2 (k-mer filter, similarity graph, anchors + edit scripts -> tuples)" if args.stages == "12"
+                                                   else "stage 1 (k-mer filter + similarity graph)")
+
+
 def workload_config(args, n_reads):
     return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
-                        f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] / 1e9:g} Gb, 10% errors)",
-            "stages": "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph); stages 2-3 not on device yet",
+                        f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] * args.gbases / 25.0 / 1e9:.3g} Gb = 20.8x, 10% errors)",
+            "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1); stage 3 not on device yet" % NS_S2["anchor_len"])
+                      if args.stages == "12" else "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph)",
             "n_reads": n_reads, "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"reads sharded by id over {args.gpus} GPU(s)"}
 
 
@@ -226,6 +239,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
+    ap.add_argument("--stages", default="12", choices=["1", "12"], help="hot-path stages inside a step (both arms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -252,7 +266,9 @@ def main():
     p = NS
     n_reads_total = int(args.gbases * 1e9 / p["mean_len"])
     lo, hi = rank * n_reads_total // world, (rank + 1) * n_reads_total // world
-    genome = make_genome(torch, device, p["genome_len"], seed=1234)
+    # reduced runs (--gbases < 25) keep the north star's 20.8x coverage by shrinking the genome with the workload
+    genome_len = max(100_000, int(p["genome_len"] * args.gbases / 25.0))
+    genome = make_genome(torch, device, genome_len, seed=1234)
     bases, offsets = gen_reads(torch, device, genome, lo, hi, seed=99)
     del genome
     torch.cuda.empty_cache()
@@ -283,7 +299,12 @@ def main():
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
         ctx.graph_build(sampled)
         out = None
-        if readback:
+        if args.stages == "12":
+            ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
+                                                           "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
+            if readback:           # the tuples are what leaves stage 2 (they feed the entropy coders)
+                out = ctx.encoded(n_local)
+        elif readback:
             out = ctx.graph_candidates()
         ctx.synchronize()
         return ctx, stats, out
@@ -353,7 +374,7 @@ def main():
                     "algorithmic_bytes_per_base": alg_per_base,
                     "kernel_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}}
         line = {
-            "metric": "input MB/s, compress-ont default, stage 1 (k-mer filter + similarity graph)", "value": value, "unit": "MB/s",
+            "metric": metric_name(args), "value": value, "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic (generated on device, BASELINE.md §2 error model)",
             "config": workload_config(args, n_reads_all), "job_fastq_bytes": job_bytes, "stats": stats,
@@ -361,7 +382,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline()
+                line["cpu_baseline"] = cpu_baseline(stages=args.stages)
             except Exception as ex:      # keep the GPU numbers even if the host baseline cannot run
                 line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
         print(json.dumps(line))

@@ -14,9 +14,12 @@
 // Parallel scheme: a task is owned by a group of GROUP lanes (1, 2, 4, 8 or 32).  Rows are cut into 64-row blocks; lane g of
 // the group owns block strip*GROUP + g and the group sweeps the columns as an anti-diagonal wavefront (lane g is g columns
 // behind lane g-1, the horizontal delta travels by shuffle).  Tasks with more blocks than lanes are strip-mined: the
-// horizontal deltas leaving a strip's last block are kept per column (1 byte) and feed the next strip.  Column state
-// (Pv, Mv, score of the block's last row) is stored per (column, block) for the traceback, which one lane walks with
-// popcounts.
+// horizontal deltas leaving a strip's last block are kept per column (1 byte) and feed the next strip.  For the traceback
+// only two bit-vectors per (block, column) are stored: Pv (vertical +1 deltas after the column) and Ph (horizontal +1 deltas
+// of the column).  edlib's preference "up if D(i-1,j)+1 == D(i,j), else left if D(i,j-1)+1 == D(i,j), else diagonal" is then
+// two bit tests per step (a diagonal step is a match iff the two symbols are equal), and the walk keeps a window of GROUP
+// columns of the current block in registers (one column per lane, fetched by shuffle) so that a step costs no memory round
+// trip.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,6 +29,13 @@ namespace clb {
 struct SeqView {            // element i = base[i * step]; step = -1 gives a reversed view
 	const uint8_t* base; int step;
 	__device__ __forceinline__ uint8_t operator[](int i) const { return base[(long long)i * step]; }
+	// symbols i .. i+n-1 (n <= 32), symbol k in bits 2k, 2k+1
+	__device__ __forceinline__ uint64_t get32(int i, int n) const
+	{
+		uint64_t x = 0;
+		for (int k = 0; k < n; ++k) x |= (uint64_t)(base[(long long)(i + k) * step] & 3) << (2 * k);
+		return x;
+	}
 	__device__ __forceinline__ SeqView sub(int off) const { return SeqView{base + (long long)off * step, step}; }
 	__device__ __forceinline__ SeqView reversed(int n) const { return SeqView{base + (long long)(n - 1) * step, -step}; }
 };
@@ -40,6 +50,20 @@ struct PackedView {
 		const long long a = origin + (long long)i * step;
 		if (a < lo || a >= hi) return 255;
 		return (uint8_t)(((uint32_t)(pk[a >> 5] >> (62 - 2 * (a & 31))) & 3u) ^ comp);
+	}
+	// symbols i .. i+n-1 (n <= 32, all inside the read), symbol k in bits 2k, 2k+1; bits above 2n are unspecified
+	__device__ __forceinline__ uint64_t get32(int i, int n) const
+	{
+		const long long a0 = origin + (long long)i * step, a1 = a0 + (long long)(n - 1) * step;
+		const long long lo = step > 0 ? a0 : a1, hi = step > 0 ? a1 : a0;
+		const uint64_t w0 = pk[lo >> 5], w1 = pk[hi >> 5];
+		const uint32_t sh = 2 * (uint32_t)(lo & 31);
+		uint64_t x = sh ? ((w0 << sh) | (w1 >> (64 - sh))) : w0;        // address lo + k in bits 63-2k, 62-2k
+		if (step > 0) {                                                  // element k = address lo + k: reverse the order of the 2-bit fields
+			x = __brevll(x);
+			x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+		} else x >>= (64 - 2 * n);                                       // element k = address hi - k
+		return comp ? ~x : x;
 	}
 	__device__ __forceinline__ PackedView sub(int off) const { PackedView v = *this; v.origin += (long long)off * step; return v; }
 	__device__ __forceinline__ PackedView reversed(int n) const { PackedView v = *this; v.origin += (long long)(n - 1) * step; v.step = -step; return v; }
@@ -59,7 +83,7 @@ __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long l
 	const bool big = edlib_column_bytes(q, t) >= EDLIB_TRACEBACK_LIMIT;
 	unsigned long long o = 0;
 	auto take = [&](unsigned long long bytes) { unsigned long long at = o; o += (bytes + 15) & ~15ULL; return at; };
-	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 : (unsigned long long)(20 * B * (t > 0 ? t : 1)));
+	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 : (unsigned long long)(16 * B * (t > 0 ? t : 1)));
 	s.carry = take((unsigned long long)t + 1);
 	s.lastrow = take(4ull * (t + 1));
 	s.ops = take((unsigned long long)(q + t + 2));
@@ -73,7 +97,7 @@ __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long l
 }
 
 // edlib.cpp:407-441 (calculateBlock); returns hout, hb = bit whose horizontal delta is returned as *sdelta
-__device__ __forceinline__ int myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint32_t score_bit, int* sdelta)
+__device__ __forceinline__ int myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint32_t score_bit, int* sdelta, uint64_t* ph_out)
 {
 	const uint64_t hin_neg = (uint64_t)((uint32_t)(hin >> 2) & 1u);
 	const uint64_t Xv = Eq | Mv;
@@ -83,12 +107,25 @@ __device__ __forceinline__ int myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t 
 	uint64_t Mh = Pv & Xh;
 	const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
 	*sdelta = (int)((Ph >> score_bit) & 1) - (int)((Mh >> score_bit) & 1);
+	*ph_out = Ph;
 	Ph <<= 1; Mh <<= 1;
 	Mh |= hin_neg;
 	Ph |= (uint64_t)((hin + 1) >> 1);
 	Pv = Mh | ~(Xv | Ph);
 	Mv = Ph & Xv;
 	return hout;
+}
+
+// bits 0, 2, 4, .. 62 of x -> bits 0 .. 31
+__device__ __forceinline__ uint64_t compress_even(uint64_t x)
+{
+	x &= 0x5555555555555555ULL;
+	x = (x | (x >> 1)) & 0x3333333333333333ULL;
+	x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL;
+	x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+	x = (x | (x >> 8)) & 0x0000ffff0000ffffULL;
+	x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+	return x;
 }
 
 template <int GROUP>
@@ -100,10 +137,11 @@ struct Aligner {
 
 	__device__ __forceinline__ void gsync() const { if (GROUP > 1) __syncwarp(gmask); }
 
-	// Forward sweep of rows[0..Q) x cols[0..T).  hist_* may be null.  lastrow (int32[T]) receives D(Q-1, c) if non-null.
+	// Forward sweep of rows[0..Q) x cols[0..T).  hist_pv / hist_ph (may be null) receive Pv / Ph of block b, column c at
+	// [b * hist_stride + c].  lastrow (int32[T]) receives D(Q-1, c) if non-null.
 	// fin_* (per block) receive the final column if non-null.  Returns D(Q-1, T-1) to every lane.
 	template <class V>
-	__device__ int sweep(V rows, int Q, V cols, int T, uint64_t* hist_pv, uint64_t* hist_mv, int32_t* hist_sc,
+	__device__ int sweep(V rows, int Q, V cols, int T, uint64_t* hist_pv, uint64_t* hist_ph, int hist_stride,
 		int32_t* lastrow, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
 	{
 		const int B = (Q + 63) >> 6;
@@ -115,29 +153,40 @@ struct Aligner {
 			const bool last_blk = b == B - 1;
 			const uint32_t sbit = last_blk ? (uint32_t)((Q - 1) & 63) : 63u;
 			uint64_t peq0 = 0, peq1 = 0, peq2 = 0, peq3 = 0;
-			if (act) {
-				const int r0 = b << 6, r1 = min(Q, r0 + 64);
-				for (int r = r0; r < r1; ++r) {
-					const uint8_t c = rows[r]; const uint64_t bit = 1ULL << (r - r0);
-					peq0 |= c == 0 ? bit : 0; peq1 |= c == 1 ? bit : 0; peq2 |= c == 2 ? bit : 0; peq3 |= c == 3 ? bit : 0;
+			if (act) {      // match vectors of the block's 64 rows from two packed words
+				const int r0 = b << 6, nr = min(Q - r0, 64);
+#pragma unroll
+				for (int h = 0; h < 2; ++h) {
+					const int n = min(nr - 32 * h, 32);
+					if (n <= 0) break;
+					const uint64_t w = rows.get32(r0 + 32 * h, n);
+					const uint64_t valid = n == 32 ? 0xffffffffULL : ((1ULL << n) - 1);
+					const uint64_t e = compress_even(w), o = compress_even(w >> 1);
+					peq0 |= (~e & ~o & valid) << (32 * h); peq1 |= (e & ~o & valid) << (32 * h);
+					peq2 |= (~e & o & valid) << (32 * h); peq3 |= (e & o & valid) << (32 * h);
 				}
 			}
 			uint64_t Pv = ~0ULL, Mv = 0;
 			int score = act ? min(Q, (b << 6) + 64) : 0;        // D(last row of block, column -1) = row index + 1
 			int hout = 0;
+			uint64_t colw = 0;                                  // 32 column symbols, refreshed every 32 columns of this lane
+			int cw = 0;                                         // GROUP carries of the previous strip, one per lane
 			const int n_steps = T + GROUP - 1;
 			for (int s = 0; s < n_steps; ++s) {
+				if (GROUP > 1 && strip > 0 && (s & (GROUP - 1)) == 0) { const int idx = s + (int)gl; cw = idx < T ? (int)carry[idx] : 0; }
 				int hin = GROUP > 1 ? __shfl_up_sync(gmask, hout, 1, GROUP) : 0;
+				const int cin = (GROUP > 1 && strip > 0) ? __shfl_sync(gmask, cw, s & (GROUP - 1), GROUP) : 0;
 				const int c = s - (int)gl;
 				if (act && c >= 0 && c < T) {
-					if (gl == 0) hin = strip == 0 ? 1 : (int)carry[c];
-					const uint8_t tc = cols[c];
-					const uint64_t Eq = tc == 0 ? peq0 : tc == 1 ? peq1 : tc == 2 ? peq2 : tc == 3 ? peq3 : 0ULL;
-					int sd;
-					hout = myers_block(Pv, Mv, Eq, hin, sbit, &sd);
+					if (gl == 0) hin = strip == 0 ? 1 : (GROUP > 1 ? cin : (int)carry[c]);
+					if ((c & 31) == 0) colw = cols.get32(c, min(32, T - c));
+					const uint32_t tc = (uint32_t)(colw >> (2 * (c & 31))) & 3u;
+					const uint64_t Eq = tc == 0 ? peq0 : tc == 1 ? peq1 : tc == 2 ? peq2 : peq3;
+					int sd; uint64_t Ph;
+					hout = myers_block(Pv, Mv, Eq, hin, sbit, &sd, &Ph);
 					score += sd;
 					if (gl == GROUP - 1 && !last_blk) carry[c] = (int8_t)hout;
-					if (hist_pv) { const size_t h = (size_t)c * B + b; hist_pv[h] = Pv; hist_mv[h] = Mv; hist_sc[h] = score; }
+					if (hist_pv) { const size_t h = (size_t)b * hist_stride + c; hist_pv[h] = Pv; hist_ph[h] = Ph; }
 					if (last_blk && lastrow) lastrow[c] = score;
 				}
 			}
@@ -153,35 +202,53 @@ struct Aligner {
 		return final_score;
 	}
 
-	// ---- traceback on stored columns (lane 0 of the group) ----
-	struct Hist { const uint64_t* pv; const uint64_t* mv; const int32_t* sc; int B, Q; };
-	__device__ __forceinline__ static int cell(const Hist& h, int i, int j)       // D at row i, column j (0-based, both >= 0)
-	{
-		const int b = i >> 6, bit = i & 63;
-		const int bot = (b == h.B - 1) ? ((h.Q - 1) & 63) : 63;
-		const size_t x = (size_t)j * h.B + b;
-		// rows bit+1 .. bot
-		uint64_t m = (bot == 63 ? ~0ULL : ((1ULL << (bot + 1)) - 1)) & ~((bit == 63) ? ~0ULL : ((1ULL << (bit + 1)) - 1));
-		return h.sc[x] - (__popcll(h.pv[x] & m) - __popcll(h.mv[x] & m));
-	}
-	__device__ __forceinline__ static int vertex(const Hist& h, int I, int J) { return I == 0 ? J : (J == 0 ? I : cell(h, I - 1, J - 1)); }
-
-	// writes the ops of rows[0..Q) x cols[0..T) in forward order to out; returns their number.  tmp: Q+T bytes.
-	__device__ static int traceback(const Hist& h, int Q, int T, uint8_t* out, uint8_t* tmp)
+	// ---- traceback on stored columns: edlib.cpp:945-1159 ----
+	// Walks from vertex (Q, T) back to (0, 0); every lane of the group runs the same walk, lane l holds column (window top - l)
+	// of the current block.  ops: 1 = up (row symbol only), 2 = left (column symbol only), 0 = diagonal.  Written in forward
+	// order to out; returns their number.  tmp: Q + T bytes.
+	__device__ int traceback(const uint64_t* hpv, const uint64_t* hph, int stride, int Q, int T, uint8_t* out, uint8_t* tmp) const
 	{
 		int I = Q, J = T, n = 0;
-		int cur = vertex(h, I, J);
-		while (I > 0 || J > 0) {
-			if (I == 0) { tmp[n++] = 2; --J; continue; }
-			if (J == 0) { tmp[n++] = 1; --I; continue; }
-			const int up = vertex(h, I - 1, J);
-			if (up + 1 == cur) { tmp[n++] = 1; --I; cur = up; continue; }
-			const int left = vertex(h, I, J - 1);
-			if (left + 1 == cur) { tmp[n++] = 2; --J; cur = left; continue; }
-			const int diag = vertex(h, I - 1, J - 1);
-			tmp[n++] = diag == cur ? 0 : 3; --I; --J; cur = diag;
+		int wb = -1, wj = -0x40000000;
+		uint64_t wpv = 0, wph = 0;
+		const uint32_t gbase = (threadIdx.x & 31) & ~(uint32_t)(GROUP - 1);       // first lane of the group inside the warp
+		const uint32_t gall = GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u);
+		while (I > 0 && J > 0) {
+			const int i = I - 1, j = J - 1, b = i >> 6, bit = i & 63;
+			if (b != wb || j > wj || j < wj - (GROUP - 1)) {
+				wb = b; wj = j;
+				const int col = wj - (int)gl;
+				if (col >= 0) { const size_t h = (size_t)b * stride + col; wpv = hpv[h]; wph = hph[h]; }
+			}
+			const int src = wj - j;                       // lane holding column j
+			const int k = (int)gl - src;                  // this lane holds column j - k
+			const uint64_t pvj = GROUP > 1 ? __shfl_sync(gmask, wpv, src, GROUP) : wpv;
+			int run; uint8_t op;
+			if ((pvj >> bit) & 1) {
+				// up: as long as the vertical delta stays +1 inside this block and column
+				run = min(__clzll((long long)~(pvj << (63 - bit))), bit + 1);
+				op = 1; I -= run;
+			} else {
+				const bool in = k >= 0 && j - k >= 0;
+				const bool left_k = in && !((wpv >> bit) & 1) && ((wph >> bit) & 1);
+				const uint32_t bl = ((__ballot_sync(gmask, left_k) >> gbase) & gall) >> src;
+				if (bl & 1) { run = ~bl ? __ffs((int)~bl) - 1 : 32; op = 2; J -= run; }     // left along row i
+				else {
+					const bool diag_k = in && bit - k >= 0 && !((wpv >> (bit - k)) & 1) && !((wph >> (bit - k)) & 1);
+					const uint32_t bd = ((__ballot_sync(gmask, diag_k) >> gbase) & gall) >> src;
+					run = ~bd ? __ffs((int)~bd) - 1 : 32; op = 0; I -= run; J -= run;      // run >= 1: the cell itself is neither up nor left
+				}
+			}
+			for (int x = (int)gl; x < run; x += GROUP) tmp[n + x] = op;
+			n += run;
 		}
-		for (int x = 0; x < n; ++x) out[x] = tmp[n - 1 - x];
+		// a border was reached: the rest is all up or all left
+		const int rest = I + J; const uint8_t rop = I > 0 ? 1 : 2;
+		for (int x = (int)gl; x < rest; x += GROUP) tmp[n + x] = rop;
+		n += rest;
+		gsync();
+		for (int x = (int)gl; x < n; x += GROUP) out[x] = tmp[n - 1 - x];
+		gsync();
 		return n;
 	}
 
@@ -227,16 +294,25 @@ struct Aligner {
 			gsync();
 			const V r = rows.sub(qo), c = cols.sub(to);
 			if (ql == 0 || tl == 0 || edlib_column_bytes(ql, tl) < EDLIB_TRACEBACK_LIMIT) {
+#ifdef CLB_ALIGN_TIMING
+				long long tl0 = clock64();
+#endif
 				n_ops += leaf(r, ql, c, tl, ops_out + n_ops, tmp);
+#ifdef CLB_ALIGN_TIMING
+				if (gl == 0 && Q > 30000) printf("[leaf] ql %d tl %d: %lld cycles\n", ql, tl, clock64() - tl0);
+#endif
 				continue;
 			}
+#ifdef CLB_ALIGN_TIMING
+			long long th0 = clock64();
+#endif
 			const int Bq = (ql + 63) >> 6;
 			uint64_t* fpv = fin_pv; uint64_t* fmv = fin_pv + Bq; int32_t* fsc = reinterpret_cast<int32_t*>(fin_pv + 2 * Bq);
 			const int lw = tl / 2, rw = tl - lw;
-			sweep(r, ql, c, lw, nullptr, nullptr, nullptr, nullptr, fpv, fmv, fsc);
+			sweep(r, ql, c, lw, nullptr, nullptr, 0, nullptr, fpv, fmv, fsc);
 			gsync();
 			decode_final(fpv, fmv, fsc, ql, lw, F);
-			sweep(r.reversed(ql), ql, c.sub(lw).reversed(rw), rw, nullptr, nullptr, nullptr, nullptr, fpv, fmv, fsc);
+			sweep(r.reversed(ql), ql, c.sub(lw).reversed(rw), rw, nullptr, nullptr, 0, nullptr, fpv, fmv, fsc);
 			gsync();
 			decode_final(fpv, fmv, fsc, ql, rw, R);           // R[z] = dist(last z rows, right half)
 			// topmost y in 1..ql-1 with F[y] + R[ql-y] == bs, then y = 0, then y = ql   (edlib.cpp:1305-1338)
@@ -245,6 +321,9 @@ struct Aligner {
 			if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) y = min(y, __shfl_xor_sync(gmask, y, d, GROUP));
 			if (y == 0x7fffffff) { if ((int)(lw + R[ql]) == bs) y = 0; else y = ql; }
 			const int ls = y == 0 ? lw : (int)F[y], rs = y == ql ? rw : (int)R[ql - y];
+#ifdef CLB_ALIGN_TIMING
+			if (gl == 0 && Q > 30000) printf("[hirsch] ql %d tl %d y %d: %lld cycles\n", ql, tl, y, clock64() - th0);
+#endif
 			gsync();
 			if (gl == 0) {
 				int32_t* e = stack + sp * 5;          // right part first so that the left part is processed first
@@ -269,13 +348,10 @@ struct Aligner {
 		}
 		const int B = (Q + 63) >> 6;
 		uint64_t* hpv = reinterpret_cast<uint64_t*>(scratch + lay.hist);
-		uint64_t* hmv = hpv + (size_t)B * T;
-		int32_t* hsc = reinterpret_cast<int32_t*>(hmv + (size_t)B * T);
-		sweep(rows, Q, cols, T, hpv, hmv, hsc, nullptr, nullptr, nullptr, nullptr);
+		uint64_t* hph = hpv + (size_t)B * T;
+		sweep(rows, Q, cols, T, hpv, hph, T, nullptr, nullptr, nullptr, nullptr);
 		gsync();
-		if (gl == 0) { Hist h{hpv, hmv, hsc, B, Q}; n = traceback(h, Q, T, out, tmp); }
-		if (GROUP > 1) n = __shfl_sync(gmask, n, 0, GROUP);
-		gsync();
+		n = traceback(hpv, hph, T, Q, T, out, tmp);
 		return n;
 	}
 };
@@ -302,11 +378,12 @@ __device__ inline void fix_in_range(char* es, uint32_t start, uint32_t end)   //
 	}
 }
 // edit_script.h:591-671; ref/enc may be indexed one past the part (the byte that follows it in the read)
+// The two passes on es[lo..hi) with the reference / read positions of symbol lo given.
 template <class V>
-__device__ inline void refactor_edit_script(V ref, V enc, char* es, uint32_t n)
+__device__ inline void refactor_range(V ref, V enc, char* es, uint32_t lo, uint32_t hi, uint32_t ref_at, uint32_t enc_at)
 {
-	uint32_t ref_start = 0, ref_pos = 0, es_start = 0;
-	for (uint32_t p = 0; p < n; ++p) {
+	uint32_t ref_start = ref_at, ref_pos = ref_at, es_start = lo;
+	for (uint32_t p = lo; p < hi; ++p) {
 		const char s = es[p]; const bool mm = es_is_mm(s), ins = es_is_ins(s);
 		if (ins || mm || ref[ref_start] != ref[ref_pos]) {
 			fix_in_range(es, es_start, p);
@@ -315,9 +392,9 @@ __device__ inline void refactor_edit_script(V ref, V enc, char* es, uint32_t n)
 		}
 		if (!ins) ++ref_pos;
 	}
-	fix_in_range(es, es_start, n);
-	uint32_t enc_start = 0, enc_pos = 0; es_start = 0;
-	for (uint32_t p = 0; p < n; ++p) {
+	fix_in_range(es, es_start, hi);
+	uint32_t enc_start = enc_at, enc_pos = enc_at; es_start = lo;
+	for (uint32_t p = lo; p < hi; ++p) {
 		const char s = es[p]; const bool mm = es_is_mm(s), del = s == 'D';
 		if (del || mm || enc[enc_start] != enc[enc_pos]) {
 			fix_in_range(es, es_start, p);
@@ -326,7 +403,75 @@ __device__ inline void refactor_edit_script(V ref, V enc, char* es, uint32_t n)
 		}
 		if (!del) ++enc_pos;
 	}
-	fix_in_range(es, es_start, n);
+	fix_in_range(es, es_start, hi);
+}
+// edit_script.h:591-671; ref/enc may be indexed one past the part (the byte that follows it in the read)
+template <class V>
+__device__ inline void refactor_edit_script(V ref, V enc, char* es, uint32_t n) { refactor_range(ref, enc, es, 0, n, 0, 0); }
+
+// ops -> script symbols -> canonical form, by all lanes of the group.
+// ops[0..n) in script order: 0 = diagonal, 1 = row symbol only, 2 = column symbol only; rows are the reference iff rows_ref.
+// The canonicalisation is two passes that only reorder symbols inside ranges: pass 1 over M / D symbols on one repeated
+// reference base (insertions and substitutions end a range), pass 2 over M / insertion symbols on one repeated read base
+// (deletions and substitutions end a range).  At some positions both passes start a new range whatever came before — next to
+// a substitution; between two reference-consuming symbols on different reference bases (pass 1 leaves either a 'D' before
+// the position or matches of different bases around it); between insertions of different bases; between a deletion and an
+// insertion.  Lanes cut the script at such positions near the n/GROUP boundaries and each runs the reference's serial
+// algorithm on its own piece, which gives the same script as one serial run.
+template <int GROUP, class V>
+__device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint32_t n, V ref, V enc, bool rows_ref, char* out)
+{
+	const uint32_t gl = A.gl;
+	const uint32_t L = (n + GROUP - 1) / GROUP;
+	const uint32_t s = min(n, gl * L), e = min(n, s + L);
+	uint32_t cr = 0, ce = 0;
+	for (uint32_t i = s; i < e; ++i) { const uint8_t o = ops[i]; cr += (o == 0) | ((o == 1) == rows_ref); ce += (o == 0) | ((o == 1) != rows_ref); }
+	uint32_t pr = cr, pe = ce;
+	if (GROUP > 1) {
+#pragma unroll
+		for (int d = 1; d < GROUP; d <<= 1) {
+			const uint32_t a = __shfl_up_sync(A.gmask, pr, d, GROUP), b = __shfl_up_sync(A.gmask, pe, d, GROUP);
+			if ((int)gl >= d) { pr += a; pe += b; }
+		}
+	}
+	pr -= cr; pe -= ce;                        // reference / read symbols consumed before position s
+	{
+		uint32_t r = pr, q = pe;
+		for (uint32_t i = s; i < e; ++i) {
+			const uint8_t o = ops[i];
+			if (o == 0) { const uint8_t a = ref[(int)r], b = enc[(int)q]; out[i] = a == b ? 'M' : mismatch_symb(a, b); ++r; ++q; }
+			else if ((o == 1) == rows_ref) { out[i] = 'D'; ++r; }
+			else { out[i] = "ACGT"[enc[(int)q] & 3]; ++q; }
+		}
+	}
+	if (GROUP == 1) { refactor_range(ref, enc, out, 0, n, 0, 0); return; }
+	A.gsync();
+	uint32_t cut = 0, cut_r = 0, cut_q = 0;
+	if (gl > 0) {
+		// first position p >= s where both passes start a new range whatever came before (a = symbol p-1, b = symbol p):
+		//   a or b is a substitution; a, b both consume the reference (M / D) and the reference base changes;
+		//   a, b are insertions of different bases; a is a deletion and b an insertion.
+		cut = n;
+		uint32_t r = pr, q = pe;
+		for (uint32_t p = s; p < n; ++p) {
+			const char b = out[p];
+			if (p > 0) {
+				const char a = out[p - 1];
+				const bool a_rc = a == 'M' || a == 'D', b_rc = b == 'M' || b == 'D';
+				bool safe = es_is_mm(a) || es_is_mm(b);
+				if (!safe && a_rc && b_rc) safe = ref[(int)r - 1] != ref[(int)r];
+				if (!safe && es_is_ins(a) && es_is_ins(b)) safe = a != b;
+				if (!safe && a == 'D' && es_is_ins(b)) safe = true;
+				if (safe) { cut = p; cut_r = r; cut_q = q; break; }
+			}
+			if (b == 'D') ++r; else if (es_is_ins(b)) ++q; else { ++r; ++q; }
+		}
+	}
+	uint32_t next = __shfl_down_sync(A.gmask, cut, 1, GROUP);
+	if (gl == GROUP - 1) next = n;
+	A.gsync();                                 // every cut is known before any lane reorders symbols
+	if (cut < next) refactor_range(ref, enc, out, cut, next, cut_r, cut_q);
+	A.gsync();
 }
 
 // One edit-script task = CEncoder::GetEditDist (encoder.cpp:1255-1283).
@@ -366,22 +511,11 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		const bool small = edlib_column_bytes(rl, el) < EDLIB_TRACEBACK_LIMIT;
 		if (small) n_ops = A.leaf(ref, (int)rl, enc, (int)el, ops, A.scratch + A.lay.tmp);
 		else {
-			best = A.sweep(ref, (int)rl, enc, (int)el, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+			best = A.sweep(ref, (int)rl, enc, (int)el, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
 			A.gsync();
 			n_ops = A.path(ref, (int)rl, enc, (int)el, best, ops);
 		}
-		if (gl == 0) {
-			uint32_t pr = 0, pe = 0;
-			for (int i = 0; i < n_ops; ++i) {
-				const uint8_t o = ops[i];
-				if (o == 0) { out[i] = 'M'; ++pr; ++pe; }
-				else if (o == 1) { out[i] = 'D'; ++pr; }
-				else if (o == 2) { out[i] = "ACGT"[enc[pe++]]; }
-				else { out[i] = mismatch_symb(ref[pr], enc[pe]); ++pr; ++pe; }
-			}
-			refactor_edit_script(ref, enc, out, (uint32_t)n_ops);
-		}
-		A.gsync();
+		finish_script<GROUP>(A, ops, (uint32_t)n_ops, ref, enc, true, out);
 		return (uint32_t)n_ops;
 	}
 	// flanks: SHW of enc against a prefix of ref limited to 2*|enc| symbols; the left flank works on reversed strings
@@ -395,13 +529,15 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		n_ops = A.leaf(r, (int)cut, e, (int)el, ops, A.scratch + A.lay.tmp);
 	} else {
 		rows_ref = false;
+#ifdef CLB_ALIGN_TIMING
+		long long tc0 = clock64();
+#endif
 		int32_t* lastrow = reinterpret_cast<int32_t*>(A.scratch + A.lay.lastrow);
 		const bool small = edlib_column_bytes(el, cut) < EDLIB_TRACEBACK_LIMIT;
 		const int B = ((int)el + 63) >> 6;
 		uint64_t* hpv = reinterpret_cast<uint64_t*>(A.scratch + A.lay.hist);
-		uint64_t* hmv = hpv + (size_t)B * cut;
-		int32_t* hsc = reinterpret_cast<int32_t*>(hmv + (size_t)B * cut);
-		A.sweep(e, (int)el, r, (int)cut, small ? hpv : nullptr, small ? hmv : nullptr, small ? hsc : nullptr, lastrow, nullptr, nullptr, nullptr);
+		uint64_t* hph = hpv + (size_t)B * cut;
+		A.sweep(e, (int)el, r, (int)cut, small ? hpv : nullptr, small ? hph : nullptr, (int)cut, lastrow, nullptr, nullptr, nullptr);
 		A.gsync();
 		// leftmost column with the minimal last-row score (edlib.cpp:660-674)
 		int best = 0x7fffffff, end = 0;
@@ -412,39 +548,27 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		}
 		ref_end = (uint32_t)end;
 		const int T = end + 1;
-		if (small) {
-			if (gl == 0) { typename Aligner<GROUP>::Hist h{hpv, hmv, hsc, B, (int)el}; n_ops = Aligner<GROUP>::traceback(h, (int)el, T, ops, A.scratch + A.lay.tmp); }
-			if (GROUP > 1) n_ops = __shfl_sync(A.gmask, n_ops, 0, GROUP);
-			A.gsync();
-		} else n_ops = A.path(e, (int)el, r, T, best, ops);
+#ifdef CLB_ALIGN_TIMING
+		long long tc1 = clock64();
+#endif
+		if (small) n_ops = A.traceback(hpv, hph, (int)cut, (int)el, T, ops, A.scratch + A.lay.tmp);
+		else n_ops = A.path(e, (int)el, r, T, best, ops);
+#ifdef CLB_ALIGN_TIMING
+		if (gl == 0 && el > 30000) printf("[task] el %u cut %u small %d: sweep %lld path %lld cycles, n_ops %d\n", el, cut, (int)small, tc1 - tc0, clock64() - tc1, n_ops);
+#endif
 	}
-	if (gl == 0) {
-		// symbols of the (possibly reversed) problem in forward order
-		char* w = out;
-		uint32_t lead = 0;
-		if (kind == 0) {
-			lead = (rl - 1) - ref_end;
-			if (lead_out) { *lead_out = lead; }
-			else { for (uint32_t i = 0; i < lead; ++i) out[i] = 'D'; w = out + lead; }
-		}
-		uint32_t pr = 0, pe = 0;
-		for (int i = 0; i < n_ops; ++i) {
-			const uint8_t o = ops[i];
-			const int at = kind == 0 ? n_ops - 1 - i : i;      // the left flank's script is reversed back
-			char ch;
-			if (o == 0) { ch = 'M'; ++pr; ++pe; }
-			else if (o == 3) { ch = mismatch_symb(r[pr], e[pe]); ++pr; ++pe; }
-			else if ((o == 1) == rows_ref) { ch = 'D'; ++pr; }              // UP consumes a row symbol, LEFT a column symbol
-			else { ch = "ACGT"[e[pe++]]; }
-			w[at] = ch;
-		}
-		if (kind == 0) refactor_edit_script(ref.sub((int)lead), enc, w, (uint32_t)n_ops);
-		else refactor_edit_script(ref, enc, w, (uint32_t)n_ops);
-		n_out = (lead_out ? 0 : lead) + (uint32_t)n_ops;
+	// the left flank was aligned on reversed strings: its script (and the order in which symbols are consumed) is the reverse
+	uint32_t lead = 0;
+	char* w = out;
+	if (kind == 0) {
+		lead = (rl - 1) - ref_end;
+		for (int x = (int)gl; x < n_ops / 2; x += GROUP) { const uint8_t t = ops[x]; ops[x] = ops[n_ops - 1 - x]; ops[n_ops - 1 - x] = t; }
+		if (lead_out) { *lead_out = lead; }
+		else { for (uint32_t i = gl; i < lead; i += GROUP) out[i] = 'D'; w = out + lead; }
+		A.gsync();
 	}
-	if (GROUP > 1) n_out = __shfl_sync(A.gmask, n_out, 0, GROUP);
-	A.gsync();
-	return n_out;
+	finish_script<GROUP>(A, ops, (uint32_t)n_ops, kind == 0 ? ref.sub((int)lead) : ref, enc, rows_ref, w);
+	return (lead_out ? 0 : lead) + (uint32_t)n_ops;
 }
 
 } // namespace clb

@@ -37,8 +37,8 @@ struct DevBuf {
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
 
 // kernel classes for the optional per-kernel timing (clb_profile_*)
-enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_N };
-static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode" };
+enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_DECIDE, K_ESTIMATE, K_EMIT, K_N };
+static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit" };
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 } // namespace clb
@@ -121,7 +121,9 @@ struct clb_ctx {
 	uint64_t es_total = 0;
 	uint32_t* d_ref_to_read = nullptr;
 	clb::DevBuf<uint8_t> s2_arena;   // pair / anchor arena of the current batch
-	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current wave
+	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current waves
+	cudaStream_t s2_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // alignment bins run concurrently
+	cudaEvent_t s2_fork = nullptr, s2_join[4] = {nullptr, nullptr, nullptr, nullptr};
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <ctime>
 #include <vector>
 
 namespace clb {
@@ -87,8 +89,11 @@ __global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes
 	if (!FILL) { cnt[id - n0] = N.n_anch + 1; capu[id - n0] = (uint32_t)(cap_sum / 4); }
 }
 
-constexpr int N_TBIN = 16, N_GCLASS = 5, N_BINS = N_TBIN * N_GCLASS;
-struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; };
+// bins: lane-group class (1/2/4/8 lanes: rows within a factor of two) x log2(columns); the 32-lane class, whose row count is
+// open-ended, is split by log2(rows) as well so that the parts of one launch cost about the same
+constexpr int N_TBIN = 16, N_QBIN = 8, N_BINS = N_TBIN * 4 + N_TBIN * N_QBIN;
+constexpr int N_ALIGN_STREAMS = 4;
+struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; unsigned long long sumq[N_BINS], sumt[N_BINS], sumqt[N_BINS]; };
 
 CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : 4; }
 CLB_HD int ilog2_u32(uint32_t x) { int r = 0; while (x >>= 1) ++r; return r; }
@@ -96,7 +101,7 @@ CLB_HD int ilog2_u32(uint32_t x) { int r = 0; while (x >>= 1) ++r; return r; }
 // Parts with an empty side need no alignment (edit_script.h:247-266): el == 0 -> 'D' x rl (kept as `lead`), rl == 0 -> the
 // part's bases as insertions.  Everything else is binned.
 __global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks, uint64_t t0, uint64_t t1, ReadStore R, const Node* __restrict__ nodes,
-	char* __restrict__ esbuf, BinStats* __restrict__ bins, uint32_t* __restrict__ bin_of)
+	char* __restrict__ esbuf, BinStats* __restrict__ bins, uint32_t* __restrict__ bin_of, bool prof)
 {
 	const uint64_t t = t0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= t1) return;
@@ -110,11 +115,13 @@ __global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks,
 	}
 	long long q, tt;
 	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
-	const int b = gclass_of(q) * N_TBIN + min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
+	const int gc = gclass_of(q), tb = min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
+	const int b = gc < 4 ? gc * N_TBIN + tb : 4 * N_TBIN + min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 9)) * N_TBIN + tb;
 	bin_of[t - t0] = (uint32_t)b;
 	atomicAdd(&bins->cnt[b], 1u);
 	atomicMax(&bins->maxq[b], (unsigned int)q);
 	atomicMax(&bins->maxt[b], (unsigned int)tt);
+	if (prof) { atomicAdd(&bins->sumq[b], (unsigned long long)q); atomicAdd(&bins->sumt[b], (unsigned long long)tt); atomicAdd(&bins->sumqt[b], (unsigned long long)(q * tt)); }
 }
 __global__ void __launch_bounds__(256) k_task_scatter(uint64_t t0, uint64_t t1, const uint32_t* __restrict__ bin_of, BinStats* __restrict__ bins, uint32_t* __restrict__ list)
 {
@@ -307,53 +314,140 @@ CLB_D void read_hist(const uint64_t* __restrict__ pk, uint64_t start, uint32_t l
 
 struct PackArgs {
 	const uint32_t* pack_first; uint32_t n_packs;       // pack_first[n_packs + 1]: read index (absolute)
-	uint32_t read_lo;
+	uint32_t read_lo, n_reads;
 	const uint32_t* slot_of_read;                        // per batch read: level-0 node or 0xFFFFFFFF
 	const uint8_t* has_n;
 	Task* tasks; const Node* nodes; const char* esbuf; ReadStore R;
+	uint4* hist;                                         // per batch read: base counts
+	uint32_t* pend_cnt; const uint64_t* pend_off; uint32_t* pend;     // short parts of every read in the reference's order
 };
 
-__global__ void __launch_bounds__(32) k_estimate(PackArgs a)
+// base counts of every read of the batch (CEntropyEstimator::LogRead input)
+__global__ void __launch_bounds__(128) k_read_hist(PackArgs a)
 {
-	const uint32_t pk_i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (pk_i >= a.n_packs) return;
-	Estimator e; est_reset(e);
-	for (uint32_t r = a.pack_first[pk_i]; r < a.pack_first[pk_i + 1]; ++r) {
-		if (a.has_n[r]) continue;
-		{	// LogRead (utils.h:946)
-			uint32_t h[4]; read_hist(a.R.pk, a.R.rd_start[r], a.R.rd_len[r], h);
-			for (int i = 0; i < 4; ++i) e.dna[i] += h[i];
-			e.dna_sum += a.R.rd_len[r];
-			est_rescale(e.dna, 4, e.dna_sum);
-			est_logs(e.dna, e.dna_log, 4, e.dna_sum);
-		}
-		const uint32_t root = a.slot_of_read[r - a.read_lo];
-		if (root == 0xFFFFFFFFu || !a.nodes[root].valid) continue;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n_reads) return;
+	const uint32_t r = a.read_lo + i;
+	uint32_t h[4] = {0, 0, 0, 0};
+	if (!a.has_n[r]) read_hist(a.R.pk, a.R.rd_start[r], a.R.rd_len[r], h);
+	a.hist[i] = make_uint4(h[0], h[1], h[2], h[3]);
+}
+
+// The estimator sees the short parts of a read in the order EncodePart is called: depth first through the alternative reads.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_pending(PackArgs a)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.n_reads) return;
+	const uint32_t root = a.slot_of_read[i];
+	uint32_t n = 0;
+	if (!a.has_n[a.read_lo + i] && root != 0xFFFFFFFFu && a.nodes[root].valid) {
+		uint32_t* out = FILL ? a.pend + a.pend_off[i] : nullptr;
 		uint32_t st_node[10], st_i[10]; int sp = 1;
 		st_node[0] = root; st_i[0] = 0;
 		while (sp > 0) {
 			const Node& N = a.nodes[st_node[sp - 1]];
 			if (st_i[sp - 1] > N.n_anch) { --sp; continue; }
-			Task& T = a.tasks[N.first_task + st_i[sp - 1]++];
-			if (T.decision == D_ALT) { st_node[sp] = T.child; st_i[sp] = 0; ++sp; continue; }
-			if (T.decision != D_PENDING) continue;
-			// EncodeWithEditScript (utils.h:1060-1126)
-			uint32_t loc[12]; uint32_t loc_sum = e.es_sum;
-			for (int i = 0; i < 12; ++i) { loc[i] = e.es[i] + T.rd[i]; loc_sum += T.rd[i]; }
-			double es_cost = e.dec_log[0], plain_cost = e.dec_log[1];
-			est_logs(loc, e.es_log, 12, loc_sum);
-			for (int i = 0; i < 12; ++i) es_cost = __dadd_rn(es_cost, __dmul_rn((double)T.rd[i], e.es_log[i]));
-			const uint8_t* runs = reinterpret_cast<const uint8_t*>(a.esbuf + T.es_off + T.es_len);
-			for (uint32_t i = 0; i < T.n_runs; ++i) es_cost = __dadd_rn(es_cost, (double)runs[i]);
-			for (int i = 0; i < 4; ++i) plain_cost = __dadd_rn(plain_cost, __dmul_rn((double)T.rp[i], e.dna_log[i]));
-			plain_cost = __dadd_rn(plain_cost, (double)(ilog2u_bits(T.rl) + 1));
-			const bool plain = plain_cost < es_cost;
-			if (plain) { ++e.dec[1]; est_rescale(e.es, 12, e.es_sum); }
-			else { ++e.dec[0]; for (int i = 0; i < 12; ++i) e.es[i] = loc[i]; e.es_sum = loc_sum; est_rescale(e.es, 12, e.es_sum); }
-			++e.dec_sum;
-			est_rescale(e.dec, 2, e.dec_sum);
-			est_logs(e.dec, e.dec_log, 2, e.dec_sum);
-			T.decision = plain ? D_PLAIN : D_ES;
+			const uint32_t t = N.first_task + st_i[sp - 1]++;
+			const uint32_t d = a.tasks[t].decision;
+			if (d == D_ALT) { st_node[sp] = a.tasks[t].child; st_i[sp] = 0; ++sp; }
+			else if (d == D_PENDING) { if (FILL) out[n] = t; ++n; }
+		}
+	}
+	if (!FILL) a.pend_cnt[i] = n;
+}
+
+// One warp per read pack replays CEntropyEstimator (utils.h:760-1126): lanes 0-11 own the edit-script symbol counters,
+// lanes 12-13 the decision counters, lanes 14-17 the base counters; every lane computes the log2 of its own counter, the
+// cost sums are taken in the reference's order through shuffles.  32 parts are loaded at a time (one per lane).
+__global__ void __launch_bounds__(32) k_estimate(PackArgs a)
+{
+	const uint32_t pk_i = blockIdx.x, lane = threadIdx.x;
+	const unsigned FULL = 0xffffffffu;
+	const bool is_es = lane < 12, is_dec = lane == 12 || lane == 13, is_dna = lane >= 14 && lane < 18;
+	uint32_t cnt = 1;
+	uint32_t es_sum = 12, dec_sum = 2, dna_sum = 4;
+	double dna_lg = is_dna ? -log2(__dmul_rn(1.0, __ddiv_rn(1.0, 4.0))) : 0.0;
+	const uint32_t LIM = 1u << 20;
+	for (uint32_t r = a.pack_first[pk_i]; r < a.pack_first[pk_i + 1]; ++r) {
+		if (a.has_n[r]) continue;
+		const uint32_t bi = r - a.read_lo;
+		{	// LogRead (utils.h:946)
+			const uint4 h = a.hist[bi];
+			if (is_dna) cnt += lane == 14 ? h.x : lane == 15 ? h.y : lane == 16 ? h.z : h.w;
+			dna_sum += a.R.rd_len[r];
+			while (dna_sum > LIM) {
+				if (is_dna) cnt = (cnt + 1) / 2;
+				dna_sum = __shfl_sync(FULL, cnt, 14) + __shfl_sync(FULL, cnt, 15) + __shfl_sync(FULL, cnt, 16) + __shfl_sync(FULL, cnt, 17);
+			}
+			if (is_dna) dna_lg = -log2(__dmul_rn((double)cnt, __ddiv_rn(1.0, (double)dna_sum)));
+		}
+		const uint64_t p0 = a.pend_off[bi], p1 = p0 + a.pend_cnt[bi];
+		for (uint64_t base = p0; base < p1; base += 32) {
+			const uint32_t m = (uint32_t)min((uint64_t)32, p1 - base);
+			uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nr = 0, rl = 0, tid = 0;
+			unsigned long long rptr = 0;
+			if (lane < m) {
+				tid = a.pend[base + lane];
+				const Task& T = a.tasks[tid];
+				const uint32_t* rw = reinterpret_cast<const uint32_t*>(T.rd);          // rd[12] + rp[4] = 8 words
+#pragma unroll
+				for (int x = 0; x < 8; ++x) w[x] = rw[x];
+				nr = T.n_runs; rl = T.rl; rptr = T.es_off + T.es_len;
+			}
+			uint32_t my_dec = 0;
+			for (uint32_t k = 0; k < m; ++k) {
+				uint32_t W[8];
+#pragma unroll
+				for (int x = 0; x < 8; ++x) W[x] = __shfl_sync(FULL, w[x], k);
+				const uint32_t nr_k = __shfl_sync(FULL, nr, k), rl_k = __shfl_sync(FULL, rl, k);
+				const unsigned long long rp_k = __shfl_sync(FULL, rptr, k);
+				// my share of the part's statistics
+				uint32_t wsel = 0;
+#pragma unroll
+				for (int x = 0; x < 8; ++x) if ((lane >> 1) == (uint32_t)x) wsel = W[x];
+				uint32_t mine = (wsel >> (16 * (lane & 1))) & 0xffffu;                   // lanes 0-11: rd[lane]
+				if (is_dna) {                                                            // lanes 14-17: rp[lane - 14] = halves of W[6], W[7]
+					const uint32_t ww = lane < 16 ? W[6] : W[7];
+					mine = (ww >> (16 * (lane & 1))) & 0xffffu;
+				}
+				uint32_t sum_rd = 0;
+#pragma unroll
+				for (int x = 0; x < 6; ++x) sum_rd += (W[x] & 0xffffu) + (W[x] >> 16);
+				const uint32_t loc = cnt + mine, loc_sum = es_sum + sum_rd;
+				double lg = 0.0;
+				if (is_es) lg = -log2(__dmul_rn((double)loc, __ddiv_rn(1.0, (double)loc_sum)));
+				else if (is_dec) lg = -log2(__dmul_rn((double)cnt, __ddiv_rn(1.0, (double)dec_sum)));
+				const double prod = is_es ? __dmul_rn((double)mine, lg) : (is_dna ? __dmul_rn((double)mine, dna_lg) : 0.0);
+				double es_cost = __shfl_sync(FULL, lg, 12), plain_cost = __shfl_sync(FULL, lg, 13);
+#pragma unroll
+				for (int x = 0; x < 12; ++x) es_cost = __dadd_rn(es_cost, __shfl_sync(FULL, prod, x));
+				const uint8_t* runs = reinterpret_cast<const uint8_t*>(a.esbuf) + rp_k;
+				for (uint32_t x = 0; x < nr_k; ++x) es_cost = __dadd_rn(es_cost, (double)runs[x]);
+#pragma unroll
+				for (int x = 14; x < 18; ++x) plain_cost = __dadd_rn(plain_cost, __shfl_sync(FULL, prod, x));
+				plain_cost = __dadd_rn(plain_cost, (double)(ilog2u_bits(rl_k) + 1));
+				const bool plain = plain_cost < es_cost;
+				if (plain) { if (lane == 13) ++cnt; }
+				else {
+					if (lane == 12) ++cnt;
+					if (is_es) cnt = loc;
+					es_sum = loc_sum;
+					while (es_sum > LIM) {
+						if (is_es) cnt = (cnt + 1) / 2;
+						uint32_t t = is_es ? cnt : 0;
+						for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
+						es_sum = t;
+					}
+				}
+				++dec_sum;
+				while (dec_sum > LIM) {
+					if (is_dec) cnt = (cnt + 1) / 2;
+					dec_sum = __shfl_sync(FULL, cnt, 12) + __shfl_sync(FULL, cnt, 13);
+				}
+				if (lane == k) my_dec = plain ? D_PLAIN : D_ES;
+			}
+			if (lane < m) a.tasks[tid].decision = my_dec;
 		}
 	}
 }
@@ -502,7 +596,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	CLB_CUDA(c, mem.get(&d_list, nt));
 	CLB_CUDA(c, cudaMemsetAsync(d_bins, 0, sizeof(BinStats), s));
 	const uint32_t blocks = (uint32_t)((nt + 255) / 256);
-	CLB_TIMED(c, K_ENCODE, (k_task_classify<<<blocks, 256, 0, s>>>(d_tasks, t0, t1, R, d_nodes, d_esbuf, d_bins, d_bin_of)));
+	CLB_TIMED(c, K_ENCODE, (k_task_classify<<<blocks, 256, 0, s>>>(d_tasks, t0, t1, R, d_nodes, d_esbuf, d_bins, d_bin_of, std::getenv("CLB_ALIGN_PROFILE") != nullptr)));
 	CLB_LAUNCH_CHECK(c, "k_task_classify");
 	BinStats hb;
 	CLB_CUDA(c, cudaMemcpyAsync(&hb, d_bins, sizeof(BinStats), cudaMemcpyDeviceToHost, s));
@@ -514,30 +608,69 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	CLB_TIMED(c, K_ENCODE, (k_task_scatter<<<blocks, 256, 0, s>>>(t0, t1, d_bin_of, d_bins, d_list)));
 	CLB_LAUNCH_CHECK(c, "k_task_scatter");
 	const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
-	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 6ull << 30;
-	for (int b = 0; b < N_BINS; ++b) {
-		if (!hb.cnt[b]) continue;
+	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 8ull << 30;
+	const bool bin_prof = std::getenv("CLB_ALIGN_PROFILE") != nullptr;
+	// bins run concurrently on a few streams (each with its own slice of the scratch) so that the tail of one bin
+	// overlaps the bulk of another; the per-bin profile serialises them on the main stream instead
+	const int n_str = bin_prof ? 1 : N_ALIGN_STREAMS;
+	if (!c->s2_streams[0]) {
+		for (int i = 0; i < N_ALIGN_STREAMS; ++i) CLB_CUDA(c, cudaStreamCreateWithFlags(&c->s2_streams[i], cudaStreamNonBlocking));
+		CLB_CUDA(c, cudaEventCreateWithFlags(&c->s2_fork, cudaEventDisableTiming));
+		for (int i = 0; i < N_ALIGN_STREAMS; ++i) CLB_CUDA(c, cudaEventCreateWithFlags(&c->s2_join[i], cudaEventDisableTiming));
+	}
+	const uint64_t slice = (budget / n_str) & ~255ull;
+	uint64_t need_total = 0;
+	for (int b = 0; b < N_BINS; ++b) if (hb.cnt[b]) {
 		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
-		const uint64_t per_wave = std::max<uint64_t>(1, budget / stride);
-		const int g = 1 << (b / N_TBIN == 4 ? 5 : b / N_TBIN);
+		if (stride > slice) return fail(c, CLB_ERR_CAPACITY, "one alignment needs more scratch than CLB_ALIGN_SCRATCH_MB allows");
+		need_total = std::max(need_total, std::min<uint64_t>(slice, stride * hb.cnt[b]));
+	}
+	CLB_CUDA(c, c->s2_scratch.reserve(slice * n_str, s, false));
+	cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+	if (bin_prof) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
+	prof_begin(c, K_ALIGN);
+	CLB_CUDA(c, cudaEventRecord(c->s2_fork, s));
+	for (int i = 0; i < n_str && !bin_prof; ++i) CLB_CUDA(c, cudaStreamWaitEvent(c->s2_streams[i], c->s2_fork, 0));
+	// heavy bins first
+	std::vector<int> order;
+	for (int b = 0; b < N_BINS; ++b) if (hb.cnt[b]) order.push_back(b);
+	std::sort(order.begin(), order.end(), [&](int x, int y) { return (double)hb.cnt[x] * hb.maxq[x] * hb.maxt[x] > (double)hb.cnt[y] * hb.maxq[y] * hb.maxt[y]; });
+	int rr = 0;
+	for (int b : order) {
+		if (bin_prof) cudaEventRecord(pe0, s);
+		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
+		const uint64_t per_wave = std::max<uint64_t>(1, slice / stride);
+		const int g = b < 4 * N_TBIN ? 1 << (b / N_TBIN) : 32;
+		const int si = rr++ % n_str;
+		cudaStream_t ls = bin_prof ? s : c->s2_streams[si];
+		uint8_t* scratch = c->s2_scratch.p + (uint64_t)si * slice;
 		for (uint64_t w0 = 0; w0 < hb.cnt[b]; w0 += per_wave) {
 			const uint32_t m = (uint32_t)std::min<uint64_t>(per_wave, hb.cnt[b] - w0);
-			CLB_CUDA(c, c->s2_scratch.reserve(m * stride, s, false));
 			const uint32_t* list = d_list + hb.base[b] + w0;
 			const uint32_t threads = 128;
 			const uint32_t grid = (uint32_t)(((uint64_t)m * g + threads - 1) / threads);
-			prof_begin(c, K_ALIGN);
 			switch (g) {
-			case 1: k_align<1><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 2: k_align<2><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 4: k_align<4><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 8: k_align<8><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			default: k_align<32><<<grid, threads, 0, s>>>(d_tasks, t0, list, m, stride, c->s2_scratch.p, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 1: k_align<1><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 2: k_align<2><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 4: k_align<4><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 8: k_align<8><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			default: k_align<32><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
 			}
-			prof_end(c);
 			CLB_LAUNCH_CHECK(c, "k_align");
 		}
+		if (bin_prof) {
+			cudaEventRecord(pe1, s); cudaEventSynchronize(pe1);
+			float ms = 0; cudaEventElapsedTime(&ms, pe0, pe1);
+			fprintf(stderr, "[align] group %2d bin %3d: %9u tasks, max q %7u, max t %7u, mean q %7.0f, mean t %7.0f, Gcells %8.3f, stride %9llu, %9.3f ms\n", g, b, hb.cnt[b], hb.maxq[b], hb.maxt[b],
+				(double)hb.sumq[b] / hb.cnt[b], (double)hb.sumt[b] / hb.cnt[b], (double)hb.sumqt[b] * 1e-9, (unsigned long long)stride, ms);
+		}
 	}
+	if (bin_prof) { cudaEventDestroy(pe0); cudaEventDestroy(pe1); }
+	else for (int i = 0; i < n_str; ++i) {
+		CLB_CUDA(c, cudaEventRecord(c->s2_join[i], c->s2_streams[i]));
+		CLB_CUDA(c, cudaStreamWaitEvent(s, c->s2_join[i], 0));
+	}
+	prof_end(c);
 	CLB_CUDA(c, cudaStreamSynchronize(s));        // d_list / d_bin_of die with `mem`
 	return CLB_OK;
 }
@@ -566,6 +699,13 @@ static clb_status dump_candidates(clb_ctx* c, const S2P& P, const std::vector<ui
 	return CLB_OK;
 }
 
+struct Trace {            // CLB_S2_TRACE=1: wall time of every phase of a batch (synchronising; debugging aid)
+	bool on; cudaStream_t s; double t0; const char* what;
+	static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	Trace(cudaStream_t st) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), t0(now()), what("start") {}
+	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s2] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
+};
+
 // one batch = whole read packs [pack_lo, pack_hi)
 static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& pack_first, uint32_t pack_lo, uint32_t pack_hi, const std::vector<uint32_t>& h_cand_n)
 {
@@ -573,6 +713,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	const uint32_t lo = pack_first[pack_lo], hi = pack_first[pack_hi], nr = hi - lo;
 	if (!nr) return CLB_OK;
 	Scoped mem;
+	Trace tr(s);
 	const ReadStore R{c->pk.p, c->rd_start.p, c->rd_len.p, c->nmask.p, c->d_ref_to_read};
 	// reads that go through the anchor search
 	std::vector<uint32_t> h_list, h_slot(nr, 0xFFFFFFFFu);
@@ -594,6 +735,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>((uint64_t)nb * P.c, 1), s, false));
 	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes.p, cviews.p, d_cursor);
 	if (st != CLB_OK) return st;
+	tr.mark("anchors");
 	if (c->keep_candidates) { st = dump_candidates(c, P, h_list, nodes.p, cviews.p); if (st != CLB_OK) return st; }
 
 	// ---- level waves ----
@@ -614,8 +756,10 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 		CLB_CUDA(c, esbuf.reserve(es_used + ncap * 4 + 16, s, true, es_used));
 		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
 		CLB_LAUNCH_CHECK(c, "k_tasks<fill>");
+		tr.mark("level: task lists");
 		st = align_level(c, P, tasks.p, n_tasks, n_tasks + nt, R, nodes.p, cviews.p, esbuf.p, d_bins);
 		if (st != CLB_OK) return st;
+		tr.mark("level: align");
 		// decisions; children are appended to the node array
 		const uint64_t cap_nodes = n_nodes + nt;
 		if (cap_nodes >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "too many nodes in one batch");
@@ -625,37 +769,52 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 		CLB_CUDA(c, cudaMemcpyAsync(d_cursor, &cur, sizeof(cur), cudaMemcpyHostToDevice, s));
 		if (nt) {
 			DecideArgs da{tasks.p, n_tasks, n_tasks + nt, nodes.p, cviews.p, reinterpret_cast<unsigned int*>(d_cursor), (uint32_t)cap_nodes, c->s2_arena.p, R, esbuf.p, P};
-			CLB_TIMED(c, K_ENCODE, (k_decide<<<(uint32_t)((nt + 127) / 128), 128, 0, s>>>(da)));
+			CLB_TIMED(c, K_DECIDE, (k_decide<<<(uint32_t)((nt + 127) / 128), 128, 0, s>>>(da)));
 			CLB_LAUNCH_CHECK(c, "k_decide");
 		}
 		CLB_CUDA(c, cudaMemcpyAsync(&cur, d_cursor, sizeof(cur), cudaMemcpyDeviceToHost, s));
 		CLB_CUDA(c, cudaStreamSynchronize(s));
+		tr.mark("level: decide");
 		n_tasks += nt; es_used += ncap * 4;
 		n0 = n1; n_nodes = std::min<uint64_t>(cur, cap_nodes);
 		if (level > P.max_rec + 1) break;
 	}
 
-	// ---- adaptive estimator, one thread per pack ----
+	// ---- adaptive estimator: one warp per pack over the short parts listed in the reference's order ----
 	const uint32_t np = pack_hi - pack_lo;
-	PackArgs pa{d_pack_first, np, lo, d_slot, c->d_has_n, tasks.p, nodes.p, esbuf.p, R};
-	CLB_TIMED(c, K_ENCODE, (k_estimate<<<(np + 31) / 32, 32, 0, s>>>(pa)));
+	uint4* d_hist = nullptr; uint32_t* d_pcnt = nullptr; uint64_t* d_poff = nullptr; uint32_t* d_pend = nullptr;
+	CLB_CUDA(c, mem.get(&d_hist, nr)); CLB_CUDA(c, mem.get(&d_pcnt, nr)); CLB_CUDA(c, mem.get(&d_poff, nr));
+	PackArgs pa{d_pack_first, np, lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, esbuf.p, R, d_hist, d_pcnt, d_poff, nullptr};
+	CLB_TIMED(c, K_ESTIMATE, (k_read_hist<<<(nr + 127) / 128, 128, 0, s>>>(pa)));
+	CLB_LAUNCH_CHECK(c, "k_read_hist");
+	CLB_TIMED(c, K_ESTIMATE, (k_pending<false><<<(nr + 127) / 128, 128, 0, s>>>(pa)));
+	CLB_LAUNCH_CHECK(c, "k_pending<count>");
+	uint64_t n_pend = 0;
+	st = exclusive_scan(c, d_pcnt, nr, d_poff, &n_pend); if (st != CLB_OK) return st;
+	CLB_CUDA(c, mem.get(&d_pend, n_pend));
+	pa.pend = d_pend;
+	CLB_TIMED(c, K_ESTIMATE, (k_pending<true><<<(nr + 127) / 128, 128, 0, s>>>(pa)));
+	CLB_LAUNCH_CHECK(c, "k_pending<fill>");
+	CLB_TIMED(c, K_ESTIMATE, (k_estimate<<<np, 32, 0, s>>>(pa)));
 	CLB_LAUNCH_CHECK(c, "k_estimate");
+	tr.mark("estimator");
 
 	// ---- tuples ----
 	uint32_t* d_size = nullptr; uint32_t* d_kind = nullptr; uint64_t* d_off = nullptr;
 	CLB_CUDA(c, mem.get(&d_size, nr)); CLB_CUDA(c, mem.get(&d_kind, nr)); CLB_CUDA(c, mem.get(&d_off, nr));
 	EmitArgs ea{lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, cviews.p, P.c, c->s2_arena.p, esbuf.p, R, d_size, d_kind, d_off, c->es_total, nullptr, c->es_off};
-	CLB_TIMED(c, K_ENCODE, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	CLB_TIMED(c, K_EMIT, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit<size>");
 	uint64_t total = 0;
 	st = exclusive_scan(c, d_size, nr, d_off, &total); if (st != CLB_OK) return st;
 	CLB_CUDA(c, c->es.reserve(c->es_total + total + 16, s, true, c->es_total));
 	ea.out = c->es.p;
-	CLB_TIMED(c, K_ENCODE, (k_emit<true><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	CLB_TIMED(c, K_EMIT, (k_emit<true><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit<write>");
-	CLB_TIMED(c, K_ENCODE, (k_emit_plain<<<nr, 256, 0, s>>>(ea)));
+	CLB_TIMED(c, K_EMIT, (k_emit_plain<<<nr, 256, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit_plain");
 	CLB_CUDA(c, cudaStreamSynchronize(s));
+	tr.mark("emit");
 	c->es_total += total;
 	return CLB_OK;
 }
@@ -668,6 +827,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	if (prm->anchor_len < 8 || prm->anchor_len > 32) return fail(c, CLB_ERR_BAD_ARG, "anchor_len must be in [8, 32]");
 	if (prm->max_recurence > 7) return fail(c, CLB_ERR_BAD_ARG, "max_recurence above 7 is not supported");
 	cudaStream_t s = c->stream;
+	Trace tr(s);
 	const uint64_t n = c->n_reads;
 	S2P P{prm->anchor_len, prm->min_part_len_alt, prm->max_recurence, prm->min_anchors, c->prm.max_candidates,
 		prm->min_mmer_frac, prm->min_mmer_force, prm->max_matches_mult, prm->es_cost_mult};
@@ -700,23 +860,29 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
 	const char* env_batch = std::getenv("CLB_BATCH_MBASES");
 	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 256) << 20;
+	tr.mark("encode: setup");
 	for (uint32_t p = 0; p < np;) {
 		uint32_t q = p + 1;
 		auto bases_of = [&](uint32_t a, uint32_t b) { return c->h_rd_start[b - 1] + c->h_rd_len[b - 1] - c->h_rd_start[a]; };
 		while (q < np && bases_of(pack_first[p], pack_first[q + 1]) <= batch_bases) ++q;
 		clb_status st = encode_batch(c, P, pack_first, p, q, h_cand_n);
 		if (st != CLB_OK) return st;
+		tr.mark("encode: batch");
 		p = q;
 	}
 	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	c->s2_arena.release(); c->s2_scratch.release();
+	tr.mark("encode: release");
 	c->enc_done = true;
 	return CLB_OK;
 }
 
 void s2_free(clb_ctx* c)
 {
+	for (int i = 0; i < 4; ++i) { if (c->s2_streams[i]) cudaStreamDestroy(c->s2_streams[i]); if (c->s2_join[i]) cudaEventDestroy(c->s2_join[i]); c->s2_streams[i] = nullptr; c->s2_join[i] = nullptr; }
+	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
+	c->s2_fork = nullptr;
 	c->es.release(); c->s2_arena.release(); c->s2_scratch.release();
 	if (c->es_off) cudaFree(c->es_off);
 	if (c->d_ref_to_read) cudaFree(c->d_ref_to_read);

@@ -18,7 +18,7 @@ EXPORTS = [
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
 ]
-KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode"]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit"]
 
 
 class Params(C.Structure):

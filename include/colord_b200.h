@@ -162,7 +162,7 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
 /* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
  * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
- * k_vote, k_common, k_misc, k_align, k_anchors, k_encode.  clb_profile_get synchronizes the stream. */
+ * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit.  clb_profile_get synchronizes the stream. */
 clb_status clb_profile_enable(clb_ctx* ctx, int on);
 clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 

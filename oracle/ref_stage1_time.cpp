@@ -5,6 +5,8 @@
 // compression.cpp:432-575 (CKmerCounter -> CKmerFilter -> CInputReads + CReadsSimilarityGraph) and stops
 // at the compress_queue, which a null consumer drains (no encoders, no entropy coders).  It prints one
 // JSON line with the wall time of each phase.  bench.py --impl reference and the cpu_baseline leg run it.
+// With COLORD_TIME_STAGES=12 the N CEncoder threads (compression.cpp:592-625) consume the compress_queue as in the real
+// pipeline and a null consumer drains their tuple packs: stage 1 + stage 2, still without the entropy coders.
 //
 // Usage: oracle/_ref/ref_stage1_time compress-ont [flags] -t N in.fastq ignored.out
 #include "compression.h"
@@ -14,6 +16,7 @@
 #include "kmer_filter.h"
 #include "in_reads.h"
 #include "reads_sim_graph.h"
+#include "encoder.h"
 #include "reference_reads.h"
 #include "ref_reads_accepter.h"
 #include "parallel_queue.h"
@@ -80,13 +83,38 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 			params.maxKmerCount, params.referenceReadsMode, accepter, (double)tot_ref_reads / tot_n_reads, n_compression_threads,
 			params.dataSource, params.fillFactorKmersToReads, false);
 	});
-	std::thread sink([&] { CCompressPack pack; while (graph_out.Pop(pack)) for (auto& e : pack.data) { ++n_out; n_links += e.ref_reads.size(); } });
-	reader.join(); drain_q.join(); drain_h.join(); graph.join(); sink.join();
+	const char* stages_env = getenv("COLORD_TIME_STAGES");
+	const bool with_encoders = stages_env && std::string(stages_env) == "12";
+	uint64_t es_bytes = 0;
+	if (!with_encoders)
+	{
+		std::thread sink([&] { CCompressPack pack; while (graph_out.Pop(pack)) for (auto& e : pack.data) { ++n_out; n_links += e.ref_reads.size(); } });
+		reader.join(); drain_q.join(); drain_h.join(); graph.join(); sink.join();
+	}
+	else
+	{
+		CParallelPriorityQueue<std::vector<es_t>> es_for_qual(2 * n_compression_threads, n_compression_threads, &qm, 3);
+		CParallelPriorityQueue<std::vector<es_t>> compressed(2 * n_compression_threads, n_compression_threads, &qm, 5);
+		std::vector<std::thread> encoders;
+		for (int i = 0; i < n_compression_threads; ++i)
+			encoders.emplace_back([&] {
+				CEncoder enc(false, graph_out, reference_reads, compressed, es_for_qual, anchorLen,
+					params.minFractionOfMmersInEncodeToAlwaysEncode, params.minFractionOfMmersInEncode, params.maxMatchesMultiplier,
+					params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors,
+					is_fastq, params.filterHashModulo, kmerLen, params.dataSource);
+				enc.Encode();
+			});
+		std::thread drain_esq([&] { std::vector<es_t> p; while (es_for_qual.Pop(p)); });
+		std::thread sink([&] { std::vector<es_t> pack; while (compressed.Pop(pack)) for (auto& es : pack) { ++n_out; es_bytes += es.size(); } });
+		reader.join(); drain_q.join(); drain_h.join(); graph.join();
+		for (auto& t : encoders) t.join();
+		drain_esq.join(); sink.join();
+	}
 	double t4 = now();
 	printf("{\"count_s\": %.4f, \"filter_s\": %.4f, \"graph_s\": %.4f, \"stage1_s\": %.4f, \"k\": %u, \"n_reads\": %u, \"tot_kmers\": %llu, "
-		"\"n_unique_counted\": %llu, \"tot_ref_reads\": %u, \"n_links\": %llu, \"threads\": %u}\n",
+		"\"n_unique_counted\": %llu, \"tot_ref_reads\": %u, \"n_links\": %llu, \"threads\": %u, \"stages\": \"%s\", \"anchor_len\": %u, \"es_bytes\": %llu, \"n_out\": %llu}\n",
 		t1 - t0, t2 - t1, t4 - t3, (t2 - t0) + (t4 - t3), kmerLen, tot_n_reads, (unsigned long long)tot_kmers, (unsigned long long)n_uniq,
-		tot_ref_reads, (unsigned long long)n_links, params.nThreads);
+		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
 	fflush(stdout);
 	_exit(0);     // skip archive/info epilogue of the CLI callback
 }
