@@ -169,17 +169,29 @@ struct Aligner {
 			uint64_t Pv = ~0ULL, Mv = 0;
 			int score = act ? min(Q, (b << 6) + 64) : 0;        // D(last row of block, column -1) = row index + 1
 			int hout = 0;
-			uint64_t colw = 0;                                  // 32 column symbols, refreshed every 32 columns of this lane
-			int cw = 0;                                         // GROUP carries of the previous strip, one per lane
+			// column symbols travel in registers: every lane holds the same three packed words (columns [S-32, S), [S, S+32) and
+			// the prefetched [S+32, S+64) of the current 32-step chunk S), so no load sits on the recurrence's critical path
+			uint64_t col_a = 0, col_b = T > 0 ? cols.get32(0, min(32, T)) : 0, col_c = T > 32 ? cols.get32(32, min(32, T - 32)) : 0;
+			// carries of the previous strip: one per lane for the current chunk of GROUP columns, next chunk prefetched
+			int cw = 0, cw_next = 0;
+			if (GROUP > 1 && strip > 0) { cw = (int)gl < T ? (int)carry[gl] : 0; cw_next = GROUP + (int)gl < T ? (int)carry[GROUP + gl] : 0; }
 			const int n_steps = T + GROUP - 1;
 			for (int s = 0; s < n_steps; ++s) {
-				if (GROUP > 1 && strip > 0 && (s & (GROUP - 1)) == 0) { const int idx = s + (int)gl; cw = idx < T ? (int)carry[idx] : 0; }
+				if (s && (s & 31) == 0) {
+					col_a = col_b; col_b = col_c;
+					col_c = s + 32 < T ? cols.get32(s + 32, min(32, T - s - 32)) : 0;
+				}
+				if (GROUP > 1 && strip > 0 && s && (s & (GROUP - 1)) == 0) {
+					cw = cw_next;
+					const int idx = s + GROUP + (int)gl;
+					cw_next = idx < T ? (int)carry[idx] : 0;
+				}
 				int hin = GROUP > 1 ? __shfl_up_sync(gmask, hout, 1, GROUP) : 0;
 				const int cin = (GROUP > 1 && strip > 0) ? __shfl_sync(gmask, cw, s & (GROUP - 1), GROUP) : 0;
 				const int c = s - (int)gl;
 				if (act && c >= 0 && c < T) {
 					if (gl == 0) hin = strip == 0 ? 1 : (GROUP > 1 ? cin : (int)carry[c]);
-					if ((c & 31) == 0) colw = cols.get32(c, min(32, T - c));
+					const uint64_t colw = (c >> 5) == (s >> 5) ? col_b : col_a;
 					const uint32_t tc = (uint32_t)(colw >> (2 * (c & 31))) & 3u;
 					const uint64_t Eq = tc == 0 ? peq0 : tc == 1 ? peq1 : tc == 2 ? peq2 : peq3;
 					int sd; uint64_t Ph;

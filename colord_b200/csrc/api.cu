@@ -40,6 +40,10 @@ clb_status clb_create(const clb_params* p, clb_ctx** out)
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
 	if (e == cudaSuccess) { c->own_stream = true; e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, p->device); }
 	if (e != cudaSuccess) { clb_status st = cuda_fail(nullptr, e, "clb_create"); delete c; return st; }
+	{	// stream-ordered scratch (cudaMallocAsync) is recycled inside the pool instead of going back to the driver after every sync
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) { unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+	}
 	clb_status st = s1a_init(c);
 	if (st != CLB_OK) { g_create_error = c->err; clb_destroy(c); return st; }
 	*out = c;
@@ -53,6 +57,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
+	{ cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, c->prm.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "../../include/colord_b200.h"
 #include "util.cuh"
+#include "stage2.h"
 
 namespace clb {
 
@@ -122,8 +123,10 @@ struct clb_ctx {
 	uint32_t* d_ref_to_read = nullptr;
 	clb::DevBuf<uint8_t> s2_arena;   // pair / anchor arena of the current batch
 	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current waves
-	cudaStream_t s2_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // alignment bins run concurrently
-	cudaEvent_t s2_fork = nullptr, s2_join[4] = {nullptr, nullptr, nullptr, nullptr};
+	clb::DevBuf<clb::Node> s2_nodes; clb::DevBuf<clb::CandView> s2_cviews;   // batch state, kept across batches (no per-batch malloc)
+	clb::DevBuf<clb::Task> s2_tasks; clb::DevBuf<char> s2_esbuf;
+	cudaStream_t s2_streams[16] = {};   // alignment bins run concurrently
+	cudaEvent_t s2_fork = nullptr, s2_join[16] = {};
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)

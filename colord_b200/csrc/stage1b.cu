@@ -551,7 +551,7 @@ clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* 
 {
 	const uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	uint64_t* tiles = nullptr;
-	CLB_CUDA(c, dev_alloc(&tiles, n_tiles + 1));
+	CLB_CUDA(c, cudaMallocAsync((void**)&tiles, sizeof(uint64_t) * (n_tiles + 1), c->stream));
 	clb_status st = CLB_OK;
 	if (n_tiles) {
 		k_scan_tiles<<<(uint32_t)n_tiles, SCAN_THREADS, 0, c->stream>>>(in, n, tiles); ++c->launches;
@@ -564,7 +564,7 @@ clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* 
 	}
 	unsigned long long sc[SC_COUNT];
 	if (st == CLB_OK) st = scal_read(c, sc);
-	cudaFree(tiles);
+	cudaFreeAsync(tiles, c->stream);
 	if (st == CLB_OK) *total = sc[SC_SUM_TRUE];
 	return st;
 }

@@ -406,10 +406,10 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (bbits > SMEM_BLOOM_WORDS * 32) { bloom_off[i] = bloom_total; bloom_total += bbits / 32; }
 	}
 	uint64_t* d_tab_off = nullptr; uint64_t* d_bloom_off = nullptr; uint32_t* g_tab = nullptr; uint32_t* g_bloom = nullptr;
-	CLB_CUDA(c, cudaMalloc(&d_tab_off, sizeof(uint64_t) * nb));
-	CLB_CUDA(c, cudaMalloc(&d_bloom_off, sizeof(uint64_t) * nb));
-	CLB_CUDA(c, cudaMalloc(&g_tab, sizeof(uint32_t) * (tab_total + 1)));
-	CLB_CUDA(c, cudaMalloc(&g_bloom, sizeof(uint32_t) * (bloom_total + 1)));
+	CLB_CUDA(c, cudaMallocAsync((void**)&d_tab_off, sizeof(uint64_t) * nb, s));
+	CLB_CUDA(c, cudaMallocAsync((void**)&d_bloom_off, sizeof(uint64_t) * nb, s));
+	CLB_CUDA(c, cudaMallocAsync((void**)&g_tab, sizeof(uint32_t) * (tab_total + 1), s));
+	CLB_CUDA(c, cudaMallocAsync((void**)&g_bloom, sizeof(uint32_t) * (bloom_total + 1), s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab_off, tab_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_bloom_off, bloom_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS);
@@ -436,7 +436,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (attempt == 2) { st = fail(c, CLB_ERR_CAPACITY, "pair arena did not converge"); break; }
 		cap_pairs = used + 1024;
 	}
-	cudaFree(d_tab_off); cudaFree(d_bloom_off); cudaFree(g_tab); cudaFree(g_bloom);
+	cudaFreeAsync(d_tab_off, s); cudaFreeAsync(d_bloom_off, s); cudaFreeAsync(g_tab, s); cudaFreeAsync(g_bloom, s);
 	if (st != CLB_OK) return st;
 	const uint32_t n_seg = nb * P.c * 2;
 	CLB_TIMED(c, K_ANCHORS, (k_pairs_sort<<<n_seg, SORT_THREADS, 0, s>>>(d_seg, n_seg, arena.p)));

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes
 // bins: lane-group class (1/2/4/8 lanes: rows within a factor of two) x log2(columns); the 32-lane class, whose row count is
 // open-ended, is split by log2(rows) as well so that the parts of one launch cost about the same
 constexpr int N_TBIN = 16, N_QBIN = 8, N_BINS = N_TBIN * 4 + N_TBIN * N_QBIN;
-constexpr int N_ALIGN_STREAMS = 4;
+constexpr int N_ALIGN_STREAMS = 16;
 struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; unsigned long long sumq[N_BINS], sumt[N_BINS], sumqt[N_BINS]; };
 
 CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : 4; }
@@ -578,10 +578,12 @@ __global__ void __launch_bounds__(256) k_emit_plain(EmitArgs a)
 
 // ------------------------------------------------------------------------------------------------ driver
 template <typename T> static cudaError_t dmalloc(T** p, uint64_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
-struct Scoped {            // frees the batch's device buffers on every exit path
+struct Scoped {            // stream-ordered scratch of a batch / level: freed (back to the pool) on every exit path
+	cudaStream_t s;
 	std::vector<void*> v;
-	template <typename T> cudaError_t get(T** p, uint64_t n) { cudaError_t e = dmalloc(p, n); if (e == cudaSuccess) v.push_back(*p); return e; }
-	~Scoped() { for (void* p : v) cudaFree(p); }
+	explicit Scoped(cudaStream_t st) : s(st) {}
+	template <typename T> cudaError_t get(T** p, uint64_t n) { cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (n ? n : 1), s); if (e == cudaSuccess) v.push_back(*p); return e; }
+	~Scoped() { for (void* p : v) cudaFreeAsync(p, s); }
 };
 
 static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t t0, uint64_t t1, const ReadStore& R, const Node* d_nodes, const CandView* d_cviews,
@@ -590,7 +592,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	cudaStream_t s = c->stream;
 	const uint64_t nt = t1 - t0;
 	if (!nt) return CLB_OK;
-	Scoped mem;
+	Scoped mem(s);
 	uint32_t* d_bin_of = nullptr; uint32_t* d_list = nullptr;
 	CLB_CUDA(c, mem.get(&d_bin_of, nt));
 	CLB_CUDA(c, mem.get(&d_list, nt));
@@ -608,7 +610,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	CLB_TIMED(c, K_ENCODE, (k_task_scatter<<<blocks, 256, 0, s>>>(t0, t1, d_bin_of, d_bins, d_list)));
 	CLB_LAUNCH_CHECK(c, "k_task_scatter");
 	const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
-	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 8ull << 30;
+	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 16ull << 30;
 	const bool bin_prof = std::getenv("CLB_ALIGN_PROFILE") != nullptr;
 	// bins run concurrently on a few streams (each with its own slice of the scratch) so that the tail of one bin
 	// overlaps the bulk of another; the per-bin profile serialises them on the main stream instead
@@ -631,10 +633,11 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	prof_begin(c, K_ALIGN);
 	CLB_CUDA(c, cudaEventRecord(c->s2_fork, s));
 	for (int i = 0; i < n_str && !bin_prof; ++i) CLB_CUDA(c, cudaStreamWaitEvent(c->s2_streams[i], c->s2_fork, 0));
-	// heavy bins first
+	// bins with the longest single parts first: a part is one warp's serial work, so the level ends no earlier than its
+	// longest part; the bulk bins fill the machine next to them
 	std::vector<int> order;
 	for (int b = 0; b < N_BINS; ++b) if (hb.cnt[b]) order.push_back(b);
-	std::sort(order.begin(), order.end(), [&](int x, int y) { return (double)hb.cnt[x] * hb.maxq[x] * hb.maxt[x] > (double)hb.cnt[y] * hb.maxq[y] * hb.maxt[y]; });
+	std::sort(order.begin(), order.end(), [&](int x, int y) { return (double)hb.maxq[x] * hb.maxt[x] > (double)hb.maxq[y] * hb.maxt[y]; });
 	int rr = 0;
 	for (int b : order) {
 		if (bin_prof) cudaEventRecord(pe0, s);
@@ -712,7 +715,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	cudaStream_t s = c->stream;
 	const uint32_t lo = pack_first[pack_lo], hi = pack_first[pack_hi], nr = hi - lo;
 	if (!nr) return CLB_OK;
-	Scoped mem;
+	Scoped mem(s);
 	Trace tr(s);
 	const ReadStore R{c->pk.p, c->rd_start.p, c->rd_len.p, c->nmask.p, c->d_ref_to_read};
 	// reads that go through the anchor search
@@ -728,8 +731,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data() + pack_lo, sizeof(uint32_t) * (pack_hi - pack_lo + 1), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * (nb ? nb : 1), s));
 
-	DevBuf<Node> nodes; DevBuf<CandView> cviews; DevBuf<Task> tasks; DevBuf<char> esbuf;
-	struct Rel { DevBuf<Node>& a; DevBuf<CandView>& b; DevBuf<Task>& t; DevBuf<char>& e; ~Rel() { a.release(); b.release(); t.release(); e.release(); } } rel{nodes, cviews, tasks, esbuf};
+	DevBuf<Node>& nodes = c->s2_nodes; DevBuf<CandView>& cviews = c->s2_cviews; DevBuf<Task>& tasks = c->s2_tasks; DevBuf<char>& esbuf = c->s2_esbuf;
 	uint64_t n_nodes = nb, n_tasks = 0, es_used = 0;
 	CLB_CUDA(c, nodes.reserve(std::max<uint64_t>(nb, 1), s, false));
 	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>((uint64_t)nb * P.c, 1), s, false));
@@ -743,7 +745,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	for (uint32_t level = 0; n0 < n_nodes; ++level) {
 		const uint64_t n1 = n_nodes, nn = n1 - n0;
 		uint32_t* d_cnt = nullptr; uint32_t* d_capu = nullptr; uint64_t* d_toff = nullptr; uint64_t* d_coff = nullptr;
-		Scoped lvl;
+		Scoped lvl(s);
 		CLB_CUDA(c, lvl.get(&d_cnt, nn)); CLB_CUDA(c, lvl.get(&d_capu, nn)); CLB_CUDA(c, lvl.get(&d_toff, nn)); CLB_CUDA(c, lvl.get(&d_coff, nn));
 		const uint32_t nblk = (uint32_t)((nn + 127) / 128);
 		CLB_TIMED(c, K_ENCODE, (k_tasks<false><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, d_cnt, d_capu, nullptr, nullptr, 0, 0, nullptr)));
@@ -859,7 +861,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	c->es_total = 0;
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
 	const char* env_batch = std::getenv("CLB_BATCH_MBASES");
-	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 256) << 20;
+	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 1024) << 20;
 	tr.mark("encode: setup");
 	for (uint32_t p = 0; p < np;) {
 		uint32_t q = p + 1;
@@ -872,7 +874,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	}
 	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	c->s2_arena.release(); c->s2_scratch.release();
+	c->s2_arena.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	tr.mark("encode: release");
 	c->enc_done = true;
 	return CLB_OK;
@@ -880,10 +882,10 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 
 void s2_free(clb_ctx* c)
 {
-	for (int i = 0; i < 4; ++i) { if (c->s2_streams[i]) cudaStreamDestroy(c->s2_streams[i]); if (c->s2_join[i]) cudaEventDestroy(c->s2_join[i]); c->s2_streams[i] = nullptr; c->s2_join[i] = nullptr; }
+	for (int i = 0; i < 16; ++i) { if (c->s2_streams[i]) cudaStreamDestroy(c->s2_streams[i]); if (c->s2_join[i]) cudaEventDestroy(c->s2_join[i]); c->s2_streams[i] = nullptr; c->s2_join[i] = nullptr; }
 	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
 	c->s2_fork = nullptr;
-	c->es.release(); c->s2_arena.release(); c->s2_scratch.release();
+	c->es.release(); c->s2_arena.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	if (c->es_off) cudaFree(c->es_off);
 	if (c->d_ref_to_read) cudaFree(c->d_ref_to_read);
 	c->es_off = nullptr; c->d_ref_to_read = nullptr;
