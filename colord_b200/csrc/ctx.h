@@ -122,6 +122,7 @@ struct clb_ctx {
 	uint64_t es_total = 0;
 	uint32_t* d_ref_to_read = nullptr;
 	clb::DevBuf<uint8_t> s2_arena;   // pair / anchor arena of the current batch
+	clb::DevBuf<uint8_t> s2_store;   // anchors of the chosen candidates of all reads
 	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current waves
 	clb::DevBuf<clb::Node> s2_nodes; clb::DevBuf<clb::CandView> s2_cviews;   // batch state, kept across batches (no per-batch malloc)
 	clb::DevBuf<clb::Task> s2_tasks; clb::DevBuf<char> s2_esbuf;

@@ -89,13 +89,13 @@ __global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes
 	if (!FILL) { cnt[id - n0] = N.n_anch + 1; capu[id - n0] = (uint32_t)(cap_sum / 4); }
 }
 
-// bins: lane-group class (1/2/4/8 lanes: rows within a factor of two) x log2(columns); the 32-lane class, whose row count is
+// bins: lane-group class (1/2/4/8/16 lanes: rows within a factor of two) x log2(columns); the 32-lane class, whose row count is
 // open-ended, is split by log2(rows) as well so that the parts of one launch cost about the same
-constexpr int N_TBIN = 16, N_QBIN = 8, N_BINS = N_TBIN * 4 + N_TBIN * N_QBIN;
+constexpr int N_TBIN = 16, N_QBIN = 8, N_SMALL = 5, N_BINS = N_TBIN * N_SMALL + N_TBIN * N_QBIN;
 constexpr int N_ALIGN_STREAMS = 16;
 struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; unsigned long long sumq[N_BINS], sumt[N_BINS], sumqt[N_BINS]; };
 
-CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : 4; }
+CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : B <= 16 ? 4 : 5; }
 CLB_HD int ilog2_u32(uint32_t x) { int r = 0; while (x >>= 1) ++r; return r; }
 
 // Parts with an empty side need no alignment (edit_script.h:247-266): el == 0 -> 'D' x rl (kept as `lead`), rl == 0 -> the
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks,
 	long long q, tt;
 	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
 	const int gc = gclass_of(q), tb = min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
-	const int b = gc < 4 ? gc * N_TBIN + tb : 4 * N_TBIN + min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 9)) * N_TBIN + tb;
+	const int b = gc < N_SMALL ? gc * N_TBIN + tb : N_SMALL * N_TBIN + min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 10)) * N_TBIN + tb;
 	bin_of[t - t0] = (uint32_t)b;
 	atomicAdd(&bins->cnt[b], 1u);
 	atomicMax(&bins->maxq[b], (unsigned int)q);
@@ -643,7 +643,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 		if (bin_prof) cudaEventRecord(pe0, s);
 		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
 		const uint64_t per_wave = std::max<uint64_t>(1, slice / stride);
-		const int g = b < 4 * N_TBIN ? 1 << (b / N_TBIN) : 32;
+		const int g = b < N_SMALL * N_TBIN ? 1 << (b / N_TBIN) : 32;
 		const int si = rr++ % n_str;
 		cudaStream_t ls = bin_prof ? s : c->s2_streams[si];
 		uint8_t* scratch = c->s2_scratch.p + (uint64_t)si * slice;
@@ -657,6 +657,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 			case 2: k_align<2><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
 			case 4: k_align<4><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
 			case 8: k_align<8><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
+			case 16: k_align<16><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
 			default: k_align<32><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
 			}
 			CLB_LAUNCH_CHECK(c, "k_align");
@@ -709,36 +710,88 @@ struct Trace {            // CLB_S2_TRACE=1: wall time of every phase of a batch
 	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s2] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
 };
 
-// one batch = whole read packs [pack_lo, pack_hi)
-static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& pack_first, uint32_t pack_lo, uint32_t pack_hi, const std::vector<uint32_t>& h_cand_n)
+// The anchors of the chosen candidates leave the per-batch pair arena for a compact store that lives until the tuples are out.
+__global__ void __launch_bounds__(128) k_anchor_count(const Node* __restrict__ nodes, const CandView* __restrict__ cviews, uint32_t n_slots, uint32_t c, uint32_t* __restrict__ cnt)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_slots) return;
+	uint32_t n = 0;
+	for (uint32_t k = 0; k < nodes[i].ncand; ++k) n += cviews[(size_t)i * c + k].n;
+	cnt[i] = n;
+}
+__global__ void __launch_bounds__(128) k_anchor_copy(const Node* __restrict__ nodes, CandView* __restrict__ cviews, uint32_t n_slots, uint32_t c,
+	const uint8_t* __restrict__ arena, uint8_t* __restrict__ store, const uint64_t* __restrict__ off, uint64_t base)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_slots) return;
+	uint64_t at = base + off[i];
+	for (uint32_t k = 0; k < nodes[i].ncand; ++k) {
+		CandView& v = cviews[(size_t)i * c + k];
+		const Anchor* src = reinterpret_cast<const Anchor*>(arena + v.anc);
+		Anchor* dst = reinterpret_cast<Anchor*>(store) + at;
+		for (uint32_t x = 0; x < v.n; ++x) dst[x] = src[x];
+		v.anc = at * sizeof(Anchor);
+		at += v.n;
+	}
+}
+
+// E1-E4 for the reads [lo, hi): level-0 nodes slot_base.. and their anchors in the store
+static clb_status anchor_batch(clb_ctx* c, const S2P& P, uint32_t lo, uint32_t hi, const std::vector<uint32_t>& h_cand_n, std::vector<uint32_t>& h_slot,
+	uint64_t& n_slots, uint64_t& store_used)
 {
 	cudaStream_t s = c->stream;
-	const uint32_t lo = pack_first[pack_lo], hi = pack_first[pack_hi], nr = hi - lo;
+	Scoped mem(s);
+	Trace tr(s);
+	std::vector<uint32_t> h_list;
+	for (uint32_t r = lo; r < hi; ++r) if (!c->h_has_n[r] && h_cand_n[r]) { h_slot[r] = (uint32_t)(n_slots + h_list.size()); h_list.push_back(r); }
+	const uint32_t nb = (uint32_t)h_list.size();
+	if (!nb) return CLB_OK;
+	uint32_t* d_list = nullptr; SegInfo* d_seg = nullptr; uint32_t* d_slot_dec = nullptr; unsigned long long* d_cursor = nullptr; uint32_t* d_acnt = nullptr; uint64_t* d_aoff = nullptr;
+	CLB_CUDA(c, mem.get(&d_list, nb)); CLB_CUDA(c, mem.get(&d_seg, (uint64_t)nb * P.c * 2)); CLB_CUDA(c, mem.get(&d_slot_dec, nb)); CLB_CUDA(c, mem.get(&d_cursor, 2));
+	CLB_CUDA(c, mem.get(&d_acnt, nb)); CLB_CUDA(c, mem.get(&d_aoff, nb));
+	CLB_CUDA(c, cudaMemcpyAsync(d_list, h_list.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * nb, s));
+	CLB_CUDA(c, c->s2_nodes.reserve(n_slots + nb, s, true, n_slots));
+	CLB_CUDA(c, c->s2_cviews.reserve((n_slots + nb) * P.c, s, true, n_slots * P.c));
+	Node* nodes = c->s2_nodes.p + n_slots; CandView* cviews = c->s2_cviews.p + n_slots * P.c;
+	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes, cviews, d_cursor);
+	if (st != CLB_OK) return st;
+	if (c->keep_candidates) { st = dump_candidates(c, P, h_list, nodes, cviews); if (st != CLB_OK) return st; }
+	CLB_TIMED(c, K_ANCHORS, (k_anchor_count<<<(nb + 127) / 128, 128, 0, s>>>(nodes, cviews, nb, P.c, d_acnt)));
+	CLB_LAUNCH_CHECK(c, "k_anchor_count");
+	uint64_t total = 0;
+	st = exclusive_scan(c, d_acnt, nb, d_aoff, &total); if (st != CLB_OK) return st;
+	CLB_CUDA(c, c->s2_store.reserve((store_used + total) * sizeof(Anchor) + 16, s, true, store_used * sizeof(Anchor)));
+	CLB_TIMED(c, K_ANCHORS, (k_anchor_copy<<<(nb + 127) / 128, 128, 0, s>>>(nodes, cviews, nb, P.c, c->s2_arena.p, c->s2_store.p, d_aoff, store_used)));
+	CLB_LAUNCH_CHECK(c, "k_anchor_copy");
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	n_slots += nb; store_used += total;
+	tr.mark("anchors");
+	return CLB_OK;
+}
+
+// E6-E9 over all reads at once (packs [0, np)): level waves, estimator, tuples
+static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& pack_first, const std::vector<uint32_t>& h_slot, uint64_t n_slots)
+{
+	cudaStream_t s = c->stream;
+	const uint32_t pack_lo = 0, pack_hi = (uint32_t)pack_first.size() - 1;
+	const uint32_t lo = 0, hi = (uint32_t)c->n_reads, nr = hi - lo;
 	if (!nr) return CLB_OK;
 	Scoped mem(s);
 	Trace tr(s);
 	const ReadStore R{c->pk.p, c->rd_start.p, c->rd_len.p, c->nmask.p, c->d_ref_to_read};
-	// reads that go through the anchor search
-	std::vector<uint32_t> h_list, h_slot(nr, 0xFFFFFFFFu);
-	for (uint32_t r = lo; r < hi; ++r) if (!c->h_has_n[r] && h_cand_n[r]) { h_slot[r - lo] = (uint32_t)h_list.size(); h_list.push_back(r); }
-	const uint32_t nb = (uint32_t)h_list.size();
-	uint32_t* d_list = nullptr; uint32_t* d_slot = nullptr; uint32_t* d_pack_first = nullptr;
-	SegInfo* d_seg = nullptr; uint32_t* d_slot_dec = nullptr; unsigned long long* d_cursor = nullptr; BinStats* d_bins = nullptr;
-	CLB_CUDA(c, mem.get(&d_list, nb)); CLB_CUDA(c, mem.get(&d_slot, nr)); CLB_CUDA(c, mem.get(&d_pack_first, pack_hi - pack_lo + 1));
-	CLB_CUDA(c, mem.get(&d_seg, (uint64_t)nb * P.c * 2)); CLB_CUDA(c, mem.get(&d_slot_dec, nb)); CLB_CUDA(c, mem.get(&d_cursor, 2)); CLB_CUDA(c, mem.get(&d_bins, 1));
-	CLB_CUDA(c, cudaMemcpyAsync(d_list, h_list.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, s));
+	const uint8_t* const arena = c->s2_store.p;
+	uint32_t* d_slot = nullptr; uint32_t* d_pack_first = nullptr; unsigned long long* d_cursor = nullptr; BinStats* d_bins = nullptr;
+	CLB_CUDA(c, mem.get(&d_slot, nr)); CLB_CUDA(c, mem.get(&d_pack_first, pack_hi - pack_lo + 1));
+	CLB_CUDA(c, mem.get(&d_cursor, 2)); CLB_CUDA(c, mem.get(&d_bins, 1));
 	CLB_CUDA(c, cudaMemcpyAsync(d_slot, h_slot.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data() + pack_lo, sizeof(uint32_t) * (pack_hi - pack_lo + 1), cudaMemcpyHostToDevice, s));
-	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * (nb ? nb : 1), s));
 
 	DevBuf<Node>& nodes = c->s2_nodes; DevBuf<CandView>& cviews = c->s2_cviews; DevBuf<Task>& tasks = c->s2_tasks; DevBuf<char>& esbuf = c->s2_esbuf;
-	uint64_t n_nodes = nb, n_tasks = 0, es_used = 0;
-	CLB_CUDA(c, nodes.reserve(std::max<uint64_t>(nb, 1), s, false));
-	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>((uint64_t)nb * P.c, 1), s, false));
-	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes.p, cviews.p, d_cursor);
-	if (st != CLB_OK) return st;
-	tr.mark("anchors");
-	if (c->keep_candidates) { st = dump_candidates(c, P, h_list, nodes.p, cviews.p); if (st != CLB_OK) return st; }
+	uint64_t n_nodes = n_slots, n_tasks = 0, es_used = 0;
+	CLB_CUDA(c, nodes.reserve(std::max<uint64_t>(n_nodes, 1), s, true, n_nodes));
+	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>(n_nodes * P.c, 1), s, true, n_nodes * P.c));
+	clb_status st = CLB_OK;
 
 	// ---- level waves ----
 	uint64_t n0 = 0;
@@ -748,7 +801,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 		Scoped lvl(s);
 		CLB_CUDA(c, lvl.get(&d_cnt, nn)); CLB_CUDA(c, lvl.get(&d_capu, nn)); CLB_CUDA(c, lvl.get(&d_toff, nn)); CLB_CUDA(c, lvl.get(&d_coff, nn));
 		const uint32_t nblk = (uint32_t)((nn + 127) / 128);
-		CLB_TIMED(c, K_ENCODE, (k_tasks<false><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, d_cnt, d_capu, nullptr, nullptr, 0, 0, nullptr)));
+		CLB_TIMED(c, K_ENCODE, (k_tasks<false><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, arena, d_cnt, d_capu, nullptr, nullptr, 0, 0, nullptr)));
 		CLB_LAUNCH_CHECK(c, "k_tasks<count>");
 		uint64_t nt = 0, ncap = 0;
 		st = exclusive_scan(c, d_cnt, nn, d_toff, &nt); if (st != CLB_OK) return st;
@@ -756,7 +809,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 		if (n_tasks + nt >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "more than 2^32 parts in one batch: lower CLB_BATCH_MBASES");
 		CLB_CUDA(c, tasks.reserve(n_tasks + nt, s, true, n_tasks));
 		CLB_CUDA(c, esbuf.reserve(es_used + ncap * 4 + 16, s, true, es_used));
-		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, c->s2_arena.p, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
+		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, arena, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
 		CLB_LAUNCH_CHECK(c, "k_tasks<fill>");
 		tr.mark("level: task lists");
 		st = align_level(c, P, tasks.p, n_tasks, n_tasks + nt, R, nodes.p, cviews.p, esbuf.p, d_bins);
@@ -770,7 +823,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 		unsigned int cur = (unsigned int)n_nodes;
 		CLB_CUDA(c, cudaMemcpyAsync(d_cursor, &cur, sizeof(cur), cudaMemcpyHostToDevice, s));
 		if (nt) {
-			DecideArgs da{tasks.p, n_tasks, n_tasks + nt, nodes.p, cviews.p, reinterpret_cast<unsigned int*>(d_cursor), (uint32_t)cap_nodes, c->s2_arena.p, R, esbuf.p, P};
+			DecideArgs da{tasks.p, n_tasks, n_tasks + nt, nodes.p, cviews.p, reinterpret_cast<unsigned int*>(d_cursor), (uint32_t)cap_nodes, arena, R, esbuf.p, P};
 			CLB_TIMED(c, K_DECIDE, (k_decide<<<(uint32_t)((nt + 127) / 128), 128, 0, s>>>(da)));
 			CLB_LAUNCH_CHECK(c, "k_decide");
 		}
@@ -804,7 +857,7 @@ static clb_status encode_batch(clb_ctx* c, const S2P& P, const std::vector<uint3
 	// ---- tuples ----
 	uint32_t* d_size = nullptr; uint32_t* d_kind = nullptr; uint64_t* d_off = nullptr;
 	CLB_CUDA(c, mem.get(&d_size, nr)); CLB_CUDA(c, mem.get(&d_kind, nr)); CLB_CUDA(c, mem.get(&d_off, nr));
-	EmitArgs ea{lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, cviews.p, P.c, c->s2_arena.p, esbuf.p, R, d_size, d_kind, d_off, c->es_total, nullptr, c->es_off};
+	EmitArgs ea{lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, cviews.p, P.c, arena, esbuf.p, R, d_size, d_kind, d_off, c->es_total, nullptr, c->es_off};
 	CLB_TIMED(c, K_EMIT, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit<size>");
 	uint64_t total = 0;
@@ -860,21 +913,27 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
 	c->es_total = 0;
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
+	// anchors batch by batch (the pair arena is the big transient), everything after them over all reads at once
 	const char* env_batch = std::getenv("CLB_BATCH_MBASES");
 	const uint64_t batch_bases = (env_batch ? (uint64_t)std::atoll(env_batch) : 1024) << 20;
+	std::vector<uint32_t> h_slot(n ? n : 1, 0xFFFFFFFFu);
+	uint64_t n_slots = 0, store_used = 0;
 	tr.mark("encode: setup");
-	for (uint32_t p = 0; p < np;) {
-		uint32_t q = p + 1;
-		auto bases_of = [&](uint32_t a, uint32_t b) { return c->h_rd_start[b - 1] + c->h_rd_len[b - 1] - c->h_rd_start[a]; };
-		while (q < np && bases_of(pack_first[p], pack_first[q + 1]) <= batch_bases) ++q;
-		clb_status st = encode_batch(c, P, pack_first, p, q, h_cand_n);
+	for (uint32_t lo = 0; lo < n;) {
+		uint32_t hi = lo; uint64_t bases = 0;
+		while (hi < n && (hi == lo || bases + c->h_rd_len[hi] <= batch_bases)) bases += c->h_rd_len[hi++];
+		clb_status st = anchor_batch(c, P, lo, hi, h_cand_n, h_slot, n_slots, store_used);
 		if (st != CLB_OK) return st;
-		tr.mark("encode: batch");
-		p = q;
+		lo = hi;
+	}
+	c->s2_arena.release();
+	{
+		clb_status st = encode_all(c, P, pack_first, h_slot, n_slots);
+		if (st != CLB_OK) return st;
 	}
 	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	c->s2_arena.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	tr.mark("encode: release");
 	c->enc_done = true;
 	return CLB_OK;
@@ -885,7 +944,7 @@ void s2_free(clb_ctx* c)
 	for (int i = 0; i < 16; ++i) { if (c->s2_streams[i]) cudaStreamDestroy(c->s2_streams[i]); if (c->s2_join[i]) cudaEventDestroy(c->s2_join[i]); c->s2_streams[i] = nullptr; c->s2_join[i] = nullptr; }
 	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
 	c->s2_fork = nullptr;
-	c->es.release(); c->s2_arena.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	if (c->es_off) cudaFree(c->es_off);
 	if (c->d_ref_to_read) cudaFree(c->d_ref_to_read);
 	c->es_off = nullptr; c->d_ref_to_read = nullptr;
