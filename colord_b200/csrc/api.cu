@@ -57,6 +57,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
+	c->qs.release();
 	{ cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, c->prm.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -234,6 +235,29 @@ clb_status clb_encode_candidates(clb_ctx* c, uint64_t* cand_off, uint32_t* data,
 		t += c->dbg_cand[i].size();
 	}
 	cand_off[c->dbg_cand.size()] = t;
+	return CLB_OK;
+}
+
+clb_status clb_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	if (!prm || !quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s3_qual_encode(c, prm, quals, offsets, on_device, pack_sizes, n_packs);
+}
+clb_status clb_qual_size(clb_ctx* c, uint64_t* total)
+{
+	CLB_ENTER(c);
+	if (!c->qual_done) return fail(c, CLB_ERR_STATE, "clb_qual_encode has not run");
+	*total = c->qs_total;
+	return CLB_OK;
+}
+clb_status clb_qual_get(clb_ctx* c, uint8_t* stream, uint64_t cap, int on_device)
+{
+	CLB_ENTER(c);
+	if (!c->qual_done) return fail(c, CLB_ERR_STATE, "clb_qual_encode has not run");
+	if (cap < c->qs_total) return fail(c, CLB_ERR_CAPACITY, "clb_qual_get: buffer too small");
+	CLB_CUDA(c, cudaMemcpyAsync(stream, c->qs.p, c->qs_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return CLB_OK;
 }
 

@@ -1,0 +1,322 @@
+// stage3_qual.cu — quality stream on device, the "*-avg" modes.
+//
+// What is kept from the reference (src/colord): the lossy transform and the context model —
+//   quality_coder.cpp:250-270      phred -> bin by the forward thresholds
+//   quality_coder_impl.cpp:191-249 per-read per-bin means coded as (uint32)(mean * 256) (:821-835), then one bin symbol per
+//                                  base under [previous 3 (6) symbols] + [bases i-2 .. i+1] + [match / anchor flags, level > 1]
+//   quality_coder_impl.cpp:25-76   the flags come from the read's tuples
+// so the decoder's error-diffusion reconstruction (:559-601) prints exactly what the reference prints (test/*.quan).
+// What is replaced: the reference codes the symbols with ONE adaptive range coder whose models persist over the whole file
+// (entr_qual.h:100-126) — a serial chain.  Here the models are static: pass 1 counts (context, symbol) pairs of all reads with
+// atomics, the host turns the 2^17..2^19-entry count table into 12-bit frequency tables (contexts seen fewer than 32 times
+// share a fallback table; metadata-sized work), pass 2 codes every read pack with 64 interleaved rANS lanes (32-bit state,
+// 16-bit renormalisation), one thread per lane, thousands of lanes in lockstep.  Container layout and its CPU twin + decoder:
+// oracle/stage3_qual.c (the bytes must be identical).
+#include "ctx.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace clb {
+
+constexpr uint32_t QB_LANES = 64, QB_PROB_BITS = 12, QB_M = 1u << QB_PROB_BITS, QB_L = 1u << 16, QB_MIN_CTX = 32;
+
+struct QP { uint32_t nb, level, bps, cb, cbits; uint32_t thr[4]; };
+
+struct QArgs {
+	const uint64_t* pk; const uint64_t* rd_start; const uint32_t* rd_len;
+	const uint8_t* quals; const uint64_t* qoff;         // quality bytes of read r: quals[qoff[r] .. + rd_len[r])
+	const uint8_t* flags;                               // level > 1: per base 0 / 1 (match) / 2 (anchor), same layout as quals
+	uint32_t n_reads; QP P;
+	uint32_t* avg16;                                    // n_reads x 5
+	uint32_t* hist; uint32_t* mhist;                    // 2^cbits x nb, nb x 128
+	const uint32_t* tab;                                // freq | cum << 16 per (context, symbol)
+	const uint32_t* mtab;                               // same for the means' high byte
+};
+
+CLB_D uint32_t q_bin(const QP& P, uint32_t phred) { uint32_t b = 0; while (b + 1 < P.nb && phred >= P.thr[b]) ++b; return b; }
+
+// context of position i of a read (quality_coder_impl.cpp:222-240 with :528-537 unrolled)
+CLB_D uint32_t q_context(const QArgs& a, uint64_t rs, uint32_t n, const uint8_t* q, const uint8_t* fl, uint32_t i)
+{
+	const QP& P = a.P;
+	uint32_t c = 0;
+	const uint32_t n_prev = P.cb / P.bps;
+	for (uint32_t k = n_prev; k >= 1; --k) c = (c << P.bps) | (i >= k ? q_bin(P, q[i - k] - 33u) : ((1u << P.bps) - 1));
+	uint32_t dna = 0;
+	for (int d = -2; d <= 1; ++d) { const long long j = (long long)i + d; dna = (dna << 2) | ((j >= 0 && j < (long long)n) ? base_at(a.pk, rs + (uint64_t)j) : 0u); }
+	c |= dna << P.cb;
+	if (P.level > 1) { c |= (uint32_t)(fl[i] == 1) << (P.cb + 8); c |= (uint32_t)(fl[i] == 2) << (P.cb + 9); }
+	return c;
+}
+
+// per-base flags from the tuples (quality_coder_impl.cpp:25-76); one thread per read
+__global__ void __launch_bounds__(128) k_q_flags(const uint8_t* __restrict__ es, const uint64_t* __restrict__ es_off, const uint64_t* __restrict__ qoff,
+	const uint32_t* __restrict__ rd_len, uint32_t n_reads, uint8_t* __restrict__ flags)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const uint8_t* t = es + es_off[r]; const uint64_t tn = es_off[r + 1] - es_off[r];
+	uint8_t* fl = flags + qoff[r]; const uint32_t n = rd_len[r];
+	if (!tn) return;
+	const uint32_t t0 = t[0] >> 4;
+	if (t0 == 9 || t0 == 11) return;                    // plain reads: no flags (the buffer is zeroed)
+	uint64_t p = 5; uint32_t at = 0;
+	while (p < tn) {
+		const uint32_t ty = t[p] >> 4;
+		if (ty == 4) { const uint32_t len = ((uint32_t)(t[p] & 15) << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; for (uint32_t k = 0; k < len && at < n; ++k) fl[at++] = 2; p += 4; }
+		else if (ty == 5) p += 4;
+		else if (ty == 6) p += 5;
+		else { if (ty == 2) { if (at < n) fl[at] = 1; ++at; } else if (ty == 0 || ty == 3) ++at; p += 1; }
+	}
+}
+
+// pass 1: per-read means + (context, symbol) counts; one CTA per read
+__global__ void __launch_bounds__(128) k_q_count(QArgs a)
+{
+	__shared__ unsigned long long s_sum[5]; __shared__ uint32_t s_cnt[5];
+	const uint32_t r = blockIdx.x;
+	const uint32_t n = a.rd_len[r]; const uint64_t rs = a.rd_start[r];
+	const uint8_t* q = a.quals + a.qoff[r];
+	const uint8_t* fl = a.flags ? a.flags + a.qoff[r] : nullptr;
+	if (threadIdx.x < 5) { s_sum[threadIdx.x] = 0; s_cnt[threadIdx.x] = 0; }
+	__syncthreads();
+	unsigned long long sum[5] = {0, 0, 0, 0, 0}; uint32_t cnt[5] = {0, 0, 0, 0, 0};
+	for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+		const uint32_t ph = q[i] - 33u, b = q_bin(a.P, ph);
+#pragma unroll
+		for (int k = 0; k < 5; ++k) if (b == (uint32_t)k) { sum[k] += ph; ++cnt[k]; }
+		atomicAdd(&a.hist[(size_t)q_context(a, rs, n, q, fl, i) * a.P.nb + b], 1u);
+	}
+#pragma unroll
+	for (int k = 0; k < 5; ++k) {
+		for (int d = 16; d; d >>= 1) { sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], d); cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], d); }
+		if ((threadIdx.x & 31) == 0 && cnt[k]) { atomicAdd(&s_sum[k], sum[k]); atomicAdd(&s_cnt[k], cnt[k]); }
+	}
+	__syncthreads();
+	if (threadIdx.x < a.P.nb) {
+		// quality_coder_impl.cpp:205-217: mean in double, then (uint32)(mean * 256); sums of integers are exact in either order
+		const double avg = s_cnt[threadIdx.x] ? __ddiv_rn((double)s_sum[threadIdx.x], (double)s_cnt[threadIdx.x]) : 0.0;
+		const uint32_t v = (uint32_t)__dmul_rn(avg, 256.0);
+		a.avg16[(size_t)r * 5 + threadIdx.x] = v;
+		atomicAdd(&a.mhist[threadIdx.x * 128 + ((v >> 8) & 127)], 1u);
+	}
+}
+
+CLB_D uint32_t rans_put(uint32_t x, uint32_t fc, uint16_t* w, uint32_t& nw)
+{
+	const uint32_t f = fc & 0xffffu, c = fc >> 16;
+	if ((unsigned long long)x >= ((unsigned long long)f << 20)) { w[nw++] = (uint16_t)x; x >>= 16; }
+	return ((x / f) << QB_PROB_BITS) + (x % f) + c;
+}
+
+struct QEnc {
+	const uint32_t* pack_first; uint32_t pack_lo, n_packs;     // packs of this chunk
+	const uint64_t* lane_off;                                   // first temp word of every lane of the chunk
+	uint16_t* tmp; uint32_t* lane_words; uint32_t* lane_state;
+};
+
+// pass 2: one thread per (pack, lane): its reads last to first, symbols last to first (rANS decodes in the opposite order)
+__global__ void __launch_bounds__(64) k_q_encode(QArgs a, QEnc e)
+{
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= e.n_packs * QB_LANES) return;
+	const uint32_t p = e.pack_lo + li / QB_LANES, l = li % QB_LANES;
+	const uint32_t r0 = e.pack_first[p], r1 = e.pack_first[p + 1];
+	uint16_t* w = e.tmp + e.lane_off[li]; uint32_t nw = 0;
+	uint32_t x = QB_L;
+	if (r0 + l < r1) {
+		uint32_t last = r0 + l + ((r1 - 1 - (r0 + l)) / QB_LANES) * QB_LANES;
+		for (long long r = last; r >= (long long)(r0 + l); r -= QB_LANES) {
+			const uint32_t n = a.rd_len[r]; const uint64_t rs = a.rd_start[r];
+			const uint8_t* q = a.quals + a.qoff[r];
+			const uint8_t* fl = a.flags ? a.flags + a.qoff[r] : nullptr;
+			for (uint32_t i = n; i-- > 0;) {
+				const uint32_t b = q_bin(a.P, q[i] - 33u);
+				x = rans_put(x, a.tab[(size_t)q_context(a, rs, n, q, fl, i) * a.P.nb + b], w, nw);
+			}
+			for (uint32_t b = a.P.nb; b-- > 0;) {
+				const uint32_t v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
+				x = rans_put(x, (QB_M >> 8) | ((a2 * (QB_M >> 8)) << 16), w, nw);
+				x = rans_put(x, a.mtab[b * 128 + a1], w, nw);
+			}
+		}
+	}
+	e.lane_words[li] = nw; e.lane_state[li] = x;
+}
+
+// lane streams into the final container: state, then the words in decoding order (last written first); one warp per lane
+__global__ void __launch_bounds__(128) k_q_gather(QEnc e, const uint64_t* __restrict__ dst_off, const uint64_t* __restrict__ pack_hdr_off, uint8_t* __restrict__ out)
+{
+	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (li >= e.n_packs * QB_LANES) return;
+	const uint32_t nw = e.lane_words[li];
+	uint8_t* d = out + dst_off[li];
+	const uint16_t* w = e.tmp + e.lane_off[li];
+	if (lane == 0) {
+		const uint32_t x = e.lane_state[li];
+		d[0] = (uint8_t)x; d[1] = (uint8_t)(x >> 8); d[2] = (uint8_t)(x >> 16); d[3] = (uint8_t)(x >> 24);
+		// size field in the pack header, and the pack's read count
+		const uint32_t p = li / QB_LANES, l = li % QB_LANES;
+		uint8_t* h = out + pack_hdr_off[p];
+		const uint32_t bytes = 4 + 2 * nw;
+		h[4 + 4 * l] = (uint8_t)bytes; h[5 + 4 * l] = (uint8_t)(bytes >> 8); h[6 + 4 * l] = (uint8_t)(bytes >> 16); h[7 + 4 * l] = (uint8_t)(bytes >> 24);
+		if (l == 0) { const uint32_t np = e.pack_first[e.pack_lo + p + 1] - e.pack_first[e.pack_lo + p]; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
+	}
+	for (uint32_t k = lane; k < nw; k += 32) { const uint16_t v = w[nw - 1 - k]; d[4 + 2 * k] = (uint8_t)v; d[5 + 2 * k] = (uint8_t)(v >> 8); }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
+{
+	uint64_t tot = 0; uint32_t best = 0;
+	for (uint32_t i = 0; i < n; ++i) { tot += cnt[i]; if (cnt[i] > cnt[best]) best = i; }
+	if (!tot) { for (uint32_t i = 0; i < n; ++i) f[i] = 0; return; }
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < n; ++i) { uint32_t v = (uint32_t)(((uint64_t)cnt[i] << QB_PROB_BITS) / tot); if (cnt[i] && !v) v = 1; f[i] = (uint16_t)v; sum += v; }
+	f[best] = (uint16_t)(f[best] + QB_M - sum);
+}
+template <typename T> static void put(std::vector<uint8_t>& o, const T& v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); o.insert(o.end(), p, p + sizeof(T)); }
+
+clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	cudaStream_t s = c->stream;
+	const uint64_t n = c->n_reads;
+	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_qual_encode before the reads are complete (clb_count_finalize)");
+	if (prm->n_bins != 2 && prm->n_bins != 4 && prm->n_bins != 5) return fail(c, CLB_ERR_BAD_ARG, "clb_qual_encode: the *-avg modes have 2, 4 or 5 bins");
+	if (prm->level > 1 && !c->enc_done) return fail(c, CLB_ERR_STATE, "clb_qual_encode at level > 1 needs the tuples (clb_encode) for the match / anchor flags");
+	if (c->qual_done) return fail(c, CLB_ERR_STATE, "clb_qual_encode called twice");
+	QP P{}; P.nb = prm->n_bins; P.level = prm->level; P.bps = P.nb == 2 ? 2 : 3; P.cb = P.bps * (P.nb == 2 ? 6 : 3); P.cbits = P.cb + 8 + (P.level > 1 ? 2 : 0);
+	for (int i = 0; i < 4; ++i) P.thr[i] = prm->thresholds[i];
+	const uint64_t n_ctx = 1ull << P.cbits;
+	// packs (same rule as stage 2)
+	std::vector<uint32_t> pack_first{0};
+	if (pack_sizes) {
+		uint64_t at = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) { at += pack_sizes[i]; if (pack_sizes[i]) pack_first.push_back((uint32_t)at); }
+		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
+	} else {
+		uint64_t bytes = 0;
+		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
+		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
+	}
+	const uint32_t np = (uint32_t)pack_first.size() - 1;
+	// qualities on the device
+	std::vector<uint64_t> h_off(n + 1);
+	if (on_device) CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+	else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+	const uint64_t tot = h_off[n] - h_off[0];
+	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
+	const uint8_t* d_q = nullptr; uint64_t* d_qoff = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_qoff, sizeof(uint64_t) * (n + 1)));
+	{
+		std::vector<uint64_t> rel(n + 1);
+		for (uint64_t i = 0; i <= n; ++i) rel[i] = h_off[i] - h_off[0];
+		CLB_CUDA(c, cudaMemcpyAsync(d_qoff, rel.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+	}
+	if (on_device) d_q = quals + h_off[0];
+	else { uint8_t* b = nullptr; CLB_CUDA(c, dalloc((void**)&b, tot + 16)); CLB_CUDA(c, cudaMemcpyAsync(b, quals + h_off[0], tot, cudaMemcpyHostToDevice, s)); d_q = b; }
+	uint8_t* d_flags = nullptr;
+	if (P.level > 1) {
+		CLB_CUDA(c, dalloc((void**)&d_flags, tot + 16));
+		CLB_CUDA(c, cudaMemsetAsync(d_flags, 0, tot + 16, s));
+		if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(c->es.p, c->es_off, d_qoff, c->rd_len.p, (uint32_t)n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
+	}
+	QArgs a{};
+	a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.n_reads = (uint32_t)n; a.P = P;
+	uint32_t* d_avg = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_mhist = nullptr; uint32_t* d_tab = nullptr; uint32_t* d_mtab = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_avg, sizeof(uint32_t) * 5 * (n + 1)));
+	CLB_CUDA(c, dalloc((void**)&d_hist, sizeof(uint32_t) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mhist, sizeof(uint32_t) * 5 * 128));
+	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint32_t) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mtab, sizeof(uint32_t) * 5 * 128));
+	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * n_ctx * P.nb, s)); CLB_CUDA(c, cudaMemsetAsync(d_mhist, 0, sizeof(uint32_t) * 5 * 128, s));
+	a.avg16 = d_avg; a.hist = d_hist; a.mhist = d_mhist;
+	if (n) { CLB_TIMED(c, K_QUAL, (k_q_count<<<(uint32_t)n, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_q_count"); }
+	// ---- count table -> frequency tables + the container's header (metadata-sized, on the host) ----
+	std::vector<uint32_t> hist(n_ctx * P.nb), mh(5 * 128);
+	CLB_CUDA(c, cudaMemcpyAsync(hist.data(), d_hist, sizeof(uint32_t) * hist.size(), cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaMemcpyAsync(mh.data(), d_mhist, sizeof(uint32_t) * mh.size(), cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	const uint32_t nb = P.nb, n_fb = 1u << P.cb;
+	std::vector<uint32_t> fbh((size_t)n_fb * nb, 0); std::vector<uint8_t> dense(n_ctx, 0);
+	for (uint64_t x = 0; x < n_ctx; ++x) {
+		uint64_t t = 0; for (uint32_t k = 0; k < nb; ++k) t += hist[x * nb + k];
+		if (t >= QB_MIN_CTX) dense[x] = 1; else for (uint32_t k = 0; k < nb; ++k) fbh[(x & (n_fb - 1)) * nb + k] += hist[x * nb + k];
+	}
+	std::vector<uint16_t> freq(n_ctx * nb), fbf((size_t)n_fb * nb), mf(5 * 128, 0);
+	for (uint32_t x = 0; x < n_fb; ++x) normalise(&fbh[(size_t)x * nb], nb, &fbf[(size_t)x * nb]);
+	std::vector<uint32_t> tab(n_ctx * nb), mtab(5 * 128, 0);
+	for (uint64_t x = 0; x < n_ctx; ++x) {
+		if (dense[x]) normalise(&hist[x * nb], nb, &freq[x * nb]); else std::memcpy(&freq[x * nb], &fbf[(x & (n_fb - 1)) * nb], 2 * nb);
+		uint32_t acc = 0; for (uint32_t k = 0; k < nb; ++k) { tab[x * nb + k] = freq[x * nb + k] | (acc << 16); acc += freq[x * nb + k]; }
+	}
+	for (uint32_t b = 0; b < nb; ++b) { normalise(&mh[b * 128], 128, &mf[b * 128]); uint32_t acc = 0; for (uint32_t k = 0; k < 128; ++k) { mtab[b * 128 + k] = mf[b * 128 + k] | (acc << 16); acc += mf[b * 128 + k]; } }
+	std::vector<uint8_t> hdr;
+	hdr.insert(hdr.end(), {'Q', 'B', '0', '1'}); put(hdr, nb); put(hdr, P.level); for (int i = 0; i < 4; ++i) put(hdr, P.thr[i]); put(hdr, (uint64_t)n); put(hdr, np); put(hdr, P.cbits);
+	for (uint32_t i = 0; i < nb * 128; ++i) put(hdr, mf[i]);
+	for (uint32_t x = 0; x < n_fb; ++x) for (uint32_t k = 0; k + 1 < nb; ++k) put(hdr, fbf[(size_t)x * nb + k]);
+	{
+		uint32_t nd = 0; for (uint64_t x = 0; x < n_ctx; ++x) nd += dense[x];
+		put(hdr, nd);
+		uint64_t prev = 0;
+		for (uint64_t x = 0; x < n_ctx; ++x) if (dense[x]) {
+			uint64_t gap = x - prev; prev = x;
+			do { uint8_t by = (uint8_t)(gap & 127); gap >>= 7; if (gap) by |= 128; hdr.push_back(by); } while (gap);
+			for (uint32_t k = 0; k + 1 < nb; ++k) put(hdr, freq[x * nb + k]);
+		}
+	}
+	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_mtab, mtab.data(), sizeof(uint32_t) * mtab.size(), cudaMemcpyHostToDevice, s));
+	a.tab = d_tab; a.mtab = d_mtab;
+	// ---- pass 2 in chunks of packs (the temp holds one 16-bit word per symbol at worst) ----
+	uint32_t* d_pack_first = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_pack_first, sizeof(uint32_t) * (np + 1)));
+	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, c->qs.reserve(hdr.size() + tot / 3 + (uint64_t)np * (4 + 4 * QB_LANES + 4 * QB_LANES) + 1024, s, false));
+	CLB_CUDA(c, cudaMemcpyAsync(c->qs.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
+	uint64_t out_at = hdr.size();
+	const uint64_t chunk_syms = 1ull << 31;
+	for (uint32_t p0 = 0; p0 < np;) {
+		uint32_t p1 = p0; uint64_t syms = 0;
+		while (p1 < np && (p1 == p0 || syms + (h_off[pack_first[p1 + 1]] - h_off[pack_first[p1]]) <= chunk_syms)) { syms += h_off[pack_first[p1 + 1]] - h_off[pack_first[p1]] + 2ull * nb * (pack_first[p1 + 1] - pack_first[p1]); ++p1; }
+		const uint32_t cp = p1 - p0, nl = cp * QB_LANES;
+		std::vector<uint64_t> lane_off(nl + 1, 0);
+		for (uint32_t p = p0; p < p1; ++p)
+			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * QB_LANES + (r - pack_first[p]) % QB_LANES + 1] += c->h_rd_len[r] + 2ull * nb;
+		for (uint32_t i = 0; i < nl; ++i) lane_off[i + 1] += lane_off[i];
+		uint64_t* d_lane_off = nullptr; uint16_t* d_tmp = nullptr; uint32_t* d_words = nullptr; uint32_t* d_state = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
+		Tmp ct{{}, s};
+		auto calloc_ = [&](void** q, uint64_t bytes) { cudaError_t e = cudaMallocAsync(q, bytes ? bytes : 1, s); if (e == cudaSuccess) ct.v.push_back(*q); return e; };
+		CLB_CUDA(c, calloc_((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1))); CLB_CUDA(c, calloc_((void**)&d_tmp, sizeof(uint16_t) * (lane_off[nl] + 8)));
+		CLB_CUDA(c, calloc_((void**)&d_words, sizeof(uint32_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_state, sizeof(uint32_t) * nl));
+		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
+		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
+		QEnc e{d_pack_first, p0, cp, d_lane_off, d_tmp, d_words, d_state};
+		CLB_TIMED(c, K_QUAL, (k_q_encode<<<(nl + 63) / 64, 64, 0, s>>>(a, e)));
+		CLB_LAUNCH_CHECK(c, "k_q_encode");
+		std::vector<uint32_t> words(nl);
+		CLB_CUDA(c, cudaMemcpyAsync(words.data(), d_words, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		std::vector<uint64_t> dst(nl), phdr(cp);
+		for (uint32_t p = 0; p < cp; ++p) {
+			phdr[p] = out_at; out_at += 4 + 4 * QB_LANES;
+			for (uint32_t l = 0; l < QB_LANES; ++l) { dst[(size_t)p * QB_LANES + l] = out_at; out_at += 4 + 2ull * words[(size_t)p * QB_LANES + l]; }
+		}
+		CLB_CUDA(c, c->qs.reserve(out_at + 16, s, true, phdr[0]));
+		CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
+		CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * cp, cudaMemcpyHostToDevice, s));
+		CLB_TIMED(c, K_QUAL, (k_q_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(e, d_dst, d_phdr, c->qs.p)));
+		CLB_LAUNCH_CHECK(c, "k_q_gather");
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		p0 = p1;
+	}
+	c->qs_total = out_at;
+	c->qual_done = true;
+	return CLB_OK;
+}
+
+} // namespace clb

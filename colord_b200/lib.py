@@ -17,8 +17,9 @@ EXPORTS = [
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
+    "clb_qual_encode", "clb_qual_size", "clb_qual_get",
 ]
-KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit"]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual"]
 
 
 class Params(C.Structure):
@@ -37,6 +38,10 @@ class KmerStats(C.Structure):
 class EncodeParams(C.Structure):
     _fields_ = [("anchor_len", C.c_uint32), ("min_part_len_alt", C.c_uint32), ("max_recurence", C.c_uint32), ("min_anchors", C.c_uint32),
                 ("min_mmer_frac", C.c_double), ("min_mmer_force", C.c_double), ("max_matches_mult", C.c_double), ("es_cost_mult", C.c_double)]
+
+
+class QualParams(C.Structure):
+    _fields_ = [("n_bins", C.c_uint32), ("thresholds", C.c_uint32 * 4), ("level", C.c_uint32)]
 
 
 class ClbError(RuntimeError):
@@ -88,6 +93,9 @@ def load():
     L.clb_encode_keep_candidates.argtypes = [vp, i32]
     L.clb_encode_candidates_size.argtypes = [vp, C.POINTER(u64)]
     L.clb_encode_candidates.argtypes = [vp, vp, vp, u64]
+    L.clb_qual_encode.argtypes = [vp, C.POINTER(QualParams), vp, vp, i32, vp, u32]
+    L.clb_qual_size.argtypes = [vp, C.POINTER(u64)]
+    L.clb_qual_get.argtypes = [vp, vp, u64, i32]
     L.clb_profile_enable.argtypes = [vp, i32]
     L.clb_profile_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     for name in EXPORTS:
@@ -335,6 +343,32 @@ class Context:
                 p += 3 * na
             out.append(rec)
         return out
+
+    # ---- stage 3
+    def qual_encode(self, n_bins, thresholds, level, quals, offsets, pack_sizes=None, on_device=False):
+        """Quality stream of all appended reads (native container QB01).  quals/offsets: numpy arrays, or device pointers (ints)."""
+        prm = QualParams()
+        prm.n_bins, prm.level = n_bins, level
+        for i, t in enumerate(thresholds):
+            prm.thresholds[i] = t
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        if on_device:
+            qp, op = C.c_void_p(quals), C.c_void_p(offsets)
+        else:
+            q = np.ascontiguousarray(quals, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
+            qp, op = _np_ptr(q), _np_ptr(o)
+        self._ck(self.L.clb_qual_encode(self.h, C.byref(prm), qp, op, int(on_device), None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+
+    def qual_size(self):
+        n = C.c_uint64()
+        self._ck(self.L.clb_qual_size(self.h, C.byref(n)))
+        return n.value
+
+    def qual_stream(self):
+        n = self.qual_size()
+        out = np.zeros(max(n, 1), np.uint8)
+        self._ck(self.L.clb_qual_get(self.h, _np_ptr(out), n, 0))
+        return out[:n]
 
     def profile_enable(self, on=True):
         self._ck(self.L.clb_profile_enable(self.h, int(on)))

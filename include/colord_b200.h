@@ -147,6 +147,26 @@ clb_status clb_encode_keep_candidates(clb_ctx* ctx, int on);
 clb_status clb_encode_candidates_size(clb_ctx* ctx, uint64_t* n_words);
 clb_status clb_encode_candidates(clb_ctx* ctx, uint64_t* cand_off, uint32_t* data, uint64_t cap_words);
 
+/* ---- Stage 3: quality stream ------------------------------------------------------------------------
+ * Replaces CEntrComprQuals::Compress -> CQualityCoder::Encode (entr_qual.h:100-126, quality_coder.cpp:560) for the "*-avg"
+ * modes (ONT default 4-avg, HiFi default 5-avg, 2-avg): the reference's lossy transform and context model
+ * (quality_coder_impl.cpp:130-310: bins by the forward thresholds, per-read per-bin means, one bin symbol per base under the
+ * previous symbols + neighbouring bases [+ match / anchor flags from the tuples when level > 1]) are kept, so the qualities a
+ * decoder reconstructs are the reference's (test/<name>.quan).  The reference's single adaptive range-coder chain is replaced
+ * by static per-context tables + 64 interleaved rANS lanes per read pack (native container "QB01"; layout, CPU twin and
+ * decoder in oracle/stage3_qual.c; SURVEY.md §7 explains why the reference's byte stream cannot be produced in lockstep). */
+typedef struct {
+	uint32_t n_bins;                /* 2, 4 or 5 (QualityComprMode Binary/Quad/QuinaryAverage, params.h:37)             */
+	uint32_t thresholds[4];         /* qualityFwdThresholds (-T): bin = number of thresholds <= phred; n_bins - 1 used  */
+	uint32_t level;                 /* compressionLevel: > 1 puts the match / anchor flags in the context (needs clb_encode) */
+} clb_qual_params;
+/* quals: phred+33 bytes of all appended reads, read r at quals[offsets[r] .. offsets[r+1]) with the reads' lengths
+ * (device pointers iff on_device).  pack_sizes as for clb_encode (NULL: the reference's pack rule).  Result stays on the device. */
+clb_status clb_qual_encode(clb_ctx* ctx, const clb_qual_params* params, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status clb_qual_size(clb_ctx* ctx, uint64_t* total_bytes);
+clb_status clb_qual_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
+
 /* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
  * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
  * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
@@ -162,7 +182,7 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
 /* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
  * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
- * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit.  clb_profile_get synchronizes the stream. */
+ * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit, k_qual.  clb_profile_get synchronizes the stream. */
 clb_status clb_profile_enable(clb_ctx* ctx, int on);
 clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 

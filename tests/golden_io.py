@@ -48,3 +48,21 @@ def load_edit_scripts():
         enc = np.frombuffer(raw, np.uint8, el, pos).copy(); pos += el
         out.append((kind, ref, enc, rt, et, raw[pos:pos + sn])); pos += sn
     return out
+
+
+def load_qual_golden(name):
+    """-> (bases u8 ASCII, quals u8, expected lossy quals u8, offsets u64) from tests/golden/qual_<name>.bin.gz."""
+    import gzip
+    import struct
+    with gzip.open(os.path.join(GOLDEN, f"qual_{name}.bin.gz"), "rb") as f:
+        raw = f.read()
+    (n,) = struct.unpack_from("<I", raw, 0)
+    lens = np.frombuffer(raw, np.uint32, n, 4)
+    tot = int(lens.sum())
+    p = 4 + 4 * n
+    bases = np.frombuffer(raw, np.uint8, tot, p).copy()
+    quals = np.frombuffer(raw, np.uint8, tot, p + tot).copy()
+    quan = np.frombuffer(raw, np.uint8, tot, p + 2 * tot).copy()
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    return bases, quals, quan, off

@@ -170,3 +170,54 @@ def candidates(bases, offsets, is_ref, cand, cand_n, params):
             p += 3 * na
         out.append(rec)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------- stage 3: quality
+class QualParams(C.Structure):
+    _fields_ = [("n_bins", C.c_uint32), ("thr", C.c_uint32 * 4), ("level", C.c_uint32)]
+
+
+def qual_params(n_bins, thr, level):
+    p = QualParams()
+    p.n_bins, p.level = n_bins, level
+    for i, t in enumerate(thr):
+        p.thr[i] = t
+    return p
+
+
+def qual_lossy(P, bases, quals, offsets):
+    """The reference's lossy quality transform (what `colord decompress` prints) — oracle/stage3_qual.c."""
+    L = lib()
+    L.orc_qual_lossy.restype = None
+    L.orc_qual_lossy.argtypes = [C.POINTER(QualParams), _u8p, _u8p, _u64p, C.c_uint32, _u8p]
+    out = np.zeros(len(quals), np.uint8)
+    L.orc_qual_lossy(C.byref(P), np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(quals, np.uint8), np.ascontiguousarray(offsets, np.uint64), len(offsets) - 1, out)
+    return out
+
+
+def qual_encode(P, bases, quals, offsets, pack_sizes, es=None, es_off=None):
+    L = lib()
+    L.orc_qual_encode.restype = C.c_uint64
+    L.orc_qual_encode.argtypes = [C.POINTER(QualParams), _u8p, _u8p, _u64p, C.c_uint32, C.c_void_p, C.c_void_p, _u32p, C.c_uint32, _u8p, C.c_uint64]
+    cap = int(len(quals)) + (1 << 20) + (8 << (P.level > 1 and 21 or 19))
+    out = np.zeros(cap, np.uint8)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    esp = es.ctypes.data if es is not None else None
+    eop = es_off.ctypes.data if es_off is not None else None
+    n = L.orc_qual_encode(C.byref(P), np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(quals, np.uint8), np.ascontiguousarray(offsets, np.uint64),
+                          len(offsets) - 1, esp, eop, ps, len(ps), out, cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def qual_decode(stream, bases, offsets, es=None, es_off=None):
+    L = lib()
+    L.orc_qual_decode.restype = C.c_int
+    L.orc_qual_decode.argtypes = [_u8p, C.c_uint64, _u8p, _u64p, C.c_uint32, C.c_void_p, C.c_void_p, _u8p]
+    out = np.zeros(int(offsets[-1]), np.uint8)
+    esp = es.ctypes.data if es is not None else None
+    eop = es_off.ctypes.data if es_off is not None else None
+    rc = L.orc_qual_decode(np.ascontiguousarray(stream, np.uint8), len(stream), np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(offsets, np.uint64),
+                           len(offsets) - 1, esp, eop, out)
+    assert rc == 0, rc
+    return out
