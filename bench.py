@@ -5,8 +5,9 @@ One "step" = one pass of the hot path built so far over the whole synthetic ONT 
 canonical k-mer scan + murmur64 % f filter + count table, thresholding into the filtered set, accepted k-mers per
 read, similarity graph with top-c candidates) and STAGE 2 (m-mer anchors against the candidates, edit scripts of the
 parts between anchors, edit-script / plain / alternative-read decisions, CompactES tuples).  Stage 3 (entropy coders) is
-not on the device yet; `config.stages` says so and the reference arm times the SAME stages of the reference
-(`--stages 1` restricts both arms to stage 1).
+represented by its quality stream (the reference's lossy 4-avg transform + context model, static tables, interleaved rANS;
+the DNA-tuple and header coders are not on the device yet); `config.stages` says so and the reference arm times the SAME
+stages of the reference (`--stages 1` / `--stages 12` restrict both arms).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--gbases G] [--impl reference]
 
@@ -184,7 +185,7 @@ def cpu_baseline(sample_reads=12500, stages="12"):
         desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
             r = run_reference_stage1(fq, cores, stages)
-            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + ("+CEncoder threads (stages 1+2)" if stages == "12" else " (stage 1 only)")
+            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
             return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
                     "sample": desc + "; unmodified reference " + what, "detail": r}
         dt = run_port_stage1(s)
@@ -220,15 +221,18 @@ def main_reference(args):
 
 
 def metric_name(args):
-    return "input MB/s, compress-ont default, " + ("stages 1+2 (k-mer filter, similarity graph, anchors + edit scripts -> tuples)" if args.stages == "12"
-                                                   else "stage 1 (k-mer filter + similarity graph)")
+    return "input MB/s, compress-ont default, " + {
+        "12q": "stages 1+2 + quality stream of stage 3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, 4-avg quality coder)",
+        "12": "stages 1+2 (k-mer filter, similarity graph, anchors + edit scripts -> tuples)",
+        "1": "stage 1 (k-mer filter + similarity graph)"}[args.stages]
 
 
 def workload_config(args, n_reads):
     return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
                         f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] * args.gbases / 25.0 / 1e9:.3g} Gb = 20.8x, 10% errors)",
-            "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1); stage 3 not on device yet" % NS_S2["anchor_len"])
-                      if args.stages == "12" else "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph)",
+            "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1)" % NS_S2["anchor_len"]
+                       + ("; stage 3: quality stream (4-avg, thresholds 7 14 26) only — DNA-tuple and header coders not on device yet" if args.stages == "12q" else "; stage 3 not included"))
+                      if args.stages != "1" else "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph)",
             "n_reads": n_reads, "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"reads sharded by id over {args.gpus} GPU(s)"}
 
 
@@ -239,7 +243,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
-    ap.add_argument("--stages", default="12", choices=["1", "12"], help="hot-path stages inside a step (both arms)")
+    ap.add_argument("--stages", default="12q", choices=["1", "12", "12q"], help="hot-path stages inside a step (both arms); q = quality stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -272,6 +276,15 @@ def main():
     bases, offsets = gen_reads(torch, device, genome, lo, hi, seed=99)
     del genome
     torch.cuda.empty_cache()
+    quals = None
+    if args.stages == "12q":      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
+        quals = torch.empty(bases.numel(), dtype=torch.uint8, device=device)
+        gq = torch.Generator(device=device)
+        gq.manual_seed(4242 + rank)
+        for q0 in range(0, bases.numel(), 1 << 28):
+            q1 = min(bases.numel(), q0 + (1 << 28))
+            quals[q0:q1] = (torch.randn(q1 - q0, device=device, generator=gq) * 5 + 12).round_().clamp_(1, 40).to(torch.uint8) + 33
+        torch.cuda.empty_cache()
     n_local = hi - lo
     n_bases_local = int(bases.numel())
     off_u64 = offsets.contiguous()
@@ -284,7 +297,7 @@ def main():
     stream = torch.cuda.Stream(device=device)
     peak, peak_src = measured_peak_hbm()
 
-    def one_step(host_bases=None, host_offsets=None, profile=False, readback=False):
+    def one_step(host_bases=None, host_offsets=None, host_quals=None, profile=False, readback=False):
         ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], expected_bases=n_bases_local, device=local_rank)
         ctx.set_stream(stream.cuda_stream)
         if profile:
@@ -299,11 +312,18 @@ def main():
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
         ctx.graph_build(sampled)
         out = None
-        if args.stages == "12":
+        if args.stages in ("12", "12q"):
             ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
-            if readback:           # the tuples are what leaves stage 2 (they feed the entropy coders)
+            if args.stages == "12q":
+                if host_quals is None:
+                    ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
+                else:
+                    ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
+            if readback:           # what leaves the device: the tuples (they feed the DNA entropy coder) and the finished quality stream
                 out = ctx.encoded(n_local)
+                if args.stages == "12q":
+                    out = out + (ctx.qual_stream(),)
         elif readback:
             out = ctx.graph_candidates()
         ctx.synchronize()
@@ -347,32 +367,43 @@ def main():
         host_bases.copy_(bases)
         host_off = offsets.cpu().numpy().astype(np.uint64)
         hb = host_bases.numpy()
-        e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, readback=True)
-        d2h = int(out[0].nbytes + out[1].nbytes)
+        hq = None
+        if quals is not None:
+            host_quals = torch.empty(n_bases_local, dtype=torch.uint8, pin_memory=True)
+            host_quals.copy_(quals)
+            hq = host_quals.numpy()
+        e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, host_quals=hq, readback=True)
+        d2h = int(sum(x.nbytes for x in out))
         e2e = {"value": job_bytes / (e_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(n_bases_local + host_off.nbytes), "d2h_bytes_per_step": d2h, "host_memory": "pinned"}
+               "h2d_bytes_per_step": int(n_bases_local * (2 if hq is not None else 1) + host_off.nbytes), "d2h_bytes_per_step": d2h, "host_memory": "pinned"}
         del host_bases, hb
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        # roofline of the dominant kernel (k_count): algorithmic bytes per launch / mean launch time
-        kc_ms, kc_n = prof.get("k_count", (0.0, 0))
-        alg_per_base = 0.5 + 16.0 / p["modulo"]           # packed + 2 masks read, one 8 B key+count RMW per passing k-mer
+        # roofline of the dominant kernel class of the step: ALGORITHMIC bytes / device time
+        alg = {"k_count": 0.5 + 16.0 / p["modulo"],                    # packed + 2 masks read, one 8 B key+count RMW per passing k-mer
+               "k_accept": 0.5 + 12.0 / p["modulo"],
+               "k_anchors": 0.25 * (1 + 2 * p["max_candidates"]),      # the read + both strands of c candidates, 2-bit packed
+               "k_align": 0.25 + 0.25 + 1.0,                           # the two parts (2-bit) read, one script byte written per symbol
+               "k_decide": 1.0, "k_emit": 1.0 + 1.25,                  # scripts read, CompactES bytes written
+               "k_qual": 2 * (1.0 + 0.25) + 0.25}                      # two passes over qualities + packed bases, stream written
+        per_step = {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}
         roof = None
-        if kc_n:
-            per_launch_bytes = alg_per_base * n_bases_local * args.steps / kc_n
-            per_launch_ms = kc_ms / kc_n
-            achieved = per_launch_bytes / (per_launch_ms / 1e3) / 1e9
+        if per_step:
+            top = max((k for k in per_step if k in alg), key=lambda k: per_step[k])
+            k_ms, k_n = prof[top]
+            achieved = alg[top] * n_bases_local / (per_step[top] / 1e3) / 1e9
             traffic = None
             try:      # DRAM bytes per launch of this kernel from the committed ncu --set full capture
-                with open(os.path.join(ROOT, "profiles", "k_count_traffic.json")) as f:
-                    traffic = json.load(f)["traffic_bytes_per_launch"]
+                with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+                    traffic = json.load(f)[top]["traffic_bytes_per_launch"]
             except Exception:
                 pass
-            roof = {"kernel": "k_count", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "launches": kc_n // max(1, args.steps), "ms_per_launch": per_launch_ms,
-                    "algorithmic_bytes_per_base": alg_per_base,
-                    "kernel_ms_per_step": {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}}
+            roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "launches": k_n // max(1, args.steps), "ms_per_launch": k_ms / max(1, k_n),
+                    "algorithmic_bytes_per_base": alg[top],
+                    "note": "k_align is bound by the dependent-issue latency of the bit-vector recurrence, not by HBM (profiles/r01_summary.md)" if top == "k_align" else None,
+                    "kernel_ms_per_step": per_step}
         line = {
             "metric": metric_name(args), "value": value, "unit": "MB/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",

@@ -9,17 +9,20 @@
 // What is replaced: the reference codes the symbols with ONE adaptive range coder whose models persist over the whole file
 // (entr_qual.h:100-126) — a serial chain.  Here the models are static: pass 1 counts (context, symbol) pairs of all reads with
 // atomics, the host turns the 2^17..2^19-entry count table into 12-bit frequency tables (contexts seen fewer than 32 times
-// share a fallback table; metadata-sized work), pass 2 codes every read pack with 64 interleaved rANS lanes (32-bit state,
+// share a fallback table; metadata-sized work), pass 2 codes every read pack with 64 interleaved rANS lanes (31-bit state,
 // 16-bit renormalisation), one thread per lane, thousands of lanes in lockstep.  Container layout and its CPU twin + decoder:
 // oracle/stage3_qual.c (the bytes must be identical).
 #include "ctx.h"
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 
 namespace clb {
 
-constexpr uint32_t QB_LANES = 64, QB_PROB_BITS = 12, QB_M = 1u << QB_PROB_BITS, QB_L = 1u << 16, QB_MIN_CTX = 32;
+constexpr uint32_t QB_LANES = 64, QB_PROB_BITS = 12, QB_M = 1u << QB_PROB_BITS, QB_L = 1u << 15, QB_MIN_CTX = 32;
 
 struct QP { uint32_t nb, level, bps, cb, cbits; uint32_t thr[4]; };
 
@@ -30,8 +33,8 @@ struct QArgs {
 	uint32_t n_reads; QP P;
 	uint32_t* avg16;                                    // n_reads x 5
 	uint32_t* hist; uint32_t* mhist;                    // 2^cbits x nb, nb x 128
-	const uint32_t* tab;                                // freq | cum << 16 per (context, symbol)
-	const uint32_t* mtab;                               // same for the means' high byte
+	const uint4* tab;                                   // per (context, symbol): reciprocal, bias, complement | shift << 16, frequency
+	const uint4* mtab;                                  // same for the means' high byte
 };
 
 CLB_D uint32_t q_bin(const QP& P, uint32_t phred) { uint32_t b = 0; while (b + 1 < P.nb && phred >= P.thr[b]) ++b; return b; }
@@ -103,11 +106,28 @@ __global__ void __launch_bounds__(128) k_q_count(QArgs a)
 	}
 }
 
-CLB_D uint32_t rans_put(uint32_t x, uint32_t fc, uint16_t* w, uint32_t& nw)
+// Encoder symbol with the division replaced by a multiplication with a 32-bit reciprocal (exact for states below 2^31;
+// the construction is the one of the public-domain ryg_rans RansEncSymbolInit): x' = x + bias + (x / f) * (M - f).
+CLB_HD uint4 rans_symbol(uint32_t start, uint32_t freq)
 {
-	const uint32_t f = fc & 0xffffu, c = fc >> 16;
-	if ((unsigned long long)x >= ((unsigned long long)f << 20)) { w[nw++] = (uint16_t)x; x >>= 16; }
-	return ((x / f) << QB_PROB_BITS) + (x % f) + c;
+	uint4 s;
+	if (freq < 2) { s.x = ~0u; s.y = start + QB_M - 1; s.z = (QB_M - freq) | (0u << 16); }
+	else {
+		uint32_t shift = 0; while (freq > (1u << shift)) ++shift;
+		s.x = (uint32_t)(((1ull << (shift + 31)) + freq - 1) / freq);
+		s.y = start; s.z = (QB_M - freq) | ((shift - 1) << 16);
+	}
+	s.w = freq;
+	return s;
+}
+// one coding step with the symbol held by thread k of the warp; the state is the same in all threads, thread 0 stores
+CLB_D uint32_t rans_step(uint32_t x, const uint4& fc, int k, uint16_t* w, uint32_t& nw, uint32_t t)
+{
+	const unsigned FULL = 0xffffffffu;
+	const uint32_t rcp = __shfl_sync(FULL, fc.x, k), bias = __shfl_sync(FULL, fc.y, k), cs = __shfl_sync(FULL, fc.z, k), f = __shfl_sync(FULL, fc.w, k);
+	if (x >= (f << 19)) { if (t == 0) w[nw] = (uint16_t)x; ++nw; x >>= 16; }       // f <= 2^12: no overflow
+	const uint32_t q = __umulhi(x, rcp) >> (cs >> 16);
+	return x + bias + q * (cs & 0xffffu);
 }
 
 struct QEnc {
@@ -116,33 +136,45 @@ struct QEnc {
 	uint16_t* tmp; uint32_t* lane_words; uint32_t* lane_state;
 };
 
-// pass 2: one thread per (pack, lane): its reads last to first, symbols last to first (rANS decodes in the opposite order)
-__global__ void __launch_bounds__(64) k_q_encode(QArgs a, QEnc e)
+// pass 2: one WARP per (pack, lane) stream; its reads last to first, symbols last to first (rANS decodes in the opposite
+// order).  The 32 threads fetch the table entries of 32 consecutive symbols side by side (coalesced quality bytes, one
+// packed word of bases), then the rANS state — the same in every thread — takes the 32 dependent steps; thread 0 stores.
+__global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 {
-	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, t = threadIdx.x & 31;
 	if (li >= e.n_packs * QB_LANES) return;
+	const unsigned FULL = 0xffffffffu;
 	const uint32_t p = e.pack_lo + li / QB_LANES, l = li % QB_LANES;
 	const uint32_t r0 = e.pack_first[p], r1 = e.pack_first[p + 1];
 	uint16_t* w = e.tmp + e.lane_off[li]; uint32_t nw = 0;
 	uint32_t x = QB_L;
+	const QP& P = a.P;
 	if (r0 + l < r1) {
-		uint32_t last = r0 + l + ((r1 - 1 - (r0 + l)) / QB_LANES) * QB_LANES;
+		const uint32_t last = r0 + l + ((r1 - 1 - (r0 + l)) / QB_LANES) * QB_LANES;
 		for (long long r = last; r >= (long long)(r0 + l); r -= QB_LANES) {
 			const uint32_t n = a.rd_len[r]; const uint64_t rs = a.rd_start[r];
 			const uint8_t* q = a.quals + a.qoff[r];
 			const uint8_t* fl = a.flags ? a.flags + a.qoff[r] : nullptr;
-			for (uint32_t i = n; i-- > 0;) {
-				const uint32_t b = q_bin(a.P, q[i] - 33u);
-				x = rans_put(x, a.tab[(size_t)q_context(a, rs, n, q, fl, i) * a.P.nb + b], w, nw);
+			for (long long hi = n; hi > 0; hi -= 32) {
+				const long long j = hi - 1 - t;                  // thread 0 holds the last symbol of the chunk = the first to be coded
+				uint4 fc = make_uint4(0, 0, 0, 1);
+				if (j >= 0) fc = a.tab[(size_t)q_context(a, rs, n, q, fl, (uint32_t)j) * P.nb + q_bin(P, q[j] - 33u)];
+				const int cnt = (int)min((long long)32, hi);
+				for (int k = 0; k < cnt; ++k) x = rans_step(x, fc, k, w, nw, t);
 			}
-			for (uint32_t b = a.P.nb; b-- > 0;) {
-				const uint32_t v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
-				x = rans_put(x, (QB_M >> 8) | ((a2 * (QB_M >> 8)) << 16), w, nw);
-				x = rans_put(x, a.mtab[b * 128 + a1], w, nw);
+			{	// the read's bin means come first in decoding order: bin 0 high byte, low byte, bin 1 ... -> coded last, backwards
+				const uint32_t ns = 2 * P.nb;
+				uint4 fc = make_uint4(0, 0, 0, 1);
+				if (t < ns) {
+					const uint32_t m = ns - 1 - t, b = m >> 1;
+					const uint32_t v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
+					fc = (m & 1) ? rans_symbol(a2 * (QB_M >> 8), QB_M >> 8) : a.mtab[b * 128 + a1];
+				}
+				for (uint32_t k = 0; k < ns; ++k) x = rans_step(x, fc, (int)k, w, nw, t);
 			}
 		}
 	}
-	e.lane_words[li] = nw; e.lane_state[li] = x;
+	if (t == 0) { e.lane_words[li] = nw; e.lane_state[li] = x; }
 }
 
 // lane streams into the final container: state, then the words in decoding order (last written first); one warp per lane
@@ -167,6 +199,12 @@ __global__ void __launch_bounds__(128) k_q_gather(QEnc e, const uint64_t* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+struct QTrace {            // CLB_S2_TRACE=1: wall time of every phase (synchronising; debugging aid)
+	bool on; cudaStream_t s; double t0;
+	static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	explicit QTrace(cudaStream_t st) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), t0(now()) {}
+	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s3q] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
+};
 static void normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
 {
 	uint64_t tot = 0; uint32_t best = 0;
@@ -182,6 +220,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	cudaStream_t s = c->stream;
+	QTrace tr(s);
 	const uint64_t n = c->n_reads;
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_qual_encode before the reads are complete (clb_count_finalize)");
 	if (prm->n_bins != 2 && prm->n_bins != 4 && prm->n_bins != 5) return fail(c, CLB_ERR_BAD_ARG, "clb_qual_encode: the *-avg modes have 2, 4 or 5 bins");
@@ -229,13 +268,15 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	}
 	QArgs a{};
 	a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.n_reads = (uint32_t)n; a.P = P;
-	uint32_t* d_avg = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_mhist = nullptr; uint32_t* d_tab = nullptr; uint32_t* d_mtab = nullptr;
+	uint32_t* d_avg = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_mhist = nullptr; uint4* d_tab = nullptr; uint4* d_mtab = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_avg, sizeof(uint32_t) * 5 * (n + 1)));
 	CLB_CUDA(c, dalloc((void**)&d_hist, sizeof(uint32_t) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mhist, sizeof(uint32_t) * 5 * 128));
-	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint32_t) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mtab, sizeof(uint32_t) * 5 * 128));
+	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint4) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mtab, sizeof(uint4) * 5 * 128));
 	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * n_ctx * P.nb, s)); CLB_CUDA(c, cudaMemsetAsync(d_mhist, 0, sizeof(uint32_t) * 5 * 128, s));
 	a.avg16 = d_avg; a.hist = d_hist; a.mhist = d_mhist;
+	tr.mark("setup");
 	if (n) { CLB_TIMED(c, K_QUAL, (k_q_count<<<(uint32_t)n, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_q_count"); }
+	tr.mark("k_q_count");
 	// ---- count table -> frequency tables + the container's header (metadata-sized, on the host) ----
 	std::vector<uint32_t> hist(n_ctx * P.nb), mh(5 * 128);
 	CLB_CUDA(c, cudaMemcpyAsync(hist.data(), d_hist, sizeof(uint32_t) * hist.size(), cudaMemcpyDeviceToHost, s));
@@ -249,12 +290,12 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	}
 	std::vector<uint16_t> freq(n_ctx * nb), fbf((size_t)n_fb * nb), mf(5 * 128, 0);
 	for (uint32_t x = 0; x < n_fb; ++x) normalise(&fbh[(size_t)x * nb], nb, &fbf[(size_t)x * nb]);
-	std::vector<uint32_t> tab(n_ctx * nb), mtab(5 * 128, 0);
+	std::vector<uint4> tab(n_ctx * nb), mtab(5 * 128, make_uint4(0, 0, 0, 1));
 	for (uint64_t x = 0; x < n_ctx; ++x) {
 		if (dense[x]) normalise(&hist[x * nb], nb, &freq[x * nb]); else std::memcpy(&freq[x * nb], &fbf[(x & (n_fb - 1)) * nb], 2 * nb);
-		uint32_t acc = 0; for (uint32_t k = 0; k < nb; ++k) { tab[x * nb + k] = freq[x * nb + k] | (acc << 16); acc += freq[x * nb + k]; }
+		uint32_t acc = 0; for (uint32_t k = 0; k < nb; ++k) { tab[x * nb + k] = freq[x * nb + k] ? rans_symbol(acc, freq[x * nb + k]) : make_uint4(0, 0, 0, 1); acc += freq[x * nb + k]; }
 	}
-	for (uint32_t b = 0; b < nb; ++b) { normalise(&mh[b * 128], 128, &mf[b * 128]); uint32_t acc = 0; for (uint32_t k = 0; k < 128; ++k) { mtab[b * 128 + k] = mf[b * 128 + k] | (acc << 16); acc += mf[b * 128 + k]; } }
+	for (uint32_t b = 0; b < nb; ++b) { normalise(&mh[b * 128], 128, &mf[b * 128]); uint32_t acc = 0; for (uint32_t k = 0; k < 128; ++k) { mtab[b * 128 + k] = mf[b * 128 + k] ? rans_symbol(acc, mf[b * 128 + k]) : make_uint4(0, 0, 0, 1); acc += mf[b * 128 + k]; } }
 	std::vector<uint8_t> hdr;
 	hdr.insert(hdr.end(), {'Q', 'B', '0', '1'}); put(hdr, nb); put(hdr, P.level); for (int i = 0; i < 4; ++i) put(hdr, P.thr[i]); put(hdr, (uint64_t)n); put(hdr, np); put(hdr, P.cbits);
 	for (uint32_t i = 0; i < nb * 128; ++i) put(hdr, mf[i]);
@@ -269,9 +310,10 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 			for (uint32_t k = 0; k + 1 < nb; ++k) put(hdr, freq[x * nb + k]);
 		}
 	}
-	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * tab.size(), cudaMemcpyHostToDevice, s));
-	CLB_CUDA(c, cudaMemcpyAsync(d_mtab, mtab.data(), sizeof(uint32_t) * mtab.size(), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint4) * tab.size(), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_mtab, mtab.data(), sizeof(uint4) * mtab.size(), cudaMemcpyHostToDevice, s));
 	a.tab = d_tab; a.mtab = d_mtab;
+	tr.mark("tables (host)");
 	// ---- pass 2 in chunks of packs (the temp holds one 16-bit word per symbol at worst) ----
 	uint32_t* d_pack_first = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_pack_first, sizeof(uint32_t) * (np + 1)));
@@ -296,8 +338,9 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
 		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
 		QEnc e{d_pack_first, p0, cp, d_lane_off, d_tmp, d_words, d_state};
-		CLB_TIMED(c, K_QUAL, (k_q_encode<<<(nl + 63) / 64, 64, 0, s>>>(a, e)));
+		CLB_TIMED(c, K_QUAL, (k_q_encode<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e)));
 		CLB_LAUNCH_CHECK(c, "k_q_encode");
+		tr.mark("k_q_encode");
 		std::vector<uint32_t> words(nl);
 		CLB_CUDA(c, cudaMemcpyAsync(words.data(), d_words, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
 		CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -312,6 +355,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		CLB_TIMED(c, K_QUAL, (k_q_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(e, d_dst, d_phdr, c->qs.p)));
 		CLB_LAUNCH_CHECK(c, "k_q_gather");
 		CLB_CUDA(c, cudaStreamSynchronize(s));
+		tr.mark("k_q_gather");
 		p0 = p1;
 	}
 	c->qs_total = out_at;

@@ -7,6 +7,8 @@
 // JSON line with the wall time of each phase.  bench.py --impl reference and the cpu_baseline leg run it.
 // With COLORD_TIME_STAGES=12 the N CEncoder threads (compression.cpp:592-625) consume the compress_queue as in the real
 // pipeline and a null consumer drains their tuple packs: stage 1 + stage 2, still without the entropy coders.
+// With COLORD_TIME_STAGES=12q the quality entropy coder thread (CEntrComprQuals, compression.cpp:654-668) runs as well,
+// writing its parts to the archive given on the command line: stages 1 + 2 + the quality stream of stage 3.
 //
 // Usage: oracle/_ref/ref_stage1_time compress-ont [flags] -t N in.fastq ignored.out
 #include "compression.h"
@@ -17,6 +19,8 @@
 #include "in_reads.h"
 #include "reads_sim_graph.h"
 #include "encoder.h"
+#include "entr_qual.h"
+#include "archive.h"
 #include "reference_reads.h"
 #include "ref_reads_accepter.h"
 #include "parallel_queue.h"
@@ -76,7 +80,9 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	double t3 = now();
 	uint64_t n_links = 0, n_out = 0;
 	std::thread reader([&] { CInputReads r(false, params.inputFilePath, reads_queue, quals_queue, headers_queue); });
-	std::thread drain_q([&] { qual_pack_t p; while (quals_queue.Pop(p)); });
+	const char* stages_env0 = getenv("COLORD_TIME_STAGES");
+	const bool qual_consumed = stages_env0 && std::string(stages_env0) == "12q";
+	std::thread drain_q([&] { if (qual_consumed) return; qual_pack_t p; while (quals_queue.Pop(p)); });
 	std::thread drain_h([&] { header_pack_t p; while (headers_queue.Pop(p)); });
 	std::thread graph([&] {
 		CReadsSimilarityGraph g(reads_queue, graph_out, reference_reads, nullptr, filtered_kmers, kmerLen, params.maxCandidates,
@@ -84,7 +90,8 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 			params.dataSource, params.fillFactorKmersToReads, false);
 	});
 	const char* stages_env = getenv("COLORD_TIME_STAGES");
-	const bool with_encoders = stages_env && std::string(stages_env) == "12";
+	const bool with_qual = stages_env && std::string(stages_env) == "12q";
+	const bool with_encoders = with_qual || (stages_env && std::string(stages_env) == "12");
 	uint64_t es_bytes = 0;
 	if (!with_encoders)
 	{
@@ -104,7 +111,14 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 					is_fastq, params.filterHashModulo, kmerLen, params.dataSource);
 				enc.Encode();
 			});
-		std::thread drain_esq([&] { std::vector<es_t> p; while (es_for_qual.Pop(p)); });
+		CArchive archive(false);
+		if (with_qual && !archive.Open(params.outputFilePath)) { std::cerr << "cannot open " << params.outputFilePath << "\n"; exit(1); }
+		std::thread drain_esq([&] {
+			if (!with_qual) { std::vector<es_t> p; while (es_for_qual.Pop(p)); return; }
+			CEntrComprQuals compr{ quals_queue, archive, params.qualityComprMode, params.qualityFwdThresholds, params.qualityRevThresholds, false,
+				params.compressionLevel, (uint64_t)tot_n_reads * mean_read_len, es_for_qual, params.dataSource };
+			compr.Compress();
+		});
 		std::thread sink([&] { std::vector<es_t> pack; while (compressed.Pop(pack)) for (auto& es : pack) { ++n_out; es_bytes += es.size(); } });
 		reader.join(); drain_q.join(); drain_h.join(); graph.join();
 		for (auto& t : encoders) t.join();
@@ -114,7 +128,7 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	printf("{\"count_s\": %.4f, \"filter_s\": %.4f, \"graph_s\": %.4f, \"stage1_s\": %.4f, \"k\": %u, \"n_reads\": %u, \"tot_kmers\": %llu, "
 		"\"n_unique_counted\": %llu, \"tot_ref_reads\": %u, \"n_links\": %llu, \"threads\": %u, \"stages\": \"%s\", \"anchor_len\": %u, \"es_bytes\": %llu, \"n_out\": %llu}\n",
 		t1 - t0, t2 - t1, t4 - t3, (t2 - t0) + (t4 - t3), kmerLen, tot_n_reads, (unsigned long long)tot_kmers, (unsigned long long)n_uniq,
-		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
+		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_qual ? "1+2+3q" : with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
 	fflush(stdout);
 	_exit(0);     // skip archive/info epilogue of the CLI callback
 }

@@ -14,7 +14,7 @@
  *                                test/<name>.quan fixtures (tests/golden/qual_*.bin.gz)
  * Part 2 is the CPU twin of the device's NATIVE container for these symbols (not the reference's adaptive range coder, whose
  * single serial model chain cannot run in lockstep — SURVEY.md §7): two passes, static per-context frequency tables
- * normalised to 2^12, interleaved rANS (32-bit state, 16-bit renormalisation), 64 lanes per read pack.  The device output
+ * normalised to 2^12, interleaved rANS (31-bit state, 16-bit renormalisation), 64 lanes per read pack.  The device output
  * must equal this byte for byte; the decoder below gives the round trip.  Parity of the native container with the reference
  * is by (a) identical reconstructed qualities and (b) stream size within the north star's 0.5 % — there is no reference
  * bitstream to compare with, which tests/test_oracle_stage3.py states.
@@ -26,7 +26,7 @@
 #define QB_LANES 64
 #define QB_PROB_BITS 12
 #define QB_M (1u << QB_PROB_BITS)
-#define QB_L (1u << 16)
+#define QB_L (1u << 15)        /* states stay below 2^31: the device divides by multiplying with a 32-bit reciprocal */
 #define QB_MIN_CTX 32u         /* contexts seen fewer times share the fallback model of their previous-symbol part */
 
 typedef struct {
@@ -136,7 +136,7 @@ static void ob_u64(obuf* o, uint64_t v) { ob_put(o, &v, 8); }
 /* one rANS step, 16-bit words are pushed to a stack that is later read backwards */
 static inline uint32_t rans_put(uint32_t x, uint32_t f, uint32_t c, uint16_t* w, uint64_t* nw)
 {
-	const uint64_t x_max = (uint64_t)f << 20;       /* ((L >> PROB_BITS) << 16) * f; f = 2^12 makes it 2^32 */
+	const uint64_t x_max = (uint64_t)f << 19;       /* ((L >> PROB_BITS) << 16) * f */
 	while (x >= x_max) { w[(*nw)++] = (uint16_t)x; x >>= 16; }
 	return ((x / f) << QB_PROB_BITS) + (x % f) + c;
 }
