@@ -50,6 +50,7 @@ struct MatchArgs {
 	const uint64_t* bloom_off; uint32_t* g_bloom;
 	uint8_t* arena; unsigned long long arena_cap; unsigned long long* cursor;     // in pair slots
 	SegInfo* seg; uint32_t* slot_dec;                 // per slot: 1 = too few distinct m-mers (no candidates)
+	const uint8_t* skip;                              // HiFi: per (slot, candidate) 1 = anchors already found from the shared k-mers
 };
 
 struct MatchShared {
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 			const uint32_t rr = a.ref_to_read[a.cand[(size_t)read * c + j]];
 			sh.ref_read[j] = rr; sh.word_base[j] = wb;
 			const uint32_t rl = a.rd_len[rr];
-			if (rl >= m) wb += (rl - m + 1 + 31) / 32;
+			if (rl >= m && !(a.skip && a.skip[(size_t)slot * c + j])) wb += (rl - m + 1 + 31) / 32;
 		}
 		sh.word_base[n_cand] = wb;
 	}
@@ -230,6 +231,140 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	__syncthreads();
 	// ---- write the pairs ----
 	scan_refs<true>(a, sh, tab, tmask, bloom, bmask, estart, n_cand);
+}
+
+// ------------------------------------------------------------------------------------------------ HiFi: anchors from shared k-mers
+// encoder.cpp:870-1012 (AnalyseRefReadWithKmers) + :1113-1147 (KmerBasedAnchors): a shared k-mer (or its reverse complement)
+// that occurs exactly once as a forward k-mer in the read and exactly once in the oriented reference read is an anchor; the
+// anchors must be colinear, overlapping ones are dropped, then they are extended over equal bases and merged.
+// One CTA per (read, candidate): a small table of the shared k-mers' two strands collects (count, position) from one scan of
+// the read and one scan of the forward reference (the reverse-complement read's k-mer at rl-k-p is the complement of the
+// forward one at p); two threads then build the anchors of the two orientations.
+struct KEntry { unsigned long long key; uint32_t enc_cnt, enc_pos, ref_cnt, ref_pos; };
+struct KmerArgs {
+	const uint64_t* pk; const uint64_t* rd_start; const uint32_t* rd_len;
+	const uint32_t* enc_list; uint32_t n_list;
+	const uint32_t* cand; const uint32_t* cand_n; const uint32_t* common_n; const uint64_t* common_off; const uint64_t* common; const uint32_t* ref_to_read;
+	uint32_t k, c;
+	const uint64_t* tab_off; KEntry* tab;               // per (slot, candidate): first entry / capacity is 4 * common_n rounded up to a power of two
+	const uint64_t* anc_off; uint8_t* anc;              // per (slot, candidate): pair-slot offset of 2 anchor lists (one per orientation)
+	SegInfo* kseg; uint8_t* skip;
+};
+CLB_D KEntry* ktab_find(KEntry* tab, uint32_t mask, uint64_t key)
+{
+	uint32_t i = mm_hash(key) & mask;
+	for (;;) { if (tab[i].key == key) return &tab[i]; if (tab[i].key == ~0ULL) return nullptr; i = (i + 1) & mask; }
+}
+__global__ void __launch_bounds__(128) k_kmer_anchors(KmerArgs a)
+{
+	const uint32_t slot = blockIdx.x / a.c, j = blockIdx.x % a.c;
+	const uint32_t read = a.enc_list[slot];
+	const size_t sc = (size_t)slot * a.c + j;
+	SegInfo* ks = a.kseg + sc * 2;
+	if (threadIdx.x < 2) ks[threadIdx.x] = SegInfo{0, 0, 0, 0, 1};
+	if (threadIdx.x == 0) a.skip[sc] = 0;
+	if (j >= min(a.cand_n[read], a.c)) return;
+	const uint32_t nco = a.common_n[(size_t)read * a.c + j], k = a.k;
+	if (!nco) return;
+	const uint64_t* common = a.common + a.common_off[(size_t)read * a.c + j];
+	uint32_t cap = 8; while (cap < 4 * nco) cap <<= 1;
+	const uint32_t mask = cap - 1;
+	KEntry* tab = a.tab + a.tab_off[sc];
+	for (uint32_t i = threadIdx.x; i < cap; i += blockDim.x) tab[i] = KEntry{~0ULL, 0, 0, 0, 0};
+	__syncthreads();
+	for (uint32_t i = threadIdx.x; i < 2 * nco; i += blockDim.x) {
+		const uint64_t km = common[i >> 1], key = (i & 1) ? revcomp(km, k) : km;
+		uint32_t h = mm_hash(key) & mask;
+		for (;;) {
+			const unsigned long long old = atomicCAS(&tab[h].key, ~0ULL, (unsigned long long)key);
+			if (old == ~0ULL || old == key) break;
+			h = (h + 1) & mask;
+		}
+	}
+	__syncthreads();
+	const uint64_t kmask = k == 32 ? ~0ULL : ((1ULL << (2 * k)) - 1);
+	const uint32_t rr = a.ref_to_read[a.cand[(size_t)read * a.c + j]];
+	const uint64_t estart = a.rd_start[read], rstart = a.rd_start[rr];
+	const uint32_t el = a.rd_len[read], rl = a.rd_len[rr];
+	for (int which = 0; which < 2; ++which) {
+		const uint64_t st = which ? rstart : estart; const uint32_t len = which ? rl : el;
+		if (len < k) continue;
+		const uint32_t n_pos = len - k + 1, n_words = (n_pos + 31) / 32;
+		for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+			const uint32_t p0 = w * 32, p1 = min(p0 + 32, n_pos);
+			uint64_t f = window(a.pk, st + p0, k);
+			for (uint32_t p = p0; p < p1; ++p) {
+				if (p > p0) f = ((f << 2) | base_at(a.pk, st + p + k - 1)) & kmask;
+				KEntry* e = ktab_find(tab, mask, f);
+				if (!e) continue;
+				if (which) { atomicAdd(&e->ref_cnt, 1u); e->ref_pos = p; } else { atomicAdd(&e->enc_cnt, 1u); e->enc_pos = p; }
+			}
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x >= 2) return;
+	const uint32_t o = threadIdx.x;                       // 0: forward reference, 1: reverse complement
+	const uint64_t seg_slot = a.anc_off[sc] + (uint64_t)o * ((12ull * nco + PAIR_SLOT_BYTES - 1) / PAIR_SLOT_BYTES + 1);
+	Anchor* an = reinterpret_cast<Anchor*>(a.anc + seg_slot * PAIR_SLOT_BYTES);
+	uint32_t n = 0;
+	for (uint32_t i = 0; i < nco; ++i) {
+		for (int form = 0; form < 2; ++form) {
+			const uint64_t F = form ? revcomp(common[i], k) : common[i];
+			const KEntry* e = ktab_find(tab, mask, F);
+			if (!e || e->enc_cnt != 1) continue;
+			uint32_t ir;
+			if (!o) { if (e->ref_cnt != 1) continue; ir = e->ref_pos; }
+			else { const KEntry* e2 = ktab_find(tab, mask, revcomp(F, k)); if (!e2 || e2->ref_cnt != 1) continue; ir = rl - k - e2->ref_pos; }
+			// insertion by pos_enc (positions are distinct)
+			uint32_t q = n++;
+			while (q > 0 && an[q - 1].pos_enc > e->enc_pos) { an[q] = an[q - 1]; --q; }
+			an[q] = Anchor{k, e->enc_pos, ir};
+			break;
+		}
+	}
+	if (!n) return;
+	for (uint32_t i = 1; i < n; ++i) if (an[i].pos_ref < an[i - 1].pos_ref) return;          // not colinear
+	{	// drop k-mers overlapping their predecessor (:917-926)
+		uint32_t w = 1;
+		for (uint32_t i = 1; i < n; ++i) { const Anchor& p = an[w - 1]; if (p.pos_enc + p.len > an[i].pos_enc || p.pos_ref + p.len > an[i].pos_ref) continue; an[w++] = an[i]; }
+		n = w;
+	}
+	auto eb = [&](uint32_t x) { return base_at(a.pk, estart + x); };
+	auto rb = [&](uint32_t y) { return o ? 3u - base_at(a.pk, rstart + (rl - 1 - y)) : base_at(a.pk, rstart + y); };
+	while (an[0].pos_enc > 0 && an[0].pos_ref > 0 && eb(an[0].pos_enc - 1) == rb(an[0].pos_ref - 1)) { --an[0].pos_enc; --an[0].pos_ref; ++an[0].len; }
+	// extend / merge (:944-998), the reference's loop on a vector with erase, restated literally
+	for (unsigned long long i = 0; i < n; ++i) {
+		if (i > 0) {
+			const uint32_t pe = an[i - 1].pos_enc + an[i - 1].len, pr = an[i - 1].pos_ref + an[i - 1].len;
+			for (;;) {
+				const bool re = an[i].pos_enc == pe, rr2 = an[i].pos_ref == pr;
+				if (re && rr2) { an[i].len += an[i - 1].len; for (uint32_t x = (uint32_t)i - 1; x + 1 < n; ++x) an[x] = an[x + 1]; --n; break; }
+				if (re || rr2) break;
+				if (eb(an[i].pos_enc - 1) != rb(an[i].pos_ref - 1)) break;
+				an[i].len++; an[i].pos_enc--; an[i].pos_ref--;
+			}
+		}
+		if (i >= n) break;
+		if (i != (unsigned long long)n - 1) {
+			const uint32_t ne = an[i + 1].pos_enc, nr = an[i + 1].pos_ref;
+			uint32_t pe = an[i].pos_enc + an[i].len, pr = an[i].pos_ref + an[i].len;
+			for (;;) {
+				const bool re = pe == ne, rr2 = pr == nr;
+				if (re && rr2) { an[i].len += an[i + 1].len; for (uint32_t x = (uint32_t)i + 1; x + 1 < n; ++x) an[x] = an[x + 1]; --n; --i; break; }
+				else if (re || rr2) break;
+				if (eb(pe) != rb(pr)) break;
+				++pe; ++pr; ++an[i].len;
+			}
+		}
+	}
+	{
+		Anchor& l = an[n - 1];
+		uint32_t pe = l.pos_enc + l.len, pr = l.pos_ref + l.len;
+		while (pe < el && pr < rl && eb(pe) == rb(pr)) { ++pe; ++pr; ++l.len; }
+	}
+	uint32_t tot = 0; for (uint32_t i = 0; i < n; ++i) tot += an[i].len;
+	ks[o] = SegInfo{seg_slot, 1, n, tot, 1};
+	a.skip[sc] = 1;
 }
 
 // ------------------------------------------------------------------------------------------------ sort
@@ -344,7 +479,7 @@ __global__ void __launch_bounds__(128) k_lis(SegInfo* __restrict__ seg, uint32_t
 // encoder.cpp:1149-1192 (MmerBasedAnchors: both orientations, keep the better), :1577-1622 (fix overlaps), :1103-1108 (sort)
 __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg, uint32_t n_slots, const uint32_t* __restrict__ enc_list,
 	const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_n, const uint32_t* __restrict__ rd_len, const uint32_t* __restrict__ slot_dec,
-	uint8_t* __restrict__ arena, S2P P, Node* __restrict__ nodes, CandView* __restrict__ cviews)
+	uint8_t* __restrict__ arena, S2P P, Node* __restrict__ nodes, CandView* __restrict__ cviews, const SegInfo* __restrict__ kseg, uint64_t kbase)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	if (slot >= n_slots) return;
@@ -353,8 +488,13 @@ __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg,
 	CandView* out = cviews + (size_t)slot * c;
 	uint32_t n_out = 0;
 	for (uint32_t j = 0; j < n_cand; ++j) {
-		const SegInfo f = seg[((size_t)slot * c + j) * 2], r = seg[((size_t)slot * c + j) * 2 + 1];
-		const bool af = f.n > 0 && f.n_anch >= P.min_anchors, ar = r.n > 0 && r.n_anch >= P.min_anchors;
+		SegInfo f = seg[((size_t)slot * c + j) * 2], r = seg[((size_t)slot * c + j) * 2 + 1];
+		bool kmer = false;
+		if (kseg) {      // HiFi: the k-mer based anchors win when either orientation gave some (encoder.cpp:1214-1232)
+			const SegInfo kf = kseg[((size_t)slot * c + j) * 2], kr = kseg[((size_t)slot * c + j) * 2 + 1];
+			if (kf.n || kr.n) { f = kf; r = kr; f.off += kbase; r.off += kbase; kmer = true; }
+		}
+		const bool af = f.n > 0 && (kmer || f.n_anch >= P.min_anchors), ar = r.n > 0 && (kmer || r.n_anch >= P.min_anchors);
 		if (!af && !ar) continue;
 		const bool use_f = af && (!ar || f.tot > r.tot);
 		const SegInfo& g = use_f ? f : r;
@@ -412,20 +552,51 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 	CLB_CUDA(c, cudaMallocAsync((void**)&g_bloom, sizeof(uint32_t) * (bloom_total + 1), s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab_off, tab_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_bloom_off, bloom_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
+	// HiFi: anchors from the shared k-mers first; candidates that get some are skipped by the m-mer search
+	SegInfo* d_kseg = nullptr; uint8_t* d_skip = nullptr; uint8_t* d_kanc = nullptr; uint64_t kanc_slots = 0, kbase = 0;
+	struct KFree { std::vector<void*> v; cudaStream_t s; ~KFree() { for (void* q : v) cudaFreeAsync(q, s); } } kfree{{}, s};
+	if (c->prm.is_hifi) {
+		const uint64_t nsc = (uint64_t)nb * P.c;
+		std::vector<uint32_t> votes(c->n_reads * P.c);
+		CLB_CUDA(c, cudaMemcpyAsync(votes.data(), c->cand_votes, sizeof(uint32_t) * votes.size(), cudaMemcpyDeviceToHost, s));
+		std::vector<uint32_t> cn(c->n_reads);
+		CLB_CUDA(c, cudaMemcpyAsync(cn.data(), c->cand_n, sizeof(uint32_t) * cn.size(), cudaMemcpyDeviceToHost, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		std::vector<uint64_t> ktab_off(nsc, 0), kanc_off(nsc, 0);
+		uint64_t ktab_total = 0;
+		for (uint32_t i = 0; i < nb; ++i) for (uint32_t j = 0; j < P.c; ++j) {
+			const uint32_t nco = j < cn[h_list[i]] ? votes[(size_t)h_list[i] * P.c + j] : 0;
+			uint64_t cap = 8; while (cap < 4ull * nco) cap <<= 1;
+			ktab_off[(size_t)i * P.c + j] = ktab_total; ktab_total += nco ? cap : 0;
+			kanc_off[(size_t)i * P.c + j] = kanc_slots; kanc_slots += nco ? 2 * ((12ull * nco + PAIR_SLOT_BYTES - 1) / PAIR_SLOT_BYTES + 1) : 0;
+		}
+		uint64_t* d_ktab_off = nullptr; uint64_t* d_kanc_off = nullptr; KEntry* d_ktab = nullptr;
+		auto kalloc = [&](void** q, uint64_t bytes) { cudaError_t e = cudaMallocAsync(q, bytes ? bytes : 1, s); if (e == cudaSuccess) kfree.v.push_back(*q); return e; };
+		CLB_CUDA(c, kalloc((void**)&d_kseg, sizeof(SegInfo) * nsc * 2)); CLB_CUDA(c, kalloc((void**)&d_skip, nsc));
+		CLB_CUDA(c, kalloc((void**)&d_ktab_off, sizeof(uint64_t) * nsc)); CLB_CUDA(c, kalloc((void**)&d_kanc_off, sizeof(uint64_t) * nsc));
+		CLB_CUDA(c, kalloc((void**)&d_ktab, sizeof(KEntry) * (ktab_total + 1))); CLB_CUDA(c, kalloc((void**)&d_kanc, kanc_slots * PAIR_SLOT_BYTES + 64));
+		CLB_CUDA(c, cudaMemcpyAsync(d_ktab_off, ktab_off.data(), sizeof(uint64_t) * nsc, cudaMemcpyHostToDevice, s));
+		CLB_CUDA(c, cudaMemcpyAsync(d_kanc_off, kanc_off.data(), sizeof(uint64_t) * nsc, cudaMemcpyHostToDevice, s));
+		KmerArgs ka{c->pk.p, c->rd_start.p, c->rd_len.p, d_list, nb, c->cand, c->cand_n, c->cand_votes, c->common_off, c->common, d_ref_to_read,
+			c->prm.kmer_len, P.c, d_ktab_off, d_ktab, d_kanc_off, d_kanc, d_kseg, d_skip};
+		CLB_TIMED(c, K_ANCHORS, (k_kmer_anchors<<<(uint32_t)nsc, 128, 0, s>>>(ka)));
+		CLB_LAUNCH_CHECK(c, "k_kmer_anchors");
+		CLB_CUDA(c, cudaStreamSynchronize(s));          // the host vectors above were read by the copies
+	}
 	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS);
 	CLB_CUDA(c, cudaFuncSetAttribute(k_anchor_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// first guess of the arena: one pair per base of every read and candidate half-used; the kernel reports the exact need
 	uint64_t cap_pairs = std::max<uint64_t>(1u << 16, est_pairs * 2);
 	clb_status st = CLB_OK;
 	for (int attempt = 0; attempt < 3; ++attempt) {
-		cudaError_t e = arena.reserve(cap_pairs * PAIR_SLOT_BYTES + 64, s, false);
+		cudaError_t e = arena.reserve((cap_pairs + kanc_slots + 4) * PAIR_SLOT_BYTES + 64, s, false);
 		if (e != cudaSuccess) { st = cuda_fail(c, e, "pair arena"); break; }
 		CLB_CUDA(c, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), s));
 		MatchArgs a{};
 		a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.enc_list = d_list; a.n_list = nb;
 		a.cand = c->cand; a.cand_n = c->cand_n; a.ref_to_read = d_ref_to_read; a.P = P;
 		a.tab_off = d_tab_off; a.g_tab = g_tab; a.bloom_off = d_bloom_off; a.g_bloom = g_bloom;
-		a.arena = arena.p; a.arena_cap = cap_pairs; a.cursor = d_cursor; a.seg = d_seg; a.slot_dec = d_slot_dec;
+		a.arena = arena.p; a.arena_cap = cap_pairs; a.cursor = d_cursor; a.seg = d_seg; a.slot_dec = d_slot_dec; a.skip = d_skip;
 		CLB_TIMED(c, K_ANCHORS, (k_anchor_match<<<nb, MATCH_THREADS, smem, s>>>(a)));
 		CLB_LAUNCH_CHECK(c, "k_anchor_match");
 		unsigned long long used = 0;
@@ -438,12 +609,16 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 	}
 	cudaFreeAsync(d_tab_off, s); cudaFreeAsync(d_bloom_off, s); cudaFreeAsync(g_tab, s); cudaFreeAsync(g_bloom, s);
 	if (st != CLB_OK) return st;
+	if (kanc_slots) {      // the k-mer anchors join the arena behind the pair region
+		kbase = (arena.cap - 64) / PAIR_SLOT_BYTES - kanc_slots - 2;
+		CLB_CUDA(c, cudaMemcpyAsync(arena.p + kbase * PAIR_SLOT_BYTES, d_kanc, kanc_slots * PAIR_SLOT_BYTES, cudaMemcpyDeviceToDevice, s));
+	}
 	const uint32_t n_seg = nb * P.c * 2;
 	CLB_TIMED(c, K_ANCHORS, (k_pairs_sort<<<n_seg, SORT_THREADS, 0, s>>>(d_seg, n_seg, arena.p)));
 	CLB_LAUNCH_CHECK(c, "k_pairs_sort");
 	CLB_TIMED(c, K_ANCHORS, (k_lis<<<(n_seg + 127) / 128, 128, 0, s>>>(d_seg, n_seg, arena.p, P.m)));
 	CLB_LAUNCH_CHECK(c, "k_lis");
-	CLB_TIMED(c, K_ANCHORS, (k_select<<<(nb + 127) / 128, 128, 0, s>>>(d_seg, nb, d_list, c->cand, c->cand_n, c->rd_len.p, d_slot_dec, arena.p, P, d_nodes, d_cviews)));
+	CLB_TIMED(c, K_ANCHORS, (k_select<<<(nb + 127) / 128, 128, 0, s>>>(d_seg, nb, d_list, c->cand, c->cand_n, c->rd_len.p, d_slot_dec, arena.p, P, d_nodes, d_cviews, d_kseg, kbase)));
 	CLB_LAUNCH_CHECK(c, "k_select");
 	return CLB_OK;
 }

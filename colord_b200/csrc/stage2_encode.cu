@@ -878,7 +878,6 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 {
 	if (!c->graph_done) return fail(c, CLB_ERR_STATE, "clb_encode before clb_graph_build");
 	if (c->enc_done) return fail(c, CLB_ERR_STATE, "clb_encode called twice");
-	if (c->prm.is_hifi) return fail(c, CLB_ERR_STATE, "clb_encode: the HiFi k-mer anchor path (encoder.cpp:870-1012) is not on the device yet");
 	if (prm->anchor_len < 8 || prm->anchor_len > 32) return fail(c, CLB_ERR_BAD_ARG, "anchor_len must be in [8, 32]");
 	if (prm->max_recurence > 7) return fail(c, CLB_ERR_BAD_ARG, "max_recurence above 7 is not supported");
 	cudaStream_t s = c->stream;

@@ -94,7 +94,7 @@ def test_candidates_match_oracle(golden, case):
     assert not bad, (len(bad), bad[:10], got[bad[0]][:1], want[bad[0]][:1])
 
 
-@pytest.mark.parametrize("case", MMER_CASES)
+@pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_compact_es_bytes_golden(golden, case):
     """E1-E9: the CompactES bytes of every read equal what the unmodified reference's CEncoder produced."""
     g = golden(case)
@@ -191,4 +191,30 @@ def test_encode_repeats():
     P = dict(P_BAL, anchor_len=14)
     bad, n_es = _device_vs_oracle(s, 18, 5, 2, 200, 10, P)
     assert n_es > 400
+    assert not bad, (len(bad), bad[:10])
+
+
+def test_encode_hifi_kmer_anchors_vs_oracle():
+    """HiFi path (encoder.cpp:870-1012, :1113-1147, :1194-1253): anchors from the graph's shared k-mers, m-mer fallback,
+    against the C oracle fed with the device's own candidates and shared k-mers."""
+    from colord_b200 import synth
+    s = synth.generate(400, 150000, 6000, seed=31, profile="hifi", n_frac=0.01)
+    n = s.n_reads
+    k, f, lo, hi, c = 21, 20, 2, 100, 8
+    P = dict(P_BAL, anchor_len=18, k=k, modulo=f, hifi=1)
+    sampled = np.ones(n, np.uint8)
+    with lib.Context(k, f, lo, hi, c, is_hifi=True) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        ctx.graph_build(sampled)
+        cand, cn = ctx.graph_candidates()
+        common = ctx.graph_common()
+        ctx.encode(P, [150, 250])
+        off, es = ctx.encoded(n)
+    got = [es[int(off[i]):int(off[i + 1])].tobytes() for i in range(n)]
+    has_n = np.array([(s.bases[int(s.offsets[i]):int(s.offsets[i + 1])] == ord("N")).any() for i in range(n)], np.uint8)
+    is_ref = (sampled & (1 - has_n)).astype(np.uint8)
+    want = oracle_lib.encode_reads(s.bases, s.offsets, is_ref, cand, cn, np.array([150, 250], np.uint32), P, common)
+    bad = [i for i in range(n) if got[i] != want[i]]
+    assert sum(1 for e in want if (e[0] >> 4) == 10) > 350
     assert not bad, (len(bad), bad[:10])
