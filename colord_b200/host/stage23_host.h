@@ -1,0 +1,61 @@
+// stage23_host.h — C++ host-side mirrors of the reference's stage-2 / stage-3 classes over the C-ABI
+// (include/colord_b200.h).  Same argument meaning and order of use as
+//   CEncoder              src/colord/encoder.h:371-410 (ctor), encoder.cpp:1672-1691 (Encode)
+//   CEntrComprQuals       src/colord/entr_qual.h:82-126 (ctor, Compress)
+// The reference runs N CEncoder threads over CCompressPacks and one quality thread over quals packs; here one call covers
+// all appended reads and the results stay on the device until they are fetched.  Header-only; link -lcolord_b200.
+#pragma once
+#include "stage1_host.h"
+
+namespace clbhost {
+
+class CEncoder {
+	clb_ctx* ctx; uint32_t n_reads;
+	clb_encode_params prm;
+public:
+	// same order as the reference ctor after the queues: anchor_len, the four doubles, minPartLenToConsiderAltRead, maxRecurence, minAnchors
+	CEncoder(CKmerCounter& counter, uint32_t anchor_len, double minFractionOfMmersInEncodeToAlwaysEncode, double minFractionOfMmersInEncode,
+		double maxMatchesMultiplier, double editScriptCostMultiplier, uint32_t minPartLenToConsiderAltRead, uint32_t maxRecurence, uint32_t minAnchors)
+		: ctx(counter.Context()), n_reads(counter.GetNReads()),
+		  prm{anchor_len, minPartLenToConsiderAltRead, maxRecurence, minAnchors, minFractionOfMmersInEncode, minFractionOfMmersInEncodeToAlwaysEncode, maxMatchesMultiplier, editScriptCostMultiplier} {}
+	// pack_sizes: reads per read pack in input order (the estimator is reset per pack, encoder.cpp:1677); empty = the reference's pack rule
+	void Encode(const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_encode(ctx, &prm, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_encode");
+	}
+	// es_t of every read (CompactES bytes, utils.h:69-273), what the reference pushes to compressed_queue
+	void GetTuples(std::vector<uint64_t>& es_off, std::vector<uint8_t>& es) const
+	{
+		uint64_t tot = 0; check(ctx, clb_encode_size(ctx, &tot), "clb_encode_size");
+		es_off.assign(n_reads + 1, 0); es.assign(tot + 1, 0);
+		check(ctx, clb_encode_get(ctx, es_off.data(), es.data(), tot, 0), "clb_encode_get");
+		es.resize(tot);
+	}
+};
+
+class CEntrComprQuals {
+	clb_ctx* ctx;
+	clb_qual_params prm{};
+public:
+	// n_bins 2 / 4 / 5 = QualityComprMode Binary/Quad/QuinaryAverage; thresholds = qualityFwdThresholds; level = compressionLevel
+	CEntrComprQuals(CKmerCounter& counter, uint32_t n_bins, const std::vector<uint32_t>& qualityFwdThresholds, int32_t compression_level) : ctx(counter.Context())
+	{
+		prm.n_bins = n_bins; prm.level = static_cast<uint32_t>(compression_level);
+		for (size_t i = 0; i < 4 && i < qualityFwdThresholds.size(); ++i) prm.thresholds[i] = qualityFwdThresholds[i];
+	}
+	// quals: phred+33 of all reads, offsets[n_reads + 1]
+	void Compress(const std::vector<uint8_t>& quals, const std::vector<uint64_t>& offsets, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_qual_encode(ctx, &prm, quals.data(), offsets.data(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode");
+	}
+	std::vector<uint8_t> GetStream() const
+	{
+		uint64_t tot = 0; check(ctx, clb_qual_size(ctx, &tot), "clb_qual_size");
+		std::vector<uint8_t> out(tot + 1);
+		check(ctx, clb_qual_get(ctx, out.data(), tot, 0), "clb_qual_get");
+		out.resize(tot);
+		return out;
+	}
+};
+
+} // namespace clbhost

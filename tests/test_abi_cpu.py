@@ -60,5 +60,5 @@ def test_sampler_matches_reference(golden, case):
 def test_cpp_host_mirror_compiles():
     """The C++ host-side mirror of the reference classes (colord_b200/host) builds against the C-ABI."""
     import subprocess
-    src = '#include "colord_b200/host/stage1_host.h"\nint main() { clbhost::CRefReadsAccepter a(7, 1.0, 0); return a.GetNAccepted(100) > 100; }\n'
+    src = '#include "colord_b200/host/stage23_host.h"\nint main() { clbhost::CRefReadsAccepter a(7, 1.0, 0); return a.GetNAccepted(100) > 100; }\n'
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src.encode(), check=True, cwd=ROOT)
