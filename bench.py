@@ -285,6 +285,9 @@ def main():
             q1 = min(bases.numel(), q0 + (1 << 28))
             quals[q0:q1] = (torch.randn(q1 - q0, device=device, generator=gq) * 5 + 12).round_().clamp_(1, 40).to(torch.uint8) + 33
         torch.cuda.empty_cache()
+    free_b, total_b = torch.cuda.mem_get_info()
+    print(f"[bench] rank {rank}: inputs resident, {free_b / 2**30:.1f} of {total_b / 2**30:.1f} GiB free "
+          f"(torch reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB)", file=sys.stderr)
     n_local = hi - lo
     n_bases_local = int(bases.numel())
     off_u64 = offsets.contiguous()

@@ -415,7 +415,8 @@ clb_status s1a_init(clb_ctx* c)
 {
 	CLB_CUDA(c, cudaMalloc(&c->d_scal, sizeof(unsigned long long) * SC_COUNT));
 	CLB_CUDA(c, cudaMemsetAsync(c->d_scal, 0, sizeof(unsigned long long) * SC_COUNT, c->stream));
-	const uint64_t exp_keys = c->prm.expected_bases / c->prm.modulo + c->prm.expected_bases / (4 * (uint64_t)c->prm.modulo);
+	// distinct keys <= passing occurrences ~ bases / f (the table grows by re-insertion if the hint was low)
+	const uint64_t exp_keys = c->prm.expected_bases / c->prm.modulo + c->prm.expected_bases / (32 * (uint64_t)c->prm.modulo);
 	c->tab_log2 = log2_for(exp_keys);
 	return tab_alloc(c, c->tab_log2, &c->tab);
 }

@@ -787,8 +787,11 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 	CLB_CUDA(c, cudaMemcpyAsync(d_slot, h_slot.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data() + pack_lo, sizeof(uint32_t) * (pack_hi - pack_lo + 1), cudaMemcpyHostToDevice, s));
 
-	DevBuf<Node>& nodes = c->s2_nodes; DevBuf<CandView>& cviews = c->s2_cviews; DevBuf<Task>& tasks = c->s2_tasks; DevBuf<char>& esbuf = c->s2_esbuf;
-	uint64_t n_nodes = n_slots, n_tasks = 0, es_used = 0;
+	DevBuf<Node>& nodes = c->s2_nodes; DevBuf<CandView>& cviews = c->s2_cviews; DevBuf<Task>& tasks = c->s2_tasks;
+	// scripts: one exactly-sized buffer per level wave, addressed absolutely (Task::es_off holds a device address), so that no
+	// wave has to copy the earlier ones into a bigger buffer
+	struct { char* p; } esbuf{nullptr};
+	uint64_t n_nodes = n_slots, n_tasks = 0;
 	CLB_CUDA(c, nodes.reserve(std::max<uint64_t>(n_nodes, 1), s, true, n_nodes));
 	CLB_CUDA(c, cviews.reserve(std::max<uint64_t>(n_nodes * P.c, 1), s, true, n_nodes * P.c));
 	clb_status st = CLB_OK;
@@ -808,7 +811,9 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 		st = exclusive_scan(c, d_capu, nn, d_coff, &ncap); if (st != CLB_OK) return st;
 		if (n_tasks + nt >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "more than 2^32 parts in one batch: lower CLB_BATCH_MBASES");
 		CLB_CUDA(c, tasks.reserve(n_tasks + nt, s, true, n_tasks));
-		CLB_CUDA(c, esbuf.reserve(es_used + ncap * 4 + 16, s, true, es_used));
+		char* level_buf = nullptr;
+		CLB_CUDA(c, mem.get(&level_buf, ncap * 4 + 16));
+		const uint64_t es_used = reinterpret_cast<uint64_t>(level_buf);
 		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, arena, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
 		CLB_LAUNCH_CHECK(c, "k_tasks<fill>");
 		tr.mark("level: task lists");
@@ -830,7 +835,7 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 		CLB_CUDA(c, cudaMemcpyAsync(&cur, d_cursor, sizeof(cur), cudaMemcpyDeviceToHost, s));
 		CLB_CUDA(c, cudaStreamSynchronize(s));
 		tr.mark("level: decide");
-		n_tasks += nt; es_used += ncap * 4;
+		n_tasks += nt;
 		n0 = n1; n_nodes = std::min<uint64_t>(cur, cap_nodes);
 		if (level > P.max_rec + 1) break;
 	}
