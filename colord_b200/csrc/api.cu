@@ -57,7 +57,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
-	c->qs.release();
+	c->qs.release(); c->ds.release();
 	{ cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, c->prm.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -238,6 +238,23 @@ clb_status clb_encode_candidates(clb_ctx* c, uint64_t* cand_off, uint32_t* data,
 	return CLB_OK;
 }
 
+clb_status clb_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs) { CLB_ENTER(c); return s3_dna_encode(c, level, pack_sizes, n_packs); }
+clb_status clb_dna_size(clb_ctx* c, uint64_t* total, uint64_t* header)
+{
+	CLB_ENTER(c);
+	if (!c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode has not run");
+	*total = c->ds_total; if (header) *header = c->ds_header;
+	return CLB_OK;
+}
+clb_status clb_dna_get(clb_ctx* c, uint8_t* stream, uint64_t cap, int on_device)
+{
+	CLB_ENTER(c);
+	if (!c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode has not run");
+	if (cap < c->ds_total) return fail(c, CLB_ERR_CAPACITY, "clb_dna_get: buffer too small");
+	CLB_CUDA(c, cudaMemcpyAsync(stream, c->ds.p, c->ds_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
 clb_status clb_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	CLB_ENTER(c);

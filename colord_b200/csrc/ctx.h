@@ -38,8 +38,8 @@ struct DevBuf {
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
 
 // kernel classes for the optional per-kernel timing (clb_profile_*)
-enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_DECIDE, K_ESTIMATE, K_EMIT, K_QUAL, K_N };
-static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual" };
+enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_DECIDE, K_ESTIMATE, K_EMIT, K_QUAL, K_DNA, K_N };
+static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna" };
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 } // namespace clb
@@ -132,6 +132,10 @@ struct clb_ctx {
 	bool qual_done = false;
 	clb::DevBuf<uint8_t> qs;         // native quality container
 	uint64_t qs_total = 0;
+	// ---- stage 3: DNA / edit-script stream ----
+	bool dna_done = false;
+	clb::DevBuf<uint8_t> ds;         // native DNA container
+	uint64_t ds_total = 0, ds_header = 0;
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)
@@ -171,6 +175,7 @@ void s1_free(clb_ctx* c);
 clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total);   // stage1b.cu; synchronizes
 clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* pack_sizes, uint32_t n_packs);
 void s2_free(clb_ctx* c);
+clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,

@@ -1,0 +1,274 @@
+// stage3_dna.cu — DNA / edit-script stream on device.
+//
+// Kept from the reference: the event model of CDNACoder (dna_model.h: which symbols a read's tuples turn into and the context
+// of each) and the arithmetic of its range coder (sub_rc.h:83-201: 64-bit low / range, carry-less renormalisation byte by
+// byte, 8-byte flush).  Replaced: the adaptive models whose state runs through the whole file (entr_read.h:56-80), which make
+// the reference's stream one serial chain.  Here pass 1 counts (family, context, symbol) triples of all reads with atomics,
+// the host turns the counts into static 12-bit frequency tables (rare contexts of the two big families share a fallback
+// table; metadata-sized work) and writes them into the container header, pass 2 codes every read pack with 64 independent
+// range-coder lanes (lane l takes reads l, l+64, ... of its pack), one thread per lane.  Native container "DB01"; decoder:
+// oracle/stage3_dna.c (it rebuilds the reads, which is the round-trip proof).
+#include "ctx.h"
+#include "dna_model.h"
+#include <algorithm>
+#include <cstring>
+#include <vector>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+namespace clb {
+
+constexpr uint32_t DB_LANES = 64, DB_PROB_BITS = 12, DB_M = 1u << DB_PROB_BITS, DB_MIN_CTX = 64;
+
+struct HistSink {
+	uint32_t* hist; const DnaModel* M;
+	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym) { atomicAdd(&hist[dna_entry(*M, f, ctx, sym)], 1u); }
+};
+// sub_rc.h:83-201 with totalFreqSum = 2^12
+struct RangeSink {
+	const uint32_t* tab; const DnaModel* M;
+	uint8_t* out; uint64_t n, cap;
+	unsigned long long low, range;
+	CLB_D void start() { low = 0; range = 0xff00000000000000ULL; n = 0; }
+	CLB_D void byte(uint8_t b) { if (n < cap) out[n] = b; ++n; }          // n past cap = overflow, reported by the host
+	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym)
+	{
+		const uint32_t e = tab[dna_entry(*M, f, ctx, sym)];
+		range >>= DB_PROB_BITS;
+		low += range * (e >> 16);
+		range *= (e & 0xffffu);
+		while (range <= 0x0000ffffffffffffULL) {
+			if ((low ^ (low + range)) & 0xff00000000000000ULL) { const unsigned long long r = low; range = (r | 0x0000ffffffffffffULL) - r; }
+			byte((uint8_t)(low >> 56));
+			low <<= 8; range <<= 8;
+		}
+	}
+	CLB_D void end() { for (int i = 0; i < 8; ++i) { byte((uint8_t)(low >> 56)); low <<= 8; } }
+};
+
+struct DArgs {
+	DnaReads R; DnaModel M;
+	const uint32_t* pack_first; uint32_t n_packs; uint32_t n_reads;
+	uint32_t* hist; const uint32_t* tab;
+};
+
+CLB_D uint32_t lane_flag_ctx(const DnaReads& R, uint32_t r, uint32_t pack_start)
+{
+	uint32_t c = 0;
+	for (int k = 4; k >= 1; --k) { const long long rr = (long long)r - (long long)DB_LANES * k; if (rr >= (long long)pack_start) c = ((c << 2) + read_flag_of(R, (uint32_t)rr)) & 0xff; }
+	return c;
+}
+
+// pass 1: one thread per read
+__global__ void __launch_bounds__(128) k_d_count(DArgs a)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= a.n_reads) return;
+	uint32_t lo = 0, hi = a.n_packs;              // pack of the read: last pack_first <= r
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.pack_first[mid] <= r) lo = mid; else hi = mid; }
+	HistSink s{a.hist, &a.M};
+	dna_walk(a.M, a.R, r, lane_flag_ctx(a.R, r, a.pack_first[lo]), s);
+}
+
+struct DEnc { uint32_t pack_lo, n_packs; const uint64_t* lane_off; uint8_t* tmp; uint32_t* lane_bytes; };
+
+// pass 2: one thread per (pack, lane)
+__global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
+{
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= e.n_packs * DB_LANES) return;
+	const uint32_t p = e.pack_lo + li / DB_LANES, l = li % DB_LANES;
+	const uint32_t r0 = a.pack_first[p], r1 = a.pack_first[p + 1];
+	RangeSink s{a.tab, &a.M, e.tmp + e.lane_off[li], 0, e.lane_off[li + 1] - e.lane_off[li], 0, 0};
+	s.start();
+	uint32_t fctx = 0;
+	for (uint32_t r = r0 + l; r < r1; r += DB_LANES) {
+		dna_walk(a.M, a.R, r, fctx, s);
+		fctx = ((fctx << 2) + read_flag_of(a.R, r)) & 0xff;
+	}
+	s.end();
+	e.lane_bytes[li] = (uint32_t)s.n;
+}
+
+__global__ void __launch_bounds__(128) k_d_gather(DArgs a, DEnc e, const uint64_t* __restrict__ dst_off, const uint64_t* __restrict__ pack_hdr_off, uint8_t* __restrict__ out)
+{
+	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (li >= e.n_packs * DB_LANES) return;
+	const uint32_t nb = e.lane_bytes[li];
+	uint8_t* d = out + dst_off[li];
+	const uint8_t* w = e.tmp + e.lane_off[li];
+	if (lane == 0) {
+		const uint32_t p = li / DB_LANES, l = li % DB_LANES;
+		uint8_t* h = out + pack_hdr_off[p];
+		h[4 + 4 * l] = (uint8_t)nb; h[5 + 4 * l] = (uint8_t)(nb >> 8); h[6 + 4 * l] = (uint8_t)(nb >> 16); h[7 + 4 * l] = (uint8_t)(nb >> 24);
+		if (l == 0) { const uint32_t np = a.pack_first[e.pack_lo + p + 1] - a.pack_first[e.pack_lo + p]; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
+	}
+	for (uint32_t k = lane; k < nb; k += 32) d[k] = w[k];
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
+{
+	uint64_t tot = 0; uint32_t best = 0;
+	for (uint32_t i = 0; i < n; ++i) { tot += cnt[i]; if (cnt[i] > cnt[best]) best = i; }
+	if (!tot) { for (uint32_t i = 0; i < n; ++i) f[i] = 0; return; }
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < n; ++i) { uint32_t v = (uint32_t)(((uint64_t)cnt[i] << DB_PROB_BITS) / tot); if (cnt[i] && !v) v = 1; f[i] = (uint16_t)v; sum += v; }
+	if (sum > DB_M) {                        // the +1 floors of many rare symbols can overshoot: take it from the largest ones
+		uint32_t over = sum - DB_M;
+		while (over) { uint32_t b = 0; for (uint32_t i = 1; i < n; ++i) if (f[i] > f[b]) b = i; const uint32_t d = std::min<uint32_t>(over, f[b] - 1); f[b] = (uint16_t)(f[b] - d); over -= d; if (!d) break; }
+	} else f[best] = (uint16_t)(f[best] + DB_M - sum);
+}
+template <typename T> static void put(std::vector<uint8_t>& o, const T& v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); o.insert(o.end(), p, p + sizeof(T)); }
+// frequencies of one context: alphabets up to 8 as a presence mask + all present frequencies but the last; larger ones as a list
+static void put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
+{
+	if (A <= 8) {
+		uint8_t mask = 0; int last = -1;
+		for (uint32_t k = 0; k < A; ++k) if (f[k]) { mask |= (uint8_t)(1u << k); last = (int)k; }
+		o.push_back(mask);
+		for (int k = 0; k < last; ++k) if (f[k]) put(o, f[k]);
+	} else {
+		uint16_t nz = 0; for (uint32_t k = 0; k < A; ++k) nz += f[k] != 0;
+		put(o, nz);
+		for (uint32_t k = 0; k < A; ++k) if (f[k]) { o.push_back((uint8_t)k); put(o, f[k]); }
+	}
+}
+
+clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	cudaStream_t s = c->stream;
+	const uint64_t n = c->n_reads;
+	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode needs the tuples (clb_encode)");
+	if (c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode called twice");
+	if (level < 1 || level > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_dna_encode: level must be 1, 2 or 3");
+	if (c->prm.max_candidates > 32) return fail(c, CLB_ERR_BAD_ARG, "clb_dna_encode: max_candidates above 32 is not supported");
+	const DnaModel M = make_dna_model(level, c->prm.max_candidates);
+	std::vector<uint32_t> pack_first{0};
+	if (pack_sizes) {
+		uint64_t at = 0;
+		for (uint32_t i = 0; i < n_packs; ++i) { at += pack_sizes[i]; if (pack_sizes[i]) pack_first.push_back((uint32_t)at); }
+		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
+	} else {
+		uint64_t bytes = 0;
+		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
+		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
+	}
+	const uint32_t np = (uint32_t)pack_first.size() - 1;
+	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t bytes, Tmp& t) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s); if (e == cudaSuccess) t.v.push_back(*p); return e; };
+	const uint64_t n_entries = M.base[F_COUNT];
+	uint32_t* d_hist = nullptr; uint32_t* d_pack_first = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_hist, sizeof(uint32_t) * n_entries, tmp));
+	CLB_CUDA(c, dalloc((void**)&d_pack_first, sizeof(uint32_t) * (np + 1), tmp));
+	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * n_entries, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice, s));
+	DArgs a{};
+	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off};
+	a.M = M; a.pack_first = d_pack_first; a.n_packs = np; a.n_reads = (uint32_t)n; a.hist = d_hist;
+	if (n) { CLB_TIMED(c, K_DNA, (k_d_count<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_d_count"); }
+	// ---- counts -> static tables + container header (host, metadata-sized) ----
+	std::vector<uint32_t> hist(n_entries);
+	CLB_CUDA(c, cudaMemcpyAsync(hist.data(), d_hist, sizeof(uint32_t) * n_entries, cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	std::vector<uint32_t> tab(n_entries, 0);
+	std::vector<uint8_t> hdr;
+	hdr.insert(hdr.end(), {'D', 'B', '0', '1'}); put(hdr, level); put(hdr, c->prm.max_candidates); put(hdr, (uint64_t)n); put(hdr, np);
+	std::vector<uint16_t> fr(256);
+	for (uint32_t f = 0; f < F_COUNT; ++f) {
+		const uint32_t A = M.A[f]; const uint64_t n_ctx = 1ull << M.cbits[f], n_fb = M.fbits[f] ? (1ull << M.fbits[f]) : 0;
+		const uint32_t* h = hist.data() + M.base[f]; uint32_t* tb = tab.data() + M.base[f];
+		std::vector<uint32_t> fbh(n_fb * A, 0); std::vector<uint16_t> fbf(n_fb * A, 0);
+		std::vector<uint8_t> dense(n_ctx, 0);
+		uint32_t nd = 0;
+		for (uint64_t x = 0; x < n_ctx; ++x) {
+			uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
+			if (!t) continue;
+			if (!n_fb || t >= DB_MIN_CTX) { dense[x] = 1; ++nd; }
+			else for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
+		}
+		for (uint64_t x = 0; x < n_fb; ++x) { normalise(&fbh[x * A], A, &fbf[x * A]); put_freqs(hdr, &fbf[x * A], A); }
+		put(hdr, nd);
+		uint64_t prev = 0;
+		for (uint64_t x = 0; x < n_ctx; ++x) {
+			const uint16_t* src;
+			if (dense[x]) {
+				normalise(&h[x * A], A, fr.data()); src = fr.data();
+				uint64_t gap = x - prev; prev = x;
+				do { uint8_t by = (uint8_t)(gap & 127); gap >>= 7; if (gap) by |= 128; hdr.push_back(by); } while (gap);
+				put_freqs(hdr, src, A);
+			} else if (n_fb) src = &fbf[(x & (n_fb - 1)) * A];
+			else continue;
+			uint32_t acc = 0; for (uint32_t k = 0; k < A; ++k) { tb[x * A + k] = src[k] | (acc << 16); acc += src[k]; }
+		}
+		if (std::getenv("CLB_S2_TRACE")) {      // where the bits go: events, cost under the static tables, empirical context entropy
+			double ev = 0, cost = 0, ent = 0;
+			for (uint64_t x = 0; x < n_ctx; ++x) {
+				uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
+				if (!t) continue;
+				for (uint32_t k = 0; k < A; ++k) if (h[x * A + k]) {
+					const double cn = h[x * A + k];
+					ev += cn; cost += cn * -std::log2((tb[x * A + k] & 0xffff) / 4096.0); ent += cn * -std::log2(cn / (double)t);
+				}
+			}
+			fprintf(stderr, "[s3d] family %2u: %12.0f events, %12.0f bytes coded, %12.0f bytes empirical, %u dense contexts\n", f, ev, cost / 8, ent / 8, nd);
+		}
+	}
+	uint32_t* d_tab = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint32_t) * n_entries, tmp));
+	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * n_entries, cudaMemcpyHostToDevice, s));
+	a.tab = d_tab;
+	// ---- pass 2 in chunks of packs: a lane's temp holds at most 3 bytes per tuple byte + the flush ----
+	std::vector<uint64_t> es_off(n + 1);
+	CLB_CUDA(c, cudaMemcpyAsync(es_off.data(), c->es_off, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	CLB_CUDA(c, c->ds.reserve(hdr.size() + c->es_total / 4 + (uint64_t)np * (4 + 12 * DB_LANES) + 1024, s, false));
+	CLB_CUDA(c, cudaMemcpyAsync(c->ds.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
+	uint64_t out_at = hdr.size();
+	const uint64_t chunk_bytes = 3ull << 30;
+	for (uint32_t p0 = 0; p0 < np;) {
+		uint32_t p1 = p0; uint64_t need = 0;
+		// worst case per read: <= 2 events (3 bytes) per tuple byte, anchor / skip lengths in chunks of 22 / 254, header and flush
+		auto read_need = [&](uint32_t r) { return 3 * (es_off[r + 1] - es_off[r]) + c->h_rd_len[r] / 8 + 4096ull; };
+		auto pack_need = [&](uint32_t p) { uint64_t t = 16ull * DB_LANES; for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) t += read_need(r); return t; };
+		while (p1 < np && (p1 == p0 || need + pack_need(p1) <= chunk_bytes)) { need += pack_need(p1); ++p1; }
+		const uint32_t cp = p1 - p0, nl = cp * DB_LANES;
+		std::vector<uint64_t> lane_off(nl + 1, 0);
+		for (uint32_t p = p0; p < p1; ++p) {
+			for (uint32_t l = 0; l < DB_LANES; ++l) lane_off[(size_t)(p - p0) * DB_LANES + l + 1] = 16;
+			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * DB_LANES + (r - pack_first[p]) % DB_LANES + 1] += read_need(r);
+		}
+		for (uint32_t i = 0; i < nl; ++i) lane_off[i + 1] += lane_off[i];
+		Tmp ct{{}, s};
+		uint64_t* d_lane_off = nullptr; uint8_t* d_tmp = nullptr; uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
+		CLB_CUDA(c, dalloc((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1), ct)); CLB_CUDA(c, dalloc((void**)&d_tmp, lane_off[nl] + 16, ct));
+		CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl, ct)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl, ct)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * cp, ct));
+		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
+		DEnc e{p0, cp, d_lane_off, d_tmp, d_bytes};
+		CLB_TIMED(c, K_DNA, (k_d_encode<<<(nl + 63) / 64, 64, 0, s>>>(a, e)));
+		CLB_LAUNCH_CHECK(c, "k_d_encode");
+		std::vector<uint32_t> bytes(nl);
+		CLB_CUDA(c, cudaMemcpyAsync(bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		for (uint32_t i = 0; i < nl; ++i) if (bytes[i] > lane_off[i + 1] - lane_off[i]) return fail(c, CLB_ERR_CAPACITY, "clb_dna_encode: a lane outgrew its worst-case buffer");
+		std::vector<uint64_t> dst(nl), phdr(cp);
+		for (uint32_t p = 0; p < cp; ++p) {
+			phdr[p] = out_at; out_at += 4 + 4 * DB_LANES;
+			for (uint32_t l = 0; l < DB_LANES; ++l) { dst[(size_t)p * DB_LANES + l] = out_at; out_at += bytes[(size_t)p * DB_LANES + l]; }
+		}
+		CLB_CUDA(c, c->ds.reserve(out_at + 16, s, true, phdr[0]));
+		CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
+		CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * cp, cudaMemcpyHostToDevice, s));
+		CLB_TIMED(c, K_DNA, (k_d_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e, d_dst, d_phdr, c->ds.p)));
+		CLB_LAUNCH_CHECK(c, "k_d_gather");
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		p0 = p1;
+	}
+	c->ds_total = out_at;
+	c->ds_header = hdr.size();
+	c->dna_done = true;
+	return CLB_OK;
+}
+
+} // namespace clb

@@ -17,9 +17,9 @@ EXPORTS = [
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
-    "clb_qual_encode", "clb_qual_size", "clb_qual_get",
+    "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get",
 ]
-KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual"]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna"]
 
 
 class Params(C.Structure):
@@ -93,6 +93,9 @@ def load():
     L.clb_encode_keep_candidates.argtypes = [vp, i32]
     L.clb_encode_candidates_size.argtypes = [vp, C.POINTER(u64)]
     L.clb_encode_candidates.argtypes = [vp, vp, vp, u64]
+    L.clb_dna_encode.argtypes = [vp, u32, vp, u32]
+    L.clb_dna_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.clb_dna_get.argtypes = [vp, vp, u64, i32]
     L.clb_qual_encode.argtypes = [vp, C.POINTER(QualParams), vp, vp, i32, vp, u32]
     L.clb_qual_size.argtypes = [vp, C.POINTER(u64)]
     L.clb_qual_get.argtypes = [vp, vp, u64, i32]
@@ -345,6 +348,19 @@ class Context:
         return out
 
     # ---- stage 3
+    def dna_encode(self, level, pack_sizes=None):
+        """DNA / edit-script stream of all reads from the tuples of encode() (native container DB01)."""
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        self._ck(self.L.clb_dna_encode(self.h, level, None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+
+    def dna_stream(self):
+        """-> (container bytes, bytes of its table header)."""
+        n, h = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.clb_dna_size(self.h, C.byref(n), C.byref(h)))
+        out = np.zeros(max(n.value, 1), np.uint8)
+        self._ck(self.L.clb_dna_get(self.h, _np_ptr(out), n.value, 0))
+        return out[:n.value], h.value
+
     def qual_encode(self, n_bins, thresholds, level, quals, offsets, pack_sizes=None, on_device=False):
         """Quality stream of all appended reads (native container QB01).  quals/offsets: numpy arrays, or device pointers (ints)."""
         prm = QualParams()

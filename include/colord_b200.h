@@ -147,6 +147,19 @@ clb_status clb_encode_keep_candidates(clb_ctx* ctx, int on);
 clb_status clb_encode_candidates_size(clb_ctx* ctx, uint64_t* n_words);
 clb_status clb_encode_candidates(clb_ctx* ctx, uint64_t* cand_off, uint32_t* data, uint64_t cap_words);
 
+/* ---- Stage 3: DNA / edit-script stream --------------------------------------------------------------
+ * Replaces CEntrComprReads::Compress -> CDNACoder::Encode (entr_read.h:56-80, dna_coder.cpp:26-231) over the tuples clb_encode
+ * left on the device.  The reference's event model is kept (which symbols a read's tuples turn into and the context of each one:
+ * read flag, length, plain symbols, reference ids, reverse-complement flags, tuple types under the tuple / symbol histories +
+ * reference base + indel drift, anchor / skip lengths, insertions, substitutions, alternative reads — dna_coder.cpp:440-1239),
+ * and so is the arithmetic of its range coder (sub_rc.h:83-201); the adaptive models running through the whole file are
+ * replaced by static per-context tables (two passes) and 64 independent coder lanes per read pack.  Native container "DB01";
+ * decoder (rebuilds the reads): oracle/stage3_dna.c.  level = compressionLevel (1..3: history widths, dna_coder.cpp:1253-1280). */
+clb_status clb_dna_encode(clb_ctx* ctx, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
+/* header_bytes (may be NULL): the part of the container that holds the frequency tables */
+clb_status clb_dna_size(clb_ctx* ctx, uint64_t* total_bytes, uint64_t* header_bytes);
+clb_status clb_dna_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
+
 /* ---- Stage 3: quality stream ------------------------------------------------------------------------
  * Replaces CEntrComprQuals::Compress -> CQualityCoder::Encode (entr_qual.h:100-126, quality_coder.cpp:560) for the "*-avg"
  * modes (ONT default 4-avg, HiFi default 5-avg, 2-avg): the reference's lossy transform and context model
@@ -182,7 +195,7 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
 /* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
  * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
- * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit, k_qual.  clb_profile_get synchronizes the stream. */
+ * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit, k_qual, k_dna.  clb_profile_get synchronizes the stream. */
 clb_status clb_profile_enable(clb_ctx* ctx, int on);
 clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 

@@ -221,3 +221,15 @@ def qual_decode(stream, bases, offsets, es=None, es_off=None):
                            len(offsets) - 1, esp, eop, out)
     assert rc == 0, rc
     return out
+
+
+def dna_decode(stream, n_reads, is_ref, cap_bases):
+    """Decoder of the native DNA container (oracle/stage3_dna.c) -> (bases ASCII, offsets)."""
+    L = lib()
+    L.orc_dna_decode.restype = C.c_int64
+    L.orc_dna_decode.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u8p, _u8p, C.c_uint64, _u64p]
+    out = np.zeros(int(cap_bases) + 16, np.uint8)
+    off = np.zeros(n_reads + 1, np.uint64)
+    rc = L.orc_dna_decode(np.ascontiguousarray(stream, np.uint8), len(stream), n_reads, np.ascontiguousarray(is_ref, np.uint8), out, int(cap_bases), off)
+    assert rc == 0, rc
+    return out[:int(off[-1])], off

@@ -61,3 +61,49 @@ def test_quality_stream_size_vs_reference():
     assert len(got) <= 1.005 * 18_452_133, len(got)
     lossy = oracle_lib.qual_lossy(oracle_lib.qual_params(4, [7, 14, 26], 1), s.bases, s.quals, s.offsets)
     assert np.array_equal(oracle_lib.qual_decode(got, s.bases, s.offsets), lossy)
+
+
+# ------------------------------------------------------------------------------------------------ DNA / edit-script stream
+def _dna_round_trip(s, k, f, lo, hi, c, P, level, sparse_g=None, packs=None, is_hifi=False):
+    n = s.n_reads
+    with lib.Context(k, f, lo, hi, c, is_hifi=is_hifi) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        st = ctx.count_finalize()
+        if sparse_g is None:
+            sampled = np.ones(n, np.uint8)
+        else:      # compression.cpp:443, :501-503
+            mean_len = int(st["tot_kmers"] * f / max(1, st["n_reads"]) + k - 1)
+            sampled = lib.sampler(max(1, int(sparse_g * st["n_unique_counted"] * f / max(1, mean_len))), 1.0, 0, n)
+        ctx.graph_build(sampled)
+        ctx.encode(P, packs)
+        ctx.dna_encode(level, packs)
+        stream, hdr = ctx.dna_stream()
+        tuples = ctx.encode_size()
+    has_n = np.array([(s.bases[int(s.offsets[i]):int(s.offsets[i + 1])] == ord("N")).any() for i in range(n)], np.uint8)
+    is_ref = (sampled & (1 - has_n)).astype(np.uint8)
+    bases, off = oracle_lib.dna_decode(stream, n, is_ref, s.n_bases)
+    assert np.array_equal(off, s.offsets)
+    assert np.array_equal(bases, s.bases)
+    return len(stream), hdr, tuples
+
+
+@pytest.mark.parametrize("level,prof", [(1, "ont"), (2, "ont"), (3, "clr")])
+def test_dna_stream_round_trip(level, prof):
+    """Device container -> independent C decoder -> the input reads, byte for byte (plain reads, reads with N, edit scripts,
+    alternative reads, skips, every history width)."""
+    s = synth.generate(800, 150000, 3000, seed=40 + level, profile=prof, n_frac=0.02)
+    P = dict(P_BAL, min_part_len_alt=64 if level == 1 else 48, max_recurence=3 if level == 1 else 5)
+    size, hdr, tuples = _dna_round_trip(s, 20, 9, 3, 100, 8, P, level, packs=[300, 1, 499])
+    assert size < tuples
+
+
+def test_dna_stream_size_vs_reference():
+    """12 500 synthetic ONT reads / 100 Mbases (BASELINE.md §2 recipe, seed 1) at the compress-ont default (k20 a16 f12 L4 H80 c5
+    sparse g=1, level 1): the unmodified reference writes an 18 231 949-byte DNA stream.  The tuples are the
+    reference's own (bit-exact stage 2), so the two coders see the same events."""
+    s = synth.generate(12500, 5_000_000, 8000, seed=1, profile="ont")
+    P = dict(anchor_len=16, k=20, modulo=12, hifi=0, min_part_len_alt=64, max_recurence=3, min_anchors=1,
+             min_mmer_frac=0.5, min_mmer_force=0.9, max_matches_mult=10.0, es_cost_mult=1.0)
+    size, hdr, tuples = _dna_round_trip(s, 20, 12, 4, 80, 5, P, 1, sparse_g=1.0)
+    print(f"native DNA container {size} B (tables {hdr} B) vs reference 18231949 B: {size / 18231949:.4f}")
+    assert size <= 1.005 * 18_231_949, (size, hdr)
