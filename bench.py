@@ -6,7 +6,7 @@ canonical k-mer scan + murmur64 % f filter + count table, thresholding into the 
 read, similarity graph with top-c candidates) and STAGE 2 (m-mer anchors against the candidates, edit scripts of the
 parts between anchors, edit-script / plain / alternative-read decisions, CompactES tuples).  Stage 3 (entropy coders) is
 represented by its quality stream (the reference's lossy 4-avg transform + context model, static tables, interleaved rANS;
-the DNA-tuple and header coders are not on the device yet); `config.stages` says so and the reference arm times the SAME
+and the DNA-tuple stream, both in native containers; the header coder is not on the device yet); `config.stages` says so and the reference arm times the SAME
 stages of the reference (`--stages 1` / `--stages 12` restrict both arms).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--gbases G] [--impl reference]
@@ -185,7 +185,7 @@ def cpu_baseline(sample_reads=12500, stages="12"):
         desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
             r = run_reference_stage1(fq, cores, stages)
-            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
+            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12qd": "+CEncoder threads+CEntrComprReads+CEntrComprQuals (stages 1+2+3 without the header coder)", "12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
             return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
                     "sample": desc + "; unmodified reference " + what, "detail": r}
         dt = run_port_stage1(s)
@@ -222,6 +222,7 @@ def main_reference(args):
 
 def metric_name(args):
     return "input MB/s, compress-ont default, " + {
+        "12qd": "stages 1+2+3 without headers (k-mer filter, similarity graph, anchors + edit scripts -> tuples, DNA-tuple and 4-avg quality entropy coders)",
         "12q": "stages 1+2 + quality stream of stage 3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, 4-avg quality coder)",
         "12": "stages 1+2 (k-mer filter, similarity graph, anchors + edit scripts -> tuples)",
         "1": "stage 1 (k-mer filter + similarity graph)"}[args.stages]
@@ -231,7 +232,8 @@ def workload_config(args, n_reads):
     return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
                         f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] * args.gbases / 25.0 / 1e9:.3g} Gb = 20.8x, 10% errors)",
             "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1)" % NS_S2["anchor_len"]
-                       + ("; stage 3: quality stream (4-avg, thresholds 7 14 26) only — DNA-tuple and header coders not on device yet" if args.stages == "12q" else "; stage 3 not included"))
+                       + {"12qd": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) in native containers; header coder not on device yet",
+                          "12q": "; stage 3: quality stream (4-avg, thresholds 7 14 26) only", "12": "; stage 3 not included"}[args.stages])
                       if args.stages != "1" else "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph)",
             "n_reads": n_reads, "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"reads sharded by id over {args.gpus} GPU(s)"}
 
@@ -243,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
-    ap.add_argument("--stages", default="12q", choices=["1", "12", "12q"], help="hot-path stages inside a step (both arms); q = quality stream of stage 3")
+    ap.add_argument("--stages", default="12qd", choices=["1", "12", "12q", "12qd"], help="hot-path stages inside a step (both arms); q / d = quality / DNA-tuple stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -277,7 +279,7 @@ def main():
     del genome
     torch.cuda.empty_cache()
     quals = None
-    if args.stages == "12q":      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
+    if args.stages in ("12q", "12qd"):      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
         quals = torch.empty(bases.numel(), dtype=torch.uint8, device=device)
         gq = torch.Generator(device=device)
         gq.manual_seed(4242 + rank)
@@ -315,18 +317,23 @@ def main():
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
         ctx.graph_build(sampled)
         out = None
-        if args.stages in ("12", "12q"):
+        if args.stages in ("12", "12q", "12qd"):
             ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
-            if args.stages == "12q":
+            if args.stages == "12qd":
+                ctx.dna_encode(1)
+            if args.stages in ("12q", "12qd"):
                 if host_quals is None:
                     ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
                 else:
                     ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
-            if readback:           # what leaves the device: the tuples (they feed the DNA entropy coder) and the finished quality stream
-                out = ctx.encoded(n_local)
-                if args.stages == "12q":
-                    out = out + (ctx.qual_stream(),)
+            if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
+                if args.stages == "12qd":
+                    out = (ctx.dna_stream()[0], ctx.qual_stream())
+                else:
+                    out = ctx.encoded(n_local)
+                    if args.stages == "12q":
+                        out = out + (ctx.qual_stream(),)
         elif readback:
             out = ctx.graph_candidates()
         ctx.synchronize()
@@ -389,7 +396,8 @@ def main():
                "k_anchors": 0.25 * (1 + 2 * p["max_candidates"]),      # the read + both strands of c candidates, 2-bit packed
                "k_align": 0.25 + 0.25 + 1.0,                           # the two parts (2-bit) read, one script byte written per symbol
                "k_decide": 1.0, "k_emit": 1.0 + 1.25,                  # scripts read, CompactES bytes written
-               "k_qual": 2 * (1.0 + 0.25) + 0.25}                      # two passes over qualities + packed bases, stream written
+               "k_qual": 2 * (1.0 + 0.25) + 0.25,                      # two passes over qualities + packed bases, stream written
+               "k_dna": 2 * (1.25 + 0.25) + 0.25}                      # two passes over the tuples + reference bases for the contexts, stream written
         per_step = {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}
         roof = None
         if per_step:

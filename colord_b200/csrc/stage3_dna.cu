@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 namespace clb {
 
@@ -31,7 +32,7 @@ struct RangeSink {
 	uint8_t* out; uint64_t n, cap;
 	unsigned long long low, range;
 	CLB_D void start() { low = 0; range = 0xff00000000000000ULL; n = 0; }
-	CLB_D void byte(uint8_t b) { if (n < cap) out[n] = b; ++n; }          // n past cap = overflow, reported by the host
+	CLB_D void byte(uint8_t b) { if (out) out[n] = b; ++n; }              // out == nullptr: sizing pass
 	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym)
 	{
 		const uint32_t e = tab[dna_entry(*M, f, ctx, sym)];
@@ -71,16 +72,18 @@ __global__ void __launch_bounds__(128) k_d_count(DArgs a)
 	dna_walk(a.M, a.R, r, lane_flag_ctx(a.R, r, a.pack_first[lo]), s);
 }
 
-struct DEnc { uint32_t pack_lo, n_packs; const uint64_t* lane_off; uint8_t* tmp; uint32_t* lane_bytes; };
+struct DEnc { uint32_t* lane_bytes; const uint64_t* dst_off; const uint64_t* pack_hdr_off; uint8_t* out; };
 
-// pass 2: one thread per (pack, lane)
+// pass 2: one thread per (pack, lane).  WRITE = false sizes the lane streams (the coder's output length does not depend on
+// where it is stored), WRITE = true writes them — and the pack headers — at their final place in the container.
+template <bool WRITE>
 __global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
 {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-	if (li >= e.n_packs * DB_LANES) return;
-	const uint32_t p = e.pack_lo + li / DB_LANES, l = li % DB_LANES;
+	if (li >= a.n_packs * DB_LANES) return;
+	const uint32_t p = li / DB_LANES, l = li % DB_LANES;
 	const uint32_t r0 = a.pack_first[p], r1 = a.pack_first[p + 1];
-	RangeSink s{a.tab, &a.M, e.tmp + e.lane_off[li], 0, e.lane_off[li + 1] - e.lane_off[li], 0, 0};
+	RangeSink s{a.tab, &a.M, WRITE ? e.out + e.dst_off[li] : nullptr, 0, 0, 0, 0};
 	s.start();
 	uint32_t fctx = 0;
 	for (uint32_t r = r0 + l; r < r1; r += DB_LANES) {
@@ -88,26 +91,20 @@ __global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
 		fctx = ((fctx << 2) + read_flag_of(a.R, r)) & 0xff;
 	}
 	s.end();
-	e.lane_bytes[li] = (uint32_t)s.n;
-}
-
-__global__ void __launch_bounds__(128) k_d_gather(DArgs a, DEnc e, const uint64_t* __restrict__ dst_off, const uint64_t* __restrict__ pack_hdr_off, uint8_t* __restrict__ out)
-{
-	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	if (li >= e.n_packs * DB_LANES) return;
-	const uint32_t nb = e.lane_bytes[li];
-	uint8_t* d = out + dst_off[li];
-	const uint8_t* w = e.tmp + e.lane_off[li];
-	if (lane == 0) {
-		const uint32_t p = li / DB_LANES, l = li % DB_LANES;
-		uint8_t* h = out + pack_hdr_off[p];
-		h[4 + 4 * l] = (uint8_t)nb; h[5 + 4 * l] = (uint8_t)(nb >> 8); h[6 + 4 * l] = (uint8_t)(nb >> 16); h[7 + 4 * l] = (uint8_t)(nb >> 24);
-		if (l == 0) { const uint32_t np = a.pack_first[e.pack_lo + p + 1] - a.pack_first[e.pack_lo + p]; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
-	}
-	for (uint32_t k = lane; k < nb; k += 32) d[k] = w[k];
+	if (!WRITE) { e.lane_bytes[li] = (uint32_t)s.n; return; }
+	uint8_t* h = e.out + e.pack_hdr_off[p];
+	const uint32_t nb = (uint32_t)s.n;
+	h[4 + 4 * l] = (uint8_t)nb; h[5 + 4 * l] = (uint8_t)(nb >> 8); h[6 + 4 * l] = (uint8_t)(nb >> 16); h[7 + 4 * l] = (uint8_t)(nb >> 24);
+	if (l == 0) { const uint32_t np = r1 - r0; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+struct DTrace {            // CLB_S2_TRACE=1: wall time of every phase (synchronising; debugging aid)
+	bool on; cudaStream_t s; double t0;
+	static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	explicit DTrace(cudaStream_t st) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), t0(now()) {}
+	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s3d] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
+};
 static void normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
 {
 	uint64_t tot = 0; uint32_t best = 0;
@@ -139,6 +136,7 @@ static void put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
 clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	cudaStream_t s = c->stream;
+	DTrace tr(s);
 	const uint64_t n = c->n_reads;
 	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode needs the tuples (clb_encode)");
 	if (c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode called twice");
@@ -168,6 +166,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off};
 	a.M = M; a.pack_first = d_pack_first; a.n_packs = np; a.n_reads = (uint32_t)n; a.hist = d_hist;
 	if (n) { CLB_TIMED(c, K_DNA, (k_d_count<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_d_count"); }
+	tr.mark("k_d_count");
 	// ---- counts -> static tables + container header (host, metadata-sized) ----
 	std::vector<uint32_t> hist(n_entries);
 	CLB_CUDA(c, cudaMemcpyAsync(hist.data(), d_hist, sizeof(uint32_t) * n_entries, cudaMemcpyDeviceToHost, s));
@@ -202,7 +201,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 			else continue;
 			uint32_t acc = 0; for (uint32_t k = 0; k < A; ++k) { tb[x * A + k] = src[k] | (acc << 16); acc += src[k]; }
 		}
-		if (std::getenv("CLB_S2_TRACE")) {      // where the bits go: events, cost under the static tables, empirical context entropy
+		if (std::getenv("CLB_S3_BITS")) {      // where the bits go: events, cost under the static tables, empirical context entropy
 			double ev = 0, cost = 0, ent = 0;
 			for (uint64_t x = 0; x < n_ctx; ++x) {
 				uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
@@ -219,52 +218,31 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint32_t) * n_entries, tmp));
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * n_entries, cudaMemcpyHostToDevice, s));
 	a.tab = d_tab;
-	// ---- pass 2 in chunks of packs: a lane's temp holds at most 3 bytes per tuple byte + the flush ----
-	std::vector<uint64_t> es_off(n + 1);
-	CLB_CUDA(c, cudaMemcpyAsync(es_off.data(), c->es_off, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
+	tr.mark("tables (host)");
+	// ---- pass 2: size every lane stream, lay the container out, write ----
+	const uint32_t nl = np * DB_LANES;
+	uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl, tmp)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl, tmp)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * np, tmp));
+	DEnc e{d_bytes, d_dst, d_phdr, nullptr};
+	if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<size>"); }
+	std::vector<uint32_t> bytes(nl);
+	CLB_CUDA(c, cudaMemcpyAsync(bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	CLB_CUDA(c, c->ds.reserve(hdr.size() + c->es_total / 4 + (uint64_t)np * (4 + 12 * DB_LANES) + 1024, s, false));
-	CLB_CUDA(c, cudaMemcpyAsync(c->ds.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
+	tr.mark("k_d_encode<size>");
 	uint64_t out_at = hdr.size();
-	const uint64_t chunk_bytes = 3ull << 30;
-	for (uint32_t p0 = 0; p0 < np;) {
-		uint32_t p1 = p0; uint64_t need = 0;
-		// worst case per read: <= 2 events (3 bytes) per tuple byte, anchor / skip lengths in chunks of 22 / 254, header and flush
-		auto read_need = [&](uint32_t r) { return 3 * (es_off[r + 1] - es_off[r]) + c->h_rd_len[r] / 8 + 4096ull; };
-		auto pack_need = [&](uint32_t p) { uint64_t t = 16ull * DB_LANES; for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) t += read_need(r); return t; };
-		while (p1 < np && (p1 == p0 || need + pack_need(p1) <= chunk_bytes)) { need += pack_need(p1); ++p1; }
-		const uint32_t cp = p1 - p0, nl = cp * DB_LANES;
-		std::vector<uint64_t> lane_off(nl + 1, 0);
-		for (uint32_t p = p0; p < p1; ++p) {
-			for (uint32_t l = 0; l < DB_LANES; ++l) lane_off[(size_t)(p - p0) * DB_LANES + l + 1] = 16;
-			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * DB_LANES + (r - pack_first[p]) % DB_LANES + 1] += read_need(r);
-		}
-		for (uint32_t i = 0; i < nl; ++i) lane_off[i + 1] += lane_off[i];
-		Tmp ct{{}, s};
-		uint64_t* d_lane_off = nullptr; uint8_t* d_tmp = nullptr; uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
-		CLB_CUDA(c, dalloc((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1), ct)); CLB_CUDA(c, dalloc((void**)&d_tmp, lane_off[nl] + 16, ct));
-		CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl, ct)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl, ct)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * cp, ct));
-		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
-		DEnc e{p0, cp, d_lane_off, d_tmp, d_bytes};
-		CLB_TIMED(c, K_DNA, (k_d_encode<<<(nl + 63) / 64, 64, 0, s>>>(a, e)));
-		CLB_LAUNCH_CHECK(c, "k_d_encode");
-		std::vector<uint32_t> bytes(nl);
-		CLB_CUDA(c, cudaMemcpyAsync(bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
-		CLB_CUDA(c, cudaStreamSynchronize(s));
-		for (uint32_t i = 0; i < nl; ++i) if (bytes[i] > lane_off[i + 1] - lane_off[i]) return fail(c, CLB_ERR_CAPACITY, "clb_dna_encode: a lane outgrew its worst-case buffer");
-		std::vector<uint64_t> dst(nl), phdr(cp);
-		for (uint32_t p = 0; p < cp; ++p) {
-			phdr[p] = out_at; out_at += 4 + 4 * DB_LANES;
-			for (uint32_t l = 0; l < DB_LANES; ++l) { dst[(size_t)p * DB_LANES + l] = out_at; out_at += bytes[(size_t)p * DB_LANES + l]; }
-		}
-		CLB_CUDA(c, c->ds.reserve(out_at + 16, s, true, phdr[0]));
-		CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
-		CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * cp, cudaMemcpyHostToDevice, s));
-		CLB_TIMED(c, K_DNA, (k_d_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e, d_dst, d_phdr, c->ds.p)));
-		CLB_LAUNCH_CHECK(c, "k_d_gather");
-		CLB_CUDA(c, cudaStreamSynchronize(s));
-		p0 = p1;
+	std::vector<uint64_t> dst(nl), phdr(np);
+	for (uint32_t p = 0; p < np; ++p) {
+		phdr[p] = out_at; out_at += 4 + 4 * DB_LANES;
+		for (uint32_t l = 0; l < DB_LANES; ++l) { dst[(size_t)p * DB_LANES + l] = out_at; out_at += bytes[(size_t)p * DB_LANES + l]; }
 	}
+	CLB_CUDA(c, c->ds.reserve(out_at + 16, s, false));
+	CLB_CUDA(c, cudaMemcpyAsync(c->ds.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s));
+	e.out = c->ds.p;
+	if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<write>"); }
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	tr.mark("k_d_encode<write>");
 	c->ds_total = out_at;
 	c->ds_header = hdr.size();
 	c->dna_done = true;

@@ -8,7 +8,9 @@
 // With COLORD_TIME_STAGES=12 the N CEncoder threads (compression.cpp:592-625) consume the compress_queue as in the real
 // pipeline and a null consumer drains their tuple packs: stage 1 + stage 2, still without the entropy coders.
 // With COLORD_TIME_STAGES=12q the quality entropy coder thread (CEntrComprQuals, compression.cpp:654-668) runs as well,
-// writing its parts to the archive given on the command line: stages 1 + 2 + the quality stream of stage 3.
+// writing its parts to the archive given on the command line: stages 1 + 2 + the quality stream of stage 3; with
+// COLORD_TIME_STAGES=12qd the DNA entropy coder thread (CEntrComprReads, compression.cpp:629-647) runs too (everything but
+// the header coder).
 //
 // Usage: oracle/_ref/ref_stage1_time compress-ont [flags] -t N in.fastq ignored.out
 #include "compression.h"
@@ -20,6 +22,7 @@
 #include "reads_sim_graph.h"
 #include "encoder.h"
 #include "entr_qual.h"
+#include "entr_read.h"
 #include "archive.h"
 #include "reference_reads.h"
 #include "ref_reads_accepter.h"
@@ -81,7 +84,7 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	uint64_t n_links = 0, n_out = 0;
 	std::thread reader([&] { CInputReads r(false, params.inputFilePath, reads_queue, quals_queue, headers_queue); });
 	const char* stages_env0 = getenv("COLORD_TIME_STAGES");
-	const bool qual_consumed = stages_env0 && std::string(stages_env0) == "12q";
+	const bool qual_consumed = stages_env0 && (std::string(stages_env0) == "12q" || std::string(stages_env0) == "12qd");
 	std::thread drain_q([&] { if (qual_consumed) return; qual_pack_t p; while (quals_queue.Pop(p)); });
 	std::thread drain_h([&] { header_pack_t p; while (headers_queue.Pop(p)); });
 	std::thread graph([&] {
@@ -90,7 +93,8 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 			params.dataSource, params.fillFactorKmersToReads, false);
 	});
 	const char* stages_env = getenv("COLORD_TIME_STAGES");
-	const bool with_qual = stages_env && std::string(stages_env) == "12q";
+	const bool with_dna = stages_env && std::string(stages_env) == "12qd";
+	const bool with_qual = with_dna || (stages_env && std::string(stages_env) == "12q");
 	const bool with_encoders = with_qual || (stages_env && std::string(stages_env) == "12");
 	uint64_t es_bytes = 0;
 	if (!with_encoders)
@@ -119,7 +123,11 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 				params.compressionLevel, (uint64_t)tot_n_reads * mean_read_len, es_for_qual, params.dataSource };
 			compr.Compress();
 		});
-		std::thread sink([&] { std::vector<es_t> pack; while (compressed.Pop(pack)) for (auto& es : pack) { ++n_out; es_bytes += es.size(); } });
+		std::thread sink([&] {
+			if (!with_dna) { std::vector<es_t> pack; while (compressed.Pop(pack)) for (auto& es : pack) { ++n_out; es_bytes += es.size(); } return; }
+			CEntrComprReads compr{ compressed, reference_reads, false, params.maxCandidates, params.compressionLevel, (uint64_t)tot_n_reads * mean_read_len, archive, tot_n_reads, 0 };
+			compr.Compress();
+		});
 		reader.join(); drain_q.join(); drain_h.join(); graph.join();
 		for (auto& t : encoders) t.join();
 		drain_esq.join(); sink.join();
@@ -128,7 +136,7 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	printf("{\"count_s\": %.4f, \"filter_s\": %.4f, \"graph_s\": %.4f, \"stage1_s\": %.4f, \"k\": %u, \"n_reads\": %u, \"tot_kmers\": %llu, "
 		"\"n_unique_counted\": %llu, \"tot_ref_reads\": %u, \"n_links\": %llu, \"threads\": %u, \"stages\": \"%s\", \"anchor_len\": %u, \"es_bytes\": %llu, \"n_out\": %llu}\n",
 		t1 - t0, t2 - t1, t4 - t3, (t2 - t0) + (t4 - t3), kmerLen, tot_n_reads, (unsigned long long)tot_kmers, (unsigned long long)n_uniq,
-		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_qual ? "1+2+3q" : with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
+		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_dna ? "1+2+3qd" : with_qual ? "1+2+3q" : with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
 	fflush(stdout);
 	_exit(0);     // skip archive/info epilogue of the CLI callback
 }
