@@ -10,6 +10,7 @@
 // oracle/stage3_dna.c (it rebuilds the reads, which is the round-trip proof).
 #include "ctx.h"
 #include "dna_model.h"
+#include "static_tables.h"
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -105,34 +106,6 @@ struct DTrace {            // CLB_S2_TRACE=1: wall time of every phase (synchron
 	explicit DTrace(cudaStream_t st) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), t0(now()) {}
 	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s3d] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
 };
-static void normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
-{
-	uint64_t tot = 0; uint32_t best = 0;
-	for (uint32_t i = 0; i < n; ++i) { tot += cnt[i]; if (cnt[i] > cnt[best]) best = i; }
-	if (!tot) { for (uint32_t i = 0; i < n; ++i) f[i] = 0; return; }
-	uint32_t sum = 0;
-	for (uint32_t i = 0; i < n; ++i) { uint32_t v = (uint32_t)(((uint64_t)cnt[i] << DB_PROB_BITS) / tot); if (cnt[i] && !v) v = 1; f[i] = (uint16_t)v; sum += v; }
-	if (sum > DB_M) {                        // the +1 floors of many rare symbols can overshoot: take it from the largest ones
-		uint32_t over = sum - DB_M;
-		while (over) { uint32_t b = 0; for (uint32_t i = 1; i < n; ++i) if (f[i] > f[b]) b = i; const uint32_t d = std::min<uint32_t>(over, f[b] - 1); f[b] = (uint16_t)(f[b] - d); over -= d; if (!d) break; }
-	} else f[best] = (uint16_t)(f[best] + DB_M - sum);
-}
-template <typename T> static void put(std::vector<uint8_t>& o, const T& v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); o.insert(o.end(), p, p + sizeof(T)); }
-// frequencies of one context: alphabets up to 8 as a presence mask + all present frequencies but the last; larger ones as a list
-static void put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
-{
-	if (A <= 8) {
-		uint8_t mask = 0; int last = -1;
-		for (uint32_t k = 0; k < A; ++k) if (f[k]) { mask |= (uint8_t)(1u << k); last = (int)k; }
-		o.push_back(mask);
-		for (int k = 0; k < last; ++k) if (f[k]) put(o, f[k]);
-	} else {
-		uint16_t nz = 0; for (uint32_t k = 0; k < A; ++k) nz += f[k] != 0;
-		put(o, nz);
-		for (uint32_t k = 0; k < A; ++k) if (f[k]) { o.push_back((uint8_t)k); put(o, f[k]); }
-	}
-}
-
 clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	cudaStream_t s = c->stream;
@@ -173,47 +146,20 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	std::vector<uint32_t> tab(n_entries, 0);
 	std::vector<uint8_t> hdr;
-	hdr.insert(hdr.end(), {'D', 'B', '0', '1'}); put(hdr, level); put(hdr, c->prm.max_candidates); put(hdr, (uint64_t)n); put(hdr, np);
-	std::vector<uint16_t> fr(256);
-	for (uint32_t f = 0; f < F_COUNT; ++f) {
-		const uint32_t A = M.A[f]; const uint64_t n_ctx = 1ull << M.cbits[f], n_fb = M.fbits[f] ? (1ull << M.fbits[f]) : 0;
-		const uint32_t* h = hist.data() + M.base[f]; uint32_t* tb = tab.data() + M.base[f];
-		std::vector<uint32_t> fbh(n_fb * A, 0); std::vector<uint16_t> fbf(n_fb * A, 0);
-		std::vector<uint8_t> dense(n_ctx, 0);
-		uint32_t nd = 0;
-		for (uint64_t x = 0; x < n_ctx; ++x) {
-			uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
-			if (!t) continue;
-			if (!n_fb || t >= DB_MIN_CTX) { dense[x] = 1; ++nd; }
-			else for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
-		}
-		for (uint64_t x = 0; x < n_fb; ++x) { normalise(&fbh[x * A], A, &fbf[x * A]); put_freqs(hdr, &fbf[x * A], A); }
-		put(hdr, nd);
-		uint64_t prev = 0;
-		for (uint64_t x = 0; x < n_ctx; ++x) {
-			const uint16_t* src;
-			if (dense[x]) {
-				normalise(&h[x * A], A, fr.data()); src = fr.data();
-				uint64_t gap = x - prev; prev = x;
-				do { uint8_t by = (uint8_t)(gap & 127); gap >>= 7; if (gap) by |= 128; hdr.push_back(by); } while (gap);
-				put_freqs(hdr, src, A);
-			} else if (n_fb) src = &fbf[(x & (n_fb - 1)) * A];
-			else continue;
-			uint32_t acc = 0; for (uint32_t k = 0; k < A; ++k) { tb[x * A + k] = src[k] | (acc << 16); acc += src[k]; }
-		}
-		if (std::getenv("CLB_S3_BITS")) {      // where the bits go: events, cost under the static tables, empirical context entropy
+	hdr.insert(hdr.end(), {'D', 'B', '0', '1'}); st_put(hdr, level); st_put(hdr, c->prm.max_candidates); st_put(hdr, (uint64_t)n); st_put(hdr, np);
+	st_build_tables(M, F_COUNT, hist, tab, hdr, DB_MIN_CTX);
+	if (std::getenv("CLB_S3_BITS"))      // where the bits go: events, cost under the static tables, empirical context entropy
+		for (uint32_t f = 0; f < F_COUNT; ++f) {
+			const uint32_t A = M.A[f]; const uint64_t n_ctx = 1ull << M.cbits[f];
+			const uint32_t* h = hist.data() + M.base[f]; const uint32_t* tb = tab.data() + M.base[f];
 			double ev = 0, cost = 0, ent = 0;
 			for (uint64_t x = 0; x < n_ctx; ++x) {
 				uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
 				if (!t) continue;
-				for (uint32_t k = 0; k < A; ++k) if (h[x * A + k]) {
-					const double cn = h[x * A + k];
-					ev += cn; cost += cn * -std::log2((tb[x * A + k] & 0xffff) / 4096.0); ent += cn * -std::log2(cn / (double)t);
-				}
+				for (uint32_t k = 0; k < A; ++k) if (h[x * A + k]) { const double cn = h[x * A + k]; ev += cn; cost += cn * -std::log2((tb[x * A + k] & 0xffff) / 4096.0); ent += cn * -std::log2(cn / (double)t); }
 			}
-			fprintf(stderr, "[s3d] family %2u: %12.0f events, %12.0f bytes coded, %12.0f bytes empirical, %u dense contexts\n", f, ev, cost / 8, ent / 8, nd);
+			fprintf(stderr, "[s3d] family %2u: %12.0f events, %12.0f bytes coded, %12.0f bytes empirical\n", f, ev, cost / 8, ent / 8);
 		}
-	}
 	uint32_t* d_tab = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_tab, sizeof(uint32_t) * n_entries, tmp));
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * n_entries, cudaMemcpyHostToDevice, s));

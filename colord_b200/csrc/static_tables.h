@@ -1,0 +1,80 @@
+// static_tables.h — host side of the native entropy containers: (family, context, symbol) counts -> 12-bit frequency tables,
+// their serialisation into the container header and the encoder's lookup table.  Metadata-sized work (one pass over the
+// count table), shared by the DNA-tuple and header streams.  Layout of the serialised tables (read by oracle/rc_static.h):
+//   per family: [fallback table: 2^fbits contexts] n_dense u32, then per dense context (ascending) LEB128 gap + frequencies;
+//   frequencies of one context: alphabets <= 8 as a presence mask + every present frequency but the last (implied by the
+//   sum 2^12), larger alphabets as count u16 + (symbol u8, frequency u16) pairs.
+// A context is "dense" (own table) when it was seen at least min_ctx times, or when its family has no fallback; all other
+// contexts of the family pool their counts in the fallback table indexed by the low fbits of the context.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace clb {
+
+constexpr uint32_t ST_PROB_BITS = 12, ST_M = 1u << ST_PROB_BITS;
+
+inline void st_normalise(const uint32_t* cnt, uint32_t n, uint16_t* f)
+{
+	uint64_t tot = 0; uint32_t best = 0;
+	for (uint32_t i = 0; i < n; ++i) { tot += cnt[i]; if (cnt[i] > cnt[best]) best = i; }
+	if (!tot) { for (uint32_t i = 0; i < n; ++i) f[i] = 0; return; }
+	uint32_t sum = 0;
+	for (uint32_t i = 0; i < n; ++i) { uint32_t v = (uint32_t)(((uint64_t)cnt[i] << ST_PROB_BITS) / tot); if (cnt[i] && !v) v = 1; f[i] = (uint16_t)v; sum += v; }
+	if (sum > ST_M) {                        // the +1 floors of many rare symbols can overshoot: take it from the largest ones
+		uint32_t over = sum - ST_M;
+		while (over) { uint32_t b = 0; for (uint32_t i = 1; i < n; ++i) if (f[i] > f[b]) b = i; const uint32_t d = std::min<uint32_t>(over, f[b] - 1); f[b] = (uint16_t)(f[b] - d); over -= d; if (!d) break; }
+	} else f[best] = (uint16_t)(f[best] + ST_M - sum);
+}
+template <typename T> inline void st_put(std::vector<uint8_t>& o, const T& v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); o.insert(o.end(), p, p + sizeof(T)); }
+inline void st_put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
+{
+	if (A <= 8) {
+		uint8_t mask = 0; int last = -1;
+		for (uint32_t k = 0; k < A; ++k) if (f[k]) { mask |= (uint8_t)(1u << k); last = (int)k; }
+		o.push_back(mask);
+		for (int k = 0; k < last; ++k) if (f[k]) st_put(o, f[k]);
+	} else {
+		uint16_t nz = 0; for (uint32_t k = 0; k < A; ++k) nz += f[k] != 0;
+		st_put(o, nz);
+		for (uint32_t k = 0; k < A; ++k) if (f[k]) { o.push_back((uint8_t)k); st_put(o, f[k]); }
+	}
+}
+
+// M: anything with A[], cbits[], fbits[], base[] per family.  tab[entry] = frequency | cumulative << 16.
+template <class M>
+void st_build_tables(const M& m, uint32_t n_fam, const std::vector<uint32_t>& hist, std::vector<uint32_t>& tab, std::vector<uint8_t>& hdr, uint32_t min_ctx)
+{
+	std::vector<uint16_t> fr(256);
+	for (uint32_t f = 0; f < n_fam; ++f) {
+		const uint32_t A = m.A[f]; const uint64_t n_ctx = 1ull << m.cbits[f], n_fb = m.fbits[f] ? (1ull << m.fbits[f]) : 0;
+		const uint32_t* h = hist.data() + m.base[f]; uint32_t* tb = tab.data() + m.base[f];
+		std::vector<uint32_t> fbh(n_fb * A, 0); std::vector<uint16_t> fbf(n_fb * A, 0);
+		std::vector<uint8_t> dense(n_ctx, 0);
+		uint32_t nd = 0;
+		for (uint64_t x = 0; x < n_ctx; ++x) {
+			uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
+			if (!t) continue;
+			if (!n_fb || t >= min_ctx) { dense[x] = 1; ++nd; }
+			else for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
+		}
+		for (uint64_t x = 0; x < n_fb; ++x) { st_normalise(&fbh[x * A], A, &fbf[x * A]); st_put_freqs(hdr, &fbf[x * A], A); }
+		st_put(hdr, nd);
+		uint64_t prev = 0;
+		for (uint64_t x = 0; x < n_ctx; ++x) {
+			const uint16_t* src;
+			if (dense[x]) {
+				st_normalise(&h[x * A], A, fr.data()); src = fr.data();
+				uint64_t gap = x - prev; prev = x;
+				do { uint8_t by = (uint8_t)(gap & 127); gap >>= 7; if (gap) by |= 128; hdr.push_back(by); } while (gap);
+				st_put_freqs(hdr, src, A);
+			} else if (n_fb) src = &fbf[(x & (n_fb - 1)) * A];
+			else continue;
+			uint32_t acc = 0; for (uint32_t k = 0; k < A; ++k) { tb[x * A + k] = src[k] | (acc << 16); acc += src[k]; }
+		}
+	}
+}
+
+} // namespace clb

@@ -10,16 +10,14 @@
  * The container has no reference bitstream to be compared with ("parity unpinned" for the bytes): parity is this round trip
  * plus the stream size against the reference's own DNA stream on the same input (tests/test_gpu_stage3.py).
  */
-#include <stdint.h>
-#include <stdlib.h>
-#include <string.h>
+#include "rc_static.h"
 
 enum { F_FLAG = 0, F_LENBITS, F_LENDATA, F_SYM, F_SYMN, F_READID, F_REV, F_TUPLE, F_ANCHOR, F_SKIPL, F_SKIPD, F_SEEN, F_SHORT, F_COUNT };
 #define DB_LANES 64
-#define DB_M 4096u
 
-typedef struct { uint32_t level, n_t, n_s, A[F_COUNT], cbits[F_COUNT], fbits[F_COUNT]; uint64_t base[F_COUNT + 1]; uint16_t* freq; } model_t;
+typedef struct { st_model t; uint32_t level, n_t, n_s; } model_t;
 
+/* table widths: colord_b200/csrc/dna_model.h make_dna_model (history widths: dna_coder.cpp:1253-1280) */
 static void make_model(model_t* m, uint32_t level, uint32_t max_cand)
 {
 	m->level = level; m->n_t = level >= 3 ? 4 : level == 2 ? 3 : 2; m->n_s = level >= 3 ? 8 : level == 2 ? 7 : 5;
@@ -27,45 +25,9 @@ static void make_model(model_t* m, uint32_t level, uint32_t max_cand)
 	const uint32_t sym_bits = level >= 3 ? 24 : level == 2 ? 23 : 22;
 	const uint32_t cb[F_COUNT] = {8, 0, 9, sym_bits, 2 * m->n_s, 11, 4, 3 * m->n_t + 9, 6, 6, 8, 6, 6};
 	const uint32_t fb[F_COUNT] = {0, 0, 0, 10, 0, 0, 0, 3 * m->n_t + 6, 0, 0, 0, 0, 0};
-	uint64_t at = 0;
-	for (int f = 0; f < F_COUNT; ++f) { m->A[f] = A[f]; m->cbits[f] = cb[f]; m->fbits[f] = fb[f]; m->base[f] = at; at += ((uint64_t)A[f]) << cb[f]; }
-	m->base[F_COUNT] = at;
-}
-
-static uint64_t get_freqs(const uint8_t* in, uint64_t at, uint16_t* f, uint32_t A)
-{
-	memset(f, 0, 2 * A);
-	if (A <= 8) {
-		const uint8_t mask = in[at++]; int last = -1; uint32_t sum = 0;
-		for (uint32_t k = 0; k < A; ++k) if (mask >> k & 1) last = (int)k;
-		for (int k = 0; k < last; ++k) if (mask >> k & 1) { uint16_t v; memcpy(&v, in + at, 2); at += 2; f[k] = v; sum += v; }
-		if (last >= 0) f[last] = (uint16_t)(DB_M - sum);
-	} else {
-		uint16_t nz; memcpy(&nz, in + at, 2); at += 2;
-		for (uint32_t i = 0; i < nz; ++i) { const uint8_t k = in[at++]; uint16_t v; memcpy(&v, in + at, 2); at += 2; f[k] = v; }
-	}
-	return at;
-}
-
-/* sub_rc.h:262-386 with totalFreq = 2^12 */
-typedef struct { const uint8_t* p; uint64_t n, at; uint64_t low, range, buffer; } rcdec;
-static uint8_t rc_byte(rcdec* d) { return d->at < d->n ? d->p[d->at++] : 0; }
-static void rc_start(rcdec* d, const uint8_t* p, uint64_t n) { d->p = p; d->n = n; d->at = 0; d->buffer = 0; for (int i = 0; i < 8; ++i) d->buffer = (d->buffer << 8) + rc_byte(d); d->low = 0; d->range = 0xff00000000000000ULL; }
-static uint32_t rc_get(rcdec* d, const model_t* m, uint32_t f, uint64_t ctx)
-{
-	const uint16_t* fr = m->freq + m->base[f] + (ctx & ((1ull << m->cbits[f]) - 1)) * m->A[f];
-	d->range >>= 12;
-	const uint64_t cf = d->buffer / d->range;
-	uint32_t s = 0; uint64_t acc = 0;
-	while (s + 1 < m->A[f] && acc + fr[s] <= cf) { acc += fr[s]; ++s; }
-	const uint64_t r = acc * d->range;
-	d->buffer -= r; d->low += r; d->range *= fr[s];
-	while (d->range <= 0x0000ffffffffffffULL) {
-		if ((d->low ^ (d->low + d->range)) & 0xff00000000000000ULL) { const uint64_t x = d->low; d->range = (x | 0x0000ffffffffffffULL) - x; }
-		d->buffer = (d->buffer << 8) + rc_byte(d);
-		d->low <<= 8; d->range <<= 8;
-	}
-	return s;
+	m->t.n_fam = F_COUNT;
+	for (int f = 0; f < F_COUNT; ++f) { m->t.A[f] = A[f]; m->t.cbits[f] = cb[f]; m->t.fbits[f] = fb[f]; }
+	st_layout(&m->t);
 }
 
 typedef struct { uint8_t* p; uint64_t n, cap; } bbuf3;
@@ -87,27 +49,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 	memcpy(&level, in + at, 4); at += 4; memcpy(&max_cand, in + at, 4); at += 4; memcpy(&nr, in + at, 8); at += 8; memcpy(&n_packs, in + at, 4); at += 4;
 	if (nr != n_reads) return -2;
 	model_t M; make_model(&M, level, max_cand);
-	M.freq = (uint16_t*)calloc(M.base[F_COUNT], 2);
-	uint16_t fr[256];
-	for (int f = 0; f < F_COUNT; ++f) {
-		const uint32_t A = M.A[f]; const uint64_t n_ctx = 1ull << M.cbits[f], n_fb = M.fbits[f] ? (1ull << M.fbits[f]) : 0;
-		uint16_t* dst = M.freq + M.base[f];
-		if (n_fb) {
-			uint16_t* fbf = (uint16_t*)calloc(n_fb * A, 2);
-			for (uint64_t x = 0; x < n_fb; ++x) at = get_freqs(in, at, fbf + x * A, A);
-			for (uint64_t x = 0; x < n_ctx; ++x) memcpy(dst + x * A, fbf + (x & (n_fb - 1)) * A, 2 * A);
-			free(fbf);
-		}
-		uint32_t nd; memcpy(&nd, in + at, 4); at += 4;
-		uint64_t x = 0;
-		for (uint32_t d = 0; d < nd; ++d) {
-			uint64_t gap = 0; uint32_t sh = 0; uint8_t by;
-			do { by = in[at++]; gap |= (uint64_t)(by & 127) << sh; sh += 7; } while (by & 128);
-			x += gap;
-			at = get_freqs(in, at, fr, A);
-			memcpy(dst + x * A, fr, 2 * A);
-		}
-	}
+	at = st_read_tables(&M.t, in, at);
 	/* reference reads decoded so far (symbols 0..3) */
 	uint8_t** ref_sym = (uint8_t**)calloc((size_t)n_reads + 1, sizeof(uint8_t*)); uint32_t* ref_len = (uint32_t*)calloc((size_t)n_reads + 1, 4); uint32_t n_ref = 0;
 	const uint64_t mask_s = (1ull << (2 * M.n_s)) - 1, mask_t = (1ull << (3 * M.n_t)) - 1;
@@ -122,31 +64,31 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 		for (uint32_t r = r0; r < r0 + np; ++r) {
 			rcdec* d = &dec[(r - r0) % DB_LANES]; uint32_t* fc = &fctx[(r - r0) % DB_LANES];
 			bbuf3 rd = {0, 0, 0};                      /* symbols of this read */
-			const uint32_t flag = rc_get(d, &M, F_FLAG, *fc);
+			const uint32_t flag = rc_get(d, &M.t, F_FLAG, *fc);
 			*fc = ((*fc << 2) + flag) & 0xff;
 			uint32_t len;
 			{
-				const uint32_t nbits = rc_get(d, &M, F_LENBITS, 0);
+				const uint32_t nbits = rc_get(d, &M.t, F_LENBITS, 0);
 				if (nbits < 2) len = nbits;              /* ilog2: 0 -> 0, 1 -> 1 */
 				else {
 					uint64_t ctx = (uint64_t)nbits << 3;
-					uint32_t v = rc_get(d, &M, F_LENDATA, ctx);
+					uint32_t v = rc_get(d, &M.t, F_LENDATA, ctx);
 					if (nbits > 9) {
 						uint32_t suffix = 0, sh = 0; ctx += 4;
-						for (int nb = (int)nbits - 9; nb > 0; nb -= 8) { suffix |= rc_get(d, &M, F_LENDATA, ctx) << sh; sh += 8; ++ctx; }
+						for (int nb = (int)nbits - 9; nb > 0; nb -= 8) { suffix |= rc_get(d, &M.t, F_LENDATA, ctx) << sh; sh += 8; ++ctx; }
 						v = (v << (nbits - 9)) + suffix;
 					}
 					len = v + (1u << (nbits - 1));
 				}
 			}
 			uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
-			if (flag == 0) { for (uint32_t i = 0; i < len; ++i) { const uint32_t s = rc_get(d, &M, F_SYM, ctx_symbol << 2); b3_push(&rd, (uint8_t)s); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; } }
-			else if (flag == 1) { for (uint32_t i = 0; i < len; ++i) { const uint32_t s = rc_get(d, &M, F_SYMN, ctx_symbol); b3_push(&rd, (uint8_t)s); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; } }
+			if (flag == 0) { for (uint32_t i = 0; i < len; ++i) { const uint32_t s = rc_get(d, &M.t, F_SYM, ctx_symbol << 2); b3_push(&rd, (uint8_t)s); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; } }
+			else if (flag == 1) { for (uint32_t i = 0; i < len; ++i) { const uint32_t s = rc_get(d, &M.t, F_SYMN, ctx_symbol); b3_push(&rd, (uint8_t)s); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; } }
 			else {
 				uint32_t seen_id[34], seen_rev[34], n_seen = 0; uint64_t ctx_rev = 0xf;
 				uint32_t alt_ids[32]; int alt_revs[32], alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;
-#define GET_READ_ID(dst) do { const int nn = (int)nbytes(r); uint32_t id_ = 0; for (int i = nn - 1; i >= 0; --i) { const uint64_t add = (i == nn - 2) ? id_ : 0; id_ = (id_ << 8) + rc_get(d, &M, F_READID, (uint64_t)i + (add << 3)); } dst = id_; } while (0)
-#define GET_REV(id, dst) do { int fnd = -1; for (uint32_t k = 0; k < n_seen; ++k) if (seen_id[k] == (id)) fnd = (int)k; if (fnd >= 0) dst = (int)seen_rev[fnd]; else { const uint32_t fl_ = rc_get(d, &M, F_REV, ctx_rev); if (n_seen < 34) { seen_id[n_seen] = (id); seen_rev[n_seen] = fl_; ++n_seen; } ctx_rev = ((ctx_rev << 2) + fl_) & 0xf; dst = (int)fl_; } } while (0)
+#define GET_READ_ID(dst) do { const int nn = (int)nbytes(r); uint32_t id_ = 0; for (int i = nn - 1; i >= 0; --i) { const uint64_t add = (i == nn - 2) ? id_ : 0; id_ = (id_ << 8) + rc_get(d, &M.t, F_READID, (uint64_t)i + (add << 3)); } dst = id_; } while (0)
+#define GET_REV(id, dst) do { int fnd = -1; for (uint32_t k = 0; k < n_seen; ++k) if (seen_id[k] == (id)) fnd = (int)k; if (fnd >= 0) dst = (int)seen_rev[fnd]; else { const uint32_t fl_ = rc_get(d, &M.t, F_REV, ctx_rev); if (n_seen < 34) { seen_id[n_seen] = (id); seen_rev[n_seen] = fl_; ++n_seen; } ctx_rev = ((ctx_rev << 2) + fl_) & 0xf; dst = (int)fl_; } } while (0)
 				uint32_t main_id; GET_READ_ID(main_id);
 				int main_rev; GET_REV(main_id, main_rev);
 				if (main_id >= n_ref) { rc = -3; free(rd.p); break; }
@@ -158,14 +100,14 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 					uint64_t ctx = ctx_tuple + ((ctx_symbol & 0xf) << sh_t) + ((uint64_t)rsym << (sh_t + 4));
 					const uint32_t bucket = delta < -10 ? 1 : delta < -1 ? 2 : delta > 10 ? 3 : delta > 1 ? 4 : 0;
 					ctx += (uint64_t)bucket << (sh_t + 6);
-					const uint32_t ty = rc_get(d, &M, F_TUPLE, ctx);
+					const uint32_t ty = rc_get(d, &M.t, F_TUPLE, ctx);
 					ctx_tuple = ((ctx_tuple << 3) + ty) & mask_t;
 					if (ty == 6) {
 						if (!is_main && cur_alt >= 0) alt_saved[cur_alt] = alt_pos;
 						uint32_t id; int idx = -1;
 						if (n_alt == 0) GET_READ_ID(id);
-						else if (!rc_get(d, &M, F_SEEN, n_alt)) GET_READ_ID(id);
-						else { idx = (int)rc_get(d, &M, F_SHORT, n_alt); id = alt_ids[idx]; }
+						else if (!rc_get(d, &M.t, F_SEEN, n_alt)) GET_READ_ID(id);
+						else { idx = (int)rc_get(d, &M.t, F_SHORT, n_alt); id = alt_ids[idx]; }
 						int rev; GET_REV(id, rev);
 						if (idx < 0) { for (uint32_t k = 0; k < n_alt; ++k) if (alt_ids[k] == id) idx = (int)k; }
 						if (idx < 0 && n_alt < 32) { idx = (int)n_alt; alt_ids[n_alt] = id; alt_revs[n_alt] = rev; alt_saved[n_alt] = 0; ++n_alt; }
@@ -175,7 +117,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 						alt_pos = 0; is_main = 0; delta = 0;
 					} else if (ty == 4) {
 						uint32_t alen = 0;
-						for (uint32_t part = 0;; ++part) { const uint32_t v = rc_get(d, &M, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; }
+						for (uint32_t part = 0;; ++part) { const uint32_t v = rc_get(d, &M.t, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; }
 						for (uint32_t k = 0; k < alen; ++k) b3_push(&rd, (uint8_t)osym(o, *pos + (int)k));
 						*pos += (int)alen;
 						for (int i = (int)M.n_s; i > 0; --i) ctx_symbol = (ctx_symbol << 2) + osym(o, *pos - i);
@@ -190,7 +132,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 						else { c2 += (ctx_symbol & 0x3ff) << sh; sh += 10; if (M.level >= 3) { c2 += (uint64_t)(((ctx_symbol >> 10) & 3) == ((ctx_symbol >> 8) & 3)) << sh; ++sh; } }
 						c2 += (uint64_t)rsym << sh; sh += 2;
 						c2 += (ctx_tuple & 0777) << sh;
-						const uint32_t s = rc_get(d, &M, F_SYM, c2);
+						const uint32_t s = rc_get(d, &M.t, F_SYM, c2);
 						b3_push(&rd, (uint8_t)s);
 						ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++delta;
 					} else if (ty == 1) { ++*pos; --delta; }
@@ -200,7 +142,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 						if (M.level >= 3) { c2 += (uint64_t)(((ctx_symbol >> 6) & 3) == ((ctx_symbol >> 4) & 3)) << sh; ++sh; }
 						c2 += (uint64_t)rsym << sh; sh += 2;
 						c2 += (ctx_tuple & 07777) << sh;
-						const uint32_t s = rc_get(d, &M, F_SYM, c2);
+						const uint32_t s = rc_get(d, &M.t, F_SYM, c2);
 						b3_push(&rd, (uint8_t)s);
 						ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++*pos;
 					} else if (ty == 5) {
@@ -208,7 +150,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 						uint32_t skip;
 						const int distant_after_alt = !is_main && last_tuple == 6;
 						const int local = !distant_after_alt && last_tuple != 6 && last_tuple != 255;
-#define GET_SKIP(dst, loc) do { uint32_t v_ = 0; if (loc) { for (uint32_t part = 0;; ++part) { const uint32_t x_ = rc_get(d, &M, F_SKIPL, part < 63 ? part : 63); if (x_ < 255) { v_ += x_; break; } v_ += 254; } } else { for (int i = 3; i >= 0; --i) { const uint32_t x_ = rc_get(d, &M, F_SKIPD, (uint64_t)i * 64 + ilog2b(v_)); v_ = (v_ << 8) + x_; } } dst = v_; } while (0)
+#define GET_SKIP(dst, loc) do { uint32_t v_ = 0; if (loc) { for (uint32_t part = 0;; ++part) { const uint32_t x_ = rc_get(d, &M.t, F_SKIPL, part < 63 ? part : 63); if (x_ < 255) { v_ += x_; break; } v_ += 254; } } else { for (int i = 3; i >= 0; --i) { const uint32_t x_ = rc_get(d, &M.t, F_SKIPD, (uint64_t)i * 64 + ilog2b(v_)); v_ = (v_ << 8) + x_; } } dst = v_; } while (0)
 						if (distant_after_alt) {
 							uint32_t v; GET_SKIP(v, 0);
 							const int saved = cur_alt >= 0 ? alt_saved[cur_alt] : 0;
@@ -232,7 +174,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 	}
 	out_off[n_reads] = w;
 	for (uint32_t i = 0; i < n_ref; ++i) free(ref_sym[i]);
-	free(ref_sym); free(ref_len); free(M.freq);
+	free(ref_sym); free(ref_len); free(M.t.freq);
 	if (rc) return rc;
 	return w > cap_bases ? (int64_t)w : 0;
 }
