@@ -5,9 +5,10 @@ One "step" = one pass of the hot path built so far over the whole synthetic ONT 
 canonical k-mer scan + murmur64 % f filter + count table, thresholding into the filtered set, accepted k-mers per
 read, similarity graph with top-c candidates) and STAGE 2 (m-mer anchors against the candidates, edit scripts of the
 parts between anchors, edit-script / plain / alternative-read decisions, CompactES tuples).  Stage 3 (entropy coders) is
-represented by its quality stream (the reference's lossy 4-avg transform + context model, static tables, interleaved rANS;
-and the DNA-tuple stream, both in native containers; the header coder is not on the device yet); `config.stages` says so and the reference arm times the SAME
-stages of the reference (`--stages 1` / `--stages 12` restrict both arms).
+all three streams in native containers: the quality stream (the reference's lossy 4-avg transform + context model, static
+tables, interleaved rANS), the DNA-tuple stream and the header stream (the reference's event models, static tables, 64 range-
+coder lanes per pack); `config.stages` says so and the reference arm times the SAME stages of the reference
+(`--stages 1` / `12` / `12q` / `12qd` restrict both arms).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--gbases G] [--impl reference]
 
@@ -185,7 +186,7 @@ def cpu_baseline(sample_reads=12500, stages="12"):
         desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
             r = run_reference_stage1(fq, cores, stages)
-            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12qd": "+CEncoder threads+CEntrComprReads+CEntrComprQuals (stages 1+2+3 without the header coder)", "12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
+            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12qdh": "+CEncoder threads+CEntrComprReads+CEntrComprQuals+CEntrComprHeaders (stages 1+2+3)", "12qd": "+CEncoder threads+CEntrComprReads+CEntrComprQuals (stages 1+2+3 without the header coder)", "12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
             return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
                     "sample": desc + "; unmodified reference " + what, "detail": r}
         dt = run_port_stage1(s)
@@ -222,6 +223,7 @@ def main_reference(args):
 
 def metric_name(args):
     return "input MB/s, compress-ont default, " + {
+        "12qdh": "stages 1+2+3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, DNA-tuple, 4-avg quality and header entropy coders)",
         "12qd": "stages 1+2+3 without headers (k-mer filter, similarity graph, anchors + edit scripts -> tuples, DNA-tuple and 4-avg quality entropy coders)",
         "12q": "stages 1+2 + quality stream of stage 3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, 4-avg quality coder)",
         "12": "stages 1+2 (k-mer filter, similarity graph, anchors + edit scripts -> tuples)",
@@ -232,7 +234,8 @@ def workload_config(args, n_reads):
     return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
                         f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] * args.gbases / 25.0 / 1e9:.3g} Gb = 20.8x, 10% errors)",
             "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1)" % NS_S2["anchor_len"]
-                       + {"12qd": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) in native containers; header coder not on device yet",
+                       + {"12qdh": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) + header stream in native containers",
+                          "12qd": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) in native containers; header coder not on device yet",
                           "12q": "; stage 3: quality stream (4-avg, thresholds 7 14 26) only", "12": "; stage 3 not included"}[args.stages])
                       if args.stages != "1" else "stage 1 only (1a count+filter, 1b accepted k-mers + similarity graph)",
             "n_reads": n_reads, "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"reads sharded by id over {args.gpus} GPU(s)"}
@@ -245,7 +248,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
-    ap.add_argument("--stages", default="12qd", choices=["1", "12", "12q", "12qd"], help="hot-path stages inside a step (both arms); q / d = quality / DNA-tuple stream of stage 3")
+    ap.add_argument("--stages", default="12qdh", choices=["1", "12", "12q", "12qd", "12qdh"], help="hot-path stages inside a step (both arms); q / d / h = quality / DNA-tuple / header stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -279,7 +282,7 @@ def main():
     del genome
     torch.cuda.empty_cache()
     quals = None
-    if args.stages in ("12q", "12qd"):      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
+    if args.stages in ("12q", "12qd", "12qdh"):      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
         quals = torch.empty(bases.numel(), dtype=torch.uint8, device=device)
         gq = torch.Generator(device=device)
         gq.manual_seed(4242 + rank)
@@ -287,6 +290,18 @@ def main():
             q1 = min(bases.numel(), q0 + (1 << 28))
             quals[q0:q1] = (torch.randn(q1 - q0, device=device, generator=gq) * 5 + 12).round_().clamp_(1, 40).to(torch.uint8) + 33
         torch.cuda.empty_cache()
+    hdr_host = hdr_off_host = hdr_dev = hdr_off_dev = None
+    if args.stages == "12qdh":      # "@read_<i> ch=<1..512> start_time=<ISO>" (same text as colord_b200.synth), global read index
+        rng_h = np.random.default_rng(777 + rank)
+        chs = rng_h.integers(1, 513, hi - lo)
+        hl = [b"@read_%d ch=%d start_time=2020-01-01T%02d:%02d:%02dZ" % (i, c, (i // 3600) % 24, (i // 60) % 60, i % 60) for i, c in zip(range(lo, hi), chs.tolist())]
+        hdr_off_host = np.zeros(hi - lo + 1, np.uint64)
+        hdr_off_host[1:] = np.cumsum(np.fromiter((len(h) for h in hl), np.int64, len(hl)))
+        hdr_host = torch.empty(int(hdr_off_host[-1]), dtype=torch.uint8, pin_memory=True)
+        hdr_host.numpy()[:] = np.frombuffer(b"".join(hl), np.uint8)
+        del hl, chs
+        hdr_dev = hdr_host.to(device)
+        hdr_off_dev = torch.from_numpy(hdr_off_host.view(np.int64)).to(device)
     free_b, total_b = torch.cuda.mem_get_info()
     print(f"[bench] rank {rank}: inputs resident, {free_b / 2**30:.1f} of {total_b / 2**30:.1f} GiB free "
           f"(torch reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB)", file=sys.stderr)
@@ -297,12 +312,12 @@ def main():
     if world > 1:
         dist.all_reduce(tot)
     n_bases_total, n_reads_all = int(tot[0]), int(tot[1])
-    job_bytes = fastq_bytes(n_bases_total, n_reads_all)
+    job_bytes = fastq_bytes(n_bases_total, n_reads_all)      # header lines counted at their nominal 46 bytes (same formula for every --stages)
 
     stream = torch.cuda.Stream(device=device)
     peak, peak_src = measured_peak_hbm()
 
-    def one_step(host_bases=None, host_offsets=None, host_quals=None, profile=False, readback=False):
+    def one_step(host_bases=None, host_offsets=None, host_quals=None, host_hdr=None, profile=False, readback=False):
         ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], expected_bases=n_bases_local, device=local_rank)
         ctx.set_stream(stream.cuda_stream)
         if profile:
@@ -317,18 +332,25 @@ def main():
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
         ctx.graph_build(sampled)
         out = None
-        if args.stages in ("12", "12q", "12qd"):
+        if args.stages in ("12", "12q", "12qd", "12qdh"):
             ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
-            if args.stages == "12qd":
+            if args.stages in ("12qd", "12qdh"):
                 ctx.dna_encode(1)
-            if args.stages in ("12q", "12qd"):
+            if args.stages == "12qdh":
+                if host_hdr is None:
+                    ctx.hdr_encode(bytes_=hdr_dev.data_ptr(), offsets=hdr_off_dev.data_ptr(), n=n_local, on_device=True)
+                else:
+                    ctx.hdr_encode(bytes_=host_hdr[0], offsets=host_hdr[1])
+            if args.stages in ("12q", "12qd", "12qdh"):
                 if host_quals is None:
                     ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
                 else:
                     ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
             if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
-                if args.stages == "12qd":
+                if args.stages == "12qdh":
+                    out = (ctx.dna_stream()[0], ctx.qual_stream(), ctx.hdr_stream()[0])
+                elif args.stages == "12qd":
                     out = (ctx.dna_stream()[0], ctx.qual_stream())
                 else:
                     out = ctx.encoded(n_local)
@@ -382,10 +404,12 @@ def main():
             host_quals = torch.empty(n_bases_local, dtype=torch.uint8, pin_memory=True)
             host_quals.copy_(quals)
             hq = host_quals.numpy()
-        e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, host_quals=hq, readback=True)
+        hh = None if hdr_host is None else (hdr_host.numpy(), hdr_off_host)
+        e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, host_quals=hq, host_hdr=hh, readback=True)
         d2h = int(sum(x.nbytes for x in out))
         e2e = {"value": job_bytes / (e_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(n_bases_local * (2 if hq is not None else 1) + host_off.nbytes), "d2h_bytes_per_step": d2h, "host_memory": "pinned"}
+               "h2d_bytes_per_step": int(n_bases_local * (2 if hq is not None else 1) + host_off.nbytes + (0 if hh is None else hh[0].nbytes + hh[1].nbytes)),
+               "d2h_bytes_per_step": d2h, "host_memory": "pinned", "stream_bytes": [int(x.nbytes) for x in out]}
         del host_bases, hb
     clocks = sampler.stop() if sampler else None
 
@@ -397,7 +421,8 @@ def main():
                "k_align": 0.25 + 0.25 + 1.0,                           # the two parts (2-bit) read, one script byte written per symbol
                "k_decide": 1.0, "k_emit": 1.0 + 1.25,                  # scripts read, CompactES bytes written
                "k_qual": 2 * (1.0 + 0.25) + 0.25,                      # two passes over qualities + packed bases, stream written
-               "k_dna": 2 * (1.25 + 0.25) + 0.25}                      # two passes over the tuples + reference bases for the contexts, stream written
+               "k_dna": 2 * (1.25 + 0.25) + 0.25,                      # two passes over the tuples + reference bases for the contexts, stream written
+               "k_hdr": 0.03}                                          # ~3 passes over ~50 header bytes per 8 kb read
         per_step = {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}
         roof = None
         if per_step:

@@ -57,7 +57,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
-	c->qs.release(); c->ds.release();
+	c->qs.release(); c->ds.release(); c->hs.release();
 	{ cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, c->prm.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -252,6 +252,28 @@ clb_status clb_dna_get(clb_ctx* c, uint8_t* stream, uint64_t cap, int on_device)
 	if (!c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode has not run");
 	if (cap < c->ds_total) return fail(c, CLB_ERR_CAPACITY, "clb_dna_get: buffer too small");
 	CLB_CUDA(c, cudaMemcpyAsync(stream, c->ds.p, c->ds_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+clb_status clb_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	if (!offsets || (!bytes && n)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s3_hdr_encode(c, bytes, offsets, plus_id, n, on_device, pack_sizes, n_packs);
+}
+clb_status clb_hdr_size(clb_ctx* c, uint64_t* total, uint64_t* header)
+{
+	CLB_ENTER(c);
+	if (!c->hdr_done) return fail(c, CLB_ERR_STATE, "clb_hdr_encode has not run");
+	*total = c->hs_total; if (header) *header = c->hs_header;
+	return CLB_OK;
+}
+clb_status clb_hdr_get(clb_ctx* c, uint8_t* stream, uint64_t cap, int on_device)
+{
+	CLB_ENTER(c);
+	if (!c->hdr_done) return fail(c, CLB_ERR_STATE, "clb_hdr_encode has not run");
+	if (cap < c->hs_total) return fail(c, CLB_ERR_CAPACITY, "clb_hdr_get: buffer too small");
+	CLB_CUDA(c, cudaMemcpyAsync(stream, c->hs.p, c->hs_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
 	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
 	return CLB_OK;
 }

@@ -38,8 +38,8 @@ struct DevBuf {
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector
 
 // kernel classes for the optional per-kernel timing (clb_profile_*)
-enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_DECIDE, K_ESTIMATE, K_EMIT, K_QUAL, K_DNA, K_N };
-static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna" };
+enum KernelId : int { K_PACK = 0, K_COUNT, K_TAB_MISC, K_FINALIZE, K_ACCEPT, K_POSTINGS, K_VOTE, K_COMMON, K_MISC, K_ALIGN, K_ANCHORS, K_ENCODE, K_DECIDE, K_ESTIMATE, K_EMIT, K_QUAL, K_DNA, K_HDR, K_N };
+static const char* const kernel_names[K_N] = { "k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr" };
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 } // namespace clb
@@ -136,6 +136,10 @@ struct clb_ctx {
 	bool dna_done = false;
 	clb::DevBuf<uint8_t> ds;         // native DNA container
 	uint64_t ds_total = 0, ds_header = 0;
+	// ---- stage 3: header stream ----
+	bool hdr_done = false;
+	clb::DevBuf<uint8_t> hs;         // native header container
+	uint64_t hs_total = 0, hs_header = 0;
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)
@@ -176,6 +180,8 @@ clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* 
 clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* pack_sizes, uint32_t n_packs);
 void s2_free(clb_ctx* c);
 clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,

@@ -11,6 +11,7 @@
 #include "ctx.h"
 #include "dna_model.h"
 #include "static_tables.h"
+#include "range_sink.cuh"
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -21,33 +22,10 @@
 
 namespace clb {
 
-constexpr uint32_t DB_LANES = 64, DB_PROB_BITS = 12, DB_M = 1u << DB_PROB_BITS, DB_MIN_CTX = 64;
+constexpr uint32_t DB_LANES = 64, DB_MIN_CTX = 64;
 
-struct HistSink {
-	uint32_t* hist; const DnaModel* M;
-	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym) { atomicAdd(&hist[dna_entry(*M, f, ctx, sym)], 1u); }
-};
-// sub_rc.h:83-201 with totalFreqSum = 2^12
-struct RangeSink {
-	const uint32_t* tab; const DnaModel* M;
-	uint8_t* out; uint64_t n, cap;
-	unsigned long long low, range;
-	CLB_D void start() { low = 0; range = 0xff00000000000000ULL; n = 0; }
-	CLB_D void byte(uint8_t b) { if (out) out[n] = b; ++n; }              // out == nullptr: sizing pass
-	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym)
-	{
-		const uint32_t e = tab[dna_entry(*M, f, ctx, sym)];
-		range >>= DB_PROB_BITS;
-		low += range * (e >> 16);
-		range *= (e & 0xffffu);
-		while (range <= 0x0000ffffffffffffULL) {
-			if ((low ^ (low + range)) & 0xff00000000000000ULL) { const unsigned long long r = low; range = (r | 0x0000ffffffffffffULL) - r; }
-			byte((uint8_t)(low >> 56));
-			low <<= 8; range <<= 8;
-		}
-	}
-	CLB_D void end() { for (int i = 0; i < 8; ++i) { byte((uint8_t)(low >> 56)); low <<= 8; } }
-};
+using HistSink = HistSinkT<DnaModel>;
+using RangeSink = RangeSinkT<DnaModel>;
 
 struct DArgs {
 	DnaReads R; DnaModel M;
@@ -84,7 +62,7 @@ __global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
 	if (li >= a.n_packs * DB_LANES) return;
 	const uint32_t p = li / DB_LANES, l = li % DB_LANES;
 	const uint32_t r0 = a.pack_first[p], r1 = a.pack_first[p + 1];
-	RangeSink s{a.tab, &a.M, WRITE ? e.out + e.dst_off[li] : nullptr, 0, 0, 0, 0};
+	RangeSink s{a.tab, &a.M, WRITE ? e.out + e.dst_off[li] : nullptr, 0, 0, 0};
 	s.start();
 	uint32_t fctx = 0;
 	for (uint32_t r = r0 + l; r < r1; r += DB_LANES) {

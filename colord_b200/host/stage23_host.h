@@ -2,6 +2,8 @@
 // (include/colord_b200.h).  Same argument meaning and order of use as
 //   CEncoder              src/colord/encoder.h:371-410 (ctor), encoder.cpp:1672-1691 (Encode)
 //   CEntrComprQuals       src/colord/entr_qual.h:82-126 (ctor, Compress)
+//   CEntrComprReads       src/colord/entr_read.h:35-80 (ctor, Compress)
+//   CEntrComprHeaders     src/colord/entr_header.h:30-52, entr_header.cpp:23-46 (Compress)
 // The reference runs N CEncoder threads over CCompressPacks and one quality thread over quals packs; here one call covers
 // all appended reads and the results stay on the device until they are fetched.  Header-only; link -lcolord_b200.
 #pragma once
@@ -53,6 +55,47 @@ public:
 		uint64_t tot = 0; check(ctx, clb_qual_size(ctx, &tot), "clb_qual_size");
 		std::vector<uint8_t> out(tot + 1);
 		check(ctx, clb_qual_get(ctx, out.data(), tot, 0), "clb_qual_get");
+		out.resize(tot);
+		return out;
+	}
+};
+
+class CEntrComprReads {
+	clb_ctx* ctx; uint32_t level;
+public:
+	// compression_level = compressionLevel (history widths of the DNA model, dna_coder.cpp:1253-1280)
+	CEntrComprReads(CKmerCounter& counter, int32_t compression_level) : ctx(counter.Context()), level(static_cast<uint32_t>(compression_level)) {}
+	// codes the tuples CEncoder::Encode left on the device; one part per read pack (entr_read.h:66-78)
+	void Compress(const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_dna_encode(ctx, level, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_dna_encode");
+	}
+	std::vector<uint8_t> GetStream() const
+	{
+		uint64_t tot = 0; check(ctx, clb_dna_size(ctx, &tot, nullptr), "clb_dna_size");
+		std::vector<uint8_t> out(tot + 1);
+		check(ctx, clb_dna_get(ctx, out.data(), tot, 0), "clb_dna_get");
+		out.resize(tot);
+		return out;
+	}
+};
+
+class CEntrComprHeaders {
+	clb_ctx* ctx;
+public:
+	explicit CEntrComprHeaders(CKmerCounter& counter) : ctx(counter.Context()) {}
+	// headers: (id, the '+' line repeats the id) in input order = header_pack_t entries (entr_header.cpp:33-34)
+	void Compress(const std::vector<std::pair<std::string, bool>>& headers, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		std::vector<uint8_t> bytes, plus; std::vector<uint64_t> off{0};
+		for (const auto& [id, plus_id] : headers) { bytes.insert(bytes.end(), id.begin(), id.end()); off.push_back(bytes.size()); plus.push_back(plus_id); }
+		check(ctx, clb_hdr_encode(ctx, bytes.data(), off.data(), plus.data(), headers.size(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
+	}
+	std::vector<uint8_t> GetStream() const
+	{
+		uint64_t tot = 0; check(ctx, clb_hdr_size(ctx, &tot, nullptr), "clb_hdr_size");
+		std::vector<uint8_t> out(tot + 1);
+		check(ctx, clb_hdr_get(ctx, out.data(), tot, 0), "clb_hdr_get");
 		out.resize(tot);
 		return out;
 	}

@@ -17,9 +17,9 @@ EXPORTS = [
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
-    "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get",
+    "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
 ]
-KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna"]
+KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 
 
 class Params(C.Structure):
@@ -96,6 +96,9 @@ def load():
     L.clb_dna_encode.argtypes = [vp, u32, vp, u32]
     L.clb_dna_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.clb_dna_get.argtypes = [vp, vp, u64, i32]
+    L.clb_hdr_encode.argtypes = [vp, vp, vp, vp, u64, i32, vp, u32]
+    L.clb_hdr_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.clb_hdr_get.argtypes = [vp, vp, u64, i32]
     L.clb_qual_encode.argtypes = [vp, C.POINTER(QualParams), vp, vp, i32, vp, u32]
     L.clb_qual_size.argtypes = [vp, C.POINTER(u64)]
     L.clb_qual_get.argtypes = [vp, vp, u64, i32]
@@ -385,6 +388,30 @@ class Context:
         out = np.zeros(max(n, 1), np.uint8)
         self._ck(self.L.clb_qual_get(self.h, _np_ptr(out), n, 0))
         return out[:n]
+
+    def hdr_encode(self, headers=None, plus_id=None, pack_sizes=None, *, bytes_=None, offsets=None, n=None, on_device=False):
+        """Header stream (native container HB01).  headers: list of bytes objects — or bytes_/offsets (numpy arrays, or device
+        pointers with n and on_device=True).  plus_id: per-header flag "the '+' line repeats the header" (None = never)."""
+        if headers is not None:
+            bytes_ = np.frombuffer(b"".join(headers), np.uint8)
+            offsets = np.zeros(len(headers) + 1, np.uint64)
+            offsets[1:] = np.cumsum([len(h) for h in headers], dtype=np.uint64)
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        if on_device:
+            bp, op, pp = C.c_void_p(bytes_), C.c_void_p(offsets), (None if plus_id is None else C.c_void_p(plus_id))
+        else:
+            b = np.ascontiguousarray(bytes_, np.uint8); o = np.ascontiguousarray(offsets, np.uint64); n = len(o) - 1
+            pl = None if plus_id is None else np.ascontiguousarray(plus_id, np.uint8)
+            bp, op, pp = (_np_ptr(b) if len(b) else None), _np_ptr(o), (None if pl is None else _np_ptr(pl))
+        self._ck(self.L.clb_hdr_encode(self.h, bp, op, pp, n, int(on_device), None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+
+    def hdr_stream(self):
+        """-> (container bytes, bytes of its table part)."""
+        n, h = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.clb_hdr_size(self.h, C.byref(n), C.byref(h)))
+        out = np.zeros(max(n.value, 1), np.uint8)
+        self._ck(self.L.clb_hdr_get(self.h, _np_ptr(out), n.value, 0))
+        return out[:n.value], h.value
 
     def profile_enable(self, on=True):
         self._ck(self.L.clb_profile_enable(self.h, int(on)))

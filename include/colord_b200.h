@@ -180,6 +180,22 @@ clb_status clb_qual_encode(clb_ctx* ctx, const clb_qual_params* params, const ui
 clb_status clb_qual_size(clb_ctx* ctx, uint64_t* total_bytes);
 clb_status clb_qual_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
 
+/* ---- Stage 3: header (read id) stream ---------------------------------------------------------------
+ * Replaces CEntrComprHeaders::Compress -> CIDCoder::Encode / compress_lossless (entr_header.cpp:23-46, id_coder.cpp:210-383;
+ * HeaderComprMode::Original, the default).  The reference's event model is kept (tokens cut at every character outside
+ * [0-9A-Za-z@], the same-shape flag against the previous header, per token same / same length / the characters that differ,
+ * plain fallback) and so is the arithmetic of its range coder; its adaptive models are replaced by static per-context tables
+ * (two passes) and 64 independent coder lanes per pack; the first header of a pack has no predecessor.  Native container
+ * "HB01"; CPU twin and decoder: oracle/stage3_hdr.c.  Independent of the other stages (may run before any read is appended).
+ * bytes: the headers back to back exactly as they are to be restored (no NUL bytes), header r at bytes[offsets[r] ..
+ * offsets[r+1]) with offsets[0] = 0; plus_id[r] != 0: the read's '+' line repeats the header (qual_header_type::eq_read_header,
+ * entr_header.cpp:34; NULL = never).  Device pointers iff on_device.  pack_sizes (HOST; NULL: packs of 4096 headers). */
+clb_status clb_hdr_encode(clb_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n_headers, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
+/* table_bytes (may be NULL): the part of the container that holds the frequency tables */
+clb_status clb_hdr_size(clb_ctx* ctx, uint64_t* total_bytes, uint64_t* table_bytes);
+clb_status clb_hdr_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
+
 /* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
  * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
  * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
@@ -195,7 +211,7 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 uint64_t clb_kernel_launches(const clb_ctx* ctx);
 /* Optional per-kernel device timing with CUDA events on the context's stream (off by default; enabling
  * resets the accumulators).  Kernel classes: k_pack, k_count, k_tab_misc, k_finalize, k_accept, k_postings,
- * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit, k_qual, k_dna.  clb_profile_get synchronizes the stream. */
+ * k_vote, k_common, k_misc, k_align, k_anchors, k_encode (task lists), k_decide, k_estimate, k_emit, k_qual, k_dna, k_hdr.  clb_profile_get synchronizes the stream. */
 clb_status clb_profile_enable(clb_ctx* ctx, int on);
 clb_status clb_profile_get(clb_ctx* ctx, const char* kernel, double* ms, uint64_t* launches);
 

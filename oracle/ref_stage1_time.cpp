@@ -10,7 +10,8 @@
 // With COLORD_TIME_STAGES=12q the quality entropy coder thread (CEntrComprQuals, compression.cpp:654-668) runs as well,
 // writing its parts to the archive given on the command line: stages 1 + 2 + the quality stream of stage 3; with
 // COLORD_TIME_STAGES=12qd the DNA entropy coder thread (CEntrComprReads, compression.cpp:629-647) runs too (everything but
-// the header coder).
+// the header coder); with COLORD_TIME_STAGES=12qdh the header coder thread (CEntrComprHeaders, compression.cpp:670-689) runs as
+// well: all three compute stages of the compression path.
 //
 // Usage: oracle/_ref/ref_stage1_time compress-ont [flags] -t N in.fastq ignored.out
 #include "compression.h"
@@ -23,6 +24,7 @@
 #include "encoder.h"
 #include "entr_qual.h"
 #include "entr_read.h"
+#include "entr_header.h"
 #include "archive.h"
 #include "reference_reads.h"
 #include "ref_reads_accepter.h"
@@ -84,16 +86,23 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	uint64_t n_links = 0, n_out = 0;
 	std::thread reader([&] { CInputReads r(false, params.inputFilePath, reads_queue, quals_queue, headers_queue); });
 	const char* stages_env0 = getenv("COLORD_TIME_STAGES");
-	const bool qual_consumed = stages_env0 && (std::string(stages_env0) == "12q" || std::string(stages_env0) == "12qd");
+	const bool hdr_consumed = stages_env0 && std::string(stages_env0) == "12qdh";
+	const bool qual_consumed = hdr_consumed || (stages_env0 && (std::string(stages_env0) == "12q" || std::string(stages_env0) == "12qd"));
 	std::thread drain_q([&] { if (qual_consumed) return; qual_pack_t p; while (quals_queue.Pop(p)); });
-	std::thread drain_h([&] { header_pack_t p; while (headers_queue.Pop(p)); });
+	CArchive archive(false);
+	if (qual_consumed && !archive.Open(params.outputFilePath)) { std::cerr << "cannot open " << params.outputFilePath << "\n"; exit(1); }
+	std::thread drain_h([&] {
+		if (!hdr_consumed) { header_pack_t p; while (headers_queue.Pop(p)); return; }
+		CEntrComprHeaders compr{ headers_queue, archive, params.headerComprMode, params.compressionLevel, false };
+		compr.Compress();
+	});
 	std::thread graph([&] {
 		CReadsSimilarityGraph g(reads_queue, graph_out, reference_reads, nullptr, filtered_kmers, kmerLen, params.maxCandidates,
 			params.maxKmerCount, params.referenceReadsMode, accepter, (double)tot_ref_reads / tot_n_reads, n_compression_threads,
 			params.dataSource, params.fillFactorKmersToReads, false);
 	});
 	const char* stages_env = getenv("COLORD_TIME_STAGES");
-	const bool with_dna = stages_env && std::string(stages_env) == "12qd";
+	const bool with_dna = stages_env && (std::string(stages_env) == "12qd" || std::string(stages_env) == "12qdh");
 	const bool with_qual = with_dna || (stages_env && std::string(stages_env) == "12q");
 	const bool with_encoders = with_qual || (stages_env && std::string(stages_env) == "12");
 	uint64_t es_bytes = 0;
@@ -115,8 +124,6 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 					is_fastq, params.filterHashModulo, kmerLen, params.dataSource);
 				enc.Encode();
 			});
-		CArchive archive(false);
-		if (with_qual && !archive.Open(params.outputFilePath)) { std::cerr << "cannot open " << params.outputFilePath << "\n"; exit(1); }
 		std::thread drain_esq([&] {
 			if (!with_qual) { std::vector<es_t> p; while (es_for_qual.Pop(p)); return; }
 			CEntrComprQuals compr{ quals_queue, archive, params.qualityComprMode, params.qualityFwdThresholds, params.qualityRevThresholds, false,
@@ -136,7 +143,7 @@ void runCompression(const CCompressorParams& params, CInfo& info)
 	printf("{\"count_s\": %.4f, \"filter_s\": %.4f, \"graph_s\": %.4f, \"stage1_s\": %.4f, \"k\": %u, \"n_reads\": %u, \"tot_kmers\": %llu, "
 		"\"n_unique_counted\": %llu, \"tot_ref_reads\": %u, \"n_links\": %llu, \"threads\": %u, \"stages\": \"%s\", \"anchor_len\": %u, \"es_bytes\": %llu, \"n_out\": %llu}\n",
 		t1 - t0, t2 - t1, t4 - t3, (t2 - t0) + (t4 - t3), kmerLen, tot_n_reads, (unsigned long long)tot_kmers, (unsigned long long)n_uniq,
-		tot_ref_reads, (unsigned long long)n_links, params.nThreads, with_dna ? "1+2+3qd" : with_qual ? "1+2+3q" : with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
+		tot_ref_reads, (unsigned long long)n_links, params.nThreads, hdr_consumed ? "1+2+3" : with_dna ? "1+2+3qd" : with_qual ? "1+2+3q" : with_encoders ? "1+2" : "1", anchorLen, (unsigned long long)es_bytes, (unsigned long long)n_out);
 	fflush(stdout);
 	_exit(0);     // skip archive/info epilogue of the CLI callback
 }

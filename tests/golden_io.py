@@ -66,3 +66,20 @@ def load_qual_golden(name):
     off = np.zeros(n + 1, np.uint64)
     off[1:] = np.cumsum(lens)
     return bases, quals, quan, off
+
+
+def load_hdr_golden():
+    """-> {case: (list of header bytes, header-stream bytes of the unmodified reference)} from tests/golden/headers.json.gz
+    (written by tests/golden/make_hdr_golden.py; the synthetic case is regenerated from its recipe)."""
+    import gzip
+    import importlib.util
+    with gzip.open(os.path.join(GOLDEN, "headers.json.gz"), "rt") as f:
+        raw = json.load(f)
+    spec = importlib.util.spec_from_file_location("make_hdr_golden", os.path.join(GOLDEN, "make_hdr_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = {}
+    for name, rec in raw.items():
+        hs = mod.synth_headers() if rec["headers"] is None else [h.encode("latin-1") for h in rec["headers"]]
+        out[name] = (hs, rec["ref_header_stream_bytes"])
+    return out

@@ -233,3 +233,42 @@ def dna_decode(stream, n_reads, is_ref, cap_bases):
     rc = L.orc_dna_decode(np.ascontiguousarray(stream, np.uint8), len(stream), n_reads, np.ascontiguousarray(is_ref, np.uint8), out, int(cap_bases), off)
     assert rc == 0, rc
     return out[:int(off[-1])], off
+
+
+def _hdr_arrays(headers):
+    b = np.frombuffer(b"".join(headers), np.uint8)
+    off = np.zeros(len(headers) + 1, np.uint64)
+    off[1:] = np.cumsum([len(h) for h in headers], dtype=np.uint64)
+    return np.ascontiguousarray(b if len(b) else np.zeros(1, np.uint8)), off
+
+
+def hdr_encode(headers, plus=None, packs=None):
+    """CPU twin of the native header container (oracle/stage3_hdr.c).  packs None: packs of 4096 headers (the device default)."""
+    L = lib()
+    L.orc_hdr_encode.restype = C.c_int64
+    L.orc_hdr_encode.argtypes = [_u8p, _u64p, C.c_void_p, C.c_uint64, _u32p, C.c_uint32, _u8p, C.c_uint64]
+    n = len(headers)
+    if packs is None:
+        packs = [min(4096, n - i) for i in range(0, n, 4096)]
+    ps = np.ascontiguousarray(packs if len(packs) else [0], np.uint32)
+    b, off = _hdr_arrays(headers)
+    pl = None if plus is None else np.ascontiguousarray(plus, np.uint8)
+    cap = 2 * len(b) + 300 * (len(packs) + 1) + (1 << 20)
+    out = np.zeros(cap, np.uint8)
+    rc = L.orc_hdr_encode(b, off, None if pl is None else pl.ctypes.data, n, ps, len(packs), out, cap)
+    assert rc >= 0, rc
+    return out[:rc]
+
+
+def hdr_decode(stream, n, cap_bytes):
+    """Decoder of the native header container -> (list of bytes, plus flags)."""
+    L = lib()
+    L.orc_hdr_decode.restype = C.c_int64
+    L.orc_hdr_decode.argtypes = [_u8p, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, _u64p, _u8p]
+    out = np.zeros(int(cap_bytes) + 16, np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    plus = np.zeros(n + 1, np.uint8)
+    rc = L.orc_hdr_decode(np.ascontiguousarray(stream, np.uint8), len(stream), n, out, int(cap_bytes), off, plus)
+    assert rc >= 0, rc
+    raw = out.tobytes()
+    return [raw[int(off[i]):int(off[i + 1])] for i in range(n)], plus[:n]

@@ -107,3 +107,46 @@ def test_dna_stream_size_vs_reference():
     size, hdr, tuples = _dna_round_trip(s, 20, 12, 4, 80, 5, P, 1, sparse_g=1.0)
     print(f"native DNA container {size} B (tables {hdr} B) vs reference 18231949 B: {size / 18231949:.4f}")
     assert size <= 1.005 * 18_231_949, (size, hdr)
+
+
+# ------------------------------------------------------------------------------------------------ header stream
+def _device_headers(hs, plus=None, packs=None):
+    with lib.Context(20, 12, 3, 80, 5) as ctx:
+        ctx.hdr_encode(hs, plus, packs)
+        return ctx.hdr_stream()
+
+
+@pytest.mark.parametrize("packs", [None, "ragged"])
+def test_header_stream_edges(packs):
+    """Every branch of the event model: the device container equals the CPU twin byte for byte and decodes to the input."""
+    from test_oracle_stage3 import hdr_edge_cases
+    for case, hs in hdr_edge_cases().items():
+        n = len(hs)
+        ps = None
+        if packs == "ragged" and n:
+            ps = [min(n, 3), 0, max(0, n - 3)]
+        plus = np.array([(i * 7) % 3 == 0 for i in range(n)], np.uint8)
+        got, _ = _device_headers(hs, plus, ps)
+        want = oracle_lib.hdr_encode(hs, plus, ps)
+        assert np.array_equal(got, want), case
+        dec, dplus = oracle_lib.hdr_decode(got, n, sum(map(len, hs)))
+        assert dec == hs and np.array_equal(dplus, plus), case
+
+
+def test_header_stream_fixtures_and_size():
+    """Headers of the reference's own test inputs + 20 000 synthetic ONT headers: device == twin, decode == input, and the
+    synthetic case is no larger than the unmodified reference's header stream for the same headers."""
+    for name, (hs, ref_bytes) in golden_io.load_hdr_golden().items():
+        got, tables = _device_headers(hs)
+        assert np.array_equal(got, oracle_lib.hdr_encode(hs)), name
+        dec, _ = oracle_lib.hdr_decode(got, len(hs), sum(map(len, hs)))
+        assert dec == hs, name
+        if name.startswith("synthetic"):
+            print(f"native header container {len(got)} B (tables {tables} B) vs reference {ref_bytes} B")
+            assert len(got) <= ref_bytes
+
+
+def test_header_stream_refuses_nul():
+    with lib.Context(20, 12, 3, 80, 5) as ctx:
+        with pytest.raises(lib.ClbError):
+            ctx.hdr_encode([b"@a", b"@b\x00c"])
