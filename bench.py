@@ -14,7 +14,8 @@ coder lanes per pack); `config.stages` says so and the reference arm times the S
 
 value  = FASTQ-equivalent input bytes of the whole job / step time, inputs resident in HBM.
 e2e    = same through the C-ABI with HOST (pinned) buffers: H2D inside the timed region, candidates read back.
-Multi-GPU (torchrun): reads shard by id (strong scaling), one all-to-all + one all-gather of k-mer tables.
+Multi-GPU (torchrun): reads shard by id (strong scaling); one all-to-all + one all-gather of k-mer tables, one all-gather of the
+reference reads (every rank keeps those of the ranks before it as context reads: same candidates and tuples as one GPU).
 """
 from __future__ import annotations
 
@@ -259,7 +260,7 @@ def main():
     import torch
     import torch.distributed as dist
     from colord_b200 import lib
-    from colord_b200.dist import exchange_counts_and_finalize
+    from colord_b200.dist import exchange_counts_and_finalize, exchange_reference_reads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -316,6 +317,15 @@ def main():
 
     stream = torch.cuda.Stream(device=device)
     peak, peak_src = measured_peak_hbm()
+    lens_host = np.diff(offsets.cpu().numpy())
+    out_pinned = {}      # e2e: the finished streams land in pinned host buffers (sized on first use, kept across steps)
+
+    def read_stream(ctx, which):
+        n = {"dna": lambda: ctx.dna_stream_size(), "qual": ctx.qual_size, "hdr": lambda: ctx.hdr_stream_size()}[which]()
+        if which not in out_pinned or out_pinned[which].numel() < n:
+            out_pinned[which] = torch.empty(int(n * 1.1) + 4096, dtype=torch.uint8, pin_memory=True)
+        ctx.stream_into(which, out_pinned[which].data_ptr(), out_pinned[which].numel())
+        return out_pinned[which].numpy()[:n]
 
     def one_step(host_bases=None, host_offsets=None, host_quals=None, host_hdr=None, profile=False, readback=False):
         ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], expected_bases=n_bases_local, device=local_rank)
@@ -330,6 +340,10 @@ def main():
             stats = exchange_counts_and_finalize(ctx, device, n_local)
         rng = sparse_range(stats, p)
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
+        if world > 1:      # global reference-read set: the reference reads of the shards before mine become my context reads
+            with torch.cuda.stream(stream):
+                exchange_reference_reads(ctx, device, sampled, lens_host)
+                stream.synchronize()
         ctx.graph_build(sampled)
         out = None
         if args.stages in ("12", "12q", "12qd", "12qdh"):
@@ -349,11 +363,11 @@ def main():
                     ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
             if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
                 if args.stages == "12qdh":
-                    out = (ctx.dna_stream()[0], ctx.qual_stream(), ctx.hdr_stream()[0])
+                    out = (read_stream(ctx, "dna"), read_stream(ctx, "qual"), read_stream(ctx, "hdr"))
                 elif args.stages == "12qd":
-                    out = (ctx.dna_stream()[0], ctx.qual_stream())
+                    out = (read_stream(ctx, "dna"), read_stream(ctx, "qual"))
                 else:
-                    out = ctx.encoded(n_local)
+                    out = ctx.encoded(ctx.n_reads)
                     if args.stages == "12q":
                         out = out + (ctx.qual_stream(),)
         elif readback:

@@ -115,6 +115,19 @@ clb_status clb_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* 
 clb_status clb_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present)
 { CLB_ENTER(c); return s1a_filter_check(c, kmers, n, possible, present); }
 
+clb_status clb_append_context_reads(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device)
+{
+	CLB_ENTER(c);
+	if (!offsets || (!bases && n_reads)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s1a_append(c, bases, offsets, n_reads, on_device, true);
+}
+clb_status clb_reads_have_n(clb_ctx* c, uint8_t* flags) { CLB_ENTER(c); if (!flags) return fail(c, CLB_ERR_BAD_ARG, "null argument"); return s1b_reads_have_n(c, flags); }
+clb_status clb_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device)
+{
+	CLB_ENTER(c);
+	if ((!read_ids || !bases) && n) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s1b_reads_export(c, read_ids, n, bases, cap, on_device);
+}
 clb_status clb_graph_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo) { CLB_ENTER(c); return s1b_build(c, is_reference, n_pseudo); }
 
 clb_status clb_graph_accepted_size(clb_ctx* c, uint64_t* total)

@@ -68,6 +68,7 @@ struct clb_ctx {
 	clb::DevBuf<uint32_t> rd_len;    // per read: length in bases
 	uint64_t n_pos = 0;              // positions used in the stream (multiple of 128)
 	uint64_t n_reads = 0;
+	uint64_t n_context = 0;          // leading reads that are context only: reference reads of earlier shards (never queried, not encoded)
 	uint64_t n_reads_remote = 0;     // reads counted on other ranks (merged tables)
 	uint64_t n_bases = 0;
 	std::vector<uint64_t> h_rd_start; // host mirrors (small: 12 B per read)
@@ -166,7 +167,9 @@ void prof_resolve(clb_ctx* c);
 
 // stage entry points implemented in the .cu files
 clb_status s1a_init(clb_ctx* c);
-clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device);
+clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context = false);
+clb_status s1b_reads_have_n(clb_ctx* c, uint8_t* flags);
+clb_status s1b_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device);
 clb_status s1a_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n);
 clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_out, int on_device);
 clb_status s1a_counts_reset(clb_ctx* c);

@@ -47,6 +47,7 @@ CLB_HD uint32_t no_bytes_of(uint64_t x) { uint32_t r = 1; x >>= 8; for (; x; ++r
 struct DnaReads {                       // what the walk needs from the resident read store
 	const uint64_t* pk; const uint64_t* rd_start; const uint32_t* rd_len; const uint32_t* ref_to_read;
 	const uint8_t* es; const uint64_t* es_off;
+	uint32_t first;                     // reads are numbered from the first non-context read: read r of the walk is read first + r of the store
 };
 struct OrientedRef { uint64_t start; uint32_t len; uint32_t rev; };
 CLB_D OrientedRef oriented(const DnaReads& R, uint32_t ref_id, uint32_t rev) { const uint32_t rr = R.ref_to_read[ref_id]; return OrientedRef{R.rd_start[rr], R.rd_len[rr], rev}; }
@@ -55,15 +56,15 @@ CLB_D uint32_t ref_sym(const DnaReads& R, const OrientedRef& o, int pos)
 	if (pos < 0 || (uint32_t)pos >= o.len) return 255u;               // the guard byte of read_t
 	return o.rev ? 3u - base_at(R.pk, o.start + (o.len - 1 - (uint32_t)pos)) : base_at(R.pk, o.start + (uint32_t)pos);
 }
-CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
+CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[R.first + r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
 
 // The events of read r, in coding order.  ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).
 // sink.put(family, context, symbol)
 template <class Sink>
 __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint32_t ctx_read_type, Sink& sink)
 {
-	const uint8_t* t = R.es + R.es_off[r];
-	const uint64_t tn = R.es_off[r + 1] - R.es_off[r];
+	const uint8_t* t = R.es + R.es_off[R.first + r];
+	const uint64_t tn = R.es_off[R.first + r + 1] - R.es_off[R.first + r];
 	uint32_t n_tuples = 0;
 	for (uint64_t p = 0; p < tn; ++n_tuples) { const uint32_t ty = t[p] >> 4; p += (ty == 4 || ty == 5) ? 4 : (ty == 6 || ty == 10) ? 5 : 1; }
 	const uint32_t flag = (t[0] >> 4) == 9 ? 0u : (t[0] >> 4) == 11 ? 1u : 2u;
@@ -88,7 +89,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 
 	auto be32 = [&](uint64_t p) { return ((uint32_t)t[p] << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; };
 	auto put_read_id = [&](uint32_t id) {
-		const int n = (int)no_bytes_of(r);
+		const int n = (int)no_bytes_of(R.first + r);      // reference ids stay below the read's index in the store
 		for (int i = n - 1; i >= 0; --i) { const uint64_t add = (i == n - 2) ? ((id >> (8 * (n - 1))) & 0xff) : 0; sink.put(F_READID, (uint64_t)i + (add << 3), (id >> (8 * i)) & 0xff); }
 	};
 	uint32_t seen_id[34]; uint32_t n_seen = 0; uint64_t ctx_rev = 0xf;         // uo_rev_comp of this read

@@ -462,9 +462,12 @@ static clb_status tab_ensure(clb_ctx* c, uint64_t incoming)
 // through two device buffers on a copy stream so the H2D of chunk i+1 overlaps k_pack/k_count of chunk i.
 constexpr uint64_t APPEND_CHUNK = 1ULL << 26;      // positions; multiple of 128
 
-clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device)
+// context = true (clb_append_context_reads): the reads are packed into the store but not counted, and they take the read
+// ids 0 .. n_reads-1 in front of the reads appended so far (multi-GPU: reference reads of earlier shards)
+clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context)
 {
-	if (c->finalized) return fail(c, CLB_ERR_STATE, "clb_append_reads after clb_count_finalize");
+	if (!context && c->finalized) return fail(c, CLB_ERR_STATE, "clb_append_reads after clb_count_finalize");
+	if (context && (!c->finalized || c->graph_done || c->n_context)) return fail(c, CLB_ERR_STATE, "clb_append_context_reads: once, after clb_count_finalize and before clb_graph_build");
 	if (n_reads == 0) return CLB_OK;
 	cudaStream_t s = c->stream;
 	// offsets are needed on the host too (read bookkeeping is tiny: 12 B per read)
@@ -490,8 +493,20 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	CLB_CUDA(c, c->pk.reserve(want_words + 2, s, true, w0));      // stage 2 reads windows across a word boundary: one word of slack
 	CLB_CUDA(c, c->nmask.reserve(want_words, s, true, w0));
 	CLB_CUDA(c, c->smask.reserve(want_words, s, true, w0));
-	CLB_CUDA(c, c->rd_start.reserve(c->n_reads + n_reads, s, true, c->n_reads));
-	CLB_CUDA(c, c->rd_len.reserve(c->n_reads + n_reads, s, true, c->n_reads));
+	if (!context) {
+		CLB_CUDA(c, c->rd_start.reserve(c->n_reads + n_reads, s, true, c->n_reads));
+		CLB_CUDA(c, c->rd_len.reserve(c->n_reads + n_reads, s, true, c->n_reads));
+	} else {      // shift the existing reads up by n_reads ids
+		DevBuf<uint64_t> ns; DevBuf<uint32_t> nl;
+		CLB_CUDA(c, ns.reserve(c->n_reads + n_reads, s, false)); CLB_CUDA(c, nl.reserve(c->n_reads + n_reads, s, false));
+		if (c->n_reads) {
+			CLB_CUDA(c, cudaMemcpyAsync(ns.p + n_reads, c->rd_start.p, sizeof(uint64_t) * c->n_reads, cudaMemcpyDeviceToDevice, s));
+			CLB_CUDA(c, cudaMemcpyAsync(nl.p + n_reads, c->rd_len.p, sizeof(uint32_t) * c->n_reads, cudaMemcpyDeviceToDevice, s));
+			CLB_CUDA(c, cudaStreamSynchronize(s));
+		}
+		c->rd_start.release(); c->rd_len.release();
+		c->rd_start = ns; c->rd_len = nl;
+	}
 	if (!on_device) {
 		CLB_CUDA(c, c->stage_off.reserve(n_reads + 1, s, false));
 		CLB_CUDA(c, cudaMemcpyAsync(c->stage_off.p, offsets, sizeof(uint64_t) * (n_reads + 1), cudaMemcpyHostToDevice, s));
@@ -512,7 +527,7 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 
 	// read-start mask of the whole append first (needs only the offsets), then chunk by chunk: copy, pack, count
 	CLB_CUDA(c, cudaMemsetAsync(c->smask.p + w0, 0, sizeof(uint32_t) * n_words, s));
-	k_mark_starts<<<(n_reads + 255) / 256, 256, 0, s>>>(d_off, n_reads, pos0, c->n_reads, c->smask.p, c->rd_start.p, c->rd_len.p);
+	k_mark_starts<<<(n_reads + 255) / 256, 256, 0, s>>>(d_off, n_reads, pos0, context ? 0 : c->n_reads, c->smask.p, c->rd_start.p, c->rd_len.p);
 	CLB_LAUNCH_CHECK(c, "k_mark_starts");
 	uint32_t ci = 0;
 	for (uint64_t p = 0; p < n_words * 32; p += APPEND_CHUNK, ++ci) {
@@ -532,12 +547,23 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 			(reinterpret_cast<uintptr_t>(d_src) & 15) == 0, c->d_scal)));
 		CLB_LAUNCH_CHECK(c, "k_pack");
 		if (!on_device) CLB_CUDA(c, cudaEventRecord(c->ev_consumed[ci & 1], s));
+		if (context) continue;
 		clb_status st = tab_ensure(c, (pe - p) / c->prm.modulo + (pe - p) / (4 * (uint64_t)c->prm.modulo) + 4096);
 		if (st != CLB_OK) return st;
 		CLB_TIMED(c, K_COUNT, (k_count<false><<<grid_for(cw, COUNT_THREADS, c->n_sm, 8), COUNT_THREADS, 0, s>>>(c->pk.p, c->nmask.p, c->smask.p,
 			w0, wb, wb + cw, c->prm.kmer_len, c->mt, c->tab, c->tab_log2, c->d_scal)));
 		CLB_LAUNCH_CHECK(c, "k_count");
 	}
+	if (context) {
+		std::vector<uint64_t> hs(n_reads); std::vector<uint32_t> hl(n_reads);
+		for (uint32_t i = 0; i < n_reads; ++i) { hs[i] = pos0 + (h_off[i] - h_off[0]); hl[i] = (uint32_t)(h_off[i + 1] - h_off[i]); }
+		c->h_rd_start.insert(c->h_rd_start.begin(), hs.begin(), hs.end());
+		c->h_rd_len.insert(c->h_rd_len.begin(), hl.begin(), hl.end());
+		c->n_context = n_reads;
+		unsigned long long sc[SC_COUNT];
+		clb_status st = read_scalars(c, sc); if (st != CLB_OK) return st;
+		if (sc[SC_BAD_SYMBOL]) return fail(c, CLB_ERR_BAD_SYMBOL, "input holds a symbol outside ACGTN");
+	} else
 	for (uint32_t i = 0; i < n_reads; ++i) {
 		c->h_rd_start.push_back(pos0 + (h_off[i] - h_off[0]));
 		c->h_rd_len.push_back((uint32_t)(h_off[i + 1] - h_off[i]));

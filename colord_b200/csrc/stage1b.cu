@@ -720,7 +720,7 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 	if (!n) return CLB_OK;
 	VoteArgs a{};
 	a.acc_start = c->acc_start; a.acc_n = c->acc_n; a.acc_id = c->acc_id; a.ref_before = c->d_ref_before;
-	a.post_cnt = c->post_cnt; a.post_off = c->post_off; a.post = c->post; a.n_pseudo = n_pseudo; a.max_cand = mc;
+	a.post_cnt = c->post_cnt; a.post_off = c->post_off; a.post = c->post; a.n_pseudo = std::max<uint32_t>(n_pseudo, (uint32_t)c->n_context); a.max_cand = mc;   // neither kind is ever queried
 	a.cand = c->cand; a.cand_votes = c->cand_votes; a.cand_n = c->cand_n; a.scal = c->d_scal;
 	scal_zero(c, SC_CURSOR2);
 	CLB_TIMED(c, K_VOTE, (k_vote<4096, false><<<(uint32_t)n, VOTE_THREADS, 0, s>>>(a)));
@@ -806,7 +806,8 @@ clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo)
 	c->h_is_ref.resize(n); c->h_ref_before.resize(n);
 	uint32_t nref = 0;
 	for (uint64_t i = 0; i < n; ++i) {
-		const bool ref = i < n_pseudo ? true : ((is_reference == nullptr || is_reference[i] != 0) && !c->h_has_n[i]);
+		// context reads (ids below n_context) are reference reads of earlier shards; is_reference covers the reads after them
+		const bool ref = i < n_pseudo ? true : ((i < c->n_context || is_reference == nullptr || is_reference[i - c->n_context] != 0) && !c->h_has_n[i]);
 		c->h_is_ref[i] = ref; c->h_ref_before[i] = nref; nref += ref;
 	}
 	c->n_ref = nref;
@@ -821,6 +822,57 @@ clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo)
 	if (st == CLB_OK && c->prm.is_hifi) st = run_common(c);
 	if (st == CLB_OK) { CLB_CUDA(c, cudaStreamSynchronize(s)); c->graph_done = true; }
 	return st;
+}
+
+// has-N flag of every read in the store (context reads included), HOST buffer
+clb_status s1b_reads_have_n(clb_ctx* c, uint8_t* flags)
+{
+	cudaStream_t s = c->stream;
+	const uint64_t n = c->n_reads;
+	if (!n) return CLB_OK;
+	uint8_t* d = nullptr;
+	CLB_CUDA(c, cudaMallocAsync((void**)&d, n, s));
+	k_read_flags<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, s>>>(c->nmask.p, c->rd_start.p, c->rd_len.p, (uint32_t)n, d);
+	CLB_LAUNCH_CHECK(c, "k_read_flags");
+	CLB_CUDA(c, cudaMemcpyAsync(flags, d, n, cudaMemcpyDeviceToHost, s));
+	CLB_CUDA(c, cudaFreeAsync(d, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	return CLB_OK;
+}
+
+// ASCII bases of the listed reads back to back (one CTA per read)
+__global__ void __launch_bounds__(256) k_reads_export(const uint64_t* __restrict__ pk, const uint32_t* __restrict__ nmask, const uint64_t* __restrict__ rd_start,
+	const uint32_t* __restrict__ rd_len, const uint32_t* __restrict__ ids, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out)
+{
+	const uint32_t r = ids[blockIdx.x];
+	const uint64_t s0 = rd_start[r]; const uint32_t len = rd_len[r];
+	uint8_t* o = out + out_off[blockIdx.x];
+	for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) {
+		const uint64_t p = s0 + j;
+		o[j] = ((nmask[p >> 5] >> (p & 31)) & 1u) ? (uint8_t)'N' : (uint8_t)"ACGT"[base_at(pk, p)];
+	}
+}
+clb_status s1b_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device)
+{
+	cudaStream_t s = c->stream;
+	if (!n) return CLB_OK;
+	std::vector<uint64_t> off(n + 1, 0);
+	for (uint32_t i = 0; i < n; ++i) {
+		if (read_ids[i] >= c->n_reads) return fail(c, CLB_ERR_BAD_ARG, "clb_reads_export: read id out of range");
+		off[i + 1] = off[i] + c->h_rd_len[read_ids[i]];
+	}
+	if (off[n] > cap) return fail(c, CLB_ERR_CAPACITY, "clb_reads_export: buffer too small");
+	uint32_t* d_ids = nullptr; uint64_t* d_off = nullptr; uint8_t* d_out = bases;
+	CLB_CUDA(c, cudaMallocAsync((void**)&d_ids, sizeof(uint32_t) * n, s)); CLB_CUDA(c, cudaMallocAsync((void**)&d_off, sizeof(uint64_t) * (n + 1), s));
+	if (!on_device) CLB_CUDA(c, cudaMallocAsync((void**)&d_out, off[n] + 1, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_ids, read_ids, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_off, off.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
+	k_reads_export<<<n, 256, 0, s>>>(c->pk.p, c->nmask.p, c->rd_start.p, c->rd_len.p, d_ids, d_off, d_out);
+	CLB_LAUNCH_CHECK(c, "k_reads_export");
+	if (!on_device) { CLB_CUDA(c, cudaMemcpyAsync(bases, d_out, off[n], cudaMemcpyDeviceToHost, s)); CLB_CUDA(c, cudaFreeAsync(d_out, s)); }
+	CLB_CUDA(c, cudaFreeAsync(d_ids, s)); CLB_CUDA(c, cudaFreeAsync(d_off, s));
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	return CLB_OK;
 }
 
 void s1_free(clb_ctx* c)

@@ -754,8 +754,10 @@ static clb_status anchor_batch(clb_ctx* c, const S2P& P, uint32_t lo, uint32_t h
 	CLB_CUDA(c, c->s2_nodes.reserve(n_slots + nb, s, true, n_slots));
 	CLB_CUDA(c, c->s2_cviews.reserve((n_slots + nb) * P.c, s, true, n_slots * P.c));
 	Node* nodes = c->s2_nodes.p + n_slots; CandView* cviews = c->s2_cviews.p + n_slots * P.c;
+	tr.mark("anchors: setup");
 	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes, cviews, d_cursor);
 	if (st != CLB_OK) return st;
+	tr.mark("anchors: s2_anchors");
 	if (c->keep_candidates) { st = dump_candidates(c, P, h_list, nodes, cviews); if (st != CLB_OK) return st; }
 	CLB_TIMED(c, K_ANCHORS, (k_anchor_count<<<(nb + 127) / 128, 128, 0, s>>>(nodes, cviews, nb, P.c, d_acnt)));
 	CLB_LAUNCH_CHECK(c, "k_anchor_count");
@@ -775,7 +777,7 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 {
 	cudaStream_t s = c->stream;
 	const uint32_t pack_lo = 0, pack_hi = (uint32_t)pack_first.size() - 1;
-	const uint32_t lo = 0, hi = (uint32_t)c->n_reads, nr = hi - lo;
+	const uint32_t lo = (uint32_t)c->n_context, hi = (uint32_t)c->n_reads, nr = hi - lo;
 	if (!nr) return CLB_OK;
 	Scoped mem(s);
 	Trace tr(s);
@@ -784,7 +786,7 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 	uint32_t* d_slot = nullptr; uint32_t* d_pack_first = nullptr; unsigned long long* d_cursor = nullptr; BinStats* d_bins = nullptr;
 	CLB_CUDA(c, mem.get(&d_slot, nr)); CLB_CUDA(c, mem.get(&d_pack_first, pack_hi - pack_lo + 1));
 	CLB_CUDA(c, mem.get(&d_cursor, 2)); CLB_CUDA(c, mem.get(&d_bins, 1));
-	CLB_CUDA(c, cudaMemcpyAsync(d_slot, h_slot.data(), sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_slot, h_slot.data() + lo, sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data() + pack_lo, sizeof(uint32_t) * (pack_hi - pack_lo + 1), cudaMemcpyHostToDevice, s));
 
 	DevBuf<Node>& nodes = c->s2_nodes; DevBuf<CandView>& cviews = c->s2_cviews; DevBuf<Task>& tasks = c->s2_tasks;
@@ -809,10 +811,13 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 		uint64_t nt = 0, ncap = 0;
 		st = exclusive_scan(c, d_cnt, nn, d_toff, &nt); if (st != CLB_OK) return st;
 		st = exclusive_scan(c, d_capu, nn, d_coff, &ncap); if (st != CLB_OK) return st;
+		tr.mark("level: count + scans");
 		if (n_tasks + nt >= 0xFFFFFFF0ull) return fail(c, CLB_ERR_CAPACITY, "more than 2^32 parts in one batch: lower CLB_BATCH_MBASES");
 		CLB_CUDA(c, tasks.reserve(n_tasks + nt, s, true, n_tasks));
+		tr.mark("level: tasks.reserve");
 		char* level_buf = nullptr;
 		CLB_CUDA(c, mem.get(&level_buf, ncap * 4 + 16));
+		tr.mark("level: script buffer");
 		const uint64_t es_used = reinterpret_cast<uint64_t>(level_buf);
 		CLB_TIMED(c, K_ENCODE, (k_tasks<true><<<nblk, 128, 0, s>>>(nodes.p, nodes.p, cviews.p, (uint32_t)n0, (uint32_t)n1, P.c, R, arena, nullptr, nullptr, d_toff, d_coff, n_tasks, es_used, tasks.p)));
 		CLB_LAUNCH_CHECK(c, "k_tasks<fill>");
@@ -891,14 +896,15 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	S2P P{prm->anchor_len, prm->min_part_len_alt, prm->max_recurence, prm->min_anchors, c->prm.max_candidates,
 		prm->min_mmer_frac, prm->min_mmer_force, prm->max_matches_mult, prm->es_cost_mult};
 	// packs
-	std::vector<uint32_t> pack_first{0};
+	const uint64_t nc = c->n_context;                 // context reads are not encoded: packs cover the reads after them
+	std::vector<uint32_t> pack_first{(uint32_t)nc};
 	if (pack_sizes) {
-		uint64_t at = 0;
+		uint64_t at = nc;
 		for (uint32_t i = 0; i < n_packs; ++i) { at += pack_sizes[i]; if (pack_sizes[i]) pack_first.push_back((uint32_t)at); }
 		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
 	} else {
 		uint64_t bytes = 0;
-		for (uint64_t i = 0; i < n; ++i) {           // in_reads.cpp:62-76
+		for (uint64_t i = nc; i < n; ++i) {           // in_reads.cpp:62-76
 			bytes += (uint64_t)c->h_rd_len[i] + 1;
 			if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); }
 		}
@@ -914,6 +920,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	if (n) CLB_CUDA(c, cudaMemcpyAsync(h_cand_n.data(), c->cand_n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	CLB_CUDA(c, dmalloc(&c->es_off, n + 1));
+	if (nc) CLB_CUDA(c, cudaMemsetAsync(c->es_off, 0, sizeof(uint64_t) * nc, s));
 	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
 	c->es_total = 0;
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
@@ -923,7 +930,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	std::vector<uint32_t> h_slot(n ? n : 1, 0xFFFFFFFFu);
 	uint64_t n_slots = 0, store_used = 0;
 	tr.mark("encode: setup");
-	for (uint32_t lo = 0; lo < n;) {
+	for (uint32_t lo = (uint32_t)nc; lo < n;) {
 		uint32_t hi = lo; uint64_t bases = 0;
 		while (hi < n && (hi == lo || bases + c->h_rd_len[hi] <= batch_bases)) bases += c->h_rd_len[hi++];
 		clb_status st = anchor_batch(c, P, lo, hi, h_cand_n, h_slot, n_slots, store_used);

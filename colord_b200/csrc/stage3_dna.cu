@@ -88,7 +88,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 {
 	cudaStream_t s = c->stream;
 	DTrace tr(s);
-	const uint64_t n = c->n_reads;
+	const uint64_t nc = c->n_context, n = c->n_reads - nc;      // context reads are not coded
 	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode needs the tuples (clb_encode)");
 	if (c->dna_done) return fail(c, CLB_ERR_STATE, "clb_dna_encode called twice");
 	if (level < 1 || level > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_dna_encode: level must be 1, 2 or 3");
@@ -101,7 +101,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
 	} else {
 		uint64_t bytes = 0;
-		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
+		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[nc + i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
 		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
@@ -114,7 +114,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * n_entries, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice, s));
 	DArgs a{};
-	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off};
+	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off, (uint32_t)nc};
 	a.M = M; a.pack_first = d_pack_first; a.n_packs = np; a.n_reads = (uint32_t)n; a.hist = d_hist;
 	if (n) { CLB_TIMED(c, K_DNA, (k_d_count<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_d_count"); }
 	tr.mark("k_d_count");
@@ -124,7 +124,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	std::vector<uint32_t> tab(n_entries, 0);
 	std::vector<uint8_t> hdr;
-	hdr.insert(hdr.end(), {'D', 'B', '0', '1'}); st_put(hdr, level); st_put(hdr, c->prm.max_candidates); st_put(hdr, (uint64_t)n); st_put(hdr, np);
+	hdr.insert(hdr.end(), {'D', 'B', '0', '1'}); st_put(hdr, level); st_put(hdr, c->prm.max_candidates); st_put(hdr, (uint64_t)n); st_put(hdr, np); st_put(hdr, (uint32_t)nc);
 	st_build_tables(M, F_COUNT, hist, tab, hdr, DB_MIN_CTX);
 	if (std::getenv("CLB_S3_BITS"))      // where the bits go: events, cost under the static tables, empirical context entropy
 		for (uint32_t f = 0; f < F_COUNT; ++f) {

@@ -221,7 +221,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 {
 	cudaStream_t s = c->stream;
 	QTrace tr(s);
-	const uint64_t n = c->n_reads;
+	const uint64_t nc = c->n_context, n = c->n_reads - nc;      // context reads carry no qualities: the stream covers the reads after them
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_qual_encode before the reads are complete (clb_count_finalize)");
 	if (prm->n_bins != 2 && prm->n_bins != 4 && prm->n_bins != 5) return fail(c, CLB_ERR_BAD_ARG, "clb_qual_encode: the *-avg modes have 2, 4 or 5 bins");
 	if (prm->level > 1 && !c->enc_done) return fail(c, CLB_ERR_STATE, "clb_qual_encode at level > 1 needs the tuples (clb_encode) for the match / anchor flags");
@@ -237,7 +237,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
 	} else {
 		uint64_t bytes = 0;
-		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
+		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[nc + i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back((uint32_t)(i + 1)); } }
 		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
@@ -246,7 +246,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	if (on_device) CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
 	else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[nc + i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
 	const uint64_t tot = h_off[n] - h_off[0];
 	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
 	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
@@ -264,10 +264,10 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	if (P.level > 1) {
 		CLB_CUDA(c, dalloc((void**)&d_flags, tot + 16));
 		CLB_CUDA(c, cudaMemsetAsync(d_flags, 0, tot + 16, s));
-		if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(c->es.p, c->es_off, d_qoff, c->rd_len.p, (uint32_t)n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
+		if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, (uint32_t)n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
 	}
 	QArgs a{};
-	a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.n_reads = (uint32_t)n; a.P = P;
+	a.pk = c->pk.p; a.rd_start = c->rd_start.p + nc; a.rd_len = c->rd_len.p + nc; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.n_reads = (uint32_t)n; a.P = P;
 	uint32_t* d_avg = nullptr; uint32_t* d_hist = nullptr; uint32_t* d_mhist = nullptr; uint4* d_tab = nullptr; uint4* d_mtab = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_avg, sizeof(uint32_t) * 5 * (n + 1)));
 	CLB_CUDA(c, dalloc((void**)&d_hist, sizeof(uint32_t) * n_ctx * P.nb)); CLB_CUDA(c, dalloc((void**)&d_mhist, sizeof(uint32_t) * 5 * 128));
@@ -328,7 +328,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		const uint32_t cp = p1 - p0, nl = cp * QB_LANES;
 		std::vector<uint64_t> lane_off(nl + 1, 0);
 		for (uint32_t p = p0; p < p1; ++p)
-			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * QB_LANES + (r - pack_first[p]) % QB_LANES + 1] += c->h_rd_len[r] + 2ull * nb;
+			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * QB_LANES + (r - pack_first[p]) % QB_LANES + 1] += c->h_rd_len[nc + r] + 2ull * nb;
 		for (uint32_t i = 0; i < nl; ++i) lane_off[i + 1] += lane_off[i];
 		uint64_t* d_lane_off = nullptr; uint16_t* d_tmp = nullptr; uint32_t* d_words = nullptr; uint32_t* d_state = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
 		Tmp ct{{}, s};

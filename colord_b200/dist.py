@@ -1,13 +1,17 @@
-"""Multi-GPU plumbing of stage 1a (one process per GPU, torch.distributed).
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
 
-Reads are sharded by id; every rank counts the k-mers of its shard.  The only exchange the path has
-(SURVEY.md §8e): k-mers are owned by hash partition, so one all-to-all moves every (k-mer, count) pair to
-its owner, the owner thresholds its share, and one all-gather hands every rank the union of survivors.
+Reads are sharded by id; every rank counts the k-mers of its shard.  The exchanges the path has:
+(1) k-mers are owned by hash partition, so one all-to-all moves every (k-mer, count) pair to its owner, the owner
+thresholds its share, and one all-gather hands every rank the union of survivors (`exchange_counts_and_finalize`);
+(2) the reference-read set is global: one all-gather of every rank's reference reads, of which a rank keeps those of the
+ranks before it as context reads (`exchange_reference_reads`), so that the candidates, tuples and streams of its shard are
+the ones a single GPU would produce for the same reads.
 `ctx` is a colord_b200.lib.Context (or, in the CPU gloo tests, any object with the same methods); all
 buffers that cross NCCL are device tensors whose pointers go straight into the C-ABI.
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -69,3 +73,46 @@ def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
     uni_c = all_c[keep].contiguous()
     ctx.filter_import_device(uni_k.data_ptr(), uni_c.data_ptr(), int(uni_k.numel()), stats)
     return stats
+
+
+def exchange_reference_reads(ctx, device, sampled_local, lengths_local, group=None):
+    """Make the reference-read set global.  Call after exchange_counts_and_finalize and before ctx.graph_build.
+
+    sampled_local: the sampler's decisions for this rank's reads (numpy u8, the slice of the GLOBAL decision vector);
+    lengths_local: their lengths (numpy).  Every rank exports its reference reads (sampled and free of N) as ASCII on the
+    device; one all-gather (padded to the largest share) hands them to everybody; the reads of the ranks before this one
+    become the context reads of `ctx`.  Returns the number of context reads (0 on rank 0 / world size 1).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return 0
+    rank = dist.get_rank(group)
+    n_local = len(sampled_local)
+    has_n = ctx.reads_have_n(n_local)
+    ids = np.nonzero((np.asarray(sampled_local) != 0) & (has_n == 0))[0].astype(np.uint32)
+    lens = np.asarray(lengths_local)[ids].astype(np.int64)
+    n_bases = int(lens.sum())
+    sizes = torch.zeros(world, 2, dtype=torch.int64, device=device)
+    sizes[rank, 0], sizes[rank, 1] = len(ids), n_bases
+    dist.all_reduce(sizes, group=group)
+    sizes_l = sizes.tolist()
+    pad_r, pad_b = max(1, max(x[0] for x in sizes_l)), max(1, max(x[1] for x in sizes_l))
+    my_lens = torch.zeros(pad_r, dtype=torch.int64, device=device)
+    my_lens[:len(ids)] = torch.from_numpy(lens).to(device)
+    my_bases = torch.zeros(pad_b, dtype=torch.uint8, device=device)
+    if n_bases:
+        ctx.reads_export(ids, n_bases, device_ptr=my_bases.data_ptr())
+    all_lens = torch.empty(world * pad_r, dtype=torch.int64, device=device)
+    all_bases = torch.empty(world * pad_b, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(all_lens, my_lens, group=group)
+    dist.all_gather_into_tensor(all_bases, my_bases, group=group)
+    n_ctx = sum(sizes_l[q][0] for q in range(rank))
+    if n_ctx == 0:
+        return 0
+    ctx_lens = torch.cat([all_lens[q * pad_r:q * pad_r + sizes_l[q][0]] for q in range(rank)])
+    ctx_bases = torch.cat([all_bases[q * pad_b:q * pad_b + sizes_l[q][1]] for q in range(rank)]).contiguous()
+    ctx_off = torch.zeros(n_ctx + 1, dtype=torch.int64, device=device)
+    ctx_off[1:] = torch.cumsum(ctx_lens, 0)
+    del all_lens, all_bases
+    ctx.append_context_reads(ctx_bases.data_ptr(), ctx_off.data_ptr(), n_ctx, on_device=True)
+    return n_ctx

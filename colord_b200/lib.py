@@ -18,6 +18,7 @@ EXPORTS = [
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
     "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
+    "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 
@@ -96,6 +97,9 @@ def load():
     L.clb_dna_encode.argtypes = [vp, u32, vp, u32]
     L.clb_dna_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.clb_dna_get.argtypes = [vp, vp, u64, i32]
+    L.clb_append_context_reads.argtypes = [vp, vp, vp, u32, i32]
+    L.clb_reads_have_n.argtypes = [vp, vp]
+    L.clb_reads_export.argtypes = [vp, vp, u32, vp, u64, i32]
     L.clb_hdr_encode.argtypes = [vp, vp, vp, vp, u64, i32, vp, u32]
     L.clb_hdr_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.clb_hdr_get.argtypes = [vp, vp, u64, i32]
@@ -133,7 +137,8 @@ class Context:
         if st != 0:
             raise ClbError(st, self.L.clb_last_error(None).decode())
         self.h = h
-        self.n_reads = 0
+        self.n_reads = 0          # reads in the store (context reads included)
+        self.n_context = 0
 
     def _ck(self, st):
         if st != 0:
@@ -252,7 +257,7 @@ class Context:
             ptr = None
         else:
             is_reference = np.ascontiguousarray(is_reference, np.uint8)
-            assert len(is_reference) == self.n_reads
+            assert len(is_reference) == self.n_reads - self.n_context
             ptr = _np_ptr(is_reference)
         self._ck(self.L.clb_graph_build(self.h, ptr, n_pseudo))
 
@@ -350,6 +355,33 @@ class Context:
             out.append(rec)
         return out
 
+    # ---- multi-GPU: global reference-read set
+    def append_context_reads(self, bases, offsets, n_reads=None, on_device=False):
+        """Reference reads of earlier shards: ids in front of this context's own reads, not counted, never queried or encoded."""
+        if on_device:
+            self._ck(self.L.clb_append_context_reads(self.h, C.c_void_p(bases), C.c_void_p(offsets), n_reads, 1))
+        else:
+            b = np.ascontiguousarray(bases, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
+            n_reads = len(o) - 1
+            self._ck(self.L.clb_append_context_reads(self.h, _np_ptr(b) if len(b) else None, _np_ptr(o), n_reads, 0))
+        self.n_reads += n_reads
+        self.n_context += n_reads
+
+    def reads_have_n(self, n_reads):
+        out = np.zeros(max(n_reads, 1), np.uint8)
+        self._ck(self.L.clb_reads_have_n(self.h, _np_ptr(out)))
+        return out[:n_reads]
+
+    def reads_export(self, read_ids, total_bases, device_ptr=None):
+        """ASCII bases of the listed reads back to back -> numpy array (or written to device_ptr)."""
+        ids = np.ascontiguousarray(read_ids, np.uint32)
+        if device_ptr is not None:
+            self._ck(self.L.clb_reads_export(self.h, _np_ptr(ids) if len(ids) else None, len(ids), C.c_void_p(device_ptr), int(total_bases), 1))
+            return None
+        out = np.zeros(max(int(total_bases), 1), np.uint8)
+        self._ck(self.L.clb_reads_export(self.h, _np_ptr(ids) if len(ids) else None, len(ids), _np_ptr(out), int(total_bases), 0))
+        return out[:int(total_bases)]
+
     # ---- stage 3
     def dna_encode(self, level, pack_sizes=None):
         """DNA / edit-script stream of all reads from the tuples of encode() (native container DB01)."""
@@ -412,6 +444,26 @@ class Context:
         out = np.zeros(max(n.value, 1), np.uint8)
         self._ck(self.L.clb_hdr_get(self.h, _np_ptr(out), n.value, 0))
         return out[:n.value], h.value
+
+    def dna_stream_size(self):
+        n, h = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.clb_dna_size(self.h, C.byref(n), C.byref(h)))
+        return n.value
+
+    def hdr_stream_size(self):
+        n, h = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.clb_hdr_size(self.h, C.byref(n), C.byref(h)))
+        return n.value
+
+    def stream_into(self, which, host_ptr, cap):
+        """Copy a finished stream ("dna" / "qual" / "hdr") into caller-owned HOST memory (e.g. pinned); -> its size in bytes."""
+        n, h = C.c_uint64(), C.c_uint64()
+        if which == "qual":
+            self._ck(self.L.clb_qual_size(self.h, C.byref(n)))
+        else:
+            self._ck(getattr(self.L, f"clb_{which}_size")(self.h, C.byref(n), C.byref(h)))
+        self._ck(getattr(self.L, f"clb_{which}_get")(self.h, C.c_void_p(host_ptr), cap, 0))
+        return n.value
 
     def profile_enable(self, on=True):
         self._ck(self.L.clb_profile_enable(self.h, int(on)))

@@ -89,9 +89,26 @@ clb_status clb_filter_import(clb_ctx* ctx, const uint64_t* kmers, const uint32_t
 /* CKmerFilter::Possible && Check for a batch of canonical k-mers (kmer_filter.h:129-137); HOST buffers. */
 clb_status clb_filter_check(clb_ctx* ctx, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
 
+/* ---- Multi-GPU: the global reference-read set -----------------------------------------
+ * Reads shard by id, but the candidates of a read are EARLIER reference reads of the whole input (reads_sim_graph.cpp:374-395),
+ * most of which sit at the start of the file in sparse mode (ref_reads_accepter.h:51-57).  Rank r therefore receives the
+ * reference reads of the shards before its own as context reads: they take the read ids 0 .. n-1 in front of the rank's own
+ * reads, are inserted into the k-mers -> reads table like any reference read (same order, same cap: the table a read of the
+ * shard sees is the one the single-GPU run builds), are never queried and never encoded: clb_encode, clb_dna_encode and
+ * clb_qual_encode cover only the reads after them (pack_sizes / qualities are given for those), and their tuples / streams are
+ * identical to what a single GPU produces for the same reads.  Call once, after clb_count_finalize (context reads are not
+ * counted: their k-mers were counted on their own rank) and before clb_graph_build; reads holding N are not reference reads
+ * and must not be sent.  bases / offsets as in clb_append_reads. */
+clb_status clb_append_context_reads(clb_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device);
+/* has-N flag of every read in the store (what CInputReads reports per read, utils.h:46); HOST buffer of n_reads bytes. */
+clb_status clb_reads_have_n(clb_ctx* ctx, uint8_t* flags);
+/* ASCII bases of the listed reads (ids: HOST, store numbering) back to back, e.g. a rank's reference reads for the exchange;
+ * `bases` is a device pointer iff on_device.  CLB_ERR_CAPACITY if cap is below the sum of the reads' lengths. */
+clb_status clb_reads_export(clb_ctx* ctx, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device);
+
 /* ---- Stage 1b: similarity graph -------------------------------------------------------------------
  * Replaces CReadsSimilarityGraph (reads_sim_graph.cpp:530; per pack :324 / HiFi :429) over ALL appended
- * reads at once.  is_reference[i] (HOST, one byte per read, input order) = the value of acceptRefRead
+ * reads at once.  is_reference[i] (HOST, one byte per appended read after the context reads, input order) = the value of acceptRefRead
  * the reference would compute before its hasN test, i.e. the CRefReadsAccepter decision (all ones for
  * -R all); reads holding N are excluded inside.  n_pseudo leading reads are reference-genome
  * pseudo-reads (inserted uncapped, never queried: reads_sim_graph.cpp:295-322). */

@@ -42,16 +42,26 @@ static uint32_t osym(const oref* o, int pos) { if (pos < 0 || (uint32_t)pos >= o
 /* Decodes the container.  is_ref[r]: read r joins the reference reads (the sampler decision, false for reads with N).
  * out_bases: ASCII bases of all reads back to back (capacity cap_bases), out_off[n_reads + 1].  Returns 0, or < 0 on a
  * malformed container, or the needed capacity if cap_bases is too small. */
-int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const uint8_t* is_ref, uint8_t* out_bases, uint64_t cap_bases, uint64_t* out_off)
+/* ctx_bases / ctx_off / n_ctx: the context reads of a shard's container (multi-GPU: the reference reads of earlier shards, which
+ * take the reference ids 0 .. n_ctx-1 and the read ids in front of the container's own reads); n_ctx = 0 for a whole-file container. */
+int64_t orc_dna_decode_ctx(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const uint8_t* is_ref, const uint8_t* ctx_bases, const uint64_t* ctx_off, uint32_t n_ctx,
+	uint8_t* out_bases, uint64_t cap_bases, uint64_t* out_off)
 {
-	if (in_n < 24 || memcmp(in, "DB01", 4)) return -1;
-	uint32_t level, max_cand, n_packs; uint64_t nr, at = 4;
+	if (in_n < 28 || memcmp(in, "DB01", 4)) return -1;
+	uint32_t level, max_cand, n_packs, hdr_ctx; uint64_t nr, at = 4;
 	memcpy(&level, in + at, 4); at += 4; memcpy(&max_cand, in + at, 4); at += 4; memcpy(&nr, in + at, 8); at += 8; memcpy(&n_packs, in + at, 4); at += 4;
-	if (nr != n_reads) return -2;
+	memcpy(&hdr_ctx, in + at, 4); at += 4;
+	if (nr != n_reads || hdr_ctx != n_ctx) return -2;
 	model_t M; make_model(&M, level, max_cand);
 	at = st_read_tables(&M.t, in, at);
 	/* reference reads decoded so far (symbols 0..3) */
-	uint8_t** ref_sym = (uint8_t**)calloc((size_t)n_reads + 1, sizeof(uint8_t*)); uint32_t* ref_len = (uint32_t*)calloc((size_t)n_reads + 1, 4); uint32_t n_ref = 0;
+	uint8_t** ref_sym = (uint8_t**)calloc((size_t)n_reads + n_ctx + 1, sizeof(uint8_t*)); uint32_t* ref_len = (uint32_t*)calloc((size_t)n_reads + n_ctx + 1, 4); uint32_t n_ref = 0;
+	for (uint32_t i = 0; i < n_ctx; ++i) {
+		const uint64_t b = ctx_off[i], len = ctx_off[i + 1] - b;
+		uint8_t* q = (uint8_t*)malloc(len + 1);
+		for (uint64_t k = 0; k < len; ++k) { const uint8_t ch = ctx_bases[b + k]; q[k] = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3; }
+		ref_sym[n_ref] = q; ref_len[n_ref] = (uint32_t)len; ++n_ref;
+	}
 	const uint64_t mask_s = (1ull << (2 * M.n_s)) - 1, mask_t = (1ull << (3 * M.n_t)) - 1;
 	const uint32_t sh_t = 3 * M.n_t;
 	uint64_t w = 0; int64_t rc = 0;
@@ -87,7 +97,7 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 			else {
 				uint32_t seen_id[34], seen_rev[34], n_seen = 0; uint64_t ctx_rev = 0xf;
 				uint32_t alt_ids[32]; int alt_revs[32], alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;
-#define GET_READ_ID(dst) do { const int nn = (int)nbytes(r); uint32_t id_ = 0; for (int i = nn - 1; i >= 0; --i) { const uint64_t add = (i == nn - 2) ? id_ : 0; id_ = (id_ << 8) + rc_get(d, &M.t, F_READID, (uint64_t)i + (add << 3)); } dst = id_; } while (0)
+#define GET_READ_ID(dst) do { const int nn = (int)nbytes((uint64_t)n_ctx + r); uint32_t id_ = 0; for (int i = nn - 1; i >= 0; --i) { const uint64_t add = (i == nn - 2) ? id_ : 0; id_ = (id_ << 8) + rc_get(d, &M.t, F_READID, (uint64_t)i + (add << 3)); } dst = id_; } while (0)
 #define GET_REV(id, dst) do { int fnd = -1; for (uint32_t k = 0; k < n_seen; ++k) if (seen_id[k] == (id)) fnd = (int)k; if (fnd >= 0) dst = (int)seen_rev[fnd]; else { const uint32_t fl_ = rc_get(d, &M.t, F_REV, ctx_rev); if (n_seen < 34) { seen_id[n_seen] = (id); seen_rev[n_seen] = fl_; ++n_seen; } ctx_rev = ((ctx_rev << 2) + fl_) & 0xf; dst = (int)fl_; } } while (0)
 				uint32_t main_id; GET_READ_ID(main_id);
 				int main_rev; GET_REV(main_id, main_rev);
@@ -177,4 +187,9 @@ int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const
 	free(ref_sym); free(ref_len); free(M.t.freq);
 	if (rc) return rc;
 	return w > cap_bases ? (int64_t)w : 0;
+}
+
+int64_t orc_dna_decode(const uint8_t* in, uint64_t in_n, uint32_t n_reads, const uint8_t* is_ref, uint8_t* out_bases, uint64_t cap_bases, uint64_t* out_off)
+{
+	return orc_dna_decode_ctx(in, in_n, n_reads, is_ref, 0, 0, 0, out_bases, cap_bases, out_off);
 }

@@ -223,14 +223,19 @@ def qual_decode(stream, bases, offsets, es=None, es_off=None):
     return out
 
 
-def dna_decode(stream, n_reads, is_ref, cap_bases):
-    """Decoder of the native DNA container (oracle/stage3_dna.c) -> (bases ASCII, offsets)."""
+def dna_decode(stream, n_reads, is_ref, cap_bases, ctx_bases=None, ctx_off=None):
+    """Decoder of the native DNA container (oracle/stage3_dna.c) -> (bases ASCII, offsets).  ctx_bases / ctx_off: the context
+    reads of a shard's container (reference reads of earlier shards)."""
     L = lib()
-    L.orc_dna_decode.restype = C.c_int64
-    L.orc_dna_decode.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u8p, _u8p, C.c_uint64, _u64p]
+    L.orc_dna_decode_ctx.restype = C.c_int64
+    L.orc_dna_decode_ctx.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u8p, _u8p, _u64p, C.c_uint32, _u8p, C.c_uint64, _u64p]
     out = np.zeros(int(cap_bases) + 16, np.uint8)
     off = np.zeros(n_reads + 1, np.uint64)
-    rc = L.orc_dna_decode(np.ascontiguousarray(stream, np.uint8), len(stream), n_reads, np.ascontiguousarray(is_ref, np.uint8), out, int(cap_bases), off)
+    if ctx_off is None:
+        ctx_bases, ctx_off = np.zeros(1, np.uint8), np.zeros(1, np.uint64)
+    rc = L.orc_dna_decode_ctx(np.ascontiguousarray(stream, np.uint8), len(stream), n_reads, np.ascontiguousarray(is_ref if len(is_ref) else [0], np.uint8),
+                              np.ascontiguousarray(ctx_bases if len(ctx_bases) else [0], np.uint8), np.ascontiguousarray(ctx_off, np.uint64), len(ctx_off) - 1,
+                              out, int(cap_bases), off)
     assert rc == 0, rc
     return out[:int(off[-1])], off
 
