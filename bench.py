@@ -421,9 +421,12 @@ def main():
         hh = None if hdr_host is None else (hdr_host.numpy(), hdr_off_host)
         e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, host_quals=hq, host_hdr=hh, readback=True)
         d2h = int(sum(x.nbytes for x in out))
+        sizes_all = torch.tensor([int(x.nbytes) for x in out], dtype=torch.int64, device=device)
+        if world > 1:      # whole-job stream sizes (the ratio check across shard counts)
+            dist.all_reduce(sizes_all)
         e2e = {"value": job_bytes / (e_ms / 1e3) / 1e6, "unit": "MB/s", "ms_per_step": e_ms,
                "h2d_bytes_per_step": int(n_bases_local * (2 if hq is not None else 1) + host_off.nbytes + (0 if hh is None else hh[0].nbytes + hh[1].nbytes)),
-               "d2h_bytes_per_step": d2h, "host_memory": "pinned", "stream_bytes": [int(x.nbytes) for x in out]}
+               "d2h_bytes_per_step": d2h, "host_memory": "pinned", "stream_bytes_rank0": [int(x.nbytes) for x in out], "stream_bytes_job": sizes_all.tolist()}
         del host_bases, hb
     clocks = sampler.stop() if sampler else None
 

@@ -296,6 +296,12 @@ clb_status clb_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t
 	if (!prm || !quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
 	return s3_qual_encode(c, prm, quals, offsets, on_device, pack_sizes, n_packs);
 }
+clb_status clb_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	if (!quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s3_qual_encode_original(c, source, level, quals, offsets, on_device, pack_sizes, n_packs);
+}
 clb_status clb_qual_size(clb_ctx* c, uint64_t* total)
 {
 	CLB_ENTER(c);

@@ -187,6 +187,9 @@ clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offse
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3_qual_flags(clb_ctx* c, const uint64_t* d_qoff, uint32_t n, uint8_t* d_flags);
+clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
 	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);
 

@@ -9,6 +9,9 @@
 //   count thresholds + statistics  src/filtering-KMC/kb_sorter.h:1011-1065, kmc.h:1471-1479
 //   CKmerFilter / CCompactedKmers  src/colord/kmer_filter.h:30-199, filter_kmers.cpp:45-83
 #include "ctx.h"
+#include <ctime>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 
@@ -470,6 +473,13 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	if (context && (!c->finalized || c->graph_done || c->n_context)) return fail(c, CLB_ERR_STATE, "clb_append_context_reads: once, after clb_count_finalize and before clb_graph_build");
 	if (n_reads == 0) return CLB_OK;
 	cudaStream_t s = c->stream;
+	struct ATrace {      // CLB_S2_TRACE=1: wall time of the append (synchronising; debugging aid)
+		bool on; cudaStream_t s; timespec t0; uint64_t bytes = 0; int dev;
+		ATrace(cudaStream_t st, int d) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), dev(d) { clock_gettime(CLOCK_MONOTONIC, &t0); }
+		~ATrace() { if (!on) return; cudaStreamSynchronize(s); timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1);
+			const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+			fprintf(stderr, "[s1] append (%s)               %9.3f ms  %.2f GB/s\n", dev ? "device input" : "host input", ms, bytes / ms / 1e6); }
+	} atrace(s, on_device);
 	// offsets are needed on the host too (read bookkeeping is tiny: 12 B per read)
 	std::vector<uint64_t> h_off(n_reads + 1);
 	const uint64_t* d_off = nullptr;
@@ -483,6 +493,7 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	for (uint32_t i = 0; i < n_reads; ++i)
 		if (h_off[i + 1] < h_off[i] || h_off[i + 1] - h_off[i] > 0xFFFFFFFFull) return fail(c, CLB_ERR_BAD_ARG, "offsets must be non-decreasing, reads < 4 Gbases");
 	const uint64_t nb = h_off[n_reads] - h_off[0];
+	atrace.bytes = nb;
 	const uint8_t* src = bases + h_off[0];
 	// the append occupies a multiple of 128 positions, padding is N-masked
 	const uint64_t pos0 = c->n_pos;

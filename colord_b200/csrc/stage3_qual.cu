@@ -74,6 +74,14 @@ __global__ void __launch_bounds__(128) k_q_flags(const uint8_t* __restrict__ es,
 	}
 }
 
+// the flags of the reads after the context reads (shared with the lossless mode, stage3_qorg.cu); flags must be zeroed
+clb_status s3_qual_flags(clb_ctx* c, const uint64_t* d_qoff, uint32_t n, uint8_t* d_flags)
+{
+	const uint64_t nc = c->n_context;
+	if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(n + 127) / 128, 128, 0, c->stream>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
+	return CLB_OK;
+}
+
 // pass 1: per-read means + (context, symbol) counts; one CTA per read
 __global__ void __launch_bounds__(128) k_q_count(QArgs a)
 {

@@ -4,11 +4,15 @@
 //   per family: [fallback table: 2^fbits contexts] n_dense u32, then per dense context (ascending) LEB128 gap + frequencies;
 //   frequencies of one context: alphabets <= 8 as a presence mask + every present frequency but the last (implied by the
 //   sum 2^12), larger alphabets as count u16 + (symbol u8, frequency u16) pairs.
-// A context is "dense" (own table) when it was seen at least min_ctx times, or when its family has no fallback; all other
-// contexts of the family pool their counts in the fallback table indexed by the low fbits of the context.
+// A context is "dense" (own table) when its family has no fallback, or when it was seen at least min_ctx times AND its own
+// table pays for itself: the bits it saves over the family's pooled table (all contexts sharing the low fbits of the context)
+// exceed the bits its serialisation costs.  All other contexts pool their counts in the fallback table indexed by the low
+// fbits of the context.  Costs are taken in 1/256 bit from a table of -log2(f / 4096), so that the CPU twins
+// (oracle/rc_static.h) reach the same decisions.
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -43,6 +47,18 @@ inline void st_put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
 	}
 }
 
+inline const uint32_t* st_bits_q8()      // [f] = round(-log2(f / 4096) * 256), f = 1 .. 4096
+{
+	static std::vector<uint32_t> t;
+	if (t.empty()) { t.assign(ST_M + 1, 0); for (uint32_t f = 1; f <= ST_M; ++f) t[f] = (uint32_t)std::lround(-std::log2(f / 4096.0) * 256.0); }
+	return t.data();
+}
+inline uint64_t st_freqs_bytes(const uint16_t* f, uint32_t A)
+{
+	uint32_t nz = 0; for (uint32_t k = 0; k < A; ++k) nz += f[k] != 0;
+	return A <= 8 ? 1 + 2ull * (nz ? nz - 1 : 0) : 2 + 3ull * nz;
+}
+
 // M: anything with A[], cbits[], fbits[], base[] per family.  tab[entry] = frequency | cumulative << 16.
 template <class M>
 void st_build_tables(const M& m, uint32_t n_fam, const std::vector<uint32_t>& hist, std::vector<uint32_t>& tab, std::vector<uint8_t>& hdr, uint32_t min_ctx)
@@ -54,10 +70,24 @@ void st_build_tables(const M& m, uint32_t n_fam, const std::vector<uint32_t>& hi
 		std::vector<uint32_t> fbh(n_fb * A, 0); std::vector<uint16_t> fbf(n_fb * A, 0);
 		std::vector<uint8_t> dense(n_ctx, 0);
 		uint32_t nd = 0;
+		if (n_fb) {      // the pooled table of every fallback cell over ALL its contexts: what a context would be coded with otherwise
+			for (uint64_t x = 0; x < n_ctx; ++x) for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
+			for (uint64_t x = 0; x < n_fb; ++x) st_normalise(&fbh[x * A], A, &fbf[x * A]);
+			std::fill(fbh.begin(), fbh.end(), 0u);
+		}
+		const uint32_t* bq = st_bits_q8();
 		for (uint64_t x = 0; x < n_ctx; ++x) {
 			uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
 			if (!t) continue;
-			if (!n_fb || t >= min_ctx) { dense[x] = 1; ++nd; }
+			bool own = !n_fb;
+			if (n_fb && t >= min_ctx) {
+				st_normalise(&h[x * A], A, fr.data());
+				const uint16_t* pf = &fbf[(x & (n_fb - 1)) * A];
+				uint64_t c_own = 0, c_fb = 0;
+				for (uint32_t k = 0; k < A; ++k) if (h[x * A + k]) { c_own += (uint64_t)h[x * A + k] * bq[fr[k]]; c_fb += (uint64_t)h[x * A + k] * bq[pf[k]]; }
+				own = c_fb > c_own + (st_freqs_bytes(fr.data(), A) + 2) * 8 * 256;
+			}
+			if (own) { dense[x] = 1; ++nd; }
 			else for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
 		}
 		for (uint64_t x = 0; x < n_fb; ++x) { st_normalise(&fbh[x * A], A, &fbf[x * A]); st_put_freqs(hdr, &fbf[x * A], A); }

@@ -18,7 +18,7 @@ EXPORTS = [
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
     "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
-    "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export",
+    "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export", "clb_qual_encode_original",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 
@@ -100,6 +100,7 @@ def load():
     L.clb_append_context_reads.argtypes = [vp, vp, vp, u32, i32]
     L.clb_reads_have_n.argtypes = [vp, vp]
     L.clb_reads_export.argtypes = [vp, vp, u32, vp, u64, i32]
+    L.clb_qual_encode_original.argtypes = [vp, u32, u32, vp, vp, i32, vp, u32]
     L.clb_hdr_encode.argtypes = [vp, vp, vp, vp, u64, i32, vp, u32]
     L.clb_hdr_size.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.clb_hdr_get.argtypes = [vp, vp, u64, i32]
@@ -409,6 +410,16 @@ class Context:
             q = np.ascontiguousarray(quals, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
             qp, op = _np_ptr(q), _np_ptr(o)
         self._ck(self.L.clb_qual_encode(self.h, C.byref(prm), qp, op, int(on_device), None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+
+    def qual_encode_original(self, source, level, quals, offsets, pack_sizes=None, on_device=False):
+        """Lossless quality stream (-q org; native container QO01).  source: 0 ONT, 1 CLR, 2 HiFi."""
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        if on_device:
+            qp, op = C.c_void_p(quals), C.c_void_p(offsets)
+        else:
+            q = np.ascontiguousarray(quals, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
+            qp, op = _np_ptr(q), _np_ptr(o)
+        self._ck(self.L.clb_qual_encode_original(self.h, source, level, qp, op, int(on_device), None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
 
     def qual_size(self):
         n = C.c_uint64()

@@ -194,6 +194,15 @@ typedef struct {
  * (device pointers iff on_device).  pack_sizes as for clb_encode (NULL: the reference's pack rule).  Result stays on the device. */
 clb_status clb_qual_encode(clb_ctx* ctx, const clb_qual_params* params, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
+/* Lossless mode, "-q org" (QualityComprMode::Original; CQualityCoder::encode_original, quality_coder_impl.cpp:78-128): one
+ * 96-symbol phred value per base under [the two previous values quantised to 4 bits by the data source's table | bases i, i-1,
+ * (i-2), i+1 | match / anchor flags at level > 1] — the reference's context model; static tables (rare contexts fall back to
+ * the two previous values) + 64 range-coder lanes per pack instead of its adaptive chain.  Native container "QO01"; CPU twin
+ * and decoder: oracle/stage3_qorg.c.  source: 0 ONT, 1 PacBio CLR, 2 PacBio HiFi (DataSource, params.h:30 — selects the
+ * quantiser, quality_coder.cpp:272-505); level = compressionLevel 1..3.  Other arguments as clb_qual_encode; the result is
+ * fetched with clb_qual_size / clb_qual_get (one quality stream per context). */
+clb_status clb_qual_encode_original(clb_ctx* ctx, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status clb_qual_size(clb_ctx* ctx, uint64_t* total_bytes);
 clb_status clb_qual_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
 

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define ST_M 4096u
 #define ST_MAX_FAM 16
@@ -110,6 +111,12 @@ ST_FN void st_put_freqs(st_buf* o, const uint16_t* f, uint32_t A)
 		for (uint32_t k = 0; k < A; ++k) if (f[k]) { st_push8(o, (uint8_t)k); st_push(o, &f[k], 2); }
 	}
 }
+ST_FN uint32_t st_bits_q8(uint32_t f)      /* round(-log2(f / 4096) * 256) */
+{
+	static uint32_t t[ST_M + 1]; static int ready = 0;
+	if (!ready) { for (uint32_t i = 1; i <= ST_M; ++i) t[i] = (uint32_t)lround(-log2(i / 4096.0) * 256.0); ready = 1; }
+	return t[f];
+}
 /* hist[base[f] + ctx * A + sym] -> m->freq (allocated here) and the serialised tables appended to hdr */
 ST_FN void st_write_tables(st_model* m, const uint32_t* hist, st_buf* hdr, uint32_t min_ctx)
 {
@@ -121,10 +128,24 @@ ST_FN void st_write_tables(st_model* m, const uint32_t* hist, st_buf* hdr, uint3
 		uint32_t* fbh = (uint32_t*)calloc(n_fb * A + 1, 4); uint16_t* fbf = (uint16_t*)calloc(n_fb * A + 1, 2);
 		uint8_t* dense = (uint8_t*)calloc(n_ctx, 1);
 		uint32_t nd = 0;
+		if (n_fb) {      /* pooled table of every fallback cell over all its contexts: the alternative a context is compared with */
+			for (uint64_t x = 0; x < n_ctx; ++x) for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
+			for (uint64_t x = 0; x < n_fb; ++x) st_normalise(fbh + x * A, A, fbf + x * A);
+			memset(fbh, 0, (n_fb * A + 1) * 4);
+		}
 		for (uint64_t x = 0; x < n_ctx; ++x) {
 			uint64_t t = 0; for (uint32_t k = 0; k < A; ++k) t += h[x * A + k];
 			if (!t) continue;
-			if (!n_fb || t >= min_ctx) { dense[x] = 1; ++nd; }
+			int own = !n_fb;
+			if (n_fb && t >= min_ctx) {      /* own table iff the bits it saves exceed the bits of its serialisation (1/256-bit units) */
+				st_normalise(h + x * A, A, fr);
+				const uint16_t* pf = fbf + (x & (n_fb - 1)) * A;
+				uint64_t c_own = 0, c_fb = 0; uint32_t nz = 0;
+				for (uint32_t k = 0; k < A; ++k) { nz += fr[k] != 0; if (h[x * A + k]) { c_own += (uint64_t)h[x * A + k] * st_bits_q8(fr[k]); c_fb += (uint64_t)h[x * A + k] * st_bits_q8(pf[k]); } }
+				const uint64_t bytes = A <= 8 ? 1 + 2ull * (nz ? nz - 1 : 0) : 2 + 3ull * nz;
+				own = c_fb > c_own + (bytes + 2) * 8 * 256;
+			}
+			if (own) { dense[x] = 1; ++nd; }
 			else for (uint32_t k = 0; k < A; ++k) fbh[(x & (n_fb - 1)) * A + k] += h[x * A + k];
 		}
 		for (uint64_t x = 0; x < n_fb; ++x) { st_normalise(fbh + x * A, A, fbf + x * A); st_put_freqs(hdr, fbf + x * A, A); }

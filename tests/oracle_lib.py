@@ -277,3 +277,32 @@ def hdr_decode(stream, n, cap_bytes):
     assert rc >= 0, rc
     raw = out.tobytes()
     return [raw[int(off[i]):int(off[i + 1])] for i in range(n)], plus[:n]
+
+
+def qorg_encode(source, level, bases, quals, offsets, pack_sizes, es=None, es_off=None):
+    """CPU twin of the native lossless-quality container (oracle/stage3_qorg.c)."""
+    L = lib()
+    L.orc_qorg_encode.restype = C.c_int64
+    L.orc_qorg_encode.argtypes = [C.c_uint32, C.c_uint32, _u8p, _u8p, _u64p, C.c_uint32, C.c_void_p, C.c_void_p, _u32p, C.c_uint32, _u8p, C.c_uint64]
+    cap = int(len(quals)) + (64 << 20)
+    out = np.zeros(cap, np.uint8)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    esp = es.ctypes.data if es is not None else None
+    eop = es_off.ctypes.data if es_off is not None else None
+    n = L.orc_qorg_encode(source, level, np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(quals, np.uint8), np.ascontiguousarray(offsets, np.uint64),
+                          len(offsets) - 1, esp, eop, ps, len(ps), out, cap)
+    assert 0 <= n <= cap, n
+    return out[:n].copy()
+
+
+def qorg_decode(stream, bases, offsets, es=None, es_off=None):
+    L = lib()
+    L.orc_qorg_decode.restype = C.c_int
+    L.orc_qorg_decode.argtypes = [_u8p, C.c_uint64, _u8p, _u64p, C.c_uint32, C.c_void_p, C.c_void_p, _u8p]
+    out = np.zeros(int(offsets[-1]) + 1, np.uint8)
+    esp = es.ctypes.data if es is not None else None
+    eop = es_off.ctypes.data if es_off is not None else None
+    rc = L.orc_qorg_decode(np.ascontiguousarray(stream, np.uint8), len(stream), np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(offsets, np.uint64),
+                           len(offsets) - 1, esp, eop, out)
+    assert rc == 0, rc
+    return out[:int(offsets[-1])]

@@ -150,3 +150,59 @@ def test_header_stream_refuses_nul():
     with lib.Context(20, 12, 3, 80, 5) as ctx:
         with pytest.raises(lib.ClbError):
             ctx.hdr_encode([b"@a", b"@b\x00c"])
+
+
+# ------------------------------------------------------------------------------------------------ lossless quality stream (-q org)
+@pytest.mark.parametrize("name,source", [("ont", 0), ("hifi", 2), ("hifi", 1)])
+def test_lossless_quality_stream_fixture(name, source):
+    """Reference test inputs, level 1: device container == CPU twin byte for byte, decodes to the input qualities."""
+    bases, quals, _, off = golden_io.load_qual_golden(name)
+    n = len(off) - 1
+    packs = [n // 2, n - n // 2]
+    with lib.Context(20, 12, 3, 80, 5) as ctx:
+        ctx.append_reads(bases, off)
+        ctx.count_finalize()
+        ctx.qual_encode_original(source, 1, quals, off, packs)
+        got = ctx.qual_stream()
+    assert np.array_equal(got, oracle_lib.qorg_encode(source, 1, bases, quals, off, packs))
+    assert np.array_equal(oracle_lib.qorg_decode(got, bases, off), quals)
+
+
+@pytest.mark.parametrize("level,prof,source", [(2, "ont", 0), (3, "clr", 1), (2, "hifi", 2)])
+def test_lossless_quality_stream_with_flags(level, prof, source):
+    """Level > 1: match / anchor flags from the device's own tuples enter the context; N reads included."""
+    s = synth.generate(500, 120000, 3000, seed=60 + level, profile=prof, n_frac=0.02)
+    with lib.Context(20, 9, 3, 100, 8) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        ctx.graph_build(np.ones(s.n_reads, np.uint8))
+        ctx.encode(P_BAL, [500])
+        es_off, es = ctx.encoded(s.n_reads)
+        ctx.qual_encode_original(source, level, s.quals, s.offsets, [500])
+        got = ctx.qual_stream()
+    assert np.array_equal(got, oracle_lib.qorg_encode(source, level, s.bases, s.quals, s.offsets, [500], es, es_off))
+    assert np.array_equal(oracle_lib.qorg_decode(got, s.bases, s.offsets, es, es_off), s.quals)
+
+
+def test_lossless_quality_stream_size_vs_reference():
+    """2 000 synthetic HiFi reads / 29.9 Mbases (colord_b200.synth, seed 2): the unmodified reference's `compress-pbhifi -q org`
+    writes a 19 286 491-byte quality stream for this input (oracle/_ref/colord, this container)."""
+    s = synth.generate(2000, 3_000_000, 15000, seed=2, profile="hifi")
+    with lib.Context(21, 40, 3, 80, 8, is_hifi=True) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        ctx.qual_encode_original(2, 1, s.quals, s.offsets)
+        got = ctx.qual_stream()
+    print(f"native lossless quality container {len(got)} B vs reference 19286491 B: {len(got) / 19286491:.4f}")
+    assert len(got) <= 1.005 * 19_286_491
+    assert np.array_equal(oracle_lib.qorg_decode(got, s.bases, s.offsets), s.quals)
+
+
+def test_lossless_quality_refuses_bad_bytes():
+    s = synth.generate(20, 20000, 1000, seed=9, profile="ont")
+    q = s.quals.copy(); q[5] = 20
+    with lib.Context(20, 12, 3, 80, 5) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        with pytest.raises(lib.ClbError):
+            ctx.qual_encode_original(0, 1, q, s.offsets)

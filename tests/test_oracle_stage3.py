@@ -74,3 +74,27 @@ def test_header_container_fixtures_and_size():
         assert dec == hs, name
         if name.startswith("synthetic"):
             assert len(stream) <= ref_bytes, (len(stream), ref_bytes)
+
+
+# ------------------------------------------------------------------------------------------------ lossless quality stream (-q org)
+# quality-stream bytes the unmodified reference wrote with `-q org` for its own test files (ONT 284 680, HiFi 397 555)
+REF_QORG_BYTES = {"ont": (0, 284_680), "hifi": (2, 397_555)}
+
+
+@pytest.mark.parametrize("name", list(REF_QORG_BYTES))
+@pytest.mark.parametrize("level", [1, 3])
+def test_lossless_quality_container_round_trip(name, level):
+    """The reference's own test inputs: the container decodes to the input qualities (every source's quantiser, level 1 and the
+    wider level-3 context) and, at level 1, is no larger than the reference's quality stream for the same file."""
+    source, ref_bytes = REF_QORG_BYTES[name]
+    bases, quals, _, off = golden_io.load_qual_golden(name)
+    n = len(off) - 1
+    es = es_off = None
+    if level > 1:      # flags need tuples: plain-read tuples (no match / anchor flags) are enough for the round trip
+        es_off = np.zeros(n + 1, np.uint64); es_off[1:] = np.cumsum(np.ones(n, np.uint64))
+        es = np.full(n, 9 << 4, np.uint8)
+    for src in ({source, 1} if level == 1 else {source}):
+        stream = oracle_lib.qorg_encode(src, level, bases, quals, off, [n // 3, 1, n - n // 3 - 1], es, es_off)
+        assert np.array_equal(oracle_lib.qorg_decode(stream, bases, off, es, es_off), quals)
+        if level == 1 and src == source:
+            assert len(stream) <= ref_bytes, (len(stream), ref_bytes)
