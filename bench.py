@@ -111,7 +111,7 @@ class ClockSampler:
         self.rows = []
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "1000")],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -327,7 +327,16 @@ def main():
         ctx.stream_into(which, out_pinned[which].data_ptr(), out_pinned[which].numel())
         return out_pinned[which].numpy()[:n]
 
+    phases_on = os.environ.get("BENCH_PHASES") is not None
+
     def one_step(host_bases=None, host_offsets=None, host_quals=None, host_hdr=None, profile=False, readback=False):
+        t_ph = [time.perf_counter()]
+
+        def phase(name):      # BENCH_PHASES=1: wall time of every call of the step (debugging aid; the calls synchronise by themselves)
+            if phases_on and rank == 0:
+                t = time.perf_counter()
+                print(f"[phase] {'e2e' if host_bases is not None else 'res'} {name:14s} {1e3 * (t - t_ph[0]):9.1f} ms   free {torch.cuda.mem_get_info()[0] / 2**30:6.1f} GiB", file=sys.stderr)
+                t_ph[0] = t
         ctx = lib.Context(p["k"], p["modulo"], p["min_count"], p["max_count"], p["max_candidates"], expected_bases=n_bases_local, device=local_rank)
         ctx.set_stream(stream.cuda_stream)
         if profile:
@@ -336,8 +345,10 @@ def main():
             ctx.append_reads_device(bases.data_ptr(), off_u64.data_ptr(), n_local)
         else:
             ctx.append_reads(host_bases, host_offsets)
+        phase("append")
         with torch.cuda.stream(stream):
             stats = exchange_counts_and_finalize(ctx, device, n_local)
+        phase("finalize")
         rng = sparse_range(stats, p)
         sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
         if world > 1:      # global reference-read set: the reference reads of the shards before mine become my context reads
@@ -345,12 +356,15 @@ def main():
                 exchange_reference_reads(ctx, device, sampled, lens_host)
                 stream.synchronize()
         ctx.graph_build(sampled)
+        phase("graph")
         out = None
         if args.stages in ("12", "12q", "12qd", "12qdh"):
             ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
+            phase("encode")
             if args.stages in ("12qd", "12qdh"):
                 ctx.dna_encode(1)
+            phase("dna")
             if args.stages == "12qdh":
                 if host_hdr is None:
                     ctx.hdr_encode(bytes_=hdr_dev.data_ptr(), offsets=hdr_off_dev.data_ptr(), n=n_local, on_device=True)
@@ -361,6 +375,7 @@ def main():
                     ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
                 else:
                     ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
+            phase("hdr+qual")
             if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
                 if args.stages == "12qdh":
                     out = (read_stream(ctx, "dna"), read_stream(ctx, "qual"), read_stream(ctx, "hdr"))
@@ -373,6 +388,7 @@ def main():
         elif readback:
             out = ctx.graph_candidates()
         ctx.synchronize()
+        phase("readback")
         return ctx, stats, out
 
     def timed(n_warm, n_steps, **kw):

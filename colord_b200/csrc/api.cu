@@ -58,7 +58,6 @@ void clb_destroy(clb_ctx* c)
 	s1_free(c);
 	s2_free(c);
 	c->qs.release(); c->ds.release(); c->hs.release();
-	{ cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, c->prm.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -359,6 +358,14 @@ void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n,
 		const double p = std::pow(1.0 / (range_no + 1), exponent);
 		decisions[i] = dist(mt) <= p;
 	}
+}
+
+clb_status clb_release_cached_memory(int device)
+{
+	cudaMemPool_t pool;
+	if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return CLB_ERR_NO_DEVICE;
+	cudaDeviceSynchronize();
+	return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? CLB_OK : CLB_ERR_CUDA;
 }
 
 uint64_t clb_kernel_launches(const clb_ctx* c) { return c ? c->launches : 0; }

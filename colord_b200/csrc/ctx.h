@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <unordered_set>
 #include <cuda_runtime.h>
 #include "../../include/colord_b200.h"
 #include "util.cuh"
@@ -10,29 +12,51 @@
 
 namespace clb {
 
-// A growable device array (cudaMallocAsync-free: plain cudaMalloc, grown geometrically on the ctx stream).
+// Device memory.  Measured on a B200 (gpurun_out/tools/alloc_bench.cu): cudaMalloc / cudaFree of a 40 GiB block take 4 / 14 ms,
+// while the stream-ordered pool needs 0.4-0.8 s to map a fresh block of that size (and, near the capacity of the device,
+// seconds when it has to trim fragmented cached blocks first).  So: blocks of 32 MiB and more come straight from cudaMalloc
+// and go back with cudaFree; small scratch comes from the device's default stream-ordered pool, which keeps it cached
+// (clb_release_cached_memory hands it back).
+constexpr uint64_t DEV_BIG_BYTES = 32ull << 20;
+struct BigPtrs { std::mutex m; std::unordered_set<void*> v; };
+inline BigPtrs& big_ptrs() { static BigPtrs b; return b; }
+inline cudaError_t dev_malloc(void** p, uint64_t bytes, cudaStream_t s)
+{
+	if (bytes < DEV_BIG_BYTES) return cudaMallocAsync(p, bytes ? bytes : 1, s);
+	const cudaError_t e = cudaMalloc(p, bytes);
+	if (e == cudaSuccess) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); b.v.insert(*p); }
+	return e;
+}
+inline bool dev_is_big(void* p) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); return b.v.erase(p) != 0; }
+// semantics of cudaFree: everything the device was doing is finished before the memory is reused
+inline void dev_free(void* p, cudaStream_t s) { if (!p) return; if (dev_is_big(p)) { cudaFree(p); return; } cudaDeviceSynchronize(); cudaFreeAsync(p, s); }
+// stream-ordered free of scratch (a large block is freed by cudaFree, which waits for the device by itself)
+inline cudaError_t dev_free_async(void* p, cudaStream_t s) { if (!p) return cudaSuccess; if (dev_is_big(p)) return cudaFree(p); return cudaFreeAsync(p, s); }
+
+// A growable device array, grown geometrically on the ctx stream.
 template <typename T>
 struct DevBuf {
 	T* p = nullptr;
 	uint64_t cap = 0;          // elements
+	cudaStream_t st = nullptr;
 	cudaError_t reserve(uint64_t n, cudaStream_t s, bool keep, uint64_t used = 0)
 	{
+		st = s;
 		if (n <= cap) return cudaSuccess;
 		uint64_t ncap = cap ? cap : 1;
 		while (ncap < n) ncap = ncap + ncap / 2 + 1024;
 		T* q = nullptr;
-		cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+		cudaError_t e = dev_malloc((void**)&q, ncap * sizeof(T), s);
 		if (e != cudaSuccess) return e;
 		if (keep && p && used) {
 			e = cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s);
-			if (e != cudaSuccess) { cudaFree(q); return e; }
-			cudaStreamSynchronize(s);
+			if (e != cudaSuccess) { dev_free_async(q, s); return e; }
 		}
-		if (p) cudaFree(p);
+		if (p) dev_free(p, s);
 		p = q; cap = ncap;
 		return cudaSuccess;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (p) dev_free(p, st); p = nullptr; cap = 0; }
 };
 
 struct CountSlot { uint64_t key; uint32_t cnt; uint32_t pad; };   // 16 B: two slots per 32 B sector

@@ -398,7 +398,7 @@ static clb_status tab_alloc(clb_ctx* c, uint32_t log2cap, CountSlot** out)
 {
 	CountSlot* t = nullptr;
 	const uint64_t cap = 1ULL << log2cap;
-	CLB_CUDA(c, cudaMalloc(&t, cap * sizeof(CountSlot)));
+	CLB_CUDA(c, dev_malloc((void**)&t, cap * sizeof(CountSlot), c->stream));
 	CLB_TIMED(c, K_TAB_MISC, (k_tab_clear<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(t, cap)));
 	CLB_LAUNCH_CHECK(c, "k_tab_clear");
 	*out = t;
@@ -416,7 +416,7 @@ static uint32_t log2_for(uint64_t n_keys)
 
 clb_status s1a_init(clb_ctx* c)
 {
-	CLB_CUDA(c, cudaMalloc(&c->d_scal, sizeof(unsigned long long) * SC_COUNT));
+	CLB_CUDA(c, dev_malloc((void**)&c->d_scal, sizeof(unsigned long long) * SC_COUNT, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->d_scal, 0, sizeof(unsigned long long) * SC_COUNT, c->stream));
 	// distinct keys <= passing occurrences ~ bases / f (the table grows by re-insertion if the hint was low)
 	const uint64_t exp_keys = c->prm.expected_bases / c->prm.modulo + c->prm.expected_bases / (32 * (uint64_t)c->prm.modulo);
@@ -435,7 +435,7 @@ static clb_status tab_grow(clb_ctx* c, uint32_t new_log2)
 	CLB_TIMED(c, K_TAB_MISC, (k_tab_reinsert<<<grid_for(cap, 256, c->n_sm, 16), 256, 0, c->stream>>>(c->tab, cap, nt, new_log2, c->d_scal)));
 	CLB_LAUNCH_CHECK(c, "k_tab_reinsert");
 	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
-	cudaFree(c->tab);
+	dev_free(c->tab, c->stream);
 	c->tab = nt; c->tab_log2 = new_log2;
 	return CLB_OK;
 }
@@ -606,8 +606,8 @@ clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64
 	if (c->finalized) return fail(c, CLB_ERR_STATE, "count table already finalized");
 	uint64_t* dk = kmers; uint32_t* dc = counts;
 	if (!on_device) {
-		CLB_CUDA(c, cudaMalloc(&dk, sizeof(uint64_t) * (cap_out + 1)));
-		CLB_CUDA(c, cudaMalloc(&dc, sizeof(uint32_t) * (cap_out + 1)));
+		CLB_CUDA(c, dev_malloc((void**)&dk, sizeof(uint64_t) * (cap_out + 1), c->stream));
+		CLB_CUDA(c, dev_malloc((void**)&dc, sizeof(uint32_t) * (cap_out + 1), c->stream));
 	}
 	CLB_CUDA(c, cudaMemsetAsync(&c->d_scal[SC_CURSOR], 0, sizeof(unsigned long long), c->stream));
 	const uint64_t cap = 1ULL << c->tab_log2;
@@ -620,7 +620,7 @@ clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64
 		cudaMemcpy(kmers, dk, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost);
 		cudaMemcpy(counts, dc, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost);
 	}
-	if (!on_device) { cudaFree(dk); cudaFree(dc); }
+	if (!on_device) { dev_free(dk, c->stream); dev_free(dc, c->stream); }
 	if (st != CLB_OK) return st;
 	*n_out = sc[SC_CURSOR];
 	if (sc[SC_CURSOR] > cap_out) return fail(c, CLB_ERR_CAPACITY, "clb_counts_export: buffer too small");
@@ -646,8 +646,8 @@ clb_status s1a_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* c
 	const uint64_t* dk = kmers; const uint32_t* dc = counts;
 	uint64_t* tk = nullptr; uint32_t* tc = nullptr;
 	if (!on_device) {
-		CLB_CUDA(c, cudaMalloc(&tk, sizeof(uint64_t) * n));
-		CLB_CUDA(c, cudaMalloc(&tc, sizeof(uint32_t) * n));
+		CLB_CUDA(c, dev_malloc((void**)&tk, sizeof(uint64_t) * n, c->stream));
+		CLB_CUDA(c, dev_malloc((void**)&tc, sizeof(uint32_t) * n, c->stream));
 		CLB_CUDA(c, cudaMemcpyAsync(tk, kmers, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
 		CLB_CUDA(c, cudaMemcpyAsync(tc, counts, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
 		dk = tk; dc = tc;
@@ -659,7 +659,7 @@ clb_status s1a_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* c
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess) st = cuda_fail(c, e, "k_tab_merge");
 	}
-	if (!on_device) { cudaStreamSynchronize(c->stream); cudaFree(tk); cudaFree(tc); }
+	if (!on_device) { cudaStreamSynchronize(c->stream); dev_free(tk, c->stream); dev_free(tc, c->stream); }
 	return st;
 }
 
@@ -669,10 +669,10 @@ static clb_status sv_alloc(clb_ctx* c, uint64_t n_surv)
 	c->sv_log2 = 10;
 	while ((1ULL << c->sv_log2) < 2 * n_surv + 1024) ++c->sv_log2;
 	const uint64_t sv_cap = 1ULL << c->sv_log2;
-	CLB_CUDA(c, cudaMalloc(&c->sv_keys, sizeof(uint64_t) * sv_cap));
-	CLB_CUDA(c, cudaMalloc(&c->sv_ids, sizeof(uint32_t) * sv_cap));
-	CLB_CUDA(c, cudaMalloc(&c->sv_kmer, sizeof(uint64_t) * (n_surv + 1)));
-	CLB_CUDA(c, cudaMalloc(&c->sv_count, sizeof(uint32_t) * (n_surv + 1)));
+	CLB_CUDA(c, dev_malloc((void**)&c->sv_keys, sizeof(uint64_t) * sv_cap, c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&c->sv_ids, sizeof(uint32_t) * sv_cap, c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&c->sv_kmer, sizeof(uint64_t) * (n_surv + 1), c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&c->sv_count, sizeof(uint32_t) * (n_surv + 1), c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->sv_keys, 0xFF, sizeof(uint64_t) * sv_cap, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->sv_ids, 0xFF, sizeof(uint32_t) * sv_cap, c->stream));
 	return CLB_OK;
@@ -707,7 +707,7 @@ clb_status s1a_finalize(clb_ctx* c, clb_kmer_stats* stats)
 		c->sv_kmer, c->sv_count, c->sv_keys, c->sv_ids, c->sv_log2, &c->d_scal[SC_CURSOR])));
 	CLB_LAUNCH_CHECK(c, "k_build_survivors");
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	cudaFree(c->tab); c->tab = nullptr;
+	dev_free(c->tab, c->stream); c->tab = nullptr;
 	c->sum_true = local_pass;           // local passing occurrences bound the accepted k-mers of local reads
 	c->stats = r; c->finalized = true;
 	if (stats) *stats = r;
@@ -719,7 +719,7 @@ clb_status s1a_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* 
 {
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_filter_import before clb_count_finalize");
 	if (c->graph_done) return fail(c, CLB_ERR_STATE, "clb_filter_import after clb_graph_build");
-	cudaFree(c->sv_keys); cudaFree(c->sv_ids); cudaFree(c->sv_kmer); cudaFree(c->sv_count);
+	dev_free(c->sv_keys, c->stream); dev_free(c->sv_ids, c->stream); dev_free(c->sv_kmer, c->stream); dev_free(c->sv_count, c->stream);
 	c->sv_keys = nullptr; c->sv_ids = nullptr; c->sv_kmer = nullptr; c->sv_count = nullptr;
 	clb_status st = sv_alloc(c, n);
 	if (st != CLB_OK) return st;
@@ -740,8 +740,8 @@ clb_status s1a_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_filter_check before clb_count_finalize");
 	if (n == 0) return CLB_OK;
 	uint64_t* dk = nullptr; uint8_t* dp = nullptr;
-	CLB_CUDA(c, cudaMalloc(&dk, sizeof(uint64_t) * n));
-	CLB_CUDA(c, cudaMalloc(&dp, 2 * n));
+	CLB_CUDA(c, dev_malloc((void**)&dk, sizeof(uint64_t) * n, c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&dp, 2 * n, c->stream));
 	CLB_CUDA(c, cudaMemcpyAsync(dk, kmers, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
 	k_filter_check<<<(uint32_t)((n + 255) / 256), 256, 0, c->stream>>>(dk, n, c->mt, c->sv_keys, c->sv_log2, dp, dp + n);
 	++c->launches;
@@ -749,7 +749,7 @@ clb_status s1a_filter_check(clb_ctx* c, const uint64_t* kmers, uint64_t n, uint8
 	if (e == cudaSuccess) e = cudaMemcpyAsync(possible, dp, n, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(present, dp + n, n, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(dk); cudaFree(dp);
+	dev_free(dk, c->stream); dev_free(dp, c->stream);
 	if (e != cudaSuccess) return cuda_fail(c, e, "k_filter_check");
 	return CLB_OK;
 }

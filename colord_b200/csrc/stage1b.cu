@@ -545,13 +545,13 @@ static clb_status scal_zero(clb_ctx* c, int which)
 	return CLB_OK;
 }
 
-template <typename T> static cudaError_t dev_alloc(T** p, uint64_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+template <typename T> static cudaError_t dev_alloc(T** p, uint64_t n, cudaStream_t s = nullptr) { return dev_malloc((void**)p, sizeof(T) * (n ? n : 1), s); }
 
 clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* total)
 {
 	const uint64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	uint64_t* tiles = nullptr;
-	CLB_CUDA(c, cudaMallocAsync((void**)&tiles, sizeof(uint64_t) * (n_tiles + 1), c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&tiles, sizeof(uint64_t) * (n_tiles + 1), c->stream));
 	clb_status st = CLB_OK;
 	if (n_tiles) {
 		k_scan_tiles<<<(uint32_t)n_tiles, SCAN_THREADS, 0, c->stream>>>(in, n, tiles); ++c->launches;
@@ -564,7 +564,7 @@ clb_status exclusive_scan(clb_ctx* c, const uint32_t* in, uint64_t n, uint64_t* 
 	}
 	unsigned long long sc[SC_COUNT];
 	if (st == CLB_OK) st = scal_read(c, sc);
-	cudaFreeAsync(tiles, c->stream);
+	dev_free_async(tiles, c->stream);
 	if (st == CLB_OK) *total = sc[SC_SUM_TRUE];
 	return st;
 }
@@ -588,9 +588,9 @@ static clb_status run_accept(clb_ctx* c)
 	cudaStream_t s = c->stream;
 	const uint64_t n = c->n_reads;
 	c->acc_cap = c->sum_true + 1;
-	CLB_CUDA(c, dev_alloc(&c->acc_start, n));
-	CLB_CUDA(c, dev_alloc(&c->acc_n, n));
-	CLB_CUDA(c, dev_alloc(&c->acc_id, c->acc_cap));
+	CLB_CUDA(c, dev_alloc(&c->acc_start, n, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->acc_n, n, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->acc_id, c->acc_cap, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->acc_n, 0, sizeof(uint32_t) * (n ? n : 1), s));
 	scal_zero(c, SC_CURSOR); scal_zero(c, SC_CURSOR2); scal_zero(c, SC_OVERFLOW);
 
@@ -610,8 +610,8 @@ static clb_status run_accept(clb_ctx* c)
 
 	uint32_t* d_list = nullptr;
 	auto upload = [&](const std::vector<uint32_t>& v) -> clb_status {
-		if (d_list) { cudaFree(d_list); d_list = nullptr; }
-		CLB_CUDA(c, dev_alloc(&d_list, v.size()));
+		if (d_list) { dev_free(d_list, c->stream); d_list = nullptr; }
+		CLB_CUDA(c, dev_alloc(&d_list, v.size(), c->stream));
 		CLB_CUDA(c, cudaMemcpyAsync(d_list, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, s));
 		return CLB_OK;
 	};
@@ -637,10 +637,10 @@ static clb_status run_accept(clb_ctx* c)
 				moff[i + 1] = moff[i] + cap;
 				boff[i + 1] = boff[i] + 2 * ((len + 31) / 32) + 2;
 			}
-			cudaError_t e = dev_alloc(&g_map, moff.back());
-			if (e == cudaSuccess) e = dev_alloc(&g_bits, boff.back());
-			if (e == cudaSuccess) e = dev_alloc(&g_moff, moff.size());
-			if (e == cudaSuccess) e = dev_alloc(&g_boff, boff.size());
+			cudaError_t e = dev_alloc(&g_map, moff.back(), c->stream);
+			if (e == cudaSuccess) e = dev_alloc(&g_bits, boff.back(), c->stream);
+			if (e == cudaSuccess) e = dev_alloc(&g_moff, moff.size(), c->stream);
+			if (e == cudaSuccess) e = dev_alloc(&g_boff, boff.size(), c->stream);
 			if (e == cudaSuccess) e = cudaMemcpyAsync(g_moff, moff.data(), sizeof(uint64_t) * moff.size(), cudaMemcpyHostToDevice, s);
 			if (e == cudaSuccess) e = cudaMemcpyAsync(g_boff, boff.data(), sizeof(uint64_t) * boff.size(), cudaMemcpyHostToDevice, s);
 			if (e != cudaSuccess) { st = cuda_fail(c, e, "accept scratch"); }
@@ -656,7 +656,7 @@ static clb_status run_accept(clb_ctx* c)
 		}
 		unsigned long long sc[SC_COUNT];
 		if (st == CLB_OK) st = scal_read(c, sc);
-		cudaFree(g_map); cudaFree(g_bits); cudaFree(g_moff); cudaFree(g_boff);
+		dev_free(g_map, c->stream); dev_free(g_bits, c->stream); dev_free(g_moff, c->stream); dev_free(g_boff, c->stream);
 		if (st != CLB_OK) break;
 		if (sc[SC_OVERFLOW]) { st = fail(c, CLB_ERR_CUDA, "accepted k-mer arena overflow"); break; }
 		if (sc[SC_CURSOR2]) {
@@ -667,7 +667,7 @@ static clb_status run_accept(clb_ctx* c)
 		}
 		c->acc_total = sc[SC_CURSOR];
 	}
-	if (d_list) cudaFree(d_list);
+	if (d_list) dev_free(d_list, c->stream);
 	return st;
 }
 
@@ -675,8 +675,8 @@ static clb_status run_postings(clb_ctx* c, uint32_t n_pseudo)
 {
 	cudaStream_t s = c->stream;
 	const uint64_t ns = c->n_surv, n = c->n_reads;
-	CLB_CUDA(c, dev_alloc(&c->post_cnt, ns + 1));
-	CLB_CUDA(c, dev_alloc(&c->post_off, ns + 1));
+	CLB_CUDA(c, dev_alloc(&c->post_cnt, ns + 1, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->post_off, ns + 1, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->post_cnt, 0, sizeof(uint32_t) * (ns + 1), s));
 	const uint32_t warps_grid = (uint32_t)((n * 32 + 255) / 256);
 	if (n) {
@@ -685,14 +685,14 @@ static clb_status run_postings(clb_ctx* c, uint32_t n_pseudo)
 	}
 	clb_status st = exclusive_scan(c, c->post_cnt, ns, c->post_off, &c->post_total);
 	if (st != CLB_OK) return st;
-	CLB_CUDA(c, dev_alloc(&c->post, c->post_total));
+	CLB_CUDA(c, dev_alloc(&c->post, c->post_total, c->stream));
 	if (n && c->post_total) {
 		CLB_CUDA(c, cudaMemsetAsync(c->post_cnt, 0, sizeof(uint32_t) * (ns + 1), s));
 		CLB_TIMED(c, K_POSTINGS, (k_post_pass<true><<<warps_grid, 256, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_is_ref, c->d_ref_before, (uint32_t)n, c->post_cnt, c->post_off, c->post)));
 		CLB_LAUNCH_CHECK(c, "k_post_pass<fill>");
 		// lists over the cap
 		uint32_t* d_over = nullptr;
-		CLB_CUDA(c, dev_alloc(&d_over, ns));
+		CLB_CUDA(c, dev_alloc(&d_over, ns, c->stream));
 		scal_zero(c, SC_CURSOR);
 		k_post_oversize<<<(uint32_t)((ns + 255) / 256), 256, 0, s>>>(c->post_cnt, ns, c->prm.max_count, d_over, &c->d_scal[SC_CURSOR]);
 		++c->launches;
@@ -704,7 +704,7 @@ static clb_status run_postings(clb_ctx* c, uint32_t n_pseudo)
 			cudaError_t e = cudaStreamSynchronize(s);
 			if (e != cudaSuccess) st = cuda_fail(c, e, "k_post_truncate");
 		}
-		cudaFree(d_over);
+		dev_free(d_over, c->stream);
 	}
 	return st;
 }
@@ -713,9 +713,9 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 {
 	cudaStream_t s = c->stream;
 	const uint64_t n = c->n_reads; const uint32_t mc = c->prm.max_candidates;
-	CLB_CUDA(c, dev_alloc(&c->cand, n * mc));
-	CLB_CUDA(c, dev_alloc(&c->cand_votes, n * mc));
-	CLB_CUDA(c, dev_alloc(&c->cand_n, n));
+	CLB_CUDA(c, dev_alloc(&c->cand, n * mc, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->cand_votes, n * mc, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->cand_n, n, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->cand_n, 0, sizeof(uint32_t) * (n ? n : 1), s));
 	if (!n) return CLB_OK;
 	VoteArgs a{};
@@ -733,8 +733,8 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 	st = collect_pending(c, c->cand_n, pend);
 	if (st != CLB_OK) return st;
 	uint32_t* d_list = nullptr; unsigned long long* d_bound = nullptr; uint32_t* g_keys = nullptr; uint64_t* g_off = nullptr;
-	CLB_CUDA(c, dev_alloc(&d_list, pend.size()));
-	CLB_CUDA(c, dev_alloc(&d_bound, pend.size()));
+	CLB_CUDA(c, dev_alloc(&d_list, pend.size(), c->stream));
+	CLB_CUDA(c, dev_alloc(&d_bound, pend.size(), c->stream));
 	CLB_CUDA(c, cudaMemcpyAsync(d_list, pend.data(), sizeof(uint32_t) * pend.size(), cudaMemcpyHostToDevice, s));
 	k_vote_bound<<<(uint32_t)((pend.size() * 32 + 255) / 256), 256, 0, s>>>(d_list, (uint32_t)pend.size(), c->acc_start, c->acc_n, c->acc_id, c->post_cnt, d_bound);
 	++c->launches;
@@ -747,8 +747,8 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 		if (cap > (1ULL << 31)) cap = 1ULL << 31;
 		off[i + 1] = off[i] + 2 * cap;
 	}
-	if (e == cudaSuccess) e = dev_alloc(&g_keys, off.back());
-	if (e == cudaSuccess) e = dev_alloc(&g_off, off.size());
+	if (e == cudaSuccess) e = dev_alloc(&g_keys, off.back(), c->stream);
+	if (e == cudaSuccess) e = dev_alloc(&g_off, off.size(), c->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(g_off, off.data(), sizeof(uint64_t) * off.size(), cudaMemcpyHostToDevice, s);
 	if (e == cudaSuccess) {
 		a.list = d_list; a.n_list = (uint32_t)pend.size(); a.g_keys = g_keys; a.g_off = g_off;
@@ -759,7 +759,7 @@ static clb_status run_votes(clb_ctx* c, uint32_t n_pseudo)
 	}
 	if (e == cudaSuccess) { st = scal_read(c, sc); if (st == CLB_OK && sc[SC_CURSOR2]) st = fail(c, CLB_ERR_CUDA, "k_vote: global scratch class failed"); }
 	else st = cuda_fail(c, e, "k_vote<global>");
-	cudaFree(d_list); cudaFree(d_bound); cudaFree(g_keys); cudaFree(g_off);
+	dev_free(d_list, c->stream); dev_free(d_bound, c->stream); dev_free(g_keys, c->stream); dev_free(g_off, c->stream);
 	return st;
 }
 
@@ -768,7 +768,7 @@ static clb_status run_common(clb_ctx* c)
 	cudaStream_t s = c->stream;
 	const uint64_t n = c->n_reads; const uint32_t mc = c->prm.max_candidates;
 	if (mc > 32) return fail(c, CLB_ERR_BAD_ARG, "HiFi path supports max_candidates <= 32");
-	CLB_CUDA(c, dev_alloc(&c->common_off, n * mc));
+	CLB_CUDA(c, dev_alloc(&c->common_off, n * mc, c->stream));
 	CLB_CUDA(c, cudaMemsetAsync(c->common_off, 0, sizeof(uint64_t) * (n * mc ? n * mc : 1), s));
 	scal_zero(c, SC_CURSOR);
 	if (n) { k_common_total<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(c->cand_n, c->cand_votes, (uint32_t)n, mc, &c->d_scal[SC_CURSOR]); ++c->launches; }
@@ -776,7 +776,7 @@ static clb_status run_common(clb_ctx* c)
 	clb_status st = scal_read(c, sc);
 	if (st != CLB_OK) return st;
 	c->common_total = sc[SC_CURSOR];
-	CLB_CUDA(c, dev_alloc(&c->common, c->common_total));
+	CLB_CUDA(c, dev_alloc(&c->common, c->common_total, c->stream));
 	scal_zero(c, SC_CURSOR);
 	if (n && c->common_total) {
 		CLB_TIMED(c, K_COMMON, (k_common<<<(uint32_t)n, COMMON_THREADS, 0, s>>>(c->acc_start, c->acc_n, c->acc_id, c->d_ref_before, c->post_cnt, c->post_off, c->post,
@@ -794,7 +794,7 @@ clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo)
 	if (c->n_reads >= (1ULL << 30)) return fail(c, CLB_ERR_BAD_ARG, "reference ids must stay below 2^30 (hm_compact.h:545-566)");
 	cudaStream_t s = c->stream;
 	const uint64_t n = c->n_reads;
-	CLB_CUDA(c, dev_alloc(&c->d_has_n, n));
+	CLB_CUDA(c, dev_alloc(&c->d_has_n, n, c->stream));
 	if (n) {
 		k_read_flags<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, s>>>(c->nmask.p, c->rd_start.p, c->rd_len.p, (uint32_t)n, c->d_has_n);
 		CLB_LAUNCH_CHECK(c, "k_read_flags");
@@ -811,8 +811,8 @@ clb_status s1b_build(clb_ctx* c, const uint8_t* is_reference, uint32_t n_pseudo)
 		c->h_is_ref[i] = ref; c->h_ref_before[i] = nref; nref += ref;
 	}
 	c->n_ref = nref;
-	CLB_CUDA(c, dev_alloc(&c->d_is_ref, n));
-	CLB_CUDA(c, dev_alloc(&c->d_ref_before, n));
+	CLB_CUDA(c, dev_alloc(&c->d_is_ref, n, c->stream));
+	CLB_CUDA(c, dev_alloc(&c->d_ref_before, n, c->stream));
 	CLB_CUDA(c, cudaMemcpyAsync(c->d_is_ref, c->h_is_ref.data(), n, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(c->d_ref_before, c->h_ref_before.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
 
@@ -831,11 +831,11 @@ clb_status s1b_reads_have_n(clb_ctx* c, uint8_t* flags)
 	const uint64_t n = c->n_reads;
 	if (!n) return CLB_OK;
 	uint8_t* d = nullptr;
-	CLB_CUDA(c, cudaMallocAsync((void**)&d, n, s));
+	CLB_CUDA(c, dev_malloc((void**)&d, n, s));
 	k_read_flags<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, s>>>(c->nmask.p, c->rd_start.p, c->rd_len.p, (uint32_t)n, d);
 	CLB_LAUNCH_CHECK(c, "k_read_flags");
 	CLB_CUDA(c, cudaMemcpyAsync(flags, d, n, cudaMemcpyDeviceToHost, s));
-	CLB_CUDA(c, cudaFreeAsync(d, s));
+	CLB_CUDA(c, dev_free_async(d, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	return CLB_OK;
 }
@@ -863,14 +863,14 @@ clb_status s1b_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, ui
 	}
 	if (off[n] > cap) return fail(c, CLB_ERR_CAPACITY, "clb_reads_export: buffer too small");
 	uint32_t* d_ids = nullptr; uint64_t* d_off = nullptr; uint8_t* d_out = bases;
-	CLB_CUDA(c, cudaMallocAsync((void**)&d_ids, sizeof(uint32_t) * n, s)); CLB_CUDA(c, cudaMallocAsync((void**)&d_off, sizeof(uint64_t) * (n + 1), s));
-	if (!on_device) CLB_CUDA(c, cudaMallocAsync((void**)&d_out, off[n] + 1, s));
+	CLB_CUDA(c, dev_malloc((void**)&d_ids, sizeof(uint32_t) * n, s)); CLB_CUDA(c, dev_malloc((void**)&d_off, sizeof(uint64_t) * (n + 1), s));
+	if (!on_device) CLB_CUDA(c, dev_malloc((void**)&d_out, off[n] + 1, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_ids, read_ids, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_off, off.data(), sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s));
 	k_reads_export<<<n, 256, 0, s>>>(c->pk.p, c->nmask.p, c->rd_start.p, c->rd_len.p, d_ids, d_off, d_out);
 	CLB_LAUNCH_CHECK(c, "k_reads_export");
-	if (!on_device) { CLB_CUDA(c, cudaMemcpyAsync(bases, d_out, off[n], cudaMemcpyDeviceToHost, s)); CLB_CUDA(c, cudaFreeAsync(d_out, s)); }
-	CLB_CUDA(c, cudaFreeAsync(d_ids, s)); CLB_CUDA(c, cudaFreeAsync(d_off, s));
+	if (!on_device) { CLB_CUDA(c, cudaMemcpyAsync(bases, d_out, off[n], cudaMemcpyDeviceToHost, s)); CLB_CUDA(c, dev_free_async(d_out, s)); }
+	CLB_CUDA(c, dev_free_async(d_ids, s)); CLB_CUDA(c, dev_free_async(d_off, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	return CLB_OK;
 }
@@ -884,7 +884,7 @@ void s1_free(clb_ctx* c)
 	for (int b = 0; b < 2; ++b) { if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]); if (c->ev_consumed[b]) cudaEventDestroy(c->ev_consumed[b]); }
 	void* ptrs[] = { c->tab, c->d_scal, c->sv_keys, c->sv_ids, c->sv_kmer, c->sv_count, c->d_has_n, c->d_ref_before, c->d_is_ref,
 		c->acc_start, c->acc_n, c->acc_id, c->post_cnt, c->post_off, c->post, c->cand, c->cand_votes, c->cand_n, c->common_off, c->common };
-	for (void* p : ptrs) if (p) cudaFree(p);
+	for (void* p : ptrs) if (p) dev_free(p, c->stream);
 }
 
 } // namespace clb

@@ -63,8 +63,8 @@ clb_status run_edit_scripts(clb_ctx* c, std::vector<EsTask>& h_tasks, const uint
 	std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return grp[a] != grp[b] ? grp[a] < grp[b] : cost[a] < cost[b]; });
 	EsTask* d_tasks = nullptr; uint32_t* d_list = nullptr; uint8_t* d_scratch = nullptr;
 	unsigned long long scratch_cap = 0;
-	CLB_CUDA(c, cudaMalloc(&d_tasks, sizeof(EsTask) * n));
-	CLB_CUDA(c, cudaMalloc(&d_list, sizeof(uint32_t) * n));
+	CLB_CUDA(c, dev_malloc((void**)&d_tasks, sizeof(EsTask) * n, s));
+	CLB_CUDA(c, dev_malloc((void**)&d_list, sizeof(uint32_t) * n, s));
 	clb_status st = CLB_OK;
 	size_t pos = 0;
 	while (pos < n && st == CLB_OK) {
@@ -73,9 +73,9 @@ clb_status run_edit_scripts(clb_ctx* c, std::vector<EsTask>& h_tasks, const uint
 		size_t end = pos; unsigned long long used = 0;
 		while (end < n && grp[order[end]] == g && (end == pos || used + need[order[end]] <= budget)) { h_tasks[order[end]].scratch_off = used; used += need[order[end]]; ++end; }
 		if (used > scratch_cap) {
-			if (d_scratch) { cudaStreamSynchronize(s); cudaFree(d_scratch); }
+			if (d_scratch) { cudaStreamSynchronize(s); dev_free(d_scratch, s); }
 			scratch_cap = std::max(used, std::min<unsigned long long>(budget, scratch_cap * 2));
-			cudaError_t e = cudaMalloc(&d_scratch, scratch_cap);
+			cudaError_t e = dev_malloc((void**)&d_scratch, scratch_cap, s);
 			if (e != cudaSuccess) { st = cuda_fail(c, e, "edit-script scratch"); break; }
 		}
 		const uint32_t m = (uint32_t)(end - pos);
@@ -106,7 +106,7 @@ clb_status run_edit_scripts(clb_ctx* c, std::vector<EsTask>& h_tasks, const uint
 		if (e != cudaSuccess) { st = cuda_fail(c, e, "k_edit_scripts"); break; }
 		pos = end;
 	}
-	cudaFree(d_tasks); cudaFree(d_list); if (d_scratch) cudaFree(d_scratch);
+	dev_free(d_tasks, s); dev_free(d_list, s); if (d_scratch) dev_free(d_scratch, s);
 	return st;
 }
 
@@ -123,9 +123,9 @@ clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes
 		o += (unsigned long long)ref_len[i] + enc_len[i] + 2;
 	}
 	uint8_t* d_seqs = nullptr; char* d_out = nullptr; uint32_t* d_len = nullptr;
-	CLB_CUDA(c, cudaMalloc(&d_seqs, n_seq_bytes + 16));
-	CLB_CUDA(c, cudaMalloc(&d_out, o + 16));
-	CLB_CUDA(c, cudaMalloc(&d_len, sizeof(uint32_t) * (n + 1)));
+	CLB_CUDA(c, dev_malloc((void**)&d_seqs, n_seq_bytes + 16, c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&d_out, o + 16, c->stream));
+	CLB_CUDA(c, dev_malloc((void**)&d_len, sizeof(uint32_t) * (n + 1), c->stream));
 	CLB_CUDA(c, cudaMemcpyAsync(d_seqs, seqs, n_seq_bytes, cudaMemcpyHostToDevice, c->stream));
 	clb_status st = run_edit_scripts(c, tasks, d_seqs, d_out, d_len);
 	std::vector<uint32_t> len(n); std::vector<char> raw(o + 1);
@@ -135,7 +135,7 @@ clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes
 		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
 		if (e != cudaSuccess) st = cuda_fail(c, e, "clb_edit_scripts download");
 	}
-	cudaFree(d_seqs); cudaFree(d_out); cudaFree(d_len);
+	dev_free(d_seqs, c->stream); dev_free(d_out, c->stream); dev_free(d_len, c->stream);
 	if (st != CLB_OK) return st;
 	uint64_t w = 0;
 	for (uint64_t i = 0; i < n; ++i) {

@@ -546,15 +546,15 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (bbits > SMEM_BLOOM_WORDS * 32) { bloom_off[i] = bloom_total; bloom_total += bbits / 32; }
 	}
 	uint64_t* d_tab_off = nullptr; uint64_t* d_bloom_off = nullptr; uint32_t* g_tab = nullptr; uint32_t* g_bloom = nullptr;
-	CLB_CUDA(c, cudaMallocAsync((void**)&d_tab_off, sizeof(uint64_t) * nb, s));
-	CLB_CUDA(c, cudaMallocAsync((void**)&d_bloom_off, sizeof(uint64_t) * nb, s));
-	CLB_CUDA(c, cudaMallocAsync((void**)&g_tab, sizeof(uint32_t) * (tab_total + 1), s));
-	CLB_CUDA(c, cudaMallocAsync((void**)&g_bloom, sizeof(uint32_t) * (bloom_total + 1), s));
+	CLB_CUDA(c, dev_malloc((void**)&d_tab_off, sizeof(uint64_t) * nb, s));
+	CLB_CUDA(c, dev_malloc((void**)&d_bloom_off, sizeof(uint64_t) * nb, s));
+	CLB_CUDA(c, dev_malloc((void**)&g_tab, sizeof(uint32_t) * (tab_total + 1), s));
+	CLB_CUDA(c, dev_malloc((void**)&g_bloom, sizeof(uint32_t) * (bloom_total + 1), s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab_off, tab_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_bloom_off, bloom_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	// HiFi: anchors from the shared k-mers first; candidates that get some are skipped by the m-mer search
 	SegInfo* d_kseg = nullptr; uint8_t* d_skip = nullptr; uint8_t* d_kanc = nullptr; uint64_t kanc_slots = 0, kbase = 0;
-	struct KFree { std::vector<void*> v; cudaStream_t s; ~KFree() { for (void* q : v) cudaFreeAsync(q, s); } } kfree{{}, s};
+	struct KFree { std::vector<void*> v; cudaStream_t s; ~KFree() { for (void* q : v) dev_free_async(q, s); } } kfree{{}, s};
 	if (c->prm.is_hifi) {
 		const uint64_t nsc = (uint64_t)nb * P.c;
 		std::vector<uint32_t> votes(c->n_reads * P.c);
@@ -571,7 +571,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 			kanc_off[(size_t)i * P.c + j] = kanc_slots; kanc_slots += nco ? 2 * ((12ull * nco + PAIR_SLOT_BYTES - 1) / PAIR_SLOT_BYTES + 1) : 0;
 		}
 		uint64_t* d_ktab_off = nullptr; uint64_t* d_kanc_off = nullptr; KEntry* d_ktab = nullptr;
-		auto kalloc = [&](void** q, uint64_t bytes) { cudaError_t e = cudaMallocAsync(q, bytes ? bytes : 1, s); if (e == cudaSuccess) kfree.v.push_back(*q); return e; };
+		auto kalloc = [&](void** q, uint64_t bytes) { cudaError_t e = dev_malloc(q, bytes ? bytes : 1, s); if (e == cudaSuccess) kfree.v.push_back(*q); return e; };
 		CLB_CUDA(c, kalloc((void**)&d_kseg, sizeof(SegInfo) * nsc * 2)); CLB_CUDA(c, kalloc((void**)&d_skip, nsc));
 		CLB_CUDA(c, kalloc((void**)&d_ktab_off, sizeof(uint64_t) * nsc)); CLB_CUDA(c, kalloc((void**)&d_kanc_off, sizeof(uint64_t) * nsc));
 		CLB_CUDA(c, kalloc((void**)&d_ktab, sizeof(KEntry) * (ktab_total + 1))); CLB_CUDA(c, kalloc((void**)&d_kanc, kanc_slots * PAIR_SLOT_BYTES + 64));
@@ -607,7 +607,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (attempt == 2) { st = fail(c, CLB_ERR_CAPACITY, "pair arena did not converge"); break; }
 		cap_pairs = used + 1024;
 	}
-	cudaFreeAsync(d_tab_off, s); cudaFreeAsync(d_bloom_off, s); cudaFreeAsync(g_tab, s); cudaFreeAsync(g_bloom, s);
+	dev_free_async(d_tab_off, s); dev_free_async(d_bloom_off, s); dev_free_async(g_tab, s); dev_free_async(g_bloom, s);
 	if (st != CLB_OK) return st;
 	if (kanc_slots) {      // the k-mer anchors join the arena behind the pair region
 		kbase = (arena.cap - 64) / PAIR_SLOT_BYTES - kanc_slots - 2;

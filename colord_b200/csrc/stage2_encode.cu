@@ -577,13 +577,13 @@ __global__ void __launch_bounds__(256) k_emit_plain(EmitArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------ driver
-template <typename T> static cudaError_t dmalloc(T** p, uint64_t n) { return cudaMalloc(p, sizeof(T) * (n ? n : 1)); }
+template <typename T> static cudaError_t dmalloc(T** p, uint64_t n, cudaStream_t s = nullptr) { return dev_malloc((void**)p, sizeof(T) * (n ? n : 1), s); }
 struct Scoped {            // stream-ordered scratch of a batch / level: freed (back to the pool) on every exit path
 	cudaStream_t s;
 	std::vector<void*> v;
 	explicit Scoped(cudaStream_t st) : s(st) {}
-	template <typename T> cudaError_t get(T** p, uint64_t n) { cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (n ? n : 1), s); if (e == cudaSuccess) v.push_back(*p); return e; }
-	~Scoped() { for (void* p : v) cudaFreeAsync(p, s); }
+	template <typename T> cudaError_t get(T** p, uint64_t n) { cudaError_t e = dev_malloc((void**)p, sizeof(T) * (n ? n : 1), s); if (e == cudaSuccess) v.push_back(*p); return e; }
+	~Scoped() { for (void* p : v) dev_free_async(p, s); }
 };
 
 static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t t0, uint64_t t1, const ReadStore& R, const Node* d_nodes, const CandView* d_cviews,
@@ -703,11 +703,28 @@ static clb_status dump_candidates(clb_ctx* c, const S2P& P, const std::vector<ui
 	return CLB_OK;
 }
 
-struct Trace {            // CLB_S2_TRACE=1: wall time of every phase of a batch (synchronising; debugging aid)
-	bool on; cudaStream_t s; double t0; const char* what;
+struct Trace {            // CLB_S2_TRACE=1: wall time of every phase (synchronising); =2: host enqueue time + device time from events, no synchronisation
+	int mode; cudaStream_t s; double t0, h0; const char* what;
+	struct Rec { const char* w; double host; cudaEvent_t ev; };
+	std::vector<Rec> recs; cudaEvent_t ev0 = nullptr;
 	static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
-	Trace(cudaStream_t st) : on(std::getenv("CLB_S2_TRACE") != nullptr), s(st), t0(now()), what("start") {}
-	void mark(const char* w) { if (!on) return; cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s2] %-28s %9.3f ms\n", w, t - t0); t0 = t; }
+	Trace(cudaStream_t st) : mode(std::getenv("CLB_S2_TRACE") ? std::atoi(std::getenv("CLB_S2_TRACE")) : 0), s(st), t0(now()), h0(t0), what("start")
+	{ if (mode == 2) { cudaEventCreate(&ev0); cudaEventRecord(ev0, s); } }
+	void mark(const char* w)
+	{
+		if (!mode) return;
+		if (mode == 2) { Rec r{w, now(), nullptr}; cudaEventCreate(&r.ev); cudaEventRecord(r.ev, s); recs.push_back(r); return; }
+		cudaStreamSynchronize(s); const double t = now(); fprintf(stderr, "[s2] %-28s %9.3f ms\n", w, t - t0); t0 = t;
+	}
+	~Trace()
+	{
+		if (mode != 2 || !ev0) return;
+		cudaStreamSynchronize(s);
+		double hp = h0; cudaEvent_t ep = ev0;
+		for (auto& r : recs) { float ms = 0; cudaEventElapsedTime(&ms, ep, r.ev); fprintf(stderr, "[s2e] %-28s host %9.3f ms   device %9.3f ms\n", r.w, r.host - hp, ms); hp = r.host; if (ep != ev0) cudaEventDestroy(ep); ep = r.ev; }
+		if (ep != ev0) cudaEventDestroy(ep);
+		cudaEventDestroy(ev0);
+	}
 };
 
 // The anchors of the chosen candidates leave the per-batch pair arena for a compact store that lives until the tuples are out.
@@ -763,7 +780,14 @@ static clb_status anchor_batch(clb_ctx* c, const S2P& P, uint32_t lo, uint32_t h
 	CLB_LAUNCH_CHECK(c, "k_anchor_count");
 	uint64_t total = 0;
 	st = exclusive_scan(c, d_acnt, nb, d_aoff, &total); if (st != CLB_OK) return st;
-	CLB_CUDA(c, c->s2_store.reserve((store_used + total) * sizeof(Anchor) + 16, s, true, store_used * sizeof(Anchor)));
+	uint64_t want = store_used + total;
+	if (store_used == 0 && hi < c->n_reads) {      // first batch: size the store for the whole job at this batch's anchor density (no regrowth copies)
+		uint64_t b_batch = 0, b_rest = 0;
+		for (uint32_t r = lo; r < hi; ++r) b_batch += c->h_rd_len[r];
+		for (uint64_t r = hi; r < c->n_reads; ++r) b_rest += c->h_rd_len[r];
+		want = total + (uint64_t)(1.15 * (double)total * ((double)b_rest / (double)std::max<uint64_t>(1, b_batch))) + 4096;
+	}
+	CLB_CUDA(c, c->s2_store.reserve(want * sizeof(Anchor) + 16, s, true, store_used * sizeof(Anchor)));
 	CLB_TIMED(c, K_ANCHORS, (k_anchor_copy<<<(nb + 127) / 128, 128, 0, s>>>(nodes, cviews, nb, P.c, c->s2_arena.p, c->s2_store.p, d_aoff, store_used)));
 	CLB_LAUNCH_CHECK(c, "k_anchor_copy");
 	CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -914,12 +938,12 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	// reference id -> read
 	std::vector<uint32_t> r2r(c->n_ref ? c->n_ref : 1);
 	for (uint64_t i = 0, k = 0; i < n; ++i) if (c->h_is_ref[i]) r2r[k++] = (uint32_t)i;
-	CLB_CUDA(c, dmalloc(&c->d_ref_to_read, r2r.size()));
+	CLB_CUDA(c, dmalloc(&c->d_ref_to_read, r2r.size(), c->stream));
 	CLB_CUDA(c, cudaMemcpyAsync(c->d_ref_to_read, r2r.data(), sizeof(uint32_t) * r2r.size(), cudaMemcpyHostToDevice, s));
 	std::vector<uint32_t> h_cand_n(n ? n : 1);
 	if (n) CLB_CUDA(c, cudaMemcpyAsync(h_cand_n.data(), c->cand_n, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	CLB_CUDA(c, dmalloc(&c->es_off, n + 1));
+	CLB_CUDA(c, dmalloc(&c->es_off, n + 1, c->stream));
 	if (nc) CLB_CUDA(c, cudaMemsetAsync(c->es_off, 0, sizeof(uint64_t) * nc, s));
 	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
 	c->es_total = 0;
@@ -956,8 +980,8 @@ void s2_free(clb_ctx* c)
 	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
 	c->s2_fork = nullptr;
 	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
-	if (c->es_off) cudaFree(c->es_off);
-	if (c->d_ref_to_read) cudaFree(c->d_ref_to_read);
+	if (c->es_off) dev_free(c->es_off, c->stream);
+	if (c->d_ref_to_read) dev_free(c->d_ref_to_read, c->stream);
 	c->es_off = nullptr; c->d_ref_to_read = nullptr;
 }
 

@@ -105,8 +105,8 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
-	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
-	auto dalloc = [&](void** p, uint64_t bytes, Tmp& t) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s); if (e == cudaSuccess) t.v.push_back(*p); return e; };
+	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) dev_free_async(p, s); } } tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t bytes, Tmp& t) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) t.v.push_back(*p); return e; };
 	const uint64_t n_entries = M.base[F_COUNT];
 	uint32_t* d_hist = nullptr; uint32_t* d_pack_first = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_hist, sizeof(uint32_t) * n_entries, tmp));

@@ -95,8 +95,8 @@ clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offse
 		if (n) pack_first.push_back(n);
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
-	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
-	auto dalloc = [&](void** p, uint64_t nbytes) { cudaError_t e = cudaMallocAsync(p, nbytes ? nbytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
+	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) dev_free_async(p, s); } } tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t nbytes) { cudaError_t e = dev_malloc(p, nbytes ? nbytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
 	HArgs a{};
 	a.M = make_hdr_model(); a.n = n; a.n_packs = np;
 	if (on_device) a.H = HdrInput{bytes, offsets, plus_id};

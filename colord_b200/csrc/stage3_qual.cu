@@ -256,8 +256,8 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[nc + i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
 	const uint64_t tot = h_off[n] - h_off[0];
-	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) cudaFreeAsync(p, s); } } tmp{{}, s};
-	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
+	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) dev_free_async(p, s); } } tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
 	const uint8_t* d_q = nullptr; uint64_t* d_qoff = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_qoff, sizeof(uint64_t) * (n + 1)));
 	{
@@ -330,6 +330,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	CLB_CUDA(c, cudaMemcpyAsync(c->qs.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
 	uint64_t out_at = hdr.size();
 	const uint64_t chunk_syms = 1ull << 31;
+	uint16_t* d_tmp = nullptr; uint64_t tmp_cap = 0;      // one temp for all chunks (grown if a later chunk is larger)
 	for (uint32_t p0 = 0; p0 < np;) {
 		uint32_t p1 = p0; uint64_t syms = 0;
 		while (p1 < np && (p1 == p0 || syms + (h_off[pack_first[p1 + 1]] - h_off[pack_first[p1]]) <= chunk_syms)) { syms += h_off[pack_first[p1 + 1]] - h_off[pack_first[p1]] + 2ull * nb * (pack_first[p1 + 1] - pack_first[p1]); ++p1; }
@@ -338,10 +339,10 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		for (uint32_t p = p0; p < p1; ++p)
 			for (uint32_t r = pack_first[p]; r < pack_first[p + 1]; ++r) lane_off[(size_t)(p - p0) * QB_LANES + (r - pack_first[p]) % QB_LANES + 1] += c->h_rd_len[nc + r] + 2ull * nb;
 		for (uint32_t i = 0; i < nl; ++i) lane_off[i + 1] += lane_off[i];
-		uint64_t* d_lane_off = nullptr; uint16_t* d_tmp = nullptr; uint32_t* d_words = nullptr; uint32_t* d_state = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
+		uint64_t* d_lane_off = nullptr; uint32_t* d_words = nullptr; uint32_t* d_state = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
 		Tmp ct{{}, s};
-		auto calloc_ = [&](void** q, uint64_t bytes) { cudaError_t e = cudaMallocAsync(q, bytes ? bytes : 1, s); if (e == cudaSuccess) ct.v.push_back(*q); return e; };
-		CLB_CUDA(c, calloc_((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1))); CLB_CUDA(c, calloc_((void**)&d_tmp, sizeof(uint16_t) * (lane_off[nl] + 8)));
+		auto calloc_ = [&](void** q, uint64_t bytes) { cudaError_t e = dev_malloc(q, bytes ? bytes : 1, s); if (e == cudaSuccess) ct.v.push_back(*q); return e; };
+		CLB_CUDA(c, calloc_((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1))); if (lane_off[nl] + 8 > tmp_cap) { tmp_cap = lane_off[nl] + 8; CLB_CUDA(c, dalloc((void**)&d_tmp, sizeof(uint16_t) * tmp_cap)); }
 		CLB_CUDA(c, calloc_((void**)&d_words, sizeof(uint32_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_state, sizeof(uint32_t) * nl));
 		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
 		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));

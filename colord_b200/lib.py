@@ -18,7 +18,7 @@ EXPORTS = [
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
     "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
-    "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export", "clb_qual_encode_original",
+    "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export", "clb_qual_encode_original", "clb_release_cached_memory",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 
@@ -86,6 +86,7 @@ def load():
     L.clb_graph_common.argtypes = [vp, vp, vp, vp, u64]
     L.clb_get_packed_read.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
     L.clb_sampler.argtypes = [u32, C.c_double, u32, u32, vp]; L.clb_sampler.restype = None
+    L.clb_release_cached_memory.argtypes = [i32]
     L.clb_kernel_launches.argtypes = [vp]; L.clb_kernel_launches.restype = u64
     L.clb_edit_scripts.argtypes = [vp, vp, u64, vp, vp, vp, vp, vp, u64, vp, vp, u64]
     L.clb_encode.argtypes = [vp, C.POINTER(EncodeParams), vp, u32]
@@ -119,6 +120,11 @@ def load():
 
 def _np_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def release_cached_memory(device=0):
+    """Hand the device memory cached by finished jobs back to the system (clb_release_cached_memory)."""
+    return load().clb_release_cached_memory(device)
 
 
 def sampler(rng_range, exponent, n_pseudo, n):

@@ -57,6 +57,10 @@ typedef struct {
 clb_status clb_create(const clb_params* params, clb_ctx** out);
 void       clb_destroy(clb_ctx* ctx);
 const char* clb_last_error(const clb_ctx* ctx);          /* ctx may be NULL: error of the failed create  */
+/* Device memory is taken from the device's default stream-ordered memory pool and returned to it; what a finished job (or a
+ * destroyed context) returned stays cached in the pool for the next one, so that a process compressing file after file does
+ * not pay the driver for mapping and unmapping tens of GB per file.  This call hands the cached memory back to the system. */
+clb_status clb_release_cached_memory(int device);
 /* Run all of this context's work on an existing CUDA stream (cudaStream_t as void*); default: own stream. */
 clb_status clb_set_stream(clb_ctx* ctx, void* cuda_stream);
 clb_status clb_synchronize(clb_ctx* ctx);
