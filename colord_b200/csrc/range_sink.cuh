@@ -24,8 +24,9 @@ struct RangeSinkT {
 	const uint32_t* tab; const Model* M;
 	uint8_t* out; uint64_t n;
 	unsigned long long low, range;
+	uint64_t cap = ~0ull;                                                    // bytes that may be stored at `out`; n keeps counting beyond it
 	CLB_D void start() { low = 0; range = 0xff00000000000000ULL; n = 0; }
-	CLB_D void byte(uint8_t b) { if (out) out[n] = b; ++n; }              // out == nullptr: sizing pass
+	CLB_D void byte(uint8_t b) { if (out && n < cap) out[n] = b; ++n; }     // out == nullptr: sizing pass
 	CLB_D void put(uint32_t f, uint64_t ctx, uint32_t sym)
 	{
 		const uint32_t e = tab[st_entry(*M, f, ctx, sym)];

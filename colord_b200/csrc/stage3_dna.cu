@@ -51,18 +51,48 @@ __global__ void __launch_bounds__(128) k_d_count(DArgs a)
 	dna_walk(a.M, a.R, r, lane_flag_ctx(a.R, r, a.pack_first[lo]), s);
 }
 
-struct DEnc { uint32_t* lane_bytes; const uint64_t* dst_off; const uint64_t* pack_hdr_off; uint8_t* out; };
+struct DEnc { uint32_t* lane_bytes; const uint64_t* dst_off; const uint64_t* pack_hdr_off; uint8_t* out; const uint32_t* lane_cap; uint32_t* overflow; };
 
-// pass 2: one thread per (pack, lane).  WRITE = false sizes the lane streams (the coder's output length does not depend on
-// where it is stored), WRITE = true writes them — and the pack headers — at their final place in the container.
-template <bool WRITE>
-__global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
+// slot of a lane in the temp: the tuple bytes of its reads + 64 (a coded read is a fraction of its tuples; a lane that would not
+// fit raises `overflow` and the container is written by the two-walk path instead)
+__global__ void __launch_bounds__(64) k_d_lane_cap(DArgs a, uint32_t* __restrict__ cap)
 {
 	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
 	if (li >= a.n_packs * DB_LANES) return;
 	const uint32_t p = li / DB_LANES, l = li % DB_LANES;
+	uint64_t b = 64;
+	for (uint32_t r = a.pack_first[p] + l; r < a.pack_first[p + 1]; r += DB_LANES) b += a.R.es_off[a.R.first + r + 1] - a.R.es_off[a.R.first + r];
+	cap[li] = (uint32_t)min(b, (uint64_t)0xFFFFFFF0u);
+}
+// lane slots -> their final place in the container, pack headers; one warp per lane
+__global__ void __launch_bounds__(128) k_d_compact(DArgs a, DEnc e, const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ slot_off)
+{
+	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, t = threadIdx.x & 31;
+	if (li >= a.n_packs * DB_LANES) return;
+	const uint32_t nb = e.lane_bytes[li];
+	const uint8_t* src = tmp + slot_off[li]; uint8_t* dst = e.out + e.dst_off[li];
+	for (uint32_t k = t; k < nb; k += 32) dst[k] = src[k];
+	if (t == 0) {
+		const uint32_t p = li / DB_LANES, l = li % DB_LANES;
+		uint8_t* h = e.out + e.pack_hdr_off[p];
+		h[4 + 4 * l] = (uint8_t)nb; h[5 + 4 * l] = (uint8_t)(nb >> 8); h[6 + 4 * l] = (uint8_t)(nb >> 16); h[7 + 4 * l] = (uint8_t)(nb >> 24);
+		if (l == 0) { const uint32_t np = a.pack_first[p + 1] - a.pack_first[p]; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
+	}
+}
+
+// pass 2: one thread per (pack, lane).  MODE 0 sizes the lane streams (the coder's output length does not depend on where it
+// is stored), MODE 1 writes them — and the pack headers — at their final place in the container, MODE 2 writes them into the
+// lane's temp slot and reports the size (one walk instead of two; k_d_compact moves them).
+template <int MODE>
+__global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
+{
+	constexpr bool WRITE = MODE == 1;
+	const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+	if (li >= a.n_packs * DB_LANES) return;
+	const uint32_t p = li / DB_LANES, l = li % DB_LANES;
 	const uint32_t r0 = a.pack_first[p], r1 = a.pack_first[p + 1];
-	RangeSink s{a.tab, &a.M, WRITE ? e.out + e.dst_off[li] : nullptr, 0, 0, 0};
+	RangeSink s{a.tab, &a.M, MODE == 0 ? nullptr : e.out + e.dst_off[li], 0, 0, 0};
+	if (MODE == 2) s.cap = e.lane_cap[li];
 	s.start();
 	uint32_t fctx = 0;
 	for (uint32_t r = r0 + l; r < r1; r += DB_LANES) {
@@ -70,6 +100,7 @@ __global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
 		fctx = ((fctx << 2) + read_flag_of(a.R, r)) & 0xff;
 	}
 	s.end();
+	if (MODE == 2 && s.n > s.cap) atomicExch(e.overflow, 1u);
 	if (!WRITE) { e.lane_bytes[li] = (uint32_t)s.n; return; }
 	uint8_t* h = e.out + e.pack_hdr_off[p];
 	const uint32_t nb = (uint32_t)s.n;
@@ -143,16 +174,36 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab, tab.data(), sizeof(uint32_t) * n_entries, cudaMemcpyHostToDevice, s));
 	a.tab = d_tab;
 	tr.mark("tables (host)");
-	// ---- pass 2: size every lane stream, lay the container out, write ----
+	// ---- pass 2: code every lane into a temp slot (one walk), lay the container out, compact; if the temp cannot be had or a
+	// lane outgrows its slot: size every lane stream (walk), lay out, write (second walk) ----
 	const uint32_t nl = np * DB_LANES;
-	uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
+	uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr; uint32_t* d_cap = nullptr; uint64_t* d_slot = nullptr; uint32_t* d_ovf = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl, tmp)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl, tmp)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * np, tmp));
-	DEnc e{d_bytes, d_dst, d_phdr, nullptr};
-	if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<size>"); }
+	CLB_CUDA(c, dalloc((void**)&d_cap, sizeof(uint32_t) * (nl + 1), tmp)); CLB_CUDA(c, dalloc((void**)&d_slot, sizeof(uint64_t) * (nl + 1), tmp));
+	d_ovf = d_cap + nl;
+	DEnc e{d_bytes, d_dst, d_phdr, nullptr, d_cap, d_ovf};
+	uint8_t* d_tmp = nullptr; bool one_walk = false;
+	if (nl && !std::getenv("CLB_DNA_TWO_WALKS")) {
+		CLB_CUDA(c, cudaMemsetAsync(d_ovf, 0, sizeof(uint32_t), s));
+		CLB_TIMED(c, K_DNA, (k_d_lane_cap<<<(nl + 63) / 64, 64, 0, s>>>(a, d_cap))); CLB_LAUNCH_CHECK(c, "k_d_lane_cap");
+		uint64_t tmp_bytes = 0;
+		clb_status st = exclusive_scan(c, d_cap, nl, d_slot, &tmp_bytes); if (st != CLB_OK) return st;
+		size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+		if (tmp_bytes + (8ull << 30) < free_b && cudaMalloc((void**)&d_tmp, tmp_bytes + 16) == cudaSuccess) {
+			e.out = d_tmp; e.dst_off = d_slot;
+			CLB_TIMED(c, K_DNA, (k_d_encode<2><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<temp>");
+			uint32_t ovf = 0;
+			CLB_CUDA(c, cudaMemcpyAsync(&ovf, d_ovf, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+			CLB_CUDA(c, cudaStreamSynchronize(s));
+			one_walk = ovf == 0;
+			e.dst_off = d_dst;
+		} else cudaGetLastError();
+	}
+	if (nl && !one_walk) { CLB_TIMED(c, K_DNA, (k_d_encode<0><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<size>"); }
 	std::vector<uint32_t> bytes(nl);
 	CLB_CUDA(c, cudaMemcpyAsync(bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	tr.mark("k_d_encode<size>");
+	tr.mark(one_walk ? "k_d_encode<temp>" : "k_d_encode<size>");
 	uint64_t out_at = hdr.size();
 	std::vector<uint64_t> dst(nl), phdr(np);
 	for (uint32_t p = 0; p < np; ++p) {
@@ -164,9 +215,11 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s));
 	e.out = c->ds.p;
-	if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<write>"); }
+	if (nl && one_walk) { CLB_TIMED(c, K_DNA, (k_d_compact<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e, d_tmp, d_slot))); CLB_LAUNCH_CHECK(c, "k_d_compact"); }
+	else if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<1><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<write>"); }
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	tr.mark("k_d_encode<write>");
+	if (d_tmp) cudaFree(d_tmp);
+	tr.mark(one_walk ? "k_d_compact" : "k_d_encode<write>");
 	c->ds_total = out_at;
 	c->ds_header = hdr.size();
 	c->dna_done = true;

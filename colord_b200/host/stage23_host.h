@@ -50,6 +50,11 @@ public:
 	{
 		check(ctx, clb_qual_encode(ctx, &prm, quals.data(), offsets.data(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode");
 	}
+	// QualityComprMode::Original (-q org): data_source 0 ONT, 1 PBRaw, 2 PBHiFi (selects the quantiser of the context, quality_coder.cpp:272-505)
+	void CompressOriginal(uint32_t data_source, const std::vector<uint8_t>& quals, const std::vector<uint64_t>& offsets, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_qual_encode_original(ctx, data_source, prm.level, quals.data(), offsets.data(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode_original");
+	}
 	std::vector<uint8_t> GetStream() const
 	{
 		uint64_t tot = 0; check(ctx, clb_qual_size(ctx, &tot), "clb_qual_size");
