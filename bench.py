@@ -252,6 +252,8 @@ def main():
     ap.add_argument("--stages", default="12qdh", choices=["1", "12", "12q", "12qd", "12qdh"], help="hot-path stages inside a step (both arms); q / d / h = quality / DNA-tuple / header stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--side-streams", action="store_true", help="code the quality / header streams in a second host thread beside stage 2 instead of after it "
+                    "(measured on B200, 25 Gbases: 12.5-13.3 s per step against 11.8-12.0 s serial - the issue-bound quality kernels slow the latency-bound alignment down)")
     args = ap.parse_args()
     if args.impl == "reference":
         return main_reference(args)
@@ -355,6 +357,28 @@ def main():
             with torch.cuda.stream(stream):
                 exchange_reference_reads(ctx, device, sampled, lens_host)
                 stream.synchronize()
+        # the quality and header streams do not depend on stage 2 (level 1): with --side-streams a second host thread codes them on
+        # the context's stage-3 stream while the main thread runs the graph, stage 2 and the DNA stream (the reference gives these
+        # coders their own threads as well, compression.cpp:654-689); default: after stage 2, which measured faster
+        def side_streams():
+            if args.stages == "12qdh":
+                if host_hdr is None:
+                    ctx.hdr_encode(bytes_=hdr_dev.data_ptr(), offsets=hdr_off_dev.data_ptr(), n=n_local, on_device=True)
+                else:
+                    ctx.hdr_encode(bytes_=host_hdr[0], offsets=host_hdr[1])
+            if host_quals is None:
+                ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
+            else:
+                ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
+        side, side_err = None, []
+        if args.stages in ("12q", "12qd", "12qdh") and args.side_streams:
+            def side_main():
+                try:
+                    side_streams()
+                except Exception as ex:      # re-raised on the main thread
+                    side_err.append(ex)
+            side = threading.Thread(target=side_main)
+            side.start()
         ctx.graph_build(sampled)
         phase("graph")
         out = None
@@ -365,16 +389,12 @@ def main():
             if args.stages in ("12qd", "12qdh"):
                 ctx.dna_encode(1)
             phase("dna")
-            if args.stages == "12qdh":
-                if host_hdr is None:
-                    ctx.hdr_encode(bytes_=hdr_dev.data_ptr(), offsets=hdr_off_dev.data_ptr(), n=n_local, on_device=True)
-                else:
-                    ctx.hdr_encode(bytes_=host_hdr[0], offsets=host_hdr[1])
-            if args.stages in ("12q", "12qd", "12qdh"):
-                if host_quals is None:
-                    ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
-                else:
-                    ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
+            if side is not None:
+                side.join()
+                if side_err:
+                    raise side_err[0]
+            elif args.stages in ("12q", "12qd", "12qdh"):
+                side_streams()
             phase("hdr+qual")
             if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
                 if args.stages == "12qdh":
@@ -435,6 +455,10 @@ def main():
             host_quals.copy_(quals)
             hq = host_quals.numpy()
         hh = None if hdr_host is None else (hdr_host.numpy(), hdr_off_host)
+        # the device-resident copies of the inputs are not part of the end-to-end path: give their memory back first
+        del bases, quals, hdr_dev
+        bases = quals = hdr_dev = None
+        torch.cuda.empty_cache()
         e_ms, _, _, (_, out) = timed(1, max(1, min(args.steps, 2)), host_bases=hb, host_offsets=host_off, host_quals=hq, host_hdr=hh, readback=True)
         d2h = int(sum(x.nbytes for x in out))
         sizes_all = torch.tensor([int(x.nbytes) for x in out], dtype=torch.int64, device=device)

@@ -38,6 +38,7 @@ clb_status clb_create(const clb_params* p, clb_ctx** out)
 	c->mt = make_modtest(p->modulo);
 	e = cudaSetDevice(p->device);
 	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking);
 	if (e == cudaSuccess) { c->own_stream = true; e = cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, p->device); }
 	if (e != cudaSuccess) { clb_status st = cuda_fail(nullptr, e, "clb_create"); delete c; return st; }
 	{	// stream-ordered scratch (cudaMallocAsync) is recycled inside the pool instead of going back to the driver after every sync
@@ -58,6 +59,7 @@ void clb_destroy(clb_ctx* c)
 	s1_free(c);
 	s2_free(c);
 	c->qs.release(); c->ds.release(); c->hs.release();
+	if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -80,7 +82,11 @@ clb_status clb_synchronize(clb_ctx* c)
 	return CLB_OK;
 }
 
-#define CLB_ENTER(c) do { if (!(c)) return CLB_ERR_BAD_ARG; cudaSetDevice((c)->prm.device); } while (0)
+// a host thread that enters the library for the first time binds the device's primary context (cudaSetDevice + the cudaFree(0)
+// idiom): the stage-3 quality / header calls may come from a thread of their own
+static thread_local int g_bound_device = -1;
+static inline void bind_device(int dev) { cudaSetDevice(dev); if (g_bound_device != dev) { cudaFree(0); g_bound_device = dev; } }
+#define CLB_ENTER(c) do { if (!(c)) return CLB_ERR_BAD_ARG; bind_device((c)->prm.device); } while (0)
 
 clb_status clb_append_reads(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device)
 {
@@ -368,7 +374,7 @@ clb_status clb_release_cached_memory(int device)
 	return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? CLB_OK : CLB_ERR_CUDA;
 }
 
-uint64_t clb_kernel_launches(const clb_ctx* c) { return c ? c->launches : 0; }
+uint64_t clb_kernel_launches(const clb_ctx* c) { return c ? c->launches.load() : 0; }
 
 clb_status clb_profile_enable(clb_ctx* c, int on)
 {

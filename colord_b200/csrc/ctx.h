@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#include <atomic>
 #include <mutex>
 #include <unordered_set>
 #include <cuda_runtime.h>
@@ -74,13 +75,18 @@ struct clb_ctx {
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	std::string err;
-	uint64_t launches = 0;
+	std::atomic<uint64_t> launches{0};
 	int n_sm = 148;
 	// per-kernel device timing (off by default)
 	bool prof_on = false;
 	std::vector<clb::ProfRec> prof_open;
 	double prof_ms[clb::K_N] = {0};
 	uint64_t prof_n[clb::K_N] = {0};
+	// The quality and header streams of stage 3 do not depend on stage 2 (quality: at level 1) and have their own stream and
+	// profiling list, so that a second host thread can code them while stage 2 runs — the reference runs its quality and header
+	// coders in threads of their own, too (compression.cpp:654-689).
+	cudaStream_t stream3 = nullptr;
+	std::vector<clb::ProfRec> prof_open3;
 	cudaStream_t copy_stream = nullptr;      // H2D staging of host input overlaps the kernels
 	cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
 
@@ -188,6 +194,9 @@ void prof_begin(clb_ctx* c, int kid);
 void prof_end(clb_ctx* c);
 void prof_resolve(clb_ctx* c);
 #define CLB_TIMED(ctx, kid, ...) do { clb::prof_begin(ctx, kid); __VA_ARGS__; clb::prof_end(ctx); } while (0)
+void prof_begin3(clb_ctx* c, int kid);      // the same on stream3 (kernel classes k_qual, k_hdr)
+void prof_end3(clb_ctx* c);
+#define CLB_TIMED3(ctx, kid, ...) do { clb::prof_begin3(ctx, kid); __VA_ARGS__; clb::prof_end3(ctx); } while (0)
 
 // stage entry points implemented in the .cu files
 clb_status s1a_init(clb_ctx* c);

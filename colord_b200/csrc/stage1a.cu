@@ -361,6 +361,7 @@ static inline uint32_t grid_for(uint64_t n_items, uint32_t threads, int n_sm, ui
 	return (uint32_t)g;
 }
 
+static void prof_resolve_list(clb_ctx* c, std::vector<ProfRec>& open, cudaStream_t st);
 void prof_begin(clb_ctx* c, int kid)
 {
 	if (!c->prof_on) return;
@@ -373,18 +374,33 @@ void prof_end(clb_ctx* c)
 {
 	if (!c->prof_on || c->prof_open.empty()) return;
 	cudaEventRecord(c->prof_open.back().b, c->stream);
-	if (c->prof_open.size() > 4096) prof_resolve(c);
+	if (c->prof_open.size() > 4096) prof_resolve_list(c, c->prof_open, c->stream);
 }
-void prof_resolve(clb_ctx* c)
+static void prof_resolve_list(clb_ctx* c, std::vector<ProfRec>& open, cudaStream_t st)
 {
-	if (c->prof_open.empty()) return;
-	cudaStreamSynchronize(c->stream);
-	for (auto& r : c->prof_open) {
+	if (open.empty()) return;
+	cudaStreamSynchronize(st);
+	for (auto& r : open) {
 		float ms = 0;
 		if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { c->prof_ms[r.kid] += ms; c->prof_n[r.kid] += 1; }
 		cudaEventDestroy(r.a); cudaEventDestroy(r.b);
 	}
-	c->prof_open.clear();
+	open.clear();
+}
+void prof_resolve(clb_ctx* c) { prof_resolve_list(c, c->prof_open, c->stream); prof_resolve_list(c, c->prof_open3, c->stream3); }
+void prof_begin3(clb_ctx* c, int kid)
+{
+	if (!c->prof_on) return;
+	ProfRec r; r.kid = kid;
+	cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+	cudaEventRecord(r.a, c->stream3);
+	c->prof_open3.push_back(r);
+}
+void prof_end3(clb_ctx* c)
+{
+	if (!c->prof_on || c->prof_open3.empty()) return;
+	cudaEventRecord(c->prof_open3.back().b, c->stream3);
+	if (c->prof_open3.size() > 4096) prof_resolve_list(c, c->prof_open3, c->stream3);
 }
 
 static clb_status read_scalars(clb_ctx* c, unsigned long long* out)

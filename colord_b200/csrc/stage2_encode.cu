@@ -945,7 +945,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	CLB_CUDA(c, dmalloc(&c->es_off, n + 1, c->stream));
 	if (nc) CLB_CUDA(c, cudaMemsetAsync(c->es_off, 0, sizeof(uint64_t) * nc, s));
-	CLB_CUDA(c, c->es.reserve(c->n_bases + c->n_bases / 4 + 8 * n + 1024, s, false));
+	// (the tuple buffer is allocated when its exact size is known, after the sizing pass of k_emit)
 	c->es_total = 0;
 	if (c->keep_candidates) c->dbg_cand.assign(n, std::vector<uint32_t>());
 	// anchors batch by batch (the pair arena is the big transient), everything after them over all reads at once

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(64) k_h_encode(HArgs a, HEnc e)
 clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs)
 {
-	cudaStream_t s = c->stream;
+	cudaStream_t s = c->stream3;
 	if (c->hdr_done) return fail(c, CLB_ERR_STATE, "clb_hdr_encode called twice");
 	std::vector<uint64_t> pack_first{0};
 	if (pack_sizes) {
@@ -121,8 +121,8 @@ clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offse
 	a.pack_first = d_pack_first; a.hist = d_hist; a.bad = d_bad;
 	const uint32_t nblk = (uint32_t)((n + 127) / 128);
 	if (n) {
-		CLB_TIMED(c, K_HDR, (k_h_flags<<<nblk, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_h_flags");
-		CLB_TIMED(c, K_HDR, (k_h_count<<<nblk, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_h_count");
+		CLB_TIMED3(c, K_HDR, (k_h_flags<<<nblk, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_h_flags");
+		CLB_TIMED3(c, K_HDR, (k_h_count<<<nblk, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_h_count");
 	}
 	// ---- counts -> static tables + container header (host, metadata-sized) ----
 	std::vector<uint32_t> hist(n_entries + 1);
@@ -142,7 +142,7 @@ clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offse
 	uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * np));
 	HEnc e{d_bytes, d_dst, d_phdr, nullptr};
-	if (nl) { CLB_TIMED(c, K_HDR, (k_h_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_h_encode<size>"); }
+	if (nl) { CLB_TIMED3(c, K_HDR, (k_h_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_h_encode<size>"); }
 	std::vector<uint32_t> lane_bytes(nl);
 	CLB_CUDA(c, cudaMemcpyAsync(lane_bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -157,7 +157,7 @@ clb_status s3_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offse
 	CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s));
 	e.out = c->hs.p;
-	if (nl) { CLB_TIMED(c, K_HDR, (k_h_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_h_encode<write>"); }
+	if (nl) { CLB_TIMED3(c, K_HDR, (k_h_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_h_encode<write>"); }
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	c->hs_total = out_at;
 	c->hs_header = hdr.size();

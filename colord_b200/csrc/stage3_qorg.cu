@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(64) k_qo_encode(QoArgs a, QoEnc e)
 clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs)
 {
-	cudaStream_t s = c->stream;
+	cudaStream_t s = c->stream3;
 	const uint64_t nc = c->n_context, n = c->n_reads - nc;      // context reads carry no qualities
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_qual_encode_original before the reads are complete (clb_count_finalize)");
 	if (source > 2 || level < 1 || level > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_qual_encode_original: source 0..2, level 1..3");
@@ -119,7 +119,7 @@ clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, 
 	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * (n_entries + 1), s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice, s));
 	a.hist = d_hist; a.bad = d_hist + n_entries; a.pack_first = d_pack_first;
-	if (n) { CLB_TIMED(c, K_QUAL, (k_qo_count<<<(uint32_t)n, 256, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_qo_count"); }
+	if (n) { CLB_TIMED3(c, K_QUAL, (k_qo_count<<<(uint32_t)n, 256, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_qo_count"); }
 	std::vector<uint32_t> hist(n_entries + 1);
 	CLB_CUDA(c, cudaMemcpyAsync(hist.data(), d_hist, sizeof(uint32_t) * (n_entries + 1), cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -136,7 +136,7 @@ clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, 
 	uint32_t* d_bytes = nullptr; uint64_t* d_dst = nullptr; uint64_t* d_phdr = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_bytes, sizeof(uint32_t) * nl)); CLB_CUDA(c, dalloc((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, dalloc((void**)&d_phdr, sizeof(uint64_t) * np));
 	QoEnc e{d_bytes, d_dst, d_phdr, nullptr};
-	if (nl) { CLB_TIMED(c, K_QUAL, (k_qo_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_qo_encode<size>"); }
+	if (nl) { CLB_TIMED3(c, K_QUAL, (k_qo_encode<false><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_qo_encode<size>"); }
 	std::vector<uint32_t> lane_bytes(nl);
 	CLB_CUDA(c, cudaMemcpyAsync(lane_bytes.data(), d_bytes, sizeof(uint32_t) * nl, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
@@ -151,7 +151,7 @@ clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, 
 	CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * np, cudaMemcpyHostToDevice, s));
 	e.out = c->qs.p;
-	if (nl) { CLB_TIMED(c, K_QUAL, (k_qo_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_qo_encode<write>"); }
+	if (nl) { CLB_TIMED3(c, K_QUAL, (k_qo_encode<true><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_qo_encode<write>"); }
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	c->qs_total = out_at;
 	c->qual_done = true;

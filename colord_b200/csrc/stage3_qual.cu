@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) k_q_flags(const uint8_t* __restrict__ es,
 clb_status s3_qual_flags(clb_ctx* c, const uint64_t* d_qoff, uint32_t n, uint8_t* d_flags)
 {
 	const uint64_t nc = c->n_context;
-	if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(n + 127) / 128, 128, 0, c->stream>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
+	if (n) { CLB_TIMED3(c, K_QUAL, (k_q_flags<<<(n + 127) / 128, 128, 0, c->stream3>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
 	return CLB_OK;
 }
 
@@ -230,7 +230,7 @@ template <typename T> static void put(std::vector<uint8_t>& o, const T& v) { con
 clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs)
 {
-	cudaStream_t s = c->stream;
+	cudaStream_t s = c->stream3;
 	QTrace tr(s);
 	const uint64_t nc = c->n_context, n = c->n_reads - nc;      // context reads carry no qualities: the stream covers the reads after them
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_qual_encode before the reads are complete (clb_count_finalize)");
@@ -275,7 +275,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	if (P.level > 1) {
 		CLB_CUDA(c, dalloc((void**)&d_flags, tot + 16));
 		CLB_CUDA(c, cudaMemsetAsync(d_flags, 0, tot + 16, s));
-		if (n) { CLB_TIMED(c, K_QUAL, (k_q_flags<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, (uint32_t)n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
+		if (n) { CLB_TIMED3(c, K_QUAL, (k_q_flags<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(c->es.p, c->es_off + nc, d_qoff, c->rd_len.p + nc, (uint32_t)n, d_flags))); CLB_LAUNCH_CHECK(c, "k_q_flags"); }
 	}
 	QArgs a{};
 	a.pk = c->pk.p; a.rd_start = c->rd_start.p + nc; a.rd_len = c->rd_len.p + nc; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.n_reads = (uint32_t)n; a.P = P;
@@ -286,7 +286,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	CLB_CUDA(c, cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * n_ctx * P.nb, s)); CLB_CUDA(c, cudaMemsetAsync(d_mhist, 0, sizeof(uint32_t) * 5 * 128, s));
 	a.avg16 = d_avg; a.hist = d_hist; a.mhist = d_mhist;
 	tr.mark("setup");
-	if (n) { CLB_TIMED(c, K_QUAL, (k_q_count<<<(uint32_t)n, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_q_count"); }
+	if (n) { CLB_TIMED3(c, K_QUAL, (k_q_count<<<(uint32_t)n, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_q_count"); }
 	tr.mark("k_q_count");
 	// ---- count table -> frequency tables + the container's header (metadata-sized, on the host) ----
 	std::vector<uint32_t> hist(n_ctx * P.nb), mh(5 * 128);
@@ -350,7 +350,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
 		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
 		QEnc e{d_pack_first, p0, cp, d_lane_off, d_tmp, d_words, d_state};
-		CLB_TIMED(c, K_QUAL, (k_q_encode<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e)));
+		CLB_TIMED3(c, K_QUAL, (k_q_encode<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e)));
 		CLB_LAUNCH_CHECK(c, "k_q_encode");
 		tr.mark("k_q_encode");
 		std::vector<uint32_t> words(nl);
@@ -364,7 +364,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		CLB_CUDA(c, c->qs.reserve(out_at + 16, s, true, phdr[0]));
 		CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));
 		CLB_CUDA(c, cudaMemcpyAsync(d_phdr, phdr.data(), sizeof(uint64_t) * cp, cudaMemcpyHostToDevice, s));
-		CLB_TIMED(c, K_QUAL, (k_q_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(e, d_dst, d_phdr, c->qs.p)));
+		CLB_TIMED3(c, K_QUAL, (k_q_gather<<<(nl * 32 + 127) / 128, 128, 0, s>>>(e, d_dst, d_phdr, c->qs.p)));
 		CLB_LAUNCH_CHECK(c, "k_q_gather");
 		CLB_CUDA(c, cudaStreamSynchronize(s));
 		tr.mark("k_q_gather");

@@ -49,8 +49,7 @@ inline void st_put_freqs(std::vector<uint8_t>& o, const uint16_t* f, uint32_t A)
 
 inline const uint32_t* st_bits_q8()      // [f] = round(-log2(f / 4096) * 256), f = 1 .. 4096
 {
-	static std::vector<uint32_t> t;
-	if (t.empty()) { t.assign(ST_M + 1, 0); for (uint32_t f = 1; f <= ST_M; ++f) t[f] = (uint32_t)std::lround(-std::log2(f / 4096.0) * 256.0); }
+	static const std::vector<uint32_t> t = [] { std::vector<uint32_t> v(ST_M + 1, 0); for (uint32_t f = 1; f <= ST_M; ++f) v[f] = (uint32_t)std::lround(-std::log2(f / 4096.0) * 256.0); return v; }();
 	return t.data();
 }
 inline uint64_t st_freqs_bytes(const uint16_t* f, uint32_t A)
