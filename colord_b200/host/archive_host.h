@@ -26,6 +26,9 @@
 
 namespace clbhost {
 
+// `info` version of archives whose streams are the device's native containers (compressor.h); the reference's own archives are 1.x
+constexpr uint32_t B200_VERSION_MAJOR = 201, B200_VERSION_MINOR = 1, B200_VERSION_PATCH = 0;
+
 class CArchive {
 public:
 	struct Part { uint64_t offset, size; };

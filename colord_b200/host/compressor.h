@@ -1,0 +1,138 @@
+// compressor.h — runCompression over the C-ABI: input file -> archive (SURVEY.md §8b "outermost contract", §8f rows 1 and 3).
+// Follows src/colord/compression.cpp:344-810 step by step — open the archive and register `meta`, read the input, stage 1a
+// (k-mer counts -> filter), derived values (mean read length :443, sparse range :501-504, accepted reference reads :539),
+// stage 1b, stage 2, the three stage-3 streams, then the `meta` record (:705-779) and `info` (:781-783) — with every compute
+// stage a call into libcolord_b200.so (include/colord_b200.h) instead of a thread over queues.
+//
+// The stage-3 streams are the device's native containers (DB01 / QB01 / QO01 / HB01), not the reference's
+// adaptive range-coder streams, so they are stored under their own names — "dna-b200", "qual-b200", "header-b200", one part
+// each — and the archive's `info` carries B200_VERSION_MAJOR as its major version: the reference refuses such an archive at
+// its version check (decompression_common.cpp:36-43) instead of misreading it.  Container, `meta` and `info` are the
+// reference's formats (archive_host.h), so `colord info` of the reference prints this archive's record.
+// Not covered (refused with a message): -G reference genomes, the threshold / plain-average quality modes, header modes
+// other than the default.
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <ctime>
+#include <iostream>
+#include "archive_host.h"
+#include "fastq_reader.h"
+#include "presets.h"
+#include "stage23_host.h"
+
+namespace clbhost {
+
+struct CompressionReport {            // what the reference prints at the end (compression.cpp:795-808)
+	uint64_t dna = 0, qual = 0, header = 0, meta = 0, info = 0, archive = 0;
+	uint32_t kmerLen = 0, anchorLen = 0, sparse_range = 0, tot_ref_reads = 0;
+	clb_kmer_stats stats{};
+	double seconds = 0;
+};
+
+inline void refuse_unsupported(const CCompressorParams& p)
+{
+	if (!p.refGenomePath.empty()) throw std::invalid_argument("reference-genome mode (-G) is not available in this build");
+	if (p.headerComprMode != HeaderComprMode::Original) throw std::invalid_argument("header modes other than 'org' are not available in this build");
+	switch (p.qualityComprMode) {
+	case QualityComprMode::Original: case QualityComprMode::QuinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::BinaryAverage: case QualityComprMode::None: break;
+	default: throw std::invalid_argument(std::string("quality mode '") + qualityComprModeToString(p.qualityComprMode) + "' is not available in this build (org, 2-avg, 4-avg, 5-avg, none are)");
+	}
+}
+
+inline CompressionReport runCompression(const CCompressorParams& params, CInfo& info)
+{
+	const auto t0 = std::chrono::steady_clock::now();
+	refuse_unsupported(params);
+	CompressionReport rep;
+	info.version_major = B200_VERSION_MAJOR; info.version_minor = B200_VERSION_MINOR; info.version_patch = B200_VERSION_PATCH;
+
+	CArchive archive(false);
+	if (!archive.Open(params.outputFilePath)) throw std::runtime_error("Error: cannot open archive: " + params.outputFilePath);
+	const int s_meta = archive.RegisterStream("meta");
+
+	CInputReads in(params.inputFilePath);
+	const bool is_fastq = in.is_fastq;
+	info.total_bytes = in.total_bytes; info.total_bases = in.total_bases;
+
+	uint32_t kmerLen = params.kmerLen, anchorLen = params.anchorLen;
+	adjustKmerAndAnchorLen(kmerLen, anchorLen, in.is_gzip, is_fastq, in.file_bytes);
+	rep.kmerLen = kmerLen; rep.anchorLen = anchorLen;
+	const bool hifi = params.dataSource == DataSource::PBHiFi;
+
+	// stage 1a: the reference reads the file a second time through KMC; here the parsed reads go to the device once
+	CKmerCounter kmer_counter(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi, in.total_bases, params.device);
+	clb_ctx* ctx = kmer_counter.Context();
+	check(ctx, clb_append_reads(ctx, in.bases.data(), in.offsets.data(), in.n_reads(), 0), "clb_append_reads");
+	const uint32_t tot_n_reads = kmer_counter.GetNReads();
+	const uint64_t tot_kmers = kmer_counter.GetTotKmers(), n_uniq_counted_kmers = kmer_counter.GetNUniqueCounted();
+	check(ctx, clb_count_finalize(ctx, &rep.stats), "clb_count_finalize");
+	if (tot_n_reads == 0) throw std::runtime_error("Error: no reads in the input");
+	const uint64_t mean_read_len = meanReadLen(tot_kmers, params.filterHashModulo, tot_n_reads, kmerLen);
+	info.total_reads = tot_n_reads;
+	if (params.verbose) std::cerr << "tot k-mers: " << tot_kmers << "\nn uniq counted: " << n_uniq_counted_kmers << "\napprox. avg. read len: " << mean_read_len << "\n";
+
+	// reference reads: all, or the sparse sampler over the range derived from the filtered k-mers
+	const uint32_t sparseMode_range = sparseModeRange(params.sparseMode_range_symbols, n_uniq_counted_kmers, params.filterHashModulo, mean_read_len ? mean_read_len : 1);
+	const bool sparse = params.referenceReadsMode == ReferenceReadsMode::Sparse;
+	CRefReadsAccepter accepter(sparseMode_range, params.sparseMode_exponent, 0);
+	uint32_t tot_ref_reads = sparse ? accepter.GetNAccepted(tot_n_reads) : tot_n_reads;
+	rep.sparse_range = sparseMode_range; rep.tot_ref_reads = tot_ref_reads;
+
+	// stage 1b + 2
+	CReadsSimilarityGraph graph(kmer_counter, params.maxCandidates, hifi, sparse, accepter, 0);
+	CEncoder encoder(kmer_counter, anchorLen, params.minFractionOfMmersInEncodeToAlwaysEncode, params.minFractionOfMmersInEncode, params.maxMatchesMultiplier,
+		params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
+	encoder.Encode(in.read_pack_sizes);
+
+	// stage 3: one part per stream, metadata = number of reads / headers as in entr_read.h:74, entr_header.cpp:41
+	const int s_dna = archive.RegisterStream("dna-b200");
+	{
+		CEntrComprReads dna(kmer_counter, params.compressionLevel);
+		dna.Compress(in.read_pack_sizes);
+		const std::vector<uint8_t> stream = dna.GetStream();
+		archive.AddPart(s_dna, stream, tot_n_reads);
+	}
+	int s_qual = -1;
+	if (is_fastq) {
+		s_qual = archive.RegisterStream("qual-b200");
+		std::vector<uint8_t> stream;
+		if (params.qualityComprMode != QualityComprMode::None) {
+			const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
+			CEntrComprQuals q(kmer_counter, n_bins, params.qualityFwdThresholds, params.compressionLevel);
+			if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals, in.offsets, in.read_pack_sizes);
+			else q.Compress(in.quals, in.offsets, in.read_pack_sizes);
+			stream = q.GetStream();
+		}
+		archive.AddPart(s_qual, stream, 0);
+	}
+	const int s_header = archive.RegisterStream("header-b200");
+	{
+		CEntrComprHeaders h(kmer_counter);
+		h.Compress(in.headers, in.header_offsets, in.plus_id);
+		const std::vector<uint8_t> stream = h.GetStream();
+		archive.AddPart(s_header, stream, in.header_offsets.size() - 1);
+	}
+
+	// `meta` (compression.cpp:705-779)
+	CMeta meta;
+	meta.tot_ref_reads = tot_ref_reads; meta.maxCandidates = params.maxCandidates; meta.compressionLevel = params.compressionLevel;
+	meta.dataSource = params.dataSource; meta.approx_stream_size = static_cast<uint64_t>(tot_n_reads) * mean_read_len;
+	meta.is_fastq = is_fastq; meta.qualityComprMode = params.qualityComprMode;
+	meta.qualityRevThresholds = params.qualityRevThresholds;
+	meta.qualityRevThresholds.resize(CMeta::n_thresholds(params.qualityComprMode));
+	meta.headerComprMode = params.headerComprMode; meta.referenceReadsMode = params.referenceReadsMode;
+	meta.sparseMode_range = sparseMode_range; meta.sparseMode_exponent = params.sparseMode_exponent;
+	archive.AddPart(s_meta, meta.Serialize(), 0);
+	const int s_info = archive.RegisterStream("info");
+	info.time = static_cast<uint64_t>(std::time(nullptr));
+	archive.AddPart(s_info, info.Serialize(), 0);
+	archive.Close();
+
+	rep.dna = archive.GetStreamPackedSize(s_dna); rep.qual = s_qual >= 0 ? archive.GetStreamPackedSize(s_qual) : 0; rep.header = archive.GetStreamPackedSize(s_header);
+	rep.meta = archive.GetStreamPackedSize(s_meta); rep.info = archive.GetStreamPackedSize(s_info);
+	rep.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	return rep;
+}
+
+} // namespace clbhost

@@ -96,6 +96,12 @@ public:
 		for (const auto& [id, plus_id] : headers) { bytes.insert(bytes.end(), id.begin(), id.end()); off.push_back(bytes.size()); plus.push_back(plus_id); }
 		check(ctx, clb_hdr_encode(ctx, bytes.data(), off.data(), plus.data(), headers.size(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
 	}
+	// the same over headers stored back to back (what the host reader produces)
+	void Compress(const std::vector<uint8_t>& bytes, const std::vector<uint64_t>& offsets, const std::vector<uint8_t>& plus_id, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_hdr_encode(ctx, bytes.data(), offsets.data(), plus_id.empty() ? nullptr : plus_id.data(), offsets.size() - 1, 0,
+			pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
+	}
 	std::vector<uint8_t> GetStream() const
 	{
 		uint64_t tot = 0; check(ctx, clb_hdr_size(ctx, &tot, nullptr), "clb_hdr_size");

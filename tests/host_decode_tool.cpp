@@ -1,0 +1,72 @@
+// Test driver for colord_b200/host/decompressor.h and fastq_reader.h (compiled by the tests with g++; host only, no device).
+//   hdr <stream> <n> <out>                          decoded headers: per header "<plus>\t<bytes>\n"
+//   qavg|qorg <stream> <bases> <offsets> [flags] <out>   bases: ASCII back to back, offsets: u64[n+1], flags: one byte per base
+//   dna <stream> <n_reads> <decisions> <out_bases> <out_offsets> <out_flags>
+//   parse <input> <out_prefix>                      reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
+#include "../colord_b200/host/decompressor.h"
+#include "../colord_b200/host/fastq_reader.h"
+#include <cinttypes>
+#include <fstream>
+#include <iostream>
+
+using namespace clbhost;
+
+static std::vector<uint8_t> slurp(const char* p)
+{
+	std::ifstream f(p, std::ios::binary);
+	if (!f) throw std::runtime_error(std::string("cannot open ") + p);
+	return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+static void spit(const std::string& p, const void* d, size_t n) { std::ofstream f(p, std::ios::binary); f.write(static_cast<const char*>(d), static_cast<std::streamsize>(n)); }
+
+int main(int argc, char** argv)
+{
+	try {
+		const std::string cmd = argc > 1 ? argv[1] : "";
+		if (cmd == "hdr" && argc == 5) {
+			const auto s = slurp(argv[2]);
+			const dec::Headers H = dec::decode_headers(s.data(), s.size(), std::strtoull(argv[3], nullptr, 10));
+			std::ofstream o(argv[4], std::ios::binary);
+			for (size_t r = 0; r + 1 < H.offsets.size(); ++r) { o << int(H.plus_id[r]) << '\t'; o.write(reinterpret_cast<const char*>(H.bytes.data() + H.offsets[r]), static_cast<std::streamsize>(H.offsets[r + 1] - H.offsets[r])); o << '\n'; }
+			return 0;
+		}
+		if ((cmd == "qavg" || cmd == "qorg") && (argc == 6 || argc == 7)) {
+			const auto s = slurp(argv[2]);
+			dec::Reads R; R.bases = slurp(argv[3]);
+			const auto off = slurp(argv[4]);
+			R.offsets.assign(reinterpret_cast<const uint64_t*>(off.data()), reinterpret_cast<const uint64_t*>(off.data() + off.size()));
+			if (argc == 7) R.flags = slurp(argv[5]); else R.flags.assign(R.bases.size(), 0);
+			const auto q = cmd == "qavg" ? dec::decode_qual_avg(s.data(), s.size(), R) : dec::decode_qual_org(s.data(), s.size(), R);
+			spit(argv[argc - 1], q.data(), q.size());
+			return 0;
+		}
+		if (cmd == "dna" && argc == 8) {
+			const auto s = slurp(argv[2]);
+			const uint32_t n = static_cast<uint32_t>(std::strtoul(argv[3], nullptr, 10));
+			const auto decs = slurp(argv[4]);
+			dec::DnaDecoder D;
+			const dec::Reads R = D.decode(s.data(), s.size(), n, decs);
+			spit(argv[5], R.bases.data(), R.bases.size()); spit(argv[6], R.offsets.data(), 8 * R.offsets.size()); spit(argv[7], R.flags.data(), R.flags.size());
+			return 0;
+		}
+		if (cmd == "parse" && argc == 4) {
+			const CInputReads in(argv[2]);
+			const std::string pre = argv[3];
+			spit(pre + ".bases", in.bases.data(), in.bases.size()); spit(pre + ".offsets", in.offsets.data(), 8 * in.offsets.size());
+			spit(pre + ".quals", in.quals.data(), in.quals.size()); spit(pre + ".headers", in.headers.data(), in.headers.size());
+			spit(pre + ".hoff", in.header_offsets.data(), 8 * in.header_offsets.size()); spit(pre + ".plus", in.plus_id.data(), in.plus_id.size());
+			spit(pre + ".hasn", in.has_n.data(), in.has_n.size());
+			std::printf("{\"is_fastq\": %d, \"is_gzip\": %d, \"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"total_bases\": %" PRIu64 ", \"total_symb_header\": %" PRIu64 ", \"file_bytes\": %" PRIu64 ", \"read_packs\": [",
+				int(in.is_fastq), int(in.is_gzip), in.n_reads(), in.total_bytes, in.total_bases, in.total_symb_header, in.file_bytes);
+			for (size_t i = 0; i < in.read_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.read_pack_sizes[i]);
+			std::printf("], \"header_packs\": [");
+			for (size_t i = 0; i < in.header_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.header_pack_sizes[i]);
+			std::printf("]}\n");
+			return 0;
+		}
+		std::cerr << "host_decode_tool: bad arguments\n";
+		return 2;
+	} catch (const InputError& e) { std::cerr << e.what() << "\n"; return 1; }
+	catch (const DecodeError& e) { std::cerr << e.what() << "\n"; return 3; }
+	catch (const std::exception& e) { std::cerr << e.what() << "\n"; return 4; }
+}

@@ -1,0 +1,245 @@
+"""Host-side decoders of the native containers (colord_b200/host/decompressor.h) and the input reader (fastq_reader.h) on CPU.
+
+The containers decoded here are written by the oracle's CPU twins of the device encoders (byte-identical to the device's output,
+tests/test_gpu_stage3.py) or are device-made fixtures (tests/golden/b200_archives, written on a B200 by make_b200_archives.py).
+The product decoders share no code with the oracle: equal results check both.  The oracle is used as the checker only."""
+import gzip
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_io
+import oracle_lib
+from colord_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def tool(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("host_decode") / "tool")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", out, os.path.join(ROOT, "tests", "host_decode_tool.cpp"), "-lz"], check=True)
+    return out
+
+
+def _write(path, arr):
+    np.ascontiguousarray(arr).tofile(path)
+    return path
+
+
+def _packs(offsets):
+    """the reference's read-pack rule (in_reads.cpp:62-76): a pack closes at >= 4 MiB counting a guard byte per read"""
+    packs, cur, n = [], 0, 0
+    for i in range(len(offsets) - 1):
+        cur += int(offsets[i + 1] - offsets[i]) + 1
+        n += 1
+        if cur >= (2 << 21):
+            packs.append(n)
+            cur, n = 0, 0
+    if n:
+        packs.append(n)
+    return packs
+
+
+# ---------------------------------------------------------------------------------------------------------------- headers
+@pytest.mark.parametrize("case", ["ont", "hifi", "clr", "synthetic_ont_20000"])
+def test_header_decoder(tool, tmp_path, case):
+    headers, _ = golden_io.load_hdr_golden()[case]
+    headers = headers[:6000]
+    plus = (np.arange(len(headers)) % 3 == 0).astype(np.uint8)
+    stream = oracle_lib.hdr_encode(headers, plus=plus, packs=[min(1500, len(headers) - i) for i in range(0, len(headers), 1500)])
+    s, o = _write(str(tmp_path / "s"), stream), str(tmp_path / "o")
+    subprocess.run([tool, "hdr", s, str(len(headers)), o], check=True)
+    got = open(o, "rb").read().split(b"\n")[:-1]
+    assert len(got) == len(headers)
+    for g, h, p in zip(got, headers, plus):
+        assert g == b"%d\t" % p + h
+
+
+# -------------------------------------------------------------------------------------------------------------- qualities
+@pytest.mark.parametrize("name,n_bins,thr", [("ont", 4, [7, 14, 26]), ("hifi", 5, [7, 14, 26, 93]), ("ont", 2, [7])])
+def test_quality_avg_decoder_reproduces_the_reference_quan(tool, tmp_path, name, n_bins, thr):
+    """QB01 (level 1) -> the qualities `colord decompress` of the reference prints (its own .quan fixtures for 4-avg / 5-avg)."""
+    bases, quals, quan, off = golden_io.load_qual_golden(name)
+    P = oracle_lib.qual_params(n_bins, thr, 1)
+    stream = oracle_lib.qual_encode(P, bases, quals, off, _packs(off))
+    s, b, f, o = _write(str(tmp_path / "s"), stream), _write(str(tmp_path / "b"), bases), _write(str(tmp_path / "f"), off), str(tmp_path / "o")
+    subprocess.run([tool, "qavg", s, b, f, o], check=True)
+    got = np.fromfile(o, np.uint8)
+    if n_bins != 2:
+        assert np.array_equal(got, quan)            # the reference's own fixture
+    assert np.array_equal(got, oracle_lib.qual_lossy(P, bases, quals, off))
+
+
+def _fake_tuples(rng, lens):
+    """CompactES-shaped tuples whose match / anchor / other layout is random (flags only depend on the tuple types)"""
+    es, es_off, flags = [], [0], []
+    for n in lens:
+        out = bytearray([10 << 4, 0, 0, 0, 0])
+        fl, at = [], 0
+        while at < n:
+            t = int(rng.integers(0, 5))
+            if t == 4 and n - at >= 15:
+                ln = int(rng.integers(15, min(60, n - at) + 1))
+                out += bytes([(4 << 4) | (ln >> 24), (ln >> 16) & 255, (ln >> 8) & 255, ln & 255])
+                fl += [2] * ln
+                at += ln
+            elif t == 1:
+                out.append(1 << 4)              # deletion: no base
+            elif t == 2:
+                out.append(2 << 4); fl.append(1); at += 1
+            else:
+                out.append((0 if t == 0 else 3) << 4); fl.append(0); at += 1
+        es.append(bytes(out)); es_off.append(es_off[-1] + len(out)); flags += fl
+    return np.frombuffer(b"".join(es), np.uint8).copy(), np.array(es_off, np.uint64), np.array(flags, np.uint8)
+
+
+@pytest.mark.parametrize("level", [2, 3])
+def test_quality_avg_decoder_with_tuple_flags(tool, tmp_path, level):
+    s_ = synth.generate(60, 20000, 1500, seed=5, profile="ont")
+    rng = np.random.default_rng(7)
+    lens = np.diff(s_.offsets).astype(np.int64)
+    es, es_off, flags = _fake_tuples(rng, lens)
+    P = oracle_lib.qual_params(4, [7, 14, 26], level)
+    stream = oracle_lib.qual_encode(P, s_.bases, s_.quals, s_.offsets, [40, 20], es=es, es_off=es_off)
+    paths = [_write(str(tmp_path / n), a) for n, a in (("s", stream), ("b", s_.bases), ("f", s_.offsets), ("fl", flags))]
+    o = str(tmp_path / "o")
+    subprocess.run([tool, "qavg", *paths, o], check=True)
+    assert np.array_equal(np.fromfile(o, np.uint8), oracle_lib.qual_lossy(P, s_.bases, s_.quals, s_.offsets))
+
+
+@pytest.mark.parametrize("source,level", [(0, 1), (2, 2), (1, 3), (2, 3)])
+def test_quality_org_decoder_is_lossless(tool, tmp_path, source, level):
+    s_ = synth.generate(50, 20000, 1500, seed=11 + source, profile="hifi" if source == 2 else "ont")
+    rng = np.random.default_rng(3)
+    es, es_off, flags = _fake_tuples(rng, np.diff(s_.offsets).astype(np.int64))
+    quals = s_.quals.copy()
+    quals[::97] = 33 + 93                                                    # the top value has its own quantiser cell
+    stream = oracle_lib.qorg_encode(source, level, s_.bases, quals, s_.offsets, [30, 20], es=es if level > 1 else None, es_off=es_off if level > 1 else None)
+    paths = [_write(str(tmp_path / n), a) for n, a in (("s", stream), ("b", s_.bases), ("f", s_.offsets), ("fl", flags))]
+    o = str(tmp_path / "o")
+    subprocess.run([tool, "qorg", *paths, o], check=True)
+    assert np.array_equal(np.fromfile(o, np.uint8), quals)
+
+
+def test_damaged_streams_are_refused(tool, tmp_path):
+    headers, _ = golden_io.load_hdr_golden()["ont"]
+    stream = oracle_lib.hdr_encode(headers[:50])
+    for name, blob in {"cut": stream[:len(stream) // 2], "magic": np.concatenate([np.frombuffer(b"XX01", np.uint8), stream[4:]]), "empty": stream[:0]}.items():
+        s = _write(str(tmp_path / name), blob)
+        r = subprocess.run([tool, "hdr", s, "50", str(tmp_path / "o")], capture_output=True)
+        assert r.returncode == 3, (name, r.returncode, r.stderr)
+    s = _write(str(tmp_path / "count"), stream)
+    assert subprocess.run([tool, "hdr", s, "51", str(tmp_path / "o")], capture_output=True).returncode == 3
+
+
+# ------------------------------------------------------------------------------------------------------------------ reader
+def _parse(tool, path, prefix):
+    r = subprocess.run([tool, "parse", path, prefix], capture_output=True, text=True)
+    return r, (json.loads(r.stdout) if r.returncode == 0 else None)
+
+
+def _fastq(records, eol="\n", plus_header=()):
+    out = []
+    for i, (h, s, q) in enumerate(records):
+        out += ["@" + h, s, "+" + (h if i in plus_header else ""), q]
+    return (eol.join(out) + eol).encode()
+
+
+RECORDS = [("r1 a=1", "ACGTNACGT", "IIIIIIIII"), ("r2", "TTTT", "!!!!"), ("r3/x", "GATTACA", "5555555")]
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "blank_lines", "plus_header", "gzip", "cr_only"])
+def test_reader_fastq_variants(tool, tmp_path, variant):
+    """in_reads.cpp:181-221: '\\n' and '\\r' both end a line, empty lines are skipped, '+' line empty or equal to the header."""
+    data = _fastq(RECORDS, eol={"crlf": "\r\n", "cr_only": "\r"}.get(variant, "\n"), plus_header=(0, 2) if variant == "plus_header" else ())
+    if variant == "blank_lines":
+        data = data.replace(b"\n@r2", b"\n\n\n@r2") + b"\n\n"
+    p = str(tmp_path / ("in.fastq.gz" if variant == "gzip" else "in.fastq"))
+    if variant == "gzip":
+        with gzip.open(p, "wb") as f:
+            f.write(data)
+    else:
+        open(p, "wb").write(data)
+    r, st = _parse(tool, p, str(tmp_path / "o"))
+    assert r.returncode == 0, r.stderr
+    assert st["is_fastq"] == 1 and st["n_reads"] == 3 and st["is_gzip"] == (1 if variant == "gzip" else 0)
+    assert st["total_bytes"] == len(data) and st["total_bases"] == 20
+    # header statistics count the '@' / '+' lines as the reference does (in_reads.cpp:49, :81)
+    assert st["total_symb_header"] == sum(len(h) + 1 for h, _, _ in RECORDS) + 3 + (sum(len(RECORDS[i][0]) for i in (0, 2)) if variant == "plus_header" else 0)
+    assert open(str(tmp_path / "o.bases"), "rb").read() == b"".join(s.encode() for _, s, _ in RECORDS)
+    assert open(str(tmp_path / "o.quals"), "rb").read() == b"".join(q.encode() for _, _, q in RECORDS)
+    assert open(str(tmp_path / "o.headers"), "rb").read() == b"".join(h.encode() for h, _, _ in RECORDS)
+    assert list(np.fromfile(str(tmp_path / "o.offsets"), np.uint64)) == [0, 9, 13, 20]
+    assert list(np.fromfile(str(tmp_path / "o.plus"), np.uint8)) == ([1, 0, 1] if variant == "plus_header" else [0, 0, 0])
+    assert list(np.fromfile(str(tmp_path / "o.hasn"), np.uint8)) == [1, 0, 0]
+    assert st["read_packs"] == [3] and st["header_packs"] == [3]
+
+
+@pytest.mark.parametrize("variant,message", [
+    ("lowercase", "Only ACGTN symbols supported inside a read"), ("iupac", "Only ACGTN symbols supported inside a read"),
+    ("bad_plus", "quality header not empty but different than read header"), ("no_final_eol", "something went wrong during input reading"),
+    ("empty", "is empty"), ("unknown", "unknown file format"), ("truncated_record", "something went wrong during input reading")])
+def test_reader_refusals(tool, tmp_path, variant, message):
+    """The inputs the reference exits on (in_reads.cpp:31-35, :86-92, :246-260, :278-282) are refused with its messages."""
+    data = {
+        "lowercase": _fastq([("r", "ACgT", "IIII")]), "iupac": _fastq([("r", "ACRT", "IIII")]),
+        "bad_plus": b"@r1\nACGT\n+r2\nIIII\n", "no_final_eol": _fastq(RECORDS)[:-1], "empty": b"", "unknown": b"ACGT\n",
+        "truncated_record": b"@r1\nACGT\n+\nIIII\n@r2\nACGT\n",
+    }[variant]
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(data)
+    r, _ = _parse(tool, p, str(tmp_path / "o"))
+    assert r.returncode == 1 and message in r.stderr, (r.returncode, r.stderr)
+
+
+def test_reader_fasta_multiline(tool, tmp_path):
+    """in_reads.cpp:117-176: reads may span lines; '>' starts a header only at the start of a line; the last read needs no end-of-line."""
+    data = b">s1 desc\nACGT\nACGT\r\n\r\nAC\n>s2\nNNNN\n>s3\nGG\nTT"
+    p = str(tmp_path / "in.fa")
+    open(p, "wb").write(data)
+    r, st = _parse(tool, p, str(tmp_path / "o"))
+    assert r.returncode == 0, r.stderr
+    assert st["is_fastq"] == 0 and st["n_reads"] == 3 and st["total_bases"] == 18 and st["total_symb_header"] == 8 + 3 + 3
+    assert open(str(tmp_path / "o.bases"), "rb").read() == b"ACGTACGTACNNNNGGTT"
+    assert open(str(tmp_path / "o.headers"), "rb").read() == b"s1 descs2s3"
+    assert open(str(tmp_path / "o.quals"), "rb").read() == b""
+    assert list(np.fromfile(str(tmp_path / "o.hasn"), np.uint8)) == [0, 1, 0]
+
+
+def test_reader_packs_follow_the_reference_rule(tool, tmp_path):
+    """Read packs close at >= 4 MiB of reads (one guard byte each), header packs at >= 4 MiB of headers."""
+    rng = np.random.default_rng(1)
+    lens = rng.integers(150000, 250000, 60)
+    recs = [("read%d" % i, "".join("ACGT"[int(x)] for x in rng.integers(0, 4, int(n))), "I" * int(n)) for i, n in enumerate(lens)]
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(_fastq(recs))
+    r, st = _parse(tool, p, str(tmp_path / "o"))
+    assert r.returncode == 0, r.stderr
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    assert st["read_packs"] == _packs(off) and len(st["read_packs"]) > 2 and sum(st["read_packs"]) == 60
+    assert st["header_packs"] == [60]
+
+
+# ---------------------------------------------------------------------------------------- device-made archives (fixtures)
+B200 = os.path.join(ROOT, "tests", "golden", "b200_archives")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(B200, "expected.json")), reason="device-made archive fixtures not generated yet")
+@pytest.mark.parametrize("case", sorted(json.load(open(os.path.join(B200, "expected.json")))) if os.path.exists(os.path.join(B200, "expected.json")) else [])
+def test_decompress_device_made_archives(tmp_path, case):
+    """colord-b200 decompress (host code, runs without a GPU) of archives the device path wrote on a B200: the FASTQ comes back
+    with bases and headers identical and the qualities the reference's decompressor prints for that mode."""
+    import hashlib
+    cli = os.path.join(ROOT, "colord_b200", "colord-b200")
+    if not os.path.exists(cli):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "colord_b200", "csrc")], check=True, capture_output=True)
+    exp = json.load(open(os.path.join(B200, "expected.json")))[case]
+    out = str(tmp_path / "back")
+    r = subprocess.run([cli, "decompress", os.path.join(B200, case + ".colord"), out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    data = open(out, "rb").read()
+    assert len(data) == exp["output_bytes"] and hashlib.sha1(data).hexdigest() == exp["output_sha1"]
