@@ -243,3 +243,17 @@ def test_decompress_device_made_archives(tmp_path, case):
     assert r.returncode == 0, r.stderr
     data = open(out, "rb").read()
     assert len(data) == exp["output_bytes"] and hashlib.sha1(data).hexdigest() == exp["output_sha1"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "colord")) or not os.path.exists(os.path.join(B200, "expected.json")),
+                    reason="needs the reference binary (oracle/_ref, build container only) and the device-made fixtures")
+def test_reference_binary_on_device_made_archive(tmp_path):
+    """The unmodified reference reads the container and the info record of a device-made archive (`colord info`), and refuses to
+    decompress it at its version check instead of misreading the native streams."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "colord")
+    a = os.path.join(B200, "ont_default.colord")
+    r = subprocess.run([ref, "info", a], capture_output=True, text=True)
+    text = r.stdout + r.stderr
+    assert r.returncode == 0 and "version major: 201" in text and "total reads: 40" in text and "total bases: 199305" in text and "compress-ont" in text
+    r = subprocess.run([ref, "decompress", a, str(tmp_path / "x.fastq")], capture_output=True, text=True)
+    assert r.returncode == 1 and "incompatibile archive version" in (r.stdout + r.stderr)
