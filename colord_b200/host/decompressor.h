@@ -514,45 +514,57 @@ inline Headers decode_headers(const uint8_t* data, uint64_t size, uint64_t n_exp
 
 } // namespace dec
 
-// decompression_common.cpp:27-265 + decompression.cpp: archive -> file.  FASTQ records: '@' id, bases, '+' [id], qualities;
-// FASTA records: '>' id, bases on one line.
-inline void runDecompression(const std::string& archive_path, const std::string& output_path, bool verbose = false)
-{
-	CArchive archive(true);
-	if (!archive.Open(archive_path)) throw std::runtime_error("Error: cannot open archive: " + archive_path);
-	std::vector<uint8_t> raw; size_t md = 0;
-	const int s_info = archive.GetStreamId("info"), s_meta = archive.GetStreamId("meta");
-	if (s_info < 0 || s_meta < 0 || !archive.ReadPart(s_info, 0, raw, md)) throw DecodeError("Error: not a colord archive (no info / meta record)");
-	CInfo info; info.Deserialize(raw);
-	const int s_dna = archive.GetStreamId("dna-b200"), s_qual = archive.GetStreamId("qual-b200"), s_hdr = archive.GetStreamId("header-b200");
-	if (info.version_major != B200_VERSION_MAJOR || s_dna < 0 || s_hdr < 0)
-		throw DecodeError("Error: incompatibile archive version (this build reads archives written by colord-b200; use the reference's colord for its own archives)");
-	if (!archive.ReadPart(s_meta, 0, raw, md)) throw DecodeError("Error: cannot read the meta record");
-	CMeta meta; meta.Deserialize(raw, s_qual >= 0);
-	if (meta.ref_genome_available) throw DecodeError("Error: reference-genome archives are not available in this build");
-	const uint32_t n_reads = info.total_reads;
-	if (verbose) std::cerr << "reads: " << n_reads << "\nbases: " << info.total_bases << "\nquality mode: " << static_cast<int>(meta.qualityComprMode) << "\n";
+// decompression_common.cpp:27-265: the archive's records and streams decoded into memory (reads in input order)
+struct DecompressedArchive {
+	CInfo info; CMeta meta;
+	dec::Reads reads; dec::Headers headers; std::vector<uint8_t> quals;      // quals: same layout as reads.bases, empty for FASTA
 
-	std::vector<uint8_t> stream;
-	if (!archive.ReadPart(s_dna, 0, stream, md) || md != n_reads) throw DecodeError("Error: cannot read the DNA stream");
-	const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
-	dec::DnaDecoder dna;
-	const dec::Reads reads = dna.decode(stream.data(), stream.size(), n_reads, decisions);
-	if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
+	explicit DecompressedArchive(const std::string& archive_path, bool verbose = false)
+	{
+		CArchive archive(true);
+		if (!archive.Open(archive_path)) throw std::runtime_error("Error: cannot open archive: " + archive_path);
+		std::vector<uint8_t> raw; size_t md = 0;
+		const int s_info = archive.GetStreamId("info"), s_meta = archive.GetStreamId("meta");
+		if (s_info < 0 || s_meta < 0 || !archive.ReadPart(s_info, 0, raw, md)) throw DecodeError("Error: not a colord archive (no info / meta record)");
+		info.Deserialize(raw);
+		const int s_dna = archive.GetStreamId("dna-b200"), s_qual = archive.GetStreamId("qual-b200"), s_hdr = archive.GetStreamId("header-b200");
+		if (info.version_major != B200_VERSION_MAJOR || s_dna < 0 || s_hdr < 0)
+			throw DecodeError("Error: incompatibile archive version (this build reads archives written by colord-b200; use the reference's colord for its own archives)");
+		if (!archive.ReadPart(s_meta, 0, raw, md)) throw DecodeError("Error: cannot read the meta record");
+		meta.Deserialize(raw, s_qual >= 0);
+		if (meta.ref_genome_available) throw DecodeError("Error: reference-genome archives are not available in this build");
+		const uint32_t n_reads = info.total_reads;
+		if (verbose) std::cerr << "reads: " << n_reads << "\nbases: " << info.total_bases << "\nquality mode: " << static_cast<int>(meta.qualityComprMode) << "\n";
 
-	if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
-	const dec::Headers H = dec::decode_headers(stream.data(), stream.size(), n_reads);
+		std::vector<uint8_t> stream;
+		if (!archive.ReadPart(s_dna, 0, stream, md) || md != n_reads) throw DecodeError("Error: cannot read the DNA stream");
+		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
+		dec::DnaDecoder dna;
+		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions);
+		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
-	std::vector<uint8_t> quals;
-	if (meta.is_fastq) {
-		if (!archive.ReadPart(s_qual, 0, stream, md)) throw DecodeError("Error: cannot read the quality stream");
-		switch (meta.qualityComprMode) {
-		case QualityComprMode::None: quals.assign(reads.bases.size(), static_cast<uint8_t>(33 + meta.qualityRevThresholds.at(0))); break;      // quality_coder.cpp:611-617
-		case QualityComprMode::Original: quals = dec::decode_qual_org(stream.data(), stream.size(), reads); break;
-		case QualityComprMode::BinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::QuinaryAverage: quals = dec::decode_qual_avg(stream.data(), stream.size(), reads); break;
-		default: throw DecodeError("Error: quality mode of the archive is not available in this build");
+		if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
+		headers = dec::decode_headers(stream.data(), stream.size(), n_reads);
+
+		if (meta.is_fastq) {
+			if (!archive.ReadPart(s_qual, 0, stream, md)) throw DecodeError("Error: cannot read the quality stream");
+			switch (meta.qualityComprMode) {
+			case QualityComprMode::None: quals.assign(reads.bases.size(), static_cast<uint8_t>(33 + meta.qualityRevThresholds.at(0))); break;      // quality_coder.cpp:611-617
+			case QualityComprMode::Original: quals = dec::decode_qual_org(stream.data(), stream.size(), reads); break;
+			case QualityComprMode::BinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::QuinaryAverage: quals = dec::decode_qual_avg(stream.data(), stream.size(), reads); break;
+			default: throw DecodeError("Error: quality mode of the archive is not available in this build");
+			}
 		}
 	}
+	uint32_t n_reads() const { return static_cast<uint32_t>(reads.offsets.size() - 1); }
+};
+
+// decompression.cpp: archive -> file.  FASTQ records: '@' id, bases, '+' [id], qualities; FASTA records: '>' id, bases on one line.
+inline void runDecompression(const std::string& archive_path, const std::string& output_path, bool verbose = false)
+{
+	const DecompressedArchive A(archive_path, verbose);
+	const CMeta& meta = A.meta; const dec::Reads& reads = A.reads; const dec::Headers& H = A.headers; const std::vector<uint8_t>& quals = A.quals;
+	const uint32_t n_reads = A.n_reads();
 	FILE* out = std::fopen(output_path.c_str(), "wb");
 	if (!out) throw std::runtime_error("Error: cannot open output file: " + output_path);
 	std::vector<uint8_t> buf; buf.reserve(1u << 24);

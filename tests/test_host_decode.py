@@ -257,3 +257,22 @@ def test_reference_binary_on_device_made_archive(tmp_path):
     assert r.returncode == 0 and "version major: 201" in text and "total reads: 40" in text and "total bases: 199305" in text and "compress-ont" in text
     r = subprocess.run([ref, "decompress", a, str(tmp_path / "x.fastq")], capture_output=True, text=True)
     assert r.returncode == 1 and "incompatibile archive version" in (r.stdout + r.stderr)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(B200, "expected.json")), reason="device-made archive fixtures not generated yet")
+def test_api_surface_on_device_made_archives(tmp_path):
+    """include/colord_b200_api.h (mirror of src/API/colord_api.h): the reference's API example, ported by renaming the namespace,
+    prints the records of every fixture archive exactly as `decompress` writes them, and the Info block of the reference's format."""
+    import hashlib
+    exe = str(tmp_path / "api_example")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "host_api_example.cpp")], check=True)
+    exp = json.load(open(os.path.join(B200, "expected.json")))
+    for case, e in exp.items():
+        r = subprocess.run([exe, os.path.join(B200, case + ".colord")], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert hashlib.sha1(r.stdout).hexdigest() == e["output_sha1"], case
+        info = r.stderr.decode()
+        assert "colord archive version: 201.1.0" in info and f"is fastq: {'false' if case == 'ont_fasta' else 'true'}" in info
+        assert ("reads source: PBRaw" if case.startswith("clr") else "reads source: ONT") in info
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
+    assert r.returncode == 1 and "incompatibile archive version" in r.stderr         # a reference archive is refused, not misread
