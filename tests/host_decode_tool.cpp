@@ -5,6 +5,7 @@
 //   parse <input> <out_prefix>                      reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
 #include "../colord_b200/host/decompressor.h"
 #include "../colord_b200/host/fastq_reader.h"
+#include <chrono>
 #include <cinttypes>
 #include <fstream>
 #include <iostream>
@@ -47,6 +48,13 @@ int main(int argc, char** argv)
 			dec::DnaDecoder D;
 			const dec::Reads R = D.decode(s.data(), s.size(), n, decs);
 			spit(argv[5], R.bases.data(), R.bases.size()); spit(argv[6], R.offsets.data(), 8 * R.offsets.size()); spit(argv[7], R.flags.data(), R.flags.size());
+			return 0;
+		}
+		if (cmd == "parse-time" && argc == 3) {       // reader throughput: parse only, no dumps
+			const auto t0 = std::chrono::steady_clock::now();
+			const CInputReads in(argv[2]);
+			const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+			std::printf("{\"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"seconds\": %.4f, \"GBps\": %.3f}\n", in.n_reads(), in.total_bytes, s, in.total_bytes / s * 1e-9);
 			return 0;
 		}
 		if (cmd == "parse" && argc == 4) {
