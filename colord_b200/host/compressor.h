@@ -100,8 +100,8 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 		if (params.qualityComprMode != QualityComprMode::None) {
 			const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
 			CEntrComprQuals q(kmer_counter, n_bins, params.qualityFwdThresholds, params.compressionLevel);
-			if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals, in.offsets, in.read_pack_sizes);
-			else q.Compress(in.quals, in.offsets, in.read_pack_sizes);
+			if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals.data(), in.offsets.data(), in.read_pack_sizes);
+			else q.Compress(in.quals.data(), in.offsets.data(), in.read_pack_sizes);
 			stream = q.GetStream();
 		}
 		archive.AddPart(s_qual, stream, 0);
@@ -109,7 +109,7 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 	const int s_header = archive.RegisterStream("header-b200");
 	{
 		CEntrComprHeaders h(kmer_counter);
-		h.Compress(in.headers, in.header_offsets, in.plus_id);
+		h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
 		const std::vector<uint8_t> stream = h.GetStream();
 		archive.AddPart(s_header, stream, in.header_offsets.size() - 1);
 	}

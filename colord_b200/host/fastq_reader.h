@@ -11,13 +11,22 @@
 //   * read packs close when their reads hold >= 4 MiB counting one guard byte per read, header packs when their headers
 //     hold >= 4 MiB (:62-76, :43-48, :95-101; defs.h:45-46)
 //   * total_bytes = bytes delivered by the (de)compressor, total_bases, total_symb_header = header + '+' line bytes (:49, :81)
-// Construction differs: the file is mapped (gzip: inflated) once and lines are found with memchr, not pushed byte by byte.
+// Construction differs.  The file is mapped (gzip: inflated) once and lines are found with memchr.  FASTQ is parsed by several
+// threads: the input is cut at record starts (a line that begins with '@' whose second-next line begins with '+' — a quality
+// line that begins with '@' is followed by a header and then by a read, which cannot begin with '+'), pass 1 sizes every
+// piece, a prefix sum places it, pass 2 checks and copies into the final arrays — each thread first-touches its own part of
+// them, which is what the reader's time goes to (page faults).  Whenever the threaded parse meets anything irregular it is
+// abandoned and the serial parser, which follows the reference line by line, decides and words the refusal.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -29,36 +38,56 @@ namespace clbhost {
 
 struct InputError : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// A block of T that is NOT value-initialised: the thread that fills a part of it is the one that touches its pages first.
+template <typename T>
+class Block {
+	std::unique_ptr<T[]> p; size_t n = 0, cap = 0;
+public:
+	void allocate(size_t count) { p.reset(new T[count ? count : 1]); n = count; cap = count ? count : 1; }
+	void reserve(size_t count) { if (count > cap) { std::unique_ptr<T[]> q(new T[count]); if (n) std::memcpy(q.get(), p.get(), n * sizeof(T)); p.swap(q); cap = count; } }
+	void append(const T* s, size_t count) { if (n + count > cap) reserve(std::max(n + count, cap * 2)); if (count) std::memcpy(p.get() + n, s, count * sizeof(T)); n += count; }
+	void push_back(const T& v) { append(&v, 1); }
+	T* data() { return p.get(); }
+	const T* data() const { return p.get(); }
+	size_t size() const { return n; }
+	bool empty() const { return n == 0; }
+	T& operator[](size_t i) { return p[i]; }
+	const T& operator[](size_t i) const { return p[i]; }
+	const T* begin() const { return p.get(); }
+	const T* end() const { return p.get() + n; }
+};
+
 class CInputReads {
 public:
 	bool is_fastq = false, is_gzip = false;
-	std::vector<uint8_t> bases; std::vector<uint64_t> offsets{0};          // reads back to back, offsets[n + 1]
-	std::vector<uint8_t> quals;                                           // same layout as bases (FASTQ only)
-	std::vector<uint8_t> headers; std::vector<uint64_t> header_offsets{0}; // headers without their first character
-	std::vector<uint8_t> plus_id;                                         // 1: the '+' line repeats the header (qual_header_type::eq_read_header)
-	std::vector<uint8_t> has_n;
-	std::vector<uint32_t> read_pack_sizes, header_pack_sizes;             // reads per read pack / headers per header pack
+	Block<uint8_t> bases; Block<uint64_t> offsets;                  // reads back to back, offsets[n + 1]
+	Block<uint8_t> quals;                                           // same layout as bases (FASTQ only)
+	Block<uint8_t> headers; Block<uint64_t> header_offsets;         // headers without their first character, header_offsets[n + 1]
+	Block<uint8_t> plus_id;                                         // 1: the '+' line repeats the header (qual_header_type::eq_read_header)
+	Block<uint8_t> has_n;
+	std::vector<uint32_t> read_pack_sizes, header_pack_sizes;       // reads per read pack / headers per header pack
 	uint64_t total_bytes = 0, total_bases = 0, total_symb_header = 0, file_bytes = 0;
+	unsigned threads_used = 1;
 
 	uint32_t n_reads() const { return static_cast<uint32_t>(offsets.size() - 1); }
 
-	explicit CInputReads(const std::string& path)
+	// n_threads 0: CLB_READER_THREADS or the hardware's count; at most one thread per min_piece_bytes of input
+	explicit CInputReads(const std::string& path, unsigned n_threads = 0, uint64_t min_piece_bytes = 16u << 20)
 	{
 		Input in(path, *this);
 		total_bytes = in.n;
 		if (!in.n) throw InputError("Error: file " + path + " is empty");
 		if (in.p[0] != '@' && in.p[0] != '>') throw InputError("Error: unknown file format");
 		is_fastq = in.p[0] == '@';
-		if (is_fastq) parse_fastq(in.p, in.n); else parse_fasta(in.p, in.n);
-		if (cur_reads) read_pack_sizes.push_back(cur_reads);
-		if (cur_headers) header_pack_sizes.push_back(cur_headers);
+		if (!n_threads) { const char* e = std::getenv("CLB_READER_THREADS"); n_threads = e ? static_cast<unsigned>(std::atoi(e)) : std::thread::hardware_concurrency(); }
+		n_threads = static_cast<unsigned>(std::min<uint64_t>(std::max(1u, n_threads), in.n / std::max<uint64_t>(1, min_piece_bytes) + 1));
+		if (!is_fastq) parse_fasta(in.p, in.n);
+		else if (n_threads < 2 || !parse_fastq_threads(in.p, in.n, n_threads)) { reset(); parse_fastq(in.p, in.n); }
+		pack_sizes();
 	}
 
 private:
-	uint64_t cur_read_bytes = 0, cur_header_bytes = 0; uint32_t cur_reads = 0, cur_headers = 0;
-
-	// The file's bytes: plain files are mapped (no copy, no zero-filled buffer: on a 400 MB file the allocation alone cost more
-	// than the parse), gzipped files are inflated into memory.
+	// The file's bytes: plain files are mapped (no copy, no zero-filled buffer), gzipped files are inflated into memory.
 	struct Input {
 		const uint8_t* p = nullptr; uint64_t n = 0;
 		void* map = nullptr; uint64_t map_n = 0; std::vector<uint8_t> buf;
@@ -74,10 +103,10 @@ private:
 			r.is_gzip = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;              // utils.cpp izGzipFile
 			if (!r.is_gzip) {
 				if (r.file_bytes) {
-					map = ::mmap(nullptr, r.file_bytes, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+					map = ::mmap(nullptr, r.file_bytes, PROT_READ, MAP_PRIVATE, fd, 0);
 					if (map == MAP_FAILED) { map = nullptr; ::close(fd); throw InputError("Error: cannot read file: " + path); }
 					map_n = r.file_bytes;
-					::madvise(map, map_n, MADV_SEQUENTIAL);
+					::madvise(map, map_n, MADV_WILLNEED);
 				}
 				::close(fd);
 				p = static_cast<const uint8_t*>(map); n = r.file_bytes;
@@ -103,6 +132,13 @@ private:
 		Input(const Input&) = delete;
 		Input& operator=(const Input&) = delete;
 	};
+
+	void reset()
+	{
+		bases = Block<uint8_t>(); quals = Block<uint8_t>(); headers = Block<uint8_t>(); plus_id = Block<uint8_t>(); has_n = Block<uint8_t>();
+		offsets = Block<uint64_t>(); header_offsets = Block<uint64_t>();
+		total_bases = total_symb_header = 0; threads_used = 1;
+	}
 	static const uint8_t* find_eol(const uint8_t* p, const uint8_t* end)
 	{
 		const uint8_t* e = static_cast<const uint8_t*>(std::memchr(p, '\n', end - p));
@@ -110,17 +146,20 @@ private:
 		const uint8_t* r = static_cast<const uint8_t*>(std::memchr(p, '\r', e - p));
 		return r ? r : e;
 	}
-	void add_header(const uint8_t* s, size_t n, bool plus)
+	// next non-empty line at or after p: [b, e); false at the end of the data.  A last line without an end-of-line has e == end.
+	static bool next_line(const uint8_t*& p, const uint8_t* end, const uint8_t*& b, const uint8_t*& e)
 	{
-		headers.insert(headers.end(), s, s + n);
-		header_offsets.push_back(headers.size());
-		plus_id.push_back(plus ? 1 : 0);
-		cur_header_bytes += n; ++cur_headers;
-		if (cur_header_bytes >= (2u << 21)) { header_pack_sizes.push_back(cur_headers); cur_headers = 0; cur_header_bytes = 0; }
+		while (p < end) {
+			const uint8_t* q = find_eol(p, end);
+			if (q == p) { ++p; continue; }
+			b = p; e = q; p = q < end ? q + 1 : end;
+			return true;
+		}
+		return false;
 	}
-	void add_read(const uint8_t* s, size_t n)
+	// branch-free so that the compiler vectorises it; returns 0 ok, 1 ok with N, 2 a symbol outside ACGTN
+	static uint8_t classify(const uint8_t* s, size_t n)
 	{
-		// branch-free so that the compiler vectorises it: the check must not be what limits the reader
 		uint8_t any_n = 0, bad = 0;
 		for (size_t i = 0; i < n; ++i) {
 			const uint8_t c = s[i];
@@ -128,13 +167,36 @@ private:
 			bad |= static_cast<uint8_t>(!((c == 'A') | (c == 'C') | (c == 'G') | (c == 'T') | is_n));
 			any_n |= is_n;
 		}
-		if (bad) throw InputError("Only ACGTN symbols supported inside a read");
-		bases.insert(bases.end(), s, s + n);
+		return bad ? 2 : any_n;
+	}
+	void pack_sizes()
+	{
+		const uint32_t n = n_reads();
+		uint64_t cur = 0; uint32_t k = 0;
+		for (uint32_t i = 0; i < n; ++i) { cur += offsets[i + 1] - offsets[i] + 1; ++k; if (cur >= (2u << 21)) { read_pack_sizes.push_back(k); k = 0; cur = 0; } }
+		if (k) read_pack_sizes.push_back(k);
+		cur = 0; k = 0;
+		for (uint32_t i = 0; i + 1 < header_offsets.size(); ++i) { cur += header_offsets[i + 1] - header_offsets[i]; ++k; if (cur >= (2u << 21)) { header_pack_sizes.push_back(k); k = 0; cur = 0; } }
+		if (k) header_pack_sizes.push_back(k);
+	}
+
+	// ---- serial parsers: the reference's state machines ----
+	void add_header(const uint8_t* s, size_t n, bool plus)
+	{
+		if (header_offsets.empty()) header_offsets.push_back(0);
+		headers.append(s, n);
+		header_offsets.push_back(headers.size());
+		plus_id.push_back(plus ? 1 : 0);
+	}
+	void add_read(const uint8_t* s, size_t n)
+	{
+		const uint8_t cls = classify(s, n);
+		if (cls == 2) throw InputError("Only ACGTN symbols supported inside a read");
+		if (offsets.empty()) offsets.push_back(0);
+		bases.append(s, n);
 		offsets.push_back(bases.size());
-		has_n.push_back(any_n);
+		has_n.push_back(cls);
 		total_bases += n;
-		cur_read_bytes += n + 1; ++cur_reads;
-		if (cur_read_bytes >= (2u << 21)) { read_pack_sizes.push_back(cur_reads); cur_reads = 0; cur_read_bytes = 0; }
 	}
 	void parse_fastq(const uint8_t* p, uint64_t size)
 	{
@@ -142,27 +204,27 @@ private:
 		bases.reserve(size / 2 + 16); quals.reserve(size / 2 + 16);
 		int where = 0;                                     // 0 header, 1 read, 2 '+' line, 3 quality
 		const uint8_t* hdr = nullptr; size_t hdr_n = 0;
-		while (p < end) {
-			const uint8_t* e = find_eol(p, end);
-			if (e == p) { ++p; continue; }                    // empty line / second byte of a CRLF
+		const uint8_t *b, *e;
+		while (next_line(p, end, b, e)) {
 			if (e == end) throw InputError("Error: something went wrong during input reading");     // no end-of-line after the last line
-			const size_t n = static_cast<size_t>(e - p);
+			const size_t n = static_cast<size_t>(e - b);
 			switch (where) {
-			case 0: total_symb_header += n; hdr = p + 1; hdr_n = n - 1; break;
-			case 1: add_read(p, n); break;
+			case 0: total_symb_header += n; hdr = b + 1; hdr_n = n - 1; break;
+			case 1: add_read(b, n); break;
 			case 2: {
 				total_symb_header += n;
 				const bool plus = n > 1;
-				if (plus && (n - 1 != hdr_n || std::memcmp(p + 1, hdr, hdr_n) != 0)) throw InputError("Error: quality header not empty but different than read header");
+				if (plus && (n - 1 != hdr_n || std::memcmp(b + 1, hdr, hdr_n) != 0)) throw InputError("Error: quality header not empty but different than read header");
 				add_header(hdr, hdr_n, plus);
 				break;
 			}
-			default: quals.insert(quals.end(), p, p + n); break;
+			default: quals.append(b, n); break;
 			}
 			where = (where + 1) & 3;
-			p = e + 1;
 		}
 		if (quals.size() != bases.size() || where != 0) throw InputError("Error: something went wrong during input reading");
+		if (offsets.empty()) offsets.push_back(0);
+		if (header_offsets.empty()) header_offsets.push_back(0);
 	}
 	void parse_fasta(const uint8_t* p, uint64_t size)
 	{
@@ -188,6 +250,100 @@ private:
 			p = e < end ? e + 1 : end;
 		}
 		add_read(read.data(), read.size());                   // in_reads.cpp:173-175: the last read closes at the end of the file
+	}
+
+	// ---- threaded FASTQ parser ----
+	struct Piece { const uint8_t *b, *e; uint64_t n_reads = 0, n_bases = 0, n_quals = 0, n_hdr = 0, symb = 0; bool ok = true; };
+	// first record start after `from`: a line that begins with '@' whose second-next (non-empty) line begins with '+'
+	static const uint8_t* record_start(const uint8_t* from, const uint8_t* end)
+	{
+		const uint8_t* p = find_eol(from, end);                        // skip the line `from` falls into
+		if (p < end) ++p;
+		const uint8_t *b, *e;
+		for (int tries = 0; tries < 16 && next_line(p, end, b, e); ++tries) {
+			if (*b != '@') continue;
+			const uint8_t* q = p; const uint8_t *b1, *e1, *b2, *e2;
+			if (next_line(q, end, b1, e1) && next_line(q, end, b2, e2) && *b2 == '+') return b;
+		}
+		return nullptr;
+	}
+	static void size_piece(Piece& P)
+	{
+		const uint8_t* p = P.b; const uint8_t *b, *e; int where = 0; size_t read_n = 0;
+		while (next_line(p, P.e, b, e)) {
+			const size_t n = static_cast<size_t>(e - b);
+			switch (where) {
+			case 0: if (*b != '@') { P.ok = false; return; } P.symb += n; P.n_hdr += n - 1; break;
+			case 1: P.n_bases += n; read_n = n; ++P.n_reads; break;
+			case 2: if (*b != '+') { P.ok = false; return; } P.symb += n; break;
+			default: if (n != read_n) { P.ok = false; return; } P.n_quals += n; break;
+			}
+			where = (where + 1) & 3;
+		}
+		if (where != 0) P.ok = false;
+	}
+	void fill_piece(Piece& P, uint64_t r0, uint64_t b0, uint64_t h0)
+	{
+		const uint8_t* p = P.b; const uint8_t *b, *e; int where = 0;
+		const uint8_t* hdr = nullptr; size_t hdr_n = 0;
+		uint64_t r = r0, at = b0, hat = h0;
+		while (next_line(p, P.e, b, e)) {
+			const size_t n = static_cast<size_t>(e - b);
+			switch (where) {
+			case 0: hdr = b + 1; hdr_n = n - 1; break;
+			case 1: {
+				const uint8_t cls = classify(b, n);
+				if (cls == 2) { P.ok = false; return; }
+				std::memcpy(bases.data() + at, b, n); has_n[r] = cls; offsets[r + 1] = at + n;
+				break;
+			}
+			case 2: {
+				const bool plus = n > 1;
+				if (plus && (n - 1 != hdr_n || std::memcmp(b + 1, hdr, hdr_n) != 0)) { P.ok = false; return; }
+				std::memcpy(headers.data() + hat, hdr, hdr_n); hat += hdr_n; header_offsets[r + 1] = hat; plus_id[r] = plus ? 1 : 0;
+				break;
+			}
+			default: std::memcpy(quals.data() + at, b, n); at += n; ++r; break;
+			}
+			where = (where + 1) & 3;
+		}
+	}
+	// false: something irregular — the caller falls back to the serial parser
+	bool parse_fastq_threads(const uint8_t* data, uint64_t size, unsigned T)
+	{
+		const uint8_t* end = data + size;
+		if (size == 0 || (end[-1] != '\n' && end[-1] != '\r')) return false;
+		std::vector<Piece> pieces;
+		const uint8_t* at = data;
+		for (unsigned i = 1; i <= T && at < end; ++i) {
+			const uint8_t* nxt = i == T ? end : record_start(data + size / T * i, end);
+			if (!nxt) return false;
+			if (nxt <= at) continue;
+			Piece P; P.b = at; P.e = nxt; pieces.push_back(P);
+			at = nxt;
+		}
+		auto run = [&](auto&& fn) {
+			std::vector<std::thread> th;
+			for (size_t i = 1; i < pieces.size(); ++i) th.emplace_back([&fn, i] { fn(i); });
+			fn(0);
+			for (auto& t : th) t.join();
+		};
+		run([&](size_t i) { size_piece(pieces[i]); });
+		uint64_t nr = 0, nb = 0, nh = 0;
+		std::vector<uint64_t> r0(pieces.size()), b0(pieces.size()), h0(pieces.size());
+		for (size_t i = 0; i < pieces.size(); ++i) {
+			if (!pieces[i].ok || pieces[i].n_quals != pieces[i].n_bases) return false;
+			r0[i] = nr; b0[i] = nb; h0[i] = nh;
+			nr += pieces[i].n_reads; nb += pieces[i].n_bases; nh += pieces[i].n_hdr; total_symb_header += pieces[i].symb;
+		}
+		if (nr >= (1ull << 32)) return false;
+		bases.allocate(nb); quals.allocate(nb); headers.allocate(nh);
+		offsets.allocate(nr + 1); header_offsets.allocate(nr + 1); plus_id.allocate(nr); has_n.allocate(nr);
+		offsets[0] = 0; header_offsets[0] = 0;
+		run([&](size_t i) { fill_piece(pieces[i], r0[i], b0[i], h0[i]); });
+		for (const Piece& P : pieces) if (!P.ok) return false;
+		total_bases = nb; threads_used = static_cast<unsigned>(pieces.size());
+		return true;
 	}
 };
 

@@ -50,6 +50,15 @@ public:
 	{
 		check(ctx, clb_qual_encode(ctx, &prm, quals.data(), offsets.data(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode");
 	}
+	// the same over plain arrays (what the host reader holds)
+	void Compress(const uint8_t* quals, const uint64_t* offsets, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_qual_encode(ctx, &prm, quals, offsets, 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode");
+	}
+	void CompressOriginal(uint32_t data_source, const uint8_t* quals, const uint64_t* offsets, const std::vector<uint32_t>& pack_sizes = {})
+	{
+		check(ctx, clb_qual_encode_original(ctx, data_source, prm.level, quals, offsets, 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_qual_encode_original");
+	}
 	// QualityComprMode::Original (-q org): data_source 0 ONT, 1 PBRaw, 2 PBHiFi (selects the quantiser of the context, quality_coder.cpp:272-505)
 	void CompressOriginal(uint32_t data_source, const std::vector<uint8_t>& quals, const std::vector<uint64_t>& offsets, const std::vector<uint32_t>& pack_sizes = {})
 	{
@@ -97,10 +106,9 @@ public:
 		check(ctx, clb_hdr_encode(ctx, bytes.data(), off.data(), plus.data(), headers.size(), 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
 	}
 	// the same over headers stored back to back (what the host reader produces)
-	void Compress(const std::vector<uint8_t>& bytes, const std::vector<uint64_t>& offsets, const std::vector<uint8_t>& plus_id, const std::vector<uint32_t>& pack_sizes = {})
+	void Compress(const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n_headers, const std::vector<uint32_t>& pack_sizes = {})
 	{
-		check(ctx, clb_hdr_encode(ctx, bytes.data(), offsets.data(), plus_id.empty() ? nullptr : plus_id.data(), offsets.size() - 1, 0,
-			pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
+		check(ctx, clb_hdr_encode(ctx, bytes, offsets, plus_id, n_headers, 0, pack_sizes.empty() ? nullptr : pack_sizes.data(), static_cast<uint32_t>(pack_sizes.size())), "clb_hdr_encode");
 	}
 	std::vector<uint8_t> GetStream() const
 	{

@@ -2,7 +2,7 @@
 //   hdr <stream> <n> <out>                          decoded headers: per header "<plus>\t<bytes>\n"
 //   qavg|qorg <stream> <bases> <offsets> [flags] <out>   bases: ASCII back to back, offsets: u64[n+1], flags: one byte per base
 //   dna <stream> <n_reads> <decisions> <out_bases> <out_offsets> <out_flags>
-//   parse <input> <out_prefix>                      reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
+//   parse <input> <out_prefix> [threads min_piece_bytes]   reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
 #include "../colord_b200/host/decompressor.h"
 #include "../colord_b200/host/fastq_reader.h"
 #include <chrono>
@@ -57,15 +57,15 @@ int main(int argc, char** argv)
 			std::printf("{\"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"seconds\": %.4f, \"GBps\": %.3f}\n", in.n_reads(), in.total_bytes, s, in.total_bytes / s * 1e-9);
 			return 0;
 		}
-		if (cmd == "parse" && argc == 4) {
-			const CInputReads in(argv[2]);
+		if (cmd == "parse" && (argc == 4 || argc == 6)) {
+			const CInputReads in(argv[2], argc == 6 ? static_cast<unsigned>(std::atoi(argv[4])) : 0u, argc == 6 ? std::strtoull(argv[5], nullptr, 10) : (16u << 20));
 			const std::string pre = argv[3];
 			spit(pre + ".bases", in.bases.data(), in.bases.size()); spit(pre + ".offsets", in.offsets.data(), 8 * in.offsets.size());
 			spit(pre + ".quals", in.quals.data(), in.quals.size()); spit(pre + ".headers", in.headers.data(), in.headers.size());
 			spit(pre + ".hoff", in.header_offsets.data(), 8 * in.header_offsets.size()); spit(pre + ".plus", in.plus_id.data(), in.plus_id.size());
 			spit(pre + ".hasn", in.has_n.data(), in.has_n.size());
-			std::printf("{\"is_fastq\": %d, \"is_gzip\": %d, \"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"total_bases\": %" PRIu64 ", \"total_symb_header\": %" PRIu64 ", \"file_bytes\": %" PRIu64 ", \"read_packs\": [",
-				int(in.is_fastq), int(in.is_gzip), in.n_reads(), in.total_bytes, in.total_bases, in.total_symb_header, in.file_bytes);
+			std::printf("{\"threads_used\": %u, \"is_fastq\": %d, \"is_gzip\": %d, \"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"total_bases\": %" PRIu64 ", \"total_symb_header\": %" PRIu64 ", \"file_bytes\": %" PRIu64 ", \"read_packs\": [",
+				in.threads_used, int(in.is_fastq), int(in.is_gzip), in.n_reads(), in.total_bytes, in.total_bases, in.total_symb_header, in.file_bytes);
 			for (size_t i = 0; i < in.read_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.read_pack_sizes[i]);
 			std::printf("], \"header_packs\": [");
 			for (size_t i = 0; i < in.header_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.header_pack_sizes[i]);

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def tool(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("host_decode") / "tool")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", out, os.path.join(ROOT, "tests", "host_decode_tool.cpp"), "-lz"], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", out, os.path.join(ROOT, "tests", "host_decode_tool.cpp"), "-lz", "-pthread"], check=True)
     return out
 
 
@@ -276,3 +276,61 @@ def test_api_surface_on_device_made_archives(tmp_path):
         assert ("reads source: PBRaw" if case.startswith("clr") else "reads source: ONT") in info
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
     assert r.returncode == 1 and "incompatibile archive version" in r.stderr         # a reference archive is refused, not misread
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "blank_lines", "plus_header", "tricky_quals", "gzip"])
+def test_reader_threaded_equals_serial(tool, tmp_path, variant):
+    """The threaded FASTQ parse (pieces cut at record starts) gives exactly the serial parser's arrays, statistics and packs —
+    also when quality lines begin with '@' or '+', the case the record-start rule exists for."""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(400):
+        n = int(rng.integers(1, 300))
+        seq = "".join("ACGTN"[int(x)] for x in rng.choice(5, n, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        q = "".join(chr(int(x)) for x in rng.integers(33, 127, n))
+        if variant == "tricky_quals":
+            q = ("@" if i % 3 == 0 else "+" if i % 3 == 1 else "I") + q[1:]
+        recs.append(("read%d/%d x=@+" % (i, n), seq, q))
+    data = _fastq(recs, eol="\r\n" if variant == "crlf" else "\n", plus_header=range(0, 400, 7) if variant == "plus_header" else ())
+    if variant == "blank_lines":
+        data = data.replace(b"\n@read200", b"\n\n\n@read200").replace(b"\n+\n", b"\n\n+\n", 50)
+    p = str(tmp_path / ("in.fastq.gz" if variant == "gzip" else "in.fastq"))
+    if variant == "gzip":
+        with gzip.open(p, "wb") as f:
+            f.write(data)
+    else:
+        open(p, "wb").write(data)
+    outs = {}
+    for name, threads in (("serial", 1), ("threaded", 7)):
+        r = subprocess.run([tool, "parse", p, str(tmp_path / name), str(threads), "2000"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs[name] = json.loads(r.stdout)
+    assert outs["serial"]["threads_used"] == 1 and outs["threaded"]["threads_used"] >= 4
+    for key in ("n_reads", "total_bytes", "total_bases", "total_symb_header", "read_packs", "header_packs"):
+        assert outs["serial"][key] == outs["threaded"][key], key
+    assert outs["serial"]["n_reads"] == 400
+    for ext in ("bases", "offsets", "quals", "headers", "hoff", "plus", "hasn"):
+        assert open(str(tmp_path / ("serial." + ext)), "rb").read() == open(str(tmp_path / ("threaded." + ext)), "rb").read(), ext
+    assert open(str(tmp_path / "serial.bases"), "rb").read() == "".join(s for _, s, _ in recs).encode()
+    assert open(str(tmp_path / "serial.quals"), "rb").read() == "".join(q for _, _, q in recs).encode()
+
+
+@pytest.mark.parametrize("variant,message", [("bad_symbol", "Only ACGTN symbols supported inside a read"), ("bad_plus", "quality header not empty but different than read header"),
+                                             ("no_final_eol", "something went wrong during input reading"), ("missing_line", "Only ACGTN symbols supported inside a read")])
+def test_reader_threaded_refusals_are_the_serial_ones(tool, tmp_path, variant, message):
+    recs = [("r%d" % i, "ACGT" * 20, "I" * 80) for i in range(300)]
+    data = _fastq(recs)
+    if variant == "bad_symbol":
+        data = data.replace(b"@r250\nACGT", b"@r250\nACgT")
+    elif variant == "bad_plus":
+        data = data.replace(b"@r250\n" + b"ACGT" * 20 + b"\n+\n", b"@r250\n" + b"ACGT" * 20 + b"\n+r251\n")
+    elif variant == "no_final_eol":
+        data = data[:-1]
+    else:
+        data = data.replace(b"@r250\n", b"", 1)
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(data)
+    r = subprocess.run([tool, "parse", p, str(tmp_path / "o"), "6", "2000"], capture_output=True, text=True)
+    assert r.returncode == 1 and message in r.stderr, (r.returncode, r.stderr)
+    r1 = subprocess.run([tool, "parse", p, str(tmp_path / "o1"), "1", "2000"], capture_output=True, text=True)
+    assert (r1.returncode, r1.stderr) == (r.returncode, r.stderr)          # a shifted record reads the next line as the read, as in the reference
