@@ -545,11 +545,13 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (cap > SMEM_TAB_CELLS) { tab_off[i] = tab_total; tab_total += cap; }
 		if (bbits > SMEM_BLOOM_WORDS * 32) { bloom_off[i] = bloom_total; bloom_total += bbits / 32; }
 	}
-	uint64_t* d_tab_off = nullptr; uint64_t* d_bloom_off = nullptr; uint32_t* g_tab = nullptr; uint32_t* g_bloom = nullptr;
+	uint64_t* d_tab_off = nullptr; uint64_t* d_bloom_off = nullptr;
 	CLB_CUDA(c, dev_malloc((void**)&d_tab_off, sizeof(uint64_t) * nb, s));
 	CLB_CUDA(c, dev_malloc((void**)&d_bloom_off, sizeof(uint64_t) * nb, s));
-	CLB_CUDA(c, dev_malloc((void**)&g_tab, sizeof(uint32_t) * (tab_total + 1), s));
-	CLB_CUDA(c, dev_malloc((void**)&g_bloom, sizeof(uint32_t) * (bloom_total + 1), s));
+	// kept from batch to batch, with headroom for the batches to come (batches hold the same number of bases)
+	if (tab_total + 1 > c->s2_gtab.cap) CLB_CUDA(c, c->s2_gtab.reserve(tab_total + tab_total / 4 + 1, s, false));
+	if (bloom_total + 1 > c->s2_gbloom.cap) CLB_CUDA(c, c->s2_gbloom.reserve(bloom_total + bloom_total / 4 + 1, s, false));
+	uint32_t* const g_tab = c->s2_gtab.p; uint32_t* const g_bloom = c->s2_gbloom.p;
 	CLB_CUDA(c, cudaMemcpyAsync(d_tab_off, tab_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemcpyAsync(d_bloom_off, bloom_off.data(), sizeof(uint64_t) * nb, cudaMemcpyHostToDevice, s));
 	// HiFi: anchors from the shared k-mers first; candidates that get some are skipped by the m-mer search
@@ -607,7 +609,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		if (attempt == 2) { st = fail(c, CLB_ERR_CAPACITY, "pair arena did not converge"); break; }
 		cap_pairs = used + 1024;
 	}
-	dev_free_async(d_tab_off, s); dev_free_async(d_bloom_off, s); dev_free_async(g_tab, s); dev_free_async(g_bloom, s);
+	dev_free_async(d_tab_off, s); dev_free_async(d_bloom_off, s);
 	if (st != CLB_OK) return st;
 	if (kanc_slots) {      // the k-mer anchors join the arena behind the pair region
 		kbase = (arena.cap - 64) / PAIR_SLOT_BYTES - kanc_slots - 2;

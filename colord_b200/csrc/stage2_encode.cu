@@ -764,7 +764,12 @@ static clb_status anchor_batch(clb_ctx* c, const S2P& P, uint32_t lo, uint32_t h
 	const uint32_t nb = (uint32_t)h_list.size();
 	if (!nb) return CLB_OK;
 	uint32_t* d_list = nullptr; SegInfo* d_seg = nullptr; uint32_t* d_slot_dec = nullptr; unsigned long long* d_cursor = nullptr; uint32_t* d_acnt = nullptr; uint64_t* d_aoff = nullptr;
-	CLB_CUDA(c, mem.get(&d_list, nb)); CLB_CUDA(c, mem.get(&d_seg, (uint64_t)nb * P.c * 2)); CLB_CUDA(c, mem.get(&d_slot_dec, nb)); CLB_CUDA(c, mem.get(&d_cursor, 2));
+	CLB_CUDA(c, mem.get(&d_list, nb)); CLB_CUDA(c, mem.get(&d_slot_dec, nb)); CLB_CUDA(c, mem.get(&d_cursor, 2));
+	{	// segment records: kept from batch to batch (ctx.h), with headroom
+		const uint64_t seg_bytes = sizeof(SegInfo) * (uint64_t)nb * P.c * 2 + 16;
+		if (seg_bytes > c->s2_segs.cap) CLB_CUDA(c, c->s2_segs.reserve(seg_bytes + seg_bytes / 4, s, false));
+		d_seg = reinterpret_cast<SegInfo*>(c->s2_segs.p);
+	}
 	CLB_CUDA(c, mem.get(&d_acnt, nb)); CLB_CUDA(c, mem.get(&d_aoff, nb));
 	CLB_CUDA(c, cudaMemcpyAsync(d_list, h_list.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * nb, s));
@@ -961,7 +966,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 		if (st != CLB_OK) return st;
 		lo = hi;
 	}
-	c->s2_arena.release();
+	c->s2_arena.release(); c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	{
 		clb_status st = encode_all(c, P, pack_first, h_slot, n_slots);
 		if (st != CLB_OK) return st;
@@ -969,6 +974,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	tr.mark("encode: release");
 	c->enc_done = true;
 	return CLB_OK;
@@ -980,6 +986,7 @@ void s2_free(clb_ctx* c)
 	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
 	c->s2_fork = nullptr;
 	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	if (c->es_off) dev_free(c->es_off, c->stream);
 	if (c->d_ref_to_read) dev_free(c->d_ref_to_read, c->stream);
 	c->es_off = nullptr; c->d_ref_to_read = nullptr;
