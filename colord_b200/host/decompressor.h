@@ -15,8 +15,14 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <exception>
 #include <iostream>
+#include <mutex>
 #include <random>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -121,6 +127,46 @@ inline Pack read_pack(Bytes& in)
 	for (uint32_t l = 0; l < LANES; ++l) p.lane_bytes[l] = in.u32();
 	for (uint32_t l = 0; l < LANES; ++l) p.lane[l] = in.take(p.lane_bytes[l]);
 	return p;
+}
+
+// all packs of a container with the index of their first read
+struct PackAt { Pack pk; uint32_t r0; };
+inline std::vector<PackAt> read_packs(Bytes& in, uint32_t n_packs, uint64_t n_units, const char* what)
+{
+	std::vector<PackAt> v; v.reserve(n_packs);
+	uint64_t r0 = 0;
+	for (uint32_t p = 0; p < n_packs; ++p) {
+		PackAt a{read_pack(in), static_cast<uint32_t>(r0)};
+		if (a.pk.n_reads > n_units - r0) throw DecodeError(std::string("colord-b200: pack sizes of the ") + what + " stream exceed the archive's count");
+		r0 += a.pk.n_reads;
+		v.push_back(a);
+	}
+	if (r0 != n_units) throw DecodeError(std::string("colord-b200: the ") + what + " stream holds fewer records than the archive says");
+	return v;
+}
+// The lanes of a pack (and the packs) are independent streams: fn(unit) for unit in [0, n) on CLB_DECODE_THREADS threads
+// (default: the hardware's count).  The first exception is rethrown on the calling thread.
+template <class Fn>
+inline void parallel_for(uint64_t n, Fn&& fn)
+{
+	unsigned T = std::thread::hardware_concurrency();
+	if (const char* e = std::getenv("CLB_DECODE_THREADS")) T = static_cast<unsigned>(std::atoi(e));
+	T = static_cast<unsigned>(std::min<uint64_t>(std::max(1u, T), n));
+	if (T <= 1) { for (uint64_t i = 0; i < n; ++i) fn(i); return; }
+	std::atomic<uint64_t> next{0}; std::atomic<bool> failed{false};
+	std::exception_ptr err; std::mutex m;
+	auto work = [&] {
+		for (;;) {
+			const uint64_t i = next.fetch_add(1);
+			if (i >= n || failed.load()) return;
+			try { fn(i); } catch (...) { std::lock_guard<std::mutex> g(m); if (!err) err = std::current_exception(); failed.store(true); return; }
+		}
+	};
+	std::vector<std::thread> th;
+	for (unsigned t = 1; t < T; ++t) th.emplace_back(work);
+	work();
+	for (auto& t : th) t.join();
+	if (err) std::rethrow_exception(err);
 }
 
 // ref_reads_accepter.h:27-57 — the decisions are part of the format: the decoder replays them to know which reads became references
@@ -342,13 +388,12 @@ inline std::vector<uint8_t> decode_qual_avg(const uint8_t* data, uint64_t size, 
 	}
 	std::vector<uint8_t> out(reads.bases.size());
 	auto code = [](uint8_t ch) -> uint32_t { return ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0; };
-	std::vector<uint8_t> sym;
-	uint32_t r0 = 0;
-	for (uint32_t p = 0; p < n_packs; ++p) {
-		const Pack pk = read_pack(in);
-		if (pk.n_reads > n_reads - r0) throw DecodeError("colord-b200: quality pack sizes exceed the read count");
-		for (uint32_t l = 0; l < LANES; ++l) {
-			if (l >= pk.n_reads) continue;
+	const std::vector<PackAt> packs = read_packs(in, n_packs, n_reads, "quality");
+	parallel_for(static_cast<uint64_t>(packs.size()) * LANES, [&](uint64_t unit) {
+		const Pack& pk = packs[unit / LANES].pk; const uint32_t r0 = packs[unit / LANES].r0, l = static_cast<uint32_t>(unit % LANES);
+		{
+			if (l >= pk.n_reads) return;
+			std::vector<uint8_t> sym;
 			Bytes s(pk.lane[l], pk.lane_bytes[l]);
 			uint32_t x = s.u32();
 			auto renorm = [&]() { while (x < L) x = (x << 16) | s.u16(); };
@@ -389,9 +434,7 @@ inline std::vector<uint8_t> decode_qual_avg(const uint8_t* data, uint64_t size, 
 				}
 			}
 		}
-		r0 += pk.n_reads;
-	}
-	if (r0 != n_reads) throw DecodeError("colord-b200: quality stream holds fewer reads than the archive says");
+	});
 	return out;
 }
 
@@ -426,14 +469,12 @@ inline std::vector<uint8_t> decode_qual_org(const uint8_t* data, uint64_t size, 
 	M.read_tables(in);
 	auto bsym = [](uint8_t ch) -> uint32_t { return ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0; };
 	std::vector<uint8_t> out(reads.bases.size());
-	uint32_t r0 = 0;
-	for (uint32_t p = 0; p < n_packs; ++p) {
-		const Pack pk = read_pack(in);
-		if (pk.n_reads > n_reads - r0) throw DecodeError("colord-b200: quality pack sizes exceed the read count");
-		RangeDecoder lanes[LANES];
-		for (uint32_t l = 0; l < LANES; ++l) lanes[l].start(pk.lane[l], pk.lane_bytes[l]);
-		for (uint32_t r = r0; r < r0 + pk.n_reads; ++r) {
-			RangeDecoder& d = lanes[(r - r0) % LANES];
+	const std::vector<PackAt> packs = read_packs(in, n_packs, n_reads, "quality");
+	parallel_for(static_cast<uint64_t>(packs.size()) * LANES, [&](uint64_t unit) {
+		const Pack& pk = packs[unit / LANES].pk; const uint32_t r0 = packs[unit / LANES].r0, l = static_cast<uint32_t>(unit % LANES);
+		if (l >= pk.n_reads) return;
+		RangeDecoder d; d.start(pk.lane[l], pk.lane_bytes[l]);
+		for (uint32_t r = r0 + l; r < r0 + pk.n_reads; r += LANES) {
 			const uint64_t o = reads.offsets[r]; const uint32_t n = static_cast<uint32_t>(reads.offsets[r + 1] - o);
 			const uint8_t* b = reads.bases.data() + o; const uint8_t* fl = reads.flags.data() + o;
 			uint32_t pc = 0xff;
@@ -452,9 +493,7 @@ inline std::vector<uint8_t> decode_qual_org(const uint8_t* data, uint64_t size, 
 				pc = ((pc << 4) + quant[s]) & 0xff;
 			}
 		}
-		r0 += pk.n_reads;
-	}
-	if (r0 != n_reads) throw DecodeError("colord-b200: quality stream holds fewer reads than the archive says");
+	});
 	return out;
 }
 

@@ -334,3 +334,20 @@ def test_reader_threaded_refusals_are_the_serial_ones(tool, tmp_path, variant, m
     assert r.returncode == 1 and message in r.stderr, (r.returncode, r.stderr)
     r1 = subprocess.run([tool, "parse", p, str(tmp_path / "o1"), "1", "2000"], capture_output=True, text=True)
     assert (r1.returncode, r1.stderr) == (r.returncode, r.stderr)          # a shifted record reads the next line as the read, as in the reference
+
+
+def test_cli_without_a_gpu_fails_loudly(tmp_path):
+    """No CPU fallback behind the command line either: without a CUDA device compress-* stops with the library's message and
+    exit code 1 (on a GPU box the same command compresses: tests/test_gpu_cli.py); decompress / info need no device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    cli = os.path.join(ROOT, "colord_b200", "colord-b200")
+    if not os.path.exists(cli):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "colord_b200", "csrc")], check=True, capture_output=True)
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(b"@r1\nACGTACGTACGTACGTACGTACGTACGT\n+\nIIIIIIIIIIIIIIIIIIIIIIIIIIII\n")
+    r = subprocess.run([cli, "compress-ont", p, str(tmp_path / "o.colord")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+    r = subprocess.run([cli, "info", os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
+    assert r.returncode == 0 and "total reads: 6" in r.stderr
