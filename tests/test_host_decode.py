@@ -351,3 +351,41 @@ def test_cli_without_a_gpu_fails_loudly(tmp_path):
     assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
     r = subprocess.run([cli, "info", os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
     assert r.returncode == 0 and "total reads: 6" in r.stderr
+
+
+READER_CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "reader_cases.json")))
+
+
+@pytest.mark.parametrize("case", sorted(READER_CASES))
+def test_reader_against_the_reference_binary(tool, tmp_path, case):
+    """Differential test against the UNMODIFIED reference (fixtures by make_reader_golden.py): for every input the reference's
+    `compress-ont -q org` accepts, the reader accepts it too and holds exactly the records the reference's `decompress` writes
+    back; every input the reference refuses is refused, with the reference's message where that message is its reader's.
+    Inputs on which the reference segfaults or aborts on an assertion (truncated records, some blank-line layouts) carry no
+    verdict: there the reader only has to end in a clean accept or refusal."""
+    import base64
+    c = READER_CASES[case]
+    data = base64.b64decode(c["input_b64"])
+    p = str(tmp_path / ("in.fastq.gz" if case == "gzip" else "in.fa" if data[:1] == b">" else "in.fastq"))
+    open(p, "wb").write(data)
+    r, st = _parse(tool, p, str(tmp_path / "o"))
+    if c.get("crashed"):
+        assert r.returncode in (0, 1)
+        return
+    if not c["accepted"]:
+        assert r.returncode == 1, (case, r.stderr)
+        for phrase in ("Only ACGTN symbols supported inside a read", "something went wrong during input reading", "is empty", "unknown file format"):
+            if phrase in c["error"]:
+                assert phrase in r.stderr, (case, r.stderr)
+        return
+    assert r.returncode == 0, (case, r.stderr)
+    bases = open(str(tmp_path / "o.bases"), "rb").read(); quals = open(str(tmp_path / "o.quals"), "rb").read(); hdr = open(str(tmp_path / "o.headers"), "rb").read()
+    off = np.fromfile(str(tmp_path / "o.offsets"), np.uint64); hoff = np.fromfile(str(tmp_path / "o.hoff"), np.uint64); plus = np.fromfile(str(tmp_path / "o.plus"), np.uint8)
+    out = []
+    for i in range(st["n_reads"]):
+        h, s = hdr[int(hoff[i]):int(hoff[i + 1])], bases[int(off[i]):int(off[i + 1])]
+        if st["is_fastq"]:
+            out.append(b"@" + h + b"\n" + s + b"\n+" + (h if plus[i] else b"") + b"\n" + quals[int(off[i]):int(off[i + 1])] + b"\n")
+        else:
+            out.append(b">" + h + b"\n" + s + b"\n")
+    assert b"".join(out) == base64.b64decode(c["output_b64"]), case
