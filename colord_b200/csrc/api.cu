@@ -1,5 +1,6 @@
 // api.cu — the extern "C" boundary (include/colord_b200.h) over the stage implementations.
 #include "ctx.h"
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <cmath>
@@ -44,6 +45,16 @@ clb_status clb_create(const clb_params* p, clb_ctx** out)
 	{	// stream-ordered scratch (cudaMallocAsync) is recycled inside the pool instead of going back to the driver after every sync
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) { unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+	}
+	if (const char* gb = std::getenv("CLB_SLAB_GB")) {      // slab.h: one block per process, kept until clb_release_cached_memory; off unless asked for
+		static std::mutex slab_mutex;
+		std::lock_guard<std::mutex> g(slab_mutex);
+		const uint64_t want = static_cast<uint64_t>(std::atof(gb) * 1073741824.0);
+		if (want && !job_slab().active()) {
+			void* q = nullptr;
+			if (cudaMalloc(&q, want) == cudaSuccess) job_slab().init(reinterpret_cast<uint64_t>(q), want);
+			else cudaGetLastError();                        // not enough memory for the slab: the job runs on cudaMalloc as before
+		}
 	}
 	clb_status st = s1a_init(c);
 	if (st != CLB_OK) { g_create_error = c->err; clb_destroy(c); return st; }
@@ -371,6 +382,7 @@ clb_status clb_release_cached_memory(int device)
 	cudaMemPool_t pool;
 	if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return CLB_ERR_NO_DEVICE;
 	cudaDeviceSynchronize();
+	if (job_slab().active()) { void* q = reinterpret_cast<void*>(job_slab().base()); if (job_slab().reset()) cudaFree(q); }      // only when no context holds blocks of it
 	return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? CLB_OK : CLB_ERR_CUDA;
 }
 

@@ -10,6 +10,7 @@
 #include "../../include/colord_b200.h"
 #include "util.cuh"
 #include "stage2.h"
+#include "slab.h"
 
 namespace clb {
 
@@ -24,15 +25,20 @@ inline BigPtrs& big_ptrs() { static BigPtrs b; return b; }
 inline cudaError_t dev_malloc(void** p, uint64_t bytes, cudaStream_t s)
 {
 	if (bytes < DEV_BIG_BYTES) return cudaMallocAsync(p, bytes ? bytes : 1, s);
+	if (job_slab().active()) {      // CLB_SLAB_GB (slab.h): large blocks are cut from the process's slab, the driver is not called
+		const uint64_t at = job_slab().alloc(bytes);
+		if (at) { *p = reinterpret_cast<void*>(at); return cudaSuccess; }
+	}
 	const cudaError_t e = cudaMalloc(p, bytes);
 	if (e == cudaSuccess) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); b.v.insert(*p); }
 	return e;
 }
 inline bool dev_is_big(void* p) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); return b.v.erase(p) != 0; }
 // semantics of cudaFree: everything the device was doing is finished before the memory is reused
-inline void dev_free(void* p, cudaStream_t s) { if (!p) return; if (dev_is_big(p)) { cudaFree(p); return; } cudaDeviceSynchronize(); cudaFreeAsync(p, s); }
+inline bool slab_free(void* p) { if (!job_slab().owns(reinterpret_cast<uint64_t>(p))) return false; cudaDeviceSynchronize(); job_slab().free(reinterpret_cast<uint64_t>(p)); return true; }
+inline void dev_free(void* p, cudaStream_t s) { if (!p) return; if (slab_free(p)) return; if (dev_is_big(p)) { cudaFree(p); return; } cudaDeviceSynchronize(); cudaFreeAsync(p, s); }
 // stream-ordered free of scratch (a large block is freed by cudaFree, which waits for the device by itself)
-inline cudaError_t dev_free_async(void* p, cudaStream_t s) { if (!p) return cudaSuccess; if (dev_is_big(p)) return cudaFree(p); return cudaFreeAsync(p, s); }
+inline cudaError_t dev_free_async(void* p, cudaStream_t s) { if (!p) return cudaSuccess; if (slab_free(p)) return cudaSuccess; if (dev_is_big(p)) return cudaFree(p); return cudaFreeAsync(p, s); }
 
 // A growable device array, grown geometrically on the ctx stream.
 template <typename T>

@@ -62,3 +62,13 @@ def test_cpp_host_mirror_compiles():
     import subprocess
     src = '#include "colord_b200/host/stage23_host.h"\nint main() { clbhost::CRefReadsAccepter a(7, 1.0, 0); return a.GetNAccepted(100) > 100; }\n'
     subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", ROOT, "-x", "c++", "-"], input=src.encode(), check=True, cwd=ROOT)
+
+
+def test_slab_bookkeeping(tmp_path):
+    """colord_b200/csrc/slab.h (the optional per-process device slab, CLB_SLAB_GB) is pure host bookkeeping: random
+    allocate / free sequences keep its invariants (alignment, no overlap, merging of freed ranges, refusal only when nothing fits)."""
+    import subprocess
+    exe = str(tmp_path / "slabtest")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "host_slab_test.cpp")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "slab ok" in r.stdout, r.stderr
