@@ -59,6 +59,10 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 	adjustKmerAndAnchorLen(kmerLen, anchorLen, in.is_gzip, is_fastq, in.file_bytes);
 	rep.kmerLen = kmerLen; rep.anchorLen = anchorLen;
 	const bool hifi = params.dataSource == DataSource::PBHiFi;
+	if (params.verbose) {
+		std::cerr << (in.is_gzip ? "input is gzipped\n" : "input is not gzipped\n");          // compression.cpp:365-371
+		PrintParams(std::cerr, params, kmerLen, anchorLen, params.nThreads);
+	}
 
 	// stage 1a: the reference reads the file a second time through KMC; here the parsed reads go to the device once
 	CKmerCounter kmer_counter(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi, in.total_bases, params.device);

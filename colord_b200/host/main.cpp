@@ -9,6 +9,7 @@
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <thread>
 #include "compressor.h"
 #include "decompressor.h"
 
@@ -41,6 +42,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	std::string pri = "memory";
 	for (int i = 2; i + 1 < argc; ++i) if (!std::strcmp(argv[i], "-p") || !std::strcmp(argv[i], "--priority")) pri = argv[i + 1];
 	CCompressorParams p = defaultParams(dataSourceFromCommand(cmd), compressionPriorityFromString(pri));
+	p.nThreads = std::max(std::thread::hardware_concurrency(), 1u);          // arg_parse.cpp:105
 	std::vector<std::string> pos;
 	bool qual_set = false; std::vector<uint32_t> fwd_user;
 	for (int i = 2; i < argc; ++i) {
@@ -49,7 +51,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 		if (a == "-p" || a == "--priority") need();
 		else if (a == "-k" || a == "--kmer-len") { p.kmerLen = std::stoul(need()); if (p.kmerLen < 15 || p.kmerLen > 28) throw std::invalid_argument("-k must be in 15..28"); }
 		else if (a == "-a" || a == "--anchor-len") p.anchorLen = std::stoul(need());
-		else if (a == "-t" || a == "--threads") need();
+		else if (a == "-t" || a == "--threads") p.nThreads = std::stoul(need());
 		else if (a == "-q" || a == "--qual") { p.qualityComprMode = qualityComprModeFromString(need()); qual_set = true; }
 		else if (a == "-T" || a == "--qual-thresholds") fwd_user = parse_list(need());
 		else if (a == "-L" || a == "--Lowest-count") p.minKmerCount = std::stoul(need());

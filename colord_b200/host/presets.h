@@ -8,6 +8,7 @@
 // Checked against what the unmodified reference prints under -v (tests/test_host_presets.py).  Header-only.
 #pragma once
 #include <cstdint>
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@ struct CCompressorParams {
 	double sparseMode_range_symbols = 1, sparseMode_exponent = 1.0;
 	uint32_t minAnchors = 1;
 	bool verbose = false;
+	uint32_t nThreads = 0;                                 // accepted and printed as the reference does; the device path does not use it
 	std::string refGenomePath; bool storeRefGenome = false;
 	int device = 0;                                        // CUDA device ordinal (no counterpart in the reference)
 };
@@ -104,6 +106,24 @@ inline CCompressorParams defaultParams(DataSource src, CompressionPriority pri)
 	p.qualityComprMode = src == DataSource::ONT ? QualityComprMode::QuadAverage : src == DataSource::PBRaw ? QualityComprMode::None : QualityComprMode::QuinaryAverage;
 	defaultQualityThresholds(p.qualityComprMode, p.qualityFwdThresholds, p.qualityRevThresholds);
 	return p;
+}
+
+// compression.cpp:165-207 (PrintParams): the parameter block the reference prints under -v, same lines and wording
+inline void PrintParams(std::ostream& os, const CCompressorParams& p, uint32_t kmerLen, uint32_t anchorLen, unsigned nThreads)
+{
+	auto list = [](const std::vector<uint32_t>& v) { std::string r; for (uint32_t x : v) r += " " + std::to_string(x); return r; };      // every value preceded by a blank (arg_parse.cpp vec_to_string)
+	os << " * * * * * * * * * * * * Parameters * * * * * * * * * * * * \n";
+	os << "\tinput file path: " << p.inputFilePath << "\n\toutput file path: " << p.outputFilePath << "\n\tnumber of threads: " << nThreads << "\n";
+	os << "\tk-mer length: " << kmerLen << "\n\tanchor length: " << anchorLen << "\n\tdata source type: " << dataSourceToString(p.dataSource) << "\n";
+	os << "\tmultipier for predicted cost of storing read part as edit script: " << p.editScriptCostMultiplier << "\n\tfilter modulo: " << p.filterHashModulo << "\n";
+	os << "\theader compression mode: " << (p.headerComprMode == HeaderComprMode::Original ? "org" : p.headerComprMode == HeaderComprMode::Main ? "main" : "none") << "\n";
+	os << "\tmax candidates: " << p.maxCandidates << "\n\tmin k-mer count: " << p.minKmerCount << "\n\tmax k-mer count: " << p.maxKmerCount << "\n";
+	os << "\tmax matches multiplier: " << p.maxMatchesMultiplier << "\n\tmax recurence: " << p.maxRecurence << "\n\tmin anchors: " << p.minAnchors << "\n";
+	os << "\tmin fraction of m-mers in encode: " << p.minFractionOfMmersInEncode << "\n\tmin fraction of m-mers in encode to always encode: " << p.minFractionOfMmersInEncodeToAlwaysEncode << "\n";
+	os << "\tmin part length to consider alternative reference read: " << p.minPartLenToConsiderAltRead << "\n\tcompression priority: " << compressionPriorityToString(p.priority) << "\n";
+	os << "\tquality compression mode: " << qualityComprModeToString(p.qualityComprMode) << "\n\tquality thresholds: " << list(p.qualityFwdThresholds) << "\n\tquality values: " << list(p.qualityRevThresholds) << "\n";
+	os << "\treference reads mode: " << (p.referenceReadsMode == ReferenceReadsMode::All ? "all" : "sparse") << "\n\tsparse mode exponent: " << p.sparseMode_exponent << "\n\tsparse mode range: " << p.sparseMode_range_symbols << "\n";
+	os << "\tfill factor filtered k-mers: 0.75\n\tfill factor k-mers to reads: 0.8\n";          // the reference's hash-table fill factors; the device tables have their own
 }
 
 // compression.cpp:41-93: the estimate of the number of bases from the file size, then the table

@@ -53,3 +53,35 @@ def test_kmer_length_table(tool, file_bytes, gz, fastq, k, a):
     """compression.cpp:52-92: bases ~ 0.49 x bytes (FASTQ), 0.98 (FASTA), 2.08 / 3.98 when gzipped; 50 GB FASTQ -> k 24, anchors 22."""
     got = json.loads(subprocess.run([tool, "derive", str(file_bytes), str(gz), str(fastq), "1000", "12", "10", "10", "1"], check=True, capture_output=True, text=True).stdout)
     assert (got["kmerLen"], got["anchorLen"]) == (k, a)
+
+
+CLI = os.path.join(ROOT, "colord_b200", "colord-b200")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "colord")
+
+
+def _cli_params_block(args, cwd):
+    if not os.path.exists(CLI):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "colord_b200", "csrc")], check=True, capture_output=True)
+    r = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True)
+    return r.stderr.split("\n")
+
+
+@pytest.mark.parametrize("args", [["compress-ont"], ["compress-pbraw", "-p", "ratio"], ["compress-pbhifi", "-p", "balanced"], ["compress-ont", "-q", "none", "-p", "balanced"],
+                                  ["compress-pbhifi", "-q", "org", "-k", "22", "-a", "19", "-c", "3"]])
+def test_verbose_parameter_block(tmp_path, args):
+    """`colord-b200 compress-* -v` prints the reference's parameter block (PrintParams, compression.cpp:165-207) line for line.
+    The block is printed before the device is touched, so this runs without a GPU (the command then stops at clb_create)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("on a GPU box the command goes on to compress; the block is the same code")
+    open(str(tmp_path / "s.fastq"), "w").write("@r1\n" + "ACGT" * 30 + "\n+\n" + "I" * 120 + "\n")
+    ours = _cli_params_block(args + ["-v", "-t", "3", "s.fastq", "o.colord"], str(tmp_path))[:29]
+    assert ours[0] == "input is not gzipped" and ours[1].startswith(" * * *") and "\tnumber of threads: 3" in ours
+    key = " ".join(args[:1] + (["-p", args[args.index("-p") + 1]] if "-p" in args else ["-p", "memory"]))
+    gold = GOLD["presets"].get(key)
+    if gold and "-q" not in args and "-k" not in args:
+        assert f"\tfilter modulo: {gold['filterHashModulo']}" in ours and f"\tmax k-mer count: {gold['maxKmerCount']}" in ours
+        assert f"\tquality thresholds: {(' ' + gold['qualityFwdThresholds']) if gold['qualityFwdThresholds'] else ''}" in ours
+    if os.path.exists(REF_BIN):
+        ref = subprocess.run([REF_BIN] + args + ["-v", "-t", "3", "s.fastq", "o.colord"], cwd=str(tmp_path), capture_output=True, text=True)
+        assert ours == ref.stderr.split("\n")[:29]
