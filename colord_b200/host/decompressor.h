@@ -193,7 +193,8 @@ class DnaDecoder {
 	static uint32_t n_bits(uint64_t x) { uint32_t r = 0; for (; x; x >>= 1) ++r; return r; }
 public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
-	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions)
+	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
+	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true)
 	{
 		Bytes in(data, size);
 		in.magic("DB01");
@@ -240,7 +241,7 @@ public:
 				else decode_edit_script(d, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t);
 				fl.resize(rd.size(), 0);
 				for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
-				out.flags.insert(out.flags.end(), fl.begin(), fl.end());
+				if (want_flags) out.flags.insert(out.flags.end(), fl.begin(), fl.end());
 				out.offsets.push_back(out.bases.size());
 				if (decisions[r] && flag != 1) refs.push_back(rd);
 			}
@@ -369,6 +370,7 @@ inline std::vector<uint8_t> decode_qual_avg(const uint8_t* data, uint64_t size, 
 	if (nb != 2 && nb != 4 && nb != 5) throw DecodeError("colord-b200: bad quality stream");
 	const uint32_t bps = nb == 2 ? 2 : 3, cb = bps * (nb == 2 ? 6 : 3), cmask = (1u << cb) - 1;
 	if (nr != n_reads || cbits != cb + 8 + (level > 1 ? 2 : 0)) throw DecodeError("colord-b200: quality stream does not fit the archive");
+	if (level > 1 && reads.flags.size() != reads.bases.size()) throw DecodeError("colord-b200: the quality stream needs the per-base flags of the DNA stream");
 	std::vector<uint16_t> mf(nb * 128);
 	for (uint16_t& v : mf) v = in.u16();
 	const uint64_t n_ctx = 1ull << cbits; const uint32_t n_fb = 1u << cb;
@@ -464,6 +466,7 @@ inline std::vector<uint8_t> decode_qual_org(const uint8_t* data, uint64_t size, 
 	const uint32_t source = in.u32(), level = in.u32(); const uint64_t nr = in.u64(); const uint32_t n_packs = in.u32();
 	const uint32_t n_reads = static_cast<uint32_t>(reads.offsets.size() - 1);
 	if (nr != n_reads || source > 2 || level < 1 || level > 3) throw DecodeError("colord-b200: quality stream does not fit the archive");
+	if (level > 1 && reads.flags.size() != reads.bases.size()) throw DecodeError("colord-b200: the quality stream needs the per-base flags of the DNA stream");
 	uint8_t quant[96]; qorg_quantiser(source, level, quant);
 	StaticModel M; M.add(96, 8 + (level >= 3 ? 8 : 7) + (level > 1 ? 2 : 0), 8);
 	M.read_tables(in);
@@ -476,7 +479,7 @@ inline std::vector<uint8_t> decode_qual_org(const uint8_t* data, uint64_t size, 
 		RangeDecoder d; d.start(pk.lane[l], pk.lane_bytes[l]);
 		for (uint32_t r = r0 + l; r < r0 + pk.n_reads; r += LANES) {
 			const uint64_t o = reads.offsets[r]; const uint32_t n = static_cast<uint32_t>(reads.offsets[r + 1] - o);
-			const uint8_t* b = reads.bases.data() + o; const uint8_t* fl = reads.flags.data() + o;
+			const uint8_t* b = reads.bases.data() + o; const uint8_t* fl = level > 1 ? reads.flags.data() + o : nullptr;
 			uint32_t pc = 0xff;
 			for (uint32_t i = 0; i < n; ++i) {
 				uint32_t c = pc, sh = 8;
@@ -579,7 +582,8 @@ struct DecompressedArchive {
 		if (!archive.ReadPart(s_dna, 0, stream, md) || md != n_reads) throw DecodeError("Error: cannot read the DNA stream");
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
 		dec::DnaDecoder dna;
-		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions);
+		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
+		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
 		if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
