@@ -194,7 +194,8 @@ class DnaDecoder {
 public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
 	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
-	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true)
+	// max_bases: what the archive's info record announces; a damaged stream that decodes past it is refused instead of growing without bound
+	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull)
 	{
 		Bytes in(data, size);
 		in.magic("DB01");
@@ -235,10 +236,12 @@ public:
 						len = v + (1u << (nbits - 1));
 					}
 				}
+				if (len > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
 				if (flag == 0) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYM, ctx_symbol << 2); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; }
 				else if (flag == 1) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYMN, ctx_symbol); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; }
 				else decode_edit_script(d, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t);
+				if (rd.size() > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				fl.resize(rd.size(), 0);
 				for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
 				if (want_flags) out.flags.insert(out.flags.end(), fl.begin(), fl.end());
@@ -305,7 +308,8 @@ private:
 			}
 			case 4: {          // anchor: a run of matches
 				uint32_t alen = 0;
-				for (uint32_t part = 0;; ++part) { const uint32_t v = d.get(M, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; }
+				for (uint32_t part = 0;; ++part) { const uint32_t v = d.get(M, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; if (alen > (1u << 30)) throw DecodeError("colord-b200: damaged DNA stream"); }
+				if (alen > o.len) throw DecodeError("colord-b200: damaged DNA stream (anchor longer than its reference read)");
 				for (uint32_t k = 0; k < alen; ++k) { rd.push_back(static_cast<uint8_t>(o.at(pos + static_cast<int>(k)))); fl.push_back(2); }
 				pos += static_cast<int>(alen);
 				for (int i = static_cast<int>(n_s); i > 0; --i) ctx_symbol = (ctx_symbol << 2) + o.at(pos - i);
@@ -583,7 +587,7 @@ struct DecompressedArchive {
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
 		dec::DnaDecoder dna;
 		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
-		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed);
+		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
 		if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");

@@ -389,3 +389,33 @@ def test_reader_against_the_reference_binary(tool, tmp_path, case):
         else:
             out.append(b">" + h + b"\n" + s + b"\n")
     assert b"".join(out) == base64.b64decode(c["output_b64"]), case
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(B200, "expected.json")), reason="device-made archive fixtures not generated yet")
+def test_damaged_archives_never_crash_the_decompressor(tmp_path):
+    """Bytes of device-made archives are overwritten at random places: `decompress` must end — with exit code 1 and a message, or
+    (when the damage hits nothing that is checked) with a file — never with a signal or a hang."""
+    cli = os.path.join(ROOT, "colord_b200", "colord-b200")
+    if not os.path.exists(cli):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "colord_b200", "csrc")], check=True, capture_output=True)
+    rng = np.random.default_rng(11)
+    refused = 0
+    for case in ("ont_default", "ont_org_small", "clr_ratio_none"):
+        data = bytearray(open(os.path.join(B200, case + ".colord"), "rb").read())
+        for trial in range(12):
+            bad = bytearray(data)
+            n_hits = int(rng.integers(1, 6))
+            for _ in range(n_hits):
+                at = int(rng.integers(0, len(bad)))
+                span = int(rng.integers(1, 9))
+                bad[at:at + span] = rng.integers(0, 256, min(span, len(bad) - at), dtype=np.uint8).tobytes()
+            if trial % 4 == 3:
+                bad = bad[:int(rng.integers(8, len(bad)))]          # truncation
+            p = str(tmp_path / "bad.colord")
+            open(p, "wb").write(bytes(bad))
+            r = subprocess.run([cli, "decompress", p, str(tmp_path / "out")], capture_output=True, text=True, timeout=60)
+            assert r.returncode in (0, 1), (case, trial, r.returncode, r.stderr[-200:])
+            refused += r.returncode == 1
+            if r.returncode == 1:
+                assert r.stderr.strip(), (case, trial)
+    assert refused >= 18          # most damage is noticed
