@@ -9,8 +9,7 @@
 // each — and the archive's `info` carries B200_VERSION_MAJOR as its major version: the reference refuses such an archive at
 // its version check (decompression_common.cpp:36-43) instead of misreading it.  Container, `meta` and `info` are the
 // reference's formats (archive_host.h), so `colord info` of the reference prints this archive's record.
-// Not covered (refused with a message): -G reference genomes, the threshold / plain-average quality modes, header modes
-// other than the default.
+// Not covered (refused with a message): -G reference genomes, the threshold / plain-average quality modes.
 #pragma once
 #include <chrono>
 #include <cstdio>
@@ -33,7 +32,6 @@ struct CompressionReport {            // what the reference prints at the end (c
 inline void refuse_unsupported(const CCompressorParams& p)
 {
 	if (!p.refGenomePath.empty()) throw std::invalid_argument("reference-genome mode (-G) is not available in this build");
-	if (p.headerComprMode != HeaderComprMode::Original) throw std::invalid_argument("header modes other than 'org' are not available in this build");
 	switch (p.qualityComprMode) {
 	case QualityComprMode::Original: case QualityComprMode::QuinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::BinaryAverage: case QualityComprMode::None: break;
 	default: throw std::invalid_argument(std::string("quality mode '") + qualityComprModeToString(p.qualityComprMode) + "' is not available in this build (org, 2-avg, 4-avg, 5-avg, none are)");
@@ -111,10 +109,14 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 		archive.AddPart(s_qual, stream, 0);
 	}
 	const int s_header = archive.RegisterStream("header-b200");
-	{
-		CEntrComprHeaders h(kmer_counter);
-		h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
-		const std::vector<uint8_t> stream = h.GetStream();
+	{	// -i none / main store no header bytes, as in the reference (id_coder.cpp:102-110: Encode returns at once for `none`, and
+		// compress_instrument — `main` — is an empty function there); the decompressor prints "@" / "" for every read (:393-396, :588-591)
+		std::vector<uint8_t> stream;
+		if (params.headerComprMode == HeaderComprMode::Original) {
+			CEntrComprHeaders h(kmer_counter);
+			h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
+			stream = h.GetStream();
+		}
 		archive.AddPart(s_header, stream, in.header_offsets.size() - 1);
 	}
 

@@ -590,8 +590,16 @@ struct DecompressedArchive {
 		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
-		if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
-		headers = dec::decode_headers(stream.data(), stream.size(), n_reads);
+		if (meta.headerComprMode == HeaderComprMode::Original) {
+			if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
+			headers = dec::decode_headers(stream.data(), stream.size(), n_reads);
+		} else {	// no header bytes were stored: the reference prints the id "@" for `none` (id_coder.cpp:393-396) and an empty id for `main` (:588-591)
+			for (uint32_t r = 0; r < n_reads; ++r) {
+				if (meta.headerComprMode == HeaderComprMode::None) headers.bytes.push_back('@');
+				headers.offsets.push_back(headers.bytes.size());
+				headers.plus_id.push_back(0);
+			}
+		}
 
 		if (meta.is_fastq) {
 			if (!archive.ReadPart(s_qual, 0, stream, md)) throw DecodeError("Error: cannot read the quality stream");

@@ -4,7 +4,7 @@
 //   colord-b200 decompress <archive> <output>
 //   colord-b200 info <archive>
 // Exit code 1 with a message on stderr for every error, as the reference does.  Options the device path does not implement
-// (-G / -s, the threshold quality modes, -i main / none) are refused with a message instead of being ignored.
+// (-G / -s, the threshold quality modes) are refused with a message instead of being ignored.
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -24,7 +24,7 @@ static void usage()
 		"      -T,--qual-thresholds a,b,..  -L,--Lowest-count N  -H,--Highest-count N  -f,--filter-modulo N  -c,--max-candidates N\n"
 		"      -e,--edit-script-mult X  -r,--max-recurence-level N  --min-to-alt N  --min-mmer-frac X  --min-mmer-force-enc X\n"
 		"      --max-matches-mult X  --min-anchors N  -R,--reference-reads-mode all|sparse  -g,--sparse-range X  -x,--sparse-exponent X\n"
-		"      -t,--threads N (accepted, unused)  -v,--verbose  --device N\n"
+		"      -i,--identifier org|main|none  -t,--threads N (accepted, unused)  -v,--verbose  --device N\n"
 		"  colord-b200 decompress archive output\n"
 		"  colord-b200 info archive\n";
 }
@@ -68,7 +68,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 		else if (a == "-R" || a == "--reference-reads-mode") { const std::string m = need(); if (m != "all" && m != "sparse") throw std::invalid_argument("-R takes all or sparse"); p.referenceReadsMode = m == "all" ? ReferenceReadsMode::All : ReferenceReadsMode::Sparse; }
 		else if (a == "-g" || a == "--sparse-range") p.sparseMode_range_symbols = std::stod(need());
 		else if (a == "-x" || a == "--sparse-exponent") p.sparseMode_exponent = std::stod(need());
-		else if (a == "-i" || a == "--identifier") { const std::string m = need(); p.headerComprMode = m == "org" ? HeaderComprMode::Original : m == "main" ? HeaderComprMode::Main : HeaderComprMode::None; }
+		else if (a == "-i" || a == "--identifier") { const std::string m = need(); if (m != "org" && m != "main" && m != "none") throw std::invalid_argument("-i takes org, main or none"); p.headerComprMode = m == "org" ? HeaderComprMode::Original : m == "main" ? HeaderComprMode::Main : HeaderComprMode::None; }
 		else if (a == "-G" || a == "--reference-genome") p.refGenomePath = need();
 		else if (a == "-s" || a == "--store-reference") p.storeRefGenome = true;
 		else if (a == "-v" || a == "--verbose") p.verbose = true;

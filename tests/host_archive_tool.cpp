@@ -19,7 +19,7 @@ static bool load_records(CArchive& in, CMeta& meta, CInfo& info, std::vector<uin
 	const int s_meta = in.GetStreamId("meta"), s_info = in.GetStreamId("info");
 	if (s_meta < 0 || s_info < 0) return false;
 	if (!in.ReadPart(s_meta, 0, meta_raw, md) || !in.ReadPart(s_info, 0, info_raw, md)) return false;
-	meta.Deserialize(meta_raw, in.GetStreamId("qual") >= 0);
+	meta.Deserialize(meta_raw, in.GetStreamId("qual") >= 0 || in.GetStreamId("qual-b200") >= 0);
 	info.Deserialize(info_raw);
 	return true;
 }
@@ -68,6 +68,27 @@ int main(int argc, char** argv)
 			(void)off;
 			if (!in.ReadPart(s, p, data, md)) return fail("cannot read a part");
 			if (!out.AddPartComplete(s, (int)p, data, md)) return fail("cannot write a part");
+		}
+		return out.Close() ? 0 : fail("close failed");
+	}
+	if (cmd == "set-header-mode") {      // <in> <out> <0|1|2>: the same archive with the header stream emptied and meta.headerComprMode changed
+		if (argc < 5) return fail("set-header-mode needs <in> <out> <mode>");
+		CArchive out(false);
+		if (!out.Open(argv[3])) return fail("cannot create the output");
+		CMeta m; CInfo i; std::vector<uint8_t> mr, ir;
+		if (!load_records(in, m, i, mr, ir)) return fail("no meta / info stream");
+		m.headerComprMode = static_cast<HeaderComprMode>(std::atoi(argv[4]));
+		for (size_t s = 0; s < in.GetNoStreams(); ++s) {
+			const std::string name = in.GetStreamName((int)s);
+			const int id = out.RegisterStream(name);
+			const auto parts = in.Parts((int)s);
+			for (size_t p = 0; p < parts.size(); ++p) {
+				std::vector<uint8_t> d; size_t md = 0;
+				if (!in.ReadPart((int)s, p, d, md)) return fail("cannot read a part");
+				if (name == "header-b200") d.clear();
+				if (name == "meta") d = m.Serialize();
+				out.AddPart(id, d, md);
+			}
 		}
 		return out.Close() ? 0 : fail("close failed");
 	}

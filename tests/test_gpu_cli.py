@@ -58,6 +58,9 @@ CASES = {
     "clr_ratio_none": (lambda: _synthetic(120, "clr", 4), "compress-pbraw", ["-p", "ratio"], "none", False, False),
     "ont_fasta": (lambda: _records("ont", 60), "compress-ont", ["-p", "balanced"], None, True, False),
     "ont_2avg_k18": (lambda: _synthetic(150, "ont", 9), "compress-ont", ["-q", "2-avg", "-k", "18", "-a", "15", "-R", "all"], "2avg", False, False),
+    # -i none / main: the reference stores no header bytes and prints "@@" / "@" (tests/test_host_decode.py::test_header_modes_none_and_main)
+    "ont_hdr_none": (lambda: _records("ont", 30), "compress-ont", ["-i", "none", "-q", "org"], "org", False, False),
+    "ont_hdr_main": (lambda: _records("ont", 30), "compress-ont", ["-i", "main", "-q", "org"], "org", False, False),
 }
 
 
@@ -85,6 +88,9 @@ def test_cli_round_trip(cli, tmp_path, case):
             off = np.concatenate([[0], np.cumsum([len(r[1]) for r in recs])]).astype(np.uint64)
             lossy = oracle_lib.qual_lossy(P, bases, quals, off)
             want = _fastq([(r[0], r[1], lossy[int(off[i]):int(off[i + 1])].tobytes(), None) for i, r in enumerate(recs)], 2, plus)
+    if "-i" in opts:
+        hdr = b"@" if opts[opts.index("-i") + 1] == "none" else b""
+        want = _fastq([(hdr, r[1], r[2], None) for r in recs], 2, False)
     open(inp, "wb").write(data)
     arch, back = str(tmp_path / "a.colord"), str(tmp_path / "back")
     r = subprocess.run([cli, cmd, *opts, inp, arch], capture_output=True, text=True)

@@ -419,3 +419,24 @@ def test_damaged_archives_never_crash_the_decompressor(tmp_path):
             if r.returncode == 1:
                 assert r.stderr.strip(), (case, trial)
     assert refused >= 18          # most damage is noticed
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(B200, "expected.json")), reason="device-made archive fixtures not generated yet")
+@pytest.mark.parametrize("mode,header", [(2, b"@@"), (1, b"@")])
+def test_header_modes_none_and_main(tmp_path, mode, header):
+    """-i none / -i main: no header bytes are stored and every record comes back as "@@" / "@" with an empty '+' line — what the
+    unmodified reference writes for these modes (its `main` coder is an empty function).  The archive is made on the CPU from a
+    device-made fixture by emptying the header stream and changing meta.headerComprMode (tests/host_archive_tool.cpp)."""
+    tool2 = str(tmp_path / "atool")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", tool2, os.path.join(ROOT, "tests", "host_archive_tool.cpp")], check=True)
+    cli = os.path.join(ROOT, "colord_b200", "colord-b200")
+    a = str(tmp_path / "a.colord")
+    subprocess.run([tool2, "set-header-mode", os.path.join(B200, "ont_org_small.colord"), a, str(mode)], check=True)
+    full, got = str(tmp_path / "full"), str(tmp_path / "got")
+    subprocess.run([cli, "decompress", os.path.join(B200, "ont_org_small.colord"), full], check=True)
+    subprocess.run([cli, "decompress", a, got], check=True)
+    want = open(full, "rb").read().split(b"\n")
+    for i in range(0, len(want) - 1, 4):
+        want[i] = header
+        want[i + 2] = b"+"
+    assert open(got, "rb").read() == b"\n".join(want)
