@@ -48,6 +48,9 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 	CArchive archive(false);
 	if (!archive.Open(params.outputFilePath)) throw std::runtime_error("Error: cannot open archive: " + params.outputFilePath);
 	const int s_meta = archive.RegisterStream("meta");
+	auto add_part = [&](int stream_id, const std::vector<uint8_t>& data, size_t metadata) {
+		if (!archive.AddPart(stream_id, data, metadata)) throw std::runtime_error("Error: cannot write to archive: " + params.outputFilePath);
+	};
 
 	CInputReads in(params.inputFilePath);
 	const bool is_fastq = in.is_fastq;
@@ -93,7 +96,7 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 		CEntrComprReads dna(kmer_counter, params.compressionLevel);
 		dna.Compress(in.read_pack_sizes);
 		const std::vector<uint8_t> stream = dna.GetStream();
-		archive.AddPart(s_dna, stream, tot_n_reads);
+		add_part(s_dna, stream, tot_n_reads);
 	}
 	int s_qual = -1;
 	if (is_fastq) {
@@ -106,7 +109,7 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 			else q.Compress(in.quals.data(), in.offsets.data(), in.read_pack_sizes);
 			stream = q.GetStream();
 		}
-		archive.AddPart(s_qual, stream, 0);
+		add_part(s_qual, stream, 0);
 	}
 	const int s_header = archive.RegisterStream("header-b200");
 	{	// -i none / main store no header bytes, as in the reference (id_coder.cpp:102-110: Encode returns at once for `none`, and
@@ -117,7 +120,7 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 			h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
 			stream = h.GetStream();
 		}
-		archive.AddPart(s_header, stream, in.header_offsets.size() - 1);
+		add_part(s_header, stream, in.header_offsets.size() - 1);
 	}
 
 	// `meta` (compression.cpp:705-779)
@@ -129,11 +132,11 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 	meta.qualityRevThresholds.resize(CMeta::n_thresholds(params.qualityComprMode));
 	meta.headerComprMode = params.headerComprMode; meta.referenceReadsMode = params.referenceReadsMode;
 	meta.sparseMode_range = sparseMode_range; meta.sparseMode_exponent = params.sparseMode_exponent;
-	archive.AddPart(s_meta, meta.Serialize(), 0);
+	add_part(s_meta, meta.Serialize(), 0);
 	const int s_info = archive.RegisterStream("info");
 	info.time = static_cast<uint64_t>(std::time(nullptr));
-	archive.AddPart(s_info, info.Serialize(), 0);
-	archive.Close();
+	add_part(s_info, info.Serialize(), 0);
+	if (!archive.Close()) throw std::runtime_error("Error: cannot write to archive: " + params.outputFilePath);
 
 	rep.dna = archive.GetStreamPackedSize(s_dna); rep.qual = s_qual >= 0 ? archive.GetStreamPackedSize(s_qual) : 0; rep.header = archive.GetStreamPackedSize(s_header);
 	rep.meta = archive.GetStreamPackedSize(s_meta); rep.info = archive.GetStreamPackedSize(s_info);
