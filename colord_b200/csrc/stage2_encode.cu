@@ -559,6 +559,170 @@ __global__ void __launch_bounds__(128) k_emit(EmitArgs a)
 	}
 }
 
+// ---- variant (CLB_EMIT_WARP=1; written at the end of round 1 after the GPU budget was spent: NOT yet run on a device, off by default) ----
+// k_emit gives a read to one thread: ncu shows 1.5 of 32 lanes active and every script symbol costs a byte load, a branchy push
+// and a byte store of its own.  Here a read belongs to a warp.  The walk over the node tree is the one of emit_read, executed by
+// all 32 lanes with identical (uniform) state; what changes is the per-symbol work: a script string or a run of plain bases is
+// taken 32 symbols at a time — a ballot marks where runs start, the first segment joins the pending run, every complete run
+// inside the chunk is sized by its lanes (one byte per symbol, or one 4-byte anchor / skip tuple), a warp scan places the bytes
+// and the last segment becomes the pending run.  The chunk rule was checked against the serial push on 20 000 random strings
+// and pending states with a lane-by-lane emulation before it was written down here (profiles/r01_summary.md).
+template <bool W>
+struct WarpOut {
+	uint8_t* p; uint64_t n; uint32_t lane;
+	CLB_D void byte(uint32_t b) { if (W && lane == 0) p[n] = (uint8_t)b; ++n; }
+	CLB_D void len28(uint32_t type, uint32_t v) { if (W && lane == 0) { p[n] = (uint8_t)((type << 4) + (v >> 24)); p[n + 1] = (uint8_t)(v >> 16); p[n + 2] = (uint8_t)(v >> 8); p[n + 3] = (uint8_t)v; } n += 4; }
+	CLB_D void id(uint32_t type, uint32_t x, uint32_t rev) { if (W && lane == 0) { p[n] = (uint8_t)((type << 4) + rev); p[n + 1] = (uint8_t)(x >> 24); p[n + 2] = (uint8_t)(x >> 16); p[n + 3] = (uint8_t)(x >> 8); p[n + 4] = (uint8_t)x; } n += 5; }
+	static CLB_D uint32_t sym_byte(char s)
+	{
+		if (s == 'M') return T_MATCH << 4;
+		if (s == 'D') return T_DEL << 4;
+		if (s == 'X' || s == 'Y' || s == 'Z') return (T_SUB << 4) + (uint32_t)(s - 'X');
+		return (T_INS << 4) + (uint32_t)es_code(s);
+	}
+	static CLB_D bool four(char s, uint32_t rep) { return (s == 'M' && rep >= 15) || (s == 'D' && rep > 16); }
+	CLB_D void run(char s, uint32_t rep)                       // TupleOut::run, the bytes of a short run written side by side
+	{
+		if (four(s, rep)) { len28(s == 'M' ? T_ANCHOR : T_SKIP, rep); return; }
+		if (W) { const uint8_t b = (uint8_t)sym_byte(s); for (uint32_t i = lane; i < rep; i += 32) p[n + i] = b; }
+		n += rep;
+	}
+};
+
+// symbols [0, len) of a string (get(k) = symbol k, called with a lane's own index) through the pending run (ps, pr)
+template <bool W, class Get>
+CLB_D void push_string(WarpOut<W>& o, char& ps, uint32_t& pr, uint32_t len, Get get)
+{
+	const unsigned FULL = 0xffffffffu;
+	const uint32_t lane = o.lane;
+	for (uint32_t k0 = 0; k0 < len; k0 += 32) {
+		const uint32_t n = min(32u, len - k0);
+		const int c = lane < n ? (int)get(k0 + lane) : 0;
+		int prev = __shfl_up_sync(FULL, c, 1);
+		if (lane == 0) prev = pr ? (int)ps : 0;                  // 0 is no script symbol: without a pending run lane 0 starts one
+		const uint32_t mask = __ballot_sync(FULL, lane < n && c != prev);
+		uint32_t lo = 0;
+		if (mask & 1u) { if (pr) o.run(ps, pr); pr = 0; }        // the chunk opens a new run: the pending one is complete
+		else {
+			if (mask == 0) { pr += n; continue; }                 // the whole chunk continues the pending run
+			lo = (uint32_t)__ffs((int)mask) - 1u;
+			pr += lo; o.run(ps, pr); pr = 0;                      // the first segment completes it
+		}
+		const uint32_t m2 = mask & ~((1u << lo) - 1u);           // run starts from lo on (bit lo is set)
+		const uint32_t last_b = 31u - (uint32_t)__clz((int)m2);
+		uint32_t contrib = 0, L = 0; bool f4 = false;
+		if (lane >= lo && lane < n) {
+			const uint32_t upto = lane == 31 ? 0xffffffffu : ((2u << lane) - 1u);
+			const uint32_t b = 31u - (uint32_t)__clz((int)(m2 & upto));
+			const uint32_t above = m2 & ~upto;
+			const uint32_t e = above ? (uint32_t)__ffs((int)above) - 1u : n;
+			if (b != last_b) {                                    // a complete run inside the chunk
+				L = e - b;
+				f4 = WarpOut<W>::four((char)c, L);
+				contrib = f4 ? (lane == b ? 4u : 0u) : 1u;
+			}
+		}
+		uint32_t incl = contrib;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if ((int)lane >= d) incl += v; }
+		const uint32_t total = __shfl_sync(FULL, incl, 31);
+		if (W && contrib) {
+			uint8_t* q = o.p + o.n + (incl - contrib);
+			if (f4) { const uint32_t ty = c == 'M' ? T_ANCHOR : T_SKIP; q[0] = (uint8_t)((ty << 4) + (L >> 24)); q[1] = (uint8_t)(L >> 16); q[2] = (uint8_t)(L >> 8); q[3] = (uint8_t)L; }
+			else q[0] = (uint8_t)WarpOut<W>::sym_byte((char)c);
+		}
+		o.n += total;
+		ps = (char)__shfl_sync(FULL, c, (int)last_b); pr = n - last_b;      // the last segment is the pending run now
+	}
+}
+
+template <bool W>
+__device__ uint64_t emit_read_w(const EmitArgs& a, uint32_t root, uint8_t* dst, uint32_t lane)
+{
+	WarpOut<W> o{dst, 0, lane};
+	struct Frame { uint32_t node, i, last_pos, cur_ref, after_d, open; } st[10];
+	int sp = 1;
+	st[0] = Frame{root, 0, 0, 0, 0, 0};
+	const CandView& V0 = a.cviews[(size_t)root * a.c];
+	const uint32_t main_ref = V0.ref_id;
+	o.id(T_START_ES, main_ref, V0.rev);
+	bool first = true;
+	char ps = 0; uint32_t pr = 0;
+	while (sp > 0) {
+		Frame& f = st[sp - 1];
+		const Node& N = a.nodes[f.node];
+		const CandView& V = a.cviews[(size_t)f.node * a.c + N.level];
+		// the segment header is written when the first symbol arrives (encoder.cpp:1414-1443): same as emit_read
+		auto open = [&]() {
+			if (f.open) return;
+			f.open = 1;
+			if (N.level == 0) { if (V.ref_id != main_ref) o.id(T_ALT, V.ref_id, V.rev); else if (!first) o.byte(T_MAIN << 4); }
+			else { if (V.ref_id != main_ref) o.id(T_ALT, V.ref_id, V.rev); else o.byte(T_MAIN << 4); }
+			ps = 'D'; pr = N.level > 0 ? f.last_pos : 0;
+		};
+		auto push = [&](char s, uint32_t rep) {
+			if (!rep) return;
+			open();
+			if (pr && ps == s) pr += rep;
+			else { if (pr) o.run(ps, pr); ps = s; pr = rep; }
+		};
+		auto flush = [&](uint32_t cur_pos) {
+			if (f.open) { if (pr) o.run(ps, pr); pr = 0; f.last_pos = cur_pos; first = false; f.open = 0; }
+		};
+		if (f.after_d) { const uint32_t d = f.after_d; f.after_d = 0; push('D', d); }
+		const uint32_t n_frag = 2 * N.n_anch + 1;
+		if (f.i >= n_frag) { flush(f.cur_ref); --sp; continue; }
+		const uint32_t i = f.i++;
+		if (i & 1) {
+			const Anchor an = cv_get(a.arena, V, i >> 1);
+			push('M', an.len);
+			f.cur_ref = an.pos_ref + an.len;
+			continue;
+		}
+		const Task& T = a.tasks[N.first_task + (i >> 1)];
+		const bool last = i == n_frag - 1;
+		if (T.decision == D_ES) {
+			push('D', T.lead);
+			if (T.es_len) {
+				open();
+				const char* es = a.esbuf + T.es_off;
+				push_string<W>(o, ps, pr, T.es_len, [&](uint32_t k) { return es[k]; });
+			}
+		} else if (T.decision == D_ALT) {
+			flush(f.cur_ref);
+			if (!last) f.after_d = T.rl;
+			st[sp] = Frame{T.child, 0, 0, 0, 0, 0};
+			++sp;
+		} else {
+			if (T.el) {
+				open();
+				const PackedView e = enc_view(a.R, N.read, T.enc_start);
+				push_string<W>(o, ps, pr, T.el, [&](uint32_t k) { return "ACGT"[e[(int)k] & 3]; });
+			}
+			if (!last) push('D', T.rl);
+		}
+	}
+	return o.n;
+}
+
+template <bool W>
+__global__ void __launch_bounds__(128) k_emit_w(EmitArgs a)
+{
+	const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (i >= a.n_reads) return;                              // whole warps leave together
+	const uint32_t r = a.read_lo + i;
+	const uint32_t root = a.slot_of_read[i];
+	if (!W) {
+		if (a.has_n[r]) { if (lane == 0) { a.kind[i] = 2; a.size[i] = 1 + a.R.rd_len[r]; } return; }
+		if (root == 0xFFFFFFFFu || !a.nodes[root].valid) { if (lane == 0) { a.kind[i] = 1; a.size[i] = 1 + a.R.rd_len[r]; } return; }
+		const uint32_t sz = (uint32_t)emit_read_w<false>(a, root, nullptr, lane);
+		if (lane == 0) { a.kind[i] = 0; a.size[i] = sz; }
+	} else {
+		if (lane == 0) a.es_off[r] = a.base + a.off[i];
+		if (a.kind[i] == 0) emit_read_w<true>(a, root, a.out + a.base + a.off[i], lane);
+	}
+}
+
 // plain reads: start tuple + one plain(base) tuple per symbol (encoder.cpp:663-682)
 __global__ void __launch_bounds__(256) k_emit_plain(EmitArgs a)
 {
@@ -897,13 +1061,17 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 	uint32_t* d_size = nullptr; uint32_t* d_kind = nullptr; uint64_t* d_off = nullptr;
 	CLB_CUDA(c, mem.get(&d_size, nr)); CLB_CUDA(c, mem.get(&d_kind, nr)); CLB_CUDA(c, mem.get(&d_off, nr));
 	EmitArgs ea{lo, nr, d_slot, c->d_has_n, tasks.p, nodes.p, cviews.p, P.c, arena, esbuf.p, R, d_size, d_kind, d_off, c->es_total, nullptr, c->es_off};
-	CLB_TIMED(c, K_EMIT, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	static const bool emit_warp = std::getenv("CLB_EMIT_WARP") != nullptr;      // the warp-per-read variant above; off unless asked for
+	const uint32_t emit_warp_blocks = (uint32_t)(((uint64_t)nr * 32 + 127) / 128);
+	if (emit_warp) CLB_TIMED(c, K_EMIT, (k_emit_w<false><<<emit_warp_blocks, 128, 0, s>>>(ea)));
+	else CLB_TIMED(c, K_EMIT, (k_emit<false><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit<size>");
 	uint64_t total = 0;
 	st = exclusive_scan(c, d_size, nr, d_off, &total); if (st != CLB_OK) return st;
 	CLB_CUDA(c, c->es.reserve(c->es_total + total + 16, s, true, c->es_total));
 	ea.out = c->es.p;
-	CLB_TIMED(c, K_EMIT, (k_emit<true><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
+	if (emit_warp) CLB_TIMED(c, K_EMIT, (k_emit_w<true><<<emit_warp_blocks, 128, 0, s>>>(ea)));
+	else CLB_TIMED(c, K_EMIT, (k_emit<true><<<(nr + 127) / 128, 128, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit<write>");
 	CLB_TIMED(c, K_EMIT, (k_emit_plain<<<nr, 256, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit_plain");
