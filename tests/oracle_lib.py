@@ -306,3 +306,20 @@ def qorg_decode(stream, bases, offsets, es=None, es_off=None):
                            len(offsets) - 1, esp, eop, out)
     assert rc == 0, rc
     return out[:int(offsets[-1])]
+
+
+def dna_encode(level, max_cand, es_list, bases, offsets, is_ref, pack_sizes):
+    """CPU twin of the native DNA container's encoder (oracle/stage3_dna.c: orc_dna_encode) from per-read CompactES byte strings."""
+    L = lib()
+    L.orc_dna_encode.restype = C.c_int64
+    L.orc_dna_encode.argtypes = [C.c_uint32, C.c_uint32, _u8p, _u64p, _u8p, _u64p, _u8p, C.c_uint32, _u32p, C.c_uint32, _u8p, C.c_uint64]
+    es = np.frombuffer(b"".join(es_list), np.uint8).copy()
+    es_off = np.zeros(len(es_list) + 1, np.uint64)
+    es_off[1:] = np.cumsum([len(x) for x in es_list], dtype=np.uint64)
+    cap = int(len(es)) + int(len(bases)) // 2 + (8 << 20)
+    out = np.zeros(cap, np.uint8)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    n = L.orc_dna_encode(level, max_cand, es, es_off, np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(offsets, np.uint64),
+                         np.ascontiguousarray(is_ref, np.uint8), len(es_list), ps, len(ps), out, cap)
+    assert 0 <= n <= cap, n
+    return out[:n].copy()

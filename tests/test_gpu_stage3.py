@@ -97,6 +97,33 @@ def test_dna_stream_round_trip(level, prof):
     assert size < tuples
 
 
+@pytest.mark.xfail(strict=False, reason="the CPU twin of the DNA encoder (oracle/stage3_dna.c: orc_dna_encode) was written after the round's GPU budget "
+                                        "was spent: this is the first device run of the byte comparison")
+@pytest.mark.parametrize("level,prof,c", [(1, "ont", 5), (2, "ont", 8), (3, "clr", 10)])
+def test_dna_stream_equals_cpu_twin(level, prof, c):
+    """Device container == the oracle's twin encoder fed with the device's own (bit-exact) tuples, byte for byte — the same kind of
+    pin the quality and header containers have.  (On the CPU the twin is checked on the reference's tuples through both decoders:
+    tests/test_host_decode.py::test_reference_tuples_through_the_dna_container_on_cpu.)"""
+    s = synth.generate(500, 120000, 2500, seed=70 + level, profile=prof, n_frac=0.02)
+    P = dict(P_BAL, min_part_len_alt=64 if level == 1 else 48, max_recurence=3 if level == 1 else 5)
+    packs = [200, 300]
+    n = s.n_reads
+    with lib.Context(20, 9, 3, 100, c) as ctx:
+        ctx.append_reads(s.bases, s.offsets)
+        ctx.count_finalize()
+        sampled = np.ones(n, np.uint8)
+        ctx.graph_build(sampled)
+        ctx.encode(P, packs)
+        es_off, es = ctx.encoded(n)
+        ctx.dna_encode(level, packs)
+        stream, _ = ctx.dna_stream()
+    has_n = np.array([(s.bases[int(s.offsets[i]):int(s.offsets[i + 1])] == ord("N")).any() for i in range(n)], np.uint8)
+    is_ref = (sampled & (1 - has_n)).astype(np.uint8)
+    es_list = [es[int(es_off[i]):int(es_off[i + 1])].tobytes() for i in range(n)]
+    twin = oracle_lib.dna_encode(level, c, es_list, s.bases, s.offsets, is_ref, packs)
+    assert len(twin) == len(stream) and np.array_equal(twin, stream)
+
+
 def test_dna_stream_size_vs_reference():
     """12 500 synthetic ONT reads / 100 Mbases (BASELINE.md §2 recipe, seed 1) at the compress-ont default (k20 a16 f12 L4 H80 c5
     sparse g=1, level 1): the unmodified reference writes an 18 231 949-byte DNA stream.  The tuples are the

@@ -440,3 +440,24 @@ def test_header_modes_none_and_main(tmp_path, mode, header):
         want[i] = header
         want[i + 2] = b"+"
     assert open(got, "rb").read() == b"\n".join(want)
+
+
+@pytest.mark.parametrize("case", ["ont_mem", "ont_bal", "clr_ratio", "hifi"])
+def test_reference_tuples_through_the_dna_container_on_cpu(golden, tool, tmp_path, case):
+    """The CompactES tuples the UNMODIFIED reference emitted (tests/golden/<case>/es.bin) -> the oracle's twin of the device's DNA
+    encoder -> container "DB01" -> the two independent decoders (oracle/stage3_dna.c, host/decompressor.h) -> the input reads.
+    Closes the loop on the CPU at levels 1, 2 and 3, sparse and all-reference modes, ONT / CLR / HiFi."""
+    g = golden(case)
+    s = g.reads_in
+    packs = g.es_packs if sum(g.es_packs) == s.n_reads else [s.n_reads]
+    stream = oracle_lib.dna_encode(int(g.params["level"]), int(g.params["max_candidates"]), g.es, s.bases, s.offsets, g.is_ref, packs)
+    assert len(stream) < s.n_bases                                        # it is a compressor
+    bases, off = oracle_lib.dna_decode(stream, s.n_reads, g.is_ref, s.n_bases)
+    assert np.array_equal(off, s.offsets) and np.array_equal(bases, s.bases)
+    # the product decoder: decisions = the sampler's answer; reads holding N are dropped from the references inside
+    dec = (g.is_ref | g.has_n).astype(np.uint8)
+    paths = [_write(str(tmp_path / "s"), stream), str(s.n_reads), _write(str(tmp_path / "d"), dec)]
+    ob, oo, of = str(tmp_path / "ob"), str(tmp_path / "oo"), str(tmp_path / "of")
+    subprocess.run([tool, "dna", *paths, ob, oo, of], check=True)
+    assert np.array_equal(np.fromfile(ob, np.uint8), s.bases) and np.array_equal(np.fromfile(oo, np.uint64), s.offsets)
+    assert os.path.getsize(of) == s.n_bases
