@@ -442,14 +442,17 @@ def test_header_modes_none_and_main(tmp_path, mode, header):
     assert open(got, "rb").read() == b"\n".join(want)
 
 
+@pytest.mark.parametrize("ragged", [False, True])
 @pytest.mark.parametrize("case", ["ont_mem", "ont_bal", "clr_ratio", "hifi"])
-def test_reference_tuples_through_the_dna_container_on_cpu(golden, tool, tmp_path, case):
+def test_reference_tuples_through_the_dna_container_on_cpu(golden, tool, tmp_path, case, ragged):
     """The CompactES tuples the UNMODIFIED reference emitted (tests/golden/<case>/es.bin) -> the oracle's twin of the device's DNA
     encoder -> container "DB01" -> the two independent decoders (oracle/stage3_dna.c, host/decompressor.h) -> the input reads.
     Closes the loop on the CPU at levels 1, 2 and 3, sparse and all-reference modes, ONT / CLR / HiFi."""
     g = golden(case)
     s = g.reads_in
     packs = g.es_packs if sum(g.es_packs) == s.n_reads else [s.n_reads]
+    if ragged:                                                            # packs of 1, 63, 64, 65 reads and the rest: lanes with 0, 1 and 2 reads
+        packs = [1, 63, 64, 65, s.n_reads - 193]
     stream = oracle_lib.dna_encode(int(g.params["level"]), int(g.params["max_candidates"]), g.es, s.bases, s.offsets, g.is_ref, packs)
     assert len(stream) < s.n_bases                                        # it is a compressor
     bases, off = oracle_lib.dna_decode(stream, s.n_reads, g.is_ref, s.n_bases)
