@@ -563,7 +563,16 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 #ifdef CLB_ALIGN_TIMING
 		long long tc1 = clock64();
 #endif
-		if (small) n_ops = A.traceback(hpv, hph, (int)cut, (int)el, T, ops, A.scratch + A.lay.tmp);
+		// edlib pads the query to whole words with wildcards and reads the score of prefix c - W in column c, so the EMPTY prefix
+		// (position -1, score |enc|) is a candidate too and comes first: if no prefix beats inserting the whole part,
+		// endLocations[0] = -1, the path is |enc| insertions and ref_end wraps around (edlib.cpp:660-694, edit_script.h:352)
+		if (best >= (int)el) {
+			ref_end = 0xFFFFFFFFu;
+			for (int x = (int)gl; x < (int)el; x += GROUP) ops[x] = 1;
+			n_ops = (int)el;
+			A.gsync();
+		}
+		else if (small) n_ops = A.traceback(hpv, hph, (int)cut, (int)el, T, ops, A.scratch + A.lay.tmp);
 		else n_ops = A.path(e, (int)el, r, T, best, ops);
 #ifdef CLB_ALIGN_TIMING
 		if (gl == 0 && el > 30000) printf("[task] el %u cut %u small %d: sweep %lld path %lld cycles, n_ops %d\n", el, cut, (int)small, tc1 - tc0, clock64() - tc1, n_ops);

@@ -188,77 +188,6 @@ __global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 	if (t == 0) { e.lane_words[li] = nw; e.lane_state[li] = x; }
 }
 
-// ---- variant (CLB_QENC2=1; written at the end of round 1 after the GPU budget was spent: NOT yet run on a device, off by default) ----
-// k_q_encode spends its issue slots 32 times over: all threads of a warp carry the same rANS state through the 32 steps of a
-// chunk (ncu: ~19 warp instructions per symbol).  Here a stream belongs to ONE thread — a CTA of 64 threads is a pack, thread l
-// is lane l — and the warp only cooperates where cooperation pays: in phase A the 32 threads fetch, stream after stream, the
-// table entries of that stream's next 32 symbols (coalesced quality bytes, one packed word of bases, 32 independent 16-byte
-// table loads in flight) into shared memory; in phase B every thread walks its own stream's 32 entries (one LDS.128, the
-// renormalisation test, a multiply-high and a multiply-add per symbol).  Row stride 33 entries: thread t reads entry 33 t + k,
-// which lands the 8 threads of a quarter-warp on 8 different bank quadruples.  Symbol order per stream, words and final state
-// are those of k_q_encode, so k_q_gather and the container do not change.
-constexpr int QE2_STRIDE = 33;
-CLB_D uint32_t rans_step1(uint32_t x, const uint4& fc, uint16_t* w, uint32_t& nw)
-{
-	if (x >= (fc.w << 19)) { w[nw] = (uint16_t)x; ++nw; x >>= 16; }
-	const uint32_t q = __umulhi(x, fc.x) >> (fc.z >> 16);
-	return x + fc.y + q * (fc.z & 0xffffu);
-}
-__global__ void __launch_bounds__(64) k_q_encode2(QArgs a, QEnc e)
-{
-	__shared__ uint4 s_fc[2][32 * QE2_STRIDE];
-	const uint32_t wp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	const uint32_t pk = blockIdx.x;                          // pack within the chunk
-	if (pk >= e.n_packs) return;
-	const unsigned FULL = 0xffffffffu;
-	const uint32_t p = e.pack_lo + pk, l = wp * 32 + t, li = pk * QB_LANES + l;
-	const uint32_t r0 = e.pack_first[p], r1 = e.pack_first[p + 1];
-	uint16_t* w = e.tmp + e.lane_off[li]; uint32_t nw = 0;
-	uint32_t x = QB_L;
-	const QP& P = a.P;
-	uint4* fcs = s_fc[wp];
-	// the stream's position: its current read (reads last to first) and how many of that read's symbols are still to be coded
-	long long r = -1; uint32_t hi = 0;
-	int active = r0 + l < r1;
-	if (active) { r = (long long)(r0 + l) + (long long)((r1 - 1 - (r0 + l)) / QB_LANES) * QB_LANES; hi = a.rd_len[r]; }
-	while (__any_sync(FULL, active)) {
-		// phase A: stream after stream, all threads fetch the entries of its next <= 32 symbols (thread t: the t-th to be coded)
-		for (int s = 0; s < 32; ++s) {
-			if (!__shfl_sync(FULL, active, s)) continue;          // the same answer in every thread
-			const long long rr = __shfl_sync(FULL, r, s);
-			const uint32_t hs = __shfl_sync(FULL, hi, s);
-			const long long j = (long long)hs - 1 - (long long)t;
-			if (j >= 0) {
-				const uint32_t n = a.rd_len[rr]; const uint64_t rs = a.rd_start[rr];
-				const uint8_t* q = a.quals + a.qoff[rr];
-				const uint8_t* fl = a.flags ? a.flags + a.qoff[rr] : nullptr;
-				fcs[s * QE2_STRIDE + t] = a.tab[(size_t)q_context(a, rs, n, q, fl, (uint32_t)j) * P.nb + q_bin(P, q[j] - 33u)];
-			}
-		}
-		__syncwarp();
-		// phase B: every thread codes the chunk of its own stream
-		if (active) {
-			const uint32_t cnt = min(32u, hi);
-			for (uint32_t k = 0; k < cnt; ++k) x = rans_step1(x, fcs[t * QE2_STRIDE + k], w, nw);
-			hi -= cnt;
-			if (hi == 0) {
-				// the read's bin means come first in decoding order -> coded after its symbols, last one first (as in k_q_encode)
-				const uint32_t ns = 2 * P.nb;
-				for (uint32_t k = 0; k < ns; ++k) {
-					const uint32_t m = ns - 1 - k, b = m >> 1;
-					const uint32_t v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
-					const uint4 fc = (m & 1) ? rans_symbol(a2 * (QB_M >> 8), QB_M >> 8) : a.mtab[b * 128 + a1];
-					x = rans_step1(x, fc, w, nw);
-				}
-				r -= QB_LANES;
-				if (r < (long long)(r0 + l)) active = 0; else hi = a.rd_len[r];
-			}
-		}
-		__syncwarp();                                         // the rows are rewritten in the next round
-	}
-	e.lane_words[li] = nw; e.lane_state[li] = x;
-}
-
 // lane streams into the final container: state, then the words in decoding order (last written first); one warp per lane
 __global__ void __launch_bounds__(128) k_q_gather(QEnc e, const uint64_t* __restrict__ dst_off, const uint64_t* __restrict__ pack_hdr_off, uint8_t* __restrict__ out)
 {
@@ -421,9 +350,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
 		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
 		QEnc e{d_pack_first, p0, cp, d_lane_off, d_tmp, d_words, d_state};
-		static const bool qenc2 = std::getenv("CLB_QENC2") != nullptr;       // the thread-per-stream variant above; off unless asked for
-		if (qenc2) CLB_TIMED3(c, K_QUAL, (k_q_encode2<<<cp, 64, 0, s>>>(a, e)));
-		else CLB_TIMED3(c, K_QUAL, (k_q_encode<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e)));
+		CLB_TIMED3(c, K_QUAL, (k_q_encode<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e)));
 		CLB_LAUNCH_CHECK(c, "k_q_encode");
 		tr.mark("k_q_encode");
 		std::vector<uint32_t> words(nl);

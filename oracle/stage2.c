@@ -12,6 +12,7 @@
  */
 #include <stdint.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include <math.h>
 
@@ -195,6 +196,10 @@ static uint32_t script_shw(const uint8_t* ref, int rl, const uint8_t* enc, int e
 	int end = 1; uint32_t best = row[1];
 	for (int j = 2; j <= rl; ++j) if (row[j] < best) { best = row[j]; end = j; }   /* columns 0..rl-1 <-> prefixes of length 1..rl */
 	free(row); free(col);
+	/* edlib pads the query to a multiple of 64 with wildcards and reads the score of target prefix c - W in column c (edlib.cpp:660-674,
+	 * :683-694), so the EMPTY prefix (position -1, score |enc|) takes part, first in the list: when no prefix beats inserting the whole
+	 * query, endLocations[0] = -1 and the path is |enc| insertions (ref_end wraps to 0xFFFFFFFF as in edit_script.h:352) */
+	if (best >= (uint32_t)el) { *ref_end = 0xFFFFFFFFu; for (int i = 0; i < el; ++i) sb_push(es, "ACGT"[enc[i]]); return (uint32_t)el; }
 	*ref_end = (uint32_t)(end - 1);
 	uint8_t* ops = (uint8_t*)malloc((size_t)end + el + 2); int n = 0;
 	edlib_path(enc, el, ref, end, (int)best, ops, &n);

@@ -56,6 +56,16 @@ def cases():
         if kind == 1:
             ref = np.concatenate([ref, rng.integers(0, 4, 500).astype(np.uint8)])
         out.append((kind, ref, enc))
+    # short flanks against unrelated reference symbols: edlib's SHW also scores the EMPTY target prefix (position -1 of its
+    # wildcard-padded query) and lists it first, so a part no prefix aligns to better than |enc| insertions comes out as insertions only
+    for kind in (0, 1):
+        for el in (2, 3, 4, 5, 6, 8, 11):
+            for rl in (2, 3, 4, 7, 16, 40):
+                for _ in range(3):
+                    out.append((kind, rng.integers(0, 4, rl).astype(np.uint8), rng.integers(0, 4, el).astype(np.uint8)))
+        for el in (2, 3, 5):              # no symbol of the part occurs in the reference window at all
+            out.append((kind, np.full(9, 1, np.uint8), np.full(el, 2, np.uint8)))
+            out.append((kind, np.array([0, 1] * 6, np.uint8), np.array([2, 3] * el, np.uint8)[:el]))
     return out, rng
 
 

@@ -323,3 +323,109 @@ def dna_encode(level, max_cand, es_list, bases, offsets, is_ref, pack_sizes):
                          np.ascontiguousarray(is_ref, np.uint8), len(es_list), ps, len(ps), out, cap)
     assert 0 <= n <= cap, n
     return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------- exact (reference-format) streams
+def _split_parts(out, sizes):
+    parts, at = [], 0
+    for s in sizes:
+        parts.append(out[at:at + int(s)].tobytes())
+        at += int(s)
+    return parts
+
+
+def _es_arrays(es_list):
+    n = len(es_list)
+    es_off = np.zeros(n + 1, np.uint64)
+    es_off[1:] = np.cumsum([len(e) for e in es_list])
+    es = np.frombuffer(b"".join(es_list), np.uint8).copy() if n and es_off[-1] else np.zeros(1, np.uint8)
+    return es, es_off
+
+
+def xdna_encode(level, max_cand, es_list, bases, offsets, is_ref, pack_sizes, n_skip=0):
+    """oracle/stage3_exact.c: the reference's `dna` stream parts (list of bytes, one per pack)."""
+    L = lib()
+    L.orc_xdna_encode.restype = C.c_int64
+    L.orc_xdna_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, _u8p, _u64p, _u8p, _u64p, _u8p, C.c_uint32, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p]
+    es, es_off = _es_arrays(es_list)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    sizes = np.zeros(len(ps) + 1, np.uint64)
+    cap = len(es) + 64 * len(ps) + 1024
+    out = np.zeros(cap, np.uint8)
+    n = L.orc_xdna_encode(level, max_cand, n_skip, es, es_off, np.ascontiguousarray(bases), np.ascontiguousarray(offsets, np.uint64),
+                          np.ascontiguousarray(is_ref, np.uint8), len(offsets) - 1, ps, len(ps), out, cap, sizes)
+    assert n >= 0
+    return _split_parts(out, sizes[:len(ps)])
+
+
+QMODES = {"org": 0, "5-avg": 1, "4-avg": 2, "2-avg": 3, "5-fix": 4, "4-fix": 5, "2-fix": 6, "avg": 7, "none": 8}
+
+
+def xqual_encode(mode, source, level, thr, bases, quals, offsets, pack_sizes, es_list=None):
+    """oracle/stage3_exact.c: the reference's `qual` stream parts.  mode: a -q name; source 0 ONT / 1 CLR / 2 HiFi."""
+    L = lib()
+    L.orc_xqual_encode.restype = C.c_int64
+    L.orc_xqual_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _u8p, _u8p, _u64p, _u8p, _u64p, C.c_uint32, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p]
+    n = len(offsets) - 1
+    es, es_off = _es_arrays(es_list if es_list is not None else [bytes([9 << 4])] * n)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    sizes = np.zeros(len(ps) + 1, np.uint64)
+    cap = int(offsets[-1]) * 2 + 64 * len(ps) + 4096
+    out = np.zeros(cap, np.uint8)
+    t = np.zeros(8, np.uint32)
+    t[:len(thr)] = thr
+    r = L.orc_xqual_encode(QMODES[mode], source, level, t, np.ascontiguousarray(bases), np.ascontiguousarray(quals), np.ascontiguousarray(offsets, np.uint64),
+                           es, es_off, n, ps, len(ps), out, cap, sizes)
+    assert r >= 0
+    return _split_parts(out, sizes[:len(ps)])
+
+
+def xhdr_encode(headers, plus, pack_sizes):
+    """oracle/stage3_exact.c: the reference's `header` stream parts.  headers: list of bytes without the leading '@' / '>'."""
+    L = lib()
+    L.orc_xhdr_encode.restype = C.c_int64
+    L.orc_xhdr_encode.argtypes = [_u8p, _u64p, _u8p, C.c_uint32, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p]
+    n = len(headers)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum([len(h) for h in headers])
+    by = np.frombuffer(b"".join(headers), np.uint8).copy() if n and off[-1] else np.zeros(1, np.uint8)
+    ps = np.ascontiguousarray(pack_sizes, np.uint32)
+    sizes = np.zeros(len(ps) + 1, np.uint64)
+    cap = len(by) * 2 + 64 * len(ps) + 4096
+    out = np.zeros(cap, np.uint8)
+    r = L.orc_xhdr_encode(by, off, np.ascontiguousarray(plus, np.uint8), n, ps, len(ps), out, cap, sizes)
+    assert r >= 0
+    return _split_parts(out, sizes[:len(ps)])
+
+
+def read_packs(offsets, limit=2 << 21):
+    """Pack sizes of the reader (in_reads.cpp:62-76: a pack closes once its read_t bytes — length + guard — reach 4 MiB)."""
+    packs, cur, n = [], 0, 0
+    for ln in np.diff(np.asarray(offsets, np.int64)):
+        cur += int(ln) + 1
+        n += 1
+        if cur >= limit:
+            packs.append(n)
+            cur = n = 0
+    if n:
+        packs.append(n)
+    return packs
+
+
+def pipeline(s, p):
+    """Stages 1 + 2 of the oracle on synthetic reads `s` with the parameter dict `p` (keys as in a golden params.txt).
+    -> (CompactES list, is_ref, pack sizes)"""
+    km, ct, st = count_kmers(s.bases, s.offsets, p["k"], p["modulo"], p["min_count"], p["max_count"])
+    off, acc = accepted_kmers(s.bases, s.offsets, p["k"], p["modulo"], km)
+    if p.get("sparse", 1):
+        mean_len = int(st["tot_kmers"] * p["modulo"] / max(1, s.n_reads) + p["k"] - 1)
+        rng = max(1, int(p.get("sparse_g", 1.0) * st["n_unique_counted"] * p["modulo"] / max(1, mean_len)))
+        sampled = sampler(rng, p.get("sparse_exponent", 1.0), 0, s.n_reads)
+    else:
+        sampled = np.ones(s.n_reads, np.uint8)
+    has_n = np.array([(s.bases[int(s.offsets[i]):int(s.offsets[i + 1])] == ord("N")).any() for i in range(s.n_reads)], np.uint8)
+    cand, cn, common = sim_graph(off, acc, has_n, sampled, p["max_candidates"], p["max_count"], hifi=bool(p.get("hifi", 0)))
+    is_ref = (sampled & (1 - has_n)).astype(np.uint8)
+    packs = read_packs(s.offsets)
+    es = encode_reads(s.bases, s.offsets, is_ref, cand, cn, np.array(packs, np.uint32), s2_params(p), common)
+    return es, is_ref, packs
