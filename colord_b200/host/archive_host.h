@@ -145,6 +145,9 @@ public:
 		f = nullptr;
 		return ok;
 	}
+	bool IsOpen() const { std::lock_guard<std::mutex> lck(mtx); return f != nullptr; }
+	// a failed run: close without writing a footer (the caller removes the file)
+	void Abandon() { std::lock_guard<std::mutex> lck(mtx); if (f) { std::fclose(f); f = nullptr; } }
 	int RegisterStream(const std::string& stream_name)
 	{
 		std::lock_guard<std::mutex> lck(mtx);
@@ -250,6 +253,13 @@ struct CInfo {
 	uint64_t time = 0;
 	std::string full_command_line;
 
+	// asctime(localtime(&t)) of the reference (info.cpp:51, colord_api.cpp) for a time taken from a file: localtime has no answer for every 64-bit value
+	static std::string time_string(uint64_t time)
+	{
+		const time_t t = static_cast<time_t>(time); struct tm tmv; char buf[64];
+		if (!localtime_r(&t, &tmv) || !asctime_r(&tmv, buf)) return "(time out of range)\n";
+		return buf;
+	}
 	std::vector<uint8_t> Serialize() const
 	{
 		std::vector<uint8_t> r;
@@ -332,16 +342,18 @@ struct CMeta {
 	{
 		le::Reader in{data.data(), data.data() + data.size()};
 		tot_ref_reads = in.get<uint32_t>(); maxCandidates = in.get<uint32_t>(); compressionLevel = static_cast<int32_t>(in.get<uint32_t>());
-		dataSource = static_cast<DataSource>(in.get<uint8_t>());
+		// enum bytes come from the file: anything outside params.h:33-46 is refused here, before a table is indexed with it
+		auto enum_byte = [&](unsigned n_values, const char* what) { const uint8_t v = in.get<uint8_t>(); if (v >= n_values) throw std::runtime_error(std::string("colord_b200: bad ") + what + " in the meta record"); return v; };
+		dataSource = static_cast<DataSource>(enum_byte(3, "data source"));
 		approx_stream_size = in.get<uint64_t>();
 		is_fastq = archive_has_qual_stream;
 		qualityRevThresholds.clear();
 		if (is_fastq) {
-			qualityComprMode = static_cast<QualityComprMode>(in.get<uint8_t>());
+			qualityComprMode = static_cast<QualityComprMode>(enum_byte(9, "quality mode"));
 			for (size_t i = n_thresholds(qualityComprMode); i; --i) qualityRevThresholds.push_back(in.get<uint32_t>());
 		}
-		headerComprMode = static_cast<HeaderComprMode>(in.get<uint8_t>());
-		referenceReadsMode = static_cast<ReferenceReadsMode>(in.get<uint8_t>());
+		headerComprMode = static_cast<HeaderComprMode>(enum_byte(3, "header mode"));
+		referenceReadsMode = static_cast<ReferenceReadsMode>(enum_byte(2, "reference reads mode"));
 		sparseMode_range = 0; sparseMode_exponent = 0;
 		if (referenceReadsMode == ReferenceReadsMode::Sparse) { sparseMode_range = in.get<uint32_t>(); sparseMode_exponent = in.get_double(); }
 		ref_genome_available = in.get<uint8_t>() != 0;

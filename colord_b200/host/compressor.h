@@ -32,27 +32,43 @@ struct CompressionReport {            // what the reference prints at the end (c
 inline void refuse_unsupported(const CCompressorParams& p)
 {
 	if (!p.refGenomePath.empty()) throw std::invalid_argument("reference-genome mode (-G) is not available in this build");
+	// limits of the device path, checked before any work is done (the C-ABI would refuse them only after stages 1 and 2)
+	if (p.maxCandidates < 1 || p.maxCandidates > 32) throw std::invalid_argument("the number of candidate reads (-c) must be in 1..32 in this build");
+	if (p.compressionLevel < 1 || p.compressionLevel > 3) throw std::invalid_argument("the compression level must be in 1..3");
 	switch (p.qualityComprMode) {
 	case QualityComprMode::Original: case QualityComprMode::QuinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::BinaryAverage: case QualityComprMode::None: break;
 	default: throw std::invalid_argument(std::string("quality mode '") + qualityComprModeToString(p.qualityComprMode) + "' is not available in this build (org, 2-avg, 4-avg, 5-avg, none are)");
 	}
 }
 
+inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive);
+
+// The output is opened only once the input has been read and the parameters accepted, and a run that fails removes what it
+// wrote: no truncated file is left looking like an archive.
 inline CompressionReport runCompression(const CCompressorParams& params, CInfo& info)
 {
-	const auto t0 = std::chrono::steady_clock::now();
 	refuse_unsupported(params);
+	CArchive archive(false);
+	try {
+		return runCompressionTo(params, info, archive);
+	} catch (...) {
+		if (archive.IsOpen()) { archive.Abandon(); std::remove(params.outputFilePath.c_str()); }
+		throw;
+	}
+}
+
+inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive)
+{
+	const auto t0 = std::chrono::steady_clock::now();
 	CompressionReport rep;
 	info.version_major = B200_VERSION_MAJOR; info.version_minor = B200_VERSION_MINOR; info.version_patch = B200_VERSION_PATCH;
 
-	CArchive archive(false);
+	CInputReads in(params.inputFilePath);
 	if (!archive.Open(params.outputFilePath)) throw std::runtime_error("Error: cannot open archive: " + params.outputFilePath);
 	const int s_meta = archive.RegisterStream("meta");
 	auto add_part = [&](int stream_id, const std::vector<uint8_t>& data, size_t metadata) {
 		if (!archive.AddPart(stream_id, data, metadata)) throw std::runtime_error("Error: cannot write to archive: " + params.outputFilePath);
 	};
-
-	CInputReads in(params.inputFilePath);
 	const bool is_fastq = in.is_fastq;
 	info.total_bytes = in.total_bytes; info.total_bases = in.total_bases;
 

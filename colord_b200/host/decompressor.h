@@ -53,9 +53,10 @@ constexpr uint32_t M12 = 4096, LANES = 64;
 struct StaticModel {
 	struct Family { uint32_t A, cbits, fbits; uint64_t base; };
 	std::vector<Family> fam; std::vector<uint16_t> freq;
-	void add(uint32_t A, uint32_t cbits, uint32_t fbits) { const uint64_t b = fam.empty() ? 0 : fam.back().base + (static_cast<uint64_t>(fam.back().A) << fam.back().cbits); fam.push_back(Family{A, cbits, fbits, b}); }
+	void add(uint32_t A, uint32_t cbits, uint32_t fbits) { if (A < 1 || A > 256) throw DecodeError("colord-b200: bad alphabet size"); const uint64_t b = fam.empty() ? 0 : fam.back().base + (static_cast<uint64_t>(fam.back().A) << fam.back().cbits); fam.push_back(Family{A, cbits, fbits, b}); }
 	static void get_freqs(Bytes& in, uint16_t* f, uint32_t A)
 	{
+		if (A > 256) throw DecodeError("colord-b200: bad alphabet size");      // callers hand in uint16_t[256]
 		std::memset(f, 0, 2 * A);
 		if (A <= 8) {
 			const uint8_t mask = in.u8(); int last = -1; uint32_t sum = 0;
@@ -65,7 +66,7 @@ struct StaticModel {
 			if (last >= 0) f[last] = static_cast<uint16_t>(M12 - sum);
 		} else {
 			const uint16_t nz = in.u16(); uint32_t sum = 0;
-			for (uint32_t i = 0; i < nz; ++i) { const uint8_t k = in.u8(); if (k >= A) throw DecodeError("colord-b200: bad frequency table"); f[k] = in.u16(); sum += f[k]; }
+			for (uint32_t i = 0; i < nz; ++i) { const uint32_t k = in.u8(); if (k >= A) throw DecodeError("colord-b200: bad frequency table"); f[k] = in.u16(); sum += f[k]; }
 			if (nz && sum != M12) throw DecodeError("colord-b200: bad frequency table");
 		}
 	}
@@ -195,12 +196,13 @@ public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
 	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
 	// max_bases: what the archive's info record announces; a damaged stream that decodes past it is refused instead of growing without bound
-	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull)
+	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull, uint32_t want_max_cand = 0)
 	{
 		Bytes in(data, size);
 		in.magic("DB01");
 		level = in.u32(); const uint32_t max_cand = in.u32(); const uint64_t nr = in.u64(); const uint32_t n_packs = in.u32(), n_ctx = in.u32();
 		if (nr != n_reads || n_ctx != 0 || level < 1 || level > 3) throw DecodeError("colord-b200: DNA stream does not fit the archive");
+		if (max_cand < 1 || max_cand > 32 || (want_max_cand && max_cand != want_max_cand)) throw DecodeError("colord-b200: DNA stream does not fit the archive (candidate limit)");
 		n_t = level >= 3 ? 4 : level == 2 ? 3 : 2; n_s = level >= 3 ? 8 : level == 2 ? 7 : 5;
 		{	// table widths: colord_b200/csrc/dna_model.h (history widths dna_coder.cpp:1253-1280)
 			const uint32_t A[13] = {3, 32, 256, 4, 5, 256, 2, 8, 24, 256, 256, 2, max_cand < 2 ? 2 : max_cand};
@@ -240,7 +242,7 @@ public:
 				uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
 				if (flag == 0) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYM, ctx_symbol << 2); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; }
 				else if (flag == 1) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYMN, ctx_symbol); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; }
-				else decode_edit_script(d, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t);
+				else decode_edit_script(d, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t, max_bases - std::min<uint64_t>(max_bases, out.bases.size()));
 				if (rd.size() > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				fl.resize(rd.size(), 0);
 				for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
@@ -268,8 +270,10 @@ private:
 		return v;
 	}
 	void decode_edit_script(RangeDecoder& d, uint32_t r, uint32_t n_tuples, const std::vector<std::vector<uint8_t>>& refs, std::vector<uint8_t>& rd, std::vector<uint8_t>& fl,
-		uint64_t ctx_symbol, uint64_t ctx_tuple, uint64_t mask_s, uint64_t mask_t, uint32_t sh_t)
+		uint64_t ctx_symbol, uint64_t ctx_tuple, uint64_t mask_s, uint64_t mask_t, uint32_t sh_t, uint64_t budget)
 	{
+		// budget: bases the archive still announces; checked before anything is appended, so a damaged script cannot grow memory past it
+		auto room = [&](uint64_t k) { if (k > budget || rd.size() > budget - k) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)"); };
 		uint32_t seen_id[34], seen_rev[34], n_seen = 0; uint64_t ctx_rev = 0xf;
 		uint32_t alt_ids[32]; bool alt_revs[32]; int alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;
 		auto get_rev = [&](uint32_t id) -> bool {
@@ -310,13 +314,14 @@ private:
 				uint32_t alen = 0;
 				for (uint32_t part = 0;; ++part) { const uint32_t v = d.get(M, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; if (alen > (1u << 30)) throw DecodeError("colord-b200: damaged DNA stream"); }
 				if (alen > o.len) throw DecodeError("colord-b200: damaged DNA stream (anchor longer than its reference read)");
+				room(alen);
 				for (uint32_t k = 0; k < alen; ++k) { rd.push_back(static_cast<uint8_t>(o.at(pos + static_cast<int>(k)))); fl.push_back(2); }
 				pos += static_cast<int>(alen);
 				for (int i = static_cast<int>(n_s); i > 0; --i) ctx_symbol = (ctx_symbol << 2) + o.at(pos - i);
 				ctx_symbol &= mask_s; delta = 0;
 				break;
 			}
-			case 2: rd.push_back(static_cast<uint8_t>(rsym)); fl.push_back(1); ctx_symbol = ((ctx_symbol << 2) + rsym) & mask_s; ++pos; break;
+			case 2: room(1); rd.push_back(static_cast<uint8_t>(rsym)); fl.push_back(1); ctx_symbol = ((ctx_symbol << 2) + rsym) & mask_s; ++pos; break;
 			case 0: {          // insertion
 				uint64_t c2 = 2; uint32_t sh = 2;
 				if (level <= 1) { c2 += (ctx_symbol & 0xff) << sh; sh += 8; }
@@ -324,7 +329,7 @@ private:
 				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
 				c2 += (ctx_tuple & 0777) << sh;
 				const uint32_t s = d.get(M, F_SYM, c2);
-				rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
+				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
 				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++delta;
 				break;
 			}
@@ -336,7 +341,7 @@ private:
 				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
 				c2 += (ctx_tuple & 07777) << sh;
 				const uint32_t s = d.get(M, F_SYM, c2);
-				rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
+				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
 				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++pos;
 				break;
 			}
@@ -587,7 +592,7 @@ struct DecompressedArchive {
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
 		dec::DnaDecoder dna;
 		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
-		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases);
+		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases, meta.maxCandidates);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
 		if (meta.headerComprMode == HeaderComprMode::Original) {

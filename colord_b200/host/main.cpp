@@ -100,8 +100,7 @@ static int run_info(const std::string& path)
 	// info.cpp:43-53
 	std::cerr << "version major: " << info.version_major << "\nversion minor: " << info.version_minor << "\nversion patch: " << info.version_patch << "\n";
 	std::cerr << "total bytes: " << info.total_bytes << "\ntotal bases: " << info.total_bases << "\ntotal reads: " << info.total_reads << "\n";
-	time_t t = static_cast<time_t>(info.time);
-	std::cerr << "time: " << asctime(localtime(&t)) << "\n" << "command: " << info.full_command_line << "\n";
+	std::cerr << "time: " << CInfo::time_string(info.time) << "\n" << "command: " << info.full_command_line << "\n";
 	return 0;
 }
 

@@ -50,13 +50,13 @@ struct Info {
 		oss << "is fastq: " << std::boolalpha << isFastq << "\n";
 		oss << "colord archive version: " << versionMajor << "." << versionMinor << "." << versionPatch << "\n";
 		oss << "total reads: " << totalReads << "\n";
-		time_t t = static_cast<time_t>(time);
-		oss << "colord archive creaton datetime: " << asctime(localtime(&t));
+		oss << "colord archive creaton datetime: " << clbhost::CInfo::time_string(time);
 		oss << "command line used to create colord archive: " << fullCommandLine << "\n";
 		oss << "compression level: " << compressionLevel << "\n";
-		oss << "reads source: " << src[static_cast<int>(readsSource)] << "\n";
-		oss << "quality compression mode: " << qm[static_cast<int>(qualityCompressionMode)] << "\n";
-		oss << "header compression mode: " << hm[static_cast<int>(headerCompressionMode)] << "\n";
+		auto name = [](const char* const* tab, int n, int v) { return v >= 0 && v < n ? tab[v] : "?"; };
+		oss << "reads source: " << name(src, 3, static_cast<int>(readsSource)) << "\n";
+		oss << "quality compression mode: " << name(qm, 9, static_cast<int>(qualityCompressionMode)) << "\n";
+		oss << "header compression mode: " << name(hm, 3, static_cast<int>(headerCompressionMode)) << "\n";
 		oss << "quality reverse thresholds: ";
 		for (auto v : qualityReverseThresholds) oss << v << " ";
 		oss << "\n";

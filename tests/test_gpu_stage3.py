@@ -97,8 +97,6 @@ def test_dna_stream_round_trip(level, prof):
     assert size < tuples
 
 
-@pytest.mark.xfail(strict=False, reason="the CPU twin of the DNA encoder (oracle/stage3_dna.c: orc_dna_encode) was written after the round's GPU budget "
-                                        "was spent: this is the first device run of the byte comparison")
 @pytest.mark.parametrize("level,prof,c", [(1, "ont", 5), (2, "ont", 8), (3, "clr", 10)])
 def test_dna_stream_equals_cpu_twin(level, prof, c):
     """Device container == the oracle's twin encoder fed with the device's own (bit-exact) tuples, byte for byte — the same kind of

@@ -136,6 +136,20 @@ def test_damaged_streams_are_refused(tool, tmp_path):
     assert subprocess.run([tool, "hdr", s, "51", str(tmp_path / "o")], capture_output=True).returncode == 3
 
 
+def test_crafted_dna_stream_with_oversized_alphabet_is_refused(tool, tmp_path):
+    """A DB01 header announcing max_cand = 1000 would make the short-id family's alphabet larger than the decoder's table scratch:
+    refused at the header (the encoder's own limit is 32), and a script can never append past the archive's base count."""
+    import struct
+    blob = b"DB01" + struct.pack("<IIQII", 1, 1000, 1, 1, 0) + bytes(4096)
+    s = _write(str(tmp_path / "crafted"), np.frombuffer(blob, np.uint8))
+    d = _write(str(tmp_path / "dec"), np.ones(1, np.uint8))
+    r = subprocess.run([tool, "dna", s, "1", d, str(tmp_path / "b"), str(tmp_path / "o"), str(tmp_path / "f")], capture_output=True)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    blob = b"DB01" + struct.pack("<IIQII", 1, 0, 1, 1, 0) + bytes(4096)
+    s = _write(str(tmp_path / "crafted0"), np.frombuffer(blob, np.uint8))
+    assert subprocess.run([tool, "dna", s, "1", d, str(tmp_path / "b"), str(tmp_path / "o"), str(tmp_path / "f")], capture_output=True).returncode == 3
+
+
 # ------------------------------------------------------------------------------------------------------------------ reader
 def _parse(tool, path, prefix):
     r = subprocess.run([tool, "parse", path, prefix], capture_output=True, text=True)
