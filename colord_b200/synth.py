@@ -103,3 +103,108 @@ def generate(n_reads: int, genome_len: int, mean_len: int, seed: int, profile: s
         headers.append(h)
         offsets[i + 1] = offsets[i] + np.uint64(len(out))
     return SynthReads(np.concatenate(seqs), np.concatenate(quals), offsets, headers)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FASTQ files of the BASELINE configurations at file scale (tools/ratio_check.py, bench.py): same error / quality / header
+# model as generate(), read lengths per SURVEY.md §8d (ONT / CLR: gamma(2); HiFi: normal), written by a pool of processes.
+# Deterministic in (profile, n_reads, genome_len, mean_len, seed) — not in the number of workers (chunks are fixed-size).
+# ----------------------------------------------------------------------------------------------------------------------
+_FILE_CHUNK = 2000
+_G = {}
+
+
+def _file_chunk(args):
+    profile, c, n_reads, mean_len, seed = args
+    genome = _G["genome"]
+    G = len(genome)
+    p = PROFILES[profile]
+    e = p["err"]
+    t_sub = p["split"][0] * e
+    t_del = t_sub + p["split"][1] * e
+    qm, qs, qlo, qhi = p["q"]
+    rng = np.random.default_rng([seed, c])
+    lo, hi = c * _FILE_CHUNK, min(n_reads, (c + 1) * _FILE_CHUNK)
+    n = hi - lo
+    if profile == "hifi":
+        lens = np.clip(rng.normal(mean_len, mean_len / 7.5, n), 1000, None).astype(np.int64)
+    else:
+        lens = np.clip(rng.gamma(2.0, mean_len / 2.0, n), 200, 200000).astype(np.int64)
+    lens = np.minimum(lens, G - 1)
+    start = (rng.random(n) * (G - lens)).astype(np.int64)
+    rev = rng.random(n) < 0.5
+    off = np.zeros(n + 1, np.int64)
+    off[1:] = np.cumsum(lens)
+    rid = np.repeat(np.arange(n), lens)
+    within = np.arange(off[-1]) - off[rid]
+    src = np.where(rev[rid], start[rid] + lens[rid] - 1 - within, start[rid] + within)
+    frag = genome[src]
+    frag = np.where(rev[rid], 3 - frag, frag).astype(np.uint8)
+    r = rng.random(len(frag))
+    sub = r < t_sub
+    rep = np.ones(len(frag), np.int64)
+    rep[(r >= t_sub) & (r < t_del)] = 0
+    ins = (r >= t_del) & (r < e)
+    rep[ins] = 2
+    frag[sub] = (frag[sub] + rng.integers(1, 4, int(sub.sum()), dtype=np.uint8)) & 3
+    out = np.repeat(frag, rep)
+    out[np.cumsum(rep)[ins] - 1] = rng.integers(0, 4, int(ins.sum()), dtype=np.uint8)
+    out_len = np.add.reduceat(rep, off[:-1]) if n else np.zeros(0, np.int64)
+    out_len = np.maximum(out_len, 0)
+    if profile == "hifi":      # mostly '~' (93) with dips
+        q = np.full(len(out), 93, np.int64)
+        dip = rng.random(len(out)) < 0.08
+        q[dip] = np.clip(np.rint(rng.normal(40, 20, int(dip.sum()))), 1, 93).astype(np.int64)
+    else:
+        q = np.clip(np.rint(rng.normal(qm, qs, len(out))), qlo, qhi).astype(np.int64)
+    q = (q + 33).astype(np.uint8)
+    asc = _ACGT[out]
+    ooff = np.zeros(n + 1, np.int64)
+    ooff[1:] = np.cumsum(out_len)
+    chs = rng.integers(1, 513, n)
+    parts = []
+    n_bases = 0
+    for j in range(n):
+        i = lo + j
+        a, b = int(ooff[j]), int(ooff[j + 1])
+        if b == a:      # every base deleted: keep the record non-empty
+            continue
+        if profile == "ont":
+            h = b"@read_%d ch=%d start_time=2020-01-01T%02d:%02d:%02dZ\n" % (i, chs[j], (i // 3600) % 24, (i // 60) % 60, i % 60)
+        elif profile == "hifi":
+            h = b"@m64011_190830_220126/%d/ccs\n" % (i * 3 + 17)
+        else:
+            h = b"@m54238_180901_011437/%d/0_%d\n" % (i * 5 + 11, b - a)
+        parts += [h, asc[a:b].tobytes(), b"\n+\n", q[a:b].tobytes(), b"\n"]
+        n_bases += b - a
+    return b"".join(parts), n_bases
+
+
+def generate_file(path: str, profile: str, n_reads: int, genome_len: int, mean_len: int, seed: int, workers: int | None = None, fasta_genome: str | None = None):
+    """Writes a FASTQ of `n_reads` synthetic reads; returns (file bytes, bases).  fasta_genome: also write the genome (for -G)."""
+    import multiprocessing as mp
+    import os
+    _G["genome"] = np.random.default_rng([seed, 1 << 30]).integers(0, 4, genome_len, dtype=np.uint8)
+    if fasta_genome:
+        with open(fasta_genome, "wb") as f:
+            f.write(b">synthetic_genome\n")
+            asc = _ACGT[_G["genome"]]
+            for a in range(0, genome_len, 80 * 100000):
+                blk = asc[a:a + 80 * 100000]
+                rows = [blk[r:r + 80].tobytes() for r in range(0, len(blk), 80)]
+                f.write(b"\n".join(rows) + b"\n")
+    n_chunks = (n_reads + _FILE_CHUNK - 1) // _FILE_CHUNK
+    tasks = [(profile, c, n_reads, mean_len, seed) for c in range(n_chunks)]
+    workers = workers or min(32, os.cpu_count() or 1)
+    total = bases = 0
+    with open(path, "wb") as f:
+        if workers <= 1 or n_chunks <= 1:
+            it = map(_file_chunk, tasks)
+            for blob, nb in it:
+                f.write(blob); total += len(blob); bases += nb
+        else:
+            with mp.get_context("fork").Pool(workers) as pool:      # fork: the genome is shared copy-on-write
+                for blob, nb in pool.imap(_file_chunk, tasks, chunksize=1):
+                    f.write(blob); total += len(blob); bases += nb
+    _G.clear()
+    return total, bases
