@@ -69,7 +69,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
-	c->qs.release(); c->ds.release(); c->hs.release();
+	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release();
 	if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -304,6 +304,46 @@ clb_status clb_hdr_get(clb_ctx* c, uint8_t* stream, uint64_t cap, int on_device)
 	if (cap < c->hs_total) return fail(c, CLB_ERR_CAPACITY, "clb_hdr_get: buffer too small");
 	CLB_CUDA(c, cudaMemcpyAsync(stream, c->hs.p, c->hs_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
 	CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	return CLB_OK;
+}
+clb_status clb_xdna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	return s3x_dna_encode(c, level, pack_sizes, n_packs);
+}
+clb_status clb_xqual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t level, const uint32_t* thr, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	return s3x_qual_encode(c, mode, source, level, thr, quals, offsets, on_device, pack_sizes, n_packs);
+}
+clb_status clb_xhdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
+{
+	CLB_ENTER(c);
+	if (n && (!offsets || !bytes)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return s3x_hdr_encode(c, bytes, offsets, plus_id, n, on_device, pack_sizes, n_packs);
+}
+clb_status clb_xstream_size(clb_ctx* c, uint32_t which, uint64_t* total, uint32_t* n_parts)
+{
+	CLB_ENTER(c);
+	if (which > 2 || !total || !n_parts) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_size: bad argument");
+	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : c->xh_parts;
+	*total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : c->xh_total;
+	*n_parts = (uint32_t)parts.size();
+	return CLB_OK;
+}
+clb_status clb_xstream_get(clb_ctx* c, uint32_t which, uint8_t* bytes, uint64_t cap, uint64_t* part_sizes, int on_device)
+{
+	CLB_ENTER(c);
+	if (which > 2) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_get: bad stream");
+	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : c->xh_parts;
+	const uint64_t total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : c->xh_total;
+	const uint8_t* src = which == 0 ? c->xd.p : which == 1 ? c->xq.p : c->xh.p;
+	if (cap < total) return fail(c, CLB_ERR_CAPACITY, "clb_xstream_get: buffer too small");
+	if (part_sizes) for (size_t i = 0; i < parts.size(); ++i) part_sizes[i] = parts[i];
+	if (total) {
+		CLB_CUDA(c, cudaMemcpyAsync(bytes, src, total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+		CLB_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
 	return CLB_OK;
 }
 clb_status clb_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)

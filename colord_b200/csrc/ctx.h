@@ -180,6 +180,11 @@ struct clb_ctx {
 	bool hdr_done = false;
 	clb::DevBuf<uint8_t> hs;         // native header container
 	uint64_t hs_total = 0, hs_header = 0;
+	// ---- stage 3, compat streams (stage3_exact.cu): the reference's own parts, back to back ----
+	clb::DevBuf<uint8_t> xd, xq, xh;
+	std::vector<uint64_t> xd_parts, xq_parts, xh_parts;      // bytes of every part
+	std::vector<uint64_t> xd_packs, xh_packs;                // reads / headers of every part (the parts' metadata)
+	uint64_t xd_total = 0, xq_total = 0, xh_total = 0;
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)
@@ -231,6 +236,11 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3_qual_flags(clb_ctx* c, const uint64_t* d_qoff, uint32_t n, uint8_t* d_flags);
 clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t level, const uint32_t* thr, const uint8_t* quals, const uint64_t* offsets, int on_device,
+	const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3x_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,
 	const uint64_t* enc_off, const uint32_t* enc_len, const uint32_t* kind, uint64_t n, uint64_t* out_off, char* out, uint64_t cap);

@@ -59,8 +59,10 @@ CLB_D uint32_t ref_sym(const DnaReads& R, const OrientedRef& o, int pos)
 CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[R.first + r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
 
 // The events of read r, in coding order.  ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).
-// sink.put(family, context, symbol)
-template <class Sink>
+// sink.put(family, context, symbol).  EXACT: the events as the reference's adaptive coder sees them (stage3_exact.cu) — the symbols a
+// tuple type / substitution cannot be are handed over as a mask (EncodeExcluding: dna_coder.cpp:651-717, :889-922; sink.putx) and the
+// chunk index of an anchor / local skip length is not capped.
+template <bool EXACT = false, class Sink>
 __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint32_t ctx_read_type, Sink& sink)
 {
 	const uint8_t* t = R.es + R.es_off[R.first + r];
@@ -100,7 +102,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 		ctx_rev = ((ctx_rev << 2) + rev) & 0xf;
 	};
 	auto put_skip = [&](uint32_t len, bool local) {
-		if (local) { for (uint32_t part = 0; len; ++part) { if (len < 255) { sink.put(F_SKIPL, min(part, 63u), len); break; } sink.put(F_SKIPL, min(part, 63u), 255); len -= 254; } }
+		if (local) { for (uint32_t part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 255) { sink.put(F_SKIPL, pc, len); break; } sink.put(F_SKIPL, pc, 255); len -= 254; } }
 		else { uint32_t enc = 0; for (int i = 3; i >= 0; --i) { const uint32_t x = (len >> (8 * i)) & 0xff; sink.put(F_SKIPD, (uint64_t)i * 64 + ilog2_bits(enc), x); enc = (enc << 8) + x; } }
 	};
 	const uint32_t main_id = be32(1), main_rev = t[0] & 15;
@@ -124,7 +126,11 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			uint64_t ctx = ctx_tuple + ((ctx_symbol & 0xf) << sh_t) + ((uint64_t)rsym << (sh_t + 4));
 			const uint32_t bucket = delta < -10 ? 1 : delta < -1 ? 2 : delta > 10 ? 3 : delta > 1 ? 4 : 0;
 			ctx += (uint64_t)bucket << (sh_t + 6);
-			sink.put(F_TUPLE, ctx, ty);
+			if constexpr (EXACT) {
+				const uint32_t excl = last_tuple == 2 ? 1u << 4 : last_tuple == 1 ? 1u << 5 : last_tuple == 4 ? (1u << 4) | (1u << 2)
+					: last_tuple == 5 ? (1u << 1) | (1u << 5) : (last_tuple == 7 || last_tuple == 6) ? (1u << 6) | (1u << 7) : 0u;
+				sink.putx(F_TUPLE, ctx, ty, excl);
+			} else sink.put(F_TUPLE, ctx, ty);
 			ctx_tuple = ((ctx_tuple << 3) + ty) & mask_t;
 		}
 		if (ty == 6) {               // alt_id: v2 = id, v1 = reverse-complement flag
@@ -142,7 +148,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			alt_ref = oriented(R, v2, idx >= 0 ? alt_revs[idx] : v1);
 			alt_pos = 0; is_main = false; delta = 0;
 		} else if (ty == 4) {        // anchor
-			for (uint32_t len = v2, part = 0; len; ++part) { if (len < 23) { sink.put(F_ANCHOR, min(part, 63u), len); break; } sink.put(F_ANCHOR, min(part, 63u), 23); len -= 22; }
+			for (uint32_t len = v2, part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 23) { sink.put(F_ANCHOR, pc, len); break; } sink.put(F_ANCHOR, pc, 23); len -= 22; }
 			int& pos = is_main ? ref_pos : alt_pos;
 			pos += (int)v2;
 			const OrientedRef& o = is_main ? main_ref : alt_ref;
@@ -172,7 +178,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			if (M.level >= 3) { ctx += (uint64_t)(((ctx_symbol >> 6) & 3) == ((ctx_symbol >> 4) & 3)) << sh; ++sh; }
 			ctx += (uint64_t)rsym << sh; sh += 2;
 			ctx += (ctx_tuple & 07777) << sh;
-			sink.put(F_SYM, ctx, symbol);
+			if constexpr (EXACT) sink.putx(F_SYM, ctx, symbol, 1u << b); else sink.put(F_SYM, ctx, symbol);
 			ctx_symbol = ((ctx_symbol << 2) + symbol) & mask_s;
 			is_main ? ++ref_pos : ++alt_pos;
 		} else if (ty == 5) {        // skip (:166-206)

@@ -19,6 +19,7 @@ EXPORTS = [
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
     "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
     "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export", "clb_qual_encode_original", "clb_release_cached_memory",
+    "clb_xdna_encode", "clb_xqual_encode", "clb_xhdr_encode", "clb_xstream_size", "clb_xstream_get",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 
@@ -108,6 +109,11 @@ def load():
     L.clb_qual_encode.argtypes = [vp, C.POINTER(QualParams), vp, vp, i32, vp, u32]
     L.clb_qual_size.argtypes = [vp, C.POINTER(u64)]
     L.clb_qual_get.argtypes = [vp, vp, u64, i32]
+    L.clb_xdna_encode.argtypes = [vp, u32, vp, u32]
+    L.clb_xqual_encode.argtypes = [vp, u32, u32, u32, vp, vp, vp, i32, vp, u32]
+    L.clb_xhdr_encode.argtypes = [vp, vp, vp, vp, u64, i32, vp, u32]
+    L.clb_xstream_size.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u32)]
+    L.clb_xstream_get.argtypes = [vp, u32, vp, u64, vp, i32]
     L.clb_profile_enable.argtypes = [vp, i32]
     L.clb_profile_get.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(u64)]
     for name in EXPORTS:
@@ -461,6 +467,43 @@ class Context:
         out = np.zeros(max(n.value, 1), np.uint8)
         self._ck(self.L.clb_hdr_get(self.h, _np_ptr(out), n.value, 0))
         return out[:n.value], h.value
+
+    # ---- compat streams: the reference's own parts (stage3_exact.cu) ----
+    QMODES = {"org": 0, "5-avg": 1, "4-avg": 2, "2-avg": 3, "5-fix": 4, "4-fix": 5, "2-fix": 6, "avg": 7, "none": 8}
+
+    def xdna_encode(self, level, pack_sizes=None):
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        self._ck(self.L.clb_xdna_encode(self.h, level, None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+        return self.xstream(0)
+
+    def xqual_encode(self, mode, source, level, thresholds, quals, offsets, pack_sizes=None):
+        """mode: a -q name of the reference; source 0 ONT / 1 CLR / 2 HiFi; thresholds: the forward thresholds of the binned modes."""
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        t = np.zeros(8, np.uint32); t[:len(thresholds)] = thresholds
+        q = np.ascontiguousarray(quals, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
+        self._ck(self.L.clb_xqual_encode(self.h, self.QMODES[mode], source, level, _np_ptr(t), _np_ptr(q), _np_ptr(o), 0, None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+        return self.xstream(1)
+
+    def xhdr_encode(self, headers, plus_id=None, pack_sizes=None):
+        b = np.frombuffer(b"".join(headers), np.uint8)
+        o = np.zeros(len(headers) + 1, np.uint64)
+        o[1:] = np.cumsum([len(h) for h in headers], dtype=np.uint64)
+        ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
+        pl = None if plus_id is None else np.ascontiguousarray(plus_id, np.uint8)
+        self._ck(self.L.clb_xhdr_encode(self.h, _np_ptr(b) if len(b) else None, _np_ptr(o), None if pl is None else _np_ptr(pl), len(headers), 0,
+                                        None if ps is None else _np_ptr(ps), 0 if ps is None else len(ps)))
+        return self.xstream(2)
+
+    def xstream(self, which):
+        """-> the parts of compat stream `which` (0 dna, 1 qual, 2 header) as a list of bytes."""
+        n, k = C.c_uint64(), C.c_uint32()
+        self._ck(self.L.clb_xstream_size(self.h, which, C.byref(n), C.byref(k)))
+        out = np.zeros(max(n.value, 1), np.uint8); sizes = np.zeros(max(k.value, 1), np.uint64)
+        self._ck(self.L.clb_xstream_get(self.h, which, _np_ptr(out), n.value, _np_ptr(sizes), 0))
+        parts, at = [], 0
+        for i in range(k.value):
+            parts.append(out[at:at + int(sizes[i])].tobytes()); at += int(sizes[i])
+        return parts
 
     def dna_stream_size(self):
         n, h = C.c_uint64(), C.c_uint64()

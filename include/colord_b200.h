@@ -226,6 +226,25 @@ clb_status clb_hdr_encode(clb_ctx* ctx, const uint8_t* bytes, const uint64_t* of
 clb_status clb_hdr_size(clb_ctx* ctx, uint64_t* total_bytes, uint64_t* table_bytes);
 clb_status clb_hdr_get(clb_ctx* ctx, uint8_t* stream, uint64_t cap, int on_device);
 
+/* ---- Stage 3, compat streams: the reference's own byte streams ------------------------------------
+ * The same three seams (CEntrComprReads / CEntrComprQuals / CEntrComprHeaders::Compress -> CDNACoder / CQualityCoder / CIDCoder::Encode:
+ * entr_read.h:56-80, entr_qual.h:100-126, entr_header.cpp:23-46) with the reference's OWN output: the parts of the "dna", "qual" and
+ * "header" streams of a reference archive, byte for byte (adaptive models rc.h, range coder sub_rc.h; one part per pack, coder
+ * restarted per pack, models kept).  An archive holding these parts is read by the unmodified `colord decompress`.  Every quality
+ * mode of the reference is covered: mode = params.h QualityComprMode (0 org, 1 5-avg, 2 4-avg, 3 2-avg, 4 5-fix, 5 4-fix, 6 2-fix,
+ * 7 avg, 8 none), source = DataSource (0 ONT, 1 PBRaw, 2 PBHiFi; the lossless quantiser), thresholds = the forward thresholds of the
+ * binned modes (arg_parse.cpp:28-84).  pack_sizes: reads (headers) per part; NULL = the reference's pack rule (headers: one part).
+ * Meant for inputs up to a few Gbases per GPU (about 30 bytes of device memory per coded symbol while a stream is built);
+ * CLB_ERR_CAPACITY beyond 2^32 symbols per stream.  Results stay on the device until clb_xstream_get. */
+clb_status clb_xdna_encode(clb_ctx* ctx, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status clb_xqual_encode(clb_ctx* ctx, uint32_t mode, uint32_t source, uint32_t level, const uint32_t* thresholds, const uint8_t* quals, const uint64_t* offsets,
+                            int on_device, const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status clb_xhdr_encode(clb_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n_headers, int on_device,
+                           const uint32_t* pack_sizes, uint32_t n_packs);
+/* which: 0 dna, 1 qual, 2 header.  The parts lie back to back in `bytes`; part_sizes[n_parts] (HOST) receives their lengths. */
+clb_status clb_xstream_size(clb_ctx* ctx, uint32_t which, uint64_t* total_bytes, uint32_t* n_parts);
+clb_status clb_xstream_get(clb_ctx* ctx, uint32_t which, uint8_t* bytes, uint64_t cap, uint64_t* part_sizes, int on_device);
+
 /* ---- Reference-read store (CReferenceReads, reference_reads.h:27) ---------------------------------
  * Read i of the appended input in the reference's byte layout (4 bases/byte MSB first + trailer byte).
  * HOST buffer of (len+3)/4+1 bytes; used by parity tests and by a host-side decoder. */
