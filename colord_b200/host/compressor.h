@@ -9,7 +9,11 @@
 // each — and the archive's `info` carries B200_VERSION_MAJOR as its major version: the reference refuses such an archive at
 // its version check (decompression_common.cpp:36-43) instead of misreading it.  Container, `meta` and `info` are the
 // reference's formats (archive_host.h), so `colord info` of the reference prints this archive's record.
-// Not covered (refused with a message): -G reference genomes, the threshold / plain-average quality modes.
+// Compat mode (--compat, and by default for inputs up to CCompressorParams::compat_max_bases): the three streams are the reference's
+// own ("dna", "qual", "header", one part per pack; clb_x*_encode, colord_b200/csrc/stage3_exact.cu) and `info` carries the
+// reference's version 1.2.1, so the unmodified `colord decompress` reads the archive and its size is the reference's; every quality
+// mode of the reference is available there.
+// Not covered (refused with a message): -G reference genomes; the threshold / plain-average quality modes in native containers.
 #pragma once
 #include <chrono>
 #include <cstdio>
@@ -22,22 +26,24 @@
 
 namespace clbhost {
 
+struct Phase { const char* name; double seconds; };
 struct CompressionReport {            // what the reference prints at the end (compression.cpp:795-808)
+	bool compat = false; std::vector<Phase> phases;
 	uint64_t dna = 0, qual = 0, header = 0, meta = 0, info = 0, archive = 0;
 	uint32_t kmerLen = 0, anchorLen = 0, sparse_range = 0, tot_ref_reads = 0;
 	clb_kmer_stats stats{};
 	double seconds = 0;
 };
 
-inline void refuse_unsupported(const CCompressorParams& p)
+inline void refuse_unsupported(const CCompressorParams& p, bool compat = false)
 {
 	if (!p.refGenomePath.empty()) throw std::invalid_argument("reference-genome mode (-G) is not available in this build");
 	// limits of the device path, checked before any work is done (the C-ABI would refuse them only after stages 1 and 2)
 	if (p.maxCandidates < 1 || p.maxCandidates > 32) throw std::invalid_argument("the number of candidate reads (-c) must be in 1..32 in this build");
 	if (p.compressionLevel < 1 || p.compressionLevel > 3) throw std::invalid_argument("the compression level must be in 1..3");
-	switch (p.qualityComprMode) {
+	if (!compat) switch (p.qualityComprMode) {
 	case QualityComprMode::Original: case QualityComprMode::QuinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::BinaryAverage: case QualityComprMode::None: break;
-	default: throw std::invalid_argument(std::string("quality mode '") + qualityComprModeToString(p.qualityComprMode) + "' is not available in this build (org, 2-avg, 4-avg, 5-avg, none are)");
+	default: throw std::invalid_argument(std::string("quality mode '") + qualityComprModeToString(p.qualityComprMode) + "' is available in compat streams only (--compat; inputs up to a few Gbases): the native containers hold org, 2-avg, 4-avg, 5-avg, none");
 	}
 }
 
@@ -47,7 +53,7 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 // wrote: no truncated file is left looking like an archive.
 inline CompressionReport runCompression(const CCompressorParams& params, CInfo& info)
 {
-	refuse_unsupported(params);
+	refuse_unsupported(params, params.streamFormat != StreamFormat::Native);
 	CArchive archive(false);
 	try {
 		return runCompressionTo(params, info, archive);
@@ -64,6 +70,13 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	info.version_major = B200_VERSION_MAJOR; info.version_minor = B200_VERSION_MINOR; info.version_patch = B200_VERSION_PATCH;
 
 	CInputReads in(params.inputFilePath);
+	const bool compat = params.streamFormat == StreamFormat::Compat || (params.streamFormat == StreamFormat::Auto && in.total_bases <= params.compat_max_bases);
+	refuse_unsupported(params, compat);
+	rep.compat = compat;
+	if (compat) { info.version_major = 1; info.version_minor = 2; info.version_patch = 1; }      // defs.h:24-26 of the reference: what its decompressor checks
+	std::vector<Phase> phases; auto t_ph = std::chrono::steady_clock::now();
+	auto phase = [&](const char* name) { const auto t = std::chrono::steady_clock::now(); phases.push_back(Phase{name, std::chrono::duration<double>(t - t_ph).count()}); t_ph = t; };
+	phase("read input");
 	if (!archive.Open(params.outputFilePath)) throw std::runtime_error("Error: cannot open archive: " + params.outputFilePath);
 	const int s_meta = archive.RegisterStream("meta");
 	auto add_part = [&](int stream_id, const std::vector<uint8_t>& data, size_t metadata) {
@@ -106,37 +119,78 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 		params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
 	encoder.Encode(in.read_pack_sizes);
 
-	// stage 3: one part per stream, metadata = number of reads / headers as in entr_read.h:74, entr_header.cpp:41
-	const int s_dna = archive.RegisterStream("dna-b200");
-	{
-		CEntrComprReads dna(kmer_counter, params.compressionLevel);
-		dna.Compress(in.read_pack_sizes);
-		const std::vector<uint8_t> stream = dna.GetStream();
-		add_part(s_dna, stream, tot_n_reads);
-	}
-	int s_qual = -1;
-	if (is_fastq) {
-		s_qual = archive.RegisterStream("qual-b200");
-		std::vector<uint8_t> stream;
-		if (params.qualityComprMode != QualityComprMode::None) {
-			const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
-			CEntrComprQuals q(kmer_counter, n_bins, params.qualityFwdThresholds, params.compressionLevel);
-			if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals.data(), in.offsets.data(), in.read_pack_sizes);
-			else q.Compress(in.quals.data(), in.offsets.data(), in.read_pack_sizes);
-			stream = q.GetStream();
+	phase("stages 1 + 2");
+	int s_dna = -1, s_qual = -1, s_header = -1;
+	if (compat) {
+		// the reference's own streams: one part per read pack / header pack (entr_read.h:56-80, entr_qual.h:100-126, entr_header.cpp:23-46)
+		auto add_parts = [&](int stream_id, uint32_t which, const std::vector<uint32_t>* metadata) {
+			uint64_t total = 0; uint32_t n_parts = 0;
+			check(ctx, clb_xstream_size(ctx, which, &total, &n_parts), "clb_xstream_size");
+			std::vector<uint8_t> bytes(total + 1); std::vector<uint64_t> sizes(n_parts + 1);
+			check(ctx, clb_xstream_get(ctx, which, bytes.data(), total, sizes.data(), 0), "clb_xstream_get");
+			uint64_t at = 0;
+			for (uint32_t p = 0; p < n_parts; ++p) {
+				if (!archive.AddPart(stream_id, bytes.data() + at, sizes[p], metadata ? (*metadata)[p] : 0)) throw std::runtime_error("Error: cannot write to archive: " + params.outputFilePath);
+				at += sizes[p];
+			}
+		};
+		s_dna = archive.RegisterStream("dna");
+		check(ctx, clb_xdna_encode(ctx, static_cast<uint32_t>(params.compressionLevel), in.read_pack_sizes.data(), static_cast<uint32_t>(in.read_pack_sizes.size())), "clb_xdna_encode");
+		add_parts(s_dna, 0, &in.read_pack_sizes);
+		phase("dna stream");
+		if (is_fastq) {
+			s_qual = archive.RegisterStream("qual");
+			uint32_t thr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+			for (size_t i = 0; i < params.qualityFwdThresholds.size() && i < 8; ++i) thr[i] = params.qualityFwdThresholds[i];
+			check(ctx, clb_xqual_encode(ctx, static_cast<uint32_t>(params.qualityComprMode), static_cast<uint32_t>(params.dataSource), static_cast<uint32_t>(params.compressionLevel), thr,
+				in.quals.data(), in.offsets.data(), 0, in.read_pack_sizes.data(), static_cast<uint32_t>(in.read_pack_sizes.size())), "clb_xqual_encode");
+			add_parts(s_qual, 1, nullptr);
+			phase("quality stream");
 		}
-		add_part(s_qual, stream, 0);
-	}
-	const int s_header = archive.RegisterStream("header-b200");
-	{	// -i none / main store no header bytes, as in the reference (id_coder.cpp:102-110: Encode returns at once for `none`, and
-		// compress_instrument — `main` — is an empty function there); the decompressor prints "@" / "" for every read (:393-396, :588-591)
-		std::vector<uint8_t> stream;
+		s_header = archive.RegisterStream("header");
 		if (params.headerComprMode == HeaderComprMode::Original) {
-			CEntrComprHeaders h(kmer_counter);
-			h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
-			stream = h.GetStream();
+			check(ctx, clb_xhdr_encode(ctx, in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1, 0,
+				in.header_pack_sizes.data(), static_cast<uint32_t>(in.header_pack_sizes.size())), "clb_xhdr_encode");
+			add_parts(s_header, 2, &in.header_pack_sizes);
+		} else {      // -i none / main: CIDCoder::Encode returns at once (id_coder.cpp:102-110), every part is the coder's 8-byte flush
+			const std::vector<uint8_t> flush(8, 0);
+			for (uint32_t n_in_pack : in.header_pack_sizes) add_part(s_header, flush, n_in_pack);
 		}
-		add_part(s_header, stream, in.header_offsets.size() - 1);
+		phase("header stream");
+	} else {
+		// stage 3: one part per stream, metadata = number of reads / headers as in entr_read.h:74, entr_header.cpp:41
+		s_dna = archive.RegisterStream("dna-b200");
+		{
+			CEntrComprReads dna(kmer_counter, params.compressionLevel);
+			dna.Compress(in.read_pack_sizes);
+			const std::vector<uint8_t> stream = dna.GetStream();
+			add_part(s_dna, stream, tot_n_reads);
+		}
+		if (is_fastq) {
+			s_qual = archive.RegisterStream("qual-b200");
+			std::vector<uint8_t> stream;
+			if (params.qualityComprMode != QualityComprMode::None) {
+				const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
+				CEntrComprQuals q(kmer_counter, n_bins, params.qualityFwdThresholds, params.compressionLevel);
+				if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals.data(), in.offsets.data(), in.read_pack_sizes);
+				else q.Compress(in.quals.data(), in.offsets.data(), in.read_pack_sizes);
+				stream = q.GetStream();
+			}
+			add_part(s_qual, stream, 0);
+		}
+		s_header = archive.RegisterStream("header-b200");
+		{	// -i none / main store no header bytes, as in the reference (id_coder.cpp:102-110: Encode returns at once for `none`, and
+			// compress_instrument — `main` — is an empty function there); the decompressor prints "@" / "" for every read (:393-396, :588-591)
+			std::vector<uint8_t> stream;
+			if (params.headerComprMode == HeaderComprMode::Original) {
+				CEntrComprHeaders h(kmer_counter);
+				h.Compress(in.headers.data(), in.header_offsets.data(), in.plus_id.data(), in.header_offsets.size() - 1);
+				stream = h.GetStream();
+			}
+			add_part(s_header, stream, in.header_offsets.size() - 1);
+		}
+
+		phase("stage 3 (native containers)");
 	}
 
 	// `meta` (compression.cpp:705-779)
@@ -156,6 +210,8 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 
 	rep.dna = archive.GetStreamPackedSize(s_dna); rep.qual = s_qual >= 0 ? archive.GetStreamPackedSize(s_qual) : 0; rep.header = archive.GetStreamPackedSize(s_header);
 	rep.meta = archive.GetStreamPackedSize(s_meta); rep.info = archive.GetStreamPackedSize(s_info);
+	phase("meta, info, close");
+	rep.phases = phases;
 	rep.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	return rep;
 }

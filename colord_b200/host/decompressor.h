@@ -11,6 +11,7 @@
 // Lane l of a pack holds reads l, l + 64, ... of the pack.  Range decoder arithmetic = sub_rc.h:262-386 with totalFreq 2^12.
 // Every reader checks its bounds: a damaged archive ends in DecodeError, never in an out-of-range access.
 #pragma once
+#include <memory>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -185,13 +186,147 @@ struct Reads {
 	std::vector<uint8_t> flags;                                       // per base: 0 / 1 match / 2 anchor (quality contexts at level > 1)
 };
 
+// The tuples of one read (dna_coder.cpp:300-437) pulled from a symbol source:  d.get(family, context) / d.getx(family, context,
+// excluded symbols); Src::exact — the reference's own streams (chunk indices of anchor / skip lengths uncapped, tuple types and
+// substituted bases coded with exclusions, dna_coder.cpp:651-717, :889-922) against the native container's folded model.
+enum DnaFamily { F_FLAG, F_LENBITS, F_LENDATA, F_SYM, F_SYMN, F_READID, F_REV, F_TUPLE, F_ANCHOR, F_SKIPL, F_SKIPD, F_SEEN, F_SHORT };
+struct DnaRef { const uint8_t* sym; uint32_t len; bool rev; uint32_t at(int pos) const { if (pos < 0 || static_cast<uint32_t>(pos) >= len) return 255; return rev ? 3u - sym[len - 1 - pos] : sym[pos]; } };
+inline uint32_t dna_n_bytes(uint64_t x) { uint32_t r = 1; for (x >>= 8; x; x >>= 8) ++r; return r; }
+inline uint32_t dna_n_bits(uint64_t x) { uint32_t r = 0; for (; x; x >>= 1) ++r; return r; }
+template <class Src>
+inline uint32_t dna_read_id(Src& d, uint32_t r)
+{
+	const int nn = static_cast<int>(dna_n_bytes(r)); uint32_t id = 0;
+	for (int i = nn - 1; i >= 0; --i) { const uint64_t add = i == nn - 2 ? id : 0; id = (id << 8) + d.get(F_READID, static_cast<uint64_t>(i) + (add << 3)); }
+	return id;
+}
+template <class Src>
+inline uint32_t dna_skip(Src& d, bool local)
+{
+	uint32_t v = 0;
+	if (local) { for (uint32_t part = 0;; ++part) { const uint32_t x = d.get(F_SKIPL, Src::exact ? part : (part < 63 ? part : 63)); if (x < 255) { v += x; break; } v += 254; if (v > (1u << 30)) throw DecodeError("colord-b200: damaged DNA stream"); } }
+	else for (int i = 3; i >= 0; --i) { const uint32_t x = d.get(F_SKIPD, static_cast<uint64_t>(i) * 64 + dna_n_bits(v)); v = (v << 8) + x; }
+	return v;
+}
+// read length = number of tuples after the start tuple (dna_coder.cpp:1004-1056 in the decoding direction)
+template <class Src>
+inline uint32_t dna_read_len(Src& d)
+{
+	const uint32_t nbits = d.get(F_LENBITS, 0);
+	if (nbits < 2) return nbits;
+	uint64_t ctx = static_cast<uint64_t>(nbits) << 3;
+	uint32_t v = d.get(F_LENDATA, ctx);
+	if (nbits > 9) { uint32_t suffix = 0, sh = 0; ctx += 4; for (int nb = static_cast<int>(nbits) - 9; nb > 0; nb -= 8) { suffix |= d.get(F_LENDATA, ctx) << sh; sh += 8; ++ctx; } v = (v << (nbits - 9)) + suffix; }
+	return v + (1u << (nbits - 1));
+}
+template <class Src>
+inline void dna_edit_script(Src& d, uint32_t level, uint32_t n_s, uint32_t r, uint32_t n_tuples, const std::vector<std::vector<uint8_t>>& refs, std::vector<uint8_t>& rd, std::vector<uint8_t>& fl,
+		uint64_t ctx_symbol, uint64_t ctx_tuple, uint64_t mask_s, uint64_t mask_t, uint32_t sh_t, uint64_t budget)
+	{
+		// budget: bases the archive still announces; checked before anything is appended, so a damaged script cannot grow memory past it
+		auto room = [&](uint64_t k) { if (k > budget || rd.size() > budget - k) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)"); };
+		uint32_t seen_id[34], seen_rev[34], n_seen = 0; uint64_t ctx_rev = 0xf;
+		uint32_t alt_ids[32]; bool alt_revs[32]; int alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;
+		auto get_rev = [&](uint32_t id) -> bool {
+			for (uint32_t k = n_seen; k-- > 0;) if (seen_id[k] == id) return seen_rev[k] != 0;
+			const uint32_t f = d.get(F_REV, ctx_rev);
+			if (n_seen < 34) { seen_id[n_seen] = id; seen_rev[n_seen] = f; ++n_seen; }
+			ctx_rev = ((ctx_rev << 2) + f) & 0xf;
+			return f != 0;
+		};
+		auto ref_of = [&](uint32_t id, bool rev) -> DnaRef { if (id >= refs.size()) throw DecodeError("colord-b200: damaged DNA stream (unknown reference read)"); return DnaRef{refs[id].data(), static_cast<uint32_t>(refs[id].size()), rev}; };
+		const uint32_t main_id = dna_read_id(d, r);
+		const bool main_rev = get_rev(main_id);
+		const DnaRef mainr = ref_of(main_id, main_rev); DnaRef altr = mainr;
+		int ref_pos = 0, alt_pos = 0, delta = 0; bool is_main = true; uint32_t last_tuple = 255;
+		for (uint32_t it = 0; it < n_tuples; ++it) {
+			const DnaRef& o = is_main ? mainr : altr; int& pos = is_main ? ref_pos : alt_pos;
+			const uint32_t rsym = o.at(pos);
+			uint64_t ctx = ctx_tuple + ((ctx_symbol & 0xf) << sh_t) + (static_cast<uint64_t>(rsym) << (sh_t + 4));
+			const uint32_t bucket = delta < -10 ? 1 : delta < -1 ? 2 : delta > 10 ? 3 : delta > 1 ? 4 : 0;
+			ctx += static_cast<uint64_t>(bucket) << (sh_t + 6);
+			const uint32_t excl = last_tuple == 2 ? 1u << 4 : last_tuple == 1 ? 1u << 5 : last_tuple == 4 ? (1u << 4) | (1u << 2)
+				: last_tuple == 5 ? (1u << 1) | (1u << 5) : (last_tuple == 7 || last_tuple == 6) ? (1u << 6) | (1u << 7) : 0u;
+			const uint32_t ty = d.getx(F_TUPLE, ctx, excl);
+			ctx_tuple = ((ctx_tuple << 3) + ty) & mask_t;
+			switch (ty) {
+			case 6: {          // alternative reference read
+				if (!is_main && cur_alt >= 0) alt_saved[cur_alt] = alt_pos;
+				uint32_t id; int idx = -1;
+				if (n_alt == 0 || !d.get(F_SEEN, n_alt)) id = dna_read_id(d, r);
+				else { idx = static_cast<int>(d.get(F_SHORT, n_alt)); if (static_cast<uint32_t>(idx) >= n_alt) throw DecodeError("colord-b200: damaged DNA stream"); id = alt_ids[idx]; }
+				const bool rev = get_rev(id);
+				if (idx < 0) for (uint32_t k = 0; k < n_alt; ++k) if (alt_ids[k] == id) idx = static_cast<int>(k);
+				if (idx < 0 && n_alt < 32) { idx = static_cast<int>(n_alt); alt_ids[n_alt] = id; alt_revs[n_alt] = rev; alt_saved[n_alt] = 0; ++n_alt; }
+				cur_alt = idx;
+				altr = ref_of(id, idx >= 0 ? alt_revs[idx] : rev);
+				alt_pos = 0; is_main = false; delta = 0;
+				break;
+			}
+			case 4: {          // anchor: a run of matches
+				uint32_t alen = 0;
+				for (uint32_t part = 0;; ++part) { const uint32_t v = d.get(F_ANCHOR, Src::exact ? part : (part < 63 ? part : 63)); if (v < 23) { alen += v; break; } alen += 22; if (alen > (1u << 30)) throw DecodeError("colord-b200: damaged DNA stream"); }
+				if (alen > o.len) throw DecodeError("colord-b200: damaged DNA stream (anchor longer than its reference read)");
+				room(alen);
+				for (uint32_t k = 0; k < alen; ++k) { rd.push_back(static_cast<uint8_t>(o.at(pos + static_cast<int>(k)))); fl.push_back(2); }
+				pos += static_cast<int>(alen);
+				for (int i = static_cast<int>(n_s); i > 0; --i) ctx_symbol = (ctx_symbol << 2) + o.at(pos - i);
+				ctx_symbol &= mask_s; delta = 0;
+				break;
+			}
+			case 2: room(1); rd.push_back(static_cast<uint8_t>(rsym)); fl.push_back(1); ctx_symbol = ((ctx_symbol << 2) + rsym) & mask_s; ++pos; break;
+			case 0: {          // insertion
+				uint64_t c2 = 2; uint32_t sh = 2;
+				if (level <= 1) { c2 += (ctx_symbol & 0xff) << sh; sh += 8; }
+				else { c2 += (ctx_symbol & 0x3ff) << sh; sh += 10; if (level >= 3) { c2 += static_cast<uint64_t>(((ctx_symbol >> 10) & 3) == ((ctx_symbol >> 8) & 3)) << sh; ++sh; } }
+				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
+				c2 += (ctx_tuple & 0777) << sh;
+				const uint32_t s = d.get(F_SYM, c2);
+				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
+				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++delta;
+				break;
+			}
+			case 1: ++pos; --delta; break;                        // deletion
+			case 3: {          // substitution
+				uint64_t c2 = 1; uint32_t sh = 2;
+				c2 += (ctx_symbol & 0x3f) << sh; sh += 6;
+				if (level >= 3) { c2 += static_cast<uint64_t>(((ctx_symbol >> 6) & 3) == ((ctx_symbol >> 4) & 3)) << sh; ++sh; }
+				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
+				c2 += (ctx_tuple & 07777) << sh;
+				const uint32_t s = d.getx(F_SYM, c2, 1u << (rsym & 3));
+				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
+				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++pos;
+				break;
+			}
+			case 5: {          // skip (dna_coder.cpp:389-412)
+				uint32_t skip;
+				const bool distant_after_alt = !is_main && last_tuple == 6;
+				const bool local = !distant_after_alt && last_tuple != 6 && last_tuple != 255;
+				if (distant_after_alt) {
+					uint32_t v = dna_skip(d, false);
+					const int saved = cur_alt >= 0 ? alt_saved[cur_alt] : 0;
+					if (v > 0) skip = v + static_cast<uint32_t>(saved);
+					else { v = dna_skip(d, false); skip = static_cast<uint32_t>(saved - static_cast<int>(v)); }
+				} else skip = dna_skip(d, local);
+				delta -= static_cast<int>(skip); pos += static_cast<int>(skip);
+				break;
+			}
+			default: is_main = true; if (cur_alt >= 0) alt_saved[cur_alt] = alt_pos; delta = 0; break;      // 7: back to the main reference
+			}
+			last_tuple = ty;
+		}
+		for (uint8_t s : rd) if (s > 3) throw DecodeError("colord-b200: damaged DNA stream (symbol outside a reference read)");
+	}
+
 // ---- DNA / edit-script stream: CDNACoder::Decode (dna_coder.cpp:237-437) over the container's tables ----
 class DnaDecoder {
-	enum { F_FLAG, F_LENBITS, F_LENDATA, F_SYM, F_SYMN, F_READID, F_REV, F_TUPLE, F_ANCHOR, F_SKIPL, F_SKIPD, F_SEEN, F_SHORT };
 	StaticModel M; uint32_t level = 0, n_t = 0, n_s = 0;
-	struct Ref { const uint8_t* sym; uint32_t len; bool rev; uint32_t at(int pos) const { if (pos < 0 || static_cast<uint32_t>(pos) >= len) return 255; return rev ? 3u - sym[len - 1 - pos] : sym[pos]; } };
-	static uint32_t n_bytes(uint64_t x) { uint32_t r = 1; for (x >>= 8; x; x >>= 8) ++r; return r; }
-	static uint32_t n_bits(uint64_t x) { uint32_t r = 0; for (; x; x >>= 1) ++r; return r; }
+	struct Src {            // a lane's range decoder over the container's static tables
+		RangeDecoder& d; const StaticModel& M;
+		static constexpr bool exact = false;
+		uint32_t get(uint32_t f, uint64_t ctx) { return d.get(M, f, ctx); }
+		uint32_t getx(uint32_t f, uint64_t ctx, uint32_t) { return d.get(M, f, ctx); }
+	};
 public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
 	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
@@ -227,22 +362,13 @@ public:
 				rd.clear(); fl.clear();
 				const uint32_t flag = d.get(M, F_FLAG, fc);
 				fc = ((fc << 2) + flag) & 0xff;
-				uint32_t len;
-				{
-					const uint32_t nbits = d.get(M, F_LENBITS, 0);
-					if (nbits < 2) len = nbits;
-					else {
-						uint64_t ctx = static_cast<uint64_t>(nbits) << 3;
-						uint32_t v = d.get(M, F_LENDATA, ctx);
-						if (nbits > 9) { uint32_t suffix = 0, sh = 0; ctx += 4; for (int nb = static_cast<int>(nbits) - 9; nb > 0; nb -= 8) { suffix |= d.get(M, F_LENDATA, ctx) << sh; sh += 8; ++ctx; } v = (v << (nbits - 9)) + suffix; }
-						len = v + (1u << (nbits - 1));
-					}
-				}
+				Src src{d, M};
+				const uint32_t len = dna_read_len(src);
 				if (len > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
 				if (flag == 0) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYM, ctx_symbol << 2); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; }
 				else if (flag == 1) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYMN, ctx_symbol); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; }
-				else decode_edit_script(d, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t, max_bases - std::min<uint64_t>(max_bases, out.bases.size()));
+				else dna_edit_script(src, level, n_s, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t, max_bases - std::min<uint64_t>(max_bases, out.bases.size()));
 				if (rd.size() > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				fl.resize(rd.size(), 0);
 				for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
@@ -254,115 +380,6 @@ public:
 		}
 		if (r0 != n_reads) throw DecodeError("colord-b200: DNA stream holds fewer reads than the archive says");
 		return out;
-	}
-private:
-	uint32_t get_read_id(RangeDecoder& d, uint32_t r)
-	{
-		const int nn = static_cast<int>(n_bytes(r)); uint32_t id = 0;
-		for (int i = nn - 1; i >= 0; --i) { const uint64_t add = i == nn - 2 ? id : 0; id = (id << 8) + d.get(M, F_READID, static_cast<uint64_t>(i) + (add << 3)); }
-		return id;
-	}
-	uint32_t get_skip(RangeDecoder& d, bool local)
-	{
-		uint32_t v = 0;
-		if (local) { for (uint32_t part = 0;; ++part) { const uint32_t x = d.get(M, F_SKIPL, part < 63 ? part : 63); if (x < 255) { v += x; break; } v += 254; } }
-		else for (int i = 3; i >= 0; --i) { const uint32_t x = d.get(M, F_SKIPD, static_cast<uint64_t>(i) * 64 + n_bits(v)); v = (v << 8) + x; }
-		return v;
-	}
-	void decode_edit_script(RangeDecoder& d, uint32_t r, uint32_t n_tuples, const std::vector<std::vector<uint8_t>>& refs, std::vector<uint8_t>& rd, std::vector<uint8_t>& fl,
-		uint64_t ctx_symbol, uint64_t ctx_tuple, uint64_t mask_s, uint64_t mask_t, uint32_t sh_t, uint64_t budget)
-	{
-		// budget: bases the archive still announces; checked before anything is appended, so a damaged script cannot grow memory past it
-		auto room = [&](uint64_t k) { if (k > budget || rd.size() > budget - k) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)"); };
-		uint32_t seen_id[34], seen_rev[34], n_seen = 0; uint64_t ctx_rev = 0xf;
-		uint32_t alt_ids[32]; bool alt_revs[32]; int alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;
-		auto get_rev = [&](uint32_t id) -> bool {
-			for (uint32_t k = n_seen; k-- > 0;) if (seen_id[k] == id) return seen_rev[k] != 0;
-			const uint32_t f = d.get(M, F_REV, ctx_rev);
-			if (n_seen < 34) { seen_id[n_seen] = id; seen_rev[n_seen] = f; ++n_seen; }
-			ctx_rev = ((ctx_rev << 2) + f) & 0xf;
-			return f != 0;
-		};
-		auto ref_of = [&](uint32_t id, bool rev) -> Ref { if (id >= refs.size()) throw DecodeError("colord-b200: damaged DNA stream (unknown reference read)"); return Ref{refs[id].data(), static_cast<uint32_t>(refs[id].size()), rev}; };
-		const uint32_t main_id = get_read_id(d, r);
-		const bool main_rev = get_rev(main_id);
-		const Ref mainr = ref_of(main_id, main_rev); Ref altr = mainr;
-		int ref_pos = 0, alt_pos = 0, delta = 0; bool is_main = true; uint32_t last_tuple = 255;
-		for (uint32_t it = 0; it < n_tuples; ++it) {
-			const Ref& o = is_main ? mainr : altr; int& pos = is_main ? ref_pos : alt_pos;
-			const uint32_t rsym = o.at(pos);
-			uint64_t ctx = ctx_tuple + ((ctx_symbol & 0xf) << sh_t) + (static_cast<uint64_t>(rsym) << (sh_t + 4));
-			const uint32_t bucket = delta < -10 ? 1 : delta < -1 ? 2 : delta > 10 ? 3 : delta > 1 ? 4 : 0;
-			ctx += static_cast<uint64_t>(bucket) << (sh_t + 6);
-			const uint32_t ty = d.get(M, F_TUPLE, ctx);
-			ctx_tuple = ((ctx_tuple << 3) + ty) & mask_t;
-			switch (ty) {
-			case 6: {          // alternative reference read
-				if (!is_main && cur_alt >= 0) alt_saved[cur_alt] = alt_pos;
-				uint32_t id; int idx = -1;
-				if (n_alt == 0 || !d.get(M, F_SEEN, n_alt)) id = get_read_id(d, r);
-				else { idx = static_cast<int>(d.get(M, F_SHORT, n_alt)); if (static_cast<uint32_t>(idx) >= n_alt) throw DecodeError("colord-b200: damaged DNA stream"); id = alt_ids[idx]; }
-				const bool rev = get_rev(id);
-				if (idx < 0) for (uint32_t k = 0; k < n_alt; ++k) if (alt_ids[k] == id) idx = static_cast<int>(k);
-				if (idx < 0 && n_alt < 32) { idx = static_cast<int>(n_alt); alt_ids[n_alt] = id; alt_revs[n_alt] = rev; alt_saved[n_alt] = 0; ++n_alt; }
-				cur_alt = idx;
-				altr = ref_of(id, idx >= 0 ? alt_revs[idx] : rev);
-				alt_pos = 0; is_main = false; delta = 0;
-				break;
-			}
-			case 4: {          // anchor: a run of matches
-				uint32_t alen = 0;
-				for (uint32_t part = 0;; ++part) { const uint32_t v = d.get(M, F_ANCHOR, part < 63 ? part : 63); if (v < 23) { alen += v; break; } alen += 22; if (alen > (1u << 30)) throw DecodeError("colord-b200: damaged DNA stream"); }
-				if (alen > o.len) throw DecodeError("colord-b200: damaged DNA stream (anchor longer than its reference read)");
-				room(alen);
-				for (uint32_t k = 0; k < alen; ++k) { rd.push_back(static_cast<uint8_t>(o.at(pos + static_cast<int>(k)))); fl.push_back(2); }
-				pos += static_cast<int>(alen);
-				for (int i = static_cast<int>(n_s); i > 0; --i) ctx_symbol = (ctx_symbol << 2) + o.at(pos - i);
-				ctx_symbol &= mask_s; delta = 0;
-				break;
-			}
-			case 2: room(1); rd.push_back(static_cast<uint8_t>(rsym)); fl.push_back(1); ctx_symbol = ((ctx_symbol << 2) + rsym) & mask_s; ++pos; break;
-			case 0: {          // insertion
-				uint64_t c2 = 2; uint32_t sh = 2;
-				if (level <= 1) { c2 += (ctx_symbol & 0xff) << sh; sh += 8; }
-				else { c2 += (ctx_symbol & 0x3ff) << sh; sh += 10; if (level >= 3) { c2 += static_cast<uint64_t>(((ctx_symbol >> 10) & 3) == ((ctx_symbol >> 8) & 3)) << sh; ++sh; } }
-				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
-				c2 += (ctx_tuple & 0777) << sh;
-				const uint32_t s = d.get(M, F_SYM, c2);
-				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
-				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++delta;
-				break;
-			}
-			case 1: ++pos; --delta; break;                        // deletion
-			case 3: {          // substitution
-				uint64_t c2 = 1; uint32_t sh = 2;
-				c2 += (ctx_symbol & 0x3f) << sh; sh += 6;
-				if (level >= 3) { c2 += static_cast<uint64_t>(((ctx_symbol >> 6) & 3) == ((ctx_symbol >> 4) & 3)) << sh; ++sh; }
-				c2 += static_cast<uint64_t>(rsym) << sh; sh += 2;
-				c2 += (ctx_tuple & 07777) << sh;
-				const uint32_t s = d.get(M, F_SYM, c2);
-				room(1); rd.push_back(static_cast<uint8_t>(s)); fl.push_back(0);
-				ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++pos;
-				break;
-			}
-			case 5: {          // skip (dna_coder.cpp:389-412)
-				uint32_t skip;
-				const bool distant_after_alt = !is_main && last_tuple == 6;
-				const bool local = !distant_after_alt && last_tuple != 6 && last_tuple != 255;
-				if (distant_after_alt) {
-					uint32_t v = get_skip(d, false);
-					const int saved = cur_alt >= 0 ? alt_saved[cur_alt] : 0;
-					if (v > 0) skip = v + static_cast<uint32_t>(saved);
-					else { v = get_skip(d, false); skip = static_cast<uint32_t>(saved - static_cast<int>(v)); }
-				} else skip = get_skip(d, local);
-				delta -= static_cast<int>(skip); pos += static_cast<int>(skip);
-				break;
-			}
-			default: is_main = true; if (cur_alt >= 0) alt_saved[cur_alt] = alt_pos; delta = 0; break;      // 7: back to the main reference
-			}
-			last_tuple = ty;
-		}
-		for (uint8_t s : rd) if (s > 3) throw DecodeError("colord-b200: damaged DNA stream (symbol outside a reference read)");
 	}
 };
 
@@ -564,6 +581,9 @@ inline Headers decode_headers(const uint8_t* data, uint64_t size, uint64_t n_exp
 }
 
 } // namespace dec
+} // namespace clbhost
+#include "compat_decoder.h"      // the reference's own streams (version-1 archives)
+namespace clbhost {
 
 // decompression_common.cpp:27-265: the archive's records and streams decoded into memory (reads in input order)
 struct DecompressedArchive {
@@ -578,15 +598,19 @@ struct DecompressedArchive {
 		const int s_info = archive.GetStreamId("info"), s_meta = archive.GetStreamId("meta");
 		if (s_info < 0 || s_meta < 0 || !archive.ReadPart(s_info, 0, raw, md)) throw DecodeError("Error: not a colord archive (no info / meta record)");
 		info.Deserialize(raw);
-		const int s_dna = archive.GetStreamId("dna-b200"), s_qual = archive.GetStreamId("qual-b200"), s_hdr = archive.GetStreamId("header-b200");
-		if (info.version_major != B200_VERSION_MAJOR || s_dna < 0 || s_hdr < 0)
-			throw DecodeError("Error: incompatibile archive version (this build reads archives written by colord-b200; use the reference's colord for its own archives)");
+		// two kinds of archives: the reference's own streams (version 1.x: written by `colord` or by colord-b200's compat mode) and the
+		// device's native containers (version B200_VERSION_MAJOR)
+		const bool compat = info.version_major == 1;
+		const int s_dna = archive.GetStreamId(compat ? "dna" : "dna-b200"), s_qual = archive.GetStreamId(compat ? "qual" : "qual-b200"), s_hdr = archive.GetStreamId(compat ? "header" : "header-b200");
+		if ((!compat && info.version_major != B200_VERSION_MAJOR) || s_dna < 0 || s_hdr < 0)
+			throw DecodeError("Error: incompatibile archive version");
 		if (!archive.ReadPart(s_meta, 0, raw, md)) throw DecodeError("Error: cannot read the meta record");
 		meta.Deserialize(raw, s_qual >= 0);
 		if (meta.ref_genome_available) throw DecodeError("Error: reference-genome archives are not available in this build");
 		const uint32_t n_reads = info.total_reads;
 		if (verbose) std::cerr << "reads: " << n_reads << "\nbases: " << info.total_bases << "\nquality mode: " << static_cast<int>(meta.qualityComprMode) << "\n";
 
+		if (compat) { decode_reference_streams(archive, s_dna, s_qual, s_hdr, n_reads); return; }
 		std::vector<uint8_t> stream;
 		if (!archive.ReadPart(s_dna, 0, stream, md) || md != n_reads) throw DecodeError("Error: cannot read the DNA stream");
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
@@ -617,6 +641,29 @@ struct DecompressedArchive {
 		}
 	}
 	uint32_t n_reads() const { return static_cast<uint32_t>(reads.offsets.size() - 1); }
+private:
+	// version-1 archives: one part per pack in every stream (entr_read.h:146-184, entr_qual.h:128-190, entr_header.cpp:49-80)
+	void decode_reference_streams(CArchive& archive, int s_dna, int s_qual, int s_hdr, uint32_t n_reads)
+	{
+		auto parts_of = [&](int stream_id) -> xdec::PartSource {
+			auto next = std::make_shared<size_t>(0);
+			const size_t n_parts = archive.Parts(stream_id).size();
+			return [&archive, stream_id, next, n_parts](std::vector<uint8_t>& data, size_t& md) { if (*next >= n_parts) return false; if (!archive.ReadPart(stream_id, (*next)++, data, md)) throw DecodeError("Error: cannot read a part of the archive"); return true; };
+		};
+		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
+		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
+		std::vector<uint32_t> part_reads;
+		reads = xdec::decode_dna(parts_of(s_dna), n_reads, decisions, static_cast<uint32_t>(meta.compressionLevel), meta.maxCandidates, flags_needed, info.total_bases, part_reads);
+		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
+		if (meta.headerComprMode == HeaderComprMode::Original) headers = xdec::decode_headers(parts_of(s_hdr), n_reads, info.total_bytes);
+		else for (uint32_t r = 0; r < n_reads; ++r) {
+			if (meta.headerComprMode == HeaderComprMode::None) headers.bytes.push_back('@');
+			headers.offsets.push_back(headers.bytes.size());
+			headers.plus_id.push_back(0);
+		}
+		if (meta.is_fastq)
+			quals = xdec::decode_qual(parts_of(s_qual), reads, part_reads, static_cast<uint32_t>(meta.qualityComprMode), static_cast<uint32_t>(meta.dataSource), static_cast<uint32_t>(meta.compressionLevel), meta.qualityRevThresholds);
+	}
 };
 
 // decompression.cpp: archive -> file.  FASTQ records: '@' id, bases, '+' [id], qualities; FASTA records: '>' id, bases on one line.

@@ -20,11 +20,13 @@ static void usage()
 	std::cerr <<
 		"colord-b200 (archive format " << B200_VERSION_MAJOR << "." << B200_VERSION_MINOR << "." << B200_VERSION_PATCH << ")\n"
 		"  colord-b200 compress-ont|compress-pbhifi|compress-pbraw [options] input output\n"
-		"      -k,--kmer-len N  -a,--anchor-len N  -p,--priority ratio|balanced|memory  -q,--qual org|2-avg|4-avg|5-avg|none\n"
+		"      -k,--kmer-len N  -a,--anchor-len N  -p,--priority ratio|balanced|memory  -q,--qual org|2-avg|4-avg|5-avg|2-fix|4-fix|5-fix|avg|none\n"
 		"      -T,--qual-thresholds a,b,..  -L,--Lowest-count N  -H,--Highest-count N  -f,--filter-modulo N  -c,--max-candidates N\n"
 		"      -e,--edit-script-mult X  -r,--max-recurence-level N  --min-to-alt N  --min-mmer-frac X  --min-mmer-force-enc X\n"
 		"      --max-matches-mult X  --min-anchors N  -R,--reference-reads-mode all|sparse  -g,--sparse-range X  -x,--sparse-exponent X\n"
 		"      -i,--identifier org|main|none  -t,--threads N (accepted, unused)  -v,--verbose  --device N\n"
+		"      --compat | --native   streams of the archive: the reference's own (readable by `colord decompress`, every -q mode) or the\n"
+		"                            device's containers (org, *-avg, none); default: --compat up to --compat-max-mbases N (512) input Mbases\n"
 		"  colord-b200 decompress archive output\n"
 		"  colord-b200 info archive\n";
 }
@@ -53,7 +55,10 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 		else if (a == "-a" || a == "--anchor-len") p.anchorLen = std::stoul(need());
 		else if (a == "-t" || a == "--threads") p.nThreads = std::stoul(need());
 		else if (a == "-q" || a == "--qual") { p.qualityComprMode = qualityComprModeFromString(need()); qual_set = true; }
-		else if (a == "-T" || a == "--qual-thresholds") fwd_user = parse_list(need());
+		else if (a == "-T" || a == "--qual-thresholds") {      // the reference's form `-T 5 12 20` (arg_parse.cpp:488-500) or one comma-separated list
+			fwd_user = parse_list(need());
+			while (i + 1 < argc && argv[i + 1][0] && std::string(argv[i + 1]).find_first_not_of("0123456789") == std::string::npos) fwd_user.push_back(static_cast<uint32_t>(std::stoul(argv[++i])));
+		}
 		else if (a == "-L" || a == "--Lowest-count") p.minKmerCount = std::stoul(need());
 		else if (a == "-H" || a == "--Highest-count") p.maxKmerCount = std::stoul(need());
 		else if (a == "-f" || a == "--filter-modulo") p.filterHashModulo = std::stoul(need());
@@ -73,6 +78,9 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 		else if (a == "-s" || a == "--store-reference") p.storeRefGenome = true;
 		else if (a == "-v" || a == "--verbose") p.verbose = true;
 		else if (a == "--device") p.device = std::stoi(need());
+		else if (a == "--compat") p.streamFormat = StreamFormat::Compat;
+		else if (a == "--native") p.streamFormat = StreamFormat::Native;
+		else if (a == "--compat-max-mbases") p.compat_max_bases = std::stoull(need()) << 20;
 		else if (!a.empty() && a[0] == '-') throw std::invalid_argument("unknown option " + a);
 		else pos.push_back(a);
 	}
@@ -82,6 +90,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	if (!fwd_user.empty()) { const size_t want = p.qualityFwdThresholds.size(); if (fwd_user.size() < want) throw std::invalid_argument("too few quality thresholds for this mode"); fwd_user.resize(want); p.qualityFwdThresholds = fwd_user; }
 	CInfo info; info.full_command_line = full_cmd;
 	const CompressionReport r = runCompression(p, info);
+	if (p.verbose) { std::cerr << "streams: " << (r.compat ? "compat (the reference's own)" : "native containers") << "\n"; for (const Phase& ph : r.phases) std::cerr << "  phase " << ph.name << ": " << ph.seconds << " s\n"; }
 	if (p.verbose) std::cerr << "k-mer length: " << r.kmerLen << "\nanchor length: " << r.anchorLen << "\nsparse mode range in reads: " << r.sparse_range << "\nreference reads: " << r.tot_ref_reads << "\n";
 	// compression.cpp:802-806
 	std::cerr << "DNA size        : " << r.dna << "\nQuality size    : " << r.qual << "\nHeader size     : " << r.header << "\nMeta size       : " << r.meta << "\nInfo size       : " << r.info << "\n";

@@ -17,6 +17,10 @@
 namespace clbhost {
 
 enum class CompressionPriority { Ratio, Balanced, Memory };
+// how the three stage-3 streams are stored (no counterpart in the reference): Compat = the reference's own streams, an archive the
+// unmodified `colord decompress` reads (colord_b200/csrc/stage3_exact.cu); Native = the device's containers; Auto = Compat up to
+// compat_max_bases input bases, where it also is the smaller archive, Native above
+enum class StreamFormat { Auto, Native, Compat };
 
 struct CCompressorParams {
 	DataSource dataSource = DataSource::ONT;
@@ -38,6 +42,8 @@ struct CCompressorParams {
 	uint32_t nThreads = 0;                                 // accepted and printed as the reference does; the device path does not use it
 	std::string refGenomePath; bool storeRefGenome = false;
 	int device = 0;                                        // CUDA device ordinal (no counterpart in the reference)
+	StreamFormat streamFormat = StreamFormat::Auto;
+	uint64_t compat_max_bases = 512ull << 20;              // Auto: inputs up to this many bases are written as the reference's own streams
 };
 
 inline DataSource dataSourceFromCommand(const std::string& cmd)

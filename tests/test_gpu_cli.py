@@ -64,9 +64,21 @@ CASES = {
 }
 
 
+REF = os.path.join(ROOT, "oracle", "_ref", "colord")      # the unmodified reference (oracle/Makefile); travels to the GPU box
+
+
+def _stream_sizes(stderr):
+    import re
+    return {k: int(v) for k, v in re.findall(r"^(DNA|Quality|Header) size\s*:\s*(\d+)", stderr, re.M)}
+
+
+@pytest.mark.parametrize("fmt", ["native", "compat"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_cli_round_trip(cli, tmp_path, case):
+def test_cli_round_trip(cli, tmp_path, case, fmt):
+    """fmt native: the device's containers; compat: the reference's own streams — the archive is then also decompressed by the
+    unmodified reference, and its three streams have exactly the sizes the reference's own compression of the file gives."""
     make, cmd, opts, qmode, fasta, plus = CASES[case]
+    opts = opts + ["--" + fmt]
     recs = make()
     inp = str(tmp_path / ("in.fa" if fasta else "in.fastq"))
     if fasta:
@@ -96,23 +108,55 @@ def test_cli_round_trip(cli, tmp_path, case):
     r = subprocess.run([cli, cmd, *opts, inp, arch], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "DNA size" in r.stderr and "Header size" in r.stderr
+    ours = _stream_sizes(r.stderr)
+    if fmt == "compat" and os.path.exists(REF):
+        ref_arch, ref_back = str(tmp_path / "ref.colord"), str(tmp_path / "ref_back")
+        rr = subprocess.run([REF, cmd, *opts[:-1], "-t", "4", inp, ref_arch], capture_output=True, text=True, cwd=str(tmp_path))
+        assert rr.returncode == 0, rr.stderr
+        assert _stream_sizes(rr.stderr) == ours, f"{case}: stream sizes differ from the reference's"
+        rr = subprocess.run([REF, "decompress", arch, ref_back], capture_output=True, text=True, cwd=str(tmp_path))
+        assert rr.returncode == 0, rr.stderr
+        assert open(ref_back, "rb").read() == want, f"{case}: the reference's decompress of our archive differs"
     r = subprocess.run([cli, "decompress", arch, back], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = open(back, "rb").read()
     assert got == want, f"{case}: round trip differs ({len(got)} vs {len(want)} bytes)"
-    if qmode != "org" or len(recs) >= 100:       # a few reads of lossless qualities do not pay for their 96-symbol tables
+    if fmt == "compat" or qmode != "org" or len(recs) >= 100:       # a few reads of lossless qualities do not pay for their 96-symbol tables
         assert os.path.getsize(arch) < len(data)
     # the info record as the reference's `colord info` prints it
     r = subprocess.run([cli, "info", arch], capture_output=True, text=True)
     assert r.returncode == 0 and f"total reads: {len(recs)}" in r.stderr and f"total bases: {sum(len(x[1]) for x in recs)}" in r.stderr and f"total bytes: {len(data)}" in r.stderr
     save = os.environ.get("CLB_SAVE_ARCHIVES")
-    if save and case in ("ont_default", "ont_org_small", "ont_fasta", "clr_ratio_none"):
+    if save and fmt == "native" and case in ("ont_default", "ont_org_small", "ont_fasta", "clr_ratio_none"):
         os.makedirs(save, exist_ok=True)
         open(os.path.join(save, case + ".colord"), "wb").write(open(arch, "rb").read())
         p = os.path.join(save, "expected.json")
         exp = json.load(open(p)) if os.path.exists(p) else {}
         exp[case] = {"made_by": " ".join(["colord-b200", cmd, *opts]), "output_bytes": len(want), "output_sha1": hashlib.sha1(want).hexdigest(), "archive_bytes": os.path.getsize(arch)}
         json.dump(exp, open(p, "w"), indent=1, sort_keys=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the stock reference binary is not built here")
+@pytest.mark.parametrize("opts", [["-q", "2-fix"], ["-q", "4-fix", "-p", "balanced"], ["-q", "5-fix", "-T", "6,13,25,50"], ["-q", "avg"], ["-q", "5-avg", "-p", "ratio"], ["-q", "none", "-c", "9"]])
+def test_cli_compat_every_quality_mode_against_the_reference(cli, tmp_path, opts):
+    """The quality modes only the compat streams hold (threshold modes, plain average) and a few more option sets: stream sizes equal
+    the reference's, and the four ways through (ours / the reference's compressor x ours / the reference's decompressor) print one file."""
+    s = synth.generate(900, 150000, 2500, seed=17, profile="ont", n_frac=0.03)
+    inp = str(tmp_path / "in.fastq")
+    s.write_fastq(inp)
+    a, b = str(tmp_path / "ours.colord"), str(tmp_path / "ref.colord")
+    r = subprocess.run([cli, "compress-ont", *opts, "--compat", inp, a], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref_opts = [x for o in opts for x in (o.split(",") if "," in o else [o])]      # the reference takes -T as separate numbers
+    rr = subprocess.run([REF, "compress-ont", *ref_opts, "-t", "4", inp, b], capture_output=True, text=True, cwd=str(tmp_path))
+    assert rr.returncode == 0, rr.stderr
+    assert _stream_sizes(r.stderr) == _stream_sizes(rr.stderr)
+    outs = []
+    for exe, arc in ((cli, a), (cli, b), (REF, a), (REF, b)):
+        o = str(tmp_path / f"out{len(outs)}")
+        assert subprocess.run([exe, "decompress", arc, o], capture_output=True, cwd=str(tmp_path)).returncode == 0
+        outs.append(open(o, "rb").read())
+    assert outs[0] == outs[1] == outs[2] == outs[3]
 
 
 def test_cli_refusals(cli, tmp_path):
@@ -123,7 +167,7 @@ def test_cli_refusals(cli, tmp_path):
     assert r.returncode == 1 and "Only ACGTN symbols supported inside a read" in r.stderr
     ok = str(tmp_path / "ok.fastq")
     open(ok, "wb").write(b"@r\nACGT\n+\nIIII\n")
-    for opts, msg in ((["-G", "x.fa"], "not available"), (["-q", "4-fix"], "not available"), (["-q", "bogus"], "unknown quality"), (["-k", "99"], "15..28")):
+    for opts, msg in ((["-G", "x.fa"], "not available"), (["-q", "4-fix", "--native"], "compat streams only"), (["-q", "bogus"], "unknown quality"), (["-k", "99"], "15..28")):
         r = subprocess.run([cli, "compress-ont", *opts, ok, str(tmp_path / "o")], capture_output=True, text=True)
         assert r.returncode == 1 and msg in r.stderr, (opts, r.stderr)
     r = subprocess.run([cli, "decompress", ok, str(tmp_path / "o2")], capture_output=True, text=True)

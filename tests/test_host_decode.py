@@ -289,7 +289,10 @@ def test_api_surface_on_device_made_archives(tmp_path):
         assert "colord archive version: 201.1.0" in info and f"is fastq: {'false' if case == 'ont_fasta' else 'true'}" in info
         assert ("reads source: PBRaw" if case.startswith("clr") else "reads source: ONT") in info
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
-    assert r.returncode == 1 and "incompatibile archive version" in r.stderr         # a reference archive is refused, not misread
+    # an archive of the unmodified reference (6 reads of its ONT test file) is read through the same surface (compat_decoder.h)
+    assert r.returncode == 0 and "colord archive version: 1.2.1" in r.stderr and r.stdout.count("\n") == 24, r.stderr
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_genome_stored.colord")], capture_output=True, text=True)
+    assert r.returncode == 1 and "reference-genome archives are not available" in r.stderr
 
 
 @pytest.mark.parametrize("variant", ["plain", "crlf", "blank_lines", "plus_header", "tricky_quals", "gzip"])

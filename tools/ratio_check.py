@@ -182,11 +182,13 @@ def main():
         ours_arc = os.path.join(args.tmp, name + ".b200.colord")
         our_t, our_sz = [], {}
         for _ in range(args.runs):
-            p, dt, cpu = run([OURS, mode, *opts, *args.ours_opts.split(), fq, ours_arc], cwd=args.tmp)
+            p, dt, cpu = run([OURS, mode, *opts, "-v", *args.ours_opts.split(), fq, ours_arc], cwd=args.tmp)
             if p.returncode != 0:
                 row["ours_error"] = p.stderr[-400:]
                 break
             our_t.append(dt); our_sz = sizes_of(p.stderr); row["ours_cpu_s"] = round(cpu, 2)
+            row["ours_phases_s"] = {k.strip(): float(v) for k, v in re.findall(r"^  phase (.*): ([0-9.e+-]+) s$", p.stderr, re.M)}
+            row["ours_streams_format"] = "compat" if "streams: compat" in p.stderr else "native"
         if our_t:
             our_t.sort()
             row.update(ours_archive_bytes=os.path.getsize(ours_arc), ours_streams=our_sz, ours_wall_s=round(our_t[len(our_t) // 2], 3),
