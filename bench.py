@@ -146,52 +146,77 @@ def measured_peak_hbm():
 
 
 # ----------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the reference's own stage 1 on the host cores (oracle/_ref/ref_stage1_time)
+# reference arm / cpu baseline: the STOCK reference binary (oracle/_ref/colord, the unmodified CLI built by oracle/Makefile) on a
+# FASTQ file that is a bounded sample of the workload — wall time from process start to exit, all host threads
 # ----------------------------------------------------------------------------------------------------
-def reference_sample_fastq(path, n_reads=12500, genome_len=5_000_000):
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "colord")
+OUR_CLI = os.path.join(ROOT, "colord_b200", "colord-b200")
+SIZE_KEYS = (("DNA", "dna"), ("Quality", "quality"), ("Header", "header"))
+
+
+def sample_fastq(path, n_reads):
+    """n_reads synthetic ONT reads of the north-star workload (same error / quality / header model, 20.8x coverage) as a FASTQ file"""
     from colord_b200 import synth
-    s = synth.generate(n_reads, genome_len, NS["mean_len"], seed=1, profile="ont")
-    s.write_fastq(path)
-    return s, os.path.getsize(path)
+    nbytes, nbases = synth.generate_file(path, "ont", n_reads, max(100_000, int(n_reads * NS["mean_len"] / 20.8)), NS["mean_len"], seed=1)
+    return nbytes, nbases
 
 
-def run_reference_stage1(fastq, threads, stages="12"):
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")
-    with tempfile.TemporaryDirectory() as tmp:
-        out = subprocess.run([exe, "compress-ont", "-k", str(NS["k"]), "-a", str(NS_S2["anchor_len"]), "-t", str(threads), fastq, os.path.join(tmp, "x.out")],
-                             cwd=tmp, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=1800,
-                             env=dict(os.environ, COLORD_TIME_STAGES=stages))
-    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
-    return json.loads(line)
+def run_cli(exe, fastq, out, extra=()):
+    """One `compress-ont` run at the north star's preset (k / anchor length forced to what a 50 GB input selects).  -> (wall s, stream sizes)"""
+    import re
+    cmd = [exe, "compress-ont", "-k", str(NS["k"]), "-a", str(NS_S2["anchor_len"]), *extra, fastq, out]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=3600, cwd=os.path.dirname(out))
+    dt = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError(f"{os.path.basename(exe)} failed: {r.stderr[-300:]}")
+    sizes = {k: int(m.group(1)) for name, k in SIZE_KEYS for m in [re.search(rf"^{name} size\s*:\s*(\d+)", r.stderr, re.M)] if m}
+    return dt, sizes
 
 
-def run_port_stage1(s):
-    """Fallback CPU baseline: the scalar C oracle (single thread)."""
+def run_port_stage1(n_reads=2000):
+    """Fallback CPU baseline where the reference binary is missing: the scalar C oracle (single thread), stage 1 only."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib
+    from colord_b200 import synth
+    s = synth.generate(n_reads, 1_000_000, NS["mean_len"], seed=1, profile="ont")
     t0 = time.time()
     km, ct, st = oracle_lib.count_kmers(s.bases, s.offsets, NS["k"], NS["modulo"], NS["min_count"], NS["max_count"])
     off, acc = oracle_lib.accepted_kmers(s.bases, s.offsets, NS["k"], NS["modulo"], km)
     rng = max(1, int(st["n_unique_counted"] * NS["modulo"] / NS["mean_len"]))
     sampled = oracle_lib.sampler(rng, 1.0, 0, s.n_reads)
     oracle_lib.sim_graph(off, acc, np.zeros(s.n_reads, np.uint8), sampled, NS["max_candidates"], NS["max_count"])
-    return time.time() - t0
+    return s.fastq_bytes(), time.time() - t0
 
 
-def cpu_baseline(sample_reads=12500, stages="12"):
+def cpu_baseline(sample_reads=25000, with_ratio_check=True):
+    """The stock reference on a 400 MB sample of the workload, once; beside it the command line of this repo on the SAME file
+    (ratio_check: archive sizes of both, and file -> archive MB/s of colord-b200 in both stream formats)."""
     cores = os.cpu_count() or 1
+    if not os.path.exists(REF_BIN):
+        nbytes, dt = run_port_stage1()
+        return {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port", "sample": "2 000 synthetic ONT reads; oracle/stage1.c scalar port, stage 1 only"}, None
     with tempfile.TemporaryDirectory() as tmp:
         fq = os.path.join(tmp, "sample.fastq")
-        s, nbytes = reference_sample_fastq(fq, sample_reads)
-        desc = f"{s.n_reads} synthetic ONT reads, {s.n_bases} bases, {nbytes} FASTQ bytes (BASELINE.md §2 recipe, seed 1), -k {NS['k']}"
-        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")):
-            r = run_reference_stage1(fq, cores, stages)
-            what = "CKmerCounter+CKmerFilter+CReadsSimilarityGraph" + {"12qdh": "+CEncoder threads+CEntrComprReads+CEntrComprQuals+CEntrComprHeaders (stages 1+2+3)", "12qd": "+CEncoder threads+CEntrComprReads+CEntrComprQuals (stages 1+2+3 without the header coder)", "12q": "+CEncoder threads+CEntrComprQuals (stages 1+2+quality stream)", "12": "+CEncoder threads (stages 1+2)", "1": " (stage 1 only)"}[stages]
-            return {"value": nbytes / r["stage1_s"] / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference",
-                    "sample": desc + "; unmodified reference " + what, "detail": r}
-        dt = run_port_stage1(s)
-        return {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": 1, "kind": "port", "sample": desc + "; oracle/stage1.c scalar port"}
+        nbytes, nbases = sample_fastq(fq, sample_reads)
+        dt, ref_sizes = run_cli(REF_BIN, fq, os.path.join(tmp, "ref.colord"), ["-t", str(cores)])
+        ref_bytes = os.path.getsize(os.path.join(tmp, "ref.colord"))
+        base = {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference", "wall_s": dt,
+                "sample": f"{sample_reads} synthetic ONT reads of the workload, {nbases} bases, {nbytes} FASTQ bytes; unmodified `colord compress-ont -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}`, "
+                          "wall time process start -> exit, one run"}
+        check = None
+        if with_ratio_check and os.path.exists(OUR_CLI):
+            check = {"config": f"compress-ont default on the same {nbytes}-byte FASTQ file", "ref_bytes": ref_bytes, "ref_streams": ref_sizes}
+            for fmt in ("native", "compat"):
+                try:
+                    t, sizes = run_cli(OUR_CLI, fq, os.path.join(tmp, fmt + ".colord"), ["--" + fmt])
+                    ours = os.path.getsize(os.path.join(tmp, fmt + ".colord"))
+                    check[fmt] = {"ours_bytes": ours, "ratio": ours / ref_bytes, "streams": sizes, "file_to_archive_MBps": nbytes / t / 1e6, "wall_s": t}
+                except Exception as ex:
+                    check[fmt] = {"error": str(ex)[:300]}
+            check["ours_bytes"] = check.get("native", {}).get("ours_bytes")
+        return base, check
 
 
 def main_reference(args):
@@ -199,25 +224,33 @@ def main_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_stage1_time")
+    n_reads = int(os.environ.get("BENCH_REF_READS", "62500"))      # 0.5 Gbases = 1 GB of FASTQ per step: ~10 s on 16 cores
+    kind = "reference" if os.path.exists(REF_BIN) else "port"
+    times, sizes, nbytes, nbases = [], {}, 0, 0
     with tempfile.TemporaryDirectory() as tmp:
-        fq = os.path.join(tmp, "sample.fastq")
-        s, nbytes = reference_sample_fastq(fq)
-        times = []
-        kind = "reference" if os.path.exists(exe) else "port"
+        if kind == "reference":
+            fq = os.path.join(tmp, "sample.fastq")
+            nbytes, nbases = sample_fastq(fq, n_reads)
         for i in range(args.warmup + args.steps):
-            dt = run_reference_stage1(fq, cores, args.stages)["stage1_s"] if kind == "reference" else run_port_stage1(s)
+            if kind == "reference":
+                dt, sizes = run_cli(REF_BIN, fq, os.path.join(tmp, "ref.colord"), ["-t", str(cores)])
+            else:
+                nbytes, dt = run_port_stage1()
             if i >= args.warmup:
                 times.append(dt)
+        archive = os.path.getsize(os.path.join(tmp, "ref.colord")) if kind == "reference" else None
     ms = 1e3 * sum(times) / len(times)
     v = nbytes / (ms / 1e3) / 1e6
-    sample = f"{s.n_reads} synthetic ONT reads / {s.n_bases} bases / {nbytes} FASTQ bytes per step (bounded sample of the workload)"
+    sample = (f"{n_reads} synthetic ONT reads of the workload / {nbases} bases / {nbytes} FASTQ bytes per step (bounded sample); the unmodified reference CLI "
+              f"`colord compress-ont -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}` (stock code path, file in -> archive out, wall time process start -> exit)"
+              if kind == "reference" else "oracle/stage1.c scalar port, stage 1 only (the reference binary is not built here)")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": "MB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, None),
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
+        "archive_bytes": archive, "stream_bytes": sizes,
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -471,31 +504,40 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        # roofline of the dominant kernel class of the step: ALGORITHMIC bytes / device time
-        alg = {"k_count": 0.5 + 16.0 / p["modulo"],                    # packed + 2 masks read, one 8 B key+count RMW per passing k-mer
-               "k_accept": 0.5 + 12.0 / p["modulo"],
-               "k_anchors": 0.25 * (1 + 2 * p["max_candidates"]),      # the read + both strands of c candidates, 2-bit packed
-               "k_align": 0.25 + 0.25 + 1.0,                           # the two parts (2-bit) read, one script byte written per symbol
-               "k_decide": 1.0, "k_emit": 1.0 + 1.25,                  # scripts read, CompactES bytes written
-               "k_qual": 2 * (1.0 + 0.25) + 0.25,                      # two passes over qualities + packed bases, stream written
-               "k_dna": 2 * (1.25 + 0.25) + 0.25,                      # two passes over the tuples + reference bases for the contexts, stream written
-               "k_hdr": 0.03}                                          # ~3 passes over ~50 header bytes per 8 kb read
+        # roofline of the dominant kernel GROUP of the step: ALGORITHMIC bytes per base of SURVEY.md §8(d) (restated in DESIGN.md §4)
+        # x the bases of the job / the group's device time (CUDA events on the launching streams, summed over its launches)
+        f, cnd = float(p["modulo"]), float(p["max_candidates"])
+        groups = {      # name: (kernel classes, algorithmic bytes per input base)
+            "ingest (k_pack)": (["k_pack"], 0.25 + 1.0),
+            "K1+K2 count + threshold": (["k_count", "k_tab_misc", "k_finalize"], 0.25 + 16.0 / f),
+            "K3+K4 accepted k-mers + graph": (["k_accept", "k_postings", "k_vote", "k_common"], 0.25 + 4.0 / f + 12.0 / f),
+            "K5-K9 anchors + edit script": (["k_anchors", "k_align", "k_encode", "k_decide", "k_estimate", "k_emit"], 0.25 * (1 + 2 * cnd) + 1.25),
+            "K10 DNA entropy": (["k_dna"], 1.25 + 0.25 + 0.25),
+            "K11 quality entropy": (["k_qual"], 1.0 + 0.25 + 0.25),
+            "K12 headers": (["k_hdr"], 0.03),
+        }
         per_step = {k: v[0] / max(1, args.steps) for k, v in prof.items() if v[1]}
         roof = None
         if per_step:
-            top = max((k for k in per_step if k in alg), key=lambda k: per_step[k])
-            k_ms, k_n = prof[top]
-            achieved = alg[top] * n_bases_local / (per_step[top] / 1e3) / 1e9
+            g_ms = {g: sum(per_step.get(k, 0.0) for k in ks) for g, (ks, _) in groups.items()}
+            g_n = {g: sum(prof.get(k, (0, 0))[1] for k in ks) // max(1, args.steps) for g, (ks, _) in groups.items()}
+            top = max(g_ms, key=lambda g: g_ms[g])
+            alg_b = groups[top][1]
+            achieved = alg_b * n_bases_local / (g_ms[top] / 1e3) / 1e9
             traffic = None
-            try:      # DRAM bytes per launch of this kernel from the committed ncu --set full capture
-                with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
-                    traffic = json.load(f)[top]["traffic_bytes_per_launch"]
+            try:      # DRAM bytes of the group from an ncu pass (profiles/r02_group_traffic.json: bytes per Gbase of input), per launch like `achieved`
+                with open(os.path.join(ROOT, "profiles", "r02_group_traffic.json")) as fh:
+                    traffic = json.load(fh)[top]["dram_bytes_per_gbase"] * (n_bases_local / 1e9) / max(1, g_n[top])
             except Exception:
                 pass
-            roof = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "launches": k_n // max(1, args.steps), "ms_per_launch": k_ms / max(1, k_n),
-                    "algorithmic_bytes_per_base": alg[top],
-                    "note": "k_align is bound by the dependent-issue latency of the bit-vector recurrence, not by HBM (profiles/r01_summary.md)" if top == "k_align" else None,
+            roof = {"kernel": top, "kernels": groups[top][0], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "launches": g_n[top], "ms_per_launch": g_ms[top] / max(1, g_n[top]),
+                    "algorithmic_bytes_per_base": alg_b, "algorithmic_bytes_per_launch": alg_b * n_bases_local / max(1, g_n[top]),
+                    "groups": {g: {"ms_per_step": g_ms[g], "algorithmic_bytes_per_base": groups[g][1], "achieved_GBps": groups[g][1] * n_bases_local / (g_ms[g] / 1e3) / 1e9 if g_ms[g] else None,
+                                   "frac": groups[g][1] * n_bases_local / (g_ms[g] / 1e3) / 1e9 / peak if g_ms[g] else None} for g in groups},
+                    "whole_path": {"algorithmic_bytes_per_base": sum(v[1] for v in groups.values()), "achieved_GBps": sum(v[1] for v in groups.values()) * n_bases_local / (ms / 1e3) / 1e9,
+                                   "frac": sum(v[1] for v in groups.values()) * n_bases_local / (ms / 1e3) / 1e9 / peak},
+                    "note": "the edit-script group is bound by the dependent-issue latency of the bit-vector recurrence and by divergent walks, not by HBM (profiles/)",
                     "kernel_ms_per_step": per_step}
         line = {
             "metric": metric_name(args), "value": value, "unit": "MB/s",
@@ -506,7 +548,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(stages=args.stages)
+                line["cpu_baseline"], line["ratio_check"] = cpu_baseline()
             except Exception as ex:      # keep the GPU numbers even if the host baseline cannot run
                 line["cpu_baseline"] = {"value": None, "unit": "MB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
         print(json.dumps(line))

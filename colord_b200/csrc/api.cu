@@ -69,7 +69,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
-	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release();
+	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release(); c->dq.release();
 	if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -104,6 +104,24 @@ clb_status clb_append_reads(clb_ctx* c, const uint8_t* bases, const uint64_t* of
 	CLB_ENTER(c);
 	if (n_reads && (!offsets || !bases)) return fail(c, CLB_ERR_BAD_ARG, "null bases/offsets");
 	return s1a_append(c, bases, offsets, n_reads, on_device);
+}
+void* clb_host_alloc(uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+void clb_host_free(void* p) { if (p) cudaFreeHost(p); }
+clb_status clb_append_quals(clb_ctx* c, const uint8_t* quals, uint64_t n, int on_device)
+{
+	CLB_ENTER(c);
+	if (n && !quals) return fail(c, CLB_ERR_BAD_ARG, "null qualities");
+	if (!c->dq.cap) { const uint64_t hint = c->prm.expected_bases + c->prm.expected_bases / 16 + 1024; CLB_CUDA(c, c->dq.reserve(std::max(hint, n) + 16, c->stream, false)); }
+	else CLB_CUDA(c, c->dq.reserve(c->dq_n + n + 16, c->stream, true, c->dq_n));
+	if (n) CLB_CUDA(c, cudaMemcpyAsync(c->dq.p + c->dq_n, quals, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+	CLB_CUDA(c, cudaStreamSynchronize(c->stream));      // the caller may reuse its buffer
+	c->dq_n += n;
+	return CLB_OK;
 }
 clb_status clb_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n) { CLB_ENTER(c); return s1a_counts_size(c, part, n_parts, n); }
 clb_status clb_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n, int on_device)
@@ -349,13 +367,13 @@ clb_status clb_xstream_get(clb_ctx* c, uint32_t which, uint8_t* bytes, uint64_t 
 clb_status clb_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	CLB_ENTER(c);
-	if (!prm || !quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	if (!prm || (quals && !offsets)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
 	return s3_qual_encode(c, prm, quals, offsets, on_device, pack_sizes, n_packs);
 }
 clb_status clb_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device, const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	CLB_ENTER(c);
-	if (!quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	if (quals && !offsets) return fail(c, CLB_ERR_BAD_ARG, "null argument");
 	return s3_qual_encode_original(c, source, level, quals, offsets, on_device, pack_sizes, n_packs);
 }
 clb_status clb_qual_size(clb_ctx* c, uint64_t* total)

@@ -109,6 +109,8 @@ struct clb_ctx {
 	uint64_t n_bases = 0;
 	std::vector<uint64_t> h_rd_start; // host mirrors (small: 12 B per read)
 	std::vector<uint32_t> h_rd_len;
+	clb::DevBuf<uint8_t> dq;            // qualities kept on the device as the input streams in (clb_append_quals), read order
+	uint64_t dq_n = 0;
 	clb::DevBuf<uint8_t> stage_in[2];   // double-buffered staging for host ASCII input
 	clb::DevBuf<uint64_t> stage_off;
 
@@ -237,6 +239,9 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 clb_status s3_qual_flags(clb_ctx* c, const uint64_t* d_qoff, uint32_t n, uint8_t* d_flags);
 clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
+// qualities of the non-context reads: the caller's (host or device) or, with quals == NULL, the resident ones of clb_append_quals.
+// h_off[n + 1] receives the offsets on the host, d_q the device pointer of the first quality (staged through `tmp_alloc` if needed).
+clb_status resolve_quals(clb_ctx* c, const uint8_t* quals, const uint64_t* offsets, int on_device, cudaStream_t s, std::vector<uint64_t>& h_off, bool& resident);
 clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t level, const uint32_t* thr, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);

@@ -22,6 +22,8 @@
 #include "dna_model.h"
 #include "hdr_model.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <cstring>
 #include <vector>
 
@@ -56,32 +58,93 @@ __global__ void __launch_bounds__(256) k_x_iota(uint32_t* __restrict__ v, uint64
 	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) v[i] = (uint32_t)i;
 }
-// triple of an event: frequency | cumulative frequency << 21 | total << 42 (total < max_total + adder <= 2^20 + 64)
-__global__ void __launch_bounds__(128) k_x_model(const uint64_t* __restrict__ key, const uint32_t* __restrict__ idx, const uint16_t* __restrict__ info,
-	uint64_t n, XFams fams, uint64_t* __restrict__ triple)
+// What the model leaves at an event for the range coder: x = frequency | cumulative frequency << 21 | total << 42 (total < max_total
+// + adder <= 2^20 + 64) and y = floor((2^64 - 1) / total), with which the coder's `range / total` is one multiply-high and a fix-up.
+CLB_D ulonglong2 x_triple(uint32_t freq, uint32_t cum, uint32_t tot) { return make_ulonglong2((uint64_t)freq | ((uint64_t)cum << 21) | ((uint64_t)tot << 42), ~0ull / tot); }
+
+__global__ void __launch_bounds__(256) k_x_heads(const uint64_t* __restrict__ key, uint64_t n, uint8_t* __restrict__ flag)
 {
-	const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i0 >= n) return;
-	const uint64_t k = key[i0];
-	if (i0 && key[i0 - 1] == k) return;                 // not the first event of its context
-	const XFam F = fams.f[k >> X_CTX_BITS];
-	const uint32_t A = F.n_sym;
-	uint32_t c[256];                                      // Init(nullptr): all counts 1 (rc.h:122-124, :329-331, :706)
-	for (uint32_t s = 0; s < A; ++s) c[s] = 1;
-	uint32_t total = A;
-	for (uint64_t i = i0; i < n && key[i] == k; ++i) {
-		const uint32_t e = idx[i], in = info[e], sym = in & 0xff, excl = in >> 8;
-		uint32_t cum = 0, tot = total;
-		for (uint32_t s = 0; s < sym; ++s) if (!(s < 8 && (excl >> s & 1))) cum += c[s];
-		if (excl) for (uint32_t s = 0; s < 8 && s < A; ++s) if (excl >> s & 1) tot -= c[s];
-		triple[e] = (uint64_t)c[sym] | ((uint64_t)cum << 21) | ((uint64_t)tot << 42);
-		c[sym] += F.adder; total += F.adder;              // Update (rc.h:178-185)
-		while (total >= F.max_total) { uint32_t t = 0; for (uint32_t s = 0; s < A; ++s) { c[s] = (c[s] + 1) >> 1; t += c[s]; } total = t; }
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) flag[i] = i == 0 || key[i - 1] != key[i];
+}
+// One WARP per context (heads[s] = first sorted position of context s; grid-stride over the contexts).  Counts, +adder, halving at
+// max_total, Encode / EncodeExcluding: rc.h:122-221, :780-803, :861-893.
+//   alphabets up to 8 symbols (every family with exclusions is one): 32 events per step — lane i takes event i, the counts it meets
+//     are the step's base counts + adder x (events of that symbol in the lanes before it: one ballot per symbol); a step ends where the
+//     total would reach max_total, the halving is applied between steps
+//   larger alphabets: events one by one, the counters spread over the lanes (lane l holds symbols l, l + 32, ...), cumulative frequency by
+//     a warp reduction
+__global__ void __launch_bounds__(128) k_x_model(const uint64_t* __restrict__ key, const uint32_t* __restrict__ idx, const uint16_t* __restrict__ info,
+	uint64_t n, const uint32_t* __restrict__ heads, const uint32_t* __restrict__ n_heads_p, XFams fams, ulonglong2* __restrict__ triple)
+{
+	const uint32_t lane = threadIdx.x & 31, n_heads = *n_heads_p;
+	const uint32_t lt = (1u << lane) - 1;
+	for (uint64_t sg = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; sg < n_heads; sg += ((uint64_t)gridDim.x * blockDim.x) >> 5) {
+		const uint64_t i0 = heads[sg], i1 = sg + 1 < n_heads ? heads[sg + 1] : n;
+		const XFam F = fams.f[key[i0] >> X_CTX_BITS];
+		const uint32_t A = F.n_sym;
+		if (A <= 8) {
+			uint32_t cb[8];
+#pragma unroll
+			for (int s = 0; s < 8; ++s) cb[s] = 1;
+			uint32_t tb = A;
+			for (uint64_t i = i0; i < i1;) {
+				const bool valid = i + lane < i1;
+				uint32_t e = 0, sym = 0, excl = 0;
+				if (valid) { e = idx[i + lane]; const uint32_t in = info[e]; sym = in & 0xff; excl = in >> 8; }
+				uint32_t n_step = __popc(__ballot_sync(0xffffffffu, valid));
+				n_step = min(n_step, (F.max_total - tb + F.adder - 1) / F.adder);      // the n_step-th event's update is the first to reach max_total
+				const bool mine = lane < n_step;
+				uint32_t cum = 0, tot = tb + F.adder * lane, freq = 0;
+#pragma unroll
+				for (int s = 0; s < 8; ++s) {
+					const uint32_t m = __ballot_sync(0xffffffffu, mine && sym == (uint32_t)s);
+					const uint32_t c = cb[s] + F.adder * __popc(m & lt);
+					const bool ex = (excl >> s) & 1;
+					if ((uint32_t)s < sym && !ex) cum += c;
+					if (ex && (uint32_t)s < A) tot -= c;
+					if ((uint32_t)s == sym) freq = c;
+					cb[s] += F.adder * __popc(m);
+				}
+				if (mine) triple[e] = x_triple(freq, cum, tot);
+				tb += F.adder * n_step;
+				while (tb >= F.max_total) {
+					uint32_t t = 0;
+#pragma unroll
+					for (int s = 0; s < 8; ++s) { cb[s] = (cb[s] + 1) >> 1; if ((uint32_t)s < A) t += cb[s]; }
+					tb = t;
+				}
+				i += n_step;
+			}
+		} else {
+			uint32_t c[8];                                    // symbol lane + 32 j
+#pragma unroll
+			for (int j = 0; j < 8; ++j) c[j] = lane + 32 * j < A ? 1u : 0u;
+			uint32_t total = A;
+			for (uint64_t i = i0; i < i1; ++i) {
+				const uint32_t e = idx[i], sym = info[e] & 0xff;
+				uint32_t part = 0, mine = 0;
+#pragma unroll
+				for (int j = 0; j < 8; ++j) { const uint32_t s = lane + 32 * j; if (s < sym) part += c[j]; if (s == sym) mine = c[j]; }
+				const uint32_t cum = __reduce_add_sync(0xffffffffu, part);
+				const uint32_t freq = __shfl_sync(0xffffffffu, mine, sym & 31);
+				if (lane == 0) triple[e] = x_triple(freq, cum, total);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) if (lane + 32 * j == sym) c[j] += F.adder;
+				total += F.adder;
+				while (total >= F.max_total) {
+					uint32_t t = 0;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) { c[j] = lane + 32 * j < A ? (c[j] + 1) >> 1 : 0u; t += c[j]; }
+					total = __reduce_add_sync(0xffffffffu, t);
+				}
+			}
+		}
 	}
 }
 
 // ---- 3. range coder: one thread per pack (sub_rc.h:72-211) -------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_x_code(const uint64_t* __restrict__ triple, const uint64_t* __restrict__ pack_ev, uint32_t n_packs,
+__global__ void __launch_bounds__(32) k_x_code(const ulonglong2* __restrict__ triple, const uint64_t* __restrict__ pack_ev, uint32_t n_packs,
 	uint8_t* __restrict__ tmp, const uint64_t* __restrict__ tmp_off, uint64_t* __restrict__ part_bytes)
 {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,17 +152,15 @@ __global__ void __launch_bounds__(32) k_x_code(const uint64_t* __restrict__ trip
 	uint8_t* out = tmp + tmp_off[p];
 	uint64_t n = 0;
 	unsigned long long low = 0, range = 0xff00000000000000ULL;
-	for (uint64_t e = pack_ev[p]; e < pack_ev[p + 1]; ++e) {
-		const uint64_t t = triple[e];
-		const uint32_t freq = (uint32_t)(t & 0x1fffff), cum = (uint32_t)((t >> 21) & 0x1fffff), tot = (uint32_t)(t >> 42);
-		{	// range /= tot without a 64-bit division: high word by a 32-bit division, low word through a double (numerator < 2^53) + fix-up
-			const uint32_t hi = (uint32_t)(range >> 32), q1 = hi / tot, r1 = hi - q1 * tot;
-			const unsigned long long num = ((unsigned long long)r1 << 32) | (uint32_t)range;
-			unsigned long long q0 = (unsigned long long)__ddiv_rn((double)num, (double)tot);
-			long long rem = (long long)(num - q0 * tot);
-			if (rem < 0) --q0; else if (rem >= (long long)tot) ++q0;
-			range = ((unsigned long long)q1 << 32) + q0;
-		}
+	const uint64_t e0 = pack_ev[p], e1 = pack_ev[p + 1];
+	ulonglong2 nxt = e0 < e1 ? triple[e0] : make_ulonglong2(0, 0);
+	for (uint64_t e = e0; e < e1; ++e) {
+		const ulonglong2 t = nxt;
+		if (e + 1 < e1) nxt = triple[e + 1];                 // the next event's triple is on its way while this one is coded
+		const uint32_t freq = (uint32_t)(t.x & 0x1fffff), cum = (uint32_t)((t.x >> 21) & 0x1fffff), tot = (uint32_t)(t.x >> 42);
+		unsigned long long q = __umul64hi(range, t.y);        // range / tot: t.y = floor((2^64 - 1) / tot) gives the quotient or one less
+		if (range - q * tot >= tot) ++q;
+		range = q;
 		low += range * cum;
 		range *= freq;
 		for (int k = 0; k < 8 && range <= 0x00ffffffffffffULL; ++k) {      // UNROLL_FREQUENCY_CODING: at most 8 bytes per symbol
@@ -131,8 +192,8 @@ static clb_status x_code_stream(clb_ctx* c, cudaStream_t s, int kid, const XFams
 	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
 	auto timed_begin = [&]() { if (s == c->stream3) prof_begin3(c, kid); else prof_begin(c, kid); };
 	auto timed_end = [&]() { if (s == c->stream3) prof_end3(c); else prof_end(c); };
-	uint64_t* d_triple = nullptr;
-	CLB_CUDA(c, dalloc((void**)&d_triple, sizeof(uint64_t) * (n_ev + 1)));
+	ulonglong2* d_triple = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_triple, sizeof(ulonglong2) * (n_ev + 1)));
 	if (n_ev) {
 		uint64_t* d_key2 = nullptr; uint32_t* d_idx = nullptr; uint32_t* d_idx2 = nullptr; void* d_sort = nullptr; size_t sort_bytes = 0;
 		CLB_CUDA(c, dalloc((void**)&d_key2, sizeof(uint64_t) * n_ev)); CLB_CUDA(c, dalloc((void**)&d_idx, sizeof(uint32_t) * n_ev)); CLB_CUDA(c, dalloc((void**)&d_idx2, sizeof(uint32_t) * n_ev));
@@ -145,7 +206,19 @@ static clb_status x_code_stream(clb_ctx* c, cudaStream_t s, int kid, const XFams
 		timed_end();
 		if (e != cudaSuccess) return cuda_fail(c, e, "cub::DeviceRadixSort::SortPairs");
 		++c->launches;
-		timed_begin(); k_x_model<<<(uint32_t)((n_ev + 127) / 128), 128, 0, s>>>(d_key2, d_idx2, d_info, n_ev, fams, d_triple); timed_end(); CLB_LAUNCH_CHECK(c, "k_x_model");
+		// the first sorted position of every context (flag + CUB select: plumbing), then one warp per context
+		uint8_t* d_flag = nullptr; uint32_t* d_heads = nullptr; uint32_t* d_n_heads = nullptr; void* d_sel = nullptr; size_t sel_bytes = 0;
+		CLB_CUDA(c, dalloc((void**)&d_flag, n_ev)); CLB_CUDA(c, dalloc((void**)&d_heads, sizeof(uint32_t) * n_ev)); CLB_CUDA(c, dalloc((void**)&d_n_heads, 4));
+		timed_begin(); k_x_heads<<<(uint32_t)((n_ev + 255) / 256), 256, 0, s>>>(d_key2, n_ev, d_flag); timed_end(); CLB_LAUNCH_CHECK(c, "k_x_heads");
+		cub::CountingInputIterator<uint32_t> first(0);
+		CLB_CUDA(c, cub::DeviceSelect::Flagged(nullptr, sel_bytes, first, d_flag, d_heads, d_n_heads, (unsigned long long)n_ev, s));
+		CLB_CUDA(c, dalloc(&d_sel, sel_bytes));
+		timed_begin();
+		e = cub::DeviceSelect::Flagged(d_sel, sel_bytes, first, d_flag, d_heads, d_n_heads, (unsigned long long)n_ev, s);
+		timed_end();
+		if (e != cudaSuccess) return cuda_fail(c, e, "cub::DeviceSelect::Flagged");
+		++c->launches;
+		timed_begin(); k_x_model<<<c->n_sm * 16, 128, 0, s>>>(d_key2, d_idx2, d_info, n_ev, d_heads, d_n_heads, fams, d_triple); timed_end(); CLB_LAUNCH_CHECK(c, "k_x_model");
 	}
 	// temp slot of a pack: at most 21 bits leave the coder per event (frequency >= 1 of a total < 2^21), + the 8-byte flush
 	std::vector<uint64_t> tmp_off(np + 1, 0);
@@ -387,11 +460,9 @@ clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t 
 	uint64_t* d_key = nullptr; uint16_t* d_info = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_key, sizeof(uint64_t) * (n_ev + 1))); CLB_CUDA(c, dalloc((void**)&d_info, sizeof(uint16_t) * (n_ev + 1)));
 	if (mode != 8 && n) {
-		if (!quals || !offsets) return fail(c, CLB_ERR_BAD_ARG, "clb_xqual_encode: no qualities given");
-		std::vector<uint64_t> h_off(n + 1);
-		if (on_device) { CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s)); CLB_CUDA(c, cudaStreamSynchronize(s)); }
-		else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
-		for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+		std::vector<uint64_t> h_off; bool resident = false;
+		{ const clb_status st = resolve_quals(c, quals, offsets, on_device, s, h_off, resident); if (st != CLB_OK) return st; }
+		if (resident) { quals = c->dq.p; on_device = 1; }
 		const uint64_t tot = h_off[n] - h_off[0];
 		uint64_t* d_qoff = nullptr; uint64_t* d_ev_off = nullptr;
 		CLB_CUDA(c, dalloc((void**)&d_qoff, sizeof(uint64_t) * (n + 1))); CLB_CUDA(c, dalloc((void**)&d_ev_off, sizeof(uint64_t) * (n + 1))); CLB_CUDA(c, dalloc((void**)&a.bad, 4));

@@ -84,11 +84,9 @@ clb_status s3_qual_encode_original(clb_ctx* c, uint32_t source, uint32_t level, 
 		if (pack_first.back() != n) pack_first.push_back((uint32_t)n);
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
-	std::vector<uint64_t> h_off(n + 1);
-	if (on_device) CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
-	else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
-	CLB_CUDA(c, cudaStreamSynchronize(s));
-	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[nc + i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+	std::vector<uint64_t> h_off; bool resident = false;
+	{ const clb_status st = resolve_quals(c, quals, offsets, on_device, s, h_off, resident); if (st != CLB_OK) return st; }
+	if (resident) { quals = c->dq.p; on_device = 1; }
 	const uint64_t tot = h_off[n] - h_off[0];
 	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) dev_free_async(p, s); } } tmp{{}, s};
 	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };

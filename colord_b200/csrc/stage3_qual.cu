@@ -53,6 +53,23 @@ CLB_D uint32_t q_context(const QArgs& a, uint64_t rs, uint32_t n, const uint8_t*
 	return c;
 }
 
+clb_status resolve_quals(clb_ctx* c, const uint8_t* quals, const uint64_t* offsets, int on_device, cudaStream_t s, std::vector<uint64_t>& h_off, bool& resident)
+{
+	const uint64_t nc = c->n_context, n = c->n_reads - nc;
+	h_off.assign(n + 1, 0);
+	resident = quals == nullptr;
+	if (resident) {
+		for (uint64_t i = 0; i < n; ++i) h_off[i + 1] = h_off[i] + c->h_rd_len[nc + i];
+		if (h_off[n] != c->dq_n) return fail(c, CLB_ERR_STATE, "no qualities given and the resident ones (clb_append_quals) do not cover the reads");
+		return CLB_OK;
+	}
+	if (!offsets) return fail(c, CLB_ERR_BAD_ARG, "qualities without offsets");
+	if (on_device) { CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s)); CLB_CUDA(c, cudaStreamSynchronize(s)); }
+	else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
+	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[nc + i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+	return CLB_OK;
+}
+
 // per-base flags from the tuples (quality_coder_impl.cpp:25-76); one thread per read
 __global__ void __launch_bounds__(128) k_q_flags(const uint8_t* __restrict__ es, const uint64_t* __restrict__ es_off, const uint64_t* __restrict__ qoff,
 	const uint32_t* __restrict__ rd_len, uint32_t n_reads, uint8_t* __restrict__ flags)
@@ -253,11 +270,9 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	}
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
 	// qualities on the device
-	std::vector<uint64_t> h_off(n + 1);
-	if (on_device) CLB_CUDA(c, cudaMemcpyAsync(h_off.data(), offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s));
-	else std::memcpy(h_off.data(), offsets, sizeof(uint64_t) * (n + 1));
-	CLB_CUDA(c, cudaStreamSynchronize(s));
-	for (uint64_t i = 0; i < n; ++i) if (h_off[i + 1] - h_off[i] != c->h_rd_len[nc + i]) return fail(c, CLB_ERR_BAD_ARG, "quality lengths differ from the read lengths");
+	std::vector<uint64_t> h_off; bool resident = false;
+	{ const clb_status st = resolve_quals(c, quals, offsets, on_device, s, h_off, resident); if (st != CLB_OK) return st; }
+	if (resident) { quals = c->dq.p; on_device = 1; }
 	const uint64_t tot = h_off[n] - h_off[0];
 	struct Tmp { std::vector<void*> v; cudaStream_t s; ~Tmp() { for (void* p : v) dev_free_async(p, s); } } tmp{{}, s};
 	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };

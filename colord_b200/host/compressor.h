@@ -28,7 +28,7 @@ namespace clbhost {
 
 struct Phase { const char* name; double seconds; };
 struct CompressionReport {            // what the reference prints at the end (compression.cpp:795-808)
-	bool compat = false; std::vector<Phase> phases;
+	bool compat = false, streamed = false; unsigned reader_threads = 1; std::vector<Phase> phases;
 	uint64_t dna = 0, qual = 0, header = 0, meta = 0, info = 0, archive = 0;
 	uint32_t kmerLen = 0, anchorLen = 0, sparse_range = 0, tot_ref_reads = 0;
 	clb_kmer_stats stats{};
@@ -47,7 +47,7 @@ inline void refuse_unsupported(const CCompressorParams& p, bool compat = false)
 	}
 }
 
-inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive);
+inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive, bool allow_streaming);
 
 // The output is opened only once the input has been read and the parameters accepted, and a run that fails removes what it
 // wrote: no truncated file is left looking like an archive.
@@ -56,27 +56,71 @@ inline CompressionReport runCompression(const CCompressorParams& params, CInfo& 
 	refuse_unsupported(params, params.streamFormat != StreamFormat::Native);
 	CArchive archive(false);
 	try {
-		return runCompressionTo(params, info, archive);
+		try {
+			return runCompressionTo(params, info, archive, true);
+		} catch (const StreamingFallback&) {      // the streaming reader met an irregular input: the whole-file reader decides (nothing has been written yet)
+			return runCompressionTo(params, info, archive, false);
+		}
 	} catch (...) {
 		if (archive.IsOpen()) { archive.Abandon(); std::remove(params.outputFilePath.c_str()); }
 		throw;
 	}
 }
 
-inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive)
+inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo& info, CArchive& archive, bool allow_streaming)
 {
 	const auto t0 = std::chrono::steady_clock::now();
 	CompressionReport rep;
 	info.version_major = B200_VERSION_MAJOR; info.version_minor = B200_VERSION_MINOR; info.version_patch = B200_VERSION_PATCH;
+	std::vector<Phase> phases; auto t_ph = t0;
+	auto phase = [&](const char* name) { const auto t = std::chrono::steady_clock::now(); phases.push_back(Phase{name, std::chrono::duration<double>(t - t_ph).count()}); t_ph = t; };
 
-	CInputReads in(params.inputFilePath);
+	// Input.  Plain FASTQ files stream: pieces parsed by a pool of threads go to the device as they arrive (clb_append_reads +
+	// clb_append_quals: stage 1a and the copies overlap the parsing, the host keeps only the headers).  Everything else (FASTA, gzip,
+	// small or irregular files) is read whole first.  The reference reads its input twice, through KMC and through CInputReads.
+	uint64_t file_bytes = 0; bool is_gzip = false, fastq_guess = false;
+	const bool stream = CInputReads::streamable(params.inputFilePath, file_bytes, is_gzip, fastq_guess) && allow_streaming;
+	uint32_t kmerLen = params.kmerLen, anchorLen = params.anchorLen;
+	const bool hifi = params.dataSource == DataSource::PBHiFi;
+	std::unique_ptr<CInputReads> inp; std::unique_ptr<CKmerCounter> counter;
+	auto make_counter = [&](bool fastq, uint64_t expected_bases) {
+		adjustKmerAndAnchorLen(kmerLen, anchorLen, is_gzip, fastq, file_bytes);
+		if (params.verbose) {
+			std::cerr << (is_gzip ? "input is gzipped\n" : "input is not gzipped\n");          // compression.cpp:365-371
+			PrintParams(std::cerr, params, kmerLen, anchorLen, params.nThreads);
+		}
+		counter = std::make_unique<CKmerCounter>(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi, expected_bases, params.device);
+	};
+	if (stream) {
+		make_counter(true, file_bytes / 2);
+		clb_ctx* c0 = counter->Context();
+		phase("device context");
+		// large inputs: the piece buffers are page-locked (full-rate, asynchronous host-to-device copies); below that the time to lock
+		// them is not paid back
+		const CInputReads::HostAlloc pinned{[](uint64_t bytes) { return clb_host_alloc(bytes); }, [](void* p) { clb_host_free(p); }};
+		const bool pin = file_bytes >= (8ull << 30) || std::getenv("CLB_PIN_INPUT") != nullptr;
+		inp = std::make_unique<CInputReads>(params.inputFilePath, [c0](const uint8_t* b, const uint8_t* q, const uint64_t* off, uint32_t n) {
+			check(c0, clb_append_reads(c0, b, off, n, 0), "clb_append_reads");
+			check(c0, clb_append_quals(c0, q, off[n], 0), "clb_append_quals");
+		}, 0, 64u << 20, pin ? &pinned : nullptr);
+		phase("read input (streamed to the device, stage 1a inside)");
+	} else {
+		inp = std::make_unique<CInputReads>(params.inputFilePath);
+		is_gzip = inp->is_gzip; file_bytes = inp->file_bytes;
+		phase("read input");
+		make_counter(inp->is_fastq, inp->total_bases);
+		check(counter->Context(), clb_append_reads(counter->Context(), inp->bases.data(), inp->offsets.data(), inp->n_reads(), 0), "clb_append_reads");
+		phase("device context + reads to the device (stage 1a inside)");
+	}
+	CInputReads& in = *inp; CKmerCounter& kmer_counter = *counter;
+	clb_ctx* ctx = kmer_counter.Context();
+	rep.kmerLen = kmerLen; rep.anchorLen = anchorLen; rep.streamed = in.streamed; rep.reader_threads = in.threads_used;
+	const uint8_t* quals_ptr = in.streamed ? nullptr : in.quals.data();      // streamed: the qualities are on the device already
+	const uint64_t* quals_off = in.streamed ? nullptr : in.offsets.data();
 	const bool compat = params.streamFormat == StreamFormat::Compat || (params.streamFormat == StreamFormat::Auto && in.total_bases <= params.compat_max_bases);
 	refuse_unsupported(params, compat);
 	rep.compat = compat;
 	if (compat) { info.version_major = 1; info.version_minor = 2; info.version_patch = 1; }      // defs.h:24-26 of the reference: what its decompressor checks
-	std::vector<Phase> phases; auto t_ph = std::chrono::steady_clock::now();
-	auto phase = [&](const char* name) { const auto t = std::chrono::steady_clock::now(); phases.push_back(Phase{name, std::chrono::duration<double>(t - t_ph).count()}); t_ph = t; };
-	phase("read input");
 	if (!archive.Open(params.outputFilePath)) throw std::runtime_error("Error: cannot open archive: " + params.outputFilePath);
 	const int s_meta = archive.RegisterStream("meta");
 	auto add_part = [&](int stream_id, const std::vector<uint8_t>& data, size_t metadata) {
@@ -85,19 +129,6 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	const bool is_fastq = in.is_fastq;
 	info.total_bytes = in.total_bytes; info.total_bases = in.total_bases;
 
-	uint32_t kmerLen = params.kmerLen, anchorLen = params.anchorLen;
-	adjustKmerAndAnchorLen(kmerLen, anchorLen, in.is_gzip, is_fastq, in.file_bytes);
-	rep.kmerLen = kmerLen; rep.anchorLen = anchorLen;
-	const bool hifi = params.dataSource == DataSource::PBHiFi;
-	if (params.verbose) {
-		std::cerr << (in.is_gzip ? "input is gzipped\n" : "input is not gzipped\n");          // compression.cpp:365-371
-		PrintParams(std::cerr, params, kmerLen, anchorLen, params.nThreads);
-	}
-
-	// stage 1a: the reference reads the file a second time through KMC; here the parsed reads go to the device once
-	CKmerCounter kmer_counter(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi, in.total_bases, params.device);
-	clb_ctx* ctx = kmer_counter.Context();
-	check(ctx, clb_append_reads(ctx, in.bases.data(), in.offsets.data(), in.n_reads(), 0), "clb_append_reads");
 	const uint32_t tot_n_reads = kmer_counter.GetNReads();
 	const uint64_t tot_kmers = kmer_counter.GetTotKmers(), n_uniq_counted_kmers = kmer_counter.GetNUniqueCounted();
 	check(ctx, clb_count_finalize(ctx, &rep.stats), "clb_count_finalize");
@@ -119,7 +150,7 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 		params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
 	encoder.Encode(in.read_pack_sizes);
 
-	phase("stages 1 + 2");
+	phase("stages 1b + 2");
 	int s_dna = -1, s_qual = -1, s_header = -1;
 	if (compat) {
 		// the reference's own streams: one part per read pack / header pack (entr_read.h:56-80, entr_qual.h:100-126, entr_header.cpp:23-46)
@@ -143,7 +174,7 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 			uint32_t thr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 			for (size_t i = 0; i < params.qualityFwdThresholds.size() && i < 8; ++i) thr[i] = params.qualityFwdThresholds[i];
 			check(ctx, clb_xqual_encode(ctx, static_cast<uint32_t>(params.qualityComprMode), static_cast<uint32_t>(params.dataSource), static_cast<uint32_t>(params.compressionLevel), thr,
-				in.quals.data(), in.offsets.data(), 0, in.read_pack_sizes.data(), static_cast<uint32_t>(in.read_pack_sizes.size())), "clb_xqual_encode");
+				quals_ptr, quals_off, 0, in.read_pack_sizes.data(), static_cast<uint32_t>(in.read_pack_sizes.size())), "clb_xqual_encode");
 			add_parts(s_qual, 1, nullptr);
 			phase("quality stream");
 		}
@@ -172,8 +203,8 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 			if (params.qualityComprMode != QualityComprMode::None) {
 				const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
 				CEntrComprQuals q(kmer_counter, n_bins, params.qualityFwdThresholds, params.compressionLevel);
-				if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), in.quals.data(), in.offsets.data(), in.read_pack_sizes);
-				else q.Compress(in.quals.data(), in.offsets.data(), in.read_pack_sizes);
+				if (params.qualityComprMode == QualityComprMode::Original) q.CompressOriginal(static_cast<uint32_t>(params.dataSource), quals_ptr, quals_off, in.read_pack_sizes);
+				else q.Compress(quals_ptr, quals_off, in.read_pack_sizes);
 				stream = q.GetStream();
 			}
 			add_part(s_qual, stream, 0);

@@ -17,6 +17,11 @@
 // piece, a prefix sum places it, pass 2 checks and copies into the final arrays — each thread first-touches its own part of
 // them, which is what the reader's time goes to (page faults).  Whenever the threaded parse meets anything irregular it is
 // abandoned and the serial parser, which follows the reference line by line, decides and words the refusal.
+// Streaming form ("pinned-memory H2D double buffering", in_reads.cpp:229 — the reference's reader thread feeds
+// 32 MiB blocks to its queues while the stages run): plain FASTQ files are cut into pieces at record starts, a pool of threads
+// parses the pieces one pass each into reused buffers (a ring of slots: no page faults after the first lap, host memory bounded by
+// the ring), and the constructing thread hands every piece, in file order, to a sink — compressor.h's sink is clb_append_reads +
+// clb_append_quals, so parsing overlaps the host-to-device copies and stage 1a, and only the headers stay on the host.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -28,6 +33,10 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -37,6 +46,9 @@
 namespace clbhost {
 
 struct InputError : std::runtime_error { using std::runtime_error::runtime_error; };
+// the streaming parser met something irregular: the caller starts over with the whole-file reader, which follows the reference line
+// by line and words the refusal (or accepts the input)
+struct StreamingFallback : std::runtime_error { StreamingFallback() : std::runtime_error("irregular FASTQ: whole-file reader needed") {} };
 
 // A block of T that is NOT value-initialised: the thread that fills a part of it is the one that touches its pages first.
 template <typename T>
@@ -68,8 +80,42 @@ public:
 	std::vector<uint32_t> read_pack_sizes, header_pack_sizes;       // reads per read pack / headers per header pack
 	uint64_t total_bytes = 0, total_bases = 0, total_symb_header = 0, file_bytes = 0;
 	unsigned threads_used = 1;
+	bool streamed = false; uint64_t n_reads_streamed = 0;          // streaming form: bases / quals / offsets went to the sink, not into the blocks above
 
-	uint32_t n_reads() const { return static_cast<uint32_t>(offsets.size() - 1); }
+	uint32_t n_reads() const { return streamed ? static_cast<uint32_t>(n_reads_streamed) : static_cast<uint32_t>(offsets.size() - 1); }
+
+	// ---- streaming form ----
+	using PieceSink = std::function<void(const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n_reads)>;
+	// piece buffers: plain memory, or whatever the caller's allocator hands out (compressor.h: page-locked memory for large inputs)
+	struct HostAlloc { std::function<void*(uint64_t)> alloc; std::function<void(void*)> free; };
+	// plain (not gzipped) FASTQ of at least min_bytes: what the streaming form takes; fills file_bytes / is_gzip either way
+	static bool streamable(const std::string& path, uint64_t& file_bytes, bool& is_gzip, bool& is_fastq, uint64_t min_bytes = 64u << 20)
+	{
+		const int fd = ::open(path.c_str(), O_RDONLY);
+		if (fd < 0) throw InputError("Error: cannot open file: " + path);
+		struct stat st{};
+		uint8_t head[2] = {0, 0};
+		const bool ok = ::fstat(fd, &st) == 0;
+		const ssize_t got = ::pread(fd, head, 2, 0);
+		::close(fd);
+		if (!ok) throw InputError("Error: cannot open file: " + path);
+		file_bytes = static_cast<uint64_t>(st.st_size);
+		is_gzip = got == 2 && head[0] == 0x1f && head[1] == 0x8b;
+		is_fastq = got >= 1 && head[0] == '@';
+		if (const char* e = std::getenv("CLB_NO_STREAMING")) if (*e && *e != '0') return false;
+		return !is_gzip && is_fastq && file_bytes >= min_bytes;
+	}
+	CInputReads(const std::string& path, const PieceSink& sink, unsigned n_threads = 0, uint64_t piece_bytes = 64u << 20, const HostAlloc* host_alloc = nullptr)
+	{
+		Input in(path, *this);
+		total_bytes = in.n;
+		if (!in.n || in.p[0] != '@' || is_gzip || (in.p[in.n - 1] != '\n' && in.p[in.n - 1] != '\r')) throw StreamingFallback();
+		is_fastq = true; streamed = true;
+		if (!n_threads) { const char* e = std::getenv("CLB_READER_THREADS"); n_threads = e ? static_cast<unsigned>(std::atoi(e)) : std::thread::hardware_concurrency(); }
+		stream_fastq(in.p, in.n, std::max(1u, n_threads), std::max<uint64_t>(piece_bytes, 1u << 20), sink, host_alloc);
+		pack_sizes_from(stream_lens);
+		stream_lens = std::vector<uint32_t>();
+	}
 
 	// n_threads 0: CLB_READER_THREADS or the hardware's count; at most one thread per min_piece_bytes of input
 	explicit CInputReads(const std::string& path, unsigned n_threads = 0, uint64_t min_piece_bytes = 16u << 20)
@@ -178,6 +224,115 @@ private:
 		cur = 0; k = 0;
 		for (uint32_t i = 0; i + 1 < header_offsets.size(); ++i) { cur += header_offsets[i + 1] - header_offsets[i]; ++k; if (cur >= (2u << 21)) { header_pack_sizes.push_back(k); k = 0; cur = 0; } }
 		if (k) header_pack_sizes.push_back(k);
+	}
+
+	// ---- streaming FASTQ parser ----
+	std::vector<uint32_t> stream_lens;                               // read lengths (the pack rule needs them), dropped after construction
+	void pack_sizes_from(const std::vector<uint32_t>& lens)
+	{
+		uint64_t cur = 0; uint32_t k = 0;
+		for (uint32_t len : lens) { cur += static_cast<uint64_t>(len) + 1; ++k; if (cur >= (2u << 21)) { read_pack_sizes.push_back(k); k = 0; cur = 0; } }
+		if (k) read_pack_sizes.push_back(k);
+		cur = 0; k = 0;
+		for (uint32_t i = 0; i + 1 < header_offsets.size(); ++i) { cur += header_offsets[i + 1] - header_offsets[i]; ++k; if (cur >= (2u << 21)) { header_pack_sizes.push_back(k); k = 0; cur = 0; } }
+		if (k) header_pack_sizes.push_back(k);
+	}
+	struct Buf {
+		uint8_t* p = nullptr; const HostAlloc* A = nullptr; bool own_new = false;
+		uint8_t* get() const { return p; }
+		void reset(uint64_t bytes, const HostAlloc* a) { drop(); A = a; p = a && a->alloc ? static_cast<uint8_t*>(a->alloc(bytes)) : nullptr; if (!p) { p = new uint8_t[bytes]; own_new = true; } else own_new = false; }
+		void drop() { if (!p) return; if (own_new) delete[] p; else A->free(p); p = nullptr; }
+		~Buf() { drop(); }
+		Buf() = default; Buf(const Buf&) = delete; Buf& operator=(const Buf&) = delete;
+	};
+	struct Slot {
+		Buf bases, quals; uint64_t cap = 0;
+		std::vector<uint64_t> offsets; std::vector<uint8_t> hdr, plus; std::vector<uint64_t> hdr_off;
+		uint64_t n_bases = 0, symb = 0; bool ok = true;
+		uint64_t holds = ~0ull, free_for = 0;                          // piece parsed into the slot / piece that may be parsed into it next
+	};
+	// one pass over a piece: checks of size_piece + fill_piece, output into the slot
+	static void parse_piece(const uint8_t* pb, const uint8_t* pe, Slot& S, const HostAlloc* A)
+	{
+		const uint64_t need = static_cast<uint64_t>(pe - pb) / 2 + 64;
+		if (need > S.cap) { S.cap = need + need / 8; S.bases.reset(S.cap, A); S.quals.reset(S.cap, A); }
+		S.offsets.clear(); S.offsets.push_back(0); S.hdr.clear(); S.plus.clear(); S.hdr_off.clear(); S.hdr_off.push_back(0);
+		S.n_bases = 0; S.symb = 0; S.ok = true;
+		const uint8_t* p = pb; const uint8_t *b, *e; int where = 0;
+		const uint8_t* hdr = nullptr; size_t hdr_n = 0, read_n = 0; uint64_t at = 0;
+		while (next_line(p, pe, b, e)) {
+			const size_t n = static_cast<size_t>(e - b);
+			switch (where) {
+			case 0: if (*b != '@') { S.ok = false; return; } S.symb += n; hdr = b + 1; hdr_n = n - 1; break;
+			case 1:
+				if (at + n > S.cap || classify(b, n) == 2) { S.ok = false; return; }
+				std::memcpy(S.bases.get() + at, b, n); read_n = n;
+				break;
+			case 2: {
+				if (*b != '+') { S.ok = false; return; }
+				S.symb += n;
+				const bool plus = n > 1;
+				if (plus && (n - 1 != hdr_n || std::memcmp(b + 1, hdr, hdr_n) != 0)) { S.ok = false; return; }
+				S.hdr.insert(S.hdr.end(), hdr, hdr + hdr_n); S.hdr_off.push_back(S.hdr.size()); S.plus.push_back(plus ? 1 : 0);
+				break;
+			}
+			default:
+				if (n != read_n) { S.ok = false; return; }
+				std::memcpy(S.quals.get() + at, b, n); at += n; S.offsets.push_back(at);
+				break;
+			}
+			where = (where + 1) & 3;
+		}
+		if (where != 0) S.ok = false;
+		S.n_bases = at;
+	}
+	void stream_fastq(const uint8_t* data, uint64_t size, unsigned T, uint64_t piece, const PieceSink& sink, const HostAlloc* A)
+	{
+		const uint8_t* end = data + size;
+		const uint64_t n_pieces = (size + piece - 1) / piece;
+		T = static_cast<unsigned>(std::min<uint64_t>(T, n_pieces));
+		const uint64_t W = std::min<uint64_t>(n_pieces, static_cast<uint64_t>(T) + 2);
+		std::vector<Slot> slots(W);      // declared before the threads: destroyed after they are joined
+		for (uint64_t i = 0; i < W; ++i) slots[i].free_for = i;
+		std::mutex m; std::condition_variable cv; std::atomic<uint64_t> next_piece{0}; bool stop = false;
+		auto start_of = [&](uint64_t i) -> const uint8_t* { return i == 0 ? data : i >= n_pieces ? end : record_start(data + i * piece, end); };
+		auto worker = [&] {
+			for (;;) {
+				const uint64_t i = next_piece.fetch_add(1);
+				if (i >= n_pieces) return;
+				Slot& S = slots[i % W];
+				{ std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return stop || S.free_for == i; }); if (stop) return; }
+				const uint8_t* pb = start_of(i); const uint8_t* pe = start_of(i + 1);
+				if (!pb || !pe) { S.ok = false; S.offsets.assign(1, 0); S.n_bases = 0; }
+				else if (pe <= pb) { S.ok = true; S.offsets.assign(1, 0); S.hdr.clear(); S.plus.clear(); S.hdr_off.assign(1, 0); S.n_bases = 0; S.symb = 0; }      // a record longer than a piece
+				else parse_piece(pb, pe, S, A);
+				{ std::lock_guard<std::mutex> lk(m); S.holds = i; }
+				cv.notify_all();
+			}
+		};
+		std::vector<std::thread> th;
+		for (unsigned t = 0; t < T; ++t) th.emplace_back(worker);
+		auto shut = [&] { { std::lock_guard<std::mutex> lk(m); stop = true; } cv.notify_all(); for (auto& t : th) t.join(); };
+		try {
+			header_offsets.push_back(0);
+			for (uint64_t i = 0; i < n_pieces; ++i) {
+				Slot& S = slots[i % W];
+				{ std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return S.holds == i; }); }
+				if (!S.ok) throw StreamingFallback();
+				const uint32_t n = static_cast<uint32_t>(S.offsets.size() - 1);
+				if (n_reads_streamed + n >= (1ull << 32)) throw StreamingFallback();
+				if (n) sink(S.bases.get(), S.quals.get(), S.offsets.data(), n);
+				const uint64_t h0 = headers.size();
+				headers.append(S.hdr.data(), S.hdr.size());
+				for (uint32_t r = 0; r < n; ++r) { header_offsets.push_back(h0 + S.hdr_off[r + 1]); stream_lens.push_back(static_cast<uint32_t>(S.offsets[r + 1] - S.offsets[r])); }
+				plus_id.append(S.plus.data(), S.plus.size());
+				n_reads_streamed += n; total_bases += S.n_bases; total_symb_header += S.symb;
+				{ std::lock_guard<std::mutex> lk(m); S.free_for = i + W; }
+				cv.notify_all();
+			}
+		} catch (...) { shut(); throw; }
+		shut();
+		threads_used = T;
 	}
 
 	// ---- serial parsers: the reference's state machines ----

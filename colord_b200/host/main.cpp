@@ -90,7 +90,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	if (!fwd_user.empty()) { const size_t want = p.qualityFwdThresholds.size(); if (fwd_user.size() < want) throw std::invalid_argument("too few quality thresholds for this mode"); fwd_user.resize(want); p.qualityFwdThresholds = fwd_user; }
 	CInfo info; info.full_command_line = full_cmd;
 	const CompressionReport r = runCompression(p, info);
-	if (p.verbose) { std::cerr << "streams: " << (r.compat ? "compat (the reference's own)" : "native containers") << "\n"; for (const Phase& ph : r.phases) std::cerr << "  phase " << ph.name << ": " << ph.seconds << " s\n"; }
+	if (p.verbose) { std::cerr << "streams: " << (r.compat ? "compat (the reference's own)" : "native containers") << "\ninput: " << (r.streamed ? "streamed to the device in pieces" : "read whole") << ", " << r.reader_threads << " reader thread(s)\n"; for (const Phase& ph : r.phases) std::cerr << "  phase " << ph.name << ": " << ph.seconds << " s\n"; }
 	if (p.verbose) std::cerr << "k-mer length: " << r.kmerLen << "\nanchor length: " << r.anchorLen << "\nsparse mode range in reads: " << r.sparse_range << "\nreference reads: " << r.tot_ref_reads << "\n";
 	// compression.cpp:802-806
 	std::cerr << "DNA size        : " << r.dna << "\nQuality size    : " << r.qual << "\nHeader size     : " << r.header << "\nMeta size       : " << r.meta << "\nInfo size       : " << r.info << "\n";

@@ -194,6 +194,10 @@ typedef struct {
 	uint32_t thresholds[4];         /* qualityFwdThresholds (-T): bin = number of thresholds <= phred; n_bins - 1 used  */
 	uint32_t level;                 /* compressionLevel: > 1 puts the match / anchor flags in the context (needs clb_encode) */
 } clb_qual_params;
+/* Qualities kept on the device as the input streams in: the ASCII quality bytes of the reads of the clb_append_reads call just made, in the
+ * same order (the reader's quals_pack follows its reads pack: in_reads.cpp:103-111).  HOST buffer unless on_device; it may be reused
+ * when the call returns.  The quality encoders below then take quals == NULL ("the resident ones"). */
+clb_status clb_append_quals(clb_ctx* ctx, const uint8_t* quals, uint64_t n_bytes, int on_device);
 /* quals: phred+33 bytes of all appended reads, read r at quals[offsets[r] .. offsets[r+1]) with the reads' lengths
  * (device pointers iff on_device).  pack_sizes as for clb_encode (NULL: the reference's pack rule).  Result stays on the device. */
 clb_status clb_qual_encode(clb_ctx* ctx, const clb_qual_params* params, const uint8_t* quals, const uint64_t* offsets, int on_device,
@@ -254,6 +258,12 @@ clb_status clb_get_packed_read(clb_ctx* ctx, uint32_t read_id, uint8_t* out, uin
  * Host-side, serial by construction (default-seeded std::mt19937 stream is part of the format).
  * decisions[i] = ShouldAddToReference(i) for i in [0, n). */
 void clb_sampler(uint32_t range, double exponent, uint32_t n_pseudo, uint32_t n, uint8_t* decisions);
+
+/* ---- Page-locked host memory --------------------------------------------------------------------
+ * Buffers a host hands to clb_append_reads / clb_append_quals are copied at the full host-to-device rate (and asynchronously) only
+ * when they are page-locked; the streaming reader of the command line takes its piece buffers from here.  NULL on failure. */
+void* clb_host_alloc(uint64_t bytes);
+void  clb_host_free(void* p);
 
 /* ---- Instrumentation -------------------------------------------------------------------------------
  * Number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -268,7 +268,18 @@ static void refactor_edit_script(const uint8_t* ref, const uint8_t* enc, char* e
 
 /* encoder.cpp:1255-1283 (GetEditDist).  ref/enc point into the (oriented) reference read and the read being encoded.
  * kind: 0 = left flank (frag 0), 1 = right flank (last frag), 2 = between anchors.  Appends the script to `es`. */
+static void get_edit_dist_inner(const uint8_t* ref, uint32_t rl, const uint8_t* enc, uint32_t el, int kind, sbuf* es);
+/* ORC_ALIGN_LOG=<file>: one line per alignment problem (kind, reference symbols, read symbols, non-match script symbols) — the
+ * problem-size statistics DESIGN.md quotes for the device aligner */
 static void get_edit_dist(const uint8_t* ref, uint32_t rl, const uint8_t* enc, uint32_t el, int kind, sbuf* es)
+{
+	static FILE* logf = NULL; static int tried = 0;
+	if (!tried) { tried = 1; const char* p = getenv("ORC_ALIGN_LOG"); if (p) logf = fopen(p, "w"); }
+	const size_t at = es->n;
+	get_edit_dist_inner(ref, rl, enc, el, kind, es);
+	if (logf) { uint32_t d = 0; for (size_t i = at; i < es->n; ++i) d += es->p[i] != 'M'; fprintf(logf, "%d %u %u %u\n", kind, rl, el, d); fflush(logf); }
+}
+static void get_edit_dist_inner(const uint8_t* ref, uint32_t rl, const uint8_t* enc, uint32_t el, int kind, sbuf* es)
 {
 	if (rl == 0 || el == 0)
 	{	/* edit_script.h:247-266 */

@@ -57,6 +57,34 @@ int main(int argc, char** argv)
 			std::printf("{\"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"seconds\": %.4f, \"GBps\": %.3f}\n", in.n_reads(), in.total_bytes, s, in.total_bytes / s * 1e-9);
 			return 0;
 		}
+		if (cmd == "stream" && argc == 6) {            // the streaming form of the reader: pieces collected back into whole arrays; exit code 5 = fallback asked for
+			std::vector<uint8_t> bases, quals; std::vector<uint64_t> offsets{0};
+			const bool dump = std::string(argv[3]) != "-";
+			uint64_t n_sunk = 0;
+			try {
+				const auto t0 = std::chrono::steady_clock::now();
+				const CInputReads in(argv[2], [&](const uint8_t* b, const uint8_t* q, const uint64_t* off, uint32_t n) {
+					n_sunk += off[n];
+					if (!dump) return;
+					const uint64_t base = bases.size();
+					bases.insert(bases.end(), b, b + off[n]); quals.insert(quals.end(), q, q + off[n]);
+					for (uint32_t i = 0; i < n; ++i) offsets.push_back(base + off[i + 1]);
+				}, static_cast<unsigned>(std::atoi(argv[4])), std::strtoull(argv[5], nullptr, 10));
+				const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+				const std::string pre = argv[3];
+				if (dump) {
+					spit(pre + ".bases", bases.data(), bases.size()); spit(pre + ".offsets", offsets.data(), 8 * offsets.size()); spit(pre + ".quals", quals.data(), quals.size());
+					spit(pre + ".headers", in.headers.data(), in.headers.size()); spit(pre + ".hoff", in.header_offsets.data(), 8 * in.header_offsets.size()); spit(pre + ".plus", in.plus_id.data(), in.plus_id.size());
+				}
+				std::printf("{\"threads_used\": %u, \"n_reads\": %u, \"total_bytes\": %" PRIu64 ", \"total_bases\": %" PRIu64 ", \"total_symb_header\": %" PRIu64 ", \"sunk\": %" PRIu64 ", \"seconds\": %.4f, \"GBps\": %.3f, \"read_packs\": [",
+					in.threads_used, in.n_reads(), in.total_bytes, in.total_bases, in.total_symb_header, n_sunk, sec, in.total_bytes / sec * 1e-9);
+				for (size_t i = 0; i < in.read_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.read_pack_sizes[i]);
+				std::printf("], \"header_packs\": [");
+				for (size_t i = 0; i < in.header_pack_sizes.size(); ++i) std::printf("%s%u", i ? ", " : "", in.header_pack_sizes[i]);
+				std::printf("]}\n");
+				return 0;
+			} catch (const StreamingFallback&) { return 5; }
+		}
 		if (cmd == "parse" && (argc == 4 || argc == 6)) {
 			const CInputReads in(argv[2], argc == 6 ? static_cast<unsigned>(std::atoi(argv[4])) : 0u, argc == 6 ? std::strtoull(argv[5], nullptr, 10) : (16u << 20));
 			const std::string pre = argv[3];

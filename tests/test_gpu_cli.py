@@ -72,6 +72,19 @@ def _stream_sizes(stderr):
     return {k: int(v) for k, v in re.findall(r"^(DNA|Quality|Header) size\s*:\s*(\d+)", stderr, re.M)}
 
 
+def _same_parts(ours, theirs, what):
+    """the three streams of two archives hold the same parts: metadata and payload bytes (the printed sizes also count the footer's
+    varints, which move with the order the streams' parts were appended in)"""
+    import colord_archive
+    a, b = colord_archive.read_parts(ours), colord_archive.read_parts(theirs)
+    for stream in ("dna", "qual", "header"):
+        assert (stream in a) == (stream in b), (what, stream)
+        if stream in a:
+            assert [md for md, _ in a[stream]] == [md for md, _ in b[stream]], (what, stream, "part metadata")
+            assert [len(x) for _, x in a[stream]] == [len(x) for _, x in b[stream]], (what, stream, "part sizes")
+            assert all(x == y for (_, x), (_, y) in zip(a[stream], b[stream])), (what, stream, "part bytes")
+
+
 @pytest.mark.parametrize("fmt", ["native", "compat"])
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_cli_round_trip(cli, tmp_path, case, fmt):
@@ -113,7 +126,7 @@ def test_cli_round_trip(cli, tmp_path, case, fmt):
         ref_arch, ref_back = str(tmp_path / "ref.colord"), str(tmp_path / "ref_back")
         rr = subprocess.run([REF, cmd, *opts[:-1], "-t", "4", inp, ref_arch], capture_output=True, text=True, cwd=str(tmp_path))
         assert rr.returncode == 0, rr.stderr
-        assert _stream_sizes(rr.stderr) == ours, f"{case}: stream sizes differ from the reference's"
+        _same_parts(arch, ref_arch, case)
         rr = subprocess.run([REF, "decompress", arch, ref_back], capture_output=True, text=True, cwd=str(tmp_path))
         assert rr.returncode == 0, rr.stderr
         assert open(ref_back, "rb").read() == want, f"{case}: the reference's decompress of our archive differs"
@@ -150,13 +163,40 @@ def test_cli_compat_every_quality_mode_against_the_reference(cli, tmp_path, opts
     ref_opts = [x for o in opts for x in (o.split(",") if "," in o else [o])]      # the reference takes -T as separate numbers
     rr = subprocess.run([REF, "compress-ont", *ref_opts, "-t", "4", inp, b], capture_output=True, text=True, cwd=str(tmp_path))
     assert rr.returncode == 0, rr.stderr
-    assert _stream_sizes(r.stderr) == _stream_sizes(rr.stderr)
+    _same_parts(a, b, "-".join(opts))
     outs = []
     for exe, arc in ((cli, a), (cli, b), (REF, a), (REF, b)):
         o = str(tmp_path / f"out{len(outs)}")
         assert subprocess.run([exe, "decompress", arc, o], capture_output=True, cwd=str(tmp_path)).returncode == 0
         outs.append(open(o, "rb").read())
     assert outs[0] == outs[1] == outs[2] == outs[3]
+
+
+def test_cli_streamed_input_equals_whole_file_input(cli, tmp_path):
+    """Files of 64 MiB and more stream to the device in pieces while they are parsed (qualities resident on the device); the archive's
+    streams must be the ones the whole-file path writes (CLB_NO_STREAMING=1), and the round trip lossless."""
+    import colord_archive
+    fq = str(tmp_path / "in.fastq")
+    synth.generate_file(fq, "ont", 4500, 1_700_000, 8000, seed=8, workers=8)
+    assert os.path.getsize(fq) >= 64 << 20
+    arcs = {}
+    for name, env in (("streamed", {}), ("whole", {"CLB_NO_STREAMING": "1"})):
+        arcs[name] = str(tmp_path / (name + ".colord"))
+        r = subprocess.run([cli, "compress-ont", "-q", "org", "-v", "--native", fq, arcs[name]], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr
+        assert ("streamed to the device" in r.stderr) == (name == "streamed"), r.stderr
+    a, b = colord_archive.read_parts(arcs["streamed"]), colord_archive.read_parts(arcs["whole"])
+    for stream in ("dna-b200", "qual-b200", "header-b200", "meta"):
+        assert a[stream] == b[stream], stream
+    back = str(tmp_path / "back")
+    assert subprocess.run([cli, "decompress", arcs["streamed"], back], capture_output=True).returncode == 0
+    assert subprocess.run(["cmp", "-s", fq, back]).returncode == 0
+    r = subprocess.run([cli, "compress-ont", "--compat", fq, str(tmp_path / "c.colord")], capture_output=True, text=True)      # compat streams from resident qualities
+    assert r.returncode == 0, r.stderr
+    if os.path.exists(REF):
+        rr = subprocess.run([REF, "compress-ont", "-t", "8", fq, str(tmp_path / "r.colord")], capture_output=True, text=True, cwd=str(tmp_path))
+        assert rr.returncode == 0, rr.stderr
+        _same_parts(str(tmp_path / "c.colord"), str(tmp_path / "r.colord"), "streamed compat")
 
 
 def test_cli_refusals(cli, tmp_path):

@@ -166,6 +166,52 @@ def _fastq(records, eol="\n", plus_header=()):
 RECORDS = [("r1 a=1", "ACGTNACGT", "IIIIIIIII"), ("r2", "TTTT", "!!!!"), ("r3/x", "GATTACA", "5555555")]
 
 
+@pytest.mark.parametrize("threads,piece", [(1, 1 << 20), (3, 1 << 20), (8, 3 << 20)])
+@pytest.mark.parametrize("eol,plus", [("\n", False), ("\r\n", True)])
+def test_streaming_reader_equals_the_whole_file_reader(tool, tmp_path, threads, piece, eol, plus):
+    """The streaming form (pieces cut at record starts, a ring of reused buffers, pieces handed over in file order) delivers exactly
+    what the whole-file reader holds — bases, qualities, offsets, headers, '+' flags, statistics, pack sizes — also when quality
+    lines begin with '@' or '+', reads are longer than a piece, and lines end in CRLF."""
+    rng = np.random.default_rng(threads * 7 + piece)
+    recs = []
+    A, Q = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTACGTN", np.uint8), np.frombuffer(b"@+!I5~", np.uint8)
+    for i in range(600):
+        n = int(rng.integers(1, 9000)) if i % 97 else int(2.5 * piece)
+        recs.append((f"r{i} x={i * 7}", A[rng.integers(0, len(A), n)].tobytes().decode(), Q[rng.integers(0, len(Q), n)].tobytes().decode()))
+    data = _fastq(recs, eol=eol, plus_header=range(0, 600, 3) if plus else ())
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(data)
+    r1, st1 = _parse(tool, p, str(tmp_path / "a"))
+    assert r1.returncode == 0, r1.stderr
+    r2 = subprocess.run([tool, "stream", p, str(tmp_path / "b"), str(threads), str(piece)], capture_output=True, text=True)
+    assert r2.returncode == 0, (r2.returncode, r2.stderr)
+    st2 = json.loads(r2.stdout)
+    for k in ("n_reads", "total_bytes", "total_bases", "total_symb_header", "read_packs", "header_packs"):
+        assert st1[k] == st2[k], k
+    for ext in ("bases", "quals", "offsets", "headers", "hoff", "plus"):
+        assert open(str(tmp_path / f"a.{ext}"), "rb").read() == open(str(tmp_path / f"b.{ext}"), "rb").read(), ext
+
+
+@pytest.mark.parametrize("what", ["bad_symbol", "no_final_eol", "quality_length", "plus_differs"])
+def test_streaming_reader_hands_irregular_inputs_back(tool, tmp_path, what):
+    """anything irregular ends the streaming form with a request for the whole-file reader (exit code 5 of the tool), which
+    follows the reference line by line and words the refusal"""
+    recs = [(f"r{i}", "ACGT" * 300, "IIII" * 300) for i in range(4000)]
+    data = _fastq(recs)
+    if what == "bad_symbol":
+        data = data.replace(b"ACGTACGT", b"ACXTACGT", 1)
+    elif what == "no_final_eol":
+        data = data[:-1]
+    elif what == "quality_length":
+        data = data[:len(data) // 2] + data[len(data) // 2:].replace(b"IIII\n", b"III\n", 1)
+    else:
+        data = data[:len(data) // 2] + data[len(data) // 2:].replace(b"\n+\n", b"\n+other\n", 1)
+    p = str(tmp_path / "in.fastq")
+    open(p, "wb").write(data)
+    r = subprocess.run([tool, "stream", p, "-", "4", str(1 << 20)], capture_output=True, text=True)
+    assert r.returncode == 5, (what, r.returncode, r.stderr)
+
+
 @pytest.mark.parametrize("variant", ["plain", "crlf", "blank_lines", "plus_header", "gzip", "cr_only"])
 def test_reader_fastq_variants(tool, tmp_path, variant):
     """in_reads.cpp:181-221: '\\n' and '\\r' both end a line, empty lines are skipped, '+' line empty or equal to the header."""
