@@ -69,7 +69,7 @@ void clb_destroy(clb_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	s1_free(c);
 	s2_free(c);
-	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release(); c->dq.release();
+	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release(); c->xg.release(); c->dq.release();
 	if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -340,22 +340,33 @@ clb_status clb_xhdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* off
 	if (n && (!offsets || !bytes)) return fail(c, CLB_ERR_BAD_ARG, "null argument");
 	return s3x_hdr_encode(c, bytes, offsets, plus_id, n, on_device, pack_sizes, n_packs);
 }
+clb_status clb_count_sequences(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n, int on_device)
+{
+	CLB_ENTER(c);
+	if (n && (!offsets || !bases)) return fail(c, CLB_ERR_BAD_ARG, "null bases/offsets");
+	return s1a_append(c, bases, offsets, n, on_device, false, true);
+}
+clb_status clb_xplain_encode(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_seqs, uint32_t level)
+{
+	CLB_ENTER(c);
+	return s3x_plain_encode(c, bases, offsets, n_seqs, level);
+}
 clb_status clb_xstream_size(clb_ctx* c, uint32_t which, uint64_t* total, uint32_t* n_parts)
 {
 	CLB_ENTER(c);
-	if (which > 2 || !total || !n_parts) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_size: bad argument");
-	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : c->xh_parts;
-	*total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : c->xh_total;
+	if (which > 3 || !total || !n_parts) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_size: bad argument");
+	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : which == 2 ? c->xh_parts : c->xg_parts;
+	*total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : which == 2 ? c->xh_total : c->xg_total;
 	*n_parts = (uint32_t)parts.size();
 	return CLB_OK;
 }
 clb_status clb_xstream_get(clb_ctx* c, uint32_t which, uint8_t* bytes, uint64_t cap, uint64_t* part_sizes, int on_device)
 {
 	CLB_ENTER(c);
-	if (which > 2) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_get: bad stream");
-	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : c->xh_parts;
-	const uint64_t total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : c->xh_total;
-	const uint8_t* src = which == 0 ? c->xd.p : which == 1 ? c->xq.p : c->xh.p;
+	if (which > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_xstream_get: bad stream");
+	const std::vector<uint64_t>& parts = which == 0 ? c->xd_parts : which == 1 ? c->xq_parts : which == 2 ? c->xh_parts : c->xg_parts;
+	const uint64_t total = which == 0 ? c->xd_total : which == 1 ? c->xq_total : which == 2 ? c->xh_total : c->xg_total;
+	const uint8_t* src = which == 0 ? c->xd.p : which == 1 ? c->xq.p : which == 2 ? c->xh.p : c->xg.p;
 	if (cap < total) return fail(c, CLB_ERR_CAPACITY, "clb_xstream_get: buffer too small");
 	if (part_sizes) for (size_t i = 0; i < parts.size(); ++i) part_sizes[i] = parts[i];
 	if (total) {

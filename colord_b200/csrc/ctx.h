@@ -183,8 +183,9 @@ struct clb_ctx {
 	clb::DevBuf<uint8_t> hs;         // native header container
 	uint64_t hs_total = 0, hs_header = 0;
 	// ---- stage 3, compat streams (stage3_exact.cu): the reference's own parts, back to back ----
-	clb::DevBuf<uint8_t> xd, xq, xh;
-	std::vector<uint64_t> xd_parts, xq_parts, xh_parts;      // bytes of every part
+	clb::DevBuf<uint8_t> xd, xq, xh, xg;                     // dna, qual, header, ref-genome
+	std::vector<uint64_t> xd_parts, xq_parts, xh_parts, xg_parts;      // bytes of every part
+	uint64_t xg_total = 0;
 	std::vector<uint64_t> xd_packs, xh_packs;                // reads / headers of every part (the parts' metadata)
 	uint64_t xd_total = 0, xq_total = 0, xh_total = 0;
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
@@ -216,7 +217,7 @@ void prof_end3(clb_ctx* c);
 
 // stage entry points implemented in the .cu files
 clb_status s1a_init(clb_ctx* c);
-clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context = false);
+clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context = false, bool count_only = false);
 clb_status s1b_reads_have_n(clb_ctx* c, uint8_t* flags);
 clb_status s1b_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device);
 clb_status s1a_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n);
@@ -245,6 +246,7 @@ clb_status resolve_quals(clb_ctx* c, const uint8_t* quals, const uint64_t* offse
 clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t level, const uint32_t* thr, const uint8_t* quals, const uint64_t* offsets, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
+clb_status s3x_plain_encode(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_seqs, uint32_t level);
 clb_status s3x_hdr_encode(clb_ctx* c, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n, int on_device,
 	const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status s2_edit_scripts(clb_ctx* c, const uint8_t* seqs, uint64_t n_seq_bytes, const uint64_t* ref_off, const uint32_t* ref_len,

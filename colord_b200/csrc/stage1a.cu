@@ -483,7 +483,7 @@ constexpr uint64_t APPEND_CHUNK = 1ULL << 26;      // positions; multiple of 128
 
 // context = true (clb_append_context_reads): the reads are packed into the store but not counted, and they take the read
 // ids 0 .. n_reads-1 in front of the reads appended so far (multi-GPU: reference reads of earlier shards)
-clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context)
+clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads, int on_device, bool context, bool count_only)
 {
 	if (!context && c->finalized) return fail(c, CLB_ERR_STATE, "clb_append_reads after clb_count_finalize");
 	if (context && (!c->finalized || c->graph_done || c->n_context)) return fail(c, CLB_ERR_STATE, "clb_append_context_reads: once, after clb_count_finalize and before clb_graph_build");
@@ -580,6 +580,13 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 		CLB_TIMED(c, K_COUNT, (k_count<false><<<grid_for(cw, COUNT_THREADS, c->n_sm, 8), COUNT_THREADS, 0, s>>>(c->pk.p, c->nmask.p, c->smask.p,
 			w0, wb, wb + cw, c->prm.kmer_len, c->mt, c->tab, c->tab_log2, c->d_scal)));
 		CLB_LAUNCH_CHECK(c, "k_count");
+	}
+	if (count_only) {      // the sequences were counted and are forgotten: the next append takes their place in the store
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		unsigned long long sc[SC_COUNT];
+		clb_status st = read_scalars(c, sc); if (st != CLB_OK) return st;
+		if (sc[SC_BAD_SYMBOL]) return fail(c, CLB_ERR_BAD_SYMBOL, "input holds a symbol outside ACGTN");
+		return CLB_OK;
 	}
 	if (context) {
 		std::vector<uint64_t> hs(n_reads); std::vector<uint32_t> hl(n_reads);

@@ -255,7 +255,7 @@ static clb_status x_packs(clb_ctx* c, const uint32_t* pack_sizes, uint32_t n_pac
 		if (at != n) return fail(c, CLB_ERR_BAD_ARG, "pack_sizes do not sum to the number of reads");
 	} else {
 		uint64_t bytes = 0;
-		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back(i + 1); } }
+		for (uint64_t i = 0; i < n; ++i) { bytes += (uint64_t)c->h_rd_len[c->n_context + i] + 1; if (bytes >= (2u << 21)) { bytes = 0; pack_first.push_back(i + 1); } }
 		if (pack_first.back() != n) pack_first.push_back(n);
 	}
 	return CLB_OK;
@@ -283,10 +283,11 @@ clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes
 {
 	cudaStream_t s = c->stream;
 	if (!c->enc_done) return fail(c, CLB_ERR_STATE, "clb_xdna_encode before clb_encode");
-	if (c->n_context) return fail(c, CLB_ERR_STATE, "compat streams are not available for shards with context reads");
 	if (level < 1 || level > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_xdna_encode: level must be 1, 2 or 3");
 	if (c->prm.max_candidates > 32) return fail(c, CLB_ERR_BAD_ARG, "clb_xdna_encode: at most 32 candidates");
-	const uint64_t n = c->n_reads;
+	// context reads (the pseudo-reads of a reference genome) are reference reads in front of the input's reads: not coded, but they
+	// count in the read ids — the reference starts its coder at start_read_id = n_ref_genome_pseudo_reads (compression.cpp:641)
+	const uint64_t nc = c->n_context, n = c->n_reads - nc;
 	std::vector<uint64_t> pack_first;
 	{ const clb_status st = x_packs(c, pack_sizes, n_packs, n, pack_first); if (st != CLB_OK) return st; }
 	const uint32_t np = (uint32_t)pack_first.size() - 1;
@@ -294,7 +295,7 @@ clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes
 	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
 	XDArgs a{};
 	a.M = make_dna_model(level, c->prm.max_candidates);
-	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off, 0};
+	a.R = DnaReads{c->pk.p, c->rd_start.p, c->rd_len.p, c->d_ref_to_read, c->es.p, c->es_off, (uint32_t)nc};
 	a.n_reads = (uint32_t)n;
 	uint64_t* d_ev_off = nullptr;
 	CLB_CUDA(c, dalloc((void**)&a.n_ev, sizeof(uint32_t) * (n + 1))); CLB_CUDA(c, dalloc((void**)&d_ev_off, sizeof(uint64_t) * (n + 1))); CLB_CUDA(c, dalloc((void**)&a.bad, 4));
@@ -327,6 +328,86 @@ clb_status s3x_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes
 	c->xd_packs.assign(np, 0);
 	for (uint32_t p = 0; p < np; ++p) c->xd_packs[p] = pack_first[p + 1] - pack_first[p];
 	return x_code_stream(c, s, K_DNA, F, a.key, a.info, n_ev, pack_ev, c->xd, c->xd_parts, c->xd_total);
+}
+
+// ================================================================================================ plain sequences (the stored reference genome)
+// CReferenceGenome::Store(archive) (reference_genome.cpp:319-360): every sequence of the genome goes through a CDNACoder of its own as a
+// plain read (start_plain + one plain tuple per base) at "level 9", which Init maps to one symbol of history (dna_coder.cpp:1275-1280);
+// one part for the whole genome, metadata = number of sequences.
+struct XPArgs { const uint8_t* bases; const uint64_t* off; uint32_t n_seqs; uint32_t n_s; const uint64_t* ev_off; uint64_t* key; uint16_t* info; uint32_t* bad; };
+CLB_D uint32_t xp_code(uint8_t ch) { return ch == 'C' ? 1u : ch == 'G' ? 2u : ch == 'T' ? 3u : 0u; }
+template <class Sink>
+CLB_D void xp_head(uint64_t len64, Sink& sink)      // read flag + encode_read_len (dna_coder.cpp:440-463, :1004-1056)
+{
+	sink.put(F_FLAG, 0, 0);
+	uint32_t len = (uint32_t)len64;
+	const uint32_t nbits = ilog2_bits(len);
+	sink.put(F_LENBITS, 0, nbits);
+	if (nbits >= 2) {
+		uint64_t ctx = (uint64_t)nbits << 3;
+		len -= 1u << (nbits - 1);
+		uint32_t prefix = len, suffix = 0;
+		if (nbits > 9) { prefix = len >> (nbits - 9); suffix = len - (prefix << (nbits - 9)); }
+		sink.put(F_LENDATA, ctx, prefix);
+		if (nbits > 9) { ctx += 4; for (int nb = (int)nbits - 9; nb > 0; nb -= 8) { sink.put(F_LENDATA, ctx, suffix & 0xff); suffix >>= 8; ++ctx; } }
+	}
+}
+__global__ void __launch_bounds__(128) k_xp_heads(XPArgs a)
+{
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= a.n_seqs) return;
+	XWriteSink s{a.key, a.info, a.ev_off[q], a.bad};
+	xp_head(a.off[q + 1] - a.off[q], s);
+}
+__global__ void __launch_bounds__(256) k_xp_symbols(XPArgs a, uint64_t n_bases)
+{
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_bases) return;
+	uint32_t lo = 0, hi = a.n_seqs;                       // sequence of base i: last off <= i
+	while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (a.off[mid] <= i) lo = mid; else hi = mid; }
+	const uint64_t at = i - a.off[lo];
+	uint64_t ctx = 0;
+	for (uint32_t k = a.n_s; k >= 1; --k) ctx = (ctx << 2) | (at >= k ? xp_code(a.bases[i - k]) : 3u);
+	const uint64_t e = a.ev_off[lo + 1] - (a.off[lo + 1] - a.off[lo]) + at;      // the head events come first
+	a.key[e] = ((uint64_t)F_SYM << X_CTX_BITS) | (ctx << 2);
+	a.info[e] = (uint16_t)xp_code(a.bases[i]);
+}
+
+clb_status s3x_plain_encode(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets, uint32_t n_seqs, uint32_t level)
+{
+	cudaStream_t s = c->stream;
+	if (!n_seqs || !bases || !offsets) return fail(c, CLB_ERR_BAD_ARG, "clb_xplain_encode: no sequences");
+	const uint64_t n_bases = offsets[n_seqs] - offsets[0];
+	if (offsets[0] != 0) return fail(c, CLB_ERR_BAD_ARG, "clb_xplain_encode: offsets[0] must be 0");
+	XTmp tmp{{}, s};
+	auto dalloc = [&](void** p, uint64_t bytes) { cudaError_t e = dev_malloc(p, bytes ? bytes : 1, s); if (e == cudaSuccess) tmp.v.push_back(*p); return e; };
+	XPArgs a{};
+	a.n_seqs = n_seqs; a.n_s = level >= 3 ? (level == 3 ? 8u : 1u) : level == 2 ? 7u : level == 1 ? 5u : 1u;      // dna_coder.cpp:1253-1280: anything but 1, 2, 3 keeps one symbol
+	std::vector<uint64_t> ev_off(n_seqs + 1, 0);
+	for (uint32_t q = 0; q < n_seqs; ++q) {
+		const uint64_t len = offsets[q + 1] - offsets[q];
+		if (len >> 32) return fail(c, CLB_ERR_BAD_ARG, "clb_xplain_encode: a sequence of 4 Gbases or more");
+		uint32_t nbits = 0; for (uint64_t x = len; x; x >>= 1) ++nbits;
+		ev_off[q + 1] = ev_off[q] + 2 + (nbits >= 2 ? 1 + (nbits > 9 ? (nbits - 9 + 7) / 8 : 0) : 0) + len;
+	}
+	const uint64_t n_ev = ev_off[n_seqs];
+	uint8_t* d_b = nullptr; uint64_t* d_o = nullptr; uint64_t* d_e = nullptr;
+	CLB_CUDA(c, dalloc((void**)&d_b, n_bases + 16)); CLB_CUDA(c, dalloc((void**)&d_o, sizeof(uint64_t) * (n_seqs + 1))); CLB_CUDA(c, dalloc((void**)&d_e, sizeof(uint64_t) * (n_seqs + 1)));
+	CLB_CUDA(c, dalloc((void**)&a.key, sizeof(uint64_t) * (n_ev + 1))); CLB_CUDA(c, dalloc((void**)&a.info, sizeof(uint16_t) * (n_ev + 1))); CLB_CUDA(c, dalloc((void**)&a.bad, 4));
+	CLB_CUDA(c, cudaMemcpyAsync(d_b, bases, n_bases, cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_o, offsets, sizeof(uint64_t) * (n_seqs + 1), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemcpyAsync(d_e, ev_off.data(), sizeof(uint64_t) * (n_seqs + 1), cudaMemcpyHostToDevice, s));
+	CLB_CUDA(c, cudaMemsetAsync(a.bad, 0, 4, s));
+	a.bases = d_b; a.off = d_o; a.ev_off = d_e;
+	CLB_TIMED(c, K_DNA, (k_xp_heads<<<(n_seqs + 127) / 128, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_xp_heads");
+	if (n_bases) { CLB_TIMED(c, K_DNA, (k_xp_symbols<<<(uint32_t)((n_bases + 255) / 256), 256, 0, s>>>(a, n_bases))); CLB_LAUNCH_CHECK(c, "k_xp_symbols"); }
+	CLB_CUDA(c, cudaStreamSynchronize(s));
+	XFams F{};
+	const XFam f0[F_COUNT] = {{3, 1u << 15, 1}, {32, 1u << 18, 8}, {256, 1u << 18, 8}, {4, 1u << 10, 1}, {5, 1u << 10, 1}, {256, 1u << 13, 1}, {2, 1u << 15, 1},
+		{8, 1u << 15, 1}, {24, 1u << 15, 1}, {256, 1u << 15, 1}, {256, 1u << 15, 1}, {2, 1u << 15, 1}, {2, 1u << 13, 1}};
+	for (uint32_t f = 0; f < F_COUNT; ++f) F.f[f] = f0[f];
+	const std::vector<uint64_t> pack_ev{0, n_ev};
+	return x_code_stream(c, s, K_DNA, F, a.key, a.info, n_ev, pack_ev, c->xg, c->xg_parts, c->xg_total);
 }
 
 // ================================================================================================ quality stream
@@ -425,9 +506,8 @@ clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t 
 	const uint32_t* pack_sizes, uint32_t n_packs)
 {
 	cudaStream_t s = c->stream3;
-	const uint64_t n = c->n_reads;
+	const uint64_t nc = c->n_context, n = c->n_reads - nc;      // context reads carry no qualities
 	if (!c->finalized) return fail(c, CLB_ERR_STATE, "clb_xqual_encode before the reads are complete (clb_count_finalize)");
-	if (c->n_context) return fail(c, CLB_ERR_STATE, "compat streams are not available for shards with context reads");
 	if (mode > 8 || source > 2 || level < 1 || level > 3) return fail(c, CLB_ERR_BAD_ARG, "clb_xqual_encode: bad mode / source / level");
 	if (level > 1 && mode != 8 && !c->enc_done) return fail(c, CLB_ERR_STATE, "clb_xqual_encode at level > 1 needs the tuples (clb_encode) for the match / anchor flags");
 	std::vector<uint64_t> pack_first;
@@ -453,7 +533,7 @@ clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t 
 	// events per read and their place in the stream
 	const uint32_t extra = (mode >= 1 && mode <= 3) ? 2 * a.n_bins : mode == 7 ? 2 : 0;
 	std::vector<uint64_t> ev_off(n + 1, 0);
-	for (uint64_t i = 0; i < n; ++i) ev_off[i + 1] = ev_off[i] + (mode == 8 ? 0 : extra + (mode == 7 ? 0 : c->h_rd_len[i]));
+	for (uint64_t i = 0; i < n; ++i) ev_off[i + 1] = ev_off[i] + (mode == 8 ? 0 : extra + (mode == 7 ? 0 : c->h_rd_len[nc + i]));
 	const uint64_t n_ev = ev_off[n];
 	std::vector<uint64_t> pack_ev(np + 1);
 	for (uint32_t p = 0; p <= np; ++p) pack_ev[p] = ev_off[pack_first[p]];
@@ -481,7 +561,7 @@ clb_status s3x_qual_encode(clb_ctx* c, uint32_t mode, uint32_t source, uint32_t 
 			const clb_status st = s3_qual_flags(c, d_qoff, (uint32_t)n, d_flags);
 			if (st != CLB_OK) return st;
 		}
-		a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.ev_off = d_ev_off; a.key = d_key; a.info = d_info;
+		a.pk = c->pk.p; a.rd_start = c->rd_start.p + nc; a.rd_len = c->rd_len.p + nc; a.quals = d_q; a.qoff = d_qoff; a.flags = d_flags; a.ev_off = d_ev_off; a.key = d_key; a.info = d_info;
 		CLB_TIMED3(c, K_QUAL, (k_xq_events<<<(uint32_t)n, 128, 0, s>>>(a))); CLB_LAUNCH_CHECK(c, "k_xq_events");
 		uint32_t bad = 0;
 		CLB_CUDA(c, cudaMemcpyAsync(&bad, a.bad, 4, cudaMemcpyDeviceToHost, s));

@@ -90,16 +90,21 @@ using PartSource = std::function<bool(std::vector<uint8_t>&, size_t&)>;
 
 // ---- "dna": CDNACoder::Decode.  part_reads receives the reads of every part (the quality parts follow them). ----
 inline dec::Reads decode_dna(const PartSource& next, uint32_t n_reads, const std::vector<uint8_t>& decisions, uint32_t level, uint32_t max_cand, bool want_flags, uint64_t max_bases,
-	std::vector<uint32_t>& part_reads)
+	std::vector<uint32_t>& part_reads, const std::vector<std::vector<uint8_t>>* first_refs = nullptr)
 {
 	using namespace dec;
-	if (level < 1 || level > 3 || max_cand < 1 || max_cand > 256) throw DecodeError("colord-b200: the DNA stream's parameters are out of range");
-	const uint32_t n_t = level >= 3 ? 4 : level == 2 ? 3 : 2, n_s = level >= 3 ? 8 : level == 2 ? 7 : 5;      // dna_coder.cpp:1253-1280
+	if (max_cand < 1 || max_cand > 256) throw DecodeError("colord-b200: the DNA stream's parameters are out of range");
+	// dna_coder.cpp:1253-1280: levels 1, 2, 3; anything else (the stored reference genome's "level 9") keeps one tuple / one symbol of history
+	const uint32_t n_t = level == 3 ? 4 : level == 2 ? 3 : level == 1 ? 2 : 1, n_s = level == 3 ? 8 : level == 2 ? 7 : level == 1 ? 5 : 1;
+	// first_refs: the pseudo-reads of a reference genome — reference reads in front of the archive's reads; the coder's read ids start
+	// behind them (start_read_id, compression.cpp:641)
+	const uint32_t n_first = first_refs ? static_cast<uint32_t>(first_refs->size()) : 0;
 	Models M({{3, 1u << 15, 1}, {32, 1u << 18, 8}, {256, 1u << 18, 8}, {4, 1u << 10, 1}, {5, 1u << 10, 1}, {256, 1u << 13, 1}, {2, 1u << 15, 1},
 		{8, 1u << 15, 1}, {24, 1u << 15, 1}, {256, 1u << 15, 1}, {256, 1u << 15, 1}, {2, 1u << 15, 1}, {max_cand, 1u << 13, 1}});      // dna_coder.h:48-60, dna_coder.cpp:1316-1336
 	Coder d(M);
 	const uint64_t mask_s = (1ull << (2 * n_s)) - 1, mask_t = (1ull << (3 * n_t)) - 1; const uint32_t sh_t = 3 * n_t;
 	std::vector<std::vector<uint8_t>> refs;
+	if (first_refs) refs = *first_refs;
 	Reads out; out.offsets.reserve(static_cast<size_t>(n_reads) + 1);
 	std::vector<uint8_t> rd, fl, part;
 	uint32_t r = 0; uint64_t ctx_read_type = 0; size_t md = 0;
@@ -118,7 +123,7 @@ inline dec::Reads decode_dna(const PartSource& next, uint32_t n_reads, const std
 			uint64_t ctx_symbol = mask_s;
 			if (flag == 0) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(F_SYM, ctx_symbol << 2); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; }
 			else if (flag == 1) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(F_SYMN, ctx_symbol); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; }
-			else dna_edit_script(d, level, n_s, r, len, refs, rd, fl, ctx_symbol, mask_t, mask_s, mask_t, sh_t, budget);
+			else dna_edit_script(d, level, n_s, n_first + r, len, refs, rd, fl, ctx_symbol, mask_t, mask_s, mask_t, sh_t, budget);
 			fl.resize(rd.size(), 0);
 			for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
 			if (want_flags) out.flags.insert(out.flags.end(), fl.begin(), fl.end());

@@ -13,16 +13,25 @@
 // own ("dna", "qual", "header", one part per pack; clb_x*_encode, colord_b200/csrc/stage3_exact.cu) and `info` carries the
 // reference's version 1.2.1, so the unmodified `colord decompress` reads the archive and its size is the reference's; every quality
 // mode of the reference is available there.
-// Not covered (refused with a message): -G reference genomes; the threshold / plain-average quality modes in native containers.
+// Reference-genome mode (-G [-s], compression.cpp:401-452, :508-513, :763-779): the genome's sequences are counted with the reads
+// (clb_count_sequences), its pseudo-reads enter as always-accepted reference reads in front of the input's reads
+// (clb_append_context_reads), `meta` records the pseudo-read geometry and the MD5 of the genome or, with -s, the genome itself goes
+// into the archive ("ref-genome": the reference's own coding through clb_xplain_encode in compat archives, packed 2-bit sequences in
+// native ones).
+// Not covered (refused with a message): the threshold / plain-average quality modes in native containers.
 #pragma once
 #include <chrono>
 #include <cstdio>
 #include <ctime>
 #include <iostream>
+#include <thread>
+#include <memory>
+#include <exception>
 #include "archive_host.h"
 #include "fastq_reader.h"
 #include "presets.h"
 #include "stage23_host.h"
+#include "ref_genome_host.h"
 
 namespace clbhost {
 
@@ -37,7 +46,6 @@ struct CompressionReport {            // what the reference prints at the end (c
 
 inline void refuse_unsupported(const CCompressorParams& p, bool compat = false)
 {
-	if (!p.refGenomePath.empty()) throw std::invalid_argument("reference-genome mode (-G) is not available in this build");
 	// limits of the device path, checked before any work is done (the C-ABI would refuse them only after stages 1 and 2)
 	if (p.maxCandidates < 1 || p.maxCandidates > 32) throw std::invalid_argument("the number of candidate reads (-c) must be in 1..32 in this build");
 	if (p.compressionLevel < 1 || p.compressionLevel > 3) throw std::invalid_argument("the compression level must be in 1..3");
@@ -83,34 +91,44 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	uint32_t kmerLen = params.kmerLen, anchorLen = params.anchorLen;
 	const bool hifi = params.dataSource == DataSource::PBHiFi;
 	std::unique_ptr<CInputReads> inp; std::unique_ptr<CKmerCounter> counter;
-	auto make_counter = [&](bool fastq, uint64_t expected_bases) {
-		adjustKmerAndAnchorLen(kmerLen, anchorLen, is_gzip, fastq, file_bytes);
-		if (params.verbose) {
-			std::cerr << (is_gzip ? "input is gzipped\n" : "input is not gzipped\n");          // compression.cpp:365-371
-			PrintParams(std::cerr, params, kmerLen, anchorLen, params.nThreads);
-		}
-		counter = std::make_unique<CKmerCounter>(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi, expected_bases, params.device);
-	};
+	// The device context (CUDA start-up, count table) is made by a thread of its own while the input is being read: on a fresh
+	// process it costs 1 - 3 s (measured on the B200 boxes, profiles/r02d_*), as much as parsing several GB.  What it needs — k,
+	// the table's size — follows from the file's size and first bytes alone (compression.cpp:41-93).
+	adjustKmerAndAnchorLen(kmerLen, anchorLen, is_gzip, fastq_guess, file_bytes);
+	if (params.verbose) {
+		std::cerr << (is_gzip ? "input is gzipped\n" : "input is not gzipped\n");          // compression.cpp:365-371
+		PrintParams(std::cerr, params, kmerLen, anchorLen, params.nThreads);
+	}
+	std::exception_ptr counter_error;
+	std::thread make_counter([&] {
+		try {
+			counter = std::make_unique<CKmerCounter>(kmerLen, params.minKmerCount, params.maxKmerCount, params.filterHashModulo, params.maxCandidates, hifi,
+				is_gzip ? file_bytes * 2 : file_bytes / 2, params.device);
+		} catch (...) { counter_error = std::current_exception(); }
+	});
+	struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{make_counter};
+	auto wait_counter = [&]() -> clb_ctx* { if (make_counter.joinable()) make_counter.join(); if (counter_error) std::rethrow_exception(counter_error); return counter->Context(); };
 	if (stream) {
-		make_counter(true, file_bytes / 2);
-		clb_ctx* c0 = counter->Context();
-		phase("device context");
 		// large inputs: the piece buffers are page-locked (full-rate, asynchronous host-to-device copies); below that the time to lock
 		// them is not paid back
 		const CInputReads::HostAlloc pinned{[](uint64_t bytes) { return clb_host_alloc(bytes); }, [](void* p) { clb_host_free(p); }};
 		const bool pin = file_bytes >= (8ull << 30) || std::getenv("CLB_PIN_INPUT") != nullptr;
-		inp = std::make_unique<CInputReads>(params.inputFilePath, [c0](const uint8_t* b, const uint8_t* q, const uint64_t* off, uint32_t n) {
+		clb_ctx* c0 = nullptr;
+		inp = std::make_unique<CInputReads>(params.inputFilePath, [&](const uint8_t* b, const uint8_t* q, const uint64_t* off, uint32_t n) {
+			if (!c0) { phase("first pieces parsed"); c0 = wait_counter(); phase("device context (rest of it)"); }
 			check(c0, clb_append_reads(c0, b, off, n, 0), "clb_append_reads");
 			check(c0, clb_append_quals(c0, q, off[n], 0), "clb_append_quals");
 		}, 0, 64u << 20, pin ? &pinned : nullptr);
+		wait_counter();
 		phase("read input (streamed to the device, stage 1a inside)");
 	} else {
 		inp = std::make_unique<CInputReads>(params.inputFilePath);
-		is_gzip = inp->is_gzip; file_bytes = inp->file_bytes;
 		phase("read input");
-		make_counter(inp->is_fastq, inp->total_bases);
-		check(counter->Context(), clb_append_reads(counter->Context(), inp->bases.data(), inp->offsets.data(), inp->n_reads(), 0), "clb_append_reads");
-		phase("device context + reads to the device (stage 1a inside)");
+		if (inp->is_fastq != fastq_guess || inp->is_gzip != is_gzip) throw std::runtime_error("Error: the input changed while it was being read");
+		clb_ctx* c0 = wait_counter();
+		phase("device context (rest of it)");
+		check(c0, clb_append_reads(c0, inp->bases.data(), inp->offsets.data(), inp->n_reads(), 0), "clb_append_reads");
+		phase("reads to the device (stage 1a inside)");
 	}
 	CInputReads& in = *inp; CKmerCounter& kmer_counter = *counter;
 	clb_ctx* ctx = kmer_counter.Context();
@@ -129,29 +147,71 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	const bool is_fastq = in.is_fastq;
 	info.total_bytes = in.total_bytes; info.total_bases = in.total_bases;
 
+	// reference genome: its sequences are a second counting input (compression.cpp:408-430)
+	std::unique_ptr<CReferenceGenome> ref_genome;
+	if (!params.refGenomePath.empty()) {
+		ref_genome = std::make_unique<CReferenceGenome>(params.refGenomePath);
+		std::vector<uint8_t> gb; std::vector<uint64_t> go;
+		ref_genome->Sequences(gb, go);
+		check(ctx, clb_count_sequences(ctx, gb.data(), go.data(), ref_genome->GetTotNSeqs(), 0), "clb_count_sequences");
+		phase("reference genome read and counted");
+	}
 	const uint32_t tot_n_reads = kmer_counter.GetNReads();
 	const uint64_t tot_kmers = kmer_counter.GetTotKmers(), n_uniq_counted_kmers = kmer_counter.GetNUniqueCounted();
 	check(ctx, clb_count_finalize(ctx, &rep.stats), "clb_count_finalize");
 	if (tot_n_reads == 0) throw std::runtime_error("Error: no reads in the input");
-	const uint64_t mean_read_len = meanReadLen(tot_kmers, params.filterHashModulo, tot_n_reads, kmerLen);
+	// KMC's read count includes the genome's sequences; the statistics are then corrected for them (compression.cpp:443-452)
+	const uint64_t n_genome_seqs = ref_genome ? ref_genome->GetTotNSeqs() : 0;
+	uint64_t mean_read_len = meanReadLen(tot_kmers, params.filterHashModulo, tot_n_reads + n_genome_seqs, kmerLen);
+	uint32_t ref_genome_read_len = 0, n_pseudo = 0; const uint32_t ref_genome_overlap_size = (kmerLen - 1) * 10;
+	if (ref_genome) {
+		mean_read_len = static_cast<uint64_t>(double(mean_read_len * (tot_n_reads + n_genome_seqs) - ref_genome->GetTotSeqsLen()) / tot_n_reads);
+		ref_genome_read_len = static_cast<uint32_t>(20 * mean_read_len);
+		ref_genome->SetReadLen(ref_genome_read_len, ref_genome_overlap_size);
+		if (!ref_genome->valid_read_len()) throw std::runtime_error("Error: the reads are too short for the reference-genome mode (pseudo-read length <= overlap)");
+		n_pseudo = ref_genome->GetNPseudoReads();
+		std::vector<uint8_t> pb; std::vector<uint64_t> po;
+		ref_genome->PseudoReads(pb, po);
+		check(ctx, clb_append_context_reads(ctx, pb.data(), po.data(), n_pseudo, 0), "clb_append_context_reads");
+		if (params.verbose) std::cerr << "# ref genome pseudo reads: " << n_pseudo << "\n";
+		phase("pseudo-reads to the device");
+	}
 	info.total_reads = tot_n_reads;
 	if (params.verbose) std::cerr << "tot k-mers: " << tot_kmers << "\nn uniq counted: " << n_uniq_counted_kmers << "\napprox. avg. read len: " << mean_read_len << "\n";
 
 	// reference reads: all, or the sparse sampler over the range derived from the filtered k-mers
 	const uint32_t sparseMode_range = sparseModeRange(params.sparseMode_range_symbols, n_uniq_counted_kmers, params.filterHashModulo, mean_read_len ? mean_read_len : 1);
 	const bool sparse = params.referenceReadsMode == ReferenceReadsMode::Sparse;
-	CRefReadsAccepter accepter(sparseMode_range, params.sparseMode_exponent, 0);
-	uint32_t tot_ref_reads = sparse ? accepter.GetNAccepted(tot_n_reads) : tot_n_reads;
+	CRefReadsAccepter accepter(sparseMode_range, params.sparseMode_exponent, n_pseudo);
+	uint32_t tot_ref_reads = sparse ? accepter.GetNAccepted(tot_n_reads + n_pseudo) : tot_n_reads + n_pseudo;      // ref_reads_accepter.h:42-49, compression.cpp:513
 	rep.sparse_range = sparseMode_range; rep.tot_ref_reads = tot_ref_reads;
 
 	// stage 1b + 2
-	CReadsSimilarityGraph graph(kmer_counter, params.maxCandidates, hifi, sparse, accepter, 0);
+	CReadsSimilarityGraph graph(kmer_counter, params.maxCandidates, hifi, sparse, accepter, n_pseudo);
 	CEncoder encoder(kmer_counter, anchorLen, params.minFractionOfMmersInEncodeToAlwaysEncode, params.minFractionOfMmersInEncode, params.maxMatchesMultiplier,
 		params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
 	encoder.Encode(in.read_pack_sizes);
 
 	phase("stages 1b + 2");
 	int s_dna = -1, s_qual = -1, s_header = -1;
+	if (ref_genome && params.storeRefGenome) {
+		if (compat) {      // CReferenceGenome::Store(archive) (reference_genome.cpp:319-360)
+			const int s_gen = archive.RegisterStream("ref-genome");
+			std::vector<uint8_t> gb; std::vector<uint64_t> go;
+			ref_genome->Sequences(gb, go);
+			check(ctx, clb_xplain_encode(ctx, gb.data(), go.data(), ref_genome->GetTotNSeqs(), 9), "clb_xplain_encode");
+			uint64_t total = 0; uint32_t n_parts = 0;
+			check(ctx, clb_xstream_size(ctx, 3, &total, &n_parts), "clb_xstream_size");
+			std::vector<uint8_t> bytes(total + 1); uint64_t sz[2] = {0, 0};
+			check(ctx, clb_xstream_get(ctx, 3, bytes.data(), total, sz, 0), "clb_xstream_get");
+			bytes.resize(total);
+			add_part(s_gen, bytes, ref_genome->GetTotNSeqs());
+		} else {
+			const int s_gen = archive.RegisterStream("ref-genome-b200");
+			for (const auto& seq : ref_genome->Raw()) add_part(s_gen, CReferenceGenome::Pack(seq), 0);
+		}
+		phase("reference genome stored");
+	}
 	if (compat) {
 		// the reference's own streams: one part per read pack / header pack (entr_read.h:56-80, entr_qual.h:100-126, entr_header.cpp:23-46)
 		auto add_parts = [&](int stream_id, uint32_t which, const std::vector<uint32_t>* metadata) {
@@ -233,6 +293,11 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	meta.qualityRevThresholds.resize(CMeta::n_thresholds(params.qualityComprMode));
 	meta.headerComprMode = params.headerComprMode; meta.referenceReadsMode = params.referenceReadsMode;
 	meta.sparseMode_range = sparseMode_range; meta.sparseMode_exponent = params.sparseMode_exponent;
+	if (ref_genome) {
+		meta.ref_genome_available = true; meta.storeRefGenome = params.storeRefGenome;
+		meta.ref_genome_read_len = ref_genome_read_len; meta.ref_genome_overlap_size = ref_genome_overlap_size; meta.n_ref_genome_pseudo_reads = n_pseudo;
+		if (!params.storeRefGenome) meta.ref_genome_checksum = ref_genome->GetChecksum();
+	}
 	add_part(s_meta, meta.Serialize(), 0);
 	const int s_info = archive.RegisterStream("info");
 	info.time = static_cast<uint64_t>(std::time(nullptr));

@@ -28,6 +28,7 @@
 #include <string>
 #include <vector>
 #include "archive_host.h"
+#include "ref_genome_host.h"
 
 namespace clbhost {
 
@@ -331,12 +332,16 @@ public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
 	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
 	// max_bases: what the archive's info record announces; a damaged stream that decodes past it is refused instead of growing without bound
-	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull, uint32_t want_max_cand = 0)
+	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull, uint32_t want_max_cand = 0,
+		const std::vector<std::vector<uint8_t>>* first_refs = nullptr)
 	{
+		// first_refs: reference reads that precede the container's reads (the pseudo-reads of a reference genome): the container counts
+		// them as its context reads, their ids come first and the read ids start behind them
+		const uint32_t n_first = first_refs ? static_cast<uint32_t>(first_refs->size()) : 0;
 		Bytes in(data, size);
 		in.magic("DB01");
 		level = in.u32(); const uint32_t max_cand = in.u32(); const uint64_t nr = in.u64(); const uint32_t n_packs = in.u32(), n_ctx = in.u32();
-		if (nr != n_reads || n_ctx != 0 || level < 1 || level > 3) throw DecodeError("colord-b200: DNA stream does not fit the archive");
+		if (nr != n_reads || n_ctx != n_first || level < 1 || level > 3) throw DecodeError("colord-b200: DNA stream does not fit the archive");
 		if (max_cand < 1 || max_cand > 32 || (want_max_cand && max_cand != want_max_cand)) throw DecodeError("colord-b200: DNA stream does not fit the archive (candidate limit)");
 		n_t = level >= 3 ? 4 : level == 2 ? 3 : 2; n_s = level >= 3 ? 8 : level == 2 ? 7 : 5;
 		{	// table widths: colord_b200/csrc/dna_model.h (history widths dna_coder.cpp:1253-1280)
@@ -349,6 +354,7 @@ public:
 		M.read_tables(in);
 		const uint64_t mask_s = (1ull << (2 * n_s)) - 1, mask_t = (1ull << (3 * n_t)) - 1; const uint32_t sh_t = 3 * n_t;
 		std::vector<std::vector<uint8_t>> refs;                    // reference reads decoded so far (symbols 0..3)
+		if (first_refs) refs = *first_refs;
 		Reads out; out.offsets.reserve(n_reads + 1);
 		std::vector<uint8_t> rd, fl;
 		uint32_t r0 = 0;
@@ -368,7 +374,7 @@ public:
 				uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
 				if (flag == 0) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYM, ctx_symbol << 2); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; }
 				else if (flag == 1) for (uint32_t i = 0; i < len; ++i) { const uint32_t s = d.get(M, F_SYMN, ctx_symbol); rd.push_back(static_cast<uint8_t>(s)); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; }
-				else dna_edit_script(src, level, n_s, r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t, max_bases - std::min<uint64_t>(max_bases, out.bases.size()));
+				else dna_edit_script(src, level, n_s, n_first + r, len, refs, rd, fl, ctx_symbol, ctx_tuple, mask_s, mask_t, sh_t, max_bases - std::min<uint64_t>(max_bases, out.bases.size()));
 				if (rd.size() > max_bases - std::min<uint64_t>(max_bases, out.bases.size())) throw DecodeError("colord-b200: damaged DNA stream (more bases than the archive announces)");
 				fl.resize(rd.size(), 0);
 				for (uint8_t s : rd) out.bases.push_back("ACGTN"[s > 4 ? 4 : s]);
@@ -590,7 +596,8 @@ struct DecompressedArchive {
 	CInfo info; CMeta meta;
 	dec::Reads reads; dec::Headers headers; std::vector<uint8_t> quals;      // quals: same layout as reads.bases, empty for FASTA
 
-	explicit DecompressedArchive(const std::string& archive_path, bool verbose = false)
+	// ref_genome_path: the genome of a -G archive that does not carry it (decompression_common.cpp:262-283)
+	explicit DecompressedArchive(const std::string& archive_path, bool verbose = false, const std::string& ref_genome_path = std::string())
 	{
 		CArchive archive(true);
 		if (!archive.Open(archive_path)) throw std::runtime_error("Error: cannot open archive: " + archive_path);
@@ -606,8 +613,10 @@ struct DecompressedArchive {
 			throw DecodeError("Error: incompatibile archive version");
 		if (!archive.ReadPart(s_meta, 0, raw, md)) throw DecodeError("Error: cannot read the meta record");
 		meta.Deserialize(raw, s_qual >= 0);
-		if (meta.ref_genome_available) throw DecodeError("Error: reference-genome archives are not available in this build");
 		const uint32_t n_reads = info.total_reads;
+		std::vector<std::vector<uint8_t>> pseudo;                   // the genome's pseudo-reads: the first reference reads (symbols 0..3)
+		if (meta.ref_genome_available) pseudo = pseudo_reads(archive, compat, ref_genome_path);
+		first_refs = pseudo.empty() ? nullptr : &pseudo;
 		if (verbose) std::cerr << "reads: " << n_reads << "\nbases: " << info.total_bases << "\nquality mode: " << static_cast<int>(meta.qualityComprMode) << "\n";
 
 		if (compat) { decode_reference_streams(archive, s_dna, s_qual, s_hdr, n_reads); return; }
@@ -616,7 +625,7 @@ struct DecompressedArchive {
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
 		dec::DnaDecoder dna;
 		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
-		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases, meta.maxCandidates);
+		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases, meta.maxCandidates, first_refs);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 
 		if (meta.headerComprMode == HeaderComprMode::Original) {
@@ -642,6 +651,40 @@ struct DecompressedArchive {
 	}
 	uint32_t n_reads() const { return static_cast<uint32_t>(reads.offsets.size() - 1); }
 private:
+	const std::vector<std::vector<uint8_t>>* first_refs = nullptr;
+	std::vector<std::vector<uint8_t>> pseudo_reads(CArchive& archive, bool compat, const std::string& ref_genome_path)
+	{
+		std::unique_ptr<CReferenceGenome> genome;
+		if (meta.storeRefGenome) {
+			const int s_gen = archive.GetStreamId(compat ? "ref-genome" : "ref-genome-b200");
+			if (s_gen < 0) throw DecodeError("Error: the archive announces a stored reference genome but has none");
+			std::vector<std::vector<uint8_t>> seqs; std::vector<uint8_t> part; size_t md = 0;
+			if (compat) {      // CReferenceGenome(archive): n_seqs plain reads from a DNA coder of their own, "level 9" (reference_genome.cpp:235-279)
+				if (!archive.ReadPart(s_gen, 0, part, md)) throw DecodeError("Error: cannot read the reference genome of the archive");
+				size_t served = 0;
+				const xdec::PartSource one = [&](std::vector<uint8_t>& data, size_t& m) { if (served++) return false; data = part; m = md; return true; };
+				std::vector<uint32_t> part_reads;
+				if (md >= (1ull << 32)) throw DecodeError("Error: damaged reference-genome stream");
+				const dec::Reads g = xdec::decode_dna(one, static_cast<uint32_t>(md), std::vector<uint8_t>(md, 0), 9, 2, false, ~0ull, part_reads);
+				for (size_t q = 0; q + 1 < g.offsets.size(); ++q) seqs.emplace_back(g.bases.begin() + g.offsets[q], g.bases.begin() + g.offsets[q + 1]);
+			} else {
+				const size_t n_parts = archive.Parts(s_gen).size();
+				for (size_t q = 0; q < n_parts; ++q) { if (!archive.ReadPart(s_gen, q, part, md)) throw DecodeError("Error: cannot read the reference genome of the archive"); try { seqs.push_back(CReferenceGenome::Unpack(part)); } catch (const std::runtime_error& e) { throw DecodeError(e.what()); } }
+			}
+			genome = std::make_unique<CReferenceGenome>(std::move(seqs));
+		} else {
+			if (ref_genome_path.empty()) throw DecodeError("Error: compressed file was created without -s switch, reference genome is required for decompression");
+			genome = std::make_unique<CReferenceGenome>(ref_genome_path);
+			if (genome->GetChecksum() != meta.ref_genome_checksum) throw DecodeError("Error: different reference genome was used during compression. Decompression impossible.");
+		}
+		genome->SetReadLen(meta.ref_genome_read_len, meta.ref_genome_overlap_size);
+		if (!genome->valid_read_len() || genome->GetNPseudoReads() != meta.n_ref_genome_pseudo_reads) throw DecodeError("Error: the reference genome does not fit the archive");
+		std::vector<uint8_t> pb; std::vector<uint64_t> po;
+		genome->PseudoReads(pb, po);
+		std::vector<std::vector<uint8_t>> out(po.size() - 1);
+		for (size_t q = 0; q + 1 < po.size(); ++q) { out[q].resize(po[q + 1] - po[q]); for (uint64_t i = po[q]; i < po[q + 1]; ++i) { const uint8_t ch = pb[i]; out[q][i - po[q]] = ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0; } }
+		return out;
+	}
 	// version-1 archives: one part per pack in every stream (entr_read.h:146-184, entr_qual.h:128-190, entr_header.cpp:49-80)
 	void decode_reference_streams(CArchive& archive, int s_dna, int s_qual, int s_hdr, uint32_t n_reads)
 	{
@@ -653,7 +696,7 @@ private:
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
 		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
 		std::vector<uint32_t> part_reads;
-		reads = xdec::decode_dna(parts_of(s_dna), n_reads, decisions, static_cast<uint32_t>(meta.compressionLevel), meta.maxCandidates, flags_needed, info.total_bases, part_reads);
+		reads = xdec::decode_dna(parts_of(s_dna), n_reads, decisions, static_cast<uint32_t>(meta.compressionLevel), meta.maxCandidates, flags_needed, info.total_bases, part_reads, first_refs);
 		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 		if (meta.headerComprMode == HeaderComprMode::Original) headers = xdec::decode_headers(parts_of(s_hdr), n_reads, info.total_bytes);
 		else for (uint32_t r = 0; r < n_reads; ++r) {
@@ -667,9 +710,9 @@ private:
 };
 
 // decompression.cpp: archive -> file.  FASTQ records: '@' id, bases, '+' [id], qualities; FASTA records: '>' id, bases on one line.
-inline void runDecompression(const std::string& archive_path, const std::string& output_path, bool verbose = false)
+inline void runDecompression(const std::string& archive_path, const std::string& output_path, bool verbose = false, const std::string& ref_genome_path = std::string())
 {
-	const DecompressedArchive A(archive_path, verbose);
+	const DecompressedArchive A(archive_path, verbose, ref_genome_path);
 	const CMeta& meta = A.meta; const dec::Reads& reads = A.reads; const dec::Headers& H = A.headers; const std::vector<uint8_t>& quals = A.quals;
 	const uint32_t n_reads = A.n_reads();
 	FILE* out = std::fopen(output_path.c_str(), "wb");

@@ -102,6 +102,11 @@ public:
 		file_bytes = static_cast<uint64_t>(st.st_size);
 		is_gzip = got == 2 && head[0] == 0x1f && head[1] == 0x8b;
 		is_fastq = got >= 1 && head[0] == '@';
+		if (is_gzip) {      // the first byte of the inflated data decides
+			gzFile gz = gzopen(path.c_str(), "rb");
+			uint8_t first = 0;
+			if (gz) { if (gzread(gz, &first, 1) == 1) is_fastq = first == '@'; gzclose(gz); }
+		}
 		if (const char* e = std::getenv("CLB_NO_STREAMING")) if (*e && *e != '0') return false;
 		return !is_gzip && is_fastq && file_bytes >= min_bytes;
 	}
@@ -291,7 +296,8 @@ private:
 		const uint8_t* end = data + size;
 		const uint64_t n_pieces = (size + piece - 1) / piece;
 		T = static_cast<unsigned>(std::min<uint64_t>(T, n_pieces));
-		const uint64_t W = std::min<uint64_t>(n_pieces, static_cast<uint64_t>(T) + 2);
+		// the ring: enough slots for every thread + the consumer, and up to 64 pieces (4 GiB) of head start while the consumer is not ready yet
+		const uint64_t W = std::min<uint64_t>(n_pieces, std::max<uint64_t>(static_cast<uint64_t>(T) + 2, 64));
 		std::vector<Slot> slots(W);      // declared before the threads: destroyed after they are joined
 		for (uint64_t i = 0; i < W; ++i) slots[i].free_for = i;
 		std::mutex m; std::condition_variable cv; std::atomic<uint64_t> next_piece{0}; bool stop = false;

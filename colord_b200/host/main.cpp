@@ -27,7 +27,8 @@ static void usage()
 		"      -i,--identifier org|main|none  -t,--threads N (accepted, unused)  -v,--verbose  --device N\n"
 		"      --compat | --native   streams of the archive: the reference's own (readable by `colord decompress`, every -q mode) or the\n"
 		"                            device's containers (org, *-avg, none); default: --compat up to --compat-max-mbases N (512) input Mbases\n"
-		"  colord-b200 decompress archive output\n"
+		"      -G,--reference-genome file  -s,--store-reference\n"
+		"  colord-b200 decompress [-G,--reference-genome file] archive output\n"
 		"  colord-b200 info archive\n";
 }
 
@@ -123,10 +124,10 @@ int main(int argc, char** argv)
 		if (cmd == "compress-ont" || cmd == "compress-pbhifi" || cmd == "compress-pbraw") return run_compress(cmd, argc, argv, full_cmd);
 		if (cmd == "info") { if (argc != 3) { usage(); return 1; } return run_info(argv[2]); }
 		if (cmd == "decompress") {
-			std::vector<std::string> pos; bool verbose = false;
-			for (int i = 2; i < argc; ++i) { const std::string a = argv[i]; if (a == "-v" || a == "--verbose") verbose = true; else if (a == "-G" || a == "--reference-genome") throw std::invalid_argument("reference-genome mode (-G) is not available in this build"); else pos.push_back(a); }
+			std::vector<std::string> pos; bool verbose = false; std::string genome;
+			for (int i = 2; i < argc; ++i) { const std::string a = argv[i]; if (a == "-v" || a == "--verbose") verbose = true; else if (a == "-G" || a == "--reference-genome") { if (i + 1 >= argc) throw std::invalid_argument("option -G needs a value"); genome = argv[++i]; } else pos.push_back(a); }
 			if (pos.size() != 2) { usage(); return 1; }
-			runDecompression(pos[0], pos[1], verbose);
+			runDecompression(pos[0], pos[1], verbose, genome);
 			return 0;
 		}
 		usage();

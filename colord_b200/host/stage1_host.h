@@ -98,7 +98,9 @@ public:
 	CReadsSimilarityGraph(CKmerCounter& counter, uint32_t max_candidates, bool hifi, bool sparse, const CRefReadsAccepter& accepter, uint32_t n_pseudo = 0)
 		: ctx(counter.Context()), max_candidates(max_candidates), hifi(hifi), n_reads(counter.GetNReads())
 	{
-		std::vector<uint8_t> dec = sparse ? accepter.Decisions(n_reads) : std::vector<uint8_t>(n_reads, 1);
+		// the accepter's index runs over pseudo-reads + reads; clb_graph_build takes the decisions of the reads (pseudo-reads are always accepted)
+		std::vector<uint8_t> dec(n_reads, 1);
+		if (sparse) { const std::vector<uint8_t> all = accepter.Decisions(n_pseudo + n_reads); dec.assign(all.begin() + n_pseudo, all.end()); }
 		check(ctx, clb_graph_build(ctx, dec.data(), n_pseudo), "clb_graph_build");
 	}
 	std::vector<CCompressElem> Elements() const

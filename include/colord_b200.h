@@ -93,6 +93,12 @@ clb_status clb_filter_import(clb_ctx* ctx, const uint64_t* kmers, const uint32_t
 /* CKmerFilter::Possible && Check for a batch of canonical k-mers (kmer_filter.h:129-137); HOST buffers. */
 clb_status clb_filter_check(clb_ctx* ctx, const uint64_t* kmers, uint64_t n, uint8_t* possible, uint8_t* present);
 
+/* Sequences that are counted like reads but are not reads: the reference hands the reference genome (-G) to KMC as a second input
+ * file (compression.cpp:408-430), so its k-mers count towards the thresholds and the statistics (n_reads excepted: the caller adds the
+ * number of sequences, compression.cpp:445-448).  Before clb_count_finalize.  The genome's pseudo-reads then enter through
+ * clb_append_context_reads: always-accepted reference reads in front of the input's reads, never encoded (reads_sim_graph.cpp:295-322). */
+clb_status clb_count_sequences(clb_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_seqs, int on_device);
+
 /* ---- Multi-GPU: the global reference-read set -----------------------------------------
  * Reads shard by id, but the candidates of a read are EARLIER reference reads of the whole input (reads_sim_graph.cpp:374-395),
  * most of which sit at the start of the file in sparse mode (ref_reads_accepter.h:51-57).  Rank r therefore receives the
@@ -245,7 +251,11 @@ clb_status clb_xqual_encode(clb_ctx* ctx, uint32_t mode, uint32_t source, uint32
                             int on_device, const uint32_t* pack_sizes, uint32_t n_packs);
 clb_status clb_xhdr_encode(clb_ctx* ctx, const uint8_t* bytes, const uint64_t* offsets, const uint8_t* plus_id, uint64_t n_headers, int on_device,
                            const uint32_t* pack_sizes, uint32_t n_packs);
-/* which: 0 dna, 1 qual, 2 header.  The parts lie back to back in `bytes`; part_sizes[n_parts] (HOST) receives their lengths. */
+/* The stored reference genome (CReferenceGenome::Store(archive), reference_genome.cpp:319-360): the sequences (HOST: ASCII ACGT back to back
+ * + offsets[n + 1]) coded as plain reads by a DNA coder of their own at `level` (the reference passes 9: one symbol of history); one part,
+ * fetched as stream 3 of clb_xstream_get.  One range coder over the whole genome is one serial chain: meant for genomes of megabases. */
+clb_status clb_xplain_encode(clb_ctx* ctx, const uint8_t* bases, const uint64_t* offsets, uint32_t n_seqs, uint32_t level);
+/* which: 0 dna, 1 qual, 2 header, 3 ref-genome.  The parts lie back to back in `bytes`; part_sizes[n_parts] (HOST) receives their lengths. */
 clb_status clb_xstream_size(clb_ctx* ctx, uint32_t which, uint64_t* total_bytes, uint32_t* n_parts);
 clb_status clb_xstream_get(clb_ctx* ctx, uint32_t which, uint8_t* bytes, uint64_t cap, uint64_t* part_sizes, int on_device);
 

@@ -68,11 +68,8 @@ class DecompressionStream {
 	uint32_t next = 0;
 public:
 	explicit DecompressionStream(const std::string& inputFilePath) : a(std::make_unique<clbhost::DecompressedArchive>(inputFilePath)) {}
-	// the reference's second constructor; reference-genome archives are not written by colord-b200
-	DecompressionStream(const std::string& inputFilePath, const std::string& refGenomePath) : DecompressionStream(inputFilePath)
-	{
-		if (!refGenomePath.empty()) throw std::runtime_error("colord-b200 archives carry no reference genome");
-	}
+	// the reference's second constructor (colord_api.h:96): the genome of an archive made with -G and without -s
+	DecompressionStream(const std::string& inputFilePath, const std::string& refGenomePath) : a(std::make_unique<clbhost::DecompressedArchive>(inputFilePath, false, refGenomePath)) {}
 	Info GetInfo() const
 	{
 		Info i;
@@ -104,3 +101,8 @@ public:
 };
 
 } // namespace colord_b200
+
+// a program written against the reference's src/API/colord_api.h (namespace colord) compiles unchanged against this header
+#ifndef COLORD_B200_NO_COLORD_NAMESPACE
+namespace colord = colord_b200;
+#endif

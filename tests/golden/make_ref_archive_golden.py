@@ -35,7 +35,25 @@ CASES = {
     "ont_none": (ONT, ["compress-ont", "-q", "none"]),
     "ont_id_none": (ONT, ["compress-ont", "-i", "none"]),
     "ont_fasta": (ONT, ["compress-ont"]),
+    # reference-genome mode: the genome (GENOME below, three sequences with lower case, N runs and blank lines) stored in the archive / given again
+    "ont_genome_stored": (ONT, ["compress-ont", "-G", "genome.fa", "-s"]),
+    "ont_genome_checksum_bal": (ONT, ["compress-ont", "-G", "genome.fa", "-p", "balanced"]),
 }
+
+
+def write_genome(path, gen):
+    """the genome the synthetic reads of `gen` were drawn from (synth.generate's first draw), cut into three FASTA records"""
+    import numpy as np
+    g = np.random.default_rng(gen["seed"]).integers(0, 4, gen["genome_len"], dtype=np.uint8)
+    asc = np.frombuffer(b"ACGT", np.uint8)[g].tobytes().decode()
+    a, b = len(asc) // 3, 2 * len(asc) // 3
+    recs = [("chr1 first", asc[:a]), ("chr2", asc[a:b].lower()), ("chr3 with N", asc[b:b + 500] + "N" * 37 + asc[b + 500:])]
+    with open(path, "w") as f:
+        for name, seq in recs:
+            f.write(">" + name + "\n")
+            for i in range(0, len(seq), 70):
+                f.write(seq[i:i + 70] + "\n")
+            f.write("\n")
 
 
 def main():
@@ -52,10 +70,12 @@ def main():
                         f.write(b">" + h + b"\n" + s.bases[int(s.offsets[i]):int(s.offsets[i + 1])].tobytes() + b"\n")
             else:
                 s.write_fastq(inp)
+            if "-G" in cli:
+                write_genome(os.path.join(tmp, "genome.fa"), gen)
             arc = os.path.join(OUT, name + ".colord")
             subprocess.run([exe, *cli, "-t", "2", inp, arc], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
             out = os.path.join(tmp, "out")
-            subprocess.run([exe, "decompress", arc, out], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
+            subprocess.run([exe, "decompress", *(["-G", "genome.fa"] if "-G" in cli and "-s" not in cli else []), arc, out], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=tmp)
             data = open(out, "rb").read()
             exp[name] = dict(generator=gen, cli=cli, output_sha1=hashlib.sha1(data).hexdigest(), output_bytes=len(data),
                              lossless=("org" in cli and "-i" not in cli) or name == "ont_fasta", input_sha1=hashlib.sha1(open(inp, "rb").read()).hexdigest())

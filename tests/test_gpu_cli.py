@@ -199,6 +199,48 @@ def test_cli_streamed_input_equals_whole_file_input(cli, tmp_path):
         _same_parts(str(tmp_path / "c.colord"), str(tmp_path / "r.colord"), "streamed compat")
 
 
+@pytest.mark.parametrize("fmt", ["native", "compat"])
+@pytest.mark.parametrize("store", [True, False])
+def test_cli_reference_genome_mode(cli, tmp_path, fmt, store):
+    """-G [-s] (BASELINE config 5): the genome's sequences are counted with the reads, its pseudo-reads are the first reference reads.
+    Round trip in both stream formats; in compat format the archive's parts (the stored genome included) are the stock binary's and
+    each decompressor reads the other's archive."""
+    import importlib.util
+    import colord_archive
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_ref_archive_golden.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    gen = dict(n_reads=700, genome_len=200000, mean_len=2500, seed=41, profile="ont", n_frac=0.03)
+    s = synth.generate(**gen)
+    fq, genome = str(tmp_path / "in.fastq"), str(tmp_path / "genome.fa")
+    s.write_fastq(fq)
+    mk.write_genome(genome, gen)
+    opts = ["-G", genome, "-q", "org"] + (["-s"] if store else [])
+    dopts = [] if store else ["-G", genome]
+    arch, back = str(tmp_path / "a.colord"), str(tmp_path / "back")
+    r = subprocess.run([cli, "compress-ont", *opts, "--" + fmt, "-v", fq, arch], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "# ref genome pseudo reads:" in r.stderr
+    r = subprocess.run([cli, "decompress", *dopts, arch, back], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(back, "rb").read() == open(fq, "rb").read()
+    # the genome pays: the DNA stream is smaller than without it
+    plain = str(tmp_path / "p.colord")
+    assert subprocess.run([cli, "compress-ont", "-q", "org", "--" + fmt, fq, plain], capture_output=True).returncode == 0
+    with_g, without = colord_archive.read_parts(arch), colord_archive.read_parts(plain)
+    dna = "dna" if fmt == "compat" else "dna-b200"
+    assert sum(len(b) for _, b in with_g[dna]) < sum(len(b) for _, b in without[dna])
+    if fmt == "compat" and os.path.exists(REF):
+        ref_arch, ref_back = str(tmp_path / "ref.colord"), str(tmp_path / "ref_back")
+        rr = subprocess.run([REF, "compress-ont", *opts, "-t", "4", fq, ref_arch], capture_output=True, text=True, cwd=str(tmp_path))
+        assert rr.returncode == 0, rr.stderr
+        _same_parts(arch, ref_arch, "genome")
+        if store:
+            assert with_g["ref-genome"] == colord_archive.read_parts(ref_arch)["ref-genome"]
+        rr = subprocess.run([REF, "decompress", *dopts, arch, ref_back], capture_output=True, text=True, cwd=str(tmp_path))
+        assert rr.returncode == 0, rr.stderr
+        assert open(ref_back, "rb").read() == open(fq, "rb").read()
+
+
 def test_cli_refusals(cli, tmp_path):
     """Errors end in exit code 1 with a message, as in the reference's CLI (arg_parse.cpp:820-902, in_reads.cpp)."""
     bad = str(tmp_path / "bad.fastq")
@@ -207,7 +249,7 @@ def test_cli_refusals(cli, tmp_path):
     assert r.returncode == 1 and "Only ACGTN symbols supported inside a read" in r.stderr
     ok = str(tmp_path / "ok.fastq")
     open(ok, "wb").write(b"@r\nACGT\n+\nIIII\n")
-    for opts, msg in ((["-G", "x.fa"], "not available"), (["-q", "4-fix", "--native"], "compat streams only"), (["-q", "bogus"], "unknown quality"), (["-k", "99"], "15..28")):
+    for opts, msg in ((["-G", "x.fa"], "cannot open file"), (["-q", "4-fix", "--native"], "compat streams only"), (["-q", "bogus"], "unknown quality"), (["-k", "99"], "15..28")):
         r = subprocess.run([cli, "compress-ont", *opts, ok, str(tmp_path / "o")], capture_output=True, text=True)
         assert r.returncode == 1 and msg in r.stderr, (opts, r.stderr)
     r = subprocess.run([cli, "decompress", ok, str(tmp_path / "o2")], capture_output=True, text=True)

@@ -22,10 +22,23 @@ with open(os.path.join(DIR, "expected.json")) as f:
 pytestmark = pytest.mark.skipif(not os.path.exists(CLI), reason="colord-b200 is not built")
 
 
+def _genome_args(name, tmp_path):
+    """-G archives without -s need the genome again: rebuilt as the fixture generator wrote it"""
+    e = EXPECTED[name]
+    if "-G" not in e["cli"] or "-s" in e["cli"]:
+        return []
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_ref_archive_golden.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    p = str(tmp_path / "genome.fa")
+    mk.write_genome(p, e["generator"])
+    return ["-G", p]
+
+
 @pytest.mark.parametrize("name", list(EXPECTED))
 def test_reference_archive_decodes_like_the_reference(name, tmp_path):
     out = str(tmp_path / "out")
-    r = subprocess.run([CLI, "decompress", os.path.join(DIR, name + ".colord"), out], capture_output=True, text=True)
+    r = subprocess.run([CLI, "decompress", *_genome_args(name, tmp_path), os.path.join(DIR, name + ".colord"), out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     data = open(out, "rb").read()
     e = EXPECTED[name]
@@ -33,6 +46,16 @@ def test_reference_archive_decodes_like_the_reference(name, tmp_path):
     assert hashlib.sha1(data).hexdigest() == e["output_sha1"]
     if e["lossless"]:
         assert hashlib.sha1(data).hexdigest() == e["input_sha1"]
+
+
+def test_genome_archives_refuse_a_missing_or_different_genome(tmp_path):
+    arc = os.path.join(DIR, "ont_genome_checksum_bal.colord")
+    r = subprocess.run([CLI, "decompress", arc, str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 1 and "reference genome is required" in r.stderr
+    g = str(tmp_path / "other.fa")
+    open(g, "w").write(">x\nACGTACGTTTGACCA\n")
+    r = subprocess.run([CLI, "decompress", "-G", g, arc, str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode == 1 and "different reference genome" in r.stderr
 
 
 def test_info_of_a_reference_archive():
