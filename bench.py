@@ -190,8 +190,8 @@ def run_port_stage1(n_reads=2000):
     return s.fastq_bytes(), time.time() - t0
 
 
-def cpu_baseline(sample_reads=25000, with_ratio_check=True):
-    """The stock reference on a 400 MB sample of the workload, once; beside it the command line of this repo on the SAME file
+def cpu_baseline(sample_reads=125000, with_ratio_check=True):
+    """The stock reference on a 2 GB sample of the workload, once (~20 s on 16 cores); beside it the command line of this repo on the SAME file
     (ratio_check: archive sizes of both, and file -> archive MB/s of colord-b200 in both stream formats)."""
     cores = os.cpu_count() or 1
     if not os.path.exists(REF_BIN):
@@ -210,7 +210,7 @@ def cpu_baseline(sample_reads=25000, with_ratio_check=True):
             check = {"config": f"compress-ont default on the same {nbytes}-byte FASTQ file", "ref_bytes": ref_bytes, "ref_streams": ref_sizes}
             for fmt in ("native", "compat"):
                 try:
-                    t, sizes = run_cli(OUR_CLI, fq, os.path.join(tmp, fmt + ".colord"), ["--" + fmt])
+                    t, sizes = run_cli(OUR_CLI, fq, os.path.join(tmp, fmt + ".colord"), ["--" + fmt, "-v"])
                     ours = os.path.getsize(os.path.join(tmp, fmt + ".colord"))
                     check[fmt] = {"ours_bytes": ours, "ratio": ours / ref_bytes, "streams": sizes, "file_to_archive_MBps": nbytes / t / 1e6, "wall_s": t}
                 except Exception as ex:

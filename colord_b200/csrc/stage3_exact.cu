@@ -12,7 +12,7 @@
 //                  a stable radix sort by (family, context) brings every context's events together in stream order, one thread per
 //                  context replays its model (counts, +adder, halving at max_total; Encode / EncodeExcluding rc.h:780-803,
 //                  :861-893) and leaves (frequency, cumulative frequency, total) at each event;
-//   3. range coder restarts per pack, so the packs are independent: one thread per pack runs sub_rc.h:83-201 over its events'
+//   3. range coder restarts per pack, so the packs are independent: one warp per pack runs sub_rc.h:83-201 over its events'
 //                  triples (the only serial loop left: one pack = 4 MiB of bases), parts are then laid out back to back.
 // Memory is ~30 bytes per event for the duration of a stream, so this path is meant for inputs up to a few Gbases per GPU; the
 // native containers (stage3_dna.cu, stage3_qual.cu, ...) stay the path for the whole-genome scale.
@@ -143,34 +143,43 @@ __global__ void __launch_bounds__(128) k_x_model(const uint64_t* __restrict__ ke
 	}
 }
 
-// ---- 3. range coder: one thread per pack (sub_rc.h:72-211) -------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_x_code(const ulonglong2* __restrict__ triple, const uint64_t* __restrict__ pack_ev, uint32_t n_packs,
+// ---- 3. range coder: one WARP per pack (sub_rc.h:72-211) --------------------------------------------------------------
+// The coder's state is one serial chain per pack.  A lone thread walking its pack's triples pays a DRAM round trip for every other
+// event (measured: ~1000 cycles per event, profiles/r02e_compat_launches.csv), so the warp fetches 32 events at a time with one
+// coalesced load (the next 32 already on their way), every lane then follows the same chain — event i's triple comes from lane i by
+// shuffle, the state is identical in all lanes — and lane 0 stores the bytes.
+__global__ void __launch_bounds__(128) k_x_code(const ulonglong2* __restrict__ triple, const uint64_t* __restrict__ pack_ev, uint32_t n_packs,
 	uint8_t* __restrict__ tmp, const uint64_t* __restrict__ tmp_off, uint64_t* __restrict__ part_bytes)
 {
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	if (p >= n_packs) return;
 	uint8_t* out = tmp + tmp_off[p];
 	uint64_t n = 0;
 	unsigned long long low = 0, range = 0xff00000000000000ULL;
 	const uint64_t e0 = pack_ev[p], e1 = pack_ev[p + 1];
-	ulonglong2 nxt = e0 < e1 ? triple[e0] : make_ulonglong2(0, 0);
-	for (uint64_t e = e0; e < e1; ++e) {
-		const ulonglong2 t = nxt;
-		if (e + 1 < e1) nxt = triple[e + 1];                 // the next event's triple is on its way while this one is coded
-		const uint32_t freq = (uint32_t)(t.x & 0x1fffff), cum = (uint32_t)((t.x >> 21) & 0x1fffff), tot = (uint32_t)(t.x >> 42);
-		unsigned long long q = __umul64hi(range, t.y);        // range / tot: t.y = floor((2^64 - 1) / tot) gives the quotient or one less
-		if (range - q * tot >= tot) ++q;
-		range = q;
-		low += range * cum;
-		range *= freq;
-		for (int k = 0; k < 8 && range <= 0x00ffffffffffffULL; ++k) {      // UNROLL_FREQUENCY_CODING: at most 8 bytes per symbol
-			if ((low ^ (low + range)) & 0xff00000000000000ULL) { const unsigned long long x = low; range = (x | 0x00ffffffffffffULL) - x; }
-			out[n++] = (uint8_t)(low >> 56);
-			low <<= 8; range <<= 8;
+	ulonglong2 nxt = e0 + lane < e1 ? triple[e0 + lane] : make_ulonglong2(0, 1);
+	for (uint64_t e = e0; e < e1; e += 32) {
+		const ulonglong2 cur = nxt;
+		if (e + 32 + lane < e1) nxt = triple[e + 32 + lane];
+		const uint32_t m = (uint32_t)min((uint64_t)32, e1 - e);
+		for (uint32_t i = 0; i < m; ++i) {
+			const unsigned long long x = __shfl_sync(0xffffffffu, cur.x, i), inv = __shfl_sync(0xffffffffu, cur.y, i);
+			const uint32_t freq = (uint32_t)(x & 0x1fffff), cum = (uint32_t)((x >> 21) & 0x1fffff), tot = (uint32_t)(x >> 42);
+			unsigned long long q = __umul64hi(range, inv);       // range / tot: inv = floor((2^64 - 1) / tot) gives the quotient or one less
+			if (range - q * tot >= tot) ++q;
+			range = q;
+			low += range * cum;
+			range *= freq;
+			for (int k = 0; k < 8 && range <= 0x00ffffffffffffULL; ++k) {      // UNROLL_FREQUENCY_CODING: at most 8 bytes per symbol
+				if ((low ^ (low + range)) & 0xff00000000000000ULL) { const unsigned long long y = low; range = (y | 0x00ffffffffffffULL) - y; }
+				if (lane == 0) out[n] = (uint8_t)(low >> 56);
+				++n;
+				low <<= 8; range <<= 8;
+			}
 		}
 	}
-	for (int i = 0; i < 8; ++i) { out[n++] = (uint8_t)(low >> 56); low <<= 8; }      // End (sub_rc.h:203-210)
-	part_bytes[p] = n;
+	for (int i = 0; i < 8; ++i) { if (lane == 0) out[n] = (uint8_t)(low >> 56); ++n; low <<= 8; }      // End (sub_rc.h:203-210)
+	if (lane == 0) part_bytes[p] = n;
 }
 __global__ void __launch_bounds__(256) k_x_compact(const uint8_t* __restrict__ tmp, const uint64_t* __restrict__ tmp_off, const uint64_t* __restrict__ dst_off,
 	const uint64_t* __restrict__ part_bytes, uint8_t* __restrict__ out)
@@ -232,7 +241,7 @@ static clb_status x_code_stream(clb_ctx* c, cudaStream_t s, int kid, const XFams
 	part_sizes.assign(np, 0);
 	total = 0;
 	if (!np) return CLB_OK;
-	timed_begin(); k_x_code<<<(np + 31) / 32, 32, 0, s>>>(d_triple, d_pack_ev, np, d_tmp, d_tmp_off, d_bytes); timed_end(); CLB_LAUNCH_CHECK(c, "k_x_code");
+	timed_begin(); k_x_code<<<(np + 3) / 4, 128, 0, s>>>(d_triple, d_pack_ev, np, d_tmp, d_tmp_off, d_bytes); timed_end(); CLB_LAUNCH_CHECK(c, "k_x_code");
 	CLB_CUDA(c, cudaMemcpyAsync(part_sizes.data(), d_bytes, sizeof(uint64_t) * np, cudaMemcpyDeviceToHost, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	std::vector<uint64_t> dst(np + 1, 0);
