@@ -171,6 +171,9 @@ def run_cli(exe, fastq, out, extra=()):
     if r.returncode != 0:
         raise RuntimeError(f"{os.path.basename(exe)} failed: {r.stderr[-300:]}")
     sizes = {k: int(m.group(1)) for name, k in SIZE_KEYS for m in [re.search(rf"^{name} size\s*:\s*(\d+)", r.stderr, re.M)] if m}
+    m = re.search(r"phase device context \(rest of it\): ([0-9.e+-]+) s", r.stderr)      # colord-b200 -v: what the process waited for the CUDA start-up
+    if m:
+        sizes["cuda_startup_wait_s"] = float(m.group(1))
     return dt, sizes
 
 
