@@ -332,12 +332,16 @@ public:
 	// decisions[r]: the sampler's answer for read r (all ones when every read is a reference); reads holding N never are
 	// want_flags false: the per-base flags are not kept (they only feed the quality contexts at level > 1; a third of the memory)
 	// max_bases: what the archive's info record announces; a damaged stream that decodes past it is refused instead of growing without bound
-	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const std::vector<uint8_t>& decisions, bool want_flags = true, uint64_t max_bases = ~0ull, uint32_t want_max_cand = 0,
-		const std::vector<std::vector<uint8_t>>* first_refs = nullptr)
+	// refs_io: the reference reads that precede the container's reads — the pseudo-reads of a reference genome, the reference reads of
+	// the shards before this one in a multi-GPU archive.  The container counts them as its context reads: their ids come first, the
+	// read ids start behind them.  The container's own reference reads are appended, so that the next shard finds them.
+	// decisions: the sampler's answers for the container's reads (a slice of the archive's).
+	Reads decode(const uint8_t* data, uint64_t size, uint32_t n_reads, const uint8_t* decisions, bool want_flags = true, uint64_t max_bases = ~0ull, uint32_t want_max_cand = 0,
+		std::vector<std::vector<uint8_t>>* refs_io = nullptr)
 	{
-		// first_refs: reference reads that precede the container's reads (the pseudo-reads of a reference genome): the container counts
-		// them as its context reads, their ids come first and the read ids start behind them
-		const uint32_t n_first = first_refs ? static_cast<uint32_t>(first_refs->size()) : 0;
+		std::vector<std::vector<uint8_t>> own_refs;
+		std::vector<std::vector<uint8_t>>& refs = refs_io ? *refs_io : own_refs;                    // reference reads decoded so far (symbols 0..3)
+		const uint32_t n_first = static_cast<uint32_t>(refs.size());
 		Bytes in(data, size);
 		in.magic("DB01");
 		level = in.u32(); const uint32_t max_cand = in.u32(); const uint64_t nr = in.u64(); const uint32_t n_packs = in.u32(), n_ctx = in.u32();
@@ -353,8 +357,6 @@ public:
 		}
 		M.read_tables(in);
 		const uint64_t mask_s = (1ull << (2 * n_s)) - 1, mask_t = (1ull << (3 * n_t)) - 1; const uint32_t sh_t = 3 * n_t;
-		std::vector<std::vector<uint8_t>> refs;                    // reference reads decoded so far (symbols 0..3)
-		if (first_refs) refs = *first_refs;
 		Reads out; out.offsets.reserve(n_reads + 1);
 		std::vector<uint8_t> rd, fl;
 		uint32_t r0 = 0;
@@ -616,42 +618,56 @@ struct DecompressedArchive {
 		const uint32_t n_reads = info.total_reads;
 		std::vector<std::vector<uint8_t>> pseudo;                   // the genome's pseudo-reads: the first reference reads (symbols 0..3)
 		if (meta.ref_genome_available) pseudo = pseudo_reads(archive, compat, ref_genome_path);
-		first_refs = pseudo.empty() ? nullptr : &pseudo;
 		if (verbose) std::cerr << "reads: " << n_reads << "\nbases: " << info.total_bases << "\nquality mode: " << static_cast<int>(meta.qualityComprMode) << "\n";
 
-		if (compat) { decode_reference_streams(archive, s_dna, s_qual, s_hdr, n_reads); return; }
-		std::vector<uint8_t> stream;
-		if (!archive.ReadPart(s_dna, 0, stream, md) || md != n_reads) throw DecodeError("Error: cannot read the DNA stream");
+		if (compat) { decode_reference_streams(archive, s_dna, s_qual, s_hdr, n_reads, pseudo.empty() ? nullptr : &pseudo); return; }
+		// native containers: one part per stream and shard (a single-GPU archive is one shard; colord-b200 --gpus N writes N, whose
+		// DNA containers name the reference reads of the shards before them as their context reads)
 		const std::vector<uint8_t> decisions = meta.referenceReadsMode == ReferenceReadsMode::Sparse ? dec::sampler_decisions(meta.sparseMode_range, meta.sparseMode_exponent, n_reads) : std::vector<uint8_t>(n_reads, 1);
-		dec::DnaDecoder dna;
 		const bool flags_needed = meta.is_fastq && meta.compressionLevel > 1 && meta.qualityComprMode != QualityComprMode::None;
-		reads = dna.decode(stream.data(), stream.size(), n_reads, decisions, flags_needed, info.total_bases, meta.maxCandidates, first_refs);
-		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
-
-		if (meta.headerComprMode == HeaderComprMode::Original) {
-			if (!archive.ReadPart(s_hdr, 0, stream, md)) throw DecodeError("Error: cannot read the header stream");
-			headers = dec::decode_headers(stream.data(), stream.size(), n_reads);
-		} else {	// no header bytes were stored: the reference prints the id "@" for `none` (id_coder.cpp:393-396) and an empty id for `main` (:588-591)
-			for (uint32_t r = 0; r < n_reads; ++r) {
+		const size_t n_shards = archive.Parts(s_dna).size();
+		if (!n_shards || archive.Parts(s_hdr).size() != n_shards || (meta.is_fastq && archive.Parts(s_qual).size() != n_shards)) throw DecodeError("Error: the streams of the archive do not have the same shards");
+		std::vector<std::vector<uint8_t>> refs = pseudo;
+		std::vector<uint8_t> stream;
+		uint32_t r0 = 0;
+		for (size_t sh = 0; sh < n_shards; ++sh) {
+			if (!archive.ReadPart(s_dna, sh, stream, md) || md > n_reads - r0) throw DecodeError("Error: cannot read the DNA stream");
+			const uint32_t n_sh = static_cast<uint32_t>(md);
+			dec::DnaDecoder dna;
+			dec::Reads part = dna.decode(stream.data(), stream.size(), n_sh, decisions.data() + r0, flags_needed, info.total_bases - std::min<uint64_t>(info.total_bases, reads.bases.size()), meta.maxCandidates, &refs);
+			if (meta.is_fastq) {
+				if (!archive.ReadPart(s_qual, sh, stream, md)) throw DecodeError("Error: cannot read the quality stream");
+				std::vector<uint8_t> q;
+				switch (meta.qualityComprMode) {
+				case QualityComprMode::None: q.assign(part.bases.size(), static_cast<uint8_t>(33 + meta.qualityRevThresholds.at(0))); break;      // quality_coder.cpp:611-617
+				case QualityComprMode::Original: q = dec::decode_qual_org(stream.data(), stream.size(), part); break;
+				case QualityComprMode::BinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::QuinaryAverage: q = dec::decode_qual_avg(stream.data(), stream.size(), part); break;
+				default: throw DecodeError("Error: quality mode of the archive is not available in this build");
+				}
+				quals.insert(quals.end(), q.begin(), q.end());
+			}
+			if (meta.headerComprMode == HeaderComprMode::Original) {
+				if (!archive.ReadPart(s_hdr, sh, stream, md)) throw DecodeError("Error: cannot read the header stream");
+				const dec::Headers h = dec::decode_headers(stream.data(), stream.size(), n_sh);
+				const uint64_t h0 = headers.bytes.size();
+				headers.bytes.insert(headers.bytes.end(), h.bytes.begin(), h.bytes.end());
+				for (size_t i = 1; i < h.offsets.size(); ++i) headers.offsets.push_back(h0 + h.offsets[i]);
+				headers.plus_id.insert(headers.plus_id.end(), h.plus_id.begin(), h.plus_id.end());
+			} else for (uint32_t r = 0; r < n_sh; ++r) {	// no header bytes were stored: the reference prints the id "@" for `none` (id_coder.cpp:393-396) and an empty id for `main` (:588-591)
 				if (meta.headerComprMode == HeaderComprMode::None) headers.bytes.push_back('@');
 				headers.offsets.push_back(headers.bytes.size());
 				headers.plus_id.push_back(0);
 			}
+			const uint64_t b0 = reads.bases.size();
+			reads.bases.insert(reads.bases.end(), part.bases.begin(), part.bases.end());
+			for (size_t i = 1; i < part.offsets.size(); ++i) reads.offsets.push_back(b0 + part.offsets[i]);
+			r0 += n_sh;
 		}
-
-		if (meta.is_fastq) {
-			if (!archive.ReadPart(s_qual, 0, stream, md)) throw DecodeError("Error: cannot read the quality stream");
-			switch (meta.qualityComprMode) {
-			case QualityComprMode::None: quals.assign(reads.bases.size(), static_cast<uint8_t>(33 + meta.qualityRevThresholds.at(0))); break;      // quality_coder.cpp:611-617
-			case QualityComprMode::Original: quals = dec::decode_qual_org(stream.data(), stream.size(), reads); break;
-			case QualityComprMode::BinaryAverage: case QualityComprMode::QuadAverage: case QualityComprMode::QuinaryAverage: quals = dec::decode_qual_avg(stream.data(), stream.size(), reads); break;
-			default: throw DecodeError("Error: quality mode of the archive is not available in this build");
-			}
-		}
+		if (r0 != n_reads) throw DecodeError("Error: the shards of the archive hold fewer reads than it announces");
+		if (reads.bases.size() != info.total_bases) throw DecodeError("Error: the decoded reads do not add up to the archive's base count");
 	}
 	uint32_t n_reads() const { return static_cast<uint32_t>(reads.offsets.size() - 1); }
 private:
-	const std::vector<std::vector<uint8_t>>* first_refs = nullptr;
 	std::vector<std::vector<uint8_t>> pseudo_reads(CArchive& archive, bool compat, const std::string& ref_genome_path)
 	{
 		std::unique_ptr<CReferenceGenome> genome;
@@ -686,7 +702,7 @@ private:
 		return out;
 	}
 	// version-1 archives: one part per pack in every stream (entr_read.h:146-184, entr_qual.h:128-190, entr_header.cpp:49-80)
-	void decode_reference_streams(CArchive& archive, int s_dna, int s_qual, int s_hdr, uint32_t n_reads)
+	void decode_reference_streams(CArchive& archive, int s_dna, int s_qual, int s_hdr, uint32_t n_reads, const std::vector<std::vector<uint8_t>>* first_refs)
 	{
 		auto parts_of = [&](int stream_id) -> xdec::PartSource {
 			auto next = std::make_shared<size_t>(0);

@@ -80,6 +80,7 @@ public:
 	std::vector<uint32_t> read_pack_sizes, header_pack_sizes;       // reads per read pack / headers per header pack
 	uint64_t total_bytes = 0, total_bases = 0, total_symb_header = 0, file_bytes = 0;
 	unsigned threads_used = 1;
+	const std::vector<uint32_t>& ReadLengths() const { return read_lens; }      // streaming form only
 	bool streamed = false; uint64_t n_reads_streamed = 0;          // streaming form: bases / quals / offsets went to the sink, not into the blocks above
 
 	uint32_t n_reads() const { return streamed ? static_cast<uint32_t>(n_reads_streamed) : static_cast<uint32_t>(offsets.size() - 1); }
@@ -110,16 +111,24 @@ public:
 		if (const char* e = std::getenv("CLB_NO_STREAMING")) if (*e && *e != '0') return false;
 		return !is_gzip && is_fastq && file_bytes >= min_bytes;
 	}
-	CInputReads(const std::string& path, const PieceSink& sink, unsigned n_threads = 0, uint64_t piece_bytes = 64u << 20, const HostAlloc* host_alloc = nullptr)
+	// range_begin / range_end: byte offsets into the file; the reader takes the records that START in [first record start at or after
+	// range_begin, first record start at or after range_end) — adjacent ranges tile the file (multi-GPU: one range per rank)
+	CInputReads(const std::string& path, const PieceSink& sink, unsigned n_threads = 0, uint64_t piece_bytes = 64u << 20, const HostAlloc* host_alloc = nullptr,
+		uint64_t range_begin = 0, uint64_t range_end = ~0ull)
 	{
 		Input in(path, *this);
-		total_bytes = in.n;
 		if (!in.n || in.p[0] != '@' || is_gzip || (in.p[in.n - 1] != '\n' && in.p[in.n - 1] != '\r')) throw StreamingFallback();
 		is_fastq = true; streamed = true;
 		if (!n_threads) { const char* e = std::getenv("CLB_READER_THREADS"); n_threads = e ? static_cast<unsigned>(std::atoi(e)) : std::thread::hardware_concurrency(); }
-		stream_fastq(in.p, in.n, std::max(1u, n_threads), std::max<uint64_t>(piece_bytes, 1u << 20), sink, host_alloc);
-		pack_sizes_from(stream_lens);
-		stream_lens = std::vector<uint32_t>();
+		const uint8_t* end = in.p + in.n;
+		const uint8_t* rb = range_begin == 0 ? in.p : range_begin >= in.n ? end : record_start(in.p + range_begin, end);
+		const uint8_t* re = range_end >= in.n ? end : record_start(in.p + range_end, end);
+		if (!rb || !re) throw StreamingFallback();
+		if (re < rb) re = rb;
+		total_bytes = static_cast<uint64_t>(re - rb);
+		if (re > rb) stream_fastq(rb, total_bytes, std::max(1u, n_threads), std::max<uint64_t>(piece_bytes, 1u << 20), sink, host_alloc);
+		else header_offsets.push_back(0);
+		pack_sizes_from(read_lens);
 	}
 
 	// n_threads 0: CLB_READER_THREADS or the hardware's count; at most one thread per min_piece_bytes of input
@@ -232,7 +241,7 @@ private:
 	}
 
 	// ---- streaming FASTQ parser ----
-	std::vector<uint32_t> stream_lens;                               // read lengths (the pack rule needs them), dropped after construction
+	std::vector<uint32_t> read_lens;                                 // streaming form: the read lengths (the pack rule and the multi-GPU exchange need them)
 	void pack_sizes_from(const std::vector<uint32_t>& lens)
 	{
 		uint64_t cur = 0; uint32_t k = 0;
@@ -301,7 +310,7 @@ private:
 		std::vector<Slot> slots(W);      // declared before the threads: destroyed after they are joined
 		for (uint64_t i = 0; i < W; ++i) slots[i].free_for = i;
 		std::mutex m; std::condition_variable cv; std::atomic<uint64_t> next_piece{0}; bool stop = false;
-		auto start_of = [&](uint64_t i) -> const uint8_t* { return i == 0 ? data : i >= n_pieces ? end : record_start(data + i * piece, end); };
+		auto start_of = [&](uint64_t i) -> const uint8_t* { return i == 0 ? data : i >= n_pieces ? end : record_start(data + i * piece, end); };      // a piece ends at the range's end at the latest: record_start never looks past `end`
 		auto worker = [&] {
 			for (;;) {
 				const uint64_t i = next_piece.fetch_add(1);
@@ -330,7 +339,7 @@ private:
 				if (n) sink(S.bases.get(), S.quals.get(), S.offsets.data(), n);
 				const uint64_t h0 = headers.size();
 				headers.append(S.hdr.data(), S.hdr.size());
-				for (uint32_t r = 0; r < n; ++r) { header_offsets.push_back(h0 + S.hdr_off[r + 1]); stream_lens.push_back(static_cast<uint32_t>(S.offsets[r + 1] - S.offsets[r])); }
+				for (uint32_t r = 0; r < n; ++r) { header_offsets.push_back(h0 + S.hdr_off[r + 1]); read_lens.push_back(static_cast<uint32_t>(S.offsets[r + 1] - S.offsets[r])); }
 				plus_id.append(S.plus.data(), S.plus.size());
 				n_reads_streamed += n; total_bases += S.n_bases; total_symb_header += S.symb;
 				{ std::lock_guard<std::mutex> lk(m); S.free_for = i + W; }
@@ -421,7 +430,8 @@ private:
 		const uint8_t* p = find_eol(from, end);                        // skip the line `from` falls into
 		if (p < end) ++p;
 		const uint8_t *b, *e;
-		for (int tries = 0; tries < 16 && next_line(p, end, b, e); ++tries) {
+		for (int tries = 0; tries < 16; ++tries) {
+			if (!next_line(p, end, b, e)) return end;                    // no record starts between `from` and the end of the data
 			if (*b != '@') continue;
 			const uint8_t* q = p; const uint8_t *b1, *e1, *b2, *e2;
 			if (next_line(q, end, b1, e1) && next_line(q, end, b2, e2) && *b2 == '+') return b;

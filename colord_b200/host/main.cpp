@@ -11,6 +11,7 @@
 #include <sstream>
 #include <thread>
 #include "compressor.h"
+#include "compressor_mgpu.h"
 #include "decompressor.h"
 
 using namespace clbhost;
@@ -25,6 +26,7 @@ static void usage()
 		"      -e,--edit-script-mult X  -r,--max-recurence-level N  --min-to-alt N  --min-mmer-frac X  --min-mmer-force-enc X\n"
 		"      --max-matches-mult X  --min-anchors N  -R,--reference-reads-mode all|sparse  -g,--sparse-range X  -x,--sparse-exponent X\n"
 		"      -i,--identifier org|main|none  -t,--threads N (accepted, unused)  -v,--verbose  --device N\n"
+		"      --gpus N   shard the input over N GPUs of this box (devices --device .. --device + N - 1; plain FASTQ, native containers)\n"
 		"      --compat | --native   streams of the archive: the reference's own (readable by `colord decompress`, every -q mode) or the\n"
 		"                            device's containers (org, *-avg, none); default: --compat up to --compat-max-mbases N (512) input Mbases\n"
 		"      -G,--reference-genome file  -s,--store-reference\n"
@@ -47,7 +49,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	CCompressorParams p = defaultParams(dataSourceFromCommand(cmd), compressionPriorityFromString(pri));
 	p.nThreads = std::max(std::thread::hardware_concurrency(), 1u);          // arg_parse.cpp:105
 	std::vector<std::string> pos;
-	bool qual_set = false; std::vector<uint32_t> fwd_user;
+	bool qual_set = false; std::vector<uint32_t> fwd_user; uint32_t n_gpus = 1;
 	for (int i = 2; i < argc; ++i) {
 		const std::string a = argv[i];
 		auto need = [&]() -> std::string { if (i + 1 >= argc) throw std::invalid_argument("option " + a + " needs a value"); return argv[++i]; };
@@ -79,6 +81,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 		else if (a == "-s" || a == "--store-reference") p.storeRefGenome = true;
 		else if (a == "-v" || a == "--verbose") p.verbose = true;
 		else if (a == "--device") p.device = std::stoi(need());
+		else if (a == "--gpus") n_gpus = static_cast<uint32_t>(std::stoul(need()));
 		else if (a == "--compat") p.streamFormat = StreamFormat::Compat;
 		else if (a == "--native") p.streamFormat = StreamFormat::Native;
 		else if (a == "--compat-max-mbases") p.compat_max_bases = std::stoull(need()) << 20;
@@ -90,7 +93,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	if (qual_set) defaultQualityThresholds(p.qualityComprMode, p.qualityFwdThresholds, p.qualityRevThresholds);
 	if (!fwd_user.empty()) { const size_t want = p.qualityFwdThresholds.size(); if (fwd_user.size() < want) throw std::invalid_argument("too few quality thresholds for this mode"); fwd_user.resize(want); p.qualityFwdThresholds = fwd_user; }
 	CInfo info; info.full_command_line = full_cmd;
-	const CompressionReport r = runCompression(p, info);
+	const CompressionReport r = n_gpus > 1 ? runCompressionMultiGpu(p, info, n_gpus) : runCompression(p, info);
 	if (p.verbose) { std::cerr << "streams: " << (r.compat ? "compat (the reference's own)" : "native containers") << "\ninput: " << (r.streamed ? "streamed to the device in pieces" : "read whole") << ", " << r.reader_threads << " reader thread(s)\n"; for (const Phase& ph : r.phases) std::cerr << "  phase " << ph.name << ": " << ph.seconds << " s\n"; }
 	if (p.verbose) std::cerr << "k-mer length: " << r.kmerLen << "\nanchor length: " << r.anchorLen << "\nsparse mode range in reads: " << r.sparse_range << "\nreference reads: " << r.tot_ref_reads << "\n";
 	// compression.cpp:802-806

@@ -46,7 +46,7 @@ int main(int argc, char** argv)
 			const uint32_t n = static_cast<uint32_t>(std::strtoul(argv[3], nullptr, 10));
 			const auto decs = slurp(argv[4]);
 			dec::DnaDecoder D;
-			const dec::Reads R = D.decode(s.data(), s.size(), n, decs);
+			const dec::Reads R = D.decode(s.data(), s.size(), n, decs.data());
 			spit(argv[5], R.bases.data(), R.bases.size()); spit(argv[6], R.offsets.data(), 8 * R.offsets.size()); spit(argv[7], R.flags.data(), R.flags.size());
 			return 0;
 		}

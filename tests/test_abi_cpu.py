@@ -27,6 +27,19 @@ def test_exports_every_declared_symbol():
     assert set(names) == set(lib.EXPORTS)
 
 
+def test_mgpu_library_exports_every_declared_symbol():
+    """include/colord_b200_mgpu.h <-> libcolord_b200_mgpu.so (the NCCL exchanges of the multi-GPU path)"""
+    with open(os.path.join(ROOT, "include", "colord_b200_mgpu.h")) as f:
+        names = sorted(set(re.findall(r"\b(clb_group_[a-z0-9_]+)\s*\(", f.read())))
+    assert len(names) == 5
+    # read with nm, not loaded: the library brings the system's NCCL with it, and a process that imports torch afterwards would
+    # bind torch to that copy instead of its own
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "colord_b200", "libcolord_b200_mgpu.so")], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (clb_group_[a-z0-9_]+)", out))
+    assert exported == set(names)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

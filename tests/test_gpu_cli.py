@@ -241,6 +241,43 @@ def test_cli_reference_genome_mode(cli, tmp_path, fmt, store):
         assert open(ref_back, "rb").read() == open(fq, "rb").read()
 
 
+def _n_gpus():
+    try:
+        r = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True)
+        return sum(1 for l in r.stdout.splitlines() if l.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs on the box (gpurun --gpus 2)")
+@pytest.mark.parametrize("opts", [[], ["-q", "org", "-p", "balanced"], ["-R", "all", "-q", "none"]])
+def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts):
+    """--gpus 2: the input is sharded over two GPUs (NCCL exchanges of the k-mer counts and the reference reads in
+    libcolord_b200_mgpu.so), the archive holds one part per stream and GPU, and `decompress` gives the file back.  The DNA stream
+    must stay close to the single-GPU archive's (the shards see the same reference reads; only tables and pack cuts differ)."""
+    import colord_archive
+    fq = str(tmp_path / "in.fastq")
+    synth.generate_file(fq, "ont", 3000, 1_100_000, 8000, seed=12, workers=8)
+    one, two, back = str(tmp_path / "one.colord"), str(tmp_path / "two.colord"), str(tmp_path / "back")
+    r = subprocess.run([cli, "compress-ont", *opts, "--native", fq, one], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([cli, "compress-ont", *opts, "--gpus", "2", "-v", fq, two], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    parts1, parts2 = colord_archive.read_parts(one), colord_archive.read_parts(two)
+    assert len(parts2["dna-b200"]) == 2 and len(parts1["dna-b200"]) == 1
+    assert sum(md for md, _ in parts2["dna-b200"]) == parts1["dna-b200"][0][0]
+    d1, d2 = len(parts1["dna-b200"][0][1]), sum(len(b) for _, b in parts2["dna-b200"])
+    assert d2 < 1.03 * d1, (d1, d2)
+    r = subprocess.run([cli, "decompress", two, back], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if "org" in opts:
+        assert subprocess.run(["cmp", "-s", fq, back]).returncode == 0
+    else:      # lossy / no qualities: bases and headers must be the input's, the qualities the single-GPU archive's
+        back1 = str(tmp_path / "back1")
+        assert subprocess.run([cli, "decompress", one, back1], capture_output=True).returncode == 0
+        assert subprocess.run(["cmp", "-s", back1, back]).returncode == 0
+
+
 def test_cli_refusals(cli, tmp_path):
     """Errors end in exit code 1 with a message, as in the reference's CLI (arg_parse.cpp:820-902, in_reads.cpp)."""
     bad = str(tmp_path / "bad.fastq")

@@ -325,7 +325,7 @@ def test_api_surface_on_device_made_archives(tmp_path):
     prints the records of every fixture archive exactly as `decompress` writes them, and the Info block of the reference's format."""
     import hashlib
     exe = str(tmp_path / "api_example")
-    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "host_api_example.cpp")], check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "host_api_example.cpp"), "-lz"], check=True)
     exp = json.load(open(os.path.join(B200, "expected.json")))
     for case, e in exp.items():
         r = subprocess.run([exe, os.path.join(B200, case + ".colord")], capture_output=True)
@@ -337,8 +337,11 @@ def test_api_surface_on_device_made_archives(tmp_path):
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_default.colord")], capture_output=True, text=True)
     # an archive of the unmodified reference (6 reads of its ONT test file) is read through the same surface (compat_decoder.h)
     assert r.returncode == 0 and "colord archive version: 1.2.1" in r.stderr and r.stdout.count("\n") == 24, r.stderr
+    # ... also one that carries its reference genome; one that does not asks for the genome (the API's second constructor)
     r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_genome_stored.colord")], capture_output=True, text=True)
-    assert r.returncode == 1 and "reference-genome archives are not available" in r.stderr
+    assert r.returncode == 0 and r.stdout.count("\n") == 24, r.stderr
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "archives", "ont_genome_checksum.colord")], capture_output=True, text=True)
+    assert r.returncode == 1 and "reference genome is required" in r.stderr
 
 
 @pytest.mark.parametrize("variant", ["plain", "crlf", "blank_lines", "plus_header", "tricky_quals", "gzip"])
