@@ -135,7 +135,10 @@ struct Aligner {
 	uint8_t* scratch;       // this task's scratch
 	AlignScratch lay;
 
-	__device__ __forceinline__ void gsync() const { if (GROUP > 1) __syncwarp(gmask); }
+	// the lanes of the group as a warp mask; for a whole-warp group a literal, so that the compiler drops the convergence checks of
+	// a run-time mask (MATCH.ANY / VOTEU / BRA.DIV around every shuffle)
+	__device__ __forceinline__ uint32_t mask() const { return GROUP == 32 ? 0xffffffffu : gmask; }
+	__device__ __forceinline__ void gsync() const { if (GROUP > 1) __syncwarp(mask()); }
 
 	// Forward sweep of rows[0..Q) x cols[0..T).  hist_pv / hist_ph (may be null) receive Pv / Ph of block b, column c at
 	// [b * hist_stride + c].  lastrow (int32[T]) receives D(Q-1, c) if non-null.
@@ -186,8 +189,8 @@ struct Aligner {
 					const int idx = s + GROUP + (int)gl;
 					cw_next = idx < T ? (int)carry[idx] : 0;
 				}
-				int hin = GROUP > 1 ? __shfl_up_sync(gmask, hout, 1, GROUP) : 0;
-				const int cin = (GROUP > 1 && strip > 0) ? __shfl_sync(gmask, cw, s & (GROUP - 1), GROUP) : 0;
+				int hin = GROUP > 1 ? __shfl_up_sync(mask(), hout, 1, GROUP) : 0;
+				const int cin = (GROUP > 1 && strip > 0) ? __shfl_sync(mask(), cw, s & (GROUP - 1), GROUP) : 0;
 				const int c = s - (int)gl;
 				if (act && c >= 0 && c < T) {
 					if (gl == 0) hin = strip == 0 ? 1 : (GROUP > 1 ? cin : (int)carry[c]);
@@ -209,7 +212,7 @@ struct Aligner {
 		// broadcast the final score from the lane that owns the last block
 		if (GROUP > 1) {
 			const int owner = (B - 1) % GROUP;
-			final_score = __shfl_sync(gmask, final_score, owner, GROUP);
+			final_score = __shfl_sync(mask(), final_score, owner, GROUP);
 		}
 		return final_score;
 	}
@@ -234,7 +237,7 @@ struct Aligner {
 			}
 			const int src = wj - j;                       // lane holding column j
 			const int k = (int)gl - src;                  // this lane holds column j - k
-			const uint64_t pvj = GROUP > 1 ? __shfl_sync(gmask, wpv, src, GROUP) : wpv;
+			const uint64_t pvj = GROUP > 1 ? __shfl_sync(mask(), wpv, src, GROUP) : wpv;
 			int run; uint8_t op;
 			if ((pvj >> bit) & 1) {
 				// up: as long as the vertical delta stays +1 inside this block and column
@@ -243,11 +246,11 @@ struct Aligner {
 			} else {
 				const bool in = k >= 0 && j - k >= 0;
 				const bool left_k = in && !((wpv >> bit) & 1) && ((wph >> bit) & 1);
-				const uint32_t bl = ((__ballot_sync(gmask, left_k) >> gbase) & gall) >> src;
+				const uint32_t bl = ((__ballot_sync(mask(), left_k) >> gbase) & gall) >> src;
 				if (bl & 1) { run = ~bl ? __ffs((int)~bl) - 1 : 32; op = 2; J -= run; }     // left along row i
 				else {
 					const bool diag_k = in && bit - k >= 0 && !((wpv >> (bit - k)) & 1) && !((wph >> (bit - k)) & 1);
-					const uint32_t bd = ((__ballot_sync(gmask, diag_k) >> gbase) & gall) >> src;
+					const uint32_t bd = ((__ballot_sync(mask(), diag_k) >> gbase) & gall) >> src;
 					run = ~bd ? __ffs((int)~bd) - 1 : 32; op = 0; I -= run; J -= run;      // run >= 1: the cell itself is neither up nor left
 				}
 			}
@@ -330,7 +333,7 @@ struct Aligner {
 			// topmost y in 1..ql-1 with F[y] + R[ql-y] == bs, then y = 0, then y = ql   (edlib.cpp:1305-1338)
 			int y = 0x7fffffff;
 			for (int cand = 1 + (int)gl; cand <= ql - 1; cand += GROUP) if ((int)(F[cand] + R[ql - cand]) == bs) { y = cand; break; }
-			if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) y = min(y, __shfl_xor_sync(gmask, y, d, GROUP));
+			if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) y = min(y, __shfl_xor_sync(mask(), y, d, GROUP));
 			if (y == 0x7fffffff) { if ((int)(lw + R[ql]) == bs) y = 0; else y = ql; }
 			const int ls = y == 0 ? lw : (int)F[y], rs = y == ql ? rw : (int)R[ql - y];
 #ifdef CLB_ALIGN_TIMING
@@ -442,7 +445,7 @@ __device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint3
 	if (GROUP > 1) {
 #pragma unroll
 		for (int d = 1; d < GROUP; d <<= 1) {
-			const uint32_t a = __shfl_up_sync(A.gmask, pr, d, GROUP), b = __shfl_up_sync(A.gmask, pe, d, GROUP);
+			const uint32_t a = __shfl_up_sync(A.mask(), pr, d, GROUP), b = __shfl_up_sync(A.mask(), pe, d, GROUP);
 			if ((int)gl >= d) { pr += a; pe += b; }
 		}
 	}
@@ -479,7 +482,7 @@ __device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint3
 			if (b == 'D') ++r; else if (es_is_ins(b)) ++q; else { ++r; ++q; }
 		}
 	}
-	uint32_t next = __shfl_down_sync(A.gmask, cut, 1, GROUP);
+	uint32_t next = __shfl_down_sync(A.mask(), cut, 1, GROUP);
 	if (gl == GROUP - 1) next = n;
 	A.gsync();                                 // every cut is known before any lane reorders symbols
 	if (cut < next) refactor_range(ref, enc, out, cut, next, cut_r, cut_q);
@@ -555,7 +558,7 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		int best = 0x7fffffff, end = 0;
 		for (int c = (int)gl; c < (int)cut; c += GROUP) { const int v = lastrow[c]; if (v < best) { best = v; end = c; } }
 		if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) {
-			const int ob = __shfl_xor_sync(A.gmask, best, d, GROUP), oe = __shfl_xor_sync(A.gmask, end, d, GROUP);
+			const int ob = __shfl_xor_sync(A.mask(), best, d, GROUP), oe = __shfl_xor_sync(A.mask(), end, d, GROUP);
 			if (ob < best || (ob == best && oe < end)) { best = ob; end = oe; }
 		}
 		ref_end = (uint32_t)end;
