@@ -517,7 +517,7 @@ clb_status s1a_append(clb_ctx* c, const uint8_t* bases, const uint64_t* offsets,
 	const uint64_t w0 = pos0 >> 5;
 	const uint64_t hint_words = (c->prm.expected_bases + c->prm.expected_bases / 16) / 32 + 1024;
 	const uint64_t want_words = std::max(w0 + n_words, w0 == 0 ? hint_words : 0);
-	CLB_CUDA(c, c->pk.reserve(want_words + 2, s, true, w0));      // stage 2 reads windows across a word boundary: one word of slack
+	CLB_CUDA(c, c->pk.reserve(want_words + 8, s, true, w0));      // stage 2 reads windows across a word boundary and stages 16-byte aligned tiles: a few words of slack
 	CLB_CUDA(c, c->nmask.reserve(want_words, s, true, w0));
 	CLB_CUDA(c, c->smask.reserve(want_words, s, true, w0));
 	if (!context) {

@@ -35,6 +35,28 @@ CLB_D uint64_t window(const uint64_t* __restrict__ pk, uint64_t p, uint32_t m)
 	const uint64_t x = s ? ((hi << s) | (lo >> (64 - s))) : hi;
 	return x >> (64 - 2 * m);
 }
+// ---- TMA: the packed words of the read being encoded are staged in shared memory by one bulk copy (cp.async.bulk, completion on an
+// mbarrier): every hit of the position table re-reads the read's own m-mer to verify the key (tab_matches), a gather that otherwise
+// goes to L1 / L2 for every probe.  1-D bulk copies need 16-byte aligned addresses and sizes.
+constexpr uint32_t TILE_WORDS = 1024;           // 8 KB: reads up to 32 k bases
+CLB_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+CLB_D void tma_stage_words(uint64_t* s_dst, const uint64_t* g_src, uint32_t bytes, uint64_t* bar)
+{
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+		asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+			:: "r"(smem_u32(s_dst)), "l"(g_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+	}
+	uint32_t done = 0;
+	while (!done)
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(0u) : "memory");
+}
+
 CLB_D uint32_t mm_hash(uint64_t x)
 {
 	x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL;
@@ -51,6 +73,7 @@ struct MatchArgs {
 	uint8_t* arena; unsigned long long arena_cap; unsigned long long* cursor;     // in pair slots
 	SegInfo* seg; uint32_t* slot_dec;                 // per slot: 1 = too few distinct m-mers (no candidates)
 	const uint8_t* skip;                              // HiFi: per (slot, candidate) 1 = anchors already found from the shared k-mers
+	int tma;                                          // stage the read's packed words in shared memory by a bulk copy
 };
 
 struct MatchShared {
@@ -80,7 +103,7 @@ CLB_D void tab_matches(const uint32_t* tab, uint32_t mask, const uint64_t* __res
 
 template <bool EMIT>
 __device__ void scan_refs(const MatchArgs& a, MatchShared& sh, const uint32_t* tab, uint32_t tmask, const uint32_t* bloom, uint32_t bmask,
-	uint64_t estart, uint32_t n_cand)
+	const uint64_t* epk, uint64_t estart, uint32_t n_cand)
 {
 	const uint32_t m = a.P.m;
 	const uint64_t mmask = m == 32 ? ~0ULL : ((1ULL << (2 * m)) - 1);
@@ -110,13 +133,13 @@ __device__ void scan_refs(const MatchArgs& a, MatchShared& sh, const uint32_t* t
 					const unsigned long long b = sh.base[2 * j + o];
 					if (b == ~0ULL) continue;
 					uint64_t* out = reinterpret_cast<uint64_t*>(a.arena + b * PAIR_SLOT_BYTES);
-					tab_matches(tab, tmask, a.pk, estart, m, x, h, [&](uint32_t e) {
+					tab_matches(tab, tmask, epk, estart, m, x, h, [&](uint32_t e) {
 						const uint32_t idx = atomicAdd(&sh.fill[2 * j + o], 1u);
 						out[idx] = ((uint64_t)e << 32) | (uint64_t)(0xFFFFFFFFu - pos_o);
 					});
 				} else {
 					uint32_t cnt = 0;
-					tab_matches(tab, tmask, a.pk, estart, m, x, h, [&](uint32_t) { ++cnt; });
+					tab_matches(tab, tmask, epk, estart, m, x, h, [&](uint32_t) { ++cnt; });
 					if (cnt) { if (o) { ++hits_r; pairs_r += cnt; } else { ++hits_f; pairs_f += cnt; } }
 				}
 			}
@@ -134,15 +157,24 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	MatchShared& sh = *reinterpret_cast<MatchShared*>(smem_raw);
 	uint32_t* s_tab = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(MatchShared) + 15) & ~15ull));
 	uint32_t* s_bloom = s_tab + SMEM_TAB_CELLS;
+	uint64_t* s_pk = reinterpret_cast<uint64_t*>(s_bloom + SMEM_BLOOM_WORDS);      // TILE_WORDS + 2 words, then the mbarrier
+	uint64_t* s_bar = s_pk + TILE_WORDS + 2;
 
 	const uint32_t slot = blockIdx.x;
 	const uint32_t read = a.enc_list[slot];
 	const uint32_t c = a.P.c, m = a.P.m;
-	const uint64_t estart = a.rd_start[read]; const uint32_t elen = a.rd_len[read];
+	const uint64_t estart_g = a.rd_start[read]; const uint32_t elen = a.rd_len[read];
 	const uint32_t n_cand = min(a.cand_n[read], c);
 	SegInfo* seg = a.seg + (size_t)slot * c * 2;
 	for (uint32_t i = threadIdx.x; i < 2 * c; i += blockDim.x) seg[i] = SegInfo{0, 0, 0, 0, 0};
 	if (elen < m) { if (threadIdx.x == 0) a.slot_dec[slot] = 1; return; }          // no m-mers: 0 < frac * len -> refused
+	// the read's packed words [w0, w0 + n_w): w0 even (16-byte aligned source), one word behind the last base (window() reads two words)
+	const uint64_t w0 = (estart_g >> 5) & ~1ull;
+	const uint32_t n_w = (uint32_t)((((estart_g + elen - 1) >> 5) + 2 - w0 + 1) & ~1ull);
+	const bool staged = a.tma && n_w <= TILE_WORDS + 2;
+	if (staged) tma_stage_words(s_pk, a.pk + w0, n_w * 8, s_bar);
+	const uint64_t* epk = staged ? s_pk : a.pk;
+	const uint64_t estart = staged ? estart_g - 32 * w0 : estart_g;
 	const uint32_t n_mm = elen - m + 1;
 	uint32_t cap = 64; while (cap < 2 * n_mm) cap <<= 1;
 	uint32_t bbits = 1024; while (bbits < 16 * n_mm && bbits < (1u << 30)) bbits <<= 1;
@@ -169,9 +201,9 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	const uint32_t n_words = (n_mm + 31) / 32;
 	for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
 		const uint32_t p0 = w * 32, p1 = min(p0 + 32, n_mm);
-		uint64_t f = window(a.pk, estart + p0, m);
+		uint64_t f = window(epk, estart + p0, m);
 		for (uint32_t p = p0; p < p1; ++p) {
-			if (p > p0) f = ((f << 2) | base_at(a.pk, estart + p + m - 1)) & mmask;
+			if (p > p0) f = ((f << 2) | base_at(epk, estart + p + m - 1)) & mmask;
 			const uint32_t h = mm_hash(f);
 			const uint32_t bb = (h >> 7) & bmask;
 			atomicOr(&bloom[bb >> 5], 1u << (bb & 31));
@@ -184,11 +216,11 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	uint32_t uq = 0;
 	for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) {
 		const uint32_t p0 = w * 32, p1 = min(p0 + 32, n_mm);
-		uint64_t f = window(a.pk, estart + p0, m);
+		uint64_t f = window(epk, estart + p0, m);
 		for (uint32_t p = p0; p < p1; ++p) {
-			if (p > p0) f = ((f << 2) | base_at(a.pk, estart + p + m - 1)) & mmask;
+			if (p > p0) f = ((f << 2) | base_at(epk, estart + p + m - 1)) & mmask;
 			uint32_t mn = 0xFFFFFFFFu;
-			tab_matches(tab, tmask, a.pk, estart, m, f, mm_hash(f), [&](uint32_t e) { mn = min(mn, e); });
+			tab_matches(tab, tmask, epk, estart, m, f, mm_hash(f), [&](uint32_t e) { mn = min(mn, e); });
 			uq += mn == p;
 		}
 	}
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	__syncthreads();
 	if (sh.decision == 1) return;
 	// ---- count ----
-	scan_refs<false>(a, sh, tab, tmask, bloom, bmask, estart, n_cand);
+	scan_refs<false>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned long long total = 0;
@@ -230,7 +262,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	}
 	__syncthreads();
 	// ---- write the pairs ----
-	scan_refs<true>(a, sh, tab, tmask, bloom, bmask, estart, n_cand);
+	scan_refs<true>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand);
 }
 
 // ------------------------------------------------------------------------------------------------ HiFi: anchors from shared k-mers
@@ -585,7 +617,8 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		CLB_LAUNCH_CHECK(c, "k_kmer_anchors");
 		CLB_CUDA(c, cudaStreamSynchronize(s));          // the host vectors above were read by the copies
 	}
-	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS);
+	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS) + sizeof(uint64_t) * (TILE_WORDS + 2 + 2);
+	static const int tma_on = [] { const char* e = std::getenv("CLB_TMA"); return e ? std::atoi(e) : 0; }();
 	CLB_CUDA(c, cudaFuncSetAttribute(k_anchor_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// first guess of the arena: one pair per base of every read and candidate half-used; the kernel reports the exact need
 	uint64_t cap_pairs = std::max<uint64_t>(1u << 16, est_pairs * 2);
@@ -598,7 +631,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		a.pk = c->pk.p; a.rd_start = c->rd_start.p; a.rd_len = c->rd_len.p; a.enc_list = d_list; a.n_list = nb;
 		a.cand = c->cand; a.cand_n = c->cand_n; a.ref_to_read = d_ref_to_read; a.P = P;
 		a.tab_off = d_tab_off; a.g_tab = g_tab; a.bloom_off = d_bloom_off; a.g_bloom = g_bloom;
-		a.arena = arena.p; a.arena_cap = cap_pairs; a.cursor = d_cursor; a.seg = d_seg; a.slot_dec = d_slot_dec; a.skip = d_skip;
+		a.arena = arena.p; a.arena_cap = cap_pairs; a.cursor = d_cursor; a.seg = d_seg; a.slot_dec = d_slot_dec; a.skip = d_skip; a.tma = tma_on;
 		CLB_TIMED(c, K_ANCHORS, (k_anchor_match<<<nb, MATCH_THREADS, smem, s>>>(a)));
 		CLB_LAUNCH_CHECK(c, "k_anchor_match");
 		unsigned long long used = 0;
