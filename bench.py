@@ -37,6 +37,25 @@ NS = dict(k=24, modulo=12, min_count=4, max_count=80, max_candidates=5, sparse_g
 # stage 2 at the same preset (arg_parse.cpp:154 "memory": level 1) and the anchor length compression.cpp:57-94 picks for 25 Gbases
 NS_S2 = dict(anchor_len=22, min_part_len_alt=64, max_recurence=3, min_anchors=1, min_mmer_frac=0.5, min_mmer_force=0.9,
              max_matches_mult=10.0, es_cost_mult=1.0)
+# --config: the other BASELINE configurations that run through the same device path (presets of arg_parse.cpp:89-408,
+# k / anchor length by compression.cpp:41-93 for the configuration's size).  Each overrides the workload dictionaries above.
+CONFIGS = {
+    "NS": dict(gbases=25.0, cmd="compress-ont", cli=[], level=1, qual="4-avg", sparse=True, text="compress-ont default"),
+    "C3": dict(gbases=8.0, cmd="compress-ont", cli=["-p", "balanced"], level=2, qual="4-avg", sparse=True, text="compress-ont -p balanced (BASELINE config 3: 1 M ONT reads x 8 kb)",
+               ns=dict(k=23, modulo=9, min_count=3, max_count=100, max_candidates=8, sparse_g=2.0, genome_len=400_000_000), s2=dict(anchor_len=21, min_part_len_alt=48, max_recurence=5)),
+    "C4": dict(gbases=20.0, cmd="compress-pbraw", cli=["-q", "none", "-p", "ratio"], level=3, qual=None, sparse=False, text="compress-pbraw -q none -p ratio (BASELINE config 4: 2 M CLR subreads x 10 kb)",
+               ns=dict(k=24, modulo=8, min_count=2, max_count=120, max_candidates=10, mean_len=10000, genome_len=1_000_000_000, err=(0.02, 0.04, 0.07)), s2=dict(anchor_len=22, min_part_len_alt=48, max_recurence=6)),
+}
+CFG = dict(CONFIGS["NS"], name="NS")
+
+
+def apply_config(name):
+    c = CONFIGS[name]
+    NS.update(c.get("ns", {}))
+    NS_S2.update(c.get("s2", {}))
+    CFG.clear(); CFG.update(c, name=name)
+
+
 HEADER_BYTES = 46 + 6          # "@read_<i> ch=<n> start_time=<ISO>\n" + "\n+\n" + two line ends
 
 
@@ -157,14 +176,14 @@ SIZE_KEYS = (("DNA", "dna"), ("Quality", "quality"), ("Header", "header"))
 def sample_fastq(path, n_reads):
     """n_reads synthetic ONT reads of the north-star workload (same error / quality / header model, 20.8x coverage) as a FASTQ file"""
     from colord_b200 import synth
-    nbytes, nbases = synth.generate_file(path, "ont", n_reads, max(100_000, int(n_reads * NS["mean_len"] / 20.8)), NS["mean_len"], seed=1)
+    nbytes, nbases = synth.generate_file(path, "clr" if CFG["cmd"] == "compress-pbraw" else "ont", n_reads, max(100_000, int(n_reads * NS["mean_len"] / 20.8)), NS["mean_len"], seed=1)
     return nbytes, nbases
 
 
 def run_cli(exe, fastq, out, extra=()):
     """One `compress-ont` run at the north star's preset (k / anchor length forced to what a 50 GB input selects).  -> (wall s, stream sizes)"""
     import re
-    cmd = [exe, "compress-ont", "-k", str(NS["k"]), "-a", str(NS_S2["anchor_len"]), *extra, fastq, out]
+    cmd = [exe, CFG["cmd"], *CFG["cli"], "-k", str(NS["k"]), "-a", str(NS_S2["anchor_len"]), *extra, fastq, out]
     t0 = time.perf_counter()
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=3600, cwd=os.path.dirname(out))
     dt = time.perf_counter() - t0
@@ -206,11 +225,11 @@ def cpu_baseline(sample_reads=125000, with_ratio_check=True):
         dt, ref_sizes = run_cli(REF_BIN, fq, os.path.join(tmp, "ref.colord"), ["-t", str(cores)])
         ref_bytes = os.path.getsize(os.path.join(tmp, "ref.colord"))
         base = {"value": nbytes / dt / 1e6, "unit": "MB/s", "cores": cores, "kind": "reference", "wall_s": dt,
-                "sample": f"{sample_reads} synthetic ONT reads of the workload, {nbases} bases, {nbytes} FASTQ bytes; unmodified `colord compress-ont -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}`, "
+                "sample": f"{sample_reads} synthetic ONT reads of the workload, {nbases} bases, {nbytes} FASTQ bytes; unmodified `colord {CFG['cmd']} {' '.join(CFG['cli'])} -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}`, "
                           "wall time process start -> exit, one run"}
         check = None
         if with_ratio_check and os.path.exists(OUR_CLI):
-            check = {"config": f"compress-ont default on the same {nbytes}-byte FASTQ file", "ref_bytes": ref_bytes, "ref_streams": ref_sizes}
+            check = {"config": f"{CFG['text']} on the same {nbytes}-byte FASTQ file", "ref_bytes": ref_bytes, "ref_streams": ref_sizes}
             for fmt in ("native", "compat"):
                 try:
                     t, sizes = run_cli(OUR_CLI, fq, os.path.join(tmp, fmt + ".colord"), ["--" + fmt, "-v"])
@@ -245,7 +264,7 @@ def main_reference(args):
     ms = 1e3 * sum(times) / len(times)
     v = nbytes / (ms / 1e3) / 1e6
     sample = (f"{n_reads} synthetic ONT reads of the workload / {nbases} bases / {nbytes} FASTQ bytes per step (bounded sample); the unmodified reference CLI "
-              f"`colord compress-ont -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}` (stock code path, file in -> archive out, wall time process start -> exit)"
+              f"`colord {CFG['cmd']} {' '.join(CFG['cli'])} -k {NS['k']} -a {NS_S2['anchor_len']} -t {cores}` (stock code path, file in -> archive out, wall time process start -> exit)"
               if kind == "reference" else "oracle/stage1.c scalar port, stage 1 only (the reference binary is not built here)")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args), "value": v, "unit": "MB/s",
@@ -259,7 +278,7 @@ def main_reference(args):
 
 
 def metric_name(args):
-    return "input MB/s, compress-ont default, " + {
+    return f"input MB/s, {CFG['text']}, " + {
         "12qdh": "stages 1+2+3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, DNA-tuple, 4-avg quality and header entropy coders)",
         "12qd": "stages 1+2+3 without headers (k-mer filter, similarity graph, anchors + edit scripts -> tuples, DNA-tuple and 4-avg quality entropy coders)",
         "12q": "stages 1+2 + quality stream of stage 3 (k-mer filter, similarity graph, anchors + edit scripts -> tuples, 4-avg quality coder)",
@@ -268,9 +287,9 @@ def metric_name(args):
 
 
 def workload_config(args, n_reads):
-    return {"workload": f"compress-ont default (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} sparse g=1), "
-                        f"synthetic ONT FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read 8 kb, genome {NS['genome_len'] * args.gbases / 25.0 / 1e9:.3g} Gb = 20.8x, 10% errors)",
-            "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl1)" % NS_S2["anchor_len"]
+    return {"workload": f"{CFG['text']} (k{NS['k']} f{NS['modulo']} L{NS['min_count']} H{NS['max_count']} c{NS['max_candidates']} {'sparse g=%g' % NS['sparse_g'] if CFG['sparse'] else 'all reads are references'}), "
+                        f"synthetic FASTQ ~{2 * args.gbases:.0f} GB ({args.gbases:g} Gbases, mean read {NS['mean_len'] / 1000:g} kb, genome {NS['genome_len'] * args.gbases / CFG['gbases'] / 1e9:.3g} Gb, {100 * sum(NS['err']):.0f}% errors)",
+            "stages": ("stages 1+2 (1a count+filter, 1b accepted k-mers + similarity graph, 2 anchors/edit scripts/decisions/CompactES tuples; a%d lvl%d)" % (NS_S2["anchor_len"], CFG["level"])
                        + {"12qdh": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) + header stream in native containers",
                           "12qd": "; stage 3: DNA-tuple stream (level 1) + quality stream (4-avg, thresholds 7 14 26) in native containers; header coder not on device yet",
                           "12q": "; stage 3: quality stream (4-avg, thresholds 7 14 26) only", "12": "; stage 3 not included"}[args.stages])
@@ -284,13 +303,18 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--gbases", type=float, default=25.0, help="workload size in Gbases (north star: 25 = 50 GB FASTQ)")
+    ap.add_argument("--config", default="NS", choices=sorted(CONFIGS), help="workload: the north star (default) or BASELINE configuration 3 / 4 at its own preset and size")
+    ap.add_argument("--gbases", type=float, default=None, help="workload size in Gbases (default: the configuration's own — north star 25 = 50 GB FASTQ, C3 8, C4 20)")
     ap.add_argument("--stages", default="12qdh", choices=["1", "12", "12q", "12qd", "12qdh"], help="hot-path stages inside a step (both arms); q / d / h = quality / DNA-tuple / header stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--side-streams", action="store_true", help="code the quality / header streams in a second host thread beside stage 2 instead of after it "
                     "(measured on B200, 25 Gbases: 12.5-13.3 s per step against 11.8-12.0 s serial - the issue-bound quality kernels slow the latency-bound alignment down)")
     args = ap.parse_args()
+    apply_config(args.config)
+    ref_gbases = CFG["gbases"]
+    if args.gbases is None:
+        args.gbases = ref_gbases
     if args.impl == "reference":
         return main_reference(args)
 
@@ -315,13 +339,13 @@ def main():
     n_reads_total = int(args.gbases * 1e9 / p["mean_len"])
     lo, hi = rank * n_reads_total // world, (rank + 1) * n_reads_total // world
     # reduced runs (--gbases < 25) keep the north star's 20.8x coverage by shrinking the genome with the workload
-    genome_len = max(100_000, int(p["genome_len"] * args.gbases / 25.0))
+    genome_len = max(100_000, int(p["genome_len"] * args.gbases / ref_gbases))
     genome = make_genome(torch, device, genome_len, seed=1234)
     bases, offsets = gen_reads(torch, device, genome, lo, hi, seed=99)
     del genome
     torch.cuda.empty_cache()
     quals = None
-    if args.stages in ("12q", "12qd", "12qdh"):      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
+    if args.stages in ("12q", "12qd", "12qdh") and CFG["qual"]:      # phred ~ clip(N(12, 5), 1, 40) + 33, generated in slices
         quals = torch.empty(bases.numel(), dtype=torch.uint8, device=device)
         gq = torch.Generator(device=device)
         gq.manual_seed(4242 + rank)
@@ -388,7 +412,7 @@ def main():
             stats = exchange_counts_and_finalize(ctx, device, n_local)
         phase("finalize")
         rng = sparse_range(stats, p)
-        sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi]
+        sampled = lib.sampler(rng, p["sparse_exponent"], 0, n_reads_all)[lo:hi] if CFG["sparse"] else np.ones(hi - lo, np.uint8)
         if world > 1:      # global reference-read set: the reference reads of the shards before mine become my context reads
             with torch.cuda.stream(stream):
                 exchange_reference_reads(ctx, device, sampled, lens_host)
@@ -402,10 +426,12 @@ def main():
                     ctx.hdr_encode(bytes_=hdr_dev.data_ptr(), offsets=hdr_off_dev.data_ptr(), n=n_local, on_device=True)
                 else:
                     ctx.hdr_encode(bytes_=host_hdr[0], offsets=host_hdr[1])
+            if not CFG["qual"]:
+                return
             if host_quals is None:
-                ctx.qual_encode(4, [7, 14, 26], 1, quals.data_ptr(), off_u64.data_ptr(), on_device=True)
+                ctx.qual_encode(4, [7, 14, 26], CFG["level"], quals.data_ptr(), off_u64.data_ptr(), on_device=True)
             else:
-                ctx.qual_encode(4, [7, 14, 26], 1, host_quals, host_offsets)
+                ctx.qual_encode(4, [7, 14, 26], CFG["level"], host_quals, host_offsets)
         side, side_err = None, []
         if args.stages in ("12q", "12qd", "12qdh") and args.side_streams:
             def side_main():
@@ -423,7 +449,7 @@ def main():
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
             phase("encode")
             if args.stages in ("12qd", "12qdh"):
-                ctx.dna_encode(1)
+                ctx.dna_encode(CFG["level"])
             phase("dna")
             if side is not None:
                 side.join()
@@ -434,7 +460,7 @@ def main():
             phase("hdr+qual")
             if readback:           # what leaves the device: the finished streams (the tuples too while the DNA coder is not included)
                 if args.stages == "12qdh":
-                    out = (read_stream(ctx, "dna"), read_stream(ctx, "qual"), read_stream(ctx, "hdr"))
+                    out = (read_stream(ctx, "dna"),) + ((read_stream(ctx, "qual"),) if CFG["qual"] else ()) + (read_stream(ctx, "hdr"),)
                 elif args.stages == "12qd":
                     out = (read_stream(ctx, "dna"), read_stream(ctx, "qual"))
                 else:
