@@ -618,7 +618,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		CLB_CUDA(c, cudaStreamSynchronize(s));          // the host vectors above were read by the copies
 	}
 	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS) + sizeof(uint64_t) * (TILE_WORDS + 2 + 2);
-	static const int tma_on = [] { const char* e = std::getenv("CLB_TMA"); return e ? std::atoi(e) : 0; }();
+	static const int tma_on = [] { const char* e = std::getenv("CLB_TMA"); return e ? std::atoi(e) : 1; }();      // on a B200: k_anchors 1 283 ms per 25 Gbases with the bulk-copy stage, 1 425 ms without (profiles/r02h_*)
 	CLB_CUDA(c, cudaFuncSetAttribute(k_anchor_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// first guess of the arena: one pair per base of every read and candidate half-used; the kernel reports the exact need
 	uint64_t cap_pairs = std::max<uint64_t>(1u << 16, est_pairs * 2);

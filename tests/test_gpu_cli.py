@@ -250,8 +250,9 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs on the box (gpurun --gpus 2)")
+@pytest.mark.parametrize("n_gpus", sorted({2, max(2, _n_gpus())}))
 @pytest.mark.parametrize("opts", [[], ["-q", "org", "-p", "balanced"], ["-R", "all", "-q", "none"]])
-def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts):
+def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts, n_gpus):
     """--gpus 2: the input is sharded over two GPUs (NCCL exchanges of the k-mer counts and the reference reads in
     libcolord_b200_mgpu.so), the archive holds one part per stream and GPU, and `decompress` gives the file back.  The DNA stream
     must stay close to the single-GPU archive's (the shards see the same reference reads; only tables and pack cuts differ)."""
@@ -261,13 +262,13 @@ def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts):
     one, two, back = str(tmp_path / "one.colord"), str(tmp_path / "two.colord"), str(tmp_path / "back")
     r = subprocess.run([cli, "compress-ont", *opts, "--native", fq, one], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    r = subprocess.run([cli, "compress-ont", *opts, "--gpus", "2", "-v", fq, two], capture_output=True, text=True)
+    r = subprocess.run([cli, "compress-ont", *opts, "--gpus", str(n_gpus), "-v", fq, two], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     parts1, parts2 = colord_archive.read_parts(one), colord_archive.read_parts(two)
-    assert len(parts2["dna-b200"]) == 2 and len(parts1["dna-b200"]) == 1
+    assert len(parts2["dna-b200"]) == n_gpus and len(parts1["dna-b200"]) == 1
     assert sum(md for md, _ in parts2["dna-b200"]) == parts1["dna-b200"][0][0]
     d1, d2 = len(parts1["dna-b200"][0][1]), sum(len(b) for _, b in parts2["dna-b200"])
-    assert d2 < 1.03 * d1, (d1, d2)
+    assert d2 < (1.03 if n_gpus == 2 else 1.10) * d1, (d1, d2)      # 24 Mbases over N shards: every shard pays its own tables
     r = subprocess.run([cli, "decompress", two, back], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     if "org" in opts:
