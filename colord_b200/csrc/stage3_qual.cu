@@ -9,9 +9,12 @@
 // What is replaced: the reference codes the symbols with ONE adaptive range coder whose models persist over the whole file
 // (entr_qual.h:100-126) — a serial chain.  Here the models are static: pass 1 counts (context, symbol) pairs of all reads with
 // atomics, the host turns the 2^17..2^19-entry count table into 12-bit frequency tables (contexts seen fewer than 32 times
-// share a fallback table; metadata-sized work), pass 2 codes every read pack with 64 interleaved rANS lanes (31-bit state,
-// 16-bit renormalisation), one thread per lane, thousands of lanes in lockstep.  Container layout and its CPU twin + decoder:
-// oracle/stage3_qual.c (the bytes must be identical).
+// share a fallback table; metadata-sized work), pass 2 codes every read pack as 4 streams of 32-way INTERLEAVED rANS (31-bit
+// states, 16-bit renormalisation): one warp per stream, symbol k of a read belongs to state k mod 32 = lane k mod 32, so a warp
+// codes 32 symbols per step in lockstep; the lanes that renormalise find their place in the word stream with one ballot + popc
+// (container "QB02").  Container layout and its CPU twin + decoder: oracle/stage3_qual.c (the bytes must be identical).
+// Round 1's "QB01" (64 single-state lanes per pack, the one state carried by all 32 threads of a warp: ~19 warp instructions per
+// symbol, 0.9 s of k_q_encode per 25 Gbases) is still read by the decoders.
 #include "ctx.h"
 #include <algorithm>
 #include <cstring>
@@ -22,7 +25,7 @@
 
 namespace clb {
 
-constexpr uint32_t QB_LANES = 64, QB_PROB_BITS = 12, QB_M = 1u << QB_PROB_BITS, QB_L = 1u << 15, QB_MIN_CTX = 32;
+constexpr uint32_t QB_LANES = 4 /* streams per pack */, QB_STATES = 32, QB_PROB_BITS = 12, QB_M = 1u << QB_PROB_BITS, QB_L = 1u << 15, QB_MIN_CTX = 32;
 
 struct QP { uint32_t nb, level, bps, cb, cbits; uint32_t thr[4]; };
 
@@ -145,28 +148,18 @@ CLB_HD uint4 rans_symbol(uint32_t start, uint32_t freq)
 	s.w = freq;
 	return s;
 }
-// one coding step with the symbol held by thread k of the warp; the state is the same in all threads, thread 0 stores
-CLB_D uint32_t rans_step(uint32_t x, const uint4& fc, int k, uint16_t* w, uint32_t& nw, uint32_t t)
-{
-	const unsigned FULL = 0xffffffffu;
-	const uint32_t rcp = __shfl_sync(FULL, fc.x, k), bias = __shfl_sync(FULL, fc.y, k), cs = __shfl_sync(FULL, fc.z, k), f = __shfl_sync(FULL, fc.w, k);
-	if (x >= (f << 19)) { if (t == 0) w[nw] = (uint16_t)x; ++nw; x >>= 16; }       // f <= 2^12: no overflow
-	const uint32_t q = __umulhi(x, rcp) >> (cs >> 16);
-	return x + bias + q * (cs & 0xffffu);
-}
-
 struct QEnc {
 	const uint32_t* pack_first; uint32_t pack_lo, n_packs;     // packs of this chunk
 	const uint64_t* lane_off;                                   // first temp word of every lane of the chunk
 	uint16_t* tmp; uint32_t* lane_words; uint32_t* lane_state;
 };
 
-// (Measured alternative, round 1: one THREAD per stream with a rolled context — 32 symbols per pass through the loop body
-// instead of 32 shuffle-broadcast steps — took 1.77 s instead of 0.90 s at 25 Gbases: with the temp limiting a launch to
-// 2^31 symbols there are only 33 k streams in flight, far too few threads to hide the table-lookup latency of the chains.)
-// pass 2: one WARP per (pack, lane) stream; its reads last to first, symbols last to first (rANS decodes in the opposite
-// order).  The 32 threads fetch the table entries of 32 consecutive symbols side by side (coalesced quality bytes, one
-// packed word of bases), then the rANS state — the same in every thread — takes the 32 dependent steps; thread 0 stores.
+// pass 2: one WARP per (pack, stream); stream s of a pack takes its reads s, s + 4, ...  Reads last to first, symbols last to first
+// (rANS decodes in the opposite order).  The symbols of a read are its 2 x n_bins mean bytes, then one bin symbol per base; symbol k
+// belongs to state k mod 32.  A step codes the 32 symbols k = 32 g + lane: every lane fetches its own table entry (quality bytes and
+// packed bases are read side by side), renormalises (the 16-bit words of a step go out in ascending lane order in DECODING order,
+// i.e. descending here: position = number of renormalising lanes above mine, one ballot + popc) and takes its rANS step with a
+// reciprocal multiply.
 __global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 {
 	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, t = threadIdx.x & 31;
@@ -177,35 +170,40 @@ __global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 	uint16_t* w = e.tmp + e.lane_off[li]; uint32_t nw = 0;
 	uint32_t x = QB_L;
 	const QP& P = a.P;
+	const uint32_t above = ~((2u << t) - 1u);                // lanes above mine (t = 31: none)
 	if (r0 + l < r1) {
 		const uint32_t last = r0 + l + ((r1 - 1 - (r0 + l)) / QB_LANES) * QB_LANES;
 		for (long long r = last; r >= (long long)(r0 + l); r -= QB_LANES) {
 			const uint32_t n = a.rd_len[r]; const uint64_t rs = a.rd_start[r];
 			const uint8_t* q = a.quals + a.qoff[r];
 			const uint8_t* fl = a.flags ? a.flags + a.qoff[r] : nullptr;
-			for (long long hi = n; hi > 0; hi -= 32) {
-				const long long j = hi - 1 - t;                  // thread 0 holds the last symbol of the chunk = the first to be coded
+			const uint32_t ns = 2 * P.nb, T = ns + n;
+			for (long long g = (long long)((T - 1) >> 5); g >= 0; --g) {
+				const uint32_t k = (uint32_t)(g << 5) + t;
+				const bool valid = k < T;
 				uint4 fc = make_uint4(0, 0, 0, 1);
-				if (j >= 0) fc = a.tab[(size_t)q_context(a, rs, n, q, fl, (uint32_t)j) * P.nb + q_bin(P, q[j] - 33u)];
-				const int cnt = (int)min((long long)32, hi);
-				for (int k = 0; k < cnt; ++k) x = rans_step(x, fc, k, w, nw, t);
-			}
-			{	// the read's bin means come first in decoding order: bin 0 high byte, low byte, bin 1 ... -> coded last, backwards
-				const uint32_t ns = 2 * P.nb;
-				uint4 fc = make_uint4(0, 0, 0, 1);
-				if (t < ns) {
-					const uint32_t m = ns - 1 - t, b = m >> 1;
-					const uint32_t v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
-					fc = (m & 1) ? rans_symbol(a2 * (QB_M >> 8), QB_M >> 8) : a.mtab[b * 128 + a1];
+				if (valid) {
+					if (k < ns) {                                    // bin k / 2: high byte of mean * 256 under the bin's table, then the low byte (uniform)
+						const uint32_t b = k >> 1, v = a.avg16[(size_t)r * 5 + b], a1 = (v >> 8) & 127, a2 = v & 0xff;
+						fc = (k & 1) ? rans_symbol(a2 * (QB_M >> 8), QB_M >> 8) : a.mtab[b * 128 + a1];
+					} else {
+						const uint32_t j = k - ns;
+						fc = a.tab[(size_t)q_context(a, rs, n, q, fl, j) * P.nb + q_bin(P, q[j] - 33u)];
+					}
 				}
-				for (uint32_t k = 0; k < ns; ++k) x = rans_step(x, fc, (int)k, w, nw, t);
+				const bool emit = valid && x >= (fc.w << 19);       // f <= 2^12: no overflow
+				const uint32_t m = __ballot_sync(FULL, emit);
+				if (emit) { w[nw + __popc(m & above)] = (uint16_t)x; x >>= 16; }
+				nw += __popc(m);
+				if (valid) { const uint32_t qq = __umulhi(x, fc.x) >> (fc.z >> 16); x = x + fc.y + qq * (fc.z & 0xffffu); }
 			}
 		}
 	}
-	if (t == 0) { e.lane_words[li] = nw; e.lane_state[li] = x; }
+	if (t == 0) e.lane_words[li] = nw;
+	e.lane_state[(size_t)li * QB_STATES + t] = x;
 }
 
-// lane streams into the final container: state, then the words in decoding order (last written first); one warp per lane
+// streams into the final container: the 32 states, then the words in decoding order (last written first); one warp per stream
 __global__ void __launch_bounds__(128) k_q_gather(QEnc e, const uint64_t* __restrict__ dst_off, const uint64_t* __restrict__ pack_hdr_off, uint8_t* __restrict__ out)
 {
 	const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -213,17 +211,19 @@ __global__ void __launch_bounds__(128) k_q_gather(QEnc e, const uint64_t* __rest
 	const uint32_t nw = e.lane_words[li];
 	uint8_t* d = out + dst_off[li];
 	const uint16_t* w = e.tmp + e.lane_off[li];
-	if (lane == 0) {
-		const uint32_t x = e.lane_state[li];
-		d[0] = (uint8_t)x; d[1] = (uint8_t)(x >> 8); d[2] = (uint8_t)(x >> 16); d[3] = (uint8_t)(x >> 24);
-		// size field in the pack header, and the pack's read count
+	{
+		const uint32_t x = e.lane_state[(size_t)li * QB_STATES + lane];
+		uint8_t* ds = d + 4 * lane;
+		ds[0] = (uint8_t)x; ds[1] = (uint8_t)(x >> 8); ds[2] = (uint8_t)(x >> 16); ds[3] = (uint8_t)(x >> 24);
+	}
+	if (lane == 0) {      // size field in the pack header, and the pack's read count
 		const uint32_t p = li / QB_LANES, l = li % QB_LANES;
 		uint8_t* h = out + pack_hdr_off[p];
-		const uint32_t bytes = 4 + 2 * nw;
+		const uint32_t bytes = 4 * QB_STATES + 2 * nw;
 		h[4 + 4 * l] = (uint8_t)bytes; h[5 + 4 * l] = (uint8_t)(bytes >> 8); h[6 + 4 * l] = (uint8_t)(bytes >> 16); h[7 + 4 * l] = (uint8_t)(bytes >> 24);
 		if (l == 0) { const uint32_t np = e.pack_first[e.pack_lo + p + 1] - e.pack_first[e.pack_lo + p]; h[0] = (uint8_t)np; h[1] = (uint8_t)(np >> 8); h[2] = (uint8_t)(np >> 16); h[3] = (uint8_t)(np >> 24); }
 	}
-	for (uint32_t k = lane; k < nw; k += 32) { const uint16_t v = w[nw - 1 - k]; d[4 + 2 * k] = (uint8_t)v; d[5 + 2 * k] = (uint8_t)(v >> 8); }
+	for (uint32_t k = lane; k < nw; k += 32) { const uint16_t v = w[nw - 1 - k]; d[4 * QB_STATES + 2 * k] = (uint8_t)v; d[4 * QB_STATES + 1 + 2 * k] = (uint8_t)(v >> 8); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -323,7 +323,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	}
 	for (uint32_t b = 0; b < nb; ++b) { normalise(&mh[b * 128], 128, &mf[b * 128]); uint32_t acc = 0; for (uint32_t k = 0; k < 128; ++k) { mtab[b * 128 + k] = mf[b * 128 + k] ? rans_symbol(acc, mf[b * 128 + k]) : make_uint4(0, 0, 0, 1); acc += mf[b * 128 + k]; } }
 	std::vector<uint8_t> hdr;
-	hdr.insert(hdr.end(), {'Q', 'B', '0', '1'}); put(hdr, nb); put(hdr, P.level); for (int i = 0; i < 4; ++i) put(hdr, P.thr[i]); put(hdr, (uint64_t)n); put(hdr, np); put(hdr, P.cbits);
+	hdr.insert(hdr.end(), {'Q', 'B', '0', '2'}); put(hdr, nb); put(hdr, P.level); for (int i = 0; i < 4; ++i) put(hdr, P.thr[i]); put(hdr, (uint64_t)n); put(hdr, np); put(hdr, P.cbits);
 	for (uint32_t i = 0; i < nb * 128; ++i) put(hdr, mf[i]);
 	for (uint32_t x = 0; x < n_fb; ++x) for (uint32_t k = 0; k + 1 < nb; ++k) put(hdr, fbf[(size_t)x * nb + k]);
 	{
@@ -344,7 +344,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	uint32_t* d_pack_first = nullptr;
 	CLB_CUDA(c, dalloc((void**)&d_pack_first, sizeof(uint32_t) * (np + 1)));
 	CLB_CUDA(c, cudaMemcpyAsync(d_pack_first, pack_first.data(), sizeof(uint32_t) * (np + 1), cudaMemcpyHostToDevice, s));
-	CLB_CUDA(c, c->qs.reserve(hdr.size() + tot / 3 + (uint64_t)np * (4 + 4 * QB_LANES + 4 * QB_LANES) + 1024, s, false));
+	CLB_CUDA(c, c->qs.reserve(hdr.size() + tot / 3 + (uint64_t)np * (4 + 4 * QB_LANES + 4 * QB_LANES * QB_STATES) + 1024, s, false));
 	CLB_CUDA(c, cudaMemcpyAsync(c->qs.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
 	uint64_t out_at = hdr.size();
 	const uint64_t chunk_syms = 1ull << 31;
@@ -361,7 +361,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		Tmp ct{{}, s};
 		auto calloc_ = [&](void** q, uint64_t bytes) { cudaError_t e = dev_malloc(q, bytes ? bytes : 1, s); if (e == cudaSuccess) ct.v.push_back(*q); return e; };
 		CLB_CUDA(c, calloc_((void**)&d_lane_off, sizeof(uint64_t) * (nl + 1))); if (lane_off[nl] + 8 > tmp_cap) { tmp_cap = lane_off[nl] + 8; CLB_CUDA(c, dalloc((void**)&d_tmp, sizeof(uint16_t) * tmp_cap)); }
-		CLB_CUDA(c, calloc_((void**)&d_words, sizeof(uint32_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_state, sizeof(uint32_t) * nl));
+		CLB_CUDA(c, calloc_((void**)&d_words, sizeof(uint32_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_state, sizeof(uint32_t) * nl * QB_STATES));
 		CLB_CUDA(c, calloc_((void**)&d_dst, sizeof(uint64_t) * nl)); CLB_CUDA(c, calloc_((void**)&d_phdr, sizeof(uint64_t) * cp));
 		CLB_CUDA(c, cudaMemcpyAsync(d_lane_off, lane_off.data(), sizeof(uint64_t) * (nl + 1), cudaMemcpyHostToDevice, s));
 		QEnc e{d_pack_first, p0, cp, d_lane_off, d_tmp, d_words, d_state};
@@ -374,7 +374,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 		std::vector<uint64_t> dst(nl), phdr(cp);
 		for (uint32_t p = 0; p < cp; ++p) {
 			phdr[p] = out_at; out_at += 4 + 4 * QB_LANES;
-			for (uint32_t l = 0; l < QB_LANES; ++l) { dst[(size_t)p * QB_LANES + l] = out_at; out_at += 4 + 2ull * words[(size_t)p * QB_LANES + l]; }
+			for (uint32_t l = 0; l < QB_LANES; ++l) { dst[(size_t)p * QB_LANES + l] = out_at; out_at += 4ull * QB_STATES + 2ull * words[(size_t)p * QB_LANES + l]; }
 		}
 		CLB_CUDA(c, c->qs.reserve(out_at + 16, s, true, phdr[0]));
 		CLB_CUDA(c, cudaMemcpyAsync(d_dst, dst.data(), sizeof(uint64_t) * nl, cudaMemcpyHostToDevice, s));

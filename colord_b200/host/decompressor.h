@@ -124,22 +124,22 @@ public:
 };
 
 struct Pack { uint32_t n_reads; const uint8_t* lane[LANES]; uint32_t lane_bytes[LANES]; };
-inline Pack read_pack(Bytes& in)
+inline Pack read_pack(Bytes& in, uint32_t n_lanes = LANES)
 {
-	Pack p; p.n_reads = in.u32();
-	for (uint32_t l = 0; l < LANES; ++l) p.lane_bytes[l] = in.u32();
-	for (uint32_t l = 0; l < LANES; ++l) p.lane[l] = in.take(p.lane_bytes[l]);
+	Pack p{}; p.n_reads = in.u32();
+	for (uint32_t l = 0; l < n_lanes; ++l) p.lane_bytes[l] = in.u32();
+	for (uint32_t l = 0; l < n_lanes; ++l) p.lane[l] = in.take(p.lane_bytes[l]);
 	return p;
 }
 
 // all packs of a container with the index of their first read
 struct PackAt { Pack pk; uint32_t r0; };
-inline std::vector<PackAt> read_packs(Bytes& in, uint32_t n_packs, uint64_t n_units, const char* what)
+inline std::vector<PackAt> read_packs(Bytes& in, uint32_t n_packs, uint64_t n_units, const char* what, uint32_t n_lanes = LANES)
 {
 	std::vector<PackAt> v; v.reserve(n_packs);
 	uint64_t r0 = 0;
 	for (uint32_t p = 0; p < n_packs; ++p) {
-		PackAt a{read_pack(in), static_cast<uint32_t>(r0)};
+		PackAt a{read_pack(in, n_lanes), static_cast<uint32_t>(r0)};
 		if (a.pk.n_reads > n_units - r0) throw DecodeError(std::string("colord-b200: pack sizes of the ") + what + " stream exceed the archive's count");
 		r0 += a.pk.n_reads;
 		v.push_back(a);
@@ -397,7 +397,12 @@ inline std::vector<uint8_t> decode_qual_avg(const uint8_t* data, uint64_t size, 
 {
 	constexpr uint32_t PB = 12, L = 1u << 15;
 	Bytes in(data, size);
-	in.magic("QB01");
+	// "QB02": 4 streams per pack, 32 interleaved rANS states per stream (symbol k of a read -> state k mod 32); "QB01" (round 1): 64
+	// single-state lanes per pack.  Same header, tables and symbol order.
+	in.need(4);
+	const bool v2 = std::memcmp(in.p + in.at, "QB02", 4) == 0;
+	in.magic(v2 ? "QB02" : "QB01");
+	const uint32_t n_lanes = v2 ? 4 : LANES, n_states = v2 ? 32 : 1;
 	const uint32_t nb = in.u32(), level = in.u32(); uint32_t thr[4]; for (uint32_t& t : thr) t = in.u32();
 	const uint64_t nr = in.u64(); const uint32_t n_packs = in.u32(), cbits = in.u32();
 	const uint32_t n_reads = static_cast<uint32_t>(reads.offsets.size() - 1);
@@ -424,29 +429,34 @@ inline std::vector<uint8_t> decode_qual_avg(const uint8_t* data, uint64_t size, 
 	}
 	std::vector<uint8_t> out(reads.bases.size());
 	auto code = [](uint8_t ch) -> uint32_t { return ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 0; };
-	const std::vector<PackAt> packs = read_packs(in, n_packs, n_reads, "quality");
-	parallel_for(static_cast<uint64_t>(packs.size()) * LANES, [&](uint64_t unit) {
-		const Pack& pk = packs[unit / LANES].pk; const uint32_t r0 = packs[unit / LANES].r0, l = static_cast<uint32_t>(unit % LANES);
+	const std::vector<PackAt> packs = read_packs(in, n_packs, n_reads, "quality", n_lanes);
+	parallel_for(static_cast<uint64_t>(packs.size()) * n_lanes, [&](uint64_t unit) {
+		const Pack& pk = packs[unit / n_lanes].pk; const uint32_t r0 = packs[unit / n_lanes].r0, l = static_cast<uint32_t>(unit % n_lanes);
 		{
 			if (l >= pk.n_reads) return;
 			std::vector<uint8_t> sym;
 			Bytes s(pk.lane[l], pk.lane_bytes[l]);
-			uint32_t x = s.u32();
-			auto renorm = [&]() { while (x < L) x = (x << 16) | s.u16(); };
+			uint32_t xs[32]; for (uint32_t k = 0; k < n_states; ++k) xs[k] = s.u32();
+			uint32_t kk = 0;                                       // symbol index inside the read: picks the state
 			auto pull = [&](const uint16_t* f, uint32_t A) -> uint32_t {
+				uint32_t& x = xs[kk++ % n_states];
 				const uint32_t slot = x & (M12 - 1); uint32_t dsym = 0, acc = 0;
 				while (dsym + 1 < A && acc + f[dsym] <= slot) { acc += f[dsym]; ++dsym; }
 				if (!f[dsym]) throw DecodeError("colord-b200: damaged quality stream");
-				x = f[dsym] * (x >> PB) + slot - acc; renorm();
+				x = f[dsym] * (x >> PB) + slot - acc;
+				while (x < L) x = (x << 16) | s.u16();
 				return dsym;
 			};
-			for (uint32_t r = r0 + l; r < r0 + pk.n_reads; r += LANES) {
+			for (uint32_t r = r0 + l; r < r0 + pk.n_reads; r += n_lanes) {
 				const uint64_t o = reads.offsets[r]; const uint32_t n = static_cast<uint32_t>(reads.offsets[r + 1] - o);
 				uint32_t avg16[5];
+				kk = 0;
 				for (uint32_t b = 0; b < nb; ++b) {
 					const uint32_t a1 = pull(&mf[b * 128], 128);
+					uint32_t& x = xs[kk++ % n_states];
 					const uint32_t slot = x & (M12 - 1), a2 = slot / (M12 >> 8);
-					x = (M12 >> 8) * (x >> PB) + slot - a2 * (M12 >> 8); renorm();
+					x = (M12 >> 8) * (x >> PB) + slot - a2 * (M12 >> 8);
+					while (x < L) x = (x << 16) | s.u16();
 					avg16[b] = (a1 << 8) | a2;
 				}
 				sym.resize(n);

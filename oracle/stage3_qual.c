@@ -150,7 +150,21 @@ static inline uint32_t rans_put(uint32_t x, uint32_t f, uint32_t c, uint16_t* w,
  *   per pack: n_reads u32, QB_LANES x lane size in bytes (u32), lane streams
  *   lane l codes reads l, l + QB_LANES, ... of its pack; a lane stream = final state (u32) + 16-bit words in decoding order
  * es / es_off may be NULL when level <= 1. */
+/* "QB02" (the device's container since round 2): the same header and tables; per pack: n_reads u32, QB2_STREAMS x stream size in bytes (u32),
+ * streams.  Stream s codes reads s, s + QB2_STREAMS, ... of its pack with QB2_STATES interleaved rANS states: the symbols of a read are its
+ * 2 x n_bins mean bytes, then one bin symbol per base, and symbol k of a read belongs to state k mod QB2_STATES.  A stream = the final
+ * states (u32 each) + 16-bit words in decoding order. */
+#define QB2_STREAMS 4
+#define QB2_STATES 32
+static uint64_t qual_encode_v(int version, const orc_qual_params* P, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n_reads,
+	const uint8_t* es, const uint64_t* es_off, const uint32_t* pack_sizes, uint32_t n_packs, uint8_t* out, uint64_t cap);
 uint64_t orc_qual_encode(const orc_qual_params* P, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n_reads,
+	const uint8_t* es, const uint64_t* es_off, const uint32_t* pack_sizes, uint32_t n_packs, uint8_t* out, uint64_t cap)
+{ return qual_encode_v(2, P, bases, quals, offsets, n_reads, es, es_off, pack_sizes, n_packs, out, cap); }
+uint64_t orc_qual_encode_qb01(const orc_qual_params* P, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n_reads,
+	const uint8_t* es, const uint64_t* es_off, const uint32_t* pack_sizes, uint32_t n_packs, uint8_t* out, uint64_t cap)
+{ return qual_encode_v(1, P, bases, quals, offsets, n_reads, es, es_off, pack_sizes, n_packs, out, cap); }
+static uint64_t qual_encode_v(int version, const orc_qual_params* P, const uint8_t* bases, const uint8_t* quals, const uint64_t* offsets, uint32_t n_reads,
 	const uint8_t* es, const uint64_t* es_off, const uint32_t* pack_sizes, uint32_t n_packs, uint8_t* out, uint64_t cap)
 {
 	uint8_t map[96]; make_map(P, map);
@@ -193,7 +207,7 @@ uint64_t orc_qual_encode(const orc_qual_params* P, const uint8_t* bases, const u
 	for (uint32_t b = 0; b < nb; ++b) { normalise(mh + b * 128, 128, mf + b * 128); uint32_t a = 0; for (uint32_t k = 0; k < 128; ++k) { mc[b * 128 + k] = (uint16_t)a; a += mf[b * 128 + k]; } }
 
 	obuf o = {0, 0, 0};
-	ob_put(&o, "QB01", 4); ob_u32(&o, nb); ob_u32(&o, P->level); ob_put(&o, P->thr, 16); ob_u64(&o, n_reads); ob_u32(&o, n_packs); ob_u32(&o, cbits);
+	ob_put(&o, version == 1 ? "QB01" : "QB02", 4); ob_u32(&o, nb); ob_u32(&o, P->level); ob_put(&o, P->thr, 16); ob_u64(&o, n_reads); ob_u32(&o, n_packs); ob_u32(&o, cbits);
 	ob_put(&o, mf, 2ull * nb * 128);
 	for (uint32_t c = 0; c < n_fb; ++c) ob_put(&o, fbf + (size_t)c * nb, 2ull * (nb - 1));
 	{
@@ -214,6 +228,40 @@ uint64_t orc_qual_encode(const orc_qual_params* P, const uint8_t* bases, const u
 		const uint32_t np = pack_sizes[p];
 		ob_u32(&o, np);
 		const uint64_t sizes_at = o.n;
+		if (version == 2)
+		{
+			for (int l = 0; l < QB2_STREAMS; ++l) ob_u32(&o, 0);
+			for (uint32_t l = 0; l < QB2_STREAMS; ++l)
+			{
+				uint64_t nsym = 0;
+				for (uint32_t r = r0 + l; r < r0 + np; r += QB2_STREAMS) nsym += (offsets[r + 1] - offsets[r]) + 2ull * nb;
+				uint16_t* w = (uint16_t*)malloc(2 * (nsym + 4)); uint64_t nw = 0;
+				uint32_t x[QB2_STATES]; for (int k = 0; k < QB2_STATES; ++k) x[k] = QB_L;
+				uint32_t last = r0 + l; while (last + QB2_STREAMS < r0 + np) last += QB2_STREAMS;
+				if (r0 + l < r0 + np) for (int64_t r = last; r >= (int64_t)(r0 + l); r -= QB2_STREAMS)
+				{	/* last read first, last symbol first; symbol k of the read -> state k mod QB2_STATES */
+					const uint64_t at = offsets[r]; const uint32_t n = (uint32_t)(offsets[r + 1] - at), ns = 2 * nb;
+					for (uint32_t k = ns + n; k-- > 0;)
+					{
+						uint32_t f, cf;
+						if (k >= ns) { const uint64_t e = (uint64_t)ctx[at + k - ns] * nb + sym[at + k - ns]; f = freq[e]; cf = cum[e]; }
+						else
+						{
+							const uint32_t b = k >> 1, a = avg[5 * (size_t)r + b], a1 = (a >> 8) & 127, a2 = a & 0xff;
+							if (k & 1) { f = QB_M >> 8; cf = a2 * (QB_M >> 8); } else { f = mf[b * 128 + a1]; cf = mc[b * 128 + a1]; }
+						}
+						x[k % QB2_STATES] = rans_put(x[k % QB2_STATES], f, cf, w, &nw);
+					}
+				}
+				const uint32_t bytes = (uint32_t)(4 * QB2_STATES + 2 * nw);
+				memcpy(o.p + sizes_at + 4 * l, &bytes, 4);
+				for (int k = 0; k < QB2_STATES; ++k) ob_u32(&o, x[k]);
+				for (uint64_t k = nw; k-- > 0;) ob_put(&o, &w[k], 2);
+				free(w);
+			}
+			r0 += np;
+			continue;
+		}
 		for (int l = 0; l < QB_LANES; ++l) ob_u32(&o, 0);
 		for (uint32_t l = 0; l < QB_LANES; ++l)
 		{
@@ -253,7 +301,9 @@ uint64_t orc_qual_encode(const orc_qual_params* P, const uint8_t* bases, const u
 int orc_qual_decode(const uint8_t* in, uint64_t in_n, const uint8_t* bases, const uint64_t* offsets, uint32_t n_reads,
 	const uint8_t* es, const uint64_t* es_off, uint8_t* out)
 {
-	if (in_n < 48 || memcmp(in, "QB01", 4)) return -1;
+	if (in_n < 48 || (memcmp(in, "QB01", 4) && memcmp(in, "QB02", 4))) return -1;
+	const int version = in[3] == '1' ? 1 : 2;
+	const uint32_t n_lanes = version == 1 ? QB_LANES : QB2_STREAMS, n_states = version == 1 ? 1 : QB2_STATES;
 	orc_qual_params P; uint64_t at = 4;
 	memcpy(&P.n_bins, in + at, 4); at += 4; memcpy(&P.level, in + at, 4); at += 4; memcpy(P.thr, in + at, 16); at += 16;
 	uint64_t nr; memcpy(&nr, in + at, 8); at += 8; uint32_t n_packs, cbits; memcpy(&n_packs, in + at, 4); at += 4; memcpy(&cbits, in + at, 4); at += 4;
@@ -290,13 +340,15 @@ int orc_qual_decode(const uint8_t* in, uint64_t in_n, const uint8_t* bases, cons
 	for (uint32_t p = 0; p < n_packs; ++p)
 	{
 		uint32_t np; memcpy(&np, in + at, 4); at += 4;
-		uint32_t sizes[QB_LANES]; memcpy(sizes, in + at, 4 * QB_LANES); at += 4 * QB_LANES;
-		for (uint32_t l = 0; l < QB_LANES; ++l)
+		uint32_t sizes[QB_LANES]; memcpy(sizes, in + at, 4 * n_lanes); at += 4 * n_lanes;
+		for (uint32_t l = 0; l < n_lanes; ++l)
 		{
 			const uint8_t* s = in + at; at += sizes[l];
-			uint32_t x; memcpy(&x, s, 4); uint64_t rp = 4;
-			for (uint32_t r = r0 + l; r < r0 + np; r += QB_LANES)
+			uint32_t xs[QB2_STATES]; memcpy(xs, s, 4 * n_states); uint64_t rp = 4 * n_states;
+			for (uint32_t r = r0 + l; r < r0 + np; r += n_lanes)
 			{
+				uint32_t kk = 0;                          /* symbol index inside the read: picks the state */
+#define x xs[(kk) % n_states]
 				const uint64_t o = offsets[r]; const uint32_t n = (uint32_t)(offsets[r + 1] - o);
 				uint32_t avg16[5];
 				for (uint32_t b = 0; b < nb; ++b)
@@ -305,10 +357,12 @@ int orc_qual_decode(const uint8_t* in, uint64_t in_n, const uint8_t* bases, cons
 					while (acc + mf[b * 128 + a1] <= slot) { acc += mf[b * 128 + a1]; ++a1; }
 					x = mf[b * 128 + a1] * (x >> QB_PROB_BITS) + slot - acc;
 					while (x < QB_L) { uint16_t w; memcpy(&w, s + rp, 2); rp += 2; x = (x << 16) | w; }
+					++kk;
 					slot = x & (QB_M - 1);
 					const uint32_t a2 = slot / (QB_M >> 8);
 					x = (QB_M >> 8) * (x >> QB_PROB_BITS) + slot - a2 * (QB_M >> 8);
 					while (x < QB_L) { uint16_t w; memcpy(&w, s + rp, 2); rp += 2; x = (x << 16) | w; }
+					++kk;
 					avg16[b] = (a1 << 8) | a2;
 				}
 				uint8_t* fl = (uint8_t*)calloc(n + 1, 1);
@@ -326,9 +380,11 @@ int orc_qual_decode(const uint8_t* in, uint64_t in_n, const uint8_t* bases, cons
 					while (a + f[d] <= slot) { a += f[d]; ++d; }
 					x = f[d] * (x >> QB_PROB_BITS) + slot - a;
 					while (x < QB_L) { uint16_t w; memcpy(&w, s + rp, 2); rp += 2; x = (x << 16) | w; }
+					++kk;
 					sym[i] = (uint8_t)d;
 					c = ((c << bps) + d) & cmask;
 				}
+#undef x
 				reconstruct(&P, avg16, sym, n, out + o);
 				free(sym); free(fl);
 			}
