@@ -26,6 +26,19 @@
 
 namespace clb {
 
+// -DCLB_ALIGN_PHASES (profiling builds only, `make phases`): cycles of the group's first lane per phase, summed over all tasks
+//   0 sweep, 1 traceback, 2 finish_script, 3 whole task, 4 sweep steps, 5 traceback iterations, 6 traceback window loads, 7 tasks
+#ifdef CLB_ALIGN_PHASES
+__device__ unsigned long long g_align_phase[6 * 8];
+#define CLB_PH_BEGIN long long ph_t0_ = clock64();
+#define CLB_PH_END(G, i) { if (gl == 0) atomicAdd(&g_align_phase[(G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : G == 2 ? 1 : 0) * 8 + (i)], (unsigned long long)(clock64() - ph_t0_)); }
+#define CLB_PH_COUNT(G, i, n) { if (gl == 0) atomicAdd(&g_align_phase[(G == 32 ? 5 : G == 16 ? 4 : G == 8 ? 3 : G == 4 ? 2 : G == 2 ? 1 : 0) * 8 + (i)], (unsigned long long)(n)); }
+#else
+#define CLB_PH_BEGIN
+#define CLB_PH_END(G, i)
+#define CLB_PH_COUNT(G, i, n)
+#endif
+
 struct SeqView {            // element i = base[i * step]; step = -1 gives a reversed view
 	const uint8_t* base; int step;
 	__device__ __forceinline__ uint8_t operator[](int i) const { return base[(long long)i * step]; }
@@ -147,9 +160,11 @@ struct Aligner {
 	__device__ int sweep(V rows, int Q, V cols, int T, uint64_t* hist_pv, uint64_t* hist_ph, int hist_stride,
 		int32_t* lastrow, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
 	{
+		CLB_PH_BEGIN
 		const int B = (Q + 63) >> 6;
 		int8_t* carry = reinterpret_cast<int8_t*>(scratch + lay.carry);
 		int final_score = 0;
+		CLB_PH_COUNT(GROUP, 4, (long long)((B + GROUP - 1) / GROUP) * (T + GROUP - 1))
 		for (int strip = 0; strip * GROUP < B; ++strip) {
 			const int b = strip * GROUP + (int)gl;
 			const bool act = b < B;
@@ -214,6 +229,7 @@ struct Aligner {
 			const int owner = (B - 1) % GROUP;
 			final_score = __shfl_sync(mask(), final_score, owner, GROUP);
 		}
+		CLB_PH_END(GROUP, 0)
 		return final_score;
 	}
 
@@ -223,6 +239,7 @@ struct Aligner {
 	// order to out; returns their number.  tmp: Q + T bytes.
 	__device__ int traceback(const uint64_t* hpv, const uint64_t* hph, int stride, int Q, int T, uint8_t* out, uint8_t* tmp) const
 	{
+		CLB_PH_BEGIN
 		int I = Q, J = T, n = 0;
 		int wb = -1, wj = -0x40000000;
 		uint64_t wpv = 0, wph = 0;
@@ -232,6 +249,7 @@ struct Aligner {
 			const int i = I - 1, j = J - 1, b = i >> 6, bit = i & 63;
 			if (b != wb || j > wj || j < wj - (GROUP - 1)) {
 				wb = b; wj = j;
+				CLB_PH_COUNT(GROUP, 6, 1)
 				const int col = wj - (int)gl;
 				if (col >= 0) { const size_t h = (size_t)b * stride + col; wpv = hpv[h]; wph = hph[h]; }
 			}
@@ -256,6 +274,7 @@ struct Aligner {
 			}
 			for (int x = (int)gl; x < run; x += GROUP) tmp[n + x] = op;
 			n += run;
+			CLB_PH_COUNT(GROUP, 5, 1)
 		}
 		// a border was reached: the rest is all up or all left
 		const int rest = I + J; const uint8_t rop = I > 0 ? 1 : 2;
@@ -264,6 +283,7 @@ struct Aligner {
 		gsync();
 		for (int x = (int)gl; x < n; x += GROUP) out[x] = tmp[n - 1 - x];
 		gsync();
+		CLB_PH_END(GROUP, 1)
 		return n;
 	}
 
@@ -437,6 +457,7 @@ template <int GROUP, class V>
 __device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint32_t n, V ref, V enc, bool rows_ref, char* out)
 {
 	const uint32_t gl = A.gl;
+	CLB_PH_BEGIN
 	const uint32_t L = (n + GROUP - 1) / GROUP;
 	const uint32_t s = min(n, gl * L), e = min(n, s + L);
 	uint32_t cr = 0, ce = 0;
@@ -459,7 +480,7 @@ __device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint3
 			else { out[i] = "ACGT"[enc[(int)q] & 3]; ++q; }
 		}
 	}
-	if (GROUP == 1) { refactor_range(ref, enc, out, 0, n, 0, 0); return; }
+	if (GROUP == 1) { refactor_range(ref, enc, out, 0, n, 0, 0); CLB_PH_END(GROUP, 2) return; }
 	A.gsync();
 	uint32_t cut = 0, cut_r = 0, cut_q = 0;
 	if (gl > 0) {
@@ -487,6 +508,7 @@ __device__ void finish_script(const Aligner<GROUP>& A, const uint8_t* ops, uint3
 	A.gsync();                                 // every cut is known before any lane reorders symbols
 	if (cut < next) refactor_range(ref, enc, out, cut, next, cut_r, cut_q);
 	A.gsync();
+	CLB_PH_END(GROUP, 2)
 }
 
 // One edit-script task = CEncoder::GetEditDist (encoder.cpp:1255-1283).

@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(128) k_align(Task* __restrict__ tasks, uint64_
 	const CandView& V = cviews[(size_t)T.node * c + N.level];
 	Aligner<GROUP> A;
 	A.gl = threadIdx.x & (GROUP - 1);
+#ifdef CLB_ALIGN_PHASES
+	const uint32_t gl = A.gl;
+#endif
+	CLB_PH_BEGIN
 	const uint32_t lane = threadIdx.x & 31;
 	A.gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(uint32_t)(GROUP - 1)));
 	A.scratch = scratch + (uint64_t)slot * stride;
@@ -154,6 +158,8 @@ __global__ void __launch_bounds__(128) k_align(Task* __restrict__ tasks, uint64_
 	uint32_t lead = 0;
 	const uint32_t n = edit_script_task<GROUP>(A, ref, T.rl, enc, T.el, T.kind, esbuf + T.es_off, &lead);
 	if (A.gl == 0) { T.es_len = n; T.lead = lead; }
+	CLB_PH_END(GROUP, 3)
+	CLB_PH_COUNT(GROUP, 7, 1)
 }
 
 // ------------------------------------------------------------------------------------------------ decisions
@@ -840,6 +846,15 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	}
 	prof_end(c);
 	CLB_CUDA(c, cudaStreamSynchronize(s));        // d_list / d_bin_of die with `mem`
+#ifdef CLB_ALIGN_PHASES
+	{
+		unsigned long long h[48];
+		cudaMemcpyFromSymbol(h, g_align_phase, sizeof h);
+		static const int gs[6] = {1, 2, 4, 8, 16, 32};
+		for (int g = 0; g < 6; ++g) if (h[g * 8 + 7]) fprintf(stderr, "[align phases] group %2d: tasks %llu, Mcycles sweep %.0f traceback %.0f finish %.0f whole %.0f | sweep steps %llu (%.0f cyc/step), traceback iterations %llu (%.0f cyc/it), window loads %llu\n",
+			gs[g], h[g * 8 + 7], h[g * 8] * 1e-6, h[g * 8 + 1] * 1e-6, h[g * 8 + 2] * 1e-6, h[g * 8 + 3] * 1e-6, h[g * 8 + 4], (double)h[g * 8] / (h[g * 8 + 4] ? h[g * 8 + 4] : 1), h[g * 8 + 5], (double)h[g * 8 + 1] / (h[g * 8 + 5] ? h[g * 8 + 5] : 1), h[g * 8 + 6]);
+	}
+#endif
 	return CLB_OK;
 }
 

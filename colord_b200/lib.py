@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcolord_b200.so")
+SO_PATH = os.environ.get("CLB_LIBRARY") or os.path.join(_HERE, "libcolord_b200.so")      # CLB_LIBRARY: a profiling build (make phases)
 
 STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "BAD_SYMBOL", 5: "STATE", 6: "CAPACITY"}
 EXPORTS = [

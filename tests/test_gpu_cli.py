@@ -268,7 +268,7 @@ def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts, n_gpus):
     assert len(parts2["dna-b200"]) == n_gpus and len(parts1["dna-b200"]) == 1
     assert sum(md for md, _ in parts2["dna-b200"]) == parts1["dna-b200"][0][0]
     d1, d2 = len(parts1["dna-b200"][0][1]), sum(len(b) for _, b in parts2["dna-b200"])
-    assert d2 < (1.03 if n_gpus == 2 else 1.10) * d1, (d1, d2)      # 24 Mbases over N shards: every shard pays its own tables
+    assert d2 < (1.03 if n_gpus == 2 else 1.20) * d1, (d1, d2)      # 24 Mbases over N shards: every shard pays its own tables
     r = subprocess.run([cli, "decompress", two, back], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     if "org" in opts:
