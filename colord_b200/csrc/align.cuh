@@ -86,8 +86,11 @@ __host__ __device__ inline long long edlib_column_bytes(long long q, long long t
 constexpr long long EDLIB_TRACEBACK_LIMIT = 1024 * 1024;
 
 // Scratch layout of one task (host and device agree through this function).
+// hist: Pv / Ph of every (block, column) of a stored-column sweep, 16 bytes per entry, in the order the wavefront produces
+// them (see Aligner::sweep): entry of block b, column c = strip * n_steps * G + (c + g) * Gs + g with G the lane group (<= 32),
+// strip = b / G, g = b % G, n_steps = T + G - 1, Gs = blocks of that strip — at most B * (T + 31) entries.
 struct AlignScratch {
-	unsigned long long hist, carry, lastrow, ops, tmp, F, R, fin, stack, total;
+	unsigned long long hist, carry, ops, tmp, F, R, fin, stack, total;
 };
 __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long long t)
 {
@@ -96,9 +99,9 @@ __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long l
 	const bool big = edlib_column_bytes(q, t) >= EDLIB_TRACEBACK_LIMIT;
 	unsigned long long o = 0;
 	auto take = [&](unsigned long long bytes) { unsigned long long at = o; o += (bytes + 15) & ~15ULL; return at; };
-	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 : (unsigned long long)(16 * B * (t > 0 ? t : 1)));
-	s.carry = take((unsigned long long)t + 1);
-	s.lastrow = take(4ull * (t + 1));
+	// a Hirschberg leaf has 20 B T + 8 T < 1 MiB: 16 B (T + 31) < 1 MiB + 496 B
+	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 + 512ull * B : (unsigned long long)(16 * B * ((t > 0 ? t : 1) + 31)));
+	s.carry = take(2ull * 8 * ((unsigned long long)(t + 63) / 32 + 4));      // two arrays of 2-bit horizontal deltas, 32 per word
 	s.ops = take((unsigned long long)(q + t + 2));
 	s.tmp = take((unsigned long long)(q + t + 2));
 	s.F = take(big ? 4ull * (q + 1) : 0);
@@ -107,26 +110,6 @@ __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long l
 	s.stack = take(big ? 64ull * 5 * 4 : 0);
 	s.total = o;
 	return s;
-}
-
-// edlib.cpp:407-441 (calculateBlock); returns hout, hb = bit whose horizontal delta is returned as *sdelta
-__device__ __forceinline__ int myers_block(uint64_t& Pv, uint64_t& Mv, uint64_t Eq, int hin, uint32_t score_bit, int* sdelta, uint64_t* ph_out)
-{
-	const uint64_t hin_neg = (uint64_t)((uint32_t)(hin >> 2) & 1u);
-	const uint64_t Xv = Eq | Mv;
-	Eq |= hin_neg;
-	const uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-	uint64_t Ph = Mv | ~(Xh | Pv);
-	uint64_t Mh = Pv & Xh;
-	const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-	*sdelta = (int)((Ph >> score_bit) & 1) - (int)((Mh >> score_bit) & 1);
-	*ph_out = Ph;
-	Ph <<= 1; Mh <<= 1;
-	Mh |= hin_neg;
-	Ph |= (uint64_t)((hin + 1) >> 1);
-	Pv = Mh | ~(Xv | Ph);
-	Mv = Ph & Xv;
-	return hout;
 }
 
 // bits 0, 2, 4, .. 62 of x -> bits 0 .. 31
@@ -141,105 +124,175 @@ __device__ __forceinline__ uint64_t compress_even(uint64_t x)
 	return x;
 }
 
+constexpr int ALIGN_THREADS = 128;          // CTA size of the kernels that own an Aligner (its shared match-vector table)
+
 template <int GROUP>
 struct Aligner {
 	uint32_t gl;            // lane within the group
 	uint32_t gmask;         // warp mask of the group's lanes
 	uint8_t* scratch;       // this task's scratch
 	AlignScratch lay;
+	uint64_t* peq;          // shared memory: match vector of this lane's 64 rows for base x at peq[x * ALIGN_THREADS]
 
 	// the lanes of the group as a warp mask; for a whole-warp group a literal, so that the compiler drops the convergence checks of
 	// a run-time mask (MATCH.ANY / VOTEU / BRA.DIV around every shuffle)
 	__device__ __forceinline__ uint32_t mask() const { return GROUP == 32 ? 0xffffffffu : gmask; }
 	__device__ __forceinline__ void gsync() const { if (GROUP > 1) __syncwarp(mask()); }
 
-	// Forward sweep of rows[0..Q) x cols[0..T).  hist_pv / hist_ph (may be null) receive Pv / Ph of block b, column c at
-	// [b * hist_stride + c].  lastrow (int32[T]) receives D(Q-1, c) if non-null.
-	// fin_* (per block) receive the final column if non-null.  Returns D(Q-1, T-1) to every lane.
-	template <class V>
-	__device__ int sweep(V rows, int Q, V cols, int T, uint64_t* hist_pv, uint64_t* hist_ph, int hist_stride,
-		int32_t* lastrow, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
+	// what a sweep leaves in the lanes' registers (valid in every lane of the group after the sweep)
+	struct SweepResult { int score; int best, end; };      // D(Q-1, T-1); leftmost minimum of the last row D(Q-1, .) and its column
+
+	// state of one lane during a strip
+	struct Lane {
+		uint64_t Pv, Mv;        // vertical deltas of the block after the last column done
+		uint64_t cols;          // column symbols of the coming steps of the chunk, 2 bits each, next one in bits 0-1
+		uint64_t cin;           // horizontal deltas entering lane 0 from the previous strip, same order
+		uint64_t cacc;          // horizontal deltas leaving this lane, last 32 steps (newest in the top bits)
+		uint32_t hp;            // horizontal delta leaving the block in the last column done: bit 0 = +1, bit 1 = -1
+		int score, best, end;
+	};
+
+	// One column of one 64-row block: edlib.cpp:407-441 (calculateBlock).  CHECK: the lane may be outside its columns (the
+	// wavefront's ramps); FIRST: no strip above (a +1 enters the top block); HIST: Pv / Ph go to the history; SCORE: the score of
+	// the block's last row is followed (bit sbit of the horizontal deltas) and, in the lane with the last block, its leftmost minimum.
+	template <bool CHECK, bool FIRST, bool HIST, bool SCORE>
+	__device__ __forceinline__ void step(Lane& L, int s, int T, bool act, bool last_blk, uint32_t sbit, ulonglong2* __restrict__ hp_at) const
+	{
+		uint32_t hin = GROUP > 1 ? __shfl_up_sync(mask(), L.hp, 1, GROUP) : 0u;
+		if (gl == 0) hin = FIRST ? 1u : (uint32_t)L.cin & 3u;
+		if (!FIRST) L.cin >>= 2;
+		const uint64_t Eq0 = peq[((uint32_t)L.cols & 3u) * ALIGN_THREADS];
+		L.cols >>= 2;
+		const int c = s - (int)gl;
+		if (!CHECK || (act && (unsigned)c < (unsigned)T)) {
+			const uint64_t hneg = hin >> 1, hpos = hin & 1u;
+			const uint64_t Xv = Eq0 | L.Mv;
+			const uint64_t Eq = Eq0 | hneg;
+			const uint64_t Xh = (((Eq & L.Pv) + L.Pv) ^ L.Pv) | Eq;
+			uint64_t Ph = L.Mv | ~(Xh | L.Pv);
+			uint64_t Mh = L.Pv & Xh;
+			L.hp = (uint32_t)(Ph >> 63) | ((uint32_t)(Mh >> 63) << 1);
+			if (SCORE) {
+				L.score += (int)((Ph >> sbit) & 1) - (int)((Mh >> sbit) & 1);
+				if (last_blk && L.score < L.best) { L.best = L.score; L.end = c; }
+			}
+			const uint64_t ph0 = Ph;
+			Ph = (Ph << 1) | hpos; Mh = (Mh << 1) | hneg;
+			L.Pv = Mh | ~(Xv | Ph);
+			L.Mv = Ph & Xv;
+			if (HIST && (CHECK || act)) *hp_at = make_ulonglong2(L.Pv, ph0);
+		}
+		if (GROUP == 32) L.cacc = (L.cacc >> 2) | ((uint64_t)L.hp << 62);
+	}
+
+	// Forward sweep of rows[0..Q) x cols[0..T): Myers / Hyyrö columns over 64-row blocks, lane g of the group owning block
+	// strip * GROUP + g and running g columns behind lane g - 1 (anti-diagonal wavefront; the horizontal delta at the block
+	// border travels by shuffle).  Steps come in chunks of 32: per chunk a lane takes its 32 column symbols from two packed
+	// words, and (whole-warp groups only, the others have a single strip) lane 0 its 32 incoming deltas of the strip above while
+	// the last lane leaves the deltas of its bottom border as one word.  Chunks in which every lane is inside its columns run
+	// without range checks.
+	// HIST: hist receives Pv / Ph of every (block, column) in wavefront order (layout: AlignScratch) — the lanes of a step
+	// write neighbouring 16-byte entries.  SCORE: scores are followed (see step); fin_* (per block, may be null) receive the
+	// final column.
+	template <bool HIST, bool SCORE, class V>
+	__device__ SweepResult sweep(V rows, int Q, V cols, int T, ulonglong2* __restrict__ hist, uint64_t* fin_pv, uint64_t* fin_mv, int32_t* fin_sc) const
 	{
 		CLB_PH_BEGIN
 		const int B = (Q + 63) >> 6;
-		int8_t* carry = reinterpret_cast<int8_t*>(scratch + lay.carry);
-		int final_score = 0;
-		CLB_PH_COUNT(GROUP, 4, (long long)((B + GROUP - 1) / GROUP) * (T + GROUP - 1))
+		const int n_steps = T + GROUP - 1;
+		CLB_PH_COUNT(GROUP, 4, (long long)((B + GROUP - 1) / GROUP) * n_steps)
+		uint64_t* const carry0 = reinterpret_cast<uint64_t*>(scratch + lay.carry);
+		const int carry_words = (T + 63) / 32 + 4;
+		SweepResult res{0, 0x7fffffff, 0};
 		for (int strip = 0; strip * GROUP < B; ++strip) {
 			const int b = strip * GROUP + (int)gl;
 			const bool act = b < B;
 			const bool last_blk = b == B - 1;
+			const bool more = (strip + 1) * GROUP < B;                   // another strip follows: the last lane leaves its deltas
 			const uint32_t sbit = last_blk ? (uint32_t)((Q - 1) & 63) : 63u;
-			uint64_t peq0 = 0, peq1 = 0, peq2 = 0, peq3 = 0;
-			if (act) {      // match vectors of the block's 64 rows from two packed words
-				const int r0 = b << 6, nr = min(Q - r0, 64);
+			{      // match vectors of the block's 64 rows from two packed words
+				uint64_t peq0 = 0, peq1 = 0, peq2 = 0, peq3 = 0;
+				if (act) {
+					const int r0 = b << 6, nr = min(Q - r0, 64);
 #pragma unroll
-				for (int h = 0; h < 2; ++h) {
-					const int n = min(nr - 32 * h, 32);
-					if (n <= 0) break;
-					const uint64_t w = rows.get32(r0 + 32 * h, n);
-					const uint64_t valid = n == 32 ? 0xffffffffULL : ((1ULL << n) - 1);
-					const uint64_t e = compress_even(w), o = compress_even(w >> 1);
-					peq0 |= (~e & ~o & valid) << (32 * h); peq1 |= (e & ~o & valid) << (32 * h);
-					peq2 |= (~e & o & valid) << (32 * h); peq3 |= (e & o & valid) << (32 * h);
+					for (int h = 0; h < 2; ++h) {
+						const int n = min(nr - 32 * h, 32);
+						if (n <= 0) break;
+						const uint64_t w = rows.get32(r0 + 32 * h, n);
+						const uint64_t valid = n == 32 ? 0xffffffffULL : ((1ULL << n) - 1);
+						const uint64_t e = compress_even(w), o = compress_even(w >> 1);
+						peq0 |= (~e & ~o & valid) << (32 * h); peq1 |= (e & ~o & valid) << (32 * h);
+						peq2 |= (~e & o & valid) << (32 * h); peq3 |= (e & o & valid) << (32 * h);
+					}
 				}
+				peq[0] = peq0; peq[ALIGN_THREADS] = peq1; peq[2 * ALIGN_THREADS] = peq2; peq[3 * ALIGN_THREADS] = peq3;     // this thread's own cells
 			}
-			uint64_t Pv = ~0ULL, Mv = 0;
-			int score = act ? min(Q, (b << 6) + 64) : 0;        // D(last row of block, column -1) = row index + 1
-			int hout = 0;
-			// column symbols travel in registers: every lane holds the same three packed words (columns [S-32, S), [S, S+32) and
-			// the prefetched [S+32, S+64) of the current 32-step chunk S), so no load sits on the recurrence's critical path
+			Lane L;
+			L.Pv = ~0ULL; L.Mv = 0; L.hp = 0; L.cacc = 0; L.cin = 0; L.cols = 0;
+			L.score = act ? min(Q, (b << 6) + 64) : 0;        // D(last row of block, column -1) = row index + 1
+			L.best = 0x7fffffff; L.end = 0;
+			const int Gs = min(GROUP, B - strip * GROUP);
+			ulonglong2* hp_at = HIST ? hist + ((size_t)strip * n_steps * GROUP + gl) : nullptr;       // entry of step 0; a step is Gs entries
+			const uint64_t* cin_arr = carry0 + (size_t)((strip + 1) & 1) * carry_words;          // written by the strip above
+			uint64_t* cout_arr = carry0 + (size_t)(strip & 1) * carry_words;
+			// column words: [s0 - 32, s0), [s0, s0 + 32) and the prefetched [s0 + 32, s0 + 64) of the chunk starting at step s0
 			uint64_t col_a = 0, col_b = T > 0 ? cols.get32(0, min(32, T)) : 0, col_c = T > 32 ? cols.get32(32, min(32, T - 32)) : 0;
-			// carries of the previous strip: one per lane for the current chunk of GROUP columns, next chunk prefetched
-			int cw = 0, cw_next = 0;
-			if (GROUP > 1 && strip > 0) { cw = (int)gl < T ? (int)carry[gl] : 0; cw_next = GROUP + (int)gl < T ? (int)carry[GROUP + gl] : 0; }
-			const int n_steps = T + GROUP - 1;
-			for (int s = 0; s < n_steps; ++s) {
-				if (s && (s & 31) == 0) {
+			// incoming deltas: the strip above left the delta of column c in slot (c + 31) & 31 of word (c + 31) >> 5
+			uint64_t cin_a = 0, cin_b = 0, cin_c = 0;
+			if (GROUP == 32 && strip > 0) { cin_a = cin_arr[0]; cin_b = cin_arr[1]; cin_c = cin_arr[2]; }
+			for (int s0 = 0; s0 < n_steps; s0 += 32) {
+				if (s0) {
 					col_a = col_b; col_b = col_c;
-					col_c = s + 32 < T ? cols.get32(s + 32, min(32, T - s - 32)) : 0;
+					col_c = s0 + 32 < T ? cols.get32(s0 + 32, min(32, T - s0 - 32)) : 0;
+					if (GROUP == 32 && strip > 0) { cin_a = cin_b; cin_b = cin_c; cin_c = cin_arr[(s0 >> 5) + 2]; }
 				}
-				if (GROUP > 1 && strip > 0 && s && (s & (GROUP - 1)) == 0) {
-					cw = cw_next;
-					const int idx = s + GROUP + (int)gl;
-					cw_next = idx < T ? (int)carry[idx] : 0;
+				L.cols = gl == 0 ? col_b : (col_a >> (64 - 2 * gl)) | (col_b << (2 * gl));       // columns s0 - gl .. s0 - gl + 31
+				if (GROUP == 32 && strip > 0) L.cin = (cin_a >> 62) | (cin_b << 2);
+				const int ns = min(32, n_steps - s0);
+				if (s0 >= GROUP - 1 && s0 + 31 < T) {
+					if (strip == 0) {
+#pragma unroll 4
+						for (int i = 0; i < 32; ++i) { step<false, true, HIST, SCORE>(L, s0 + i, T, act, last_blk, sbit, hp_at); if (HIST) hp_at += Gs; }
+					} else {
+#pragma unroll 4
+						for (int i = 0; i < 32; ++i) { step<false, false, HIST, SCORE>(L, s0 + i, T, act, last_blk, sbit, hp_at); if (HIST) hp_at += Gs; }
+					}
+				} else if (strip == 0) {
+					for (int i = 0; i < ns; ++i) { step<true, true, HIST, SCORE>(L, s0 + i, T, act, last_blk, sbit, hp_at); if (HIST) hp_at += Gs; }
+				} else {
+					for (int i = 0; i < ns; ++i) { step<true, false, HIST, SCORE>(L, s0 + i, T, act, last_blk, sbit, hp_at); if (HIST) hp_at += Gs; }
 				}
-				int hin = GROUP > 1 ? __shfl_up_sync(mask(), hout, 1, GROUP) : 0;
-				const int cin = (GROUP > 1 && strip > 0) ? __shfl_sync(mask(), cw, s & (GROUP - 1), GROUP) : 0;
-				const int c = s - (int)gl;
-				if (act && c >= 0 && c < T) {
-					if (gl == 0) hin = strip == 0 ? 1 : (GROUP > 1 ? cin : (int)carry[c]);
-					const uint64_t colw = (c >> 5) == (s >> 5) ? col_b : col_a;
-					const uint32_t tc = (uint32_t)(colw >> (2 * (c & 31))) & 3u;
-					const uint64_t Eq = tc == 0 ? peq0 : tc == 1 ? peq1 : tc == 2 ? peq2 : peq3;
-					int sd; uint64_t Ph;
-					hout = myers_block(Pv, Mv, Eq, hin, sbit, &sd, &Ph);
-					score += sd;
-					if (gl == GROUP - 1 && !last_blk) carry[c] = (int8_t)hout;
-					if (hist_pv) { const size_t h = (size_t)b * hist_stride + c; hist_pv[h] = Pv; hist_ph[h] = Ph; }
-					if (last_blk && lastrow) lastrow[c] = score;
-				}
+				if (GROUP == 32 && more && gl == GROUP - 1) cout_arr[s0 >> 5] = ns == 32 ? L.cacc : L.cacc >> (64 - 2 * ns);
 			}
-			if (act && fin_pv) { fin_pv[b] = Pv; fin_mv[b] = Mv; fin_sc[b] = score; }
-			if (act && last_blk) final_score = score;
-			gsync();           // carry[] written by the last lane is read by lane 0 in the next strip
+			if (act && fin_pv) { fin_pv[b] = L.Pv; fin_mv[b] = L.Mv; fin_sc[b] = L.score; }
+			if (act && last_blk) { res.score = L.score; res.best = L.best; res.end = L.end; }
+			gsync();           // the deltas written by the last lane are read by every lane in the next strip
 		}
-		// broadcast the final score from the lane that owns the last block
-		if (GROUP > 1) {
+		if (GROUP > 1) {       // from the lane that owns the last block to all
 			const int owner = (B - 1) % GROUP;
-			final_score = __shfl_sync(mask(), final_score, owner, GROUP);
+			res.score = __shfl_sync(mask(), res.score, owner, GROUP);
+			res.best = __shfl_sync(mask(), res.best, owner, GROUP);
+			res.end = __shfl_sync(mask(), res.end, owner, GROUP);
 		}
 		CLB_PH_END(GROUP, 0)
-		return final_score;
+		return res;
+	}
+
+	// history entry of block b, column c of a sweep over T columns and B blocks (layout: AlignScratch)
+	__device__ __forceinline__ size_t hist_at(int b, int c, int T, int B) const
+	{
+		const int strip = b / GROUP, g = b % GROUP, Gs = min(GROUP, B - strip * GROUP);
+		return (size_t)strip * (T + GROUP - 1) * GROUP + (size_t)(c + g) * Gs + g;
 	}
 
 	// ---- traceback on stored columns: edlib.cpp:945-1159 ----
-	// Walks from vertex (Q, T) back to (0, 0); every lane of the group runs the same walk, lane l holds column (window top - l)
-	// of the current block.  ops: 1 = up (row symbol only), 2 = left (column symbol only), 0 = diagonal.  Written in forward
-	// order to out; returns their number.  tmp: Q + T bytes.
-	__device__ int traceback(const uint64_t* hpv, const uint64_t* hph, int stride, int Q, int T, uint8_t* out, uint8_t* tmp) const
+	// Walks from vertex (Q, T) back to (0, 0) through the history of a sweep over Ts >= T columns; every lane of the group runs
+	// the same walk, lane l holds column (window top - l) of the current block.  ops: 1 = up (row symbol only), 2 = left (column
+	// symbol only), 0 = diagonal.  Written in forward order to out; returns their number.  tmp: Q + T bytes.
+	__device__ int traceback(const ulonglong2* __restrict__ hist, int Ts, int Q, int T, uint8_t* out, uint8_t* tmp) const
 	{
 		CLB_PH_BEGIN
+		const int B = (Q + 63) >> 6;
 		int I = Q, J = T, n = 0;
 		int wb = -1, wj = -0x40000000;
 		uint64_t wpv = 0, wph = 0;
@@ -251,7 +304,7 @@ struct Aligner {
 				wb = b; wj = j;
 				CLB_PH_COUNT(GROUP, 6, 1)
 				const int col = wj - (int)gl;
-				if (col >= 0) { const size_t h = (size_t)b * stride + col; wpv = hpv[h]; wph = hph[h]; }
+				if (col >= 0) { const ulonglong2 e = hist[hist_at(b, col, Ts, B)]; wpv = e.x; wph = e.y; }
 			}
 			const int src = wj - j;                       // lane holding column j
 			const int k = (int)gl - src;                  // this lane holds column j - k
@@ -344,10 +397,10 @@ struct Aligner {
 			const int Bq = (ql + 63) >> 6;
 			uint64_t* fpv = fin_pv; uint64_t* fmv = fin_pv + Bq; int32_t* fsc = reinterpret_cast<int32_t*>(fin_pv + 2 * Bq);
 			const int lw = tl / 2, rw = tl - lw;
-			sweep(r, ql, c, lw, nullptr, nullptr, 0, nullptr, fpv, fmv, fsc);
+			sweep<false, true>(r, ql, c, lw, nullptr, fpv, fmv, fsc);
 			gsync();
 			decode_final(fpv, fmv, fsc, ql, lw, F);
-			sweep(r.reversed(ql), ql, c.sub(lw).reversed(rw), rw, nullptr, nullptr, 0, nullptr, fpv, fmv, fsc);
+			sweep<false, true>(r.reversed(ql), ql, c.sub(lw).reversed(rw), rw, nullptr, fpv, fmv, fsc);
 			gsync();
 			decode_final(fpv, fmv, fsc, ql, rw, R);           // R[z] = dist(last z rows, right half)
 			// topmost y in 1..ql-1 with F[y] + R[ql-y] == bs, then y = 0, then y = ql   (edlib.cpp:1305-1338)
@@ -382,11 +435,10 @@ struct Aligner {
 			return Q + T;
 		}
 		const int B = (Q + 63) >> 6;
-		uint64_t* hpv = reinterpret_cast<uint64_t*>(scratch + lay.hist);
-		uint64_t* hph = hpv + (size_t)B * T;
-		sweep(rows, Q, cols, T, hpv, hph, T, nullptr, nullptr, nullptr, nullptr);
+		ulonglong2* hist = reinterpret_cast<ulonglong2*>(scratch + lay.hist);
+		sweep<true, false>(rows, Q, cols, T, hist, nullptr, nullptr, nullptr);
 		gsync();
-		n = traceback(hpv, hph, T, Q, T, out, tmp);
+		n = traceback(hist, T, Q, T, out, tmp);
 		return n;
 	}
 };
@@ -548,7 +600,7 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		const bool small = edlib_column_bytes(rl, el) < EDLIB_TRACEBACK_LIMIT;
 		if (small) n_ops = A.leaf(ref, (int)rl, enc, (int)el, ops, A.scratch + A.lay.tmp);
 		else {
-			best = A.sweep(ref, (int)rl, enc, (int)el, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+			best = A.template sweep<false, true>(ref, (int)rl, enc, (int)el, nullptr, nullptr, nullptr, nullptr).score;
 			A.gsync();
 			n_ops = A.path(ref, (int)rl, enc, (int)el, best, ops);
 		}
@@ -569,20 +621,13 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 #ifdef CLB_ALIGN_TIMING
 		long long tc0 = clock64();
 #endif
-		int32_t* lastrow = reinterpret_cast<int32_t*>(A.scratch + A.lay.lastrow);
 		const bool small = edlib_column_bytes(el, cut) < EDLIB_TRACEBACK_LIMIT;
-		const int B = ((int)el + 63) >> 6;
-		uint64_t* hpv = reinterpret_cast<uint64_t*>(A.scratch + A.lay.hist);
-		uint64_t* hph = hpv + (size_t)B * cut;
-		A.sweep(e, (int)el, r, (int)cut, small ? hpv : nullptr, small ? hph : nullptr, (int)cut, lastrow, nullptr, nullptr, nullptr);
+		ulonglong2* hist = reinterpret_cast<ulonglong2*>(A.scratch + A.lay.hist);
+		// leftmost column with the minimal last-row score (edlib.cpp:660-674): followed by the lane of the last block during the sweep
+		const typename Aligner<GROUP>::SweepResult sw = small ? A.template sweep<true, true>(e, (int)el, r, (int)cut, hist, nullptr, nullptr, nullptr)
+			: A.template sweep<false, true>(e, (int)el, r, (int)cut, nullptr, nullptr, nullptr, nullptr);
 		A.gsync();
-		// leftmost column with the minimal last-row score (edlib.cpp:660-674)
-		int best = 0x7fffffff, end = 0;
-		for (int c = (int)gl; c < (int)cut; c += GROUP) { const int v = lastrow[c]; if (v < best) { best = v; end = c; } }
-		if (GROUP > 1) for (int d = GROUP / 2; d; d >>= 1) {
-			const int ob = __shfl_xor_sync(A.mask(), best, d, GROUP), oe = __shfl_xor_sync(A.mask(), end, d, GROUP);
-			if (ob < best || (ob == best && oe < end)) { best = ob; end = oe; }
-		}
+		const int best = sw.best, end = sw.end;
 		ref_end = (uint32_t)end;
 		const int T = end + 1;
 #ifdef CLB_ALIGN_TIMING
@@ -597,7 +642,7 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 			n_ops = (int)el;
 			A.gsync();
 		}
-		else if (small) n_ops = A.traceback(hpv, hph, (int)cut, (int)el, T, ops, A.scratch + A.lay.tmp);
+		else if (small) n_ops = A.traceback(hist, (int)cut, (int)el, T, ops, A.scratch + A.lay.tmp);
 		else n_ops = A.path(e, (int)el, r, T, best, ops);
 #ifdef CLB_ALIGN_TIMING
 		if (gl == 0 && el > 30000) printf("[task] el %u cut %u small %d: sweep %lld path %lld cycles, n_ops %d\n", el, cut, (int)small, tc1 - tc0, clock64() - tc1, n_ops);

@@ -15,7 +15,7 @@ struct EsTask {
 };
 
 template <int GROUP>
-__global__ void __launch_bounds__(128) k_edit_scripts(const EsTask* __restrict__ tasks, const uint32_t* __restrict__ list, uint32_t n_list,
+__global__ void __launch_bounds__(ALIGN_THREADS) k_edit_scripts(const EsTask* __restrict__ tasks, const uint32_t* __restrict__ list, uint32_t n_list,
 	const uint8_t* __restrict__ seqs, char* __restrict__ out, uint32_t* __restrict__ out_len, uint8_t* __restrict__ scratch)
 {
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -23,7 +23,9 @@ __global__ void __launch_bounds__(128) k_edit_scripts(const EsTask* __restrict__
 	if (slot >= n_list) return;                 // whole groups leave together
 	const uint32_t ti = list[slot];
 	const EsTask t = tasks[ti];
+	__shared__ uint64_t s_peq[4 * ALIGN_THREADS];
 	Aligner<GROUP> A;
+	A.peq = s_peq + threadIdx.x;
 	A.gl = threadIdx.x & (GROUP - 1);
 	const uint32_t lane = threadIdx.x & 31;
 	A.gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(uint32_t)(GROUP - 1)));

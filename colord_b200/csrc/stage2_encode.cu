@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_task_scatter(uint64_t t0, uint64_t t1, 
 }
 
 template <int GROUP>
-__global__ void __launch_bounds__(128) k_align(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
+__global__ void __launch_bounds__(ALIGN_THREADS) k_align(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
 	uint8_t* __restrict__ scratch, ReadStore R, const Node* __restrict__ nodes, const CandView* __restrict__ cviews, uint32_t c, char* __restrict__ esbuf)
 {
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(128) k_align(Task* __restrict__ tasks, uint64_
 	Task& T = tasks[t0 + list[slot]];
 	const Node N = nodes[T.node];
 	const CandView& V = cviews[(size_t)T.node * c + N.level];
+	__shared__ uint64_t s_peq[4 * ALIGN_THREADS];
 	Aligner<GROUP> A;
+	A.peq = s_peq + threadIdx.x;
 	A.gl = threadIdx.x & (GROUP - 1);
 #ifdef CLB_ALIGN_PHASES
 	const uint32_t gl = A.gl;
