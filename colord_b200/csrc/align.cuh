@@ -90,7 +90,7 @@ constexpr long long EDLIB_TRACEBACK_LIMIT = 1024 * 1024;
 // them (see Aligner::sweep): entry of block b, column c = strip * n_steps * G + (c + g) * Gs + g with G the lane group (<= 32),
 // strip = b / G, g = b % G, n_steps = T + G - 1, Gs = blocks of that strip — at most B * (T + 31) entries.
 struct AlignScratch {
-	unsigned long long hist, carry, ops, tmp, F, R, fin, stack, total;
+	unsigned long long hist, carry, res, ops, tmp, F, R, fin, stack, total;
 };
 __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long long t)
 {
@@ -102,6 +102,7 @@ __host__ __device__ inline AlignScratch align_scratch_layout(long long q, long l
 	// a Hirschberg leaf has 20 B T + 8 T < 1 MiB: 16 B (T + 31) < 1 MiB + 496 B
 	s.hist = take(big ? (unsigned long long)EDLIB_TRACEBACK_LIMIT + 4096 + 512ull * B : (unsigned long long)(16 * B * ((t > 0 ? t : 1) + 31)));
 	s.carry = take(2ull * 8 * ((unsigned long long)(t + 63) / 32 + 4));      // two arrays of 2-bit horizontal deltas, 32 per word
+	s.res = take(16);                                                      // what the forward kernel leaves for the backward kernel (last-row minimum)
 	s.ops = take((unsigned long long)(q + t + 2));
 	s.tmp = take((unsigned long long)(q + t + 2));
 	s.F = take(big ? 4ull * (q + 1) : 0);
@@ -123,6 +124,8 @@ __device__ __forceinline__ uint64_t compress_even(uint64_t x)
 	x = (x | (x >> 16)) & 0x00000000ffffffffULL;
 	return x;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 constexpr int ALIGN_THREADS = 128;          // CTA size of the kernels that own an Aligner (its shared match-vector table)
 
@@ -305,6 +308,9 @@ struct Aligner {
 				CLB_PH_COUNT(GROUP, 6, 1)
 				const int col = wj - (int)gl;
 				if (col >= 0) { const ulonglong2 e = hist[hist_at(b, col, Ts, B)]; wpv = e.x; wph = e.y; }
+				// the walk goes on to the left in this block or to the block above: those entries start their way from DRAM now
+				if (col - GROUP >= 0) prefetch_l2(&hist[hist_at(b, col - GROUP, Ts, B)]);
+				if (b > 0 && col >= 0) { prefetch_l2(&hist[hist_at(b - 1, col, Ts, B)]); if (col - GROUP >= 0) prefetch_l2(&hist[hist_at(b - 1, col - GROUP, Ts, B)]); }
 			}
 			const int src = wj - j;                       // lane holding column j
 			const int k = (int)gl - src;                  // this lane holds column j - k
@@ -423,6 +429,11 @@ struct Aligner {
 		}
 		return n_ops;
 	}
+
+	// the two halves of leaf() for the split kernels (Q, T > 0): sweep with history / traceback on it
+	template <class V>
+	__device__ void leaf_fwd(V rows, int Q, V cols, int T) const { sweep<true, false>(rows, Q, cols, T, reinterpret_cast<ulonglong2*>(scratch + lay.hist), nullptr, nullptr, nullptr); }
+	__device__ int leaf_back(int Q, int T, uint8_t* out, uint8_t* tmp) const { return traceback(reinterpret_cast<const ulonglong2*>(scratch + lay.hist), T, Q, T, out, tmp); }
 
 	// stored-column traceback of a problem below edlib's 1 MiB limit
 	template <class V>
@@ -578,11 +589,15 @@ __host__ __device__ inline void align_task_dims(uint32_t rl, uint32_t el, uint32
 
 // lead_out != nullptr: the 'D' run that precedes a left flank's script (the reference symbols left of the aligned window)
 // is not written; its length is returned through *lead_out instead and the returned length excludes it.
-template <int GROUP, class V>
+// PHASE 0: the whole task.  PHASE 1 / 2: the task in two kernels (k_align_fwd / k_align_back) for problems below edlib's traceback
+// limit — 1 runs the sweep and leaves its history (and the last-row minimum of a flank) in the scratch, 2 walks back through it
+// and writes the script; the host sends problems above the limit (Hirschberg, sweeps and walks interleaved) to PHASE 0.
+template <int GROUP, int PHASE = 0, class V>
 __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl, V enc, uint32_t el, uint32_t kind, char* out, uint32_t* lead_out = nullptr)
 {
 	if (lead_out) *lead_out = 0;
 	const uint32_t gl = A.gl;
+	int* const res = reinterpret_cast<int*>(A.scratch + A.lay.res);
 	if (rl == 0 || el == 0) {      // edit_script.h:247-266
 		if (gl == 0) {
 			if (rl == 0) for (uint32_t i = 0; i < el; ++i) out[i] = "ACGT"[enc[i]];
@@ -598,7 +613,9 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		// NW, rows = ref, cols = enc: UP = 'D', LEFT = insertion
 		int best;
 		const bool small = edlib_column_bytes(rl, el) < EDLIB_TRACEBACK_LIMIT;
-		if (small) n_ops = A.leaf(ref, (int)rl, enc, (int)el, ops, A.scratch + A.lay.tmp);
+		if (PHASE == 1) { if (small) A.leaf_fwd(ref, (int)rl, enc, (int)el); return 0; }
+		if (small && PHASE == 2) n_ops = A.leaf_back((int)rl, (int)el, ops, A.scratch + A.lay.tmp);
+		else if (small) n_ops = A.leaf(ref, (int)rl, enc, (int)el, ops, A.scratch + A.lay.tmp);
 		else {
 			best = A.template sweep<false, true>(ref, (int)rl, enc, (int)el, nullptr, nullptr, nullptr, nullptr).score;
 			A.gsync();
@@ -615,7 +632,9 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 	bool rows_ref;
 	if (cut < 2 || el < 2) {       // edit_script.h:336-343: global alignment of the (cut) ref against enc, rows = ref
 		rows_ref = true; ref_end = cut - 1;
-		n_ops = A.leaf(r, (int)cut, e, (int)el, ops, A.scratch + A.lay.tmp);
+		if (PHASE == 1) { A.leaf_fwd(r, (int)cut, e, (int)el); return 0; }
+		if (PHASE == 2) n_ops = A.leaf_back((int)cut, (int)el, ops, A.scratch + A.lay.tmp);
+		else n_ops = A.leaf(r, (int)cut, e, (int)el, ops, A.scratch + A.lay.tmp);
 	} else {
 		rows_ref = false;
 #ifdef CLB_ALIGN_TIMING
@@ -624,8 +643,12 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 		const bool small = edlib_column_bytes(el, cut) < EDLIB_TRACEBACK_LIMIT;
 		ulonglong2* hist = reinterpret_cast<ulonglong2*>(A.scratch + A.lay.hist);
 		// leftmost column with the minimal last-row score (edlib.cpp:660-674): followed by the lane of the last block during the sweep
-		const typename Aligner<GROUP>::SweepResult sw = small ? A.template sweep<true, true>(e, (int)el, r, (int)cut, hist, nullptr, nullptr, nullptr)
+		if (!small && PHASE == 1) return 0;
+		typename Aligner<GROUP>::SweepResult sw{0, 0, 0};
+		if (small && PHASE == 2) { sw.best = res[0]; sw.end = res[1]; }
+		else sw = small ? A.template sweep<true, true>(e, (int)el, r, (int)cut, hist, nullptr, nullptr, nullptr)
 			: A.template sweep<false, true>(e, (int)el, r, (int)cut, nullptr, nullptr, nullptr, nullptr);
+		if (PHASE == 1) { if (gl == 0) { res[0] = sw.best; res[1] = sw.end; } return 0; }
 		A.gsync();
 		const int best = sw.best, end = sw.end;
 		ref_end = (uint32_t)end;

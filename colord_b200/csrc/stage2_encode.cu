@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes
 
 // bins: lane-group class (1/2/4/8/16 lanes: rows within a factor of two) x log2(columns); the 32-lane class, whose row count is
 // open-ended, is split by log2(rows) as well so that the parts of one launch cost about the same
-constexpr int N_TBIN = 16, N_QBIN = 8, N_SMALL = 5, N_BINS = N_TBIN * N_SMALL + N_TBIN * N_QBIN;
+// problems above edlib's traceback limit (Hirschberg: sweeps and walks interleaved) have bins of their own after those: they run in
+// the one-kernel form on whole warps, everything else as a forward and a backward kernel
+constexpr int N_TBIN = 16, N_QBIN = 8, N_SMALL = 5, N_SPLIT_BINS = N_TBIN * N_SMALL + N_TBIN * N_QBIN, N_BINS = N_SPLIT_BINS + N_TBIN * N_QBIN;
 constexpr int N_ALIGN_STREAMS = 16;
 struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; unsigned long long sumq[N_BINS], sumt[N_BINS], sumqt[N_BINS]; };
 
@@ -116,7 +118,9 @@ __global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks,
 	long long q, tt;
 	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
 	const int gc = gclass_of(q), tb = min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
-	const int b = gc < N_SMALL ? gc * N_TBIN + tb : N_SMALL * N_TBIN + min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 10)) * N_TBIN + tb;
+	const bool big = edlib_column_bytes(q, tt) >= EDLIB_TRACEBACK_LIMIT;
+	const int qb = min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 10)) * N_TBIN + tb;
+	const int b = big ? N_SPLIT_BINS + qb : gc < N_SMALL ? gc * N_TBIN + tb : N_SMALL * N_TBIN + qb;
 	bin_of[t - t0] = (uint32_t)b;
 	atomicAdd(&bins->cnt[b], 1u);
 	atomicMax(&bins->maxq[b], (unsigned int)q);
@@ -132,8 +136,10 @@ __global__ void __launch_bounds__(256) k_task_scatter(uint64_t t0, uint64_t t1, 
 	list[bins->base[b] + atomicAdd(&bins->fill[b], 1u)] = (uint32_t)(t - t0);
 }
 
-template <int GROUP>
-__global__ void __launch_bounds__(ALIGN_THREADS) k_align(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
+// PHASE 0: whole tasks; 1: forward sweep with history; 2: traceback + script (see edit_script_task).  The backward kernel is
+// bound by the latency of its walk through the history (DRAM), so it is compiled for twice the resident warps.
+template <int GROUP, int PHASE>
+__global__ void __launch_bounds__(ALIGN_THREADS, PHASE == 2 ? 6 : PHASE == 1 ? 5 : 4) k_align(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
 	uint8_t* __restrict__ scratch, ReadStore R, const Node* __restrict__ nodes, const CandView* __restrict__ cviews, uint32_t c, char* __restrict__ esbuf)
 {
 	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,8 +164,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS) k_align(Task* __restrict__ task
 	A.lay = align_scratch_layout(q, tt);
 	const PackedView ref = ref_view(R, V.ref_id, V.rev, T.ref_start), enc = enc_view(R, N.read, T.enc_start);
 	uint32_t lead = 0;
-	const uint32_t n = edit_script_task<GROUP>(A, ref, T.rl, enc, T.el, T.kind, esbuf + T.es_off, &lead);
-	if (A.gl == 0) { T.es_len = n; T.lead = lead; }
+	const uint32_t n = edit_script_task<GROUP, PHASE>(A, ref, T.rl, enc, T.el, T.kind, esbuf + T.es_off, &lead);
+	if (PHASE != 1 && A.gl == 0) { T.es_len = n; T.lead = lead; }
 	CLB_PH_END(GROUP, 3)
 	CLB_PH_COUNT(GROUP, 7, 1)
 }
@@ -816,6 +822,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
 		const uint64_t per_wave = std::max<uint64_t>(1, slice / stride);
 		const int g = b < N_SMALL * N_TBIN ? 1 << (b / N_TBIN) : 32;
+		const bool split = b < N_SPLIT_BINS && !std::getenv("CLB_ALIGN_ONE_KERNEL");
 		const int si = rr++ % n_str;
 		cudaStream_t ls = bin_prof ? s : c->s2_streams[si];
 		uint8_t* scratch = c->s2_scratch.p + (uint64_t)si * slice;
@@ -824,14 +831,12 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 			const uint32_t* list = d_list + hb.base[b] + w0;
 			const uint32_t threads = 128;
 			const uint32_t grid = (uint32_t)(((uint64_t)m * g + threads - 1) / threads);
-			switch (g) {
-			case 1: k_align<1><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 2: k_align<2><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 4: k_align<4><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 8: k_align<8><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			case 16: k_align<16><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			default: k_align<32><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf); break;
-			}
+#define CLB_ALIGN_LAUNCH(G, PH) k_align<G, PH><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf)
+#define CLB_ALIGN_GROUPS(PH) switch (g) { case 1: CLB_ALIGN_LAUNCH(1, PH); break; case 2: CLB_ALIGN_LAUNCH(2, PH); break; case 4: CLB_ALIGN_LAUNCH(4, PH); break; \
+	case 8: CLB_ALIGN_LAUNCH(8, PH); break; case 16: CLB_ALIGN_LAUNCH(16, PH); break; default: CLB_ALIGN_LAUNCH(32, PH); break; }
+			if (split) { CLB_ALIGN_GROUPS(1) CLB_ALIGN_GROUPS(2) ++c->launches; }
+			else if (b < N_SPLIT_BINS) { CLB_ALIGN_GROUPS(0) }
+			else CLB_ALIGN_LAUNCH(32, 0);
 			CLB_LAUNCH_CHECK(c, "k_align");
 		}
 		if (bin_prof) {
