@@ -18,7 +18,7 @@ except Exception as e:
 PY
 CLB_S2_TRACE=1 BENCH_PHASES=1 timeout 600 python bench.py --gbases 6 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > $O/trace.json 2> $O/trace.err
 grep -E "s3q|s3d|\[phase\]" $O/trace.err | tail -40
-timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base function -k k_align --launch-skip 180 --launch-count 1 -o $O/k_align_fwd32 -f \
+timeout 900 ncu --set full --import-source on --clock-control none --kernel-name-base function -k k_align --launch-skip 176 --launch-count 3 -o $O/k_align_fwd32 -f \
   python bench.py --gbases 1 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > $O/ncu_bench.json 2> $O/ncu_bench.err
 ncu -i $O/k_align_fwd32.ncu-rep --page raw --csv > $O/k_align_fwd32_raw.csv 2>/dev/null
 ncu -i $O/k_align_fwd32.ncu-rep --page source --csv --print-source cuda,sass > $O/k_align_fwd32_source.csv 2>/dev/null
