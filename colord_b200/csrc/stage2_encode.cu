@@ -17,6 +17,7 @@
 #include "ctx.h"
 #include "stage2.h"
 #include "align.cuh"
+#include "align_back.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -168,6 +169,25 @@ __global__ void __launch_bounds__(ALIGN_THREADS, PHASE == 2 ? 6 : PHASE == 1 ? 5
 	if (PHASE != 1 && A.gl == 0) { T.es_len = n; T.lead = lead; }
 	CLB_PH_END(GROUP, 3)
 	CLB_PH_COUNT(GROUP, 7, 1)
+}
+
+// The backward half of the tasks of a bin, one thread per task (align_back.cuh); lg = log2 of the forward kernel's lane group.
+__global__ void __launch_bounds__(ALIGN_THREADS) k_align_back(Task* __restrict__ tasks, uint64_t t0, const uint32_t* __restrict__ list, uint32_t n_list, uint64_t stride,
+	uint8_t* __restrict__ scratch, ReadStore R, const Node* __restrict__ nodes, const CandView* __restrict__ cviews, uint32_t c, char* __restrict__ esbuf, int lg)
+{
+	__shared__ ulonglong2 s_ring[BACK_RING * ALIGN_THREADS];
+	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+	if (slot >= n_list) return;
+	Task& T = tasks[t0 + list[slot]];
+	const Node N = nodes[T.node];
+	const CandView& V = cviews[(size_t)T.node * c + N.level];
+	long long q, tt;
+	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
+	const AlignScratch lay = align_scratch_layout(q, tt);
+	const PackedView ref = ref_view(R, V.ref_id, V.rev, T.ref_start), enc = enc_view(R, N.read, T.enc_start);
+	uint32_t lead = 0;
+	const uint32_t n = edit_script_back(scratch + (uint64_t)slot * stride, lay, lg, s_ring + threadIdx.x, ref, T.rl, enc, T.el, T.kind, esbuf + T.es_off, &lead);
+	T.es_len = n; T.lead = lead;
 }
 
 // ------------------------------------------------------------------------------------------------ decisions
@@ -834,7 +854,12 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 #define CLB_ALIGN_LAUNCH(G, PH) k_align<G, PH><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf)
 #define CLB_ALIGN_GROUPS(PH) switch (g) { case 1: CLB_ALIGN_LAUNCH(1, PH); break; case 2: CLB_ALIGN_LAUNCH(2, PH); break; case 4: CLB_ALIGN_LAUNCH(4, PH); break; \
 	case 8: CLB_ALIGN_LAUNCH(8, PH); break; case 16: CLB_ALIGN_LAUNCH(16, PH); break; default: CLB_ALIGN_LAUNCH(32, PH); break; }
-			if (split) { CLB_ALIGN_GROUPS(1) CLB_ALIGN_GROUPS(2) ++c->launches; }
+			if (split && std::getenv("CLB_ALIGN_GROUP_BACK")) { CLB_ALIGN_GROUPS(1) CLB_ALIGN_GROUPS(2) ++c->launches; }
+			else if (split) {
+				CLB_ALIGN_GROUPS(1)
+				k_align_back<<<(m + ALIGN_THREADS - 1) / ALIGN_THREADS, ALIGN_THREADS, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf, ilog2_u32((uint32_t)g));
+				++c->launches;
+			}
 			else if (b < N_SPLIT_BINS) { CLB_ALIGN_GROUPS(0) }
 			else CLB_ALIGN_LAUNCH(32, 0);
 			CLB_LAUNCH_CHECK(c, "k_align");
