@@ -150,6 +150,9 @@ __device__ uint32_t edit_script_back(uint8_t* scratch, const AlignScratch& lay, 
 			const ulonglong2 e = ring[(j & (BACK_RING - 1)) * nthr];
 			const bool up = (e.x >> bit) & 1, left = !up && ((e.y >> bit) & 1);
 			emit(up ? 1u : left ? 2u : 0u);
+			if (bit == 8 && b > 0 && !left) {                      // eight rows below the block above: its entries around the crossing start from DRAM
+				for (int k = 1; k <= 24; ++k) if (j - k >= 0) prefetch_l2(entry(b - 1, j - k));
+			}
 			if (!left) --I;
 			if (!up) --J;
 			if (!left && bit == 0 && I > 0 && J > 0) {           // into the block above: its columns replace the ring

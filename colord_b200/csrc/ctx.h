@@ -163,6 +163,7 @@ struct clb_ctx {
 	clb::DevBuf<uint8_t> s2_arena;   // pair / anchor arena of the current batch
 	clb::DevBuf<uint8_t> s2_store;   // anchors of the chosen candidates of all reads
 	clb::DevBuf<uint8_t> s2_scratch; // alignment scratch of the current waves
+	uint64_t s2_budget = 0;          // its size for this job (set by the first level from the free memory)
 	// per-batch scratch of the anchor search, kept from batch to batch (measured: allocating and freeing these blocks in every
 	// batch left 3.5 s of a 13 s step to the driver — single batches of 0.3-1.2 s instead of 0.07 s)
 	clb::DevBuf<uint8_t> s2_segs; clb::DevBuf<uint32_t> s2_gtab, s2_gbloom;

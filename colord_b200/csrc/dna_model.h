@@ -58,24 +58,6 @@ CLB_D uint32_t ref_sym(const DnaReads& R, const OrientedRef& o, int pos)
 }
 CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[R.first + r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
 
-// The events of one tuple wait in a small queue and go to the sink in ONE place, the end of the tuple's iteration: the lanes of a
-// warp sit at different tuple types, and with the sink inlined at every event they would never meet again for the expensive part
-// (table lookup + coder arithmetic or the counting atomic).  Order is kept; a tuple with more events than the queue holds (a very
-// long anchor or skip) hands the surplus over directly.
-template <class Sink>
-struct EventQueue {
-	static constexpr uint32_t CAP = 12;
-	Sink& s; uint64_t q[CAP]; uint32_t n = 0;
-	__device__ explicit EventQueue(Sink& sink) : s(sink) {}
-	__device__ __forceinline__ void put(uint32_t f, uint64_t ctx, uint32_t sym)
-	{
-		if (n == CAP) overflow();
-		q[n++] = (ctx << 12) | ((uint64_t)sym << 4) | f;                   // contexts are folded to <= 24 bits by the tables; families < 16, symbols < 256
-	}
-	__device__ __noinline__ void overflow() { drain(); }
-	__device__ __forceinline__ void drain() { for (uint32_t i = 0; i < n; ++i) { const uint64_t e = q[i]; s.put((uint32_t)e & 15u, e >> 12, (uint32_t)(e >> 4) & 255u); } n = 0; }
-};
-
 // The events of read r, in coding order.  ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).
 // sink.put(family, context, symbol).  EXACT: the events as the reference's adaptive coder sees them (stage3_exact.cu) — the symbols a
 // tuple type / substitution cannot be are handed over as a mask (EncodeExcluding: dna_coder.cpp:651-717, :889-922; sink.putx) and the
@@ -107,23 +89,21 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 	if (flag == 0) { for (uint64_t p = 1; p < tn; ++p) { const uint32_t s = t[p] & 15; sink.put(F_SYM, ctx_symbol << 2, s); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; } return; }
 	if (flag == 1) { for (uint64_t p = 1; p < tn; ++p) { const uint32_t s = t[p] & 15; sink.put(F_SYMN, ctx_symbol, s); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; } return; }
 
-	EventQueue<Sink> Q(sink);
-	auto ev = [&](uint32_t f, uint64_t ctx, uint32_t sym) { if constexpr (EXACT) sink.put(f, ctx, sym); else Q.put(f, ctx, sym); };
 	auto be32 = [&](uint64_t p) { return ((uint32_t)t[p] << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; };
 	auto put_read_id = [&](uint32_t id) {
 		const int n = (int)no_bytes_of(R.first + r);      // reference ids stay below the read's index in the store
-		for (int i = n - 1; i >= 0; --i) { const uint64_t add = (i == n - 2) ? ((id >> (8 * (n - 1))) & 0xff) : 0; ev(F_READID, (uint64_t)i + (add << 3), (id >> (8 * i)) & 0xff); }
+		for (int i = n - 1; i >= 0; --i) { const uint64_t add = (i == n - 2) ? ((id >> (8 * (n - 1))) & 0xff) : 0; sink.put(F_READID, (uint64_t)i + (add << 3), (id >> (8 * i)) & 0xff); }
 	};
 	uint32_t seen_id[34]; uint32_t n_seen = 0; uint64_t ctx_rev = 0xf;         // uo_rev_comp of this read
 	auto put_rev = [&](uint32_t id, uint32_t rev) {
 		for (uint32_t k = 0; k < n_seen; ++k) if (seen_id[k] == id) return;
-		ev(F_REV, ctx_rev, rev);
+		sink.put(F_REV, ctx_rev, rev);
 		if (n_seen < 34) seen_id[n_seen++] = id;
 		ctx_rev = ((ctx_rev << 2) + rev) & 0xf;
 	};
 	auto put_skip = [&](uint32_t len, bool local) {
-		if (local) { for (uint32_t part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 255) { ev(F_SKIPL, pc, len); break; } ev(F_SKIPL, pc, 255); len -= 254; } }
-		else { uint32_t enc = 0; for (int i = 3; i >= 0; --i) { const uint32_t x = (len >> (8 * i)) & 0xff; ev(F_SKIPD, (uint64_t)i * 64 + ilog2_bits(enc), x); enc = (enc << 8) + x; } }
+		if (local) { for (uint32_t part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 255) { sink.put(F_SKIPL, pc, len); break; } sink.put(F_SKIPL, pc, 255); len -= 254; } }
+		else { uint32_t enc = 0; for (int i = 3; i >= 0; --i) { const uint32_t x = (len >> (8 * i)) & 0xff; sink.put(F_SKIPD, (uint64_t)i * 64 + ilog2_bits(enc), x); enc = (enc << 8) + x; } }
 	};
 	const uint32_t main_id = be32(1), main_rev = t[0] & 15;
 	put_read_id(main_id);
@@ -135,8 +115,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 	bool is_main = true;
 	uint32_t last_tuple = 255;
 	const uint32_t sh_t = 3 * M.n_t;
-	for (uint64_t p = 5;;) {
-		if (p >= tn) { if constexpr (!EXACT) Q.drain(); break; }          // (the events of the read's head when no tuple follows)
+	for (uint64_t p = 5; p < tn;) {
 		const uint32_t ty = t[p] >> 4, v1 = t[p] & 15;
 		uint32_t v2 = 0;
 		if (ty == 4 || ty == 5) { v2 = ((uint32_t)v1 << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; p += 4; }
@@ -151,7 +130,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 				const uint32_t excl = last_tuple == 2 ? 1u << 4 : last_tuple == 1 ? 1u << 5 : last_tuple == 4 ? (1u << 4) | (1u << 2)
 					: last_tuple == 5 ? (1u << 1) | (1u << 5) : (last_tuple == 7 || last_tuple == 6) ? (1u << 6) | (1u << 7) : 0u;
 				sink.putx(F_TUPLE, ctx, ty, excl);
-			} else ev(F_TUPLE, ctx, ty);
+			} else sink.put(F_TUPLE, ctx, ty);
 			ctx_tuple = ((ctx_tuple << 3) + ty) & mask_t;
 		}
 		if (ty == 6) {               // alt_id: v2 = id, v1 = reverse-complement flag
@@ -160,8 +139,8 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			for (uint32_t k = 0; k < n_alt; ++k) if (alt_ids[k] == v2) { idx = (int)k; break; }
 			if (n_alt == 0) put_read_id(v2);
 			else {
-				ev(F_SEEN, n_alt, idx >= 0);
-				if (idx < 0) put_read_id(v2); else ev(F_SHORT, n_alt, (uint32_t)idx);
+				sink.put(F_SEEN, n_alt, idx >= 0);
+				if (idx < 0) put_read_id(v2); else sink.put(F_SHORT, n_alt, (uint32_t)idx);
 			}
 			if (idx < 0 && n_alt < 32) { idx = (int)n_alt; alt_ids[n_alt] = v2; alt_revs[n_alt] = v1; alt_saved[n_alt] = 0; ++n_alt; }
 			cur_alt = idx;
@@ -169,7 +148,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			alt_ref = oriented(R, v2, idx >= 0 ? alt_revs[idx] : v1);
 			alt_pos = 0; is_main = false; delta = 0;
 		} else if (ty == 4) {        // anchor
-			for (uint32_t len = v2, part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 23) { ev(F_ANCHOR, pc, len); break; } ev(F_ANCHOR, pc, 23); len -= 22; }
+			for (uint32_t len = v2, part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 23) { sink.put(F_ANCHOR, pc, len); break; } sink.put(F_ANCHOR, pc, 23); len -= 22; }
 			int& pos = is_main ? ref_pos : alt_pos;
 			pos += (int)v2;
 			const OrientedRef& o = is_main ? main_ref : alt_ref;
@@ -185,7 +164,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			else { ctx += (ctx_symbol & 0x3ff) << sh; sh += 10; if (M.level >= 3) { ctx += (uint64_t)(((ctx_symbol >> 10) & 3) == ((ctx_symbol >> 8) & 3)) << sh; ++sh; } }
 			ctx += (uint64_t)rsym << sh; sh += 2;
 			ctx += (ctx_tuple & 0777) << sh;
-			ev(F_SYM, ctx, v1);
+			sink.put(F_SYM, ctx, v1);
 			ctx_symbol = ((ctx_symbol << 2) + v1) & mask_s;
 			++delta;
 		} else if (ty == 1) {        // deletion
@@ -199,7 +178,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			if (M.level >= 3) { ctx += (uint64_t)(((ctx_symbol >> 6) & 3) == ((ctx_symbol >> 4) & 3)) << sh; ++sh; }
 			ctx += (uint64_t)rsym << sh; sh += 2;
 			ctx += (ctx_tuple & 07777) << sh;
-			if constexpr (EXACT) sink.putx(F_SYM, ctx, symbol, 1u << b); else ev(F_SYM, ctx, symbol);
+			if constexpr (EXACT) sink.putx(F_SYM, ctx, symbol, 1u << b); else sink.put(F_SYM, ctx, symbol);
 			ctx_symbol = ((ctx_symbol << 2) + symbol) & mask_s;
 			is_main ? ++ref_pos : ++alt_pos;
 		} else if (ty == 5) {        // skip (:166-206)
@@ -217,7 +196,6 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			delta = 0;
 		}
 		last_tuple = ty;
-		if constexpr (!EXACT) Q.drain();
 	}
 }
 

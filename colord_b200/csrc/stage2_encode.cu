@@ -94,12 +94,15 @@ __global__ void __launch_bounds__(128) k_tasks(const Node* nodes_in, Node* nodes
 // open-ended, is split by log2(rows) as well so that the parts of one launch cost about the same
 // problems above edlib's traceback limit (Hirschberg: sweeps and walks interleaved) have bins of their own after those: they run in
 // the one-kernel form on whole warps, everything else as a forward and a backward kernel
-constexpr int N_TBIN = 16, N_QBIN = 8, N_SMALL = 5, N_SPLIT_BINS = N_TBIN * N_SMALL + N_TBIN * N_QBIN, N_BINS = N_SPLIT_BINS + N_TBIN * N_QBIN;
+// Bins are half octaves of the column count and (above two blocks) of the row count: the scratch slot of a bin's wave is sized by its
+// largest task, so narrow bins put more tasks into the same scratch (the backward kernel wants many: it is one thread per task).
+constexpr int N_TBIN = 40, N_QBIN = 16, N_SMALL = 5, N_SMALL_BINS = 2 * N_SMALL * N_TBIN, N_SPLIT_BINS = N_SMALL_BINS + N_TBIN * N_QBIN, N_BINS = N_SPLIT_BINS + N_TBIN * N_QBIN;
 constexpr int N_ALIGN_STREAMS = 16;
 struct BinStats { unsigned int cnt[N_BINS], maxq[N_BINS], maxt[N_BINS], fill[N_BINS], base[N_BINS]; unsigned long long sumq[N_BINS], sumt[N_BINS], sumqt[N_BINS]; };
 
 CLB_HD int gclass_of(long long q) { const long long B = (q + 63) / 64; return B <= 1 ? 0 : B <= 2 ? 1 : B <= 4 ? 2 : B <= 8 ? 3 : B <= 16 ? 4 : 5; }
 CLB_HD int ilog2_u32(uint32_t x) { int r = 0; while (x >>= 1) ++r; return r; }
+CLB_HD int hlog2_u32(uint32_t x) { const int l = ilog2_u32(x); return 2 * l + (l > 0 ? (int)((x >> (l - 1)) & 1u) : 0); }      // half octaves
 
 // Parts with an empty side need no alignment (edit_script.h:247-266): el == 0 -> 'D' x rl (kept as `lead`), rl == 0 -> the
 // part's bases as insertions.  Everything else is binned.
@@ -118,10 +121,12 @@ __global__ void __launch_bounds__(256) k_task_classify(Task* __restrict__ tasks,
 	}
 	long long q, tt;
 	align_task_dims(T.rl, T.el, T.kind, &q, &tt);
-	const int gc = gclass_of(q), tb = min(N_TBIN - 1, ilog2_u32((uint32_t)tt));
+	const int gc = gclass_of(q), tb = min(N_TBIN - 1, hlog2_u32((uint32_t)tt));
+	const long long Bq = (q + 63) / 64;
+	const int qs = gc >= 2 && Bq > (3ll << (gc - 2)) ? 1 : 0;              // upper half of the class's block range
 	const bool big = edlib_column_bytes(q, tt) >= EDLIB_TRACEBACK_LIMIT;
-	const int qb = min(N_QBIN - 1, max(0, ilog2_u32((uint32_t)q) - 10)) * N_TBIN + tb;
-	const int b = big ? N_SPLIT_BINS + qb : gc < N_SMALL ? gc * N_TBIN + tb : N_SMALL * N_TBIN + qb;
+	const int qb = min(N_QBIN - 1, max(0, hlog2_u32((uint32_t)q) - 20)) * N_TBIN + tb;
+	const int b = big ? N_SPLIT_BINS + qb : gc < N_SMALL ? (2 * gc + qs) * N_TBIN + tb : N_SMALL_BINS + qb;
 	bin_of[t - t0] = (uint32_t)b;
 	atomicAdd(&bins->cnt[b], 1u);
 	atomicMax(&bins->maxq[b], (unsigned int)q);
@@ -808,7 +813,17 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	CLB_TIMED(c, K_ENCODE, (k_task_scatter<<<blocks, 256, 0, s>>>(t0, t1, d_bin_of, d_bins, d_list)));
 	CLB_LAUNCH_CHECK(c, "k_task_scatter");
 	const char* env_budget = std::getenv("CLB_ALIGN_SCRATCH_MB");
-	const uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 16ull << 30;
+	uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 16ull << 30;
+	if (!env_budget && c->s2_budget) budget = c->s2_budget;
+	else if (!env_budget) {      // as much as is free beyond a reserve for the later levels and stage 3, within 16 .. 40 GiB; fixed for the job
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+			const uint64_t have = (uint64_t)free_b + c->s2_scratch.cap;
+			const uint64_t reserve = 28ull << 30;
+			budget = std::min<uint64_t>(40ull << 30, std::max<uint64_t>(budget, have > reserve ? have - reserve : 0));
+		}
+		c->s2_budget = budget;
+	}
 	const bool bin_prof = std::getenv("CLB_ALIGN_PROFILE") != nullptr;
 	// bins run concurrently on a few streams (each with its own slice of the scratch) so that the tail of one bin
 	// overlaps the bulk of another; the per-bin profile serialises them on the main stream instead
@@ -841,7 +856,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 		if (bin_prof) cudaEventRecord(pe0, s);
 		const uint64_t stride = (align_scratch_layout(hb.maxq[b], hb.maxt[b]).total + 63) & ~63ull;
 		const uint64_t per_wave = std::max<uint64_t>(1, slice / stride);
-		const int g = b < N_SMALL * N_TBIN ? 1 << (b / N_TBIN) : 32;
+		const int g = b < N_SMALL_BINS ? 1 << (b / (2 * N_TBIN)) : 32;
 		const bool split = b < N_SPLIT_BINS && !std::getenv("CLB_ALIGN_ONE_KERNEL");
 		const int si = rr++ % n_str;
 		cudaStream_t ls = bin_prof ? s : c->s2_streams[si];
@@ -1188,7 +1203,7 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	}
 	CLB_CUDA(c, cudaMemcpyAsync(c->es_off + n, &c->es_total, sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_budget = 0; c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	tr.mark("encode: release");
 	c->enc_done = true;
@@ -1200,7 +1215,7 @@ void s2_free(clb_ctx* c)
 	for (int i = 0; i < 16; ++i) { if (c->s2_streams[i]) cudaStreamDestroy(c->s2_streams[i]); if (c->s2_join[i]) cudaEventDestroy(c->s2_join[i]); c->s2_streams[i] = nullptr; c->s2_join[i] = nullptr; }
 	if (c->s2_fork) cudaEventDestroy(c->s2_fork);
 	c->s2_fork = nullptr;
-	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
+	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_budget = 0; c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	if (c->es_off) dev_free(c->es_off, c->stream);
 	if (c->d_ref_to_read) dev_free(c->d_ref_to_read, c->stream);
