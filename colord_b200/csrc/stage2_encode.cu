@@ -819,7 +819,7 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 		size_t free_b = 0, total_b = 0;
 		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
 			const uint64_t have = (uint64_t)free_b + c->s2_scratch.cap;
-			const uint64_t reserve = 28ull << 30;
+			const uint64_t reserve = 60ull << 30;          // the tuples grow by reallocation (old + new alive), stage 3 wants a temp of their size
 			budget = std::min<uint64_t>(40ull << 30, std::max<uint64_t>(budget, have > reserve ? have - reserve : 0));
 		}
 		c->s2_budget = budget;
