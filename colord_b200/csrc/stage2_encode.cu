@@ -869,7 +869,9 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 #define CLB_ALIGN_LAUNCH(G, PH) k_align<G, PH><<<grid, threads, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf)
 #define CLB_ALIGN_GROUPS(PH) switch (g) { case 1: CLB_ALIGN_LAUNCH(1, PH); break; case 2: CLB_ALIGN_LAUNCH(2, PH); break; case 4: CLB_ALIGN_LAUNCH(4, PH); break; \
 	case 8: CLB_ALIGN_LAUNCH(8, PH); break; case 16: CLB_ALIGN_LAUNCH(16, PH); break; default: CLB_ALIGN_LAUNCH(32, PH); break; }
-			if (split && std::getenv("CLB_ALIGN_GROUP_BACK")) { CLB_ALIGN_GROUPS(1) CLB_ALIGN_GROUPS(2) ++c->launches; }
+			// the backward half: the lane-group kernel; the thread-per-task kernel (align_back.cuh) needs about 10^5 tasks in flight to hide
+			// its DRAM round trips, which the scratch of a 25-Gbase job does not hold (measured: k_align 4 194 ms against 2 071 ms)
+			if (split && !std::getenv("CLB_ALIGN_THREAD_BACK")) { CLB_ALIGN_GROUPS(1) CLB_ALIGN_GROUPS(2) ++c->launches; }
 			else if (split) {
 				CLB_ALIGN_GROUPS(1)
 				k_align_back<<<(m + ALIGN_THREADS - 1) / ALIGN_THREADS, ALIGN_THREADS, 0, ls>>>(d_tasks, t0, list, m, stride, scratch, R, d_nodes, d_cviews, P.c, d_esbuf, ilog2_u32((uint32_t)g));

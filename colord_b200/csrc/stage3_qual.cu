@@ -178,9 +178,11 @@ __global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 			const uint8_t* q = a.quals + a.qoff[r];
 			const uint8_t* fl = a.flags ? a.flags + a.qoff[r] : nullptr;
 			const uint32_t ns = 2 * P.nb, T = ns + n;
-			for (long long g = (long long)((T - 1) >> 5); g >= 0; --g) {
+			// the table entry of a symbol depends on the input alone: the entries of the NEXT step are fetched before the coder's
+			// arithmetic of this one, so that their way from the L2 lies beside it instead of in front of it
+			auto fetch = [&](long long g, bool& valid) -> uint4 {
 				const uint32_t k = (uint32_t)(g << 5) + t;
-				const bool valid = k < T;
+				valid = k < T;
 				uint4 fc = make_uint4(0, 0, 0, 1);
 				if (valid) {
 					if (k < ns) {                                    // bin k / 2: high byte of mean * 256 under the bin's table, then the low byte (uniform)
@@ -191,11 +193,18 @@ __global__ void __launch_bounds__(128) k_q_encode(QArgs a, QEnc e)
 						fc = a.tab[(size_t)q_context(a, rs, n, q, fl, j) * P.nb + q_bin(P, q[j] - 33u)];
 					}
 				}
+				return fc;
+			};
+			bool valid, valid_next = false;
+			uint4 fc = fetch((long long)((T - 1) >> 5), valid), fc_next = fc;
+			for (long long g = (long long)((T - 1) >> 5); g >= 0; --g) {
+				if (g > 0) fc_next = fetch(g - 1, valid_next);
 				const bool emit = valid && x >= (fc.w << 19);       // f <= 2^12: no overflow
 				const uint32_t m = __ballot_sync(FULL, emit);
 				if (emit) { w[nw + __popc(m & above)] = (uint16_t)x; x >>= 16; }
 				nw += __popc(m);
 				if (valid) { const uint32_t qq = __umulhi(x, fc.x) >> (fc.z >> 16); x = x + fc.y + qq * (fc.z & 0xffffu); }
+				fc = fc_next; valid = valid_next;
 			}
 		}
 	}
@@ -347,7 +356,8 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	CLB_CUDA(c, c->qs.reserve(hdr.size() + tot / 3 + (uint64_t)np * (4 + 4 * QB_LANES + 4 * QB_LANES * QB_STATES) + 1024, s, false));
 	CLB_CUDA(c, cudaMemcpyAsync(c->qs.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
 	uint64_t out_at = hdr.size();
-	const uint64_t chunk_syms = 1ull << 31;
+	uint64_t chunk_syms = 1ull << 31;       // more symbols per chunk = more warps in flight; the temp is 2 bytes per symbol
+	{ size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) while (chunk_syms < (1ull << 33) && 4 * chunk_syms + (16ull << 30) < free_b) chunk_syms <<= 1; }
 	uint16_t* d_tmp = nullptr; uint64_t tmp_cap = 0;      // one temp for all chunks (grown if a later chunk is larger)
 	for (uint32_t p0 = 0; p0 < np;) {
 		uint32_t p1 = p0; uint64_t syms = 0;
