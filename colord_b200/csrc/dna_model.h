@@ -49,103 +49,93 @@ struct DnaReads {                       // what the walk needs from the resident
 	const uint8_t* es; const uint64_t* es_off;
 	uint32_t first;                     // reads are numbered from the first non-context read: read r of the walk is read first + r of the store
 };
-struct OrientedRef { uint64_t start; uint32_t len; uint32_t rev; };
-CLB_D OrientedRef oriented(const DnaReads& R, uint32_t ref_id, uint32_t rev) { const uint32_t rr = R.ref_to_read[ref_id]; return OrientedRef{R.rd_start[rr], R.rd_len[rr], rev}; }
-CLB_D uint32_t ref_sym(const DnaReads& R, const OrientedRef& o, int pos)
+// A walk asks for the symbols of a reference read one after the other: the packed word it last touched stays in registers
+// (cw / cwi), so a load happens once per 32 bases instead of once per tuple.
+struct OrientedRef { uint64_t start; uint32_t len; uint32_t rev; uint64_t cw, cwi; };
+CLB_D OrientedRef oriented(const DnaReads& R, uint32_t ref_id, uint32_t rev) { const uint32_t rr = R.ref_to_read[ref_id]; return OrientedRef{R.rd_start[rr], R.rd_len[rr], rev, 0, ~0ull}; }
+CLB_D uint32_t ref_sym(const DnaReads& R, OrientedRef& o, int pos)
 {
 	if (pos < 0 || (uint32_t)pos >= o.len) return 255u;               // the guard byte of read_t
-	return o.rev ? 3u - base_at(R.pk, o.start + (o.len - 1 - (uint32_t)pos)) : base_at(R.pk, o.start + (uint32_t)pos);
+	const uint64_t a = o.rev ? o.start + (o.len - 1 - (uint32_t)pos) : o.start + (uint32_t)pos;
+	if ((a >> 5) != o.cwi) { o.cwi = a >> 5; o.cw = R.pk[a >> 5]; }
+	const uint32_t b = (uint32_t)(o.cw >> (62 - 2 * (a & 31))) & 3u;
+	return o.rev ? 3u - b : b;
 }
+// The tuple bytes of a read through a 16-byte window in registers: the walk reads them front to back, one load per 16 bytes
+// instead of one per byte (every coder lane streams through its own reads, far more lines than the L1 holds).
+struct TupleBytes {
+	const uint8_t* base; const uint4* cur; uint4 w;
+	__device__ explicit TupleBytes(const uint8_t* b) : base(b), cur(nullptr), w(make_uint4(0, 0, 0, 0)) {}
+	__device__ __forceinline__ uint32_t operator[](uint64_t p)
+	{
+		const uintptr_t a = reinterpret_cast<uintptr_t>(base + p);
+		const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);       // inside the tuple buffer: its start is aligned, its end padded
+		if (q != cur) { cur = q; w = *q; }
+		const uint32_t k = (uint32_t)(a & 15);
+		const uint32_t x = k < 8 ? (k < 4 ? w.x : w.y) : (k < 12 ? w.z : w.w);
+		return (x >> (8 * (k & 3))) & 0xffu;
+	}
+};
 CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[R.first + r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
 
-// The events of a read, in coding order, as a resumable walk: begin() codes the read's head (flag, length, and for an encoded read
-// its main reference read), every step() one tuple (or one symbol of a plain read).  The coder lanes of a warp sit in ONE loop
-// whose iterations are steps (k_d_encode), so they meet again after every tuple whatever reads they are in — nested per-read /
-// per-tuple loops would leave the lanes of a warp apart for good once their reads end at different times.
-// ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).  sink.put(family, context, symbol).
-// EXACT: the events as the reference's adaptive coder sees them (stage3_exact.cu) — the symbols a tuple type / substitution cannot
-// be are handed over as a mask (EncodeExcluding: dna_coder.cpp:651-717, :889-922; sink.putx) and the chunk index of an anchor /
-// local skip length is not capped.
-template <bool EXACT = false>
-struct DnaWalker {
-	const uint8_t* t; uint64_t tn, p; uint32_t flag, r;
-	uint64_t mask_s, mask_t, ctx_symbol, ctx_tuple, ctx_rev;
-	uint32_t sh_t, n_seen, n_alt, last_tuple;
-	int cur_alt, ref_pos, alt_pos, delta;
-	bool is_main;
-	OrientedRef main_ref, alt_ref;
-	uint32_t seen_id[34];                                       // uo_rev_comp of this read
-	uint32_t alt_ids[32], alt_revs[32]; int alt_saved[32];      // m_alt_ids / m_alt_read / m_alt_pos
+// The events of read r, in coding order.  ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).
+// sink.put(family, context, symbol).  EXACT: the events as the reference's adaptive coder sees them (stage3_exact.cu) — the symbols a
+// tuple type / substitution cannot be are handed over as a mask (EncodeExcluding: dna_coder.cpp:651-717, :889-922; sink.putx) and the
+// chunk index of an anchor / local skip length is not capped.
+template <bool EXACT = false, class Sink>
+__device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint32_t ctx_read_type, Sink& sink)
+{
+	TupleBytes t(R.es + R.es_off[R.first + r]);
+	const uint64_t tn = R.es_off[R.first + r + 1] - R.es_off[R.first + r];
+	uint32_t n_tuples = 0;
+	for (uint64_t p = 0; p < tn; ++n_tuples) { const uint32_t ty = t[p] >> 4; p += (ty == 4 || ty == 5) ? 4 : (ty == 6 || ty == 10) ? 5 : 1; }
+	const uint32_t flag = (t[0] >> 4) == 9 ? 0u : (t[0] >> 4) == 11 ? 1u : 2u;
+	sink.put(F_FLAG, ctx_read_type, flag);
+	{	// read length = number of tuples after the start tuple
+		uint32_t len = n_tuples - 1;
+		const uint32_t nbits = ilog2_bits(len);
+		sink.put(F_LENBITS, 0, nbits);
+		if (nbits >= 2) {
+			uint64_t ctx = (uint64_t)nbits << 3;
+			len -= 1u << (nbits - 1);
+			uint32_t prefix = len, suffix = 0;
+			if (nbits > 9) { prefix = len >> (nbits - 9); suffix = len - (prefix << (nbits - 9)); }
+			sink.put(F_LENDATA, ctx, prefix);
+			if (nbits > 9) { ctx += 4; for (int nb = (int)nbits - 9; nb > 0; nb -= 8) { sink.put(F_LENDATA, ctx, suffix & 0xff); suffix >>= 8; ++ctx; } }
+		}
+	}
+	const uint64_t mask_s = (1ull << (2 * M.n_s)) - 1, mask_t = (1ull << (3 * M.n_t)) - 1;
+	uint64_t ctx_symbol = mask_s, ctx_tuple = mask_t;
+	if (flag == 0) { for (uint64_t p = 1; p < tn; ++p) { const uint32_t s = t[p] & 15; sink.put(F_SYM, ctx_symbol << 2, s); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; } return; }
+	if (flag == 1) { for (uint64_t p = 1; p < tn; ++p) { const uint32_t s = t[p] & 15; sink.put(F_SYMN, ctx_symbol, s); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; } return; }
 
-	__device__ __forceinline__ uint32_t be32(uint64_t q) const { return ((uint32_t)t[q] << 24) | ((uint32_t)t[q + 1] << 16) | ((uint32_t)t[q + 2] << 8) | t[q + 3]; }
-	template <class Sink>
-	__device__ __forceinline__ void put_read_id(const DnaReads& R, Sink& sink, uint32_t id)
-	{
+	auto be32 = [&](uint64_t p) { return ((uint32_t)t[p] << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; };
+	auto put_read_id = [&](uint32_t id) {
 		const int n = (int)no_bytes_of(R.first + r);      // reference ids stay below the read's index in the store
 		for (int i = n - 1; i >= 0; --i) { const uint64_t add = (i == n - 2) ? ((id >> (8 * (n - 1))) & 0xff) : 0; sink.put(F_READID, (uint64_t)i + (add << 3), (id >> (8 * i)) & 0xff); }
-	}
-	template <class Sink>
-	__device__ __forceinline__ void put_rev(Sink& sink, uint32_t id, uint32_t rev)
-	{
+	};
+	uint32_t seen_id[34]; uint32_t n_seen = 0; uint64_t ctx_rev = 0xf;         // uo_rev_comp of this read
+	auto put_rev = [&](uint32_t id, uint32_t rev) {
 		for (uint32_t k = 0; k < n_seen; ++k) if (seen_id[k] == id) return;
 		sink.put(F_REV, ctx_rev, rev);
 		if (n_seen < 34) seen_id[n_seen++] = id;
 		ctx_rev = ((ctx_rev << 2) + rev) & 0xf;
-	}
-	template <class Sink>
-	__device__ __forceinline__ void put_skip(Sink& sink, uint32_t len, bool local)
-	{
+	};
+	auto put_skip = [&](uint32_t len, bool local) {
 		if (local) { for (uint32_t part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 255) { sink.put(F_SKIPL, pc, len); break; } sink.put(F_SKIPL, pc, 255); len -= 254; } }
 		else { uint32_t enc = 0; for (int i = 3; i >= 0; --i) { const uint32_t x = (len >> (8 * i)) & 0xff; sink.put(F_SKIPD, (uint64_t)i * 64 + ilog2_bits(enc), x); enc = (enc << 8) + x; } }
-	}
-
-	template <class Sink>
-	__device__ void begin(const DnaModel& M, const DnaReads& R, uint32_t read, uint32_t ctx_read_type, Sink& sink)
-	{
-		r = read;
-		t = R.es + R.es_off[R.first + r];
-		tn = R.es_off[R.first + r + 1] - R.es_off[R.first + r];
-		uint32_t n_tuples = 0;
-		for (uint64_t q = 0; q < tn; ++n_tuples) { const uint32_t ty = t[q] >> 4; q += (ty == 4 || ty == 5) ? 4 : (ty == 6 || ty == 10) ? 5 : 1; }
-		flag = (t[0] >> 4) == 9 ? 0u : (t[0] >> 4) == 11 ? 1u : 2u;
-		sink.put(F_FLAG, ctx_read_type, flag);
-		{	// read length = number of tuples after the start tuple
-			uint32_t len = n_tuples - 1;
-			const uint32_t nbits = ilog2_bits(len);
-			sink.put(F_LENBITS, 0, nbits);
-			if (nbits >= 2) {
-				uint64_t ctx = (uint64_t)nbits << 3;
-				len -= 1u << (nbits - 1);
-				uint32_t prefix = len, suffix = 0;
-				if (nbits > 9) { prefix = len >> (nbits - 9); suffix = len - (prefix << (nbits - 9)); }
-				sink.put(F_LENDATA, ctx, prefix);
-				if (nbits > 9) { ctx += 4; for (int nb = (int)nbits - 9; nb > 0; nb -= 8) { sink.put(F_LENDATA, ctx, suffix & 0xff); suffix >>= 8; ++ctx; } }
-			}
-		}
-		mask_s = (1ull << (2 * M.n_s)) - 1; mask_t = (1ull << (3 * M.n_t)) - 1;
-		ctx_symbol = mask_s; ctx_tuple = mask_t;
-		p = 1;
-		if (flag != 2) return;
-		n_seen = 0; ctx_rev = 0xf; n_alt = 0; cur_alt = -1;
-		const uint32_t main_id = be32(1), main_rev = t[0] & 15;
-		put_read_id(R, sink, main_id);
-		put_rev(sink, main_id, main_rev);
-		main_ref = oriented(R, main_id, main_rev);
-		alt_ref = main_ref;
-		ref_pos = 0; alt_pos = 0; delta = 0;
-		is_main = true;
-		last_tuple = 255;
-		sh_t = 3 * M.n_t;
-		p = 5;
-	}
-
-	// one tuple; false: the read is complete (nothing was coded)
-	template <class Sink>
-	__device__ bool step(const DnaModel& M, const DnaReads& R, Sink& sink)
-	{
-		if (p >= tn) return false;
-		if (flag == 0) { const uint32_t s = t[p] & 15; sink.put(F_SYM, ctx_symbol << 2, s); ctx_symbol = ((ctx_symbol << 2) + s) & mask_s; ++p; return true; }
-		if (flag == 1) { const uint32_t s = t[p] & 15; sink.put(F_SYMN, ctx_symbol, s); ctx_symbol = ((ctx_symbol << 4) + s) & mask_s; ++p; return true; }
+	};
+	const uint32_t main_id = be32(1), main_rev = t[0] & 15;
+	put_read_id(main_id);
+	put_rev(main_id, main_rev);
+	OrientedRef main_ref = oriented(R, main_id, main_rev);
+	OrientedRef alt_ref = main_ref;
+	uint32_t alt_ids[32], alt_revs[32]; int alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;      // m_alt_ids / m_alt_read / m_alt_pos
+	int ref_pos = 0, alt_pos = 0, delta = 0;
+	bool is_main = true;
+	uint32_t last_tuple = 255;
+	const uint32_t sh_t = 3 * M.n_t;
+	for (uint64_t p = 5; p < tn;) {
 		const uint32_t ty = t[p] >> 4, v1 = t[p] & 15;
 		uint32_t v2 = 0;
 		if (ty == 4 || ty == 5) { v2 = ((uint32_t)v1 << 24) | ((uint32_t)t[p + 1] << 16) | ((uint32_t)t[p + 2] << 8) | t[p + 3]; p += 4; }
@@ -167,21 +157,21 @@ struct DnaWalker {
 			if (!is_main && cur_alt >= 0) alt_saved[cur_alt] = alt_pos;
 			int idx = -1;
 			for (uint32_t k = 0; k < n_alt; ++k) if (alt_ids[k] == v2) { idx = (int)k; break; }
-			if (n_alt == 0) put_read_id(R, sink, v2);
+			if (n_alt == 0) put_read_id(v2);
 			else {
 				sink.put(F_SEEN, n_alt, idx >= 0);
-				if (idx < 0) put_read_id(R, sink, v2); else sink.put(F_SHORT, n_alt, (uint32_t)idx);
+				if (idx < 0) put_read_id(v2); else sink.put(F_SHORT, n_alt, (uint32_t)idx);
 			}
 			if (idx < 0 && n_alt < 32) { idx = (int)n_alt; alt_ids[n_alt] = v2; alt_revs[n_alt] = v1; alt_saved[n_alt] = 0; ++n_alt; }
 			cur_alt = idx;
-			put_rev(sink, v2, v1);
+			put_rev(v2, v1);
 			alt_ref = oriented(R, v2, idx >= 0 ? alt_revs[idx] : v1);
 			alt_pos = 0; is_main = false; delta = 0;
 		} else if (ty == 4) {        // anchor
 			for (uint32_t len = v2, part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 23) { sink.put(F_ANCHOR, pc, len); break; } sink.put(F_ANCHOR, pc, 23); len -= 22; }
 			int& pos = is_main ? ref_pos : alt_pos;
 			pos += (int)v2;
-			const OrientedRef& o = is_main ? main_ref : alt_ref;
+			OrientedRef& o = is_main ? main_ref : alt_ref;
 			for (int i = (int)M.n_s; i > 0; --i) ctx_symbol = (ctx_symbol << 2) + ref_sym(R, o, pos - i);
 			ctx_symbol &= mask_s;
 			delta = 0;
@@ -216,9 +206,9 @@ struct DnaWalker {
 			delta -= skip_len;
 			if (!is_main && last_tuple == 6) {
 				const int mod = skip_len - (cur_alt >= 0 ? alt_saved[cur_alt] : 0);
-				if (mod > 0) put_skip(sink, (uint32_t)mod, false);
-				else { put_skip(sink, 0, false); put_skip(sink, (uint32_t)(-mod), false); }
-			} else put_skip(sink, (uint32_t)skip_len, last_tuple != 6 && last_tuple != 255);
+				if (mod > 0) put_skip((uint32_t)mod, false);
+				else { put_skip(0, false); put_skip((uint32_t)(-mod), false); }
+			} else put_skip((uint32_t)skip_len, last_tuple != 6 && last_tuple != 255);
 			is_main ? (ref_pos += skip_len) : (alt_pos += skip_len);
 		} else if (ty == 7) {        // main_ref
 			is_main = true;
@@ -226,17 +216,7 @@ struct DnaWalker {
 			delta = 0;
 		}
 		last_tuple = ty;
-		return true;
 	}
-};
-
-// all events of read r (one thread walks the whole read)
-template <bool EXACT = false, class Sink>
-__device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint32_t ctx_read_type, Sink& sink)
-{
-	DnaWalker<EXACT> W;
-	W.begin(M, R, r, ctx_read_type, sink);
-	while (W.step(M, R, sink)) {}
 }
 
 } // namespace clb

@@ -94,18 +94,10 @@ __global__ void __launch_bounds__(64) k_d_encode(DArgs a, DEnc e)
 	RangeSink s{a.tab, &a.M, MODE == 0 ? nullptr : e.out + e.dst_off[li], 0, 0, 0};
 	if (MODE == 2) s.cap = e.lane_cap[li];
 	s.start();
-	// ONE loop whose iterations are "the head of the lane's next read" or "one tuple": the lanes of the warp meet after every iteration
-	DnaWalker<false> W;
-	uint32_t fctx = 0, r = r0 + l;
-	bool in_read = false;
-	for (;;) {
-		if (in_read) in_read = W.step(a.M, a.R, s);
-		else {
-			if (r >= r1) break;
-			W.begin(a.M, a.R, r, fctx, s);
-			fctx = ((fctx << 2) + W.flag) & 0xff;
-			r += DB_LANES; in_read = true;
-		}
+	uint32_t fctx = 0;
+	for (uint32_t r = r0 + l; r < r1; r += DB_LANES) {
+		dna_walk(a.M, a.R, r, fctx, s);
+		fctx = ((fctx << 2) + read_flag_of(a.R, r)) & 0xff;
 	}
 	s.end();
 	if (MODE == 2 && s.n > s.cap) atomicExch(e.overflow, 1u);
