@@ -22,6 +22,41 @@ clb_status s1a_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* 
 }
 using namespace clb;
 
+// slab.h: the first context on a device takes the slab, the last one gives it back (unless CLB_SLAB_GB asked for a fixed one)
+namespace {
+struct SlabRefs { std::mutex m; int refs[clb::SLAB_MAX_DEVICES] = {}; bool fixed[clb::SLAB_MAX_DEVICES] = {}; };
+SlabRefs& slab_refs() { static SlabRefs r; return r; }
+void slab_acquire(int dev)
+{
+	SlabRefs& r = slab_refs();
+	std::lock_guard<std::mutex> g(r.m);
+	if (dev < 0 || dev >= clb::SLAB_MAX_DEVICES) return;
+	if (r.refs[dev]++ != 0 || clb::job_slab(dev).active()) return;
+	uint64_t want = 0;
+	if (const char* gb = std::getenv("CLB_SLAB_GB")) { want = static_cast<uint64_t>(std::atof(gb) * 1073741824.0); r.fixed[dev] = true; }
+	else {
+		const char* rs = std::getenv("CLB_SLAB_RESERVE_GB");
+		const uint64_t reserve = static_cast<uint64_t>((rs ? std::atof(rs) : 8.0) * 1073741824.0);
+		size_t free_b = 0, total_b = 0;
+		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > reserve + (4ull << 30)) want = (free_b - reserve) & ~((1ull << 21) - 1);
+		r.fixed[dev] = false;
+	}
+	if (!want) return;
+	void* q = nullptr;
+	if (cudaMalloc(&q, want) == cudaSuccess) clb::job_slab(dev).init(reinterpret_cast<uint64_t>(q), want);
+	else cudaGetLastError();                        // not enough memory for the slab: the job runs on cudaMalloc
+}
+void slab_release(int dev)
+{
+	SlabRefs& r = slab_refs();
+	std::lock_guard<std::mutex> g(r.m);
+	if (dev < 0 || dev >= clb::SLAB_MAX_DEVICES || r.refs[dev] == 0) return;
+	if (--r.refs[dev] != 0 || r.fixed[dev] || !clb::job_slab(dev).active()) return;
+	void* q = reinterpret_cast<void*>(clb::job_slab(dev).base());
+	if (clb::job_slab(dev).reset()) cudaFree(q);
+}
+}
+
 extern "C" {
 
 clb_status clb_create(const clb_params* p, clb_ctx** out)
@@ -46,16 +81,7 @@ clb_status clb_create(const clb_params* p, clb_ctx** out)
 		cudaMemPool_t pool;
 		if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) { unsigned long long thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
 	}
-	if (const char* gb = std::getenv("CLB_SLAB_GB")) {      // slab.h: one block per process, kept until clb_release_cached_memory; off unless asked for
-		static std::mutex slab_mutex;
-		std::lock_guard<std::mutex> g(slab_mutex);
-		const uint64_t want = static_cast<uint64_t>(std::atof(gb) * 1073741824.0);
-		if (want && !job_slab().active()) {
-			void* q = nullptr;
-			if (cudaMalloc(&q, want) == cudaSuccess) job_slab().init(reinterpret_cast<uint64_t>(q), want);
-			else cudaGetLastError();                        // not enough memory for the slab: the job runs on cudaMalloc as before
-		}
-	}
+	slab_acquire(p->device);
 	clb_status st = s1a_init(c);
 	if (st != CLB_OK) { g_create_error = c->err; clb_destroy(c); return st; }
 	*out = c;
@@ -72,7 +98,9 @@ void clb_destroy(clb_ctx* c)
 	c->qs.release(); c->ds.release(); c->hs.release(); c->xd.release(); c->xq.release(); c->xh.release(); c->xg.release(); c->dq.release();
 	if (c->stream3) { cudaStreamSynchronize(c->stream3); cudaStreamDestroy(c->stream3); }
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	const int dev = c->prm.device;
 	delete c;
+	slab_release(dev);
 }
 
 const char* clb_last_error(const clb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -451,7 +479,7 @@ clb_status clb_release_cached_memory(int device)
 	cudaMemPool_t pool;
 	if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) return CLB_ERR_NO_DEVICE;
 	cudaDeviceSynchronize();
-	if (job_slab().active()) { void* q = reinterpret_cast<void*>(job_slab().base()); if (job_slab().reset()) cudaFree(q); }      // only when no context holds blocks of it
+	if (job_slab(device).active()) { void* q = reinterpret_cast<void*>(job_slab(device).base()); if (job_slab(device).reset()) cudaFree(q); }      // only when no context holds blocks of it
 	return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? CLB_OK : CLB_ERR_CUDA;
 }
 

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <mutex>
 #include <unordered_set>
+#include <algorithm>
 #include <cuda_runtime.h>
 #include "../../include/colord_b200.h"
 #include "util.cuh"
@@ -22,20 +23,35 @@ namespace clb {
 constexpr uint64_t DEV_BIG_BYTES = 32ull << 20;
 struct BigPtrs { std::mutex m; std::unordered_set<void*> v; };
 inline BigPtrs& big_ptrs() { static BigPtrs b; return b; }
+inline int dev_current() { int d = 0; cudaGetDevice(&d); return d; }
 inline cudaError_t dev_malloc(void** p, uint64_t bytes, cudaStream_t s)
 {
 	if (bytes < DEV_BIG_BYTES) return cudaMallocAsync(p, bytes ? bytes : 1, s);
-	if (job_slab().active()) {      // CLB_SLAB_GB (slab.h): large blocks are cut from the process's slab, the driver is not called
-		const uint64_t at = job_slab().alloc(bytes);
+	Slab& slab = job_slab(dev_current());
+	if (slab.active()) {      // slab.h: large blocks are cut from the device's slab, the driver is not called
+		const uint64_t at = slab.alloc(bytes);
 		if (at) { *p = reinterpret_cast<void*>(at); return cudaSuccess; }
 	}
 	const cudaError_t e = cudaMalloc(p, bytes);
 	if (e == cudaSuccess) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); b.v.insert(*p); }
 	return e;
 }
+// what a single large block may ask for: the slab's largest free range, or the driver's free memory without a slab
+inline uint64_t dev_mem_available()
+{
+	size_t free_b = 0, total_b = 0;
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 0; }
+	const Slab& slab = job_slab(dev_current());
+	return slab.active() ? std::max<uint64_t>(slab.largest_free(), free_b) : (uint64_t)free_b;
+}
 inline bool dev_is_big(void* p) { BigPtrs& b = big_ptrs(); std::lock_guard<std::mutex> g(b.m); return b.v.erase(p) != 0; }
 // semantics of cudaFree: everything the device was doing is finished before the memory is reused
-inline bool slab_free(void* p) { if (!job_slab().owns(reinterpret_cast<uint64_t>(p))) return false; cudaDeviceSynchronize(); job_slab().free(reinterpret_cast<uint64_t>(p)); return true; }
+inline bool slab_free(void* p)
+{
+	const uint64_t a = reinterpret_cast<uint64_t>(p);
+	for (int d = 0; d < SLAB_MAX_DEVICES; ++d) if (job_slab(d).owns(a)) { cudaDeviceSynchronize(); job_slab(d).free(a); return true; }
+	return false;
+}
 inline void dev_free(void* p, cudaStream_t s) { if (!p) return; if (slab_free(p)) return; if (dev_is_big(p)) { cudaFree(p); return; } cudaDeviceSynchronize(); cudaFreeAsync(p, s); }
 // stream-ordered free of scratch (a large block is freed by cudaFree, which waits for the device by itself)
 inline cudaError_t dev_free_async(void* p, cudaStream_t s) { if (!p) return cudaSuccess; if (slab_free(p)) return cudaSuccess; if (dev_is_big(p)) return cudaFree(p); return cudaFreeAsync(p, s); }

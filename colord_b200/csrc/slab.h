@@ -1,9 +1,11 @@
-// slab.h — bookkeeping of ONE device slab taken once per process, so that a running job asks the driver for nothing.
-// Why: cudaMalloc / cudaFree while a job runs cost 0.3-1.5 s of a 12 s step in driver time on a B200, in stalls that move from
-// run to run (profiles/r01_summary.md, r01e / r01f).  With CLB_SLAB_GB=<n> set, clb_create takes an n GiB block once (it stays
-// until clb_release_cached_memory) and every block of DEV_BIG_BYTES or more is cut from it: first fit in address order, freed
-// ranges merged with their neighbours.  Requests the slab cannot serve fall through to cudaMalloc.  Off by default in round 1
-// (written after the round's GPU budget was spent; enabling it is one validation run away).
+// slab.h — bookkeeping of one device slab per GPU, so that a running job asks the driver for nothing.
+// Why: cudaMalloc / cudaFree while a job runs cost 0.1-1.6 s of a 9 s step in driver time on a B200, in stalls that move from
+// run to run (profiles/r01_summary.md r01e / r01f; profiles/r02_summary.md §8: the same two calls took 29 ms, 488 ms and 1 467 ms
+// in three consecutive jobs).  clb_create of the first context on a device takes one block — the free memory minus a reserve
+// (CLB_SLAB_RESERVE_GB, default 8) — and every block of DEV_BIG_BYTES or more is cut from it: first fit in address order, freed
+// ranges merged with their neighbours; the block goes back to the driver when the last context on the device is destroyed.
+// CLB_SLAB_GB=<n>: a slab of that size that stays until clb_release_cached_memory; CLB_SLAB_GB=0: no slab (every large block is
+// a cudaMalloc).  Requests the slab cannot serve fall through to cudaMalloc.
 // This header is pure host code (no CUDA calls): tests/host_slab_test.cpp exercises it on the CPU.
 #pragma once
 #include <cstdint>
@@ -76,6 +78,7 @@ public:
 	}
 };
 
-inline Slab& job_slab() { static Slab s; return s; }
+constexpr int SLAB_MAX_DEVICES = 16;
+inline Slab& job_slab(int device) { static Slab s[SLAB_MAX_DEVICES]; return s[device >= 0 && device < SLAB_MAX_DEVICES ? device : 0]; }
 
 } // namespace clb

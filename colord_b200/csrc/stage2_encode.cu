@@ -816,12 +816,9 @@ static clb_status align_level(clb_ctx* c, const S2P& P, Task* d_tasks, uint64_t 
 	uint64_t budget = env_budget ? (uint64_t)std::atoll(env_budget) << 20 : 16ull << 30;
 	if (!env_budget && c->s2_budget) budget = c->s2_budget;
 	else if (!env_budget) {      // as much as is free beyond a reserve for the later levels and stage 3, within 16 .. 40 GiB; fixed for the job
-		size_t free_b = 0, total_b = 0;
-		if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-			const uint64_t have = (uint64_t)free_b + c->s2_scratch.cap;
-			const uint64_t reserve = 60ull << 30;          // the tuples grow by reallocation (old + new alive), stage 3 wants a temp of their size
-			budget = std::min<uint64_t>(40ull << 30, std::max<uint64_t>(budget, have > reserve ? have - reserve : 0));
-		}
+		const uint64_t have = dev_mem_available() + c->s2_scratch.cap;
+		const uint64_t reserve = 60ull << 30;          // the tuples grow by reallocation (old + new alive), stage 3 wants a temp of their size
+		budget = std::min<uint64_t>(40ull << 30, std::max<uint64_t>(budget, have > reserve ? have - reserve : 0));
 		c->s2_budget = budget;
 	}
 	const bool bin_prof = std::getenv("CLB_ALIGN_PROFILE") != nullptr;
@@ -1001,8 +998,13 @@ static clb_status anchor_batch(clb_ctx* c, const S2P& P, uint32_t lo, uint32_t h
 	CLB_CUDA(c, mem.get(&d_acnt, nb)); CLB_CUDA(c, mem.get(&d_aoff, nb));
 	CLB_CUDA(c, cudaMemcpyAsync(d_list, h_list.data(), sizeof(uint32_t) * nb, cudaMemcpyHostToDevice, s));
 	CLB_CUDA(c, cudaMemsetAsync(d_slot_dec, 0, sizeof(uint32_t) * nb, s));
-	CLB_CUDA(c, c->s2_nodes.reserve(n_slots + nb, s, true, n_slots));
-	CLB_CUDA(c, c->s2_cviews.reserve((n_slots + nb) * P.c, s, true, n_slots * P.c));
+	uint64_t slots_job = n_slots + nb;
+	if (n_slots == 0) {      // first batch: nodes and candidate views for every read of the job that will get a slot (no regrowth copies)
+		slots_job = 0;
+		for (uint64_t r = c->n_context; r < c->n_reads; ++r) slots_job += !c->h_has_n[r] && h_cand_n[r];
+	}
+	CLB_CUDA(c, c->s2_nodes.reserve(std::max<uint64_t>(slots_job, n_slots + nb), s, true, n_slots));
+	CLB_CUDA(c, c->s2_cviews.reserve(std::max<uint64_t>(slots_job, n_slots + nb) * P.c, s, true, n_slots * P.c));
 	Node* nodes = c->s2_nodes.p + n_slots; CandView* cviews = c->s2_cviews.p + n_slots * P.c;
 	tr.mark("anchors: setup");
 	clb_status st = s2_anchors(c, P, h_list, d_list, c->d_ref_to_read, c->s2_arena, d_seg, d_slot_dec, nodes, cviews, d_cursor);

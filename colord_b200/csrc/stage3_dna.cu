@@ -188,8 +188,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 		CLB_TIMED(c, K_DNA, (k_d_lane_cap<<<(nl + 63) / 64, 64, 0, s>>>(a, d_cap))); CLB_LAUNCH_CHECK(c, "k_d_lane_cap");
 		uint64_t tmp_bytes = 0;
 		clb_status st = exclusive_scan(c, d_cap, nl, d_slot, &tmp_bytes); if (st != CLB_OK) return st;
-		size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-		if (tmp_bytes + (8ull << 30) < free_b && cudaMalloc((void**)&d_tmp, tmp_bytes + 16) == cudaSuccess) {
+		if (tmp_bytes + (8ull << 30) < dev_mem_available() && dev_malloc((void**)&d_tmp, tmp_bytes + 16, s) == cudaSuccess) {
 			e.out = d_tmp; e.dst_off = d_slot;
 			CLB_TIMED(c, K_DNA, (k_d_encode<2><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<temp>");
 			uint32_t ovf = 0;
@@ -218,7 +217,7 @@ clb_status s3_dna_encode(clb_ctx* c, uint32_t level, const uint32_t* pack_sizes,
 	if (nl && one_walk) { CLB_TIMED(c, K_DNA, (k_d_compact<<<(nl * 32 + 127) / 128, 128, 0, s>>>(a, e, d_tmp, d_slot))); CLB_LAUNCH_CHECK(c, "k_d_compact"); }
 	else if (nl) { CLB_TIMED(c, K_DNA, (k_d_encode<1><<<(nl + 63) / 64, 64, 0, s>>>(a, e))); CLB_LAUNCH_CHECK(c, "k_d_encode<write>"); }
 	CLB_CUDA(c, cudaStreamSynchronize(s));
-	if (d_tmp) cudaFree(d_tmp);
+	if (d_tmp) dev_free(d_tmp, s);
 	tr.mark(one_walk ? "k_d_compact" : "k_d_encode<write>");
 	c->ds_total = out_at;
 	c->ds_header = hdr.size();

@@ -357,7 +357,7 @@ clb_status s3_qual_encode(clb_ctx* c, const clb_qual_params* prm, const uint8_t*
 	CLB_CUDA(c, cudaMemcpyAsync(c->qs.p, hdr.data(), hdr.size(), cudaMemcpyHostToDevice, s));
 	uint64_t out_at = hdr.size();
 	uint64_t chunk_syms = 1ull << 31;       // more symbols per chunk = more warps in flight; the temp is 2 bytes per symbol
-	{ size_t free_b = 0, total_b = 0; if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) while (chunk_syms < (1ull << 33) && 4 * chunk_syms + (16ull << 30) < free_b) chunk_syms <<= 1; }
+	{ const uint64_t avail = dev_mem_available(); while (chunk_syms < (1ull << 33) && 4 * chunk_syms + (16ull << 30) < avail) chunk_syms <<= 1; }
 	uint16_t* d_tmp = nullptr; uint64_t tmp_cap = 0;      // one temp for all chunks (grown if a later chunk is larger)
 	for (uint32_t p0 = 0; p0 < np;) {
 		uint32_t p1 = p0; uint64_t syms = 0;
