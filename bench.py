@@ -325,6 +325,9 @@ def main():
     from colord_b200.dist import exchange_counts_and_finalize, exchange_reference_reads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:      # the library's device slab (csrc/slab.h) takes the free memory minus a reserve when a context is created: leave room
+        # for the tensors torch allocates for the two exchanges of dist.py (pairs sent + received ~ 48 GB / world, reference reads)
+        os.environ.setdefault("CLB_SLAB_RESERVE_GB", str(10 + 56 // world))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -403,10 +406,22 @@ def main():
         ctx.set_stream(stream.cuda_stream)
         if profile:
             ctx.profile_enable(True)
+        qual_up, qual_up_err = None, []
         if host_bases is None:
             ctx.append_reads_device(bases.data_ptr(), off_u64.data_ptr(), n_local)
         else:
             ctx.append_reads(host_bases, host_offsets)
+            if host_quals is not None and CFG["qual"]:
+                # end to end: the qualities travel to the device (clb_append_quals, stage-3 stream) from a second host thread while
+                # stages 1 and 2 run — the way the command line streams them beside the bases; 1 GiB per call
+                def qual_upload():
+                    try:
+                        for a in range(0, len(host_quals), 1 << 30):
+                            ctx.append_quals(host_quals[a:a + (1 << 30)])
+                    except Exception as ex:
+                        qual_up_err.append(ex)
+                qual_up = threading.Thread(target=qual_upload)
+                qual_up.start()
         phase("append")
         with torch.cuda.stream(stream):
             stats = exchange_counts_and_finalize(ctx, device, n_local)
@@ -431,7 +446,10 @@ def main():
             if host_quals is None:
                 ctx.qual_encode(4, [7, 14, 26], CFG["level"], quals.data_ptr(), off_u64.data_ptr(), on_device=True)
             else:
-                ctx.qual_encode(4, [7, 14, 26], CFG["level"], host_quals, host_offsets)
+                qual_up.join()
+                if qual_up_err:
+                    raise qual_up_err[0]
+                ctx.qual_encode(4, [7, 14, 26], CFG["level"], None, None)
         side, side_err = None, []
         if args.stages in ("12q", "12qd", "12qdh") and args.side_streams:
             def side_main():

@@ -144,10 +144,12 @@ clb_status clb_append_quals(clb_ctx* c, const uint8_t* quals, uint64_t n, int on
 {
 	CLB_ENTER(c);
 	if (n && !quals) return fail(c, CLB_ERR_BAD_ARG, "null qualities");
-	if (!c->dq.cap) { const uint64_t hint = c->prm.expected_bases + c->prm.expected_bases / 16 + 1024; CLB_CUDA(c, c->dq.reserve(std::max(hint, n) + 16, c->stream, false)); }
-	else CLB_CUDA(c, c->dq.reserve(c->dq_n + n + 16, c->stream, true, c->dq_n));
-	if (n) CLB_CUDA(c, cudaMemcpyAsync(c->dq.p + c->dq_n, quals, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-	CLB_CUDA(c, cudaStreamSynchronize(c->stream));      // the caller may reuse its buffer
+	// on the stage-3 stream (the quality coders' own): a second host thread may bring the qualities in while stages 1 and 2 run
+	cudaStream_t qs = c->stream3;
+	if (!c->dq.cap) { const uint64_t hint = c->prm.expected_bases + c->prm.expected_bases / 16 + 1024; CLB_CUDA(c, c->dq.reserve(std::max(hint, n) + 16, qs, false)); }
+	else CLB_CUDA(c, c->dq.reserve(c->dq_n + n + 16, qs, true, c->dq_n));
+	if (n) CLB_CUDA(c, cudaMemcpyAsync(c->dq.p + c->dq_n, quals, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, qs));
+	CLB_CUDA(c, cudaStreamSynchronize(qs));             // the caller may reuse its buffer
 	c->dq_n += n;
 	return CLB_OK;
 }

@@ -49,33 +49,13 @@ struct DnaReads {                       // what the walk needs from the resident
 	const uint8_t* es; const uint64_t* es_off;
 	uint32_t first;                     // reads are numbered from the first non-context read: read r of the walk is read first + r of the store
 };
-// A walk asks for the symbols of a reference read one after the other: the packed word it last touched stays in registers
-// (cw / cwi), so a load happens once per 32 bases instead of once per tuple.
-struct OrientedRef { uint64_t start; uint32_t len; uint32_t rev; uint64_t cw, cwi; };
-CLB_D OrientedRef oriented(const DnaReads& R, uint32_t ref_id, uint32_t rev) { const uint32_t rr = R.ref_to_read[ref_id]; return OrientedRef{R.rd_start[rr], R.rd_len[rr], rev, 0, ~0ull}; }
-CLB_D uint32_t ref_sym(const DnaReads& R, OrientedRef& o, int pos)
+struct OrientedRef { uint64_t start; uint32_t len; uint32_t rev; };
+CLB_D OrientedRef oriented(const DnaReads& R, uint32_t ref_id, uint32_t rev) { const uint32_t rr = R.ref_to_read[ref_id]; return OrientedRef{R.rd_start[rr], R.rd_len[rr], rev}; }
+CLB_D uint32_t ref_sym(const DnaReads& R, const OrientedRef& o, int pos)
 {
 	if (pos < 0 || (uint32_t)pos >= o.len) return 255u;               // the guard byte of read_t
-	const uint64_t a = o.rev ? o.start + (o.len - 1 - (uint32_t)pos) : o.start + (uint32_t)pos;
-	if ((a >> 5) != o.cwi) { o.cwi = a >> 5; o.cw = R.pk[a >> 5]; }
-	const uint32_t b = (uint32_t)(o.cw >> (62 - 2 * (a & 31))) & 3u;
-	return o.rev ? 3u - b : b;
+	return o.rev ? 3u - base_at(R.pk, o.start + (o.len - 1 - (uint32_t)pos)) : base_at(R.pk, o.start + (uint32_t)pos);
 }
-// The tuple bytes of a read through a 16-byte window in registers: the walk reads them front to back, one load per 16 bytes
-// instead of one per byte (every coder lane streams through its own reads, far more lines than the L1 holds).
-struct TupleBytes {
-	const uint8_t* base; const uint4* cur; uint4 w;
-	__device__ explicit TupleBytes(const uint8_t* b) : base(b), cur(nullptr), w(make_uint4(0, 0, 0, 0)) {}
-	__device__ __forceinline__ uint32_t operator[](uint64_t p)
-	{
-		const uintptr_t a = reinterpret_cast<uintptr_t>(base + p);
-		const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);       // inside the tuple buffer: its start is aligned, its end padded
-		if (q != cur) { cur = q; w = *q; }
-		const uint32_t k = (uint32_t)(a & 15);
-		const uint32_t x = k < 8 ? (k < 4 ? w.x : w.y) : (k < 12 ? w.z : w.w);
-		return (x >> (8 * (k & 3))) & 0xffu;
-	}
-};
 CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 = R.es[R.es_off[R.first + r]] >> 4; return t0 == 9 ? 0u : t0 == 11 ? 1u : 2u; }
 
 // The events of read r, in coding order.  ctx_read_type: the last read flags seen by this coder lane (dna_coder.cpp:459-462).
@@ -85,7 +65,7 @@ CLB_D uint32_t read_flag_of(const DnaReads& R, uint32_t r) { const uint32_t t0 =
 template <bool EXACT = false, class Sink>
 __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint32_t ctx_read_type, Sink& sink)
 {
-	TupleBytes t(R.es + R.es_off[R.first + r]);
+	const uint8_t* t = R.es + R.es_off[R.first + r];
 	const uint64_t tn = R.es_off[R.first + r + 1] - R.es_off[R.first + r];
 	uint32_t n_tuples = 0;
 	for (uint64_t p = 0; p < tn; ++n_tuples) { const uint32_t ty = t[p] >> 4; p += (ty == 4 || ty == 5) ? 4 : (ty == 6 || ty == 10) ? 5 : 1; }
@@ -128,7 +108,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 	const uint32_t main_id = be32(1), main_rev = t[0] & 15;
 	put_read_id(main_id);
 	put_rev(main_id, main_rev);
-	OrientedRef main_ref = oriented(R, main_id, main_rev);
+	const OrientedRef main_ref = oriented(R, main_id, main_rev);
 	OrientedRef alt_ref = main_ref;
 	uint32_t alt_ids[32], alt_revs[32]; int alt_saved[32]; uint32_t n_alt = 0; int cur_alt = -1;      // m_alt_ids / m_alt_read / m_alt_pos
 	int ref_pos = 0, alt_pos = 0, delta = 0;
@@ -171,7 +151,7 @@ __device__ void dna_walk(const DnaModel& M, const DnaReads& R, uint32_t r, uint3
 			for (uint32_t len = v2, part = 0; len; ++part) { const uint32_t pc = EXACT ? part : min(part, 63u); if (len < 23) { sink.put(F_ANCHOR, pc, len); break; } sink.put(F_ANCHOR, pc, 23); len -= 22; }
 			int& pos = is_main ? ref_pos : alt_pos;
 			pos += (int)v2;
-			OrientedRef& o = is_main ? main_ref : alt_ref;
+			const OrientedRef& o = is_main ? main_ref : alt_ref;
 			for (int i = (int)M.n_s; i > 0; --i) ctx_symbol = (ctx_symbol << 2) + ref_sym(R, o, pos - i);
 			ctx_symbol &= mask_s;
 			delta = 0;

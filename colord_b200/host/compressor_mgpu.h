@@ -23,6 +23,9 @@ namespace clbhost {
 
 inline CompressionReport runCompressionMultiGpu(const CCompressorParams& params, CInfo& info, uint32_t n_gpus)
 {
+	// the exchange buffers of libcolord_b200_mgpu.so come from cudaMalloc after the contexts exist: the contexts must not have taken
+	// the devices' free memory as their slabs (csrc/slab.h)
+	setenv("CLB_SLAB_GB", "0", 0);
 	const auto t0 = std::chrono::steady_clock::now();
 	if (n_gpus < 2) throw std::invalid_argument("--gpus takes 2 or more (leave it out for one GPU)");
 	if (!params.refGenomePath.empty()) throw std::invalid_argument("--gpus: the reference-genome mode (-G) runs on one GPU");

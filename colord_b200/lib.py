@@ -189,6 +189,12 @@ class Context:
         self._ck(self.L.clb_append_reads(self.h, _np_ptr(bases), _np_ptr(offsets), n, 0))
         self.n_reads += n
 
+    def append_quals(self, quals: np.ndarray):
+        """Qualities of reads already appended (same order, no separators): they stay on the device and the quality encoders take
+        quals=None.  Runs on the stage-3 stream, so a second host thread may call it while stages 1 / 2 run (clb_append_quals)."""
+        q = np.ascontiguousarray(quals, np.uint8)
+        self._ck(self.L.clb_append_quals(self.h, _np_ptr(q), len(q), 0))
+
     def append_reads_device(self, bases_ptr: int, offsets_ptr: int, n_reads: int):
         self._ck(self.L.clb_append_reads(self.h, C.c_void_p(bases_ptr), C.c_void_p(offsets_ptr), n_reads, 1))
         self.n_reads += n_reads
@@ -421,7 +427,9 @@ class Context:
         for i, t in enumerate(thresholds):
             prm.thresholds[i] = t
         ps = None if pack_sizes is None else np.ascontiguousarray(pack_sizes, np.uint32)
-        if on_device:
+        if quals is None:      # resident (append_quals)
+            qp, op = None, None
+        elif on_device:
             qp, op = C.c_void_p(quals), C.c_void_p(offsets)
         else:
             q = np.ascontiguousarray(quals, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
