@@ -346,6 +346,61 @@ struct Aligner {
 		return n;
 	}
 
+	// The same walk for the groups of a warp IN LOCKSTEP (sub-warp groups, backward kernel): one loop for the whole warp whose
+	// iterations are one run of every group that is still walking, shuffles and ballots with the full mask (width GROUP).  Groups
+	// that walk on their own take turns on the warp's issue slots and pay the convergence checks of a run-time mask around every
+	// shuffle; in lockstep a step costs the same whatever the number of groups.  go == false: this group has nothing to walk.
+	__device__ int traceback_lockstep(const ulonglong2* __restrict__ hist, int Ts, int Q, int T, bool go, uint8_t* out, uint8_t* tmp) const
+	{
+		CLB_PH_BEGIN
+		constexpr unsigned FULL = 0xffffffffu;
+		const int B = (Q + 63) >> 6;
+		int I = go ? Q : 0, J = go ? T : 0, n = 0;
+		int wb = -1, wj = -0x40000000;
+		uint64_t wpv = 0, wph = 0;
+		const uint32_t gbase = (threadIdx.x & 31) & ~(uint32_t)(GROUP - 1);
+		const uint32_t gall = GROUP == 32 ? 0xffffffffu : ((1u << GROUP) - 1u);
+		for (;;) {
+			const bool act = I > 0 && J > 0;
+			if (!__any_sync(FULL, act)) break;
+			const int i = I - 1, j = J - 1, b = i >> 6, bit = i & 63;
+			if (act && (b != wb || j > wj || j < wj - (GROUP - 1))) {
+				wb = b; wj = j;
+				CLB_PH_COUNT(GROUP, 6, 1)
+				const int col = wj - (int)gl;
+				if (col >= 0) { const ulonglong2 e = hist[hist_at(b, col, Ts, B)]; wpv = e.x; wph = e.y; }
+				if (col - GROUP >= 0) prefetch_l2(&hist[hist_at(b, col - GROUP, Ts, B)]);
+				if (b > 0 && col >= 0) { prefetch_l2(&hist[hist_at(b - 1, col, Ts, B)]); if (col - GROUP >= 0) prefetch_l2(&hist[hist_at(b - 1, col - GROUP, Ts, B)]); }
+			}
+			const int src = act ? wj - j : 0;             // lane holding column j
+			const int k = (int)gl - src;                  // this lane holds column j - k
+			const uint64_t pvj = __shfl_sync(FULL, wpv, src, GROUP);
+			const bool in = act && k >= 0 && j - k >= 0;
+			const bool left_k = in && !((wpv >> bit) & 1) && ((wph >> bit) & 1);
+			const uint32_t bl = ((__ballot_sync(FULL, left_k) >> gbase) & gall) >> src;
+			const int bk = (bit - k) & 63;
+			const bool diag_k = in && bit - k >= 0 && !((wpv >> bk) & 1) && !((wph >> bk) & 1);
+			const uint32_t bd = ((__ballot_sync(FULL, diag_k) >> gbase) & gall) >> src;
+			if (act) {
+				int run; uint8_t op;
+				if ((pvj >> bit) & 1) { run = min(__clzll((long long)~(pvj << (63 - bit))), bit + 1); op = 1; I -= run; }
+				else if (bl & 1) { run = ~bl ? __ffs((int)~bl) - 1 : 32; op = 2; J -= run; }
+				else { run = ~bd ? __ffs((int)~bd) - 1 : 32; op = 0; I -= run; J -= run; }
+				for (int x = (int)gl; x < run; x += GROUP) tmp[n + x] = op;
+				n += run;
+				CLB_PH_COUNT(GROUP, 5, 1)
+			}
+		}
+		const int rest = I + J; const uint8_t rop = I > 0 ? 1 : 2;
+		for (int x = (int)gl; x < rest; x += GROUP) tmp[n + x] = rop;
+		n += rest;
+		__syncwarp(FULL);
+		for (int x = (int)gl; x < n; x += GROUP) out[x] = tmp[n - 1 - x];
+		__syncwarp(FULL);
+		CLB_PH_END(GROUP, 1)
+		return n;
+	}
+
 	// decode the final column of a sweep into D(y-1, T-1) for y = 1..Q, F[0] = T  (vertex values of the last column)
 	__device__ void decode_final(const uint64_t* fin_pv, const uint64_t* fin_mv, const int32_t* fin_sc, int Q, int T, uint32_t* F) const
 	{
@@ -609,6 +664,29 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 	uint8_t* ops = A.scratch + A.lay.ops;
 	int n_ops = 0;
 	uint32_t n_out = 0;
+	uint32_t ref_end = 0;
+	bool rows_ref = true;
+	constexpr bool LOCKSTEP = PHASE == 2 && GROUP > 1 && GROUP < 32;
+	if constexpr (LOCKSTEP) {
+		// backward kernel, sub-warp groups: what the forward kernel swept is derived per group, then every group of the warp walks
+		// back in one lockstep loop (problems above the traceback limit never come here: the host gives them bins of their own)
+		const ulonglong2* hist = reinterpret_cast<const ulonglong2*>(A.scratch + A.lay.hist);
+		int Q = (int)rl, Ts = (int)el, T = (int)el;
+		bool go = true;
+		if (kind != 2) {
+			const uint32_t cut = rl < 2 * el ? rl : 2 * el;
+			if (cut < 2 || el < 2) { Q = (int)cut; ref_end = cut - 1; }
+			else {
+				rows_ref = false;
+				Q = (int)el; Ts = (int)cut;
+				const int best = res[0], end = res[1];
+				ref_end = (uint32_t)end; T = end + 1;
+				if (best >= (int)el) { go = false; ref_end = 0xFFFFFFFFu; }      // the empty prefix wins: |enc| insertions (see below)
+			}
+		}
+		n_ops = A.traceback_lockstep(hist, Ts, Q, T, go, ops, A.scratch + A.lay.tmp);
+		if (!go) { for (int x = (int)gl; x < (int)el; x += GROUP) ops[x] = 1; n_ops = (int)el; A.gsync(); }
+	} else
 	if (kind == 2) {
 		// NW, rows = ref, cols = enc: UP = 'D', LEFT = insertion
 		int best;
@@ -628,9 +706,8 @@ __device__ uint32_t edit_script_task(const Aligner<GROUP>& A, V ref, uint32_t rl
 	const uint32_t cut = rl < 2 * el ? rl : 2 * el;
 	const V r = kind == 0 ? ref.reversed((int)rl) : ref;      // first `cut` symbols are used
 	const V e = kind == 0 ? enc.reversed((int)el) : enc;
-	uint32_t ref_end;
-	bool rows_ref;
-	if (cut < 2 || el < 2) {       // edit_script.h:336-343: global alignment of the (cut) ref against enc, rows = ref
+	if (LOCKSTEP) {}
+	else if (cut < 2 || el < 2) {       // edit_script.h:336-343: global alignment of the (cut) ref against enc, rows = ref
 		rows_ref = true; ref_end = cut - 1;
 		if (PHASE == 1) { A.leaf_fwd(r, (int)cut, e, (int)el); return 0; }
 		if (PHASE == 2) n_ops = A.leaf_back((int)cut, (int)el, ops, A.scratch + A.lay.tmp);

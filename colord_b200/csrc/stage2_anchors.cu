@@ -27,6 +27,7 @@ constexpr int MATCH_THREADS = 256;
 constexpr uint32_t SMEM_TAB_CELLS = 16384;      // 64 KB: reads up to 8192 m-mers keep the table in shared memory
 constexpr uint32_t SMEM_BLOOM_WORDS = 4096;     // 16 KB = 128 Ki bits
 constexpr uint32_t MAX_C = 32;
+constexpr uint32_t SMEM_HIT_WORDS = 2048;       // 16 KB: which (position, strand) probes of a 32-position item found the m-mer in the read's table
 
 CLB_D uint64_t window(const uint64_t* __restrict__ pk, uint64_t p, uint32_t m)
 {
@@ -101,13 +102,41 @@ CLB_D void tab_matches(const uint32_t* tab, uint32_t mask, const uint64_t* __res
 	}
 }
 
+// The candidates' m-mers are scanned twice: the counting pass (match caps, arena slots) and the pass that writes the pairs.  The counting
+// pass leaves one bit per probe that hit (hit[item], bit 2 * (position in the item) + strand; a few percent of the probes), and the
+// writing pass visits only those — when the items fit the mask (hit != nullptr), else it repeats the whole scan.
 template <bool EMIT>
 __device__ void scan_refs(const MatchArgs& a, MatchShared& sh, const uint32_t* tab, uint32_t tmask, const uint32_t* bloom, uint32_t bmask,
-	const uint64_t* epk, uint64_t estart, uint32_t n_cand)
+	const uint64_t* epk, uint64_t estart, uint32_t n_cand, uint64_t* hit)
 {
 	const uint32_t m = a.P.m;
 	const uint64_t mmask = m == 32 ? ~0ULL : ((1ULL << (2 * m)) - 1);
 	const uint32_t n_items = sh.word_base[n_cand];
+	if (EMIT && hit) {
+		for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
+			uint64_t hm = hit[it];
+			if (!hm) continue;
+			uint32_t j = 0;
+			while (sh.word_base[j + 1] <= it) ++j;
+			const uint32_t rr = sh.ref_read[j];
+			const uint64_t rstart = a.rd_start[rr]; const uint32_t rl = a.rd_len[rr];
+			const uint32_t p0 = (it - sh.word_base[j]) * 32;
+			for (; hm; hm &= hm - 1) {
+				const uint32_t bit = (uint32_t)__ffsll((long long)hm) - 1, p = p0 + (bit >> 1), o = bit & 1;
+				const unsigned long long b = sh.base[2 * j + o];
+				if (b == ~0ULL) continue;
+				const uint64_t f = window(a.pk, rstart + p, m);
+				const uint64_t x = o ? revcomp(f, m) : f;
+				const uint32_t pos_o = o ? (rl - m - p) : p;
+				uint64_t* out = reinterpret_cast<uint64_t*>(a.arena + b * PAIR_SLOT_BYTES);
+				tab_matches(tab, tmask, epk, estart, m, x, mm_hash(x), [&](uint32_t e) {
+					const uint32_t idx = atomicAdd(&sh.fill[2 * j + o], 1u);
+					out[idx] = ((uint64_t)e << 32) | (uint64_t)(0xFFFFFFFFu - pos_o);
+				});
+			}
+		}
+		return;
+	}
 	for (uint32_t it = threadIdx.x; it < n_items; it += blockDim.x) {
 		uint32_t j = 0;
 		while (sh.word_base[j + 1] <= it) ++j;
@@ -119,6 +148,7 @@ __device__ void scan_refs(const MatchArgs& a, MatchShared& sh, const uint32_t* t
 		if (EMIT && sh.base[2 * j] == ~0ULL && sh.base[2 * j + 1] == ~0ULL) continue;
 		uint64_t f = window(a.pk, rstart + p0, m);
 		uint32_t hits_f = 0, hits_r = 0; unsigned long long pairs_f = 0, pairs_r = 0;
+		uint64_t hm = 0;
 		for (uint32_t p = p0; p < p1; ++p) {
 			if (p > p0) f = ((f << 2) | base_at(a.pk, rstart + p + m - 1)) & mmask;
 			const uint64_t r = revcomp(f, m);
@@ -140,11 +170,12 @@ __device__ void scan_refs(const MatchArgs& a, MatchShared& sh, const uint32_t* t
 				} else {
 					uint32_t cnt = 0;
 					tab_matches(tab, tmask, epk, estart, m, x, h, [&](uint32_t) { ++cnt; });
-					if (cnt) { if (o) { ++hits_r; pairs_r += cnt; } else { ++hits_f; pairs_f += cnt; } }
+					if (cnt) { hm |= 1ull << (2 * (p - p0) + o); if (o) { ++hits_r; pairs_r += cnt; } else { ++hits_f; pairs_f += cnt; } }
 				}
 			}
 		}
 		if (!EMIT) {
+			if (hit) hit[it] = hm;
 			if (hits_f) { atomicAdd(&sh.hits[2 * j], hits_f); atomicAdd(&sh.pairs[2 * j], pairs_f); }
 			if (hits_r) { atomicAdd(&sh.hits[2 * j + 1], hits_r); atomicAdd(&sh.pairs[2 * j + 1], pairs_r); }
 		}
@@ -159,6 +190,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	uint32_t* s_bloom = s_tab + SMEM_TAB_CELLS;
 	uint64_t* s_pk = reinterpret_cast<uint64_t*>(s_bloom + SMEM_BLOOM_WORDS);      // TILE_WORDS + 2 words, then the mbarrier
 	uint64_t* s_bar = s_pk + TILE_WORDS + 2;
+	uint64_t* s_hit = s_bar + 2;
 
 	const uint32_t slot = blockIdx.x;
 	const uint32_t read = a.enc_list[slot];
@@ -237,7 +269,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	__syncthreads();
 	if (sh.decision == 1) return;
 	// ---- count ----
-	scan_refs<false>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand);
+	uint64_t* hit = sh.word_base[n_cand] <= SMEM_HIT_WORDS ? s_hit : nullptr;
+	scan_refs<false>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand, hit);
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		unsigned long long total = 0;
@@ -262,7 +295,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 	}
 	__syncthreads();
 	// ---- write the pairs ----
-	scan_refs<true>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand);
+	scan_refs<true>(a, sh, tab, tmask, bloom, bmask, epk, estart, n_cand, hit);
 }
 
 // ------------------------------------------------------------------------------------------------ HiFi: anchors from shared k-mers
@@ -617,7 +650,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 		CLB_LAUNCH_CHECK(c, "k_kmer_anchors");
 		CLB_CUDA(c, cudaStreamSynchronize(s));          // the host vectors above were read by the copies
 	}
-	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS) + sizeof(uint64_t) * (TILE_WORDS + 2 + 2);
+	const size_t smem = ((sizeof(MatchShared) + 15) & ~15ull) + sizeof(uint32_t) * (SMEM_TAB_CELLS + SMEM_BLOOM_WORDS) + sizeof(uint64_t) * (TILE_WORDS + 2 + 2 + SMEM_HIT_WORDS);
 	static const int tma_on = [] { const char* e = std::getenv("CLB_TMA"); return e ? std::atoi(e) : 1; }();      // on a B200: k_anchors 1 283 ms per 25 Gbases with the bulk-copy stage, 1 425 ms without (profiles/r02h_*)
 	CLB_CUDA(c, cudaFuncSetAttribute(k_anchor_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	// first guess of the arena: one pair per base of every read and candidate half-used; the kernel reports the exact need
