@@ -23,7 +23,7 @@
 
 namespace clb {
 
-constexpr int MATCH_THREADS = 256;
+constexpr int MATCH_THREADS = 512;      // 2 CTAs per SM (shared memory): 32 resident warps behind the probes' shared-memory latency
 constexpr uint32_t SMEM_TAB_CELLS = 16384;      // 64 KB: reads up to 8192 m-mers keep the table in shared memory
 constexpr uint32_t SMEM_BLOOM_WORDS = 4096;     // 16 KB = 128 Ki bits
 constexpr uint32_t MAX_C = 32;
@@ -60,8 +60,7 @@ CLB_D void tma_stage_words(uint64_t* s_dst, const uint64_t* g_src, uint32_t byte
 
 CLB_D uint32_t mm_hash(uint64_t x)
 {
-	x *= 0x9E3779B97F4A7C15ULL; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL;
-	return (uint32_t)(x >> 32);
+	return (uint32_t)((x * 0x9E3779B97F4A7C15ULL) >> 32);      // one multiply: the top half mixes every base of the m-mer (table index = low bits of it, Bloom bit from bit 7 up)
 }
 
 struct MatchArgs {

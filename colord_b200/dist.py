@@ -18,6 +18,27 @@ import torch.distributed as dist
 STAT_KEYS = ("n_reads", "tot_kmers", "n_unique", "n_unique_counted", "total_count_filtered")
 
 
+class _Trace:
+    """BENCH_PHASES=1: wall time of every step of an exchange on rank 0 (synchronising; debugging aid)."""
+
+    def __init__(self, what, rank):
+        import os
+        import sys
+        import time
+        self.on = os.environ.get("BENCH_PHASES") is not None and rank == 0 and torch.cuda.is_available()
+        self.what, self.time, self.err = what, time, sys.stderr
+        if self.on:
+            torch.cuda.synchronize()
+            self.t = time.perf_counter()
+
+    def __call__(self, name):
+        if self.on:
+            torch.cuda.synchronize()
+            t = self.time.perf_counter()
+            print(f"[exchange] {self.what}: {name:22s} {1e3 * (t - self.t):8.1f} ms", file=self.err)
+            self.t = t
+
+
 def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
     """Turn per-rank count tables into the identical global filtered set on every rank.
 
@@ -27,11 +48,13 @@ def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
     if world == 1:
         return ctx.count_finalize()
     rank = dist.get_rank(group)
+    trace = _Trace("counts", rank)
     # 1. sizes of my table's partitions, exchanged so every rank knows what it will receive
     send_sizes = torch.tensor([ctx.counts_size(p, world) for p in range(world)], dtype=torch.int64, device=device)
     recv_sizes = torch.empty_like(send_sizes)
     dist.all_to_all_single(recv_sizes, send_sizes, group=group)
     send_l, recv_l = send_sizes.tolist(), recv_sizes.tolist()
+    trace("sizes")
     # 2. export partition by partition into one send buffer, all-to-all the pairs
     send_k = torch.empty(max(1, sum(send_l)), dtype=torch.int64, device=device)
     send_c = torch.empty(max(1, sum(send_l)), dtype=torch.int32, device=device)
@@ -41,14 +64,18 @@ def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
             got = ctx.counts_export_device(p, world, send_k[off:].data_ptr(), send_c[off:].data_ptr(), send_l[p])
             assert got == send_l[p]
         off += send_l[p]
+    trace("export")
     recv_k = torch.empty(max(1, sum(recv_l)), dtype=torch.int64, device=device)
     recv_c = torch.empty(max(1, sum(recv_l)), dtype=torch.int32, device=device)
     dist.all_to_all_single(recv_k[:sum(recv_l)], send_k[:sum(send_l)], recv_l, send_l, group=group)
     dist.all_to_all_single(recv_c[:sum(recv_l)], send_c[:sum(send_l)], recv_l, send_l, group=group)
+    trace("all-to-all")
     # 3. my table now holds only what I own: everything every rank counted for my partition
     ctx.counts_reset()
     ctx.counts_merge_device(recv_k.data_ptr(), recv_c.data_ptr(), sum(recv_l), 0)
+    trace("reset + merge")
     local = ctx.count_finalize()
+    trace("finalize (local)")
     # 4. statistics are sums over owners (n_reads over shards)
     st = torch.tensor([n_local_reads] + [local[k] for k in STAT_KEYS[1:]], dtype=torch.int64, device=device)
     dist.all_reduce(st, group=group)
@@ -71,7 +98,9 @@ def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
     keep = torch.cat([torch.arange(r * pad, r * pad + sizes_l[r], device=device) for r in range(world)]) if sum(sizes_l) else torch.zeros(0, dtype=torch.int64, device=device)
     uni_k = all_k[keep].contiguous()
     uni_c = all_c[keep].contiguous()
+    trace("survivors gathered")
     ctx.filter_import_device(uni_k.data_ptr(), uni_c.data_ptr(), int(uni_k.numel()), stats)
+    trace("filter import")
     return stats
 
 
