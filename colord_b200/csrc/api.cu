@@ -156,6 +156,9 @@ clb_status clb_append_quals(clb_ctx* c, const uint8_t* quals, uint64_t n, int on
 clb_status clb_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n) { CLB_ENTER(c); return s1a_counts_size(c, part, n_parts, n); }
 clb_status clb_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n, int on_device)
 { CLB_ENTER(c); return s1a_counts_export(c, part, n_parts, kmers, counts, cap, n, on_device); }
+clb_status clb_counts_sizes(clb_ctx* c, uint32_t n_parts, uint64_t* sizes) { CLB_ENTER(c); return s1a_counts_sizes(c, n_parts, sizes); }
+clb_status clb_counts_export_all(clb_ctx* c, uint32_t n_parts, const uint64_t* first, uint64_t* kmers, uint32_t* counts, uint64_t cap)
+{ CLB_ENTER(c); return s1a_counts_export_all(c, n_parts, first, kmers, counts, cap); }
 clb_status clb_counts_reset(clb_ctx* c) { CLB_ENTER(c); return s1a_counts_reset(c); }
 clb_status clb_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device)
 { CLB_ENTER(c); return s1a_counts_merge(c, kmers, counts, n, n_reads_remote, on_device); }

@@ -239,6 +239,8 @@ clb_status s1b_reads_have_n(clb_ctx* c, uint8_t* flags);
 clb_status s1b_reads_export(clb_ctx* c, const uint32_t* read_ids, uint32_t n, uint8_t* bases, uint64_t cap, int on_device);
 clb_status s1a_counts_size(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* n);
 clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_out, int on_device);
+clb_status s1a_counts_sizes(clb_ctx* c, uint32_t n_parts, uint64_t* sizes);
+clb_status s1a_counts_export_all(clb_ctx* c, uint32_t n_parts, const uint64_t* first, uint64_t* kmers, uint32_t* counts, uint64_t cap_out);
 clb_status s1a_counts_reset(clb_ctx* c);
 clb_status s1a_filter_import(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, const clb_kmer_stats* global_stats, int on_device);
 clb_status s1a_counts_merge(clb_ctx* c, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device);

@@ -81,7 +81,7 @@ clb_status clb_group_exchange_counts(clb_group* g, uint32_t rank, clb_kmer_stats
 	DevMem mem;
 	clb_status st = CLB_OK;
 	// 1. my table's partitions
-	auto sizes_step = [&]() -> clb_status { for (uint32_t p = 0; p < N; ++p) G_CLB(clb_counts_size(c, p, N, &g->sizes[rank][p])); return CLB_OK; };
+	auto sizes_step = [&]() -> clb_status { G_CLB(clb_counts_sizes(c, N, g->sizes[rank].data())); return CLB_OK; };      // one pass for all partitions
 	st = sizes_step();
 	g->barrier(); G_CHECK_ALL();
 	uint64_t n_send = 0, n_recv = 0;
@@ -89,12 +89,9 @@ clb_status clb_group_exchange_counts(clb_group* g, uint32_t rank, clb_kmer_stats
 	uint64_t *send_k = nullptr, *recv_k = nullptr; uint32_t *send_c = nullptr, *recv_c = nullptr;
 	auto a2a_step = [&]() -> clb_status {
 		G_CUDA(mem.get(&send_k, n_send)); G_CUDA(mem.get(&send_c, n_send)); G_CUDA(mem.get(&recv_k, n_recv)); G_CUDA(mem.get(&recv_c, n_recv));
-		uint64_t off = 0;
-		for (uint32_t p = 0; p < N; ++p) {
-			const uint64_t want = g->sizes[rank][p]; uint64_t got = 0;
-			if (want) { G_CLB(clb_counts_export(c, p, N, send_k + off, send_c + off, want, &got, 1)); if (got != want) return gfail(g, rank, CLB_ERR_STATE, "count partition changed size between the two scans"); }
-			off += want;
-		}
+		std::vector<uint64_t> first(N, 0);
+		for (uint32_t p = 1; p < N; ++p) first[p] = first[p - 1] + g->sizes[rank][p - 1];
+		if (n_send) G_CLB(clb_counts_export_all(c, N, first.data(), send_k, send_c, n_send));      // one more pass writes every partition at its offset
 		G_CLB(clb_synchronize(c));
 		// 2. all-to-all of the pairs: partition p of every rank goes to rank p
 		G_NCCL(ncclGroupStart());

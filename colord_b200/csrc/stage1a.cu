@@ -258,6 +258,52 @@ __global__ void k_tab_export(const CountSlot* __restrict__ tab, uint64_t cap, ui
 	}
 }
 
+// All partitions in ONE pass over the table (the multi-GPU exchange asked for 2 N scans of it before: N sizes, N exports, each
+// paying one global atomic per warp on a single cursor).  A CTA takes tiles of 256 x EXPORT_PER_THREAD slots: the occupied slots are
+// ranked per partition in shared memory (one atomic per warp and partition present: match.any), the tile's share of every
+// partition is reserved with one global atomic per partition, then the entries are written at first[partition] + their rank.
+// WRITE == false only counts (cursor[p] = entries of partition p).
+constexpr int EXPORT_PER_THREAD = 8;
+constexpr uint32_t EXPORT_MAX_PARTS = 64;
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_tab_export_all(const CountSlot* __restrict__ tab, uint64_t cap, uint32_t n_parts,
+	uint64_t* __restrict__ kmers, uint32_t* __restrict__ counts, uint64_t out_cap, unsigned long long* __restrict__ cursor, const unsigned long long* __restrict__ first)
+{
+	__shared__ uint32_t s_cnt[EXPORT_MAX_PARTS];
+	__shared__ unsigned long long s_base[EXPORT_MAX_PARTS];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint64_t tile_slots = 256ull * EXPORT_PER_THREAD, n_tiles = (cap + tile_slots - 1) / tile_slots;
+	for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+		if (threadIdx.x < n_parts) s_cnt[threadIdx.x] = 0;
+		__syncthreads();
+		CountSlot sl[EXPORT_PER_THREAD]; uint32_t own[EXPORT_PER_THREAD], rank[EXPORT_PER_THREAD];
+#pragma unroll
+		for (int k = 0; k < EXPORT_PER_THREAD; ++k) {
+			const uint64_t i = t * tile_slots + (uint64_t)k * 256 + threadIdx.x;
+			sl[k].key = EMPTY64; sl[k].cnt = 0;
+			if (i < cap) sl[k] = tab[i];
+			const bool take = sl[k].key != EMPTY64;
+			own[k] = take ? owner_of(sl[k].key, n_parts) : 0xFFFFFFFFu;
+			const uint32_t peers = __match_any_sync(0xffffffffu, own[k]);      // lanes of the warp with the same partition (or none)
+			uint32_t base = 0;
+			if (take && lane == (uint32_t)__ffs((int)peers) - 1) base = atomicAdd(&s_cnt[own[k]], (uint32_t)__popc(peers));
+			base = __shfl_sync(0xffffffffu, base, __ffs((int)peers) - 1);
+			rank[k] = base + __popc(peers & ((1u << lane) - 1));
+		}
+		__syncthreads();
+		if (threadIdx.x < n_parts) s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+		__syncthreads();
+		if (WRITE) {
+#pragma unroll
+			for (int k = 0; k < EXPORT_PER_THREAD; ++k) if (own[k] != 0xFFFFFFFFu) {
+				const uint64_t o = first[own[k]] + s_base[own[k]] + rank[k];
+				if (o < out_cap) { kmers[o] = sl[k].key; counts[o] = sl[k].cnt; }
+			}
+		}
+		__syncthreads();
+	}
+}
+
 // Thresholding statistics (kb_sorter.h:1011-1065): a k-mer survives iff min_count <= count <= 1e9; its
 // stored count saturates at max_count.
 __global__ void __launch_bounds__(256) k_tab_stats(const CountSlot* __restrict__ tab, uint64_t cap, uint32_t min_count, uint32_t max_count,
@@ -648,6 +694,45 @@ clb_status s1a_counts_export(clb_ctx* c, uint32_t part, uint32_t n_parts, uint64
 	*n_out = sc[SC_CURSOR];
 	if (sc[SC_CURSOR] > cap_out) return fail(c, CLB_ERR_CAPACITY, "clb_counts_export: buffer too small");
 	return CLB_OK;
+}
+
+// sizes != nullptr: entries per partition (host); first != nullptr: write every partition at its offset (host array of n_parts)
+static clb_status counts_all(clb_ctx* c, uint32_t n_parts, uint64_t* sizes, const uint64_t* first, uint64_t* kmers, uint32_t* counts, uint64_t cap_out)
+{
+	if (c->finalized) return fail(c, CLB_ERR_STATE, "count table already finalized");
+	if (n_parts == 0 || n_parts > EXPORT_MAX_PARTS) return fail(c, CLB_ERR_BAD_ARG, "the count table is exported to 1 .. 64 partitions");
+	unsigned long long* d = nullptr;      // cursor[n_parts], first[n_parts]
+	CLB_CUDA(c, dev_malloc((void**)&d, sizeof(unsigned long long) * 2 * EXPORT_MAX_PARTS, c->stream));
+	cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * 2 * EXPORT_MAX_PARTS, c->stream);
+	if (e == cudaSuccess && first) e = cudaMemcpyAsync(d + EXPORT_MAX_PARTS, first, sizeof(uint64_t) * n_parts, cudaMemcpyHostToDevice, c->stream);
+	const uint64_t cap = 1ULL << c->tab_log2;
+	const uint64_t n_tiles = (cap + 256ull * EXPORT_PER_THREAD - 1) / (256ull * EXPORT_PER_THREAD);
+	const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)c->n_sm * 8);
+	if (e == cudaSuccess) {
+		if (first) k_tab_export_all<true><<<grid, 256, 0, c->stream>>>(c->tab, cap, n_parts, kmers, counts, cap_out, d, d + EXPORT_MAX_PARTS);
+		else k_tab_export_all<false><<<grid, 256, 0, c->stream>>>(c->tab, cap, n_parts, nullptr, nullptr, 0, d, d + EXPORT_MAX_PARTS);
+		++c->launches;
+		e = cudaGetLastError();
+	}
+	unsigned long long h[EXPORT_MAX_PARTS] = {};
+	if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(unsigned long long) * n_parts, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	dev_free_async(d, c->stream);
+	if (e != cudaSuccess) return cuda_fail(c, e, "k_tab_export_all");
+	uint64_t total = 0;
+	for (uint32_t p = 0; p < n_parts; ++p) { if (sizes) sizes[p] = h[p]; total += h[p]; }
+	if (first && total > cap_out) return fail(c, CLB_ERR_CAPACITY, "clb_counts_export_all: buffer too small");
+	return CLB_OK;
+}
+clb_status s1a_counts_sizes(clb_ctx* c, uint32_t n_parts, uint64_t* sizes)
+{
+	if (!sizes) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return counts_all(c, n_parts, sizes, nullptr, nullptr, nullptr, 0);
+}
+clb_status s1a_counts_export_all(clb_ctx* c, uint32_t n_parts, const uint64_t* first, uint64_t* kmers, uint32_t* counts, uint64_t cap_out)
+{
+	if (!first || !kmers || !counts) return fail(c, CLB_ERR_BAD_ARG, "null argument");
+	return counts_all(c, n_parts, nullptr, first, kmers, counts, cap_out);
 }
 
 clb_status s1a_counts_reset(clb_ctx* c)

@@ -50,20 +50,17 @@ def exchange_counts_and_finalize(ctx, device, n_local_reads: int, group=None):
     rank = dist.get_rank(group)
     trace = _Trace("counts", rank)
     # 1. sizes of my table's partitions, exchanged so every rank knows what it will receive
-    send_sizes = torch.tensor([ctx.counts_size(p, world) for p in range(world)], dtype=torch.int64, device=device)
+    send_l = ctx.counts_sizes(world)                      # one pass over the table for all partitions
+    send_sizes = torch.tensor(send_l, dtype=torch.int64, device=device)
     recv_sizes = torch.empty_like(send_sizes)
     dist.all_to_all_single(recv_sizes, send_sizes, group=group)
-    send_l, recv_l = send_sizes.tolist(), recv_sizes.tolist()
+    recv_l = recv_sizes.tolist()
     trace("sizes")
-    # 2. export partition by partition into one send buffer, all-to-all the pairs
+    # 2. export all partitions into one send buffer (one more pass), all-to-all the pairs
     send_k = torch.empty(max(1, sum(send_l)), dtype=torch.int64, device=device)
     send_c = torch.empty(max(1, sum(send_l)), dtype=torch.int32, device=device)
-    off = 0
-    for p in range(world):
-        if send_l[p]:
-            got = ctx.counts_export_device(p, world, send_k[off:].data_ptr(), send_c[off:].data_ptr(), send_l[p])
-            assert got == send_l[p]
-        off += send_l[p]
+    first = [sum(send_l[:p]) for p in range(world)]
+    ctx.counts_export_all_device(world, first, send_k.data_ptr(), send_c.data_ptr(), max(1, sum(send_l)))
     trace("export")
     recv_k = torch.empty(max(1, sum(recv_l)), dtype=torch.int64, device=device)
     recv_c = torch.empty(max(1, sum(recv_l)), dtype=torch.int32, device=device)

@@ -12,7 +12,7 @@ SO_PATH = os.environ.get("CLB_LIBRARY") or os.path.join(_HERE, "libcolord_b200.s
 STATUS = {0: "OK", 1: "NO_DEVICE", 2: "CUDA", 3: "BAD_ARG", 4: "BAD_SYMBOL", 5: "STATE", 6: "CAPACITY"}
 EXPORTS = [
     "clb_create", "clb_destroy", "clb_last_error", "clb_set_stream", "clb_synchronize", "clb_append_reads",
-    "clb_counts_size", "clb_counts_export", "clb_counts_reset", "clb_counts_merge", "clb_count_finalize",
+    "clb_counts_size", "clb_counts_export", "clb_counts_sizes", "clb_counts_export_all", "clb_counts_reset", "clb_counts_merge", "clb_count_finalize",
     "clb_filter_list", "clb_filter_import", "clb_filter_check", "clb_graph_build", "clb_graph_accepted_size",
     "clb_graph_accepted", "clb_graph_candidates", "clb_graph_common_size", "clb_graph_common", "clb_get_packed_read",
     "clb_sampler", "clb_kernel_launches", "clb_profile_enable", "clb_profile_get", "clb_edit_scripts",
@@ -73,6 +73,8 @@ def load():
     L.clb_append_reads.argtypes = [vp, vp, vp, u32, i32]
     L.clb_counts_size.argtypes = [vp, u32, u32, C.POINTER(u64)]
     L.clb_counts_export.argtypes = [vp, u32, u32, vp, vp, u64, C.POINTER(u64), i32]
+    L.clb_counts_sizes.argtypes = [vp, u32, vp]
+    L.clb_counts_export_all.argtypes = [vp, u32, vp, vp, vp, u64]
     L.clb_counts_reset.argtypes = [vp]
     L.clb_counts_merge.argtypes = [vp, vp, vp, u64, u64, i32]
     L.clb_count_finalize.argtypes = [vp, C.POINTER(KmerStats)]
@@ -217,6 +219,17 @@ class Context:
         m = C.c_uint64()
         self._ck(self.L.clb_counts_export(self.h, part, n_parts, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), cap, C.byref(m), 1))
         return m.value
+
+    def counts_sizes(self, n_parts):
+        """Entries of every partition of the count table, one pass (clb_counts_sizes)."""
+        sizes = np.zeros(n_parts, np.uint64)
+        self._ck(self.L.clb_counts_sizes(self.h, n_parts, _np_ptr(sizes)))
+        return [int(x) for x in sizes]
+
+    def counts_export_all_device(self, n_parts, first, kmers_ptr, counts_ptr, cap):
+        """Every partition at kmers / counts [first[p] ..) (device buffers), one pass (clb_counts_export_all)."""
+        f = np.ascontiguousarray(first, np.uint64)
+        self._ck(self.L.clb_counts_export_all(self.h, n_parts, _np_ptr(f), C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), cap))
 
     def counts_merge_device(self, kmers_ptr, counts_ptr, n, n_reads_remote=0):
         self._ck(self.L.clb_counts_merge(self.h, C.c_void_p(kmers_ptr), C.c_void_p(counts_ptr), n, n_reads_remote, 1))

@@ -79,6 +79,11 @@ clb_status clb_append_reads(clb_ctx* ctx, const uint8_t* bases, const uint64_t* 
  * clb_filter_import.  n_parts <= 1 exports everything.  Buffers are device pointers iff on_device. */
 clb_status clb_counts_size(clb_ctx* ctx, uint32_t part, uint32_t n_parts, uint64_t* n_entries);
 clb_status clb_counts_export(clb_ctx* ctx, uint32_t part, uint32_t n_parts, uint64_t* kmers, uint32_t* counts, uint64_t cap, uint64_t* n_entries, int on_device);
+/* The same for all partitions in ONE pass over the table each (what the exchanges call): the entries per partition
+ * (sizes: host array of n_parts, n_parts <= 64), then every partition written at kmers / counts [first[p] ..) (first: host array
+ * of n_parts — the caller's prefix sums of sizes; kmers / counts: DEVICE buffers of cap entries; order inside a partition is free). */
+clb_status clb_counts_sizes(clb_ctx* ctx, uint32_t n_parts, uint64_t* sizes);
+clb_status clb_counts_export_all(clb_ctx* ctx, uint32_t n_parts, const uint64_t* first, uint64_t* kmers, uint32_t* counts, uint64_t cap);
 clb_status clb_counts_reset(clb_ctx* ctx);
 clb_status clb_counts_merge(clb_ctx* ctx, const uint64_t* kmers, const uint32_t* counts, uint64_t n, uint64_t n_reads_remote, int on_device);
 /* Thresholds (kb_sorter.h:1011-1065) and builds the filtered-k-mer set; replaces the CKmerFilter ctor

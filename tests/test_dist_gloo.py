@@ -53,6 +53,15 @@ class OracleCtx:
         _view(cptr, len(km), np.uint32)[:] = [self.table[k] for k in km.tolist()]
         return len(km)
 
+    def counts_sizes(self, n_parts):
+        return [self.counts_size(p, n_parts) for p in range(n_parts)]
+
+    def counts_export_all_device(self, n_parts, first, kptr, cptr, cap):
+        for p in range(n_parts):
+            km = self._part(p, n_parts)
+            _view(kptr, cap, np.uint64)[first[p]:first[p] + len(km)] = km
+            _view(cptr, cap, np.uint32)[first[p]:first[p] + len(km)] = [self.table[k] for k in km.tolist()]
+
     def counts_reset(self):
         self.table = {}
 

@@ -217,6 +217,21 @@ def test_partitioned_exchange_equals_single_context():
         for c, (a, b) in zip(ctxs, shards):
             c.append_reads(s.bases, s.offsets[a:b + 1])
         exported = [[c.counts_export(part, 2) for part in range(2)] for c in ctxs]
+        # the one-pass form of the same export (clb_counts_sizes / clb_counts_export_all: what the exchanges call) gives the same sets
+        import torch
+        for c, per_part in zip(ctxs, exported):
+            for n_parts in (2, 5):
+                sizes = c.counts_sizes(n_parts)
+                first = [sum(sizes[:q]) for q in range(n_parts)]
+                tot_n = sum(sizes)
+                dk = torch.zeros(max(1, tot_n), dtype=torch.int64, device="cuda"); dc = torch.zeros(max(1, tot_n), dtype=torch.int32, device="cuda")
+                c.counts_export_all_device(n_parts, first, dk.data_ptr(), dc.data_ptr(), max(1, tot_n))
+                hk, hc = dk.cpu().numpy().view(np.uint64), dc.cpu().numpy().view(np.uint32)
+                for q in range(n_parts):
+                    k1, c1 = c.counts_export(q, n_parts)
+                    assert sizes[q] == len(k1)
+                    a, b = np.argsort(hk[first[q]:first[q] + sizes[q]]), np.argsort(k1)
+                    assert np.array_equal(hk[first[q]:first[q] + sizes[q]][a], k1[b]) and np.array_equal(hc[first[q]:first[q] + sizes[q]][a], c1[b])
         for r, c in enumerate(ctxs):
             c.counts_reset()
             for src in range(2):
