@@ -308,7 +308,6 @@ def main():
     ap.add_argument("--stages", default="12qdh", choices=["1", "12", "12q", "12qd", "12qdh"], help="hot-path stages inside a step (both arms); q / d / h = quality / DNA-tuple / header stream of stage 3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--stage3-overlap", action="store_true", help="code the quality / header streams in a second host thread beside the DNA stream (after stage 2)")
     ap.add_argument("--side-streams", action="store_true", help="code the quality / header streams in a second host thread beside stage 2 instead of after it "
                     "(measured on B200, 25 Gbases: 12.5-13.3 s per step against 11.8-12.0 s serial - the issue-bound quality kernels slow the latency-bound alignment down)")
     args = ap.parse_args()
@@ -467,14 +466,6 @@ def main():
             ctx.encode(lib.EncodeParams(*[NS_S2[k] for k in ("anchor_len", "min_part_len_alt", "max_recurence", "min_anchors",
                                                            "min_mmer_frac", "min_mmer_force", "max_matches_mult", "es_cost_mult")]))
             phase("encode")
-            if side is None and args.stage3_overlap and args.stages in ("12qd", "12qdh"):
-                def side_main3():
-                    try:
-                        side_streams()
-                    except Exception as ex:      # re-raised on the main thread
-                        side_err.append(ex)
-                side = threading.Thread(target=side_main3)
-                side.start()
             if args.stages in ("12qd", "12qdh"):
                 ctx.dna_encode(CFG["level"])
             phase("dna")
