@@ -297,6 +297,14 @@ clb_status clb_encode_get(clb_ctx* c, uint64_t* es_off, uint8_t* es, uint64_t ca
 	return CLB_OK;
 }
 clb_status clb_encode_keep_candidates(clb_ctx* c, int on) { if (!c) return CLB_ERR_BAD_ARG; c->keep_candidates = on != 0; return CLB_OK; }
+clb_status clb_encode_stats_enable(clb_ctx* c, int on) { if (!c) return CLB_ERR_BAD_ARG; c->collect_stats = on != 0; return CLB_OK; }
+clb_status clb_encode_stats_get(clb_ctx* c, clb_encode_stats* out)
+{
+	if (!c || !out) return CLB_ERR_BAD_ARG;
+	if (!c->enc_done || !c->collect_stats) return fail(c, CLB_ERR_STATE, "no statistics: clb_encode_stats_enable before clb_encode");
+	*out = c->h_stats;
+	return CLB_OK;
+}
 clb_status clb_encode_candidates_size(clb_ctx* c, uint64_t* n_words)
 {
 	if (!c || !c->enc_done || !c->keep_candidates) return fail(c, CLB_ERR_STATE, "candidates were not kept");

@@ -207,6 +207,10 @@ struct clb_ctx {
 	uint64_t xd_total = 0, xq_total = 0, xh_total = 0;
 	// debugging / parity taps: candidates after E4 of every read (filled when keep_candidates is set)
 	bool keep_candidates = false;
+	// the reference's -v counters (clb_encode_stats_enable): device array of ST_COUNT sums, filled by k_select / k_stats_*
+	bool collect_stats = false;
+	unsigned long long* d_stats = nullptr;
+	clb_encode_stats h_stats{};
 	std::vector<std::vector<uint32_t>> dbg_cand;   // per read, per candidate: ref_id, rev, tot, n_anchors, then n_anchors * (len, pos_enc, pos_ref)
 };
 

@@ -82,4 +82,12 @@ struct SegInfo {
 };
 constexpr uint32_t PAIR_SLOT_BYTES = 20;
 
+// device counters of the reference's -v report (include/colord_b200.h: clb_encode_stats); per level ST_LEVEL_FIELDS sums from ST_LEVEL0
+enum StatIdx : uint32_t { ST_NOT_ENOUGH = 0, ST_TOO_MANY, ST_TOO_LOW, ST_NON_REV, ST_REV, ST_PLAIN_READS, ST_PLAIN_SYMB, ST_PLAIN_N_READS, ST_PLAIN_N_SYMB, ST_MAX_LEVEL,
+	ST_LEVEL0 = 16 };
+enum StatLevelIdx : uint32_t { SL_ALT_LEFT = 0, SL_ALT_BETWEEN, SL_ALT_RIGHT, SL_PLAIN_SYMB, SL_CODED_SYMB, SL_ES_SYMB, SL_SUBST, SL_MATCH, SL_INS, SL_DEL,
+	SL_ANCHOR_SYMB, SL_ANCHORS, SL_LEFT_FLANK, SL_RIGHT_FLANK, ST_LEVEL_FIELDS };
+constexpr uint32_t ST_LEVELS = 8, ST_COUNT = ST_LEVEL0 + ST_LEVELS * ST_LEVEL_FIELDS;
+constexpr uint32_t SEG_TOO_MANY_MATCHES = 1;      // SegInfo::pad: the match cap refused this (candidate, orientation)
+
 } // namespace clb

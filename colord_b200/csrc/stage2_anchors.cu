@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(MATCH_THREADS) k_anchor_match(MatchArgs a)
 			unsigned long long n = sh.pairs[s];
 			// encoder.cpp:1030-1040: refuse when the number of (read, reference) m-mer matches exceeds maxMatchesMultiplier * |read|
 			if (sh.hits[s] == 0) n = 0;
-			else if (sh.decision != 0 && (double)n > a.P.max_mult * (double)(elen + 1)) n = 0;
+			else if (sh.decision != 0 && (double)n > a.P.max_mult * (double)(elen + 1)) { n = 0; seg[s].pad = SEG_TOO_MANY_MATCHES; }
 			if (n > 0x7FFFFFF0ull) n = 0x7FFFFFF0ull + 2;      // cannot be stored: reported as an overflow below
 			sh.pairs[s] = n;
 			total += (n + 1) & ~1ull;
@@ -543,7 +543,8 @@ __global__ void __launch_bounds__(128) k_lis(SegInfo* __restrict__ seg, uint32_t
 // encoder.cpp:1149-1192 (MmerBasedAnchors: both orientations, keep the better), :1577-1622 (fix overlaps), :1103-1108 (sort)
 __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg, uint32_t n_slots, const uint32_t* __restrict__ enc_list,
 	const uint32_t* __restrict__ cand, const uint32_t* __restrict__ cand_n, const uint32_t* __restrict__ rd_len, const uint32_t* __restrict__ slot_dec,
-	uint8_t* __restrict__ arena, S2P P, Node* __restrict__ nodes, CandView* __restrict__ cviews, const SegInfo* __restrict__ kseg, uint64_t kbase)
+	uint8_t* __restrict__ arena, S2P P, Node* __restrict__ nodes, CandView* __restrict__ cviews, const SegInfo* __restrict__ kseg, uint64_t kbase,
+	unsigned long long* __restrict__ stats)
 {
 	const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
 	if (slot >= n_slots) return;
@@ -551,6 +552,9 @@ __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg,
 	const uint32_t n_cand = slot_dec[slot] ? 0 : min(cand_n[read], c);
 	CandView* out = cviews + (size_t)slot * c;
 	uint32_t n_out = 0;
+	// the reference's refuse reasons / orientation choices (encoder.cpp:1074-1104, :1118-1190): per read, logged only when no candidate is left
+	bool too_many = false, too_low = false;
+	uint32_t n_fwd = 0, n_rev = 0;
 	for (uint32_t j = 0; j < n_cand; ++j) {
 		SegInfo f = seg[((size_t)slot * c + j) * 2], r = seg[((size_t)slot * c + j) * 2 + 1];
 		bool kmer = false;
@@ -559,8 +563,13 @@ __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg,
 			if (kf.n || kr.n) { f = kf; r = kr; f.off += kbase; r.off += kbase; kmer = true; }
 		}
 		const bool af = f.n > 0 && (kmer || f.n_anch >= P.min_anchors), ar = r.n > 0 && (kmer || r.n_anch >= P.min_anchors);
-		if (!af && !ar) continue;
+		if (!af && !ar) {
+			too_many |= ((f.pad | r.pad) & SEG_TOO_MANY_MATCHES) != 0;
+			too_low |= (f.n > 0 && f.n_anch < P.min_anchors) || (r.n > 0 && r.n_anch < P.min_anchors);
+			continue;
+		}
 		const bool use_f = af && (!ar || f.tot > r.tot);
+		if (use_f) ++n_fwd; else ++n_rev;
 		const SegInfo& g = use_f ? f : r;
 		CandView v{};
 		v.anc = g.off * PAIR_SLOT_BYTES; v.ref_id = cand[(size_t)read * c + j]; v.rev = use_f ? 0 : 1;
@@ -584,6 +593,12 @@ __global__ void __launch_bounds__(128) k_select(const SegInfo* __restrict__ seg,
 	nd.read = read; nd.level = 0; nd.enc_start = 0; nd.enc_len = rd_len[read]; nd.first_task = 0;
 	nd.ncand = n_out; nd.n_anch = n_out ? out[0].n : 0; nd.valid = n_out > 0;
 	nodes[slot] = nd;
+	if (stats) {
+		if (slot_dec[slot]) atomicAdd(&stats[ST_NOT_ENOUGH], 1ull);
+		else if (n_out == 0) { if (too_many) atomicAdd(&stats[ST_TOO_MANY], 1ull); if (too_low) atomicAdd(&stats[ST_TOO_LOW], 1ull); }
+		if (n_fwd) atomicAdd(&stats[ST_NON_REV], (unsigned long long)n_fwd);
+		if (n_rev) atomicAdd(&stats[ST_REV], (unsigned long long)n_rev);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -685,7 +700,7 @@ clb_status s2_anchors(clb_ctx* c, const S2P& P, const std::vector<uint32_t>& h_l
 	CLB_LAUNCH_CHECK(c, "k_pairs_sort");
 	CLB_TIMED(c, K_ANCHORS, (k_lis<<<(n_seg + 127) / 128, 128, 0, s>>>(d_seg, n_seg, arena.p, P.m)));
 	CLB_LAUNCH_CHECK(c, "k_lis");
-	CLB_TIMED(c, K_ANCHORS, (k_select<<<(nb + 127) / 128, 128, 0, s>>>(d_seg, nb, d_list, c->cand, c->cand_n, c->rd_len.p, d_slot_dec, arena.p, P, d_nodes, d_cviews, d_kseg, kbase)));
+	CLB_TIMED(c, K_ANCHORS, (k_select<<<(nb + 127) / 128, 128, 0, s>>>(d_seg, nb, d_list, c->cand, c->cand_n, c->rd_len.p, d_slot_dec, arena.p, P, d_nodes, d_cviews, d_kseg, kbase, c->collect_stats ? c->d_stats : nullptr)));
 	CLB_LAUNCH_CHECK(c, "k_select");
 	return CLB_OK;
 }

@@ -779,6 +779,62 @@ __global__ void __launch_bounds__(256) k_emit_plain(EmitArgs a)
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ the reference's -v counters
+// stats_collector.h:28-75 as logged by encoder.cpp:1445-1575: per recursion level what every EncodePart call decided (edit script with
+// its symbol classes / alternative read by fragment position / plain), per AddEncodedReadWithCandidates call its flanks and anchors;
+// per read the plain / plain-with-N starts (encoder.cpp:663-676).  Only run when clb_encode_stats_enable asked for them.
+struct StatsArgs {
+	const Task* tasks; uint64_t n_tasks; const Node* nodes; uint64_t n_nodes; const CandView* cviews; uint32_t c;
+	const uint8_t* arena; const char* esbuf; const uint32_t* kind; const uint32_t* rd_len; uint32_t read_lo, n_reads;
+	unsigned long long* st;
+};
+__global__ void __launch_bounds__(128) k_stats_tasks(StatsArgs a)
+{
+	const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= a.n_tasks) return;
+	const Task& T = a.tasks[t];
+	const Node N = a.nodes[T.node];
+	unsigned long long* L = a.st + ST_LEVEL0 + min(N.level, ST_LEVELS - 1) * ST_LEVEL_FIELDS;
+	if (T.decision == D_ES) {
+		const char* es = a.esbuf + T.es_off;
+		unsigned long long sub = 0, mat = 0, ins = 0, del = T.lead;
+		for (uint32_t i = 0; i < T.es_len; ++i) { const char ch = es[i]; if (ch == 'M') ++mat; else if (ch == 'D') ++del; else if (ch == 'X' || ch == 'Y' || ch == 'Z') ++sub; else ++ins; }
+		atomicAdd(&L[SL_CODED_SYMB], (unsigned long long)T.el);
+		atomicAdd(&L[SL_ES_SYMB], (unsigned long long)T.lead + T.es_len);
+		if (sub) atomicAdd(&L[SL_SUBST], sub);
+		if (mat) atomicAdd(&L[SL_MATCH], mat);
+		if (ins) atomicAdd(&L[SL_INS], ins);
+		if (del) atomicAdd(&L[SL_DEL], del);
+	} else if (T.decision == D_ALT) {      // encoder.cpp:1478-1483: the last fragment first, then the first one
+		atomicAdd(&L[T.frag == N.n_anch ? SL_ALT_RIGHT : T.frag == 0 ? SL_ALT_LEFT : SL_ALT_BETWEEN], 1ull);
+	} else if (T.decision == D_PLAIN) atomicAdd(&L[SL_PLAIN_SYMB], (unsigned long long)T.el);
+}
+__global__ void __launch_bounds__(128) k_stats_nodes(StatsArgs a)
+{
+	const uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= a.n_nodes) return;
+	const Node N = a.nodes[id];
+	if (!N.valid || !N.n_anch) return;
+	const CandView V = a.cviews[id * a.c + N.level];
+	unsigned long long* L = a.st + ST_LEVEL0 + min(N.level, ST_LEVELS - 1) * ST_LEVEL_FIELDS;
+	unsigned long long symb = 0;
+	for (uint32_t i = 0; i < N.n_anch; ++i) symb += cv_get(a.arena, V, i).len;
+	const Anchor a0 = cv_get(a.arena, V, 0), al = cv_get(a.arena, V, N.n_anch - 1);
+	atomicAdd(&L[SL_LEFT_FLANK], (unsigned long long)a0.pos_enc);
+	atomicAdd(&L[SL_RIGHT_FLANK], (unsigned long long)(N.enc_len - (al.pos_enc + al.len)));
+	atomicAdd(&L[SL_ANCHORS], (unsigned long long)N.n_anch);
+	atomicAdd(&L[SL_ANCHOR_SYMB], symb);
+	atomicMax(&a.st[ST_MAX_LEVEL], (unsigned long long)N.level + 1);
+}
+__global__ void __launch_bounds__(128) k_stats_reads(StatsArgs a)
+{
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= a.n_reads) return;
+	const uint32_t kind = a.kind[r];
+	if (kind == 1) { atomicAdd(&a.st[ST_PLAIN_READS], 1ull); atomicAdd(&a.st[ST_PLAIN_SYMB], (unsigned long long)a.rd_len[a.read_lo + r]); }
+	else if (kind == 2) { atomicAdd(&a.st[ST_PLAIN_N_READS], 1ull); atomicAdd(&a.st[ST_PLAIN_N_SYMB], (unsigned long long)a.rd_len[a.read_lo + r]); }
+}
+
 // ------------------------------------------------------------------------------------------------ driver
 template <typename T> static cudaError_t dmalloc(T** p, uint64_t n, cudaStream_t s = nullptr) { return dev_malloc((void**)p, sizeof(T) * (n ? n : 1), s); }
 struct Scoped {            // stream-ordered scratch of a batch / level: freed (back to the pool) on every exit path
@@ -1141,6 +1197,12 @@ static clb_status encode_all(clb_ctx* c, const S2P& P, const std::vector<uint32_
 	CLB_LAUNCH_CHECK(c, "k_emit<write>");
 	CLB_TIMED(c, K_EMIT, (k_emit_plain<<<nr, 256, 0, s>>>(ea)));
 	CLB_LAUNCH_CHECK(c, "k_emit_plain");
+	if (c->collect_stats && c->d_stats) {
+		StatsArgs sa{tasks.p, n_tasks, nodes.p, n_nodes, cviews.p, P.c, arena, esbuf.p, d_kind, c->rd_len.p, lo, nr, c->d_stats};
+		if (n_tasks) { k_stats_tasks<<<(uint32_t)((n_tasks + 127) / 128), 128, 0, s>>>(sa); CLB_LAUNCH_CHECK(c, "k_stats_tasks"); }
+		if (n_nodes) { k_stats_nodes<<<(uint32_t)((n_nodes + 127) / 128), 128, 0, s>>>(sa); CLB_LAUNCH_CHECK(c, "k_stats_nodes"); }
+		k_stats_reads<<<(nr + 127) / 128, 128, 0, s>>>(sa); CLB_LAUNCH_CHECK(c, "k_stats_reads");
+	}
 	CLB_CUDA(c, cudaStreamSynchronize(s));
 	tr.mark("emit");
 	c->es_total += total;
@@ -1156,6 +1218,10 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	cudaStream_t s = c->stream;
 	Trace tr(s);
 	const uint64_t n = c->n_reads;
+	if (c->collect_stats) {
+		if (!c->d_stats) CLB_CUDA(c, dev_malloc((void**)&c->d_stats, sizeof(unsigned long long) * ST_COUNT, s));
+		CLB_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * ST_COUNT, s));
+	}
 	S2P P{prm->anchor_len, prm->min_part_len_alt, prm->max_recurence, prm->min_anchors, c->prm.max_candidates,
 		prm->min_mmer_frac, prm->min_mmer_force, prm->max_matches_mult, prm->es_cost_mult};
 	// packs
@@ -1210,6 +1276,25 @@ clb_status s2_encode(clb_ctx* c, const clb_encode_params* prm, const uint32_t* p
 	c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_budget = 0; c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
 	tr.mark("encode: release");
+	if (c->collect_stats) {
+		unsigned long long h[ST_COUNT];
+		CLB_CUDA(c, cudaMemcpyAsync(h, c->d_stats, sizeof h, cudaMemcpyDeviceToHost, s));
+		CLB_CUDA(c, cudaStreamSynchronize(s));
+		clb_encode_stats& o = c->h_stats;
+		o = clb_encode_stats{};
+		o.n_not_enough_unique_mmers_in_enc_read = h[ST_NOT_ENOUGH]; o.n_too_many_matches = h[ST_TOO_MANY]; o.n_too_low_anchors = h[ST_TOO_LOW];
+		o.n_non_rev_choosen = h[ST_NON_REV]; o.n_rev_choosen = h[ST_REV];
+		o.n_plain_reads_tot = h[ST_PLAIN_READS]; o.n_plain_symb = h[ST_PLAIN_SYMB]; o.n_plain_reads_with_n_tot = h[ST_PLAIN_N_READS]; o.n_plain_with_n_symb = h[ST_PLAIN_N_SYMB];
+		o.n_levels = (uint32_t)std::min<unsigned long long>(h[ST_MAX_LEVEL], CLB_MAX_STAT_LEVELS);
+		for (uint32_t l = 0; l < ST_LEVELS; ++l) {
+			const unsigned long long* L = h + ST_LEVEL0 + l * ST_LEVEL_FIELDS;
+			clb_level_stats& d = o.level[l];
+			d.n_alternative_left_flank = L[SL_ALT_LEFT]; d.n_alternative_in_between = L[SL_ALT_BETWEEN]; d.n_alternative_right_flank = L[SL_ALT_RIGHT];
+			d.n_plain_symbols = L[SL_PLAIN_SYMB]; d.n_symb_coded_with_edit_script = L[SL_CODED_SYMB]; d.n_edit_script_symbols = L[SL_ES_SYMB];
+			d.n_substitution = L[SL_SUBST]; d.n_match = L[SL_MATCH]; d.n_insertion = L[SL_INS]; d.n_deletion = L[SL_DEL];
+			d.n_symb_anchors = L[SL_ANCHOR_SYMB]; d.n_anchors = L[SL_ANCHORS]; d.n_left_flank_symb = L[SL_LEFT_FLANK]; d.n_right_flank_symb = L[SL_RIGHT_FLANK];
+		}
+	}
 	c->enc_done = true;
 	return CLB_OK;
 }
@@ -1221,6 +1306,8 @@ void s2_free(clb_ctx* c)
 	c->s2_fork = nullptr;
 	c->es.release(); c->s2_arena.release(); c->s2_store.release(); c->s2_scratch.release(); c->s2_budget = 0; c->s2_nodes.release(); c->s2_cviews.release(); c->s2_tasks.release(); c->s2_esbuf.release();
 	c->s2_segs.release(); c->s2_gtab.release(); c->s2_gbloom.release();
+	if (c->d_stats) dev_free(c->d_stats, c->stream);
+	c->d_stats = nullptr;
 	if (c->es_off) dev_free(c->es_off, c->stream);
 	if (c->d_ref_to_read) dev_free(c->d_ref_to_read, c->stream);
 	c->es_off = nullptr; c->d_ref_to_read = nullptr;

@@ -32,6 +32,7 @@
 #include "presets.h"
 #include "stage23_host.h"
 #include "ref_genome_host.h"
+#include "stats_report.h"
 
 namespace clbhost {
 
@@ -41,6 +42,7 @@ struct CompressionReport {            // what the reference prints at the end (c
 	uint64_t dna = 0, qual = 0, header = 0, meta = 0, info = 0, archive = 0;
 	uint32_t kmerLen = 0, anchorLen = 0, sparse_range = 0, tot_ref_reads = 0;
 	clb_kmer_stats stats{};
+	ReadStats read_stats; clb_encode_stats encode_stats{}; bool has_encode_stats = false;      // -v: the reference's statistics block (stats_report.h)
 	double seconds = 0;
 };
 
@@ -116,6 +118,7 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 		clb_ctx* c0 = nullptr;
 		inp = std::make_unique<CInputReads>(params.inputFilePath, [&](const uint8_t* b, const uint8_t* q, const uint64_t* off, uint32_t n) {
 			if (!c0) { phase("first pieces parsed"); c0 = wait_counter(); phase("device context (rest of it)"); }
+			if (params.verbose) rep.read_stats.log_all(off, n);
 			check(c0, clb_append_reads(c0, b, off, n, 0), "clb_append_reads");
 			check(c0, clb_append_quals(c0, q, off[n], 0), "clb_append_quals");
 		}, 0, 64u << 20, pin ? &pinned : nullptr);
@@ -127,6 +130,7 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 		if (inp->is_fastq != fastq_guess || inp->is_gzip != is_gzip) throw std::runtime_error("Error: the input changed while it was being read");
 		clb_ctx* c0 = wait_counter();
 		phase("device context (rest of it)");
+		if (params.verbose) rep.read_stats.log_all(inp->offsets.data(), inp->n_reads());
 		check(c0, clb_append_reads(c0, inp->bases.data(), inp->offsets.data(), inp->n_reads(), 0), "clb_append_reads");
 		phase("reads to the device (stage 1a inside)");
 	}
@@ -190,7 +194,9 @@ inline CompressionReport runCompressionTo(const CCompressorParams& params, CInfo
 	CReadsSimilarityGraph graph(kmer_counter, params.maxCandidates, hifi, sparse, accepter, n_pseudo);
 	CEncoder encoder(kmer_counter, anchorLen, params.minFractionOfMmersInEncodeToAlwaysEncode, params.minFractionOfMmersInEncode, params.maxMatchesMultiplier,
 		params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
+	if (params.verbose) check(ctx, clb_encode_stats_enable(ctx, 1), "clb_encode_stats_enable");
 	encoder.Encode(in.read_pack_sizes);
+	if (params.verbose) { check(ctx, clb_encode_stats_get(ctx, &rep.encode_stats), "clb_encode_stats_get"); rep.has_encode_stats = true; }
 
 	phase("stages 1b + 2");
 	int s_dna = -1, s_qual = -1, s_header = -1;

@@ -103,6 +103,7 @@ static int run_compress(const std::string& cmd, int argc, char** argv, const std
 	CInfo info; info.full_command_line = full_cmd;
 	const CompressionReport r = n_gpus > 1 ? runCompressionMultiGpu(p, info, n_gpus) : runCompression(p, info);
 	if (p.verbose) { std::cerr << "streams: " << (r.compat ? "compat (the reference's own)" : "native containers") << "\ninput: " << (r.streamed ? "streamed to the device in pieces" : "read whole") << ", " << r.reader_threads << " reader thread(s)\n"; for (const Phase& ph : r.phases) std::cerr << "  phase " << ph.name << ": " << ph.seconds << " s\n"; }
+	if (p.verbose && r.has_encode_stats) print_stats_report(std::cerr, r.read_stats, r.encode_stats);      // as the reference does when it exits (stats_collector.cpp:100-146)
 	if (p.verbose) std::cerr << "k-mer length: " << r.kmerLen << "\nanchor length: " << r.anchorLen << "\nsparse mode range in reads: " << r.sparse_range << "\nreference reads: " << r.tot_ref_reads << "\n";
 	// compression.cpp:802-806
 	std::cerr << "DNA size        : " << r.dna << "\nQuality size    : " << r.qual << "\nHeader size     : " << r.header << "\nMeta size       : " << r.meta << "\nInfo size       : " << r.info << "\n";

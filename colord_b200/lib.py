@@ -19,7 +19,7 @@ EXPORTS = [
     "clb_encode", "clb_encode_size", "clb_encode_get", "clb_encode_keep_candidates", "clb_encode_candidates_size", "clb_encode_candidates",
     "clb_qual_encode", "clb_qual_size", "clb_qual_get", "clb_dna_encode", "clb_dna_size", "clb_dna_get", "clb_hdr_encode", "clb_hdr_size", "clb_hdr_get",
     "clb_append_context_reads", "clb_reads_have_n", "clb_reads_export", "clb_qual_encode_original", "clb_release_cached_memory",
-    "clb_append_quals", "clb_count_sequences", "clb_xplain_encode", "clb_host_alloc", "clb_host_free", "clb_xdna_encode", "clb_xqual_encode", "clb_xhdr_encode", "clb_xstream_size", "clb_xstream_get",
+    "clb_append_quals", "clb_encode_stats_enable", "clb_encode_stats_get", "clb_count_sequences", "clb_xplain_encode", "clb_host_alloc", "clb_host_free", "clb_xdna_encode", "clb_xqual_encode", "clb_xhdr_encode", "clb_xstream_size", "clb_xstream_get",
 ]
 KERNEL_CLASSES = ["k_pack", "k_count", "k_tab_misc", "k_finalize", "k_accept", "k_postings", "k_vote", "k_common", "k_misc", "k_align", "k_anchors", "k_encode", "k_decide", "k_estimate", "k_emit", "k_qual", "k_dna", "k_hdr"]
 

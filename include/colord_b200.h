@@ -176,6 +176,26 @@ clb_status clb_encode_get(clb_ctx* ctx, uint64_t* es_off, uint8_t* es, uint64_t 
  * clb_encode_keep_candidates(ctx, 1) before clb_encode.  cand_off[n_reads + 1] indexes `data` (uint32 words): per candidate
  * ref_id, shouldReverse, tot_anchor_len, n_anchors, then n_anchors * (len, pos_enc, pos_ref).  HOST buffers. */
 clb_status clb_encode_keep_candidates(clb_ctx* ctx, int on);
+
+/* The counters of the reference's `-v` report (stats_collector.h:28-75, logged in encoder.cpp:663-676, :1069-1190, :1445-1575),
+ * summed over all reads: call clb_encode_stats_enable(ctx, 1) before clb_encode, read them after it.  Levels = recursion depth of
+ * AddEncodedReadWithCandidates (level 0 = the main reference read). */
+#define CLB_MAX_STAT_LEVELS 8
+typedef struct clb_level_stats {
+	uint64_t n_alternative_left_flank, n_alternative_in_between, n_alternative_right_flank;
+	uint64_t n_plain_symbols, n_symb_coded_with_edit_script, n_edit_script_symbols;
+	uint64_t n_substitution, n_match, n_insertion, n_deletion;
+	uint64_t n_symb_anchors, n_anchors, n_left_flank_symb, n_right_flank_symb;
+} clb_level_stats;
+typedef struct clb_encode_stats {
+	uint64_t n_not_enough_unique_mmers_in_enc_read, n_too_many_matches, n_too_low_anchors;
+	uint64_t n_non_rev_choosen, n_rev_choosen;
+	uint64_t n_plain_reads_tot, n_plain_symb, n_plain_reads_with_n_tot, n_plain_with_n_symb;
+	uint32_t n_levels, pad;
+	clb_level_stats level[CLB_MAX_STAT_LEVELS];
+} clb_encode_stats;
+clb_status clb_encode_stats_enable(clb_ctx* ctx, int on);
+clb_status clb_encode_stats_get(clb_ctx* ctx, clb_encode_stats* out);
 clb_status clb_encode_candidates_size(clb_ctx* ctx, uint64_t* n_words);
 clb_status clb_encode_candidates(clb_ctx* ctx, uint64_t* cand_off, uint32_t* data, uint64_t cap_words);
 

@@ -172,6 +172,33 @@ def test_cli_compat_every_quality_mode_against_the_reference(cli, tmp_path, opts
     assert outs[0] == outs[1] == outs[2] == outs[3]
 
 
+def _stats_block(stderr):
+    """the statistics block of a verbose compression: from the READS STATS banner to its last counter line"""
+    lines = stderr.splitlines()
+    start = next(i for i, l in enumerate(lines) if "READS STATS" in l)
+    return [l.rstrip() for l in lines[start:] if l.startswith(" * * *") or l.startswith(" ----") or (l.startswith(("#", "min read", "max read")) and " : " in l)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="the stock reference binary is not built here")
+@pytest.mark.parametrize("mode,opts,profile", [("compress-ont", [], "ont"), ("compress-ont", ["-p", "ratio", "-c", "8"], "ont"), ("compress-pbhifi", [], "hifi"), ("compress-pbraw", ["-R", "all"], "clr")])
+def test_cli_verbose_statistics_equal_the_reference(cli, tmp_path, mode, opts, profile):
+    """-v: the statistics block the reference prints when it exits (stats_collector.cpp:100-146: reads, refuse reasons, plain reads,
+    orientation choices, and per recursion level alternatives / plain symbols / edit-script symbol classes / anchors / flanks) — every
+    line equals the stock binary's on the same file, in both stream formats."""
+    s = synth.generate(1500, 120000, 3000, seed=23, profile=profile, n_frac=0.04)
+    inp = str(tmp_path / "in.fastq")
+    s.write_fastq(inp)
+    rr = subprocess.run([REF, mode, *opts, "-v", "-t", "4", inp, str(tmp_path / "ref.colord")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert rr.returncode == 0, rr.stderr[-2000:]
+    want = _stats_block(rr.stderr)
+    assert any("level 0" in l for l in want) and len(want) > 30, want
+    for fmt in ("--native", "--compat"):
+        r = subprocess.run([cli, mode, *opts, fmt, "-v", inp, str(tmp_path / "ours.colord")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = _stats_block(r.stderr)
+        assert got == want, "\n".join(f"{a!r} | {b!r}" for a, b in zip(got, want) if a != b)
+
+
 def test_cli_streamed_input_equals_whole_file_input(cli, tmp_path):
     """Files of 64 MiB and more stream to the device in pieces while they are parsed (qualities resident on the device); the archive's
     streams must be the ones the whole-file path writes (CLB_NO_STREAMING=1), and the round trip lossless."""
