@@ -105,6 +105,20 @@ def test_compact_es_bytes_golden(golden, case):
     assert not bad, (len(bad), bad[:10])
 
 
+@pytest.mark.parametrize("env", ["CLB_ALIGN_ONE_KERNEL", "CLB_ALIGN_THREAD_BACK", "CLB_SLAB_GB"])
+@pytest.mark.parametrize("case", ["ont_bal", "clr_ratio"])
+def test_compact_es_bytes_golden_kernel_variants(golden, case, env, monkeypatch):
+    """The switchable forms of the alignment (one kernel per bin instead of forward + backward kernels; backward half with one thread
+    per task, align_back.cuh) and the path without the device slab give the reference's CompactES bytes as well."""
+    monkeypatch.setenv(env, "0" if env == "CLB_SLAB_GB" else "1")
+    g = golden(case)
+    with _run_stage2(g) as ctx:
+        off, es = ctx.encoded(g.reads_in.n_reads)
+    got = [es[int(off[i]):int(off[i + 1])].tobytes() for i in range(g.reads_in.n_reads)]
+    bad = [i for i in range(len(got)) if got[i] != g.es[i]]
+    assert not bad, (env, len(bad), bad[:10])
+
+
 def _device_vs_oracle(s, k, f, lo, hi, c, P, pack_sizes=None, sampled=None):
     n = s.n_reads
     sampled = np.ones(n, np.uint8) if sampled is None else sampled
