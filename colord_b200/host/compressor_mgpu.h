@@ -47,6 +47,7 @@ inline CompressionReport runCompressionMultiGpu(const CCompressorParams& params,
 	struct Rank {
 		std::unique_ptr<CKmerCounter> counter; std::unique_ptr<CInputReads> in; std::exception_ptr err;
 		std::vector<uint8_t> dna, qual, hdr; uint32_t n_context = 0;
+		clb_encode_stats enc_stats{};
 	};
 	std::vector<Rank> ranks(n_gpus);
 	auto run_all = [&](auto&& fn) {      // fn(rank) on one thread per rank; the first error is rethrown when all are back
@@ -111,7 +112,9 @@ inline CompressionReport runCompressionMultiGpu(const CCompressorParams& params,
 		check(c, clb_graph_build(c, dec, 0), "clb_graph_build");
 		CEncoder encoder(*K.counter, anchorLen, params.minFractionOfMmersInEncodeToAlwaysEncode, params.minFractionOfMmersInEncode, params.maxMatchesMultiplier,
 			params.editScriptCostMultiplier, params.minPartLenToConsiderAltRead, params.maxRecurence, params.minAnchors);
+		if (params.verbose) check(c, clb_encode_stats_enable(c, 1), "clb_encode_stats_enable");
 		encoder.Encode(in.read_pack_sizes);
+		if (params.verbose) check(c, clb_encode_stats_get(c, &K.enc_stats), "clb_encode_stats_get");
 		{ CEntrComprReads dna(*K.counter, params.compressionLevel); dna.Compress(in.read_pack_sizes); K.dna = dna.GetStream(); }
 		if (fastq_quals) {
 			const uint32_t n_bins = params.qualityComprMode == QualityComprMode::BinaryAverage ? 2 : params.qualityComprMode == QualityComprMode::QuadAverage ? 4 : 5;
@@ -161,6 +164,23 @@ inline CompressionReport runCompressionMultiGpu(const CCompressorParams& params,
 		throw;
 	}
 	phase("archive written");
+	if (params.verbose) {      // the reference's statistics block (stats_report.h): read statistics in file order, the ranks' counters added up —
+		// the shards' candidates and tuples are those of one GPU, so the sums are the one-GPU report
+		clb_encode_stats& t = rep.encode_stats;
+		for (Rank& K : ranks) {
+			for (uint32_t len : K.in->ReadLengths()) rep.read_stats.log(len);
+			const clb_encode_stats& e = K.enc_stats;
+			t.n_not_enough_unique_mmers_in_enc_read += e.n_not_enough_unique_mmers_in_enc_read; t.n_too_many_matches += e.n_too_many_matches; t.n_too_low_anchors += e.n_too_low_anchors;
+			t.n_non_rev_choosen += e.n_non_rev_choosen; t.n_rev_choosen += e.n_rev_choosen;
+			t.n_plain_reads_tot += e.n_plain_reads_tot; t.n_plain_symb += e.n_plain_symb; t.n_plain_reads_with_n_tot += e.n_plain_reads_with_n_tot; t.n_plain_with_n_symb += e.n_plain_with_n_symb;
+			t.n_levels = std::max(t.n_levels, e.n_levels);
+			for (uint32_t l = 0; l < CLB_MAX_STAT_LEVELS; ++l) {
+				const uint64_t* src = reinterpret_cast<const uint64_t*>(&e.level[l]); uint64_t* dst = reinterpret_cast<uint64_t*>(&t.level[l]);
+				for (size_t f = 0; f < sizeof(clb_level_stats) / sizeof(uint64_t); ++f) dst[f] += src[f];
+			}
+		}
+		rep.has_encode_stats = true;
+	}
 	rep.phases = phases;
 	rep.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 	return rep;

@@ -287,10 +287,12 @@ def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts, n_gpus):
     fq = str(tmp_path / "in.fastq")
     synth.generate_file(fq, "ont", 3000, 1_100_000, 8000, seed=12, workers=8)
     one, two, back = str(tmp_path / "one.colord"), str(tmp_path / "two.colord"), str(tmp_path / "back")
-    r = subprocess.run([cli, "compress-ont", *opts, "--native", fq, one], capture_output=True, text=True)
+    r = subprocess.run([cli, "compress-ont", *opts, "--native", "-v", fq, one], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    stats_one = _stats_block(r.stderr)
     r = subprocess.run([cli, "compress-ont", *opts, "--gpus", str(n_gpus), "-v", fq, two], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    assert _stats_block(r.stderr) == stats_one and len(stats_one) > 30      # -v: the statistics block of the shards adds up to the one-GPU report
     parts1, parts2 = colord_archive.read_parts(one), colord_archive.read_parts(two)
     assert len(parts2["dna-b200"]) == n_gpus and len(parts1["dna-b200"]) == 1
     assert sum(md for md, _ in parts2["dna-b200"]) == parts1["dna-b200"][0][0]
