@@ -165,7 +165,7 @@ inline CompressionReport runCompressionMultiGpu(const CCompressorParams& params,
 	}
 	phase("archive written");
 	if (params.verbose) {      // the reference's statistics block (stats_report.h): read statistics in file order, the ranks' counters added up —
-		// the shards' candidates and tuples are those of one GPU, so the sums are the one-GPU report
+		// the shards' candidates are those of one GPU (the estimator restarts at a shard's first pack, so a few short-part decisions differ)
 		clb_encode_stats& t = rep.encode_stats;
 		for (Rank& K : ranks) {
 			for (uint32_t len : K.in->ReadLengths()) rep.read_stats.log(len);

@@ -292,7 +292,15 @@ def test_cli_multi_gpu_archive_round_trip(cli, tmp_path, opts, n_gpus):
     stats_one = _stats_block(r.stderr)
     r = subprocess.run([cli, "compress-ont", *opts, "--gpus", str(n_gpus), "-v", fq, two], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert _stats_block(r.stderr) == stats_one and len(stats_one) > 30      # -v: the statistics block of the shards adds up to the one-GPU report
+    # -v: the ranks' counters add up to the one-GPU report — exactly for the read statistics, refuse reasons, plain reads and orientation
+    # choices (lines up to the first level); the per-level lines follow the estimator, which restarts at the shards' pack cuts
+    stats_n = _stats_block(r.stderr)
+    first_level = next(i for i, l in enumerate(stats_one) if "level 0" in l)
+    assert stats_n[:first_level] == stats_one[:first_level] and len(stats_n) == len(stats_one) > 30, (stats_n[:first_level], stats_one[:first_level])
+    for a, b in zip(stats_n[first_level:], stats_one[first_level:]):
+        if " : " in a:
+            va, vb = int(a.split(" : ")[1]), int(b.split(" : ")[1])
+            assert a.split(" : ")[0] == b.split(" : ")[0] and abs(va - vb) <= 0.02 * max(va, vb) + 64, (a, b)
     parts1, parts2 = colord_archive.read_parts(one), colord_archive.read_parts(two)
     assert len(parts2["dna-b200"]) == n_gpus and len(parts1["dna-b200"]) == 1
     assert sum(md for md, _ in parts2["dna-b200"]) == parts1["dna-b200"][0][0]
