@@ -2,9 +2,11 @@
 //   hdr <stream> <n> <out>                          decoded headers: per header "<plus>\t<bytes>\n"
 //   qavg|qorg <stream> <bases> <offsets> [flags] <out>   bases: ASCII back to back, offsets: u64[n+1], flags: one byte per base
 //   dna <stream> <n_reads> <decisions> <out_bases> <out_offsets> <out_flags>
+//   stats <input>                                   the -v statistics block (stats_report.h) with the reader's read statistics; the encoder's counters: all reads plain
 //   parse <input> <out_prefix> [threads min_piece_bytes]   reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
 #include "../colord_b200/host/decompressor.h"
 #include "../colord_b200/host/fastq_reader.h"
+#include "../colord_b200/host/stats_report.h"
 #include <chrono>
 #include <cinttypes>
 #include <fstream>
@@ -84,6 +86,17 @@ int main(int argc, char** argv)
 				std::printf("]}\n");
 				return 0;
 			} catch (const StreamingFallback&) { return 5; }
+		}
+		if (cmd == "stats" && argc == 3) {
+			const CInputReads in(argv[2]);
+			ReadStats r; r.log_all(in.offsets.data(), in.n_reads());
+			clb_encode_stats e{};      // what a run without any overlap between the reads reports: every read plain (with N where it has one)
+			for (uint32_t i = 0; i < in.n_reads(); ++i) {
+				const uint64_t len = in.offsets[i + 1] - in.offsets[i];
+				if (in.has_n[i]) { ++e.n_plain_reads_with_n_tot; e.n_plain_with_n_symb += len; } else { ++e.n_plain_reads_tot; e.n_plain_symb += len; }
+			}
+			print_stats_report(std::cout, r, e);
+			return 0;
 		}
 		if (cmd == "parse" && (argc == 4 || argc == 6)) {
 			const CInputReads in(argv[2], argc == 6 ? static_cast<unsigned>(std::atoi(argv[4])) : 0u, argc == 6 ? std::strtoull(argv[5], nullptr, 10) : (16u << 20));

@@ -16,6 +16,7 @@ import oracle_lib
 from colord_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "colord")      # the unmodified reference (oracle/Makefile), built where /root/reference exists
 
 
 @pytest.fixture(scope="module")
@@ -268,6 +269,30 @@ def test_reader_fasta_multiline(tool, tmp_path):
     assert open(str(tmp_path / "o.headers"), "rb").read() == b"s1 descs2s3"
     assert open(str(tmp_path / "o.quals"), "rb").read() == b""
     assert list(np.fromfile(str(tmp_path / "o.hasn"), np.uint8)) == [0, 1, 0]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="the stock reference binary is not built here")
+@pytest.mark.parametrize("lens", [[50, 900, 300, 1200, 70], [900, 50, 1200], [40, 40, 40], [500]])
+def test_statistics_block_on_reads_without_overlaps(tool, tmp_path, lens):
+    """stats_report.h against the stock binary's -v block on inputs whose reads share nothing (every read comes out plain, reads with N
+    counted apart): all lines equal — including the reference's rule that a read is only tried as the minimum when it is not a new
+    maximum (stats_collector.cpp:152-160: the first read never is, so `min read len` of [50, 900, ...] is not 50)."""
+    rng = np.random.default_rng(len(lens))
+    recs = []
+    for i, n in enumerate(lens):
+        b = rng.integers(0, 4, n)
+        seq = bytearray(b"ACGT"[x] for x in b)
+        if i == 2:
+            seq[n // 2] = ord("N")
+        recs.append(b"@r%d\n" % i + bytes(seq) + b"\n+\n" + b"5" * n + b"\n")
+    inp = str(tmp_path / "in.fastq")
+    open(inp, "wb").write(b"".join(recs))
+    rr = subprocess.run([REF_BIN, "compress-ont", "-v", "-t", "2", inp, str(tmp_path / "ref.colord")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert rr.returncode == 0, rr.stderr[-1000:]
+    lines = rr.stderr.splitlines()
+    want = [l.rstrip() for l in lines[next(i for i, l in enumerate(lines) if "READS STATS" in l):] if l.strip()]
+    got = [l.rstrip() for l in subprocess.run([tool, "stats", inp], capture_output=True, text=True, check=True).stdout.splitlines() if l.strip()]
+    assert got == want
 
 
 def test_reader_packs_follow_the_reference_rule(tool, tmp_path):
