@@ -4,7 +4,9 @@
 #pragma once
 #include <cstdint>
 #include <limits>
+#include <initializer_list>
 #include <ostream>
+#include <string>
 #include "../../include/colord_b200.h"
 
 namespace clbhost {
@@ -23,41 +25,29 @@ struct ReadStats {
 	void log_all(const uint64_t* offsets, uint64_t n) { for (uint64_t i = 0; i < n; ++i) log(offsets[i + 1] - offsets[i]); }
 };
 
-inline void print_stats_report(std::ostream& summary, const ReadStats& r, const clb_encode_stats& s)
+// The block's lines are "<label padded to 31 columns>: <value>" under three banners and one banner per level; the labels are the
+// reference's (a user diffs the two programs' outputs), the fields come in its order.
+inline void print_stats_report(std::ostream& os, const ReadStats& r, const clb_encode_stats& s)
 {
-	summary << " * * * * * * * * READS STATS * * * * * * * * \n";
-	summary << "# reads                        : " << r.n_reads << "\n";
-	summary << "min read len                   : " << r.min_read_len << "\n";
-	summary << "max read len                   : " << r.max_read_len << "\n";
-	summary << "# symbols                      : " << r.tot_read_len << "\n";
-	summary << " * * * * * * * * REFUSE REASONS STATS * * * * * * * * \n";
-	summary << "# not enough uniq mmers in enc : " << s.n_not_enough_unique_mmers_in_enc_read << "\n";
-	summary << "# too many matches             : " << s.n_too_many_matches << "\n";
-	summary << "# too low anchors              : " << s.n_too_low_anchors << "\n";
-	summary << " * * * * * * * * COMPRESSION STATS * * * * * * * * \n";
-	summary << "# plain reads                  : " << s.n_plain_reads_tot << "\n";
-	summary << "# symb plain reads             : " << s.n_plain_symb << "\n";
-	summary << "# plain reads (reason: N)      : " << s.n_plain_reads_with_n_tot << "\n";
-	summary << "# symb plain reads (reason: N) : " << s.n_plain_with_n_symb << "\n";
-	summary << "# non rev choosen              : " << s.n_non_rev_choosen << "\n";
-	summary << "# rev choosen                  : " << s.n_rev_choosen << "\n";
+	struct Line { const char* label; uint64_t value; };
+	auto banner = [&os](const char* text) { os << " * * * * * * * * " << text << " * * * * * * * * \n"; };
+	auto lines = [&os](std::initializer_list<Line> ls) {
+		for (const Line& l : ls) { std::string lab(l.label); lab.resize(31, ' '); os << lab << ": " << l.value << "\n"; }
+	};
+	banner("READS STATS");
+	lines({{"# reads", r.n_reads}, {"min read len", r.min_read_len}, {"max read len", r.max_read_len}, {"# symbols", r.tot_read_len}});
+	banner("REFUSE REASONS STATS");
+	lines({{"# not enough uniq mmers in enc", s.n_not_enough_unique_mmers_in_enc_read}, {"# too many matches", s.n_too_many_matches}, {"# too low anchors", s.n_too_low_anchors}});
+	banner("COMPRESSION STATS");
+	lines({{"# plain reads", s.n_plain_reads_tot}, {"# symb plain reads", s.n_plain_symb}, {"# plain reads (reason: N)", s.n_plain_reads_with_n_tot},
+		{"# symb plain reads (reason: N)", s.n_plain_with_n_symb}, {"# non rev choosen", s.n_non_rev_choosen}, {"# rev choosen", s.n_rev_choosen}});
 	for (uint32_t i = 0; i < s.n_levels && i < CLB_MAX_STAT_LEVELS; ++i) {
 		const clb_level_stats& l = s.level[i];
-		summary << " --------------- level " << i << " --------------- \n";
-		summary << "# alt for left flank           : " << l.n_alternative_left_flank << "\n";
-		summary << "# alt in between anchors       : " << l.n_alternative_in_between << "\n";
-		summary << "# alt for right flank          : " << l.n_alternative_right_flank << "\n";
-		summary << "# symb plain                   : " << l.n_plain_symbols << "\n";
-		summary << "# symb edit script encoded     : " << l.n_symb_coded_with_edit_script << "\n";
-		summary << "# symb in edit script          : " << l.n_edit_script_symbols << "\n";
-		summary << "# mismatches                   : " << l.n_substitution << "\n";
-		summary << "# matches                      : " << l.n_match << "\n";
-		summary << "# insertions                   : " << l.n_insertion << "\n";
-		summary << "# deletions                    : " << l.n_deletion << "\n";
-		summary << "# symb anchors                 : " << l.n_symb_anchors << "\n";
-		summary << "# anchors                      : " << l.n_anchors << "\n";
-		summary << "# symb left flank              : " << l.n_left_flank_symb << "\n";
-		summary << "# symb right flank             : " << l.n_right_flank_symb << "\n";
+		os << " --------------- level " << i << " --------------- \n";
+		lines({{"# alt for left flank", l.n_alternative_left_flank}, {"# alt in between anchors", l.n_alternative_in_between}, {"# alt for right flank", l.n_alternative_right_flank},
+			{"# symb plain", l.n_plain_symbols}, {"# symb edit script encoded", l.n_symb_coded_with_edit_script}, {"# symb in edit script", l.n_edit_script_symbols},
+			{"# mismatches", l.n_substitution}, {"# matches", l.n_match}, {"# insertions", l.n_insertion}, {"# deletions", l.n_deletion},
+			{"# symb anchors", l.n_symb_anchors}, {"# anchors", l.n_anchors}, {"# symb left flank", l.n_left_flank_symb}, {"# symb right flank", l.n_right_flank_symb}});
 	}
 }
 

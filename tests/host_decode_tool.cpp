@@ -2,6 +2,7 @@
 //   hdr <stream> <n> <out>                          decoded headers: per header "<plus>\t<bytes>\n"
 //   qavg|qorg <stream> <bases> <offsets> [flags] <out>   bases: ASCII back to back, offsets: u64[n+1], flags: one byte per base
 //   dna <stream> <n_reads> <decisions> <out_bases> <out_offsets> <out_flags>
+//   stats-format <numbers>                          the block printed from the numbers of a block (format check against the stock binary's text)
 //   stats <input>                                   the -v statistics block (stats_report.h) with the reader's read statistics; the encoder's counters: all reads plain
 //   parse <input> <out_prefix> [threads min_piece_bytes]   reader: writes <prefix>.bases .offsets .quals .headers .hoff .plus .packs and prints the statistics as JSON
 #include "../colord_b200/host/decompressor.h"
@@ -86,6 +87,24 @@ int main(int argc, char** argv)
 				std::printf("]}\n");
 				return 0;
 			} catch (const StreamingFallback&) { return 5; }
+		}
+		if (cmd == "stats-format" && argc == 3) {      // the block printed from numbers given in its own order (4 + 3 + 6, then 14 per level)
+			std::ifstream f(argv[2]);
+			std::vector<uint64_t> v; for (uint64_t x; f >> x;) v.push_back(x);
+			if (v.size() < 13 || (v.size() - 13) % 14) throw std::runtime_error("stats-format: 13 + 14 per level numbers");
+			ReadStats r; r.n_reads = v[0]; r.min_read_len = v[1]; r.max_read_len = v[2]; r.tot_read_len = v[3];
+			clb_encode_stats e{};
+			e.n_not_enough_unique_mmers_in_enc_read = v[4]; e.n_too_many_matches = v[5]; e.n_too_low_anchors = v[6];
+			e.n_plain_reads_tot = v[7]; e.n_plain_symb = v[8]; e.n_plain_reads_with_n_tot = v[9]; e.n_plain_with_n_symb = v[10]; e.n_non_rev_choosen = v[11]; e.n_rev_choosen = v[12];
+			e.n_levels = static_cast<uint32_t>((v.size() - 13) / 14);
+			for (uint32_t l = 0; l < e.n_levels && l < CLB_MAX_STAT_LEVELS; ++l) {
+				const uint64_t* x = v.data() + 13 + 14 * l; clb_level_stats& d = e.level[l];
+				d.n_alternative_left_flank = x[0]; d.n_alternative_in_between = x[1]; d.n_alternative_right_flank = x[2]; d.n_plain_symbols = x[3];
+				d.n_symb_coded_with_edit_script = x[4]; d.n_edit_script_symbols = x[5]; d.n_substitution = x[6]; d.n_match = x[7]; d.n_insertion = x[8]; d.n_deletion = x[9];
+				d.n_symb_anchors = x[10]; d.n_anchors = x[11]; d.n_left_flank_symb = x[12]; d.n_right_flank_symb = x[13];
+			}
+			print_stats_report(std::cout, r, e);
+			return 0;
 		}
 		if (cmd == "stats" && argc == 3) {
 			const CInputReads in(argv[2]);

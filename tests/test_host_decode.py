@@ -295,6 +295,24 @@ def test_statistics_block_on_reads_without_overlaps(tool, tmp_path, lens):
     assert got == want
 
 
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="the stock reference binary is not built here")
+def test_statistics_block_format_with_levels(tool, tmp_path):
+    """The text of the whole block, levels included: the stock binary's block on overlapping reads, its numbers fed to the host printer
+    (stats_report.h), gives the same text back."""
+    s = synth.generate(400, 40000, 2500, seed=31, profile="ont", n_frac=0.03)
+    inp = str(tmp_path / "in.fastq")
+    s.write_fastq(inp)
+    rr = subprocess.run([REF_BIN, "compress-ont", "-v", "-t", "2", inp, str(tmp_path / "ref.colord")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert rr.returncode == 0, rr.stderr[-1000:]
+    lines = rr.stderr.splitlines()
+    want = [l for l in lines[next(i for i, l in enumerate(lines) if "READS STATS" in l):] if l.strip()]
+    assert sum("level" in l for l in want) >= 2
+    nums = str(tmp_path / "nums.txt")
+    open(nums, "w").write(" ".join(l.split(" : ")[1] for l in want if " : " in l))
+    got = [l for l in subprocess.run([tool, "stats-format", nums], capture_output=True, text=True, check=True).stdout.splitlines() if l.strip()]
+    assert got == want
+
+
 def test_reader_packs_follow_the_reference_rule(tool, tmp_path):
     """Read packs close at >= 4 MiB of reads (one guard byte each), header packs at >= 4 MiB of headers."""
     rng = np.random.default_rng(1)
